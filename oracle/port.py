@@ -1,0 +1,224 @@
+"""ctypes binding to oracle/liboracle_port.so (oracle/drops_oracle.c) -- TEST INFRASTRUCTURE ONLY.
+
+The plain-C restatement of the reference hot path.  Same calling surface as oracle/ref.py so
+tests can run either checker.  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline
+legs may import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboracle_port.so")
+
+_lib = None
+_szp = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "drops_oracle.c")
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "port"], stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    L = C.CDLL(LIB_PATH)
+    sz, d, i = C.c_size_t, C.c_double, C.c_int
+    ip, dpp, vp = C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_void_p
+    csr = [_dp, _szp, _szp]
+    sig = {
+        "orc_y_Ax": (None, [_dp, sz] + csr + [_dp]),
+        "orc_y_ATx": (None, [_dp, sz, sz] + csr + [_dp]),
+        "orc_get_diag": (None, [_dp, sz] + csr),
+        "orc_dot": (d, [sz, _dp, _dp]),
+        "orc_norm_sq": (d, [sz, _dp]),
+        "orc_norm": (d, [sz, _dp]),
+        "orc_supnorm": (d, [sz, _dp]),
+        "orc_kahan_dot": (d, [sz, _dp, _dp]),
+        "orc_kahan_norm": (d, [sz, _dp]),
+        "orc_axpy": (None, [sz, d, _dp, _dp]),
+        "orc_z_xpay": (None, [sz, _dp, _dp, d, _dp]),
+        "orc_z_xpaypby2": (None, [sz, _dp, _dp, d, _dp, d, _dp]),
+        "orc_jacobi0": (None, [sz] + csr + [d, _dp, _dp]),
+        "orc_cg": (i, [sz] + csr + [_dp, _dp, ip, dpp, i, vp, i]),
+        "orc_pcg": (i, [sz] + csr + [i, d, _dp, _dp, ip, dpp, i, vp, i]),
+        "orc_gmres": (i, [sz] + csr + [i, d, _dp, _dp, i, ip, dpp, i, i]),
+        "orc_minres": (i, [sz] + csr + [i, i, d, _dp, _dp, ip, dpp, i]),
+        "orc_lanczos_basis": (i, [sz] + csr + [_dp, i, _dp, _dp, _dp]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    _lib = L
+    return L
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class PortMatrix:
+    """CSR triple in the reference layout (size_t rowbeg/colind, double val)."""
+
+    def __init__(self, rows, cols, rowbeg, colind, val):
+        self.rows, self.cols = int(rows), int(cols)
+        self.rowbeg, self.colind, self.val = _u64(rowbeg), _u64(colind), _f64(val)
+        self.nnz = int(self.val.size)
+        if self.nnz == 0:
+            self.colind, self.val = np.zeros(1, np.uint64), np.zeros(1, np.float64)
+
+    @property
+    def _csr(self):
+        return (self.val, self.rowbeg, self.colind)
+
+    def csr(self):
+        return self.rowbeg, self.colind[:self.nnz], self.val[:self.nnz]
+
+    def spmv(self, x):
+        y = np.zeros(self.rows)
+        lib().orc_y_Ax(y, self.rows, *self._csr, _f64(x))
+        return y
+
+    def spmv_raw(self, x, y):
+        lib().orc_y_Ax(y, self.rows, *self._csr, x)
+
+    def spmv_transpose(self, x):
+        y = np.zeros(self.cols)
+        lib().orc_y_ATx(y, self.rows, self.cols, *self._csr, _f64(x))
+        return y
+
+    def diag(self):
+        d = np.zeros(self.rows)
+        lib().orc_get_diag(d, self.rows, *self._csr)
+        return d
+
+    def jacobi_apply(self, b, omega=1.0):
+        x = np.zeros(self.rows)
+        lib().orc_jacobi0(self.rows, *self._csr, float(omega), _f64(b), x)
+        return x
+
+    @staticmethod
+    def _hist(max_iter, hist):
+        if hist:
+            h = np.full(int(max_iter) + 1, np.nan)
+            return h, [h.ctypes.data_as(C.c_void_p), int(h.size)]
+        return None, [None, 0]
+
+    def _pcg(self, pc_kind, omega, x0, b, max_iter, tol, relative, hist):
+        x = _f64(x0).copy()
+        it, res = C.c_int(int(max_iter)), C.c_double(float(tol))
+        h, hargs = self._hist(max_iter, hist)
+        conv = lib().orc_pcg(self.rows, *self._csr, pc_kind, float(omega), x, _f64(b),
+                             C.byref(it), C.byref(res), int(relative), *hargs)
+        out = (bool(conv), it.value, res.value, x)
+        return out + (h,) if hist else out
+
+    def pcg_jacobi(self, x0, b, max_iter, tol, relative=False, omega=1.0, hist=False):
+        return self._pcg(1, omega, x0, b, max_iter, tol, relative, hist)
+
+    def pcg_dummy(self, x0, b, max_iter, tol, relative=False, hist=False):
+        return self._pcg(0, 1.0, x0, b, max_iter, tol, relative, hist)
+
+    def pcg_jacobi_timed(self, x0, b, max_iter, tol, relative=True, omega=1.0):
+        return self._pcg(1, omega, x0, b, max_iter, tol, relative, False)
+
+    def cg(self, x0, b, max_iter, tol, relative=False, hist=False):
+        x = _f64(x0).copy()
+        it, res = C.c_int(int(max_iter)), C.c_double(float(tol))
+        h, hargs = self._hist(max_iter, hist)
+        conv = lib().orc_cg(self.rows, *self._csr, x, _f64(b), C.byref(it), C.byref(res),
+                            int(relative), *hargs)
+        out = (bool(conv), it.value, res.value, x)
+        return out + (h,) if hist else out
+
+    def _gmres(self, pc_kind, omega, x0, b, restart, max_iter, tol, relative, left):
+        x = _f64(x0).copy()
+        it, res = C.c_int(int(max_iter)), C.c_double(float(tol))
+        conv = lib().orc_gmres(self.rows, *self._csr, pc_kind, float(omega), x, _f64(b),
+                               int(restart), C.byref(it), C.byref(res), int(relative), int(left))
+        if conv < 0:
+            raise ValueError("restart < 2")
+        return bool(conv), it.value, res.value, x
+
+    def gmres_jacobi(self, x0, b, restart, max_iter, tol, relative=True, omega=1.0, left=True):
+        return self._gmres(1, omega, x0, b, restart, max_iter, tol, relative, left)
+
+    def gmres_dummy(self, x0, b, restart, max_iter, tol, relative=True, left=True):
+        return self._gmres(0, 1.0, x0, b, restart, max_iter, tol, relative, left)
+
+    def _minres(self, precond, pc_kind, omega, x0, b, max_iter, tol, relative):
+        x = _f64(x0).copy()
+        it, res = C.c_int(int(max_iter)), C.c_double(float(tol))
+        conv = lib().orc_minres(self.rows, *self._csr, precond, pc_kind, float(omega), x, _f64(b),
+                                C.byref(it), C.byref(res), int(relative))
+        return bool(conv), it.value, res.value, x
+
+    def minres(self, x0, b, max_iter, tol, relative=False):
+        return self._minres(0, 0, 1.0, x0, b, max_iter, tol, relative)
+
+    def pminres_jacobi(self, x0, b, max_iter, tol, relative=False, omega=1.0):
+        return self._minres(1, 1, omega, x0, b, max_iter, tol, relative)
+
+    def pminres_dummy(self, x0, b, max_iter, tol, relative=False):
+        return self._minres(1, 0, 1.0, x0, b, max_iter, tol, relative)
+
+    def lanczos_basis(self, r0, max_vecs=8):
+        n = self.rows
+        Q = np.zeros((max_vecs, n))
+        a, b = np.zeros(max_vecs), np.zeros(max_vecs)
+        k = lib().orc_lanczos_basis(n, *self._csr, _f64(r0), max_vecs, Q.reshape(-1), a, b)
+        return Q[:k], a[:k], b[:k]
+
+
+def dot(x, y):
+    return lib().orc_dot(len(x), _f64(x), _f64(y))
+
+
+def norm(x):
+    return lib().orc_norm(len(x), _f64(x))
+
+
+def norm_sq(x):
+    return lib().orc_norm_sq(len(x), _f64(x))
+
+
+def supnorm(x):
+    return lib().orc_supnorm(len(x), _f64(x))
+
+
+def kahan_dot(x, y):
+    return lib().orc_kahan_dot(len(x), _f64(x), _f64(y))
+
+
+def kahan_norm(x):
+    return lib().orc_kahan_norm(len(x), _f64(x))
+
+
+def axpy(a, x, y):
+    y = _f64(y).copy()
+    lib().orc_axpy(len(x), float(a), _f64(x), y)
+    return y
+
+
+def z_xpay(x, a, y):
+    z = np.zeros(len(x))
+    lib().orc_z_xpay(len(x), z, _f64(x), float(a), _f64(y))
+    return z
+
+
+def z_xpaypby2(x, a, y, b, y2):
+    z = np.zeros(len(x))
+    lib().orc_z_xpaypby2(len(x), z, _f64(x), float(a), _f64(y), float(b), _f64(y2))
+    return z
