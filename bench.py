@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- PCG-Jacobi iterations/s on the P2 Poisson brick (BASELINE.json configs[1] = C2:
+N = 185 cells/direction, n = 50 243 409 rows, nnz ~ 1.44 G) through the C ABI of libdrops_b200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one PCGSolverCL<JACPcCL>::Solve of --iters iterations with tol = 0 (fixed work,
+krylovsolver.h:149,177-178).  `value` times the device-resident entry point; `e2e` times the
+host-buffer entry point (x, b copied host->device and x device->host inside the call, pinned
+buffers) on a matrix that went through the host upload path in the reference's own CSR layout.
+`roofline` is the SpMV kernel (fused with the p.Ap dot): algorithmic bytes 12 nnz + 4(n+1) + 16 n
+per launch over its CUDA-event time inside the timed steps, against MEASURED_PEAKS.json.
+`cpu_baseline` / --impl reference time the compiled DROPS reference (oracle/_ref) -- or the plain-C
+oracle when it is absent -- on a bounded sample of the same brick family, scaled by rows to C2.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pcg_jacobi_iterations_per_s_p2_poisson"
+UNIT = "iterations/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--fe", type=int, default=2)
+    ap.add_argument("--cells", type=int, default=185, help="N cells per direction (C2: 185)")
+    ap.add_argument("--numbering", type=int, default=1, help="1 = DROPS order (vertices, then edges)")
+    ap.add_argument("--iters", type=int, default=200, help="PCG iterations per step (cdrdrops Iter = 200)")
+    ap.add_argument("--cpu-cells", type=int, default=64, help="brick size of the CPU sample")
+    ap.add_argument("--cpu-iters", type=int, default=25)
+    ap.add_argument("--no-host-matrix", action="store_true", help="skip the host CSR upload path in e2e")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 9 for i in range(4) if r[5 + i].lower() == "active"})
+        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+def cpu_reference_run(cells, iters, fe, numbering, repeats=1, warm=0):
+    """Times the reference's PCG+JACPcCL (oracle/_ref when built, else the plain-C oracle) on a
+    P2 brick of `cells` cells per direction.  Returns dict(rows, nnz, sec_per_iter, kind, cores)."""
+    from drops_b200 import capi
+    from oracle import ref as oref
+    n, rb, ci, va = capi.brick_csr_host(fe, cells, numbering)
+    xs = capi.brick_solution_host(fe, cells, numbering)
+    if oref.available():
+        kind, cores = "reference", oref.num_threads()
+        A = oref.RefMatrix(n, n, rb, ci, va)
+    else:
+        from oracle import port
+        kind, cores = "port", int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+        A = port.PortMatrix(n, n, rb, ci, va)
+    b = A.spmv(xs)
+    x0 = np.zeros(n)
+    times = []
+    for r in range(warm + repeats):
+        t0 = time.perf_counter()
+        conv, it, res, x = A.pcg_jacobi_timed(x0, b, iters, 0.0, True, 1.0)
+        dt = time.perf_counter() - t0
+        if r >= warm:
+            times.append(dt)
+    # SpMV alone, best of 5 (reference-layout bytes: 16 nnz + 8(n+1) + 16 n)
+    y = np.zeros(n)
+    best = 1e30
+    xin = np.ascontiguousarray(xs)
+    for _ in range(5):
+        t0 = time.perf_counter()
+        A.spmv_raw(xin, y)
+        best = min(best, time.perf_counter() - t0)
+    return {"rows": n, "nnz": len(va), "sec_per_iter": float(np.mean(times)) / iters, "kind": kind, "cores": cores,
+            "times": times, "resid": res, "spmv_s": best,
+            "spmv_gbs_ref_layout": (16.0 * len(va) + 8.0 * (n + 1) + 16.0 * n) / best / 1e9}
+
+
+def dist_setup(n_gpus):
+    """torch.distributed is plumbing only: rank discovery, barrier, max-over-ranks."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group(backend="nccl", rank=rank, world_size=world,
+                                    device_id=torch.device("cuda", local))
+        dist = dist_mod
+    return rank, world, local, dist
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from drops_b200 import capi
+    n_full, nnz_full = capi.brick_sizes(args.fe, args.cells)
+    # grow with the device count like our weak-scaling arm (rows per GPU fixed)
+    n_total = n_full * max(args.gpus, 1)
+    r = cpu_reference_run(args.cpu_cells, args.cpu_iters, args.fe, args.numbering,
+                          repeats=max(args.steps, 1), warm=max(args.warmup, 0))
+    scale = r["rows"] / n_total
+    value = scale / r["sec_per_iter"]
+    sample = (f"P{args.fe} brick N={args.cpu_cells} ({r['rows']} rows, {r['nnz']} nnz), {args.cpu_iters} PCG-Jacobi "
+              f"iterations per step, iterations/s scaled by rows {r['rows']}/{n_total} to the full workload")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(r["times"])),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C2: P{args.fe} Poisson, Kuhn brick N={args.cells} per GPU-count unit, "
+                               f"{n_total} rows, PCG + JACPcCL, tol=0", "numbering": args.numbering,
+                   "cpu_sample_cells": args.cpu_cells},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample,
+                         "spmv_gbs_reference_layout": r["spmv_gbs_ref_layout"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    rank, world, local, dist = dist_setup(args.gpus)
+    from drops_b200 import capi, _build
+    if not os.path.exists(_build.LIB_PATH):
+        _build.build()
+    capi.init(local)
+    if world > 1:
+        from drops_b200 import dist_bench
+        return dist_bench.run(args, rank, world, local, dist)
+
+    fe, N, numbering, iters = args.fe, args.cells, args.numbering, args.iters
+    n, nnz = capi.brick_sizes(fe, N)
+    t0 = time.perf_counter()
+    A = capi.Matrix.brick(fe, N, numbering)
+    capi.synchronize()
+    gen_s = time.perf_counter() - t0
+    xs, b, x = capi.Vector(n), capi.Vector(n), capi.Vector(n)
+    capi.brick_solution_device(fe, N, numbering, xs)
+    A.spmv_dev(xs, b)
+
+    def solve_dev():
+        x.fill(0.0)
+        conv, it, res = A.pcg_dev(x, b, iters, 0.0, True)
+        assert not conv and it == iters
+        return res
+
+    # ---- device-resident steps: `value` ------------------------------------------------------
+    for _ in range(args.warmup):
+        solve_dev()
+    capi.set_option("timing", 1)
+    capi.timing_reset()
+    sampler = ClockSampler(local)
+    sampler.start()
+    capi.synchronize()
+    l0 = capi.launch_count()
+    capi.timer_start()
+    for _ in range(args.steps):
+        resid = solve_dev()
+    ms = capi.timer_stop()
+    launches = capi.launch_count() - l0
+    clocks = sampler.stop()
+    spmv_ms, spmv_cnt = capi.timing("spmv")
+    upd_ms, upd_cnt = capi.timing("pcg.update")
+    dir_ms, dir_cnt = capi.timing("pcg.direction")
+    capi.set_option("timing", 0)
+    value = args.steps * iters / (ms / 1e3)
+
+    # ---- roofline of the dominant kernel --------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    spmv_bytes = 12.0 * nnz + 4.0 * (n + 1) + 16.0 * n
+    iter_bytes = 12.0 * nnz + 4.0 * (n + 1) + 13.0 * 8.0 * n
+    spmv_avg_ms = spmv_ms / max(spmv_cnt, 1)
+    achieved = spmv_bytes / (spmv_avg_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_spmv_sell<EPI_NONE,exact,dot> (q = A p fused with p.q)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": peak_src, "traffic": None,
+                "algorithmic_bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_avg_ms, "launches": spmv_cnt,
+                "iteration": {"algorithmic_bytes": iter_bytes,
+                              "achieved_gbs": iter_bytes * args.steps * iters / (ms / 1e3) / 1e9,
+                              "frac": iter_bytes * args.steps * iters / (ms / 1e3) / 1e9 / peak,
+                              "kernel_ms_share": {"spmv": spmv_ms / ms, "pcg.update": upd_ms / ms,
+                                                  "pcg.direction": dir_ms / ms}}}
+    prof = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- end to end through the host-buffer C ABI ----------------------------------------------
+    import torch
+    hb = torch.empty(n, dtype=torch.float64).pin_memory()
+    hx = torch.empty(n, dtype=torch.float64).pin_memory()
+    hb_np, hx_np = hb.numpy(), hx.numpy()
+    hb_np[:] = b.download()
+    upload_s, host_matrix = None, False
+    Ae = A
+    if not args.no_host_matrix:
+        import psutil
+        need = 16 * nnz + 8 * (n + 1) + (4 << 30)
+        if psutil.virtual_memory().available > need:
+            rb, ci, va = A.download()        # the reference's own layout: size_t indices, 16 B / entry
+            A.close()
+            t0 = time.perf_counter()
+            Ae = capi.Matrix(n, n, rb, ci, va, version=1)
+            capi.synchronize()
+            upload_s = time.perf_counter() - t0
+            host_matrix = True
+            del rb, ci, va
+    import ctypes as C
+    it_c, tol_c = C.c_int(), C.c_double()
+
+    def solve_host():
+        hx_np[:] = 0.0
+        it_c.value, tol_c.value = iters, 0.0
+        r = capi.lib().drops_b200_pcg(Ae.h, hx_np, hb_np, capi.PC_JACOBI, 1.0, C.byref(it_c), C.byref(tol_c), 1, None, 0)
+        capi.check(r)
+        return tol_c.value
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        solve_host()
+    capi.synchronize()
+    t0 = time.perf_counter()
+    capi.timer_start()
+    for _ in range(args.steps):
+        res_host = solve_host()
+    ms_e2e_dev = capi.timer_stop()
+    wall_e2e = time.perf_counter() - t0
+    e2e_value = args.steps * iters / max(wall_e2e, ms_e2e_dev / 1e3)
+    assert abs(res_host - resid) <= 1e-12 * abs(resid), (res_host, resid)
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 8 * n,
+           "ms_per_step": 1e3 * wall_e2e / args.steps, "matrix_via_host_csr": host_matrix,
+           "matrix_upload_s": upload_s, "matrix_upload_bytes": (16 * nnz + 8 * (n + 1)) if host_matrix else 0,
+           "note": "x,b pinned host buffers copied inside every Solve; the matrix handle is cached on "
+                   "SparseMatBaseCL::Version() and its one-time upload is reported separately"}
+
+    # ---- CPU baseline (bounded sample on the host cores) ----------------------------------------
+    cpu = None
+    if not args.no_cpu:
+        r = cpu_reference_run(args.cpu_cells, args.cpu_iters, fe, numbering)
+        cpu = {"value": (r["rows"] / n) / r["sec_per_iter"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+               "sample": f"P{fe} brick N={args.cpu_cells} ({r['rows']} rows, {r['nnz']} nnz), {args.cpu_iters} "
+                         f"PCG-Jacobi iterations, iterations/s scaled by rows {r['rows']}/{n} to C2",
+               "sample_iterations_per_s": 1.0 / r["sec_per_iter"],
+               "spmv_gbs_reference_layout": r["spmv_gbs_ref_layout"]}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C2: P{fe} Poisson on the Kuhn brick, N={N} cells/direction, {n} rows, {nnz} nnz, "
+                               f"PCGSolverCL<JACPcCL>, {iters} iterations per step, tol=0, relative",
+                   "numbering": "vertices-then-edges (DROPS order)" if numbering == 1 else "lexicographic",
+                   "cache": "inputs (17 GB matrix, 0.4 GB vectors) far exceed the 126 MB L2; no flush needed",
+                   "spmv_kernel": "sell-32-sigma exact", "generate_s": gen_s},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "final_relative_residual": resid,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

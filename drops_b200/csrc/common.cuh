@@ -1,0 +1,285 @@
+// common.cuh -- shared device helpers and the process-wide context of libdrops_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/drops_b200.h"
+
+namespace db200 {
+
+// ---------------------------------------------------------------------------------------------
+// Error plumbing: nothing throws across the C ABI.
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int  cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define DB_CUDA(call)                                                              \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess) return ::db200::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define DB_CHECK(call)                                                             \
+    do {                                                                           \
+        int s__ = (call);                                                          \
+        if (s__ < 0) return s__;                                                   \
+    } while (0)
+
+#define DB_ARG(cond, msg)                                                          \
+    do {                                                                           \
+        if (!(cond)) { ::db200::set_error("%s: %s", __func__, msg); return DROPS_B200_E_ARG; } \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Double-double accumulation for reductions.  The reference sums dot products with Kahan
+// compensation (num/spmat.h:317-333); a double-double tree has a smaller error bound and is
+// order-independent up to O(eps^2), which keeps Krylov iteration counts aligned.
+// ---------------------------------------------------------------------------------------------
+struct dd {
+    double hi, lo;
+};
+
+__host__ __device__ inline dd dd_zero() { return dd{0.0, 0.0}; }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ dd two_sum(double a, double b)
+{
+    const double s  = __dadd_rn(a, b);
+    const double bb = __dsub_rn(s, a);
+    const double e  = __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb));
+    return dd{s, e};
+}
+__device__ __forceinline__ dd quick_two_sum(double a, double b)   // |a| >= |b|
+{
+    const double s = __dadd_rn(a, b);
+    const double e = __dsub_rn(b, __dsub_rn(s, a));
+    return dd{s, e};
+}
+__device__ __forceinline__ dd dd_add(dd a, dd b)
+{
+    dd s = two_sum(a.hi, b.hi);
+    s.lo = __dadd_rn(s.lo, __dadd_rn(a.lo, b.lo));
+    return quick_two_sum(s.hi, s.lo);
+}
+// acc += a*b with the product taken exactly (FMA residual).
+__device__ __forceinline__ dd dd_add_prod(dd acc, double a, double b)
+{
+    const double p = __dmul_rn(a, b);
+    const double e = __fma_rn(a, b, -p);
+    dd s = two_sum(acc.hi, p);
+    s.lo = __dadd_rn(s.lo, __dadd_rn(acc.lo, e));
+    return quick_two_sum(s.hi, s.lo);
+}
+__device__ __forceinline__ double dd_round(dd a) { return __dadd_rn(a.hi, a.lo); }
+
+__device__ __forceinline__ dd dd_shfl_xor(dd v, int mask)
+{
+    dd o;
+    o.hi = __shfl_xor_sync(0xffffffffu, v.hi, mask);
+    o.lo = __shfl_xor_sync(0xffffffffu, v.lo, mask);
+    return o;
+}
+__device__ __forceinline__ dd warp_reduce_dd(dd v)
+{
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v = dd_add(v, dd_shfl_xor(v, m));
+    return v;
+}
+
+// Block-wide sum of NQ double-double quantities (fixed tree: lanes, then warps in order).
+// Result valid in thread 0.  smem must hold NQ * 32 dd.
+template <int NQ>
+__device__ __forceinline__ void block_reduce_dd(dd (&v)[NQ], dd* smem)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) v[q] = warp_reduce_dd(v[q]);
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) smem[q * 32 + warp] = v[q];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            dd t = lane < nwarp ? smem[q * 32 + lane] : dd_zero();
+            v[q] = warp_reduce_dd(t);
+        }
+    }
+    __syncthreads();
+}
+
+// Grid-wide deterministic reduction.  Every block stores its NQ partials, takes a ticket, and
+// the block that draws the last ticket sums all partials in block-index order (independent of
+// which block happens to be last) and returns true in ALL its threads with the totals in
+// thread 0's v[].  `partials` holds NQ*gridDim.x dd, `ticket` is zero on entry and is reset.
+template <int NQ>
+__device__ __forceinline__ bool grid_reduce_dd(dd (&v)[NQ], dd* smem, dd* partials, unsigned* ticket)
+{
+    __shared__ bool is_last;
+    block_reduce_dd<NQ>(v, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) partials[q * gridDim.x + blockIdx.x] = v[q];
+        __threadfence();
+        const unsigned t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+    dd acc[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        acc[q] = dd_zero();
+        // fixed assignment of partials to threads, fixed order inside a thread
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+            const volatile dd* p = partials + q * gridDim.x + b;
+            dd t; t.hi = p->hi; t.lo = p->lo;
+            acc[q] = dd_add(acc[q], t);
+        }
+    }
+    block_reduce_dd<NQ>(acc, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) v[q] = acc[q];
+        *ticket = 0u;
+    }
+    return true;
+}
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------------------------------------
+// Process-wide context
+// ---------------------------------------------------------------------------------------------
+struct TimingSlot {
+    double ms = 0.0;
+    long long launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+struct Ctx {
+    bool inited = false;
+    int device = -1;
+    int sm_count = 0;
+    int cc = 0;
+    cudaStream_t stream = nullptr;      // all solver work
+    cudaStream_t copy_stream = nullptr; // staging copies
+    // reduction workspace
+    dd* partials = nullptr;             // MAX_Q * max_grid
+    unsigned* tickets = nullptr;        // a few independent tickets
+    double* scratch_scalars = nullptr;  // device doubles for standalone dot/norm results
+    double* h_scalars = nullptr;        // pinned host mirror
+    int max_grid = 0;
+    long long launches = 0;
+    std::map<std::string, double> options;
+    std::map<std::string, TimingSlot> timing;
+    std::vector<cudaEvent_t> event_pool;
+};
+
+Ctx& ctx();
+int require_ctx();
+
+double opt(const char* key, double dflt);
+
+// RAII-less kernel timing: begin/end record events on ctx().stream when option "timing" != 0.
+struct ScopedTiming {
+    TimingSlot* slot = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    explicit ScopedTiming(const char* key);
+    ~ScopedTiming();
+};
+int timing_flush();
+
+inline void count_launch(int n = 1) { ctx().launches += n; }
+
+constexpr int kMaxQ = 4;            // quantities per fused reduction
+constexpr int kReduceThreads = 256;
+
+// Grid for streaming vector kernels: a multiple of the SM count.
+int vec_grid(size_t n, int threads, int per_thread);
+
+// device allocation helpers (status-returning)
+template <typename T>
+inline int dev_alloc(T** p, size_t count)
+{
+    *p = nullptr;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+        return DROPS_B200_E_NOMEM;
+    }
+    return 0;
+}
+inline void dev_free(void* p) { if (p) cudaFree(p); }
+
+}  // namespace db200
+
+// ---------------------------------------------------------------------------------------------
+// Handle types behind the C ABI
+// ---------------------------------------------------------------------------------------------
+struct drops_b200_vector_s {
+    size_t n = 0;
+    double* d = nullptr;
+    bool owns = true;
+};
+
+namespace db200 {
+
+// Sliced-ELL (C = 32, sigma-sorted) operator + the CSR it was built from.
+struct SellOp {
+    size_t rows = 0, cols = 0;
+    size_t nslices = 0;
+    size_t padded = 0;               // stored entries incl. padding
+    int64_t* slice_ptr = nullptr;    // nslices+1 offsets into col/val (multiples of 32)
+    int32_t* col = nullptr;          // -1 = padding
+    double*  val = nullptr;
+    int32_t* perm = nullptr;         // sorted position -> original row, -1 beyond rows
+    int max_width = 0;
+};
+
+struct CsrDev {
+    size_t rows = 0, cols = 0, nnz = 0;
+    int64_t* rowptr = nullptr;
+    int32_t* col = nullptr;
+    double*  val = nullptr;
+};
+
+}  // namespace db200
+
+struct drops_b200_matrix_s {
+    db200::CsrDev csr;               // kept: value updates, download, csr kernels, transpose build
+    db200::SellOp sell;              // y = A x
+    bool has_t = false;
+    db200::CsrDev csr_t;             // lazily built A^T (entries of a row ascending in source row)
+    db200::SellOp sell_t;
+    double* diag = nullptr;          // a_ii (first stored entry with col == row), rows entries
+    int* diag_missing = nullptr;     // device flag
+    bool diag_ok = false;
+    bool square = false;
+    uint64_t version = 0;
+    size_t device_bytes = 0;
+    // solver workspace cached with the matrix: vectors of max(rows, cols) doubles, grown on demand
+    std::vector<double*> work;
+    double* bridge[2] = {nullptr, nullptr};   // device copies of host x / b (host-buffer entry points)
+    void* d_scalars = nullptr;       // db200::SolverScalars
+    double* d_hist = nullptr;
+    int hist_alloc = 0;
+    double* d_small = nullptr;       // small device arrays (Hessenberg column, y, pointers)
+    size_t small_alloc = 0;
+};
+
+namespace db200 {
+// i-th cached work vector of the matrix (allocated on first use); nullptr + error on failure.
+double* work_vec(drops_b200_matrix_s* M, int i);
+void free_sell(SellOp& s);
+void free_csr(CsrDev& c);
+int build_transpose(drops_b200_matrix_s* M);
+}  // namespace db200

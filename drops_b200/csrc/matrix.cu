@@ -1,0 +1,582 @@
+// matrix.cu -- device-side SparseMatBaseCL: upload, diagonal, sliced-ELL build, transpose.
+//
+// Reference container: SparseMatBaseCL<double>, num/spmat.h:682-879 (CSR with size_t indices,
+// 16 B per stored entry).  HBM layout here, per matrix:
+//   csr  : rowptr int64[rows+1], col int32[nnz], val f64[nnz]          (12 B per entry)
+//   sell : slice_ptr int64[nslices+1], col int32[padded], val f64[padded], perm int32[32*nslices]
+//          slice = 32 rows (one warp), entry j of the 32 rows contiguous; rows are sorted by
+//          length (descending, ties by row index) inside windows of "sell.sigma" rows so that the
+//          32 rows of a slice have (almost) equal length; col = -1 marks padding.
+//   diag : f64[rows]  first stored entry with col == row (what JACPcCL divides by,
+//          num/precond.h:153-169; GetDiag num/spmat.h:993-1002 on ascending columns is the same).
+#include "common.cuh"
+
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cstring>
+#include <limits>
+
+namespace db200 {
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+__global__ void k_extract_diag(long long rows, const int64_t* __restrict__ rowptr,
+                               const int32_t* __restrict__ col, const double* __restrict__ val,
+                               double* __restrict__ diag, int* __restrict__ missing)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const int64_t b = rowptr[i], e = rowptr[i + 1];
+    int64_t k = b;
+    while (k < e && col[k] != (int32_t)i) ++k;
+    if (k < e) diag[i] = val[k];
+    else { diag[i] = 0.0; atomicExch(missing, 1); }
+}
+
+// One CTA sorts one window of SIGMA rows by (length descending, row ascending) with a bitonic
+// network in shared memory and emits perm + per-slice widths (in stored entries, i.e. width*32).
+template <int SIGMA>
+__global__ void __launch_bounds__(1024)
+k_sell_sort(long long rows, const int64_t* __restrict__ rowptr, int32_t* __restrict__ perm,
+            int64_t* __restrict__ slice_entries)
+{
+    __shared__ unsigned long long key[SIGMA];
+    const long long w0 = (long long)blockIdx.x * SIGMA;
+    for (int t = threadIdx.x; t < SIGMA; t += blockDim.x) {
+        const long long r = w0 + t;
+        if (r < rows) {
+            const unsigned long long len = (unsigned long long)(rowptr[r + 1] - rowptr[r]);
+            const unsigned long long inv = 0x7fffffffULL - (len > 0x7fffffffULL ? 0x7fffffffULL : len);
+            key[t] = (inv << 32) | (unsigned long long)(unsigned)t;
+        } else {
+            key[t] = ~0ULL;
+        }
+    }
+    __syncthreads();
+    for (int k = 2; k <= SIGMA; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < SIGMA; t += blockDim.x) {
+                const int l = t ^ j;
+                if (l > t) {
+                    const unsigned long long a = key[t], b = key[l];
+                    const bool up = (t & k) == 0;
+                    if ((a > b) == up) { key[t] = b; key[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int t = threadIdx.x; t < SIGMA; t += blockDim.x) {
+        const unsigned long long kk = key[t];
+        const bool pad = (kk == ~0ULL);
+        perm[w0 + t] = pad ? -1 : (int32_t)(w0 + (long long)(kk & 0xffffffffULL));
+        if ((t & 31) == 0) {
+            const long long len = pad ? 0 : (long long)(0x7fffffffULL - (kk >> 32));
+            slice_entries[(w0 + t) >> 5] = len * 32;
+        }
+    }
+}
+
+// sigma = 0/1: identity order (no sorting), widths = max length inside each slice.
+__global__ void k_sell_identity(long long rows, long long padded_rows, const int64_t* __restrict__ rowptr,
+                                int32_t* __restrict__ perm, int64_t* __restrict__ slice_entries)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= padded_rows) return;
+    long long len = 0;
+    if (r < rows) { perm[r] = (int32_t)r; len = rowptr[r + 1] - rowptr[r]; }
+    else perm[r] = -1;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        const long long o = __shfl_xor_sync(0xffffffffu, len, m);
+        len = o > len ? o : len;
+    }
+    if ((threadIdx.x & 31) == 0) slice_entries[r >> 5] = len * 32;
+}
+
+// One warp fills one slice.
+__global__ void k_sell_fill(long long nslices, const int64_t* __restrict__ slice_ptr,
+                            const int32_t* __restrict__ perm, const int64_t* __restrict__ rowptr,
+                            const int32_t* __restrict__ col, const double* __restrict__ val,
+                            int32_t* __restrict__ scol, double* __restrict__ sval)
+{
+    const int lane = threadIdx.x & 31;
+    const long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= nslices) return;
+    const int64_t base = slice_ptr[s];
+    const int width = (int)((slice_ptr[s + 1] - base) >> 5);
+    const int32_t row = perm[s * 32 + lane];
+    int64_t b = 0; int len = 0;
+    if (row >= 0) { b = rowptr[row]; len = (int)(rowptr[row + 1] - b); }
+    for (int j = 0; j < width; ++j) {
+        int32_t c = -1; double v = 0.0;
+        if (j < len) { c = col[b + j]; v = val[b + j]; }
+        scol[base + (int64_t)j * 32 + lane] = c;
+        sval[base + (int64_t)j * 32 + lane] = v;
+    }
+}
+
+// Only the values change (same pattern): refill sval from the CSR values.
+__global__ void k_sell_refill_values(long long nslices, const int64_t* __restrict__ slice_ptr,
+                                     const int32_t* __restrict__ perm, const int64_t* __restrict__ rowptr,
+                                     const double* __restrict__ val, double* __restrict__ sval)
+{
+    const int lane = threadIdx.x & 31;
+    const long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= nslices) return;
+    const int64_t base = slice_ptr[s];
+    const int width = (int)((slice_ptr[s + 1] - base) >> 5);
+    const int32_t row = perm[s * 32 + lane];
+    int64_t b = 0; int len = 0;
+    if (row >= 0) { b = rowptr[row]; len = (int)(rowptr[row + 1] - b); }
+    for (int j = 0; j < width; ++j)
+        sval[base + (int64_t)j * 32 + lane] = j < len ? val[b + j] : 0.0;
+}
+
+// ---- transpose ---------------------------------------------------------------------------
+__global__ void k_count_cols(long long nnz, const int32_t* __restrict__ col, unsigned long long* __restrict__ cnt)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nnz) atomicAdd(cnt + col[k], 1ULL);
+}
+
+__global__ void k_transpose_fill(long long rows, const int64_t* __restrict__ rowptr,
+                                 const int32_t* __restrict__ col, const double* __restrict__ val,
+                                 const int64_t* __restrict__ tptr, unsigned long long* __restrict__ cursor,
+                                 int32_t* __restrict__ tcol, double* __restrict__ tval)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+        const int32_t c = col[k];
+        const unsigned long long pos = atomicAdd(cursor + c, 1ULL);
+        tcol[tptr[c] + (int64_t)pos] = (int32_t)i;
+        tval[tptr[c] + (int64_t)pos] = val[k];
+    }
+}
+
+// Insertion-sort each transposed row by source row: y_ATx (num/spmat.h:1729-1746) adds the
+// contributions to y[c] in ascending row order, and so must we.
+__global__ void k_sort_rows(long long rows, const int64_t* __restrict__ ptr, int32_t* __restrict__ col,
+                            double* __restrict__ val)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const int64_t b = ptr[i], e = ptr[i + 1];
+    for (int64_t k = b + 1; k < e; ++k) {
+        const int32_t c = col[k]; const double v = val[k];
+        int64_t j = k - 1;
+        while (j >= b && col[j] > c) { col[j + 1] = col[j]; val[j + 1] = val[j]; --j; }
+        col[j + 1] = c; val[j + 1] = v;
+    }
+}
+
+__global__ void k_widen_i32(long long n, const int32_t* __restrict__ in, unsigned long long* __restrict__ out)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = (unsigned long long)(long long)in[k];
+}
+
+__global__ void k_copy_i64(long long n, const int64_t* __restrict__ in, unsigned long long* __restrict__ out)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = (unsigned long long)in[k];
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static inline int blocks_for(long long n, int threads) { return (int)std::max<long long>(1, (n + threads - 1) / threads); }
+
+static int exclusive_scan_i64(int64_t* d_inout, size_t count, cudaStream_t st)
+{
+    void* tmp = nullptr; size_t tmp_bytes = 0;
+    DB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_inout, d_inout, (long long)count, st));
+    DB_CHECK(dev_alloc((char**)&tmp, tmp_bytes));
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_inout, d_inout, (long long)count, st);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    dev_free(tmp);
+    DB_CUDA(e);
+    DB_CUDA(e2);
+    count_launch(2);
+    return 0;
+}
+
+double* work_vec(drops_b200_matrix_s* M, int i)
+{
+    if ((int)M->work.size() <= i) M->work.resize(i + 1, nullptr);
+    if (!M->work[i]) {
+        const size_t n = std::max(M->csr.rows, M->csr.cols);
+        if (dev_alloc(&M->work[i], n) < 0) return nullptr;
+    }
+    return M->work[i];
+}
+
+void free_sell(SellOp& s)
+{
+    dev_free(s.slice_ptr); dev_free(s.col); dev_free(s.val); dev_free(s.perm);
+    s = SellOp();
+}
+
+void free_csr(CsrDev& c)
+{
+    dev_free(c.rowptr); dev_free(c.col); dev_free(c.val);
+    c = CsrDev();
+}
+
+int build_sell(const CsrDev& A, SellOp& S, size_t* bytes)
+{
+    Ctx& c = ctx();
+    cudaStream_t st = c.stream;
+    free_sell(S);
+    S.rows = A.rows; S.cols = A.cols;
+    int sigma = (int)opt("sell.sigma", 4096.0);
+    const bool sorted = sigma >= 64;
+    if (sorted) {
+        if (sigma >= 4096) sigma = 4096; else if (sigma >= 2048) sigma = 2048;
+        else if (sigma >= 1024) sigma = 1024; else if (sigma >= 512) sigma = 512;
+        else if (sigma >= 256) sigma = 256; else if (sigma >= 128) sigma = 128; else sigma = 64;
+    } else sigma = 32;
+    const size_t nwin = (A.rows + sigma - 1) / sigma;
+    const size_t padded_rows = std::max<size_t>(nwin * sigma, 32);
+    S.nslices = padded_rows / 32;
+    DB_CHECK(dev_alloc(&S.perm, padded_rows));
+    DB_CHECK(dev_alloc(&S.slice_ptr, S.nslices + 1));
+    DB_CUDA(cudaMemsetAsync(S.slice_ptr, 0, (S.nslices + 1) * sizeof(int64_t), st));
+    if (A.rows > 0) {
+        if (!sorted) {
+            k_sell_identity<<<blocks_for(padded_rows, 256), 256, 0, st>>>((long long)A.rows, (long long)padded_rows, A.rowptr, S.perm, S.slice_ptr);
+        } else {
+            const int g = (int)nwin;
+            switch (sigma) {
+                case 4096: k_sell_sort<4096><<<g, 1024, 0, st>>>((long long)A.rows, A.rowptr, S.perm, S.slice_ptr); break;
+                case 2048: k_sell_sort<2048><<<g, 1024, 0, st>>>((long long)A.rows, A.rowptr, S.perm, S.slice_ptr); break;
+                case 1024: k_sell_sort<1024><<<g, 512, 0, st>>>((long long)A.rows, A.rowptr, S.perm, S.slice_ptr); break;
+                case 512:  k_sell_sort<512><<<g, 256, 0, st>>>((long long)A.rows, A.rowptr, S.perm, S.slice_ptr); break;
+                case 256:  k_sell_sort<256><<<g, 128, 0, st>>>((long long)A.rows, A.rowptr, S.perm, S.slice_ptr); break;
+                case 128:  k_sell_sort<128><<<g, 64, 0, st>>>((long long)A.rows, A.rowptr, S.perm, S.slice_ptr); break;
+                default:   k_sell_sort<64><<<g, 32, 0, st>>>((long long)A.rows, A.rowptr, S.perm, S.slice_ptr); break;
+            }
+        }
+        count_launch();
+        DB_CUDA(cudaGetLastError());
+    } else {
+        DB_CUDA(cudaMemsetAsync(S.perm, 0xff, padded_rows * sizeof(int32_t), st));
+    }
+    DB_CHECK(exclusive_scan_i64(S.slice_ptr, S.nslices + 1, st));
+    int64_t total = 0;
+    DB_CUDA(cudaMemcpyAsync(&total, S.slice_ptr + S.nslices, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    DB_CUDA(cudaStreamSynchronize(st));
+    S.padded = (size_t)total;
+    DB_CHECK(dev_alloc(&S.col, S.padded));
+    DB_CHECK(dev_alloc(&S.val, S.padded));
+    if (S.padded > 0) {
+        k_sell_fill<<<blocks_for((long long)S.nslices * 32, 256), 256, 0, st>>>(
+            (long long)S.nslices, S.slice_ptr, S.perm, A.rowptr, A.col, A.val, S.col, S.val);
+        count_launch();
+        DB_CUDA(cudaGetLastError());
+    }
+    DB_CUDA(cudaStreamSynchronize(st));
+    if (bytes) *bytes += S.padded * 12 + (S.nslices + 1) * 8 + padded_rows * 4;
+    return 0;
+}
+
+int refill_sell_values(const CsrDev& A, SellOp& S)
+{
+    if (S.padded == 0) return 0;
+    cudaStream_t st = ctx().stream;
+    k_sell_refill_values<<<blocks_for((long long)S.nslices * 32, 256), 256, 0, st>>>(
+        (long long)S.nslices, S.slice_ptr, S.perm, A.rowptr, A.val, S.val);
+    count_launch();
+    DB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int extract_diag(drops_b200_matrix_s* M)
+{
+    cudaStream_t st = ctx().stream;
+    M->diag_ok = false;
+    if (!M->square) return 0;
+    if (!M->diag) DB_CHECK(dev_alloc(&M->diag, M->csr.rows));
+    if (!M->diag_missing) DB_CHECK(dev_alloc(&M->diag_missing, 1));
+    DB_CUDA(cudaMemsetAsync(M->diag_missing, 0, sizeof(int), st));
+    if (M->csr.rows > 0) {
+        k_extract_diag<<<blocks_for((long long)M->csr.rows, 256), 256, 0, st>>>(
+            (long long)M->csr.rows, M->csr.rowptr, M->csr.col, M->csr.val, M->diag, M->diag_missing);
+        count_launch();
+        DB_CUDA(cudaGetLastError());
+    }
+    int missing = 0;
+    DB_CUDA(cudaMemcpyAsync(&missing, M->diag_missing, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DB_CUDA(cudaStreamSynchronize(st));
+    M->diag_ok = (missing == 0);
+    return 0;
+}
+
+int build_transpose(drops_b200_matrix_s* M)
+{
+    if (M->has_t) return 0;
+    Ctx& c = ctx();
+    cudaStream_t st = c.stream;
+    const CsrDev& A = M->csr;
+    CsrDev& T = M->csr_t;
+    free_csr(T);
+    T.rows = A.cols; T.cols = A.rows; T.nnz = A.nnz;
+    DB_ARG(A.rows <= (size_t)std::numeric_limits<int32_t>::max(), "too many rows for int32 column index of A^T");
+    DB_CHECK(dev_alloc(&T.rowptr, T.rows + 1));
+    DB_CHECK(dev_alloc(&T.col, T.nnz));
+    DB_CHECK(dev_alloc(&T.val, T.nnz));
+    unsigned long long* cursor = nullptr;
+    DB_CHECK(dev_alloc(&cursor, T.rows + 1));
+    DB_CUDA(cudaMemsetAsync(cursor, 0, (T.rows + 1) * sizeof(unsigned long long), st));
+    if (A.nnz > 0) {
+        k_count_cols<<<blocks_for((long long)A.nnz, 256), 256, 0, st>>>((long long)A.nnz, A.col, cursor);
+        count_launch();
+    }
+    DB_CUDA(cudaMemcpyAsync(T.rowptr, cursor, (T.rows + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    DB_CHECK(exclusive_scan_i64(T.rowptr, T.rows + 1, st));
+    DB_CUDA(cudaMemsetAsync(cursor, 0, (T.rows + 1) * sizeof(unsigned long long), st));
+    if (A.rows > 0 && A.nnz > 0) {
+        k_transpose_fill<<<blocks_for((long long)A.rows, 256), 256, 0, st>>>(
+            (long long)A.rows, A.rowptr, A.col, A.val, T.rowptr, cursor, T.col, T.val);
+        k_sort_rows<<<blocks_for((long long)T.rows, 256), 256, 0, st>>>((long long)T.rows, T.rowptr, T.col, T.val);
+        count_launch(2);
+    }
+    DB_CUDA(cudaGetLastError());
+    DB_CUDA(cudaStreamSynchronize(st));
+    dev_free(cursor);
+    size_t bytes = T.nnz * 12 + (T.rows + 1) * 8;
+    DB_CHECK(build_sell(T, M->sell_t, &bytes));
+    M->device_bytes += bytes;
+    M->has_t = true;
+    return 0;
+}
+
+void drop_transpose(drops_b200_matrix_s* M)
+{
+    if (!M->has_t) return;
+    free_csr(M->csr_t);
+    free_sell(M->sell_t);
+    M->has_t = false;
+}
+
+// Finishes a matrix whose csr member is filled.
+int finalize_matrix(drops_b200_matrix_s* M)
+{
+    M->square = (M->csr.rows == M->csr.cols);
+    M->device_bytes = M->csr.nnz * 12 + (M->csr.rows + 1) * 8;
+    DB_CHECK(extract_diag(M));
+    if (M->square) M->device_bytes += M->csr.rows * 8;
+    DB_CHECK(build_sell(M->csr, M->sell, &M->device_bytes));
+    return 0;
+}
+
+}  // namespace db200
+
+using namespace db200;
+
+extern "C" {
+
+int drops_b200_matrix_create(size_t rows, size_t cols, size_t nnz, const size_t* rowbeg,
+                             const size_t* colind, const double* val, uint64_t version,
+                             drops_b200_matrix_t* out)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(out != nullptr, "null out");
+    DB_ARG(rowbeg != nullptr, "null rowbeg");
+    DB_ARG(nnz == 0 || (colind != nullptr && val != nullptr), "null colind/val");
+    *out = nullptr;
+    if (rows > (size_t)std::numeric_limits<int32_t>::max() - 4096 ||
+        cols > (size_t)std::numeric_limits<int32_t>::max()) {
+        set_error("matrix %zux%zu exceeds the int32 row/column index of one device partition", rows, cols);
+        return DROPS_B200_E_RANGE;
+    }
+    DB_ARG(rowbeg[rows] == nnz && rowbeg[0] == 0, "rowbeg[0] != 0 or rowbeg[rows] != nnz");
+    Ctx& c = ctx();
+    cudaStream_t st = c.stream;
+    drops_b200_matrix_s* M = new drops_b200_matrix_s;
+    M->version = version;
+    CsrDev& A = M->csr;
+    A.rows = rows; A.cols = cols; A.nnz = nnz;
+    int s;
+    if ((s = dev_alloc(&A.rowptr, rows + 1)) < 0 || (s = dev_alloc(&A.col, nnz)) < 0 ||
+        (s = dev_alloc(&A.val, nnz)) < 0) {
+        drops_b200_matrix_destroy(M);
+        return s;
+    }
+    static_assert(sizeof(size_t) == sizeof(int64_t), "size_t must be 64 bit");
+    cudaError_t e = cudaMemcpyAsync(A.rowptr, rowbeg, (rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && nnz > 0)
+        e = cudaMemcpyAsync(A.val, val, nnz * sizeof(double), cudaMemcpyHostToDevice, st);
+    // narrow the column indices through a pinned double buffer
+    const size_t chunk = 8u << 20;
+    int32_t* stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool bad_col = false;
+    if (e == cudaSuccess && nnz > 0) {
+        for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+            e = cudaMallocHost((void**)&stage[b], std::min(chunk, nnz) * sizeof(int32_t));
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming);
+        }
+        int b = 0;
+        for (size_t off = 0; off < nnz && e == cudaSuccess; off += chunk, b ^= 1) {
+            const size_t m = std::min(chunk, nnz - off);
+            e = cudaEventSynchronize(ev[b]);
+            if (e != cudaSuccess) break;
+            int32_t* dst = stage[b];
+            const size_t* src = colind + off;
+            int bad = 0;
+#pragma omp parallel for reduction(| : bad)
+            for (long long k = 0; k < (long long)m; ++k) {
+                bad |= (src[k] >= cols);
+                dst[k] = (int32_t)src[k];
+            }
+            bad_col |= (bad != 0);
+            e = cudaMemcpyAsync(A.col + off, dst, m * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaEventRecord(ev[b], st);
+        }
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    for (int b = 0; b < 2; ++b) {
+        if (stage[b]) cudaFreeHost(stage[b]);
+        if (ev[b]) cudaEventDestroy(ev[b]);
+    }
+    if (e != cudaSuccess) {
+        drops_b200_matrix_destroy(M);
+        return cuda_fail(e, "matrix upload", __FILE__, __LINE__);
+    }
+    if (bad_col) {
+        drops_b200_matrix_destroy(M);
+        set_error("drops_b200_matrix_create: a column index is >= cols");
+        return DROPS_B200_E_ARG;
+    }
+    s = finalize_matrix(M);
+    if (s < 0) { drops_b200_matrix_destroy(M); return s; }
+    *out = M;
+    return 0;
+}
+
+int drops_b200_matrix_create_device(size_t rows, size_t cols, size_t nnz, const int64_t* d_rowptr,
+                                    const int32_t* d_colind, const double* d_val, uint64_t version,
+                                    drops_b200_matrix_t* out)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(out != nullptr && d_rowptr != nullptr, "null argument");
+    DB_ARG(nnz == 0 || (d_colind != nullptr && d_val != nullptr), "null colind/val");
+    *out = nullptr;
+    if (rows > (size_t)std::numeric_limits<int32_t>::max() - 4096 ||
+        cols > (size_t)std::numeric_limits<int32_t>::max()) {
+        set_error("matrix %zux%zu exceeds the int32 row/column index of one device partition", rows, cols);
+        return DROPS_B200_E_RANGE;
+    }
+    cudaStream_t st = ctx().stream;
+    drops_b200_matrix_s* M = new drops_b200_matrix_s;
+    M->version = version;
+    CsrDev& A = M->csr;
+    A.rows = rows; A.cols = cols; A.nnz = nnz;
+    int s;
+    if ((s = dev_alloc(&A.rowptr, rows + 1)) < 0 || (s = dev_alloc(&A.col, nnz)) < 0 ||
+        (s = dev_alloc(&A.val, nnz)) < 0) {
+        drops_b200_matrix_destroy(M);
+        return s;
+    }
+    cudaError_t e = cudaMemcpyAsync(A.rowptr, d_rowptr, (rows + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess && nnz)
+        e = cudaMemcpyAsync(A.col, d_colind, nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess && nnz)
+        e = cudaMemcpyAsync(A.val, d_val, nnz * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        drops_b200_matrix_destroy(M);
+        return cuda_fail(e, "device csr copy", __FILE__, __LINE__);
+    }
+    s = finalize_matrix(M);
+    if (s < 0) { drops_b200_matrix_destroy(M); return s; }
+    *out = M;
+    return 0;
+}
+
+int drops_b200_matrix_update_values(drops_b200_matrix_t M, const double* val, uint64_t version)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(M != nullptr && (val != nullptr || M->csr.nnz == 0), "null argument");
+    cudaStream_t st = ctx().stream;
+    if (M->csr.nnz)
+        DB_CUDA(cudaMemcpyAsync(M->csr.val, val, M->csr.nnz * sizeof(double), cudaMemcpyHostToDevice, st));
+    DB_CHECK(refill_sell_values(M->csr, M->sell));
+    DB_CHECK(extract_diag(M));
+    drop_transpose(M);
+    M->version = version;
+    DB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int drops_b200_matrix_destroy(drops_b200_matrix_t M)
+{
+    if (!M) return 0;
+    if (ctx().inited) cudaStreamSynchronize(ctx().stream);
+    free_csr(M->csr); free_sell(M->sell);
+    free_csr(M->csr_t); free_sell(M->sell_t);
+    dev_free(M->diag); dev_free(M->diag_missing);
+    for (double* w : M->work) dev_free(w);
+    dev_free(M->bridge[0]); dev_free(M->bridge[1]);
+    dev_free(M->d_scalars); dev_free(M->d_hist); dev_free(M->d_small);
+    delete M;
+    return 0;
+}
+
+int drops_b200_matrix_info(drops_b200_matrix_t M, size_t* rows, size_t* cols, size_t* nnz,
+                           uint64_t* version, size_t* device_bytes, size_t* padded_nnz)
+{
+    DB_ARG(M != nullptr, "null matrix");
+    if (rows) *rows = M->csr.rows;
+    if (cols) *cols = M->csr.cols;
+    if (nnz) *nnz = M->csr.nnz;
+    if (version) *version = M->version;
+    if (device_bytes) *device_bytes = M->device_bytes;
+    if (padded_nnz) *padded_nnz = M->sell.padded;
+    return 0;
+}
+
+int drops_b200_matrix_download(drops_b200_matrix_t M, size_t* rowbeg, size_t* colind, double* val)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(M != nullptr && rowbeg != nullptr, "null argument");
+    cudaStream_t st = ctx().stream;
+    const CsrDev& A = M->csr;
+    DB_CUDA(cudaMemcpyAsync(rowbeg, A.rowptr, (A.rows + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (A.nnz) {
+        DB_ARG(colind != nullptr && val != nullptr, "null colind/val");
+        DB_CUDA(cudaMemcpyAsync(val, A.val, A.nnz * sizeof(double), cudaMemcpyDeviceToHost, st));
+        // widen the columns on the device in chunks, reusing a bounce buffer
+        const size_t chunk = 32u << 20;
+        unsigned long long* wide = nullptr;
+        DB_CHECK(dev_alloc(&wide, std::min(chunk, A.nnz)));
+        for (size_t off = 0; off < A.nnz; off += chunk) {
+            const size_t m = std::min(chunk, A.nnz - off);
+            k_widen_i32<<<blocks_for((long long)m, 256), 256, 0, st>>>((long long)m, A.col + off, wide);
+            count_launch();
+            cudaError_t e = cudaMemcpyAsync(colind + off, wide, m * sizeof(size_t), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { dev_free(wide); return cuda_fail(e, "download", __FILE__, __LINE__); }
+        }
+        dev_free(wide);
+    }
+    DB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int drops_b200_matrix_diag(drops_b200_matrix_t M, double* diag)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(M != nullptr && diag != nullptr, "null argument");
+    DB_ARG(M->square, "GetDiag needs a square matrix");
+    cudaStream_t st = ctx().stream;
+    DB_CUDA(cudaMemcpyAsync(diag, M->diag, M->csr.rows * sizeof(double), cudaMemcpyDeviceToHost, st));
+    DB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"

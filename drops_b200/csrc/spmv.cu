@@ -1,0 +1,275 @@
+// spmv.cu -- y = A x on sm_100a.
+//
+// The hot kernel of every Krylov iteration (reference: y_Ax, num/spmat.h:1682-1709).  It is
+// HBM-bound (2 flops per 12 matrix bytes), so the design goal is: stream col/val exactly once,
+// fully coalesced, with many loads in flight; keep x in L1/L2; write y once.  No tensor cores.
+//
+// k_spmv_sell: sliced ELLPACK, slice height 32 = one warp, one thread per row.
+//   * inside a slice entry j of all 32 rows is contiguous -> every load instruction of a warp is
+//     one 128 B (col) / 256 B (val) fully used line; rows are sigma-sorted by length at upload so
+//     padding is < 1 % on the P2 brick (65/27/27/19 entries per row).
+//   * each thread walks ITS row left to right: sum = ((0 + a0*x0) + a1*x1) + ... with the product
+//     rounded before the add -- the reference's summation order, so the result is bit-identical
+//     to y_Ax compiled without FMA contraction ("spmv.exact" = 1, the default).  The kernel is
+//     nowhere near FP64-bound, so the unfused mul/add costs nothing.
+//   * matrix stream: ld.global.cs (evict-first, does not displace x); x: ld.global.nc (L1).
+//   * a CTA owns a contiguous range of slices and its warps walk it round-robin, so the x lines
+//     touched by neighbouring mesh lines are reused out of the SM's L1.
+//   * optional epilogues (Jacobi scaling, b - Ax, Ax - beta z) and a fused dot product with a
+//     second vector save whole passes over HBM in PCG / GMRES / MINRES.
+// k_spmv_csr_vector: LANES threads per row on plain CSR (FMA + shuffle tree); kept as the
+//   comparison point ("spmv.kernel" = 1) and for matrices where SELL padding would explode.
+#include "spmv.cuh"
+
+namespace db200 {
+
+struct SellView {
+    const int64_t* slice_ptr;
+    const int32_t* col;
+    const double* val;
+    const int32_t* perm;
+    long long nslices;
+};
+
+struct EpiArgs {
+    const double* aux;
+    double omega;
+    const double* beta;
+    double beta_val;
+    const double* dotv;
+    double* dot_out;
+    const int* done;
+    dd* partials;
+    unsigned* ticket;
+};
+
+template <int EPI>
+__device__ __forceinline__ double apply_epilogue(double s, int row, const EpiArgs& e, double beta)
+{
+    if (EPI == EPI_JACOBI) return __ddiv_rn(__dmul_rn(e.omega, s), __ldg(e.aux + row));
+    if (EPI == EPI_RESID)  return __dsub_rn(__ldg(e.aux + row), s);
+    if (EPI == EPI_AXMBY)  return __dsub_rn(s, __dmul_rn(beta, __ldg(e.aux + row)));
+    return s;
+}
+
+constexpr int kSellUnroll = 4;
+
+template <int EPI, bool EXACT, bool DOT>
+__global__ void __launch_bounds__(1024)
+k_spmv_sell(SellView A, const double* __restrict__ x, double* __restrict__ y, EpiArgs e)
+{
+    if (e.done != nullptr && *e.done != 0) return;
+    __shared__ dd red_smem[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const long long s_begin = A.nslices * (long long)blockIdx.x / gridDim.x;
+    const long long s_end   = A.nslices * (long long)(blockIdx.x + 1) / gridDim.x;
+    const double beta = (EPI == EPI_AXMBY) ? (e.beta != nullptr ? *e.beta : e.beta_val) : 0.0;
+    dd acc[1] = {dd_zero()};
+
+    for (long long s = s_begin + warp; s < s_end; s += nwarp) {
+        const int64_t base = A.slice_ptr[s];
+        const int width = (int)((A.slice_ptr[s + 1] - base) >> 5);
+        const int32_t* cp = A.col + base + lane;
+        const double* vp = A.val + base + lane;
+        double sum = 0.0;
+        int j = 0;
+        for (; j + kSellUnroll <= width; j += kSellUnroll) {
+            int c[kSellUnroll];
+            double v[kSellUnroll], xv[kSellUnroll];
+#pragma unroll
+            for (int u = 0; u < kSellUnroll; ++u) {
+                c[u] = __ldcs(cp + (size_t)(j + u) * 32);
+                v[u] = __ldcs(vp + (size_t)(j + u) * 32);
+            }
+#pragma unroll
+            for (int u = 0; u < kSellUnroll; ++u) xv[u] = c[u] >= 0 ? __ldg(x + c[u]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < kSellUnroll; ++u) {
+                if (c[u] >= 0)
+                    sum = EXACT ? __dadd_rn(sum, __dmul_rn(v[u], xv[u])) : fma(v[u], xv[u], sum);
+            }
+        }
+        for (; j < width; ++j) {
+            const int c = __ldcs(cp + (size_t)j * 32);
+            const double v = __ldcs(vp + (size_t)j * 32);
+            if (c >= 0) {
+                const double xv = __ldg(x + c);
+                sum = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv)) : fma(v, xv, sum);
+            }
+        }
+        const int row = A.perm[s * 32 + lane];
+        if (row >= 0) {
+            const double out = apply_epilogue<EPI>(sum, row, e, beta);
+            y[row] = out;
+            if (DOT) acc[0] = dd_add_prod(acc[0], out, __ldg(e.dotv + row));
+        }
+    }
+    if (DOT) {
+        if (grid_reduce_dd<1>(acc, red_smem, e.partials, e.ticket)) {
+            if (threadIdx.x == 0) *e.dot_out = dd_round(acc[0]);
+        }
+    }
+}
+
+template <int LANES, int EPI, bool DOT>
+__global__ void __launch_bounds__(256)
+k_spmv_csr_vector(long long rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                  const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
+                  EpiArgs e)
+{
+    if (e.done != nullptr && *e.done != 0) return;
+    __shared__ dd red_smem[32];
+    constexpr int GPW = 32 / LANES;   // row groups per warp
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LANES, grp = lane / LANES;
+    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const double beta = (EPI == EPI_AXMBY) ? (e.beta != nullptr ? *e.beta : e.beta_val) : 0.0;
+    dd acc[1] = {dd_zero()};
+
+    for (long long rb = warp_global * GPW; rb < rows; rb += nwarps * GPW) {
+        const long long row = rb + grp;
+        double sum = 0.0;
+        if (row < rows) {
+            const int64_t b = rowptr[row], en = rowptr[row + 1];
+            for (int64_t k = b + sub; k < en; k += LANES)
+                sum = fma(__ldcs(val + k), __ldg(x + __ldcs(col + k)), sum);
+        }
+#pragma unroll
+        for (int m = LANES / 2; m >= 1; m >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, m);
+        if (row < rows && sub == 0) {
+            const double out = apply_epilogue<EPI>(sum, (int)row, e, beta);
+            y[row] = out;
+            if (DOT) acc[0] = dd_add_prod(acc[0], out, __ldg(e.dotv + row));
+        }
+    }
+    if (DOT) {
+        if (grid_reduce_dd<1>(acc, red_smem, e.partials, e.ticket)) {
+            if (threadIdx.x == 0) *e.dot_out = dd_round(acc[0]);
+        }
+    }
+}
+
+static EpiArgs make_epi(const SpmvArgs& a)
+{
+    Ctx& c = ctx();
+    EpiArgs e;
+    e.aux = a.aux;
+    e.omega = a.omega;
+    e.beta = a.beta;
+    e.beta_val = a.beta_val;
+    e.dotv = a.dotv;
+    e.dot_out = a.dot_out;
+    e.done = a.done;
+    e.partials = c.partials + (size_t)a.slot * kMaxQ * c.max_grid;
+    e.ticket = c.tickets + a.slot;
+    return e;
+}
+
+template <int EPI, bool EXACT>
+static void launch_sell(const SellView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads,
+                        cudaStream_t st)
+{
+    if (a.dotv != nullptr)
+        k_spmv_sell<EPI, EXACT, true><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
+    else
+        k_spmv_sell<EPI, EXACT, false><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
+}
+
+template <bool EXACT>
+static void launch_sell_epi(const SellView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads,
+                            cudaStream_t st)
+{
+    switch (a.epilogue) {
+        case EPI_JACOBI: launch_sell<EPI_JACOBI, EXACT>(v, a, e, grid, threads, st); break;
+        case EPI_RESID:  launch_sell<EPI_RESID, EXACT>(v, a, e, grid, threads, st); break;
+        case EPI_AXMBY:  launch_sell<EPI_AXMBY, EXACT>(v, a, e, grid, threads, st); break;
+        default:         launch_sell<EPI_NONE, EXACT>(v, a, e, grid, threads, st); break;
+    }
+}
+
+int spmv_sell(const SellOp& A, const SpmvArgs& a)
+{
+    Ctx& c = ctx();
+    DB_ARG(a.x != nullptr && a.y != nullptr, "null vector");
+    DB_ARG(a.x != a.y, "x and y must not alias");
+    DB_ARG(a.epilogue == EPI_NONE || a.aux != nullptr, "epilogue needs aux vector");
+    DB_ARG(a.dotv == nullptr || a.dot_out != nullptr, "fused dot needs an output scalar");
+    if (A.rows == 0) return 0;
+    int threads = (int)opt("spmv.threads", 512);
+    if (threads < 32) threads = 32;
+    if (threads > 1024) threads = 1024;
+    threads &= ~31;
+    const double per_sm = opt("spmv.ctas_per_sm", 4.0);
+    long long grid = (long long)(per_sm * c.sm_count + 0.5);
+    const long long max_useful = ((long long)A.nslices * 32 + threads - 1) / threads;
+    if (grid > max_useful) grid = max_useful;
+    if (grid > c.max_grid) grid = c.max_grid;
+    if (grid < 1) grid = 1;
+    cudaStream_t st = a.stream ? a.stream : c.stream;
+    SellView v{A.slice_ptr, A.col, A.val, A.perm, (long long)A.nslices};
+    EpiArgs e = make_epi(a);
+    if (opt("spmv.exact", 1.0) != 0.0) launch_sell_epi<true>(v, a, e, (int)grid, threads, st);
+    else launch_sell_epi<false>(v, a, e, (int)grid, threads, st);
+    count_launch();
+    DB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int LANES, int EPI>
+static void launch_csrv(const CsrDev& A, const SpmvArgs& a, const EpiArgs& e, int grid, cudaStream_t st)
+{
+    if (a.dotv != nullptr)
+        k_spmv_csr_vector<LANES, EPI, true><<<grid, 256, 0, st>>>((long long)A.rows, A.rowptr, A.col, A.val, a.x, a.y, e);
+    else
+        k_spmv_csr_vector<LANES, EPI, false><<<grid, 256, 0, st>>>((long long)A.rows, A.rowptr, A.col, A.val, a.x, a.y, e);
+}
+
+template <int LANES>
+static void launch_csrv_epi(const CsrDev& A, const SpmvArgs& a, const EpiArgs& e, int grid, cudaStream_t st)
+{
+    switch (a.epilogue) {
+        case EPI_JACOBI: launch_csrv<LANES, EPI_JACOBI>(A, a, e, grid, st); break;
+        case EPI_RESID:  launch_csrv<LANES, EPI_RESID>(A, a, e, grid, st); break;
+        case EPI_AXMBY:  launch_csrv<LANES, EPI_AXMBY>(A, a, e, grid, st); break;
+        default:         launch_csrv<LANES, EPI_NONE>(A, a, e, grid, st); break;
+    }
+}
+
+int spmv_csr_vector(const CsrDev& A, const SpmvArgs& a, int lanes)
+{
+    Ctx& c = ctx();
+    DB_ARG(a.x != nullptr && a.y != nullptr && a.x != a.y, "bad vectors");
+    DB_ARG(A.rowptr != nullptr, "matrix holds no CSR copy");
+    if (A.rows == 0) return 0;
+    long long grid = (long long)c.sm_count * 8;
+    const long long rows_per_block = 256 / lanes;
+    const long long need = ((long long)A.rows + rows_per_block - 1) / rows_per_block;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    cudaStream_t st = a.stream ? a.stream : c.stream;
+    EpiArgs e = make_epi(a);
+    switch (lanes) {
+        case 2:  launch_csrv_epi<2>(A, a, e, (int)grid, st); break;
+        case 4:  launch_csrv_epi<4>(A, a, e, (int)grid, st); break;
+        case 8:  launch_csrv_epi<8>(A, a, e, (int)grid, st); break;
+        case 16: launch_csrv_epi<16>(A, a, e, (int)grid, st); break;
+        default: launch_csrv_epi<32>(A, a, e, (int)grid, st); break;
+    }
+    count_launch();
+    DB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int spmv_apply(const drops_b200_matrix_s* M, bool transposed, const SpmvArgs& a)
+{
+    ScopedTiming t(transposed ? "spmv_t" : "spmv");
+    const int kind = (int)opt("spmv.kernel", 0.0);
+    if (kind == 1) {
+        const int lanes = (int)opt("spmv.lanes", 8.0);
+        return spmv_csr_vector(transposed ? M->csr_t : M->csr, a, lanes);
+    }
+    return spmv_sell(transposed ? M->sell_t : M->sell, a);
+}
+
+}  // namespace db200

@@ -1,0 +1,624 @@
+// vecops.cu -- streaming vector kernels of the Krylov solvers, fused so that every iteration
+// touches each vector the minimum number of times (13 vector passes per
+// PCG-Jacobi iteration instead of the reference's ~21), with deterministic double-double
+// reductions finished on the device by the last block (no host round trip per iteration).
+//
+// Element arithmetic follows the reference's valarray expressions exactly: products are rounded
+// before the add (__dmul_rn/__dadd_rn, no FMA contraction), divisions are IEEE divisions.
+#include "vecops.cuh"
+
+namespace db200 {
+
+// ------------------------------------------------------------------------------------------
+// generic streaming kernel: Op provides
+//   bool begin()                         -- load scalars; false = whole kernel is a no-op
+//   void elem(size_t i, dd* acc)         -- per element work, accumulates NQ reductions
+//   void finish(const dd* acc)           -- run by ONE thread after the grid-wide reduction
+// ------------------------------------------------------------------------------------------
+template <int NQ, class Op>
+__global__ void __launch_bounds__(kReduceThreads)
+k_stream(size_t n, Op op, dd* partials, unsigned* ticket)
+{
+    constexpr int NA = NQ > 0 ? NQ : 1;
+    __shared__ dd red_smem[NA * 32];
+    if (!op.begin()) return;
+    dd acc[NA];
+#pragma unroll
+    for (int q = 0; q < NA; ++q) acc[q] = dd_zero();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) op.elem(i, acc);
+    if constexpr (NQ > 0) {
+        if (grid_reduce_dd<NA>(acc, red_smem, partials, ticket)) {
+            if (threadIdx.x == 0) op.finish(acc);
+        }
+    }
+}
+
+template <int NQ, class Op>
+static int launch_stream(size_t n, const Op& op, const char* timing_key, int slot = 0)
+{
+    Ctx& c = ctx();
+    ScopedTiming t(timing_key);
+    const int grid = vec_grid(n, kReduceThreads, 4);
+    k_stream<NQ, Op><<<grid, kReduceThreads, 0, c.stream>>>(
+        n, op, c.partials + (size_t)slot * kMaxQ * c.max_grid, c.tickets + slot);
+    count_launch();
+    DB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dvd(double a, double b) { return __ddiv_rn(a, b); }
+
+// z = M^-1 r for the two preconditioners on the path
+__device__ __forceinline__ double precond(int pc, double omega, double r, const double* d, size_t i)
+{
+    return pc == DROPS_B200_PC_JACOBI ? dvd(mul(omega, r), d[i]) : r;
+}
+
+// ------------------------------------------------------------------------------------------
+// standalone ops
+// ------------------------------------------------------------------------------------------
+struct OpDot {
+    const double* x; const double* y; double* out;
+    __device__ bool begin() { return true; }
+    __device__ void elem(size_t i, dd* acc) { acc[0] = dd_add_prod(acc[0], x[i], y[i]); }
+    __device__ void finish(const dd* acc) { *out = dd_round(acc[0]); }
+};
+int vec_dot(size_t n, const double* x, const double* y, double* d_out)
+{
+    return launch_stream<1>(n, OpDot{x, y, d_out}, "vec");
+}
+
+__global__ void k_supnorm(size_t n, const double* __restrict__ x, double* partial)
+{
+    __shared__ double sm[32];
+    double m = 0.0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) m = fmax(m, fabs(x[i]));
+    for (int k = 16; k >= 1; k >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, k));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.0;
+        for (int k = 16; k >= 1; k >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, k));
+        if (threadIdx.x == 0) partial[blockIdx.x] = m;
+    }
+}
+__global__ void k_supnorm_final(int nb, const double* partial, double* out)
+{
+    double m = 0.0;
+    for (int i = threadIdx.x; i < nb; i += 32) m = fmax(m, partial[i]);
+    for (int k = 16; k >= 1; k >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, k));
+    if (threadIdx.x == 0) *out = m;
+}
+int vec_supnorm(size_t n, const double* x, double* d_out)
+{
+    Ctx& c = ctx();
+    const int grid = vec_grid(n, kReduceThreads, 4);
+    double* partial = reinterpret_cast<double*>(c.partials);
+    k_supnorm<<<grid, kReduceThreads, 0, c.stream>>>(n, x, partial);
+    k_supnorm_final<<<1, 32, 0, c.stream>>>(grid, partial, d_out);
+    count_launch(2);
+    DB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+struct OpAxpy {
+    double a; const double* x; double* y;
+    __device__ bool begin() { return true; }
+    __device__ void elem(size_t i, dd*) { y[i] = add(y[i], mul(a, x[i])); }
+    __device__ void finish(const dd*) {}
+};
+int vec_axpy(size_t n, double a, const double* x, double* y) { return launch_stream<0>(n, OpAxpy{a, x, y}, "vec"); }
+
+struct OpZxpay {
+    double* z; const double* x; double a; const double* y;
+    __device__ bool begin() { return true; }
+    __device__ void elem(size_t i, dd*) { z[i] = add(x[i], mul(a, y[i])); }
+    __device__ void finish(const dd*) {}
+};
+int vec_z_xpay(size_t n, double* z, const double* x, double a, const double* y)
+{
+    return launch_stream<0>(n, OpZxpay{z, x, a, y}, "vec");
+}
+
+struct OpZxpaypby2 {
+    double* z; const double* x; double a; const double* y; double b; const double* y2;
+    __device__ bool begin() { return true; }
+    __device__ void elem(size_t i, dd*) { z[i] = add(add(x[i], mul(a, y[i])), mul(b, y2[i])); }
+    __device__ void finish(const dd*) {}
+};
+int vec_z_xpaypby2(size_t n, double* z, const double* x, double a, const double* y, double b, const double* y2)
+{
+    return launch_stream<0>(n, OpZxpaypby2{z, x, a, y, b, y2}, "vec");
+}
+
+struct OpJacobi {
+    double omega; const double* d; const double* b; double* x;
+    __device__ bool begin() { return true; }
+    __device__ void elem(size_t i, dd*) { x[i] = dvd(mul(omega, b[i]), d[i]); }
+    __device__ void finish(const dd*) {}
+};
+int vec_jacobi(size_t n, double omega, const double* d, const double* b, double* x)
+{
+    return launch_stream<0>(n, OpJacobi{omega, d, b, x}, "vec");
+}
+
+struct OpFill {
+    double* x; double v;
+    __device__ bool begin() { return true; }
+    __device__ void elem(size_t i, dd*) { x[i] = v; }
+    __device__ void finish(const dd*) {}
+};
+int vec_fill(size_t n, double* x, double v) { return launch_stream<0>(n, OpFill{x, v}, "vec"); }
+
+struct OpFillHash {
+    double* x;
+    __device__ bool begin() { return true; }
+    __device__ void elem(size_t i, dd*)
+    {
+        const unsigned long long h = ((unsigned long long)i * 2654435761ULL) & 0xffffffffULL;
+        x[i] = (double)h / 4294967296.0 - 0.5;
+    }
+    __device__ void finish(const dd*) {}
+};
+int vec_fill_hash(size_t n, double* x) { return launch_stream<0>(n, OpFillHash{x}, "vec"); }
+
+int vec_copy(size_t n, double* dst, const double* src)
+{
+    if (n == 0 || dst == src) return 0;
+    DB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream));
+    return 0;
+}
+
+struct OpSub {
+    double* out; const double* a; const double* b;
+    __device__ bool begin() { return true; }
+    __device__ void elem(size_t i, dd*) { out[i] = sub(a[i], b[i]); }
+    __device__ void finish(const dd*) {}
+};
+int vec_sub(size_t n, double* out, const double* a, const double* b) { return launch_stream<0>(n, OpSub{out, a, b}, "vec"); }
+
+// ------------------------------------------------------------------------------------------
+// PCG
+// ------------------------------------------------------------------------------------------
+struct OpPcgSetup {
+    const double* r; const double* b; const double* d; double* p; SolverScalars* S; double* hist;
+    int pc; double omega;
+    __device__ bool begin() { pc = S->pc; omega = S->omega; return true; }
+    __device__ void elem(size_t i, dd* acc)
+    {
+        const double ri = r[i], bi = b[i];
+        const double z = precond(pc, omega, ri, d, i);
+        p[i] = z;
+        acc[0] = dd_add_prod(acc[0], ri, ri);
+        acc[1] = dd_add_prod(acc[1], bi, bi);
+        acc[2] = dd_add_prod(acc[2], z, ri);
+    }
+    __device__ void finish(const dd* acc)
+    {
+        double normb = sqrt(dd_round(acc[1]));                  // krylovsolver.h:130-133
+        if (normb == 0.0 || !S->relative) normb = 1.0;
+        const double resid = sqrt(dd_round(acc[0])) / normb;    // :129, :134
+        S->normb = normb; S->resid = resid; S->rr = dd_round(acc[0]);
+        S->rho = dd_round(acc[2]); S->rho_1 = 0.0;              // :144
+        S->iter = 0;
+        if (hist && S->hist_cap > 0) hist[0] = resid;
+        if (resid <= S->tol) { S->done = 1; S->converged = 1; } // :137-141
+        else if (S->max_iter <= 0) S->done = 1;
+    }
+};
+int pcg_setup(size_t n, const double* r, const double* b, const double* d, double* p, SolverScalars* S, double* hist)
+{
+    return launch_stream<3>(n, OpPcgSetup{r, b, d, p, S, hist, 0, 1.0}, "pcg.setup");
+}
+
+struct OpPcgUpdate {
+    double* x; double* r; const double* p; const double* q; const double* d; SolverScalars* S; double* hist;
+    double alpha; int pc; double omega;
+    __device__ bool begin()
+    {
+        if (S->done) return false;
+        alpha = dvd(S->rho, S->lambda);                         // :152
+        pc = S->pc; omega = S->omega;
+        return true;
+    }
+    __device__ void elem(size_t i, dd* acc)
+    {
+        x[i] = add(x[i], mul(alpha, p[i]));                     // :154
+        const double ri = add(r[i], mul(-alpha, q[i]));         // :155 (axpy(-alpha, q, r))
+        r[i] = ri;
+        const double z = precond(pc, omega, ri, d, i);          // :170
+        acc[0] = dd_add_prod(acc[0], ri, ri);                   // :158
+        acc[1] = dd_add_prod(acc[1], z, ri);                    // :172
+    }
+    __device__ void finish(const dd* acc)
+    {
+        const double rr = dd_round(acc[0]);
+        const double resid = sqrt(rr) / S->normb;
+        const int it = S->iter + 1;
+        S->iter = it; S->rr = rr; S->resid = resid;
+        S->rho_1 = S->rho; S->rho = dd_round(acc[1]);
+        if (hist && it < S->hist_cap) hist[it] = resid;
+        if (resid <= S->tol) { S->done = 1; S->converged = 1; } // :164-168
+        else if (it >= S->max_iter) S->done = 1;
+    }
+};
+int pcg_update(size_t n, double* x, double* r, const double* p, const double* q, const double* d,
+               SolverScalars* S, double* hist)
+{
+    return launch_stream<2>(n, OpPcgUpdate{x, r, p, q, d, S, hist, 0.0, 0, 1.0}, "pcg.update");
+}
+
+struct OpPcgDirection {
+    double* p; const double* r; const double* d; SolverScalars* S;
+    double beta; int pc; double omega;
+    __device__ bool begin()
+    {
+        if (S->done) return false;
+        beta = dvd(S->rho, S->rho_1);                           // :173
+        pc = S->pc; omega = S->omega;
+        return true;
+    }
+    __device__ void elem(size_t i, dd*)
+    {
+        const double z = precond(pc, omega, r[i], d, i);
+        p[i] = add(z, mul(beta, p[i]));                         // z_xpay(p, z, beta, p)
+    }
+    __device__ void finish(const dd*) {}
+};
+int pcg_direction(size_t n, double* p, const double* r, const double* d, SolverScalars* S)
+{
+    return launch_stream<0>(n, OpPcgDirection{p, r, d, S, 0.0, 0, 1.0}, "pcg.direction");
+}
+
+// ------------------------------------------------------------------------------------------
+// CG (sign convention of the reference: r = A x - b, d = -r)
+// ------------------------------------------------------------------------------------------
+struct OpCgSetup {
+    const double* r; const double* b; double* dv; SolverScalars* S; double* hist;
+    __device__ bool begin() { return true; }
+    __device__ void elem(size_t i, dd* acc)
+    {
+        const double ri = r[i], bi = b[i];
+        dv[i] = -ri;                                            // :65
+        acc[0] = dd_add_prod(acc[0], ri, ri);
+        acc[1] = dd_add_prod(acc[1], bi, bi);
+    }
+    __device__ void finish(const dd* acc)
+    {
+        double normb = sqrt(dd_round(acc[1]));                  // :62
+        if (normb == 0.0 || !S->relative) normb = 1.0;          // :67
+        const double rr = dd_round(acc[0]);                     // resid = Norm_sq :64
+        const double res = sqrt(rr) / normb;
+        S->normb = normb; S->rr = rr; S->resid = res; S->iter = 0;
+        if (hist && S->hist_cap > 0) hist[0] = sqrt(rr);
+        if (res <= S->tol) { S->done = 1; S->converged = 1; }   // :69-74
+        else if (S->max_iter <= 0) S->done = 1;
+    }
+};
+int cg_setup(size_t n, const double* r, const double* b, double* dvec, SolverScalars* S, double* hist)
+{
+    return launch_stream<2>(n, OpCgSetup{r, b, dvec, S, hist}, "cg.setup");
+}
+
+struct OpCgUpdate {
+    double* x; double* r; const double* dv; const double* Ad; SolverScalars* S; double* hist;
+    double alpha;
+    __device__ bool begin()
+    {
+        if (S->done) return false;
+        alpha = dvd(S->rr, S->lambda);                          // alpha = resid/delta :80
+        return true;
+    }
+    __device__ void elem(size_t i, dd* acc)
+    {
+        x[i] = add(x[i], mul(alpha, dv[i]));                    // :83
+        const double ri = add(r[i], mul(alpha, Ad[i]));         // :84
+        r[i] = ri;
+        acc[0] = dd_add_prod(acc[0], ri, ri);                   // :86
+    }
+    __device__ void finish(const dd* acc)
+    {
+        const double rr = dd_round(acc[0]);
+        const int it = S->iter + 1;
+        S->rho_1 = S->rr;                                       // beta = resid_new / resid_old :98
+        S->rr = rr; S->iter = it;
+        const double res = sqrt(rr) / S->normb;
+        S->resid = res;
+        if (hist && it < S->hist_cap) hist[it] = sqrt(rr);      // :88-90
+        if (res <= S->tol) { S->done = 1; S->converged = 1; }
+        else if (it >= S->max_iter) S->done = 1;
+    }
+};
+int cg_update(size_t n, double* x, double* r, const double* dvec, const double* Ad, SolverScalars* S, double* hist)
+{
+    return launch_stream<1>(n, OpCgUpdate{x, r, dvec, Ad, S, hist, 0.0}, "cg.update");
+}
+
+struct OpCgDirection {
+    double* dv; const double* r; SolverScalars* S; double beta;
+    __device__ bool begin()
+    {
+        if (S->done) return false;
+        beta = dvd(S->rr, S->rho_1);
+        return true;
+    }
+    __device__ void elem(size_t i, dd*) { dv[i] = sub(mul(beta, dv[i]), r[i]); }   // :99
+    __device__ void finish(const dd*) {}
+};
+int cg_direction(size_t n, double* dvec, const double* r, SolverScalars* S)
+{
+    return launch_stream<0>(n, OpCgDirection{dvec, r, S, 0.0}, "cg.direction");
+}
+
+// ------------------------------------------------------------------------------------------
+// GMRES pieces
+// ------------------------------------------------------------------------------------------
+struct OpScaleInv {
+    double* out; const double* in; const double* scale; double inv;
+    __device__ bool begin() { inv = dvd(1.0, *scale); return true; }
+    __device__ void elem(size_t i, dd*) { out[i] = mul(in[i], inv); }
+    __device__ void finish(const dd*) {}
+};
+int vec_scale_inv(size_t n, double* out, const double* in, const double* d_scale)
+{
+    return launch_stream<0>(n, OpScaleInv{out, in, d_scale, 0.0}, "vec");
+}
+
+template <bool PREV, bool NORM>
+struct OpMgs {
+    double* w; const double* vprev; const double* hprev; const double* vk; double* hout; double h;
+    __device__ bool begin() { h = PREV ? *hprev : 0.0; return true; }
+    __device__ void elem(size_t i, dd* acc)
+    {
+        double wi = w[i];
+        if (PREV) { wi = sub(wi, mul(h, vprev[i])); w[i] = wi; }   // w -= H(k,i)*v[k]  :380
+        acc[0] = NORM ? dd_add_prod(acc[0], wi, wi) : dd_add_prod(acc[0], wi, vk[i]);
+    }
+    __device__ void finish(const dd* acc) { *hout = NORM ? sqrt(dd_round(acc[0])) : dd_round(acc[0]); }
+};
+int mgs_step(size_t n, double* w, const double* vprev, const double* d_hprev, const double* vk,
+             double* d_hout, bool want_norm)
+{
+    if (vprev) {
+        if (want_norm) return launch_stream<1>(n, OpMgs<true, true>{w, vprev, d_hprev, vk, d_hout, 0.0}, "gmres.mgs");
+        return launch_stream<1>(n, OpMgs<true, false>{w, vprev, d_hprev, vk, d_hout, 0.0}, "gmres.mgs");
+    }
+    if (want_norm) return launch_stream<1>(n, OpMgs<false, true>{w, vprev, d_hprev, vk, d_hout, 0.0}, "gmres.mgs");
+    return launch_stream<1>(n, OpMgs<false, false>{w, vprev, d_hprev, vk, d_hout, 0.0}, "gmres.mgs");
+}
+
+struct OpMultiAxpy {
+    double* x; const double* const* v; const double* y; int k;
+    __device__ bool begin() { return true; }
+    __device__ void elem(size_t i, dd*)
+    {
+        double xi = x[i];
+        for (int j = 0; j < k; ++j) xi = add(xi, mul(y[j], v[j][i]));   // x += y[i]*v[i]  :295-296
+        x[i] = xi;
+    }
+    __device__ void finish(const dd*) {}
+};
+int multi_axpy(size_t n, double* x, const double* const* d_vptrs, const double* d_y, int k)
+{
+    return launch_stream<0>(n, OpMultiAxpy{x, d_vptrs, d_y, k}, "gmres.update");
+}
+
+// ------------------------------------------------------------------------------------------
+// MINRES pieces
+// ------------------------------------------------------------------------------------------
+struct OpLanczosOrth {
+    double* q2; const double* q1; const double* a1p; double* b1; double a1;
+    __device__ bool begin() { a1 = *a1p; return true; }
+    __device__ void elem(size_t i, dd* acc)
+    {
+        const double v = sub(q2[i], mul(a1, q1[i]));            // q2 -= a1*q1  :933
+        q2[i] = v;
+        acc[0] = dd_add_prod(acc[0], v, v);
+    }
+    __device__ void finish(const dd* acc) { *b1 = sqrt(dd_round(acc[0])); }   // :934
+};
+int lanczos_orth(size_t n, double* q2, const double* q1, const double* d_a1, double* d_b1)
+{
+    return launch_stream<1>(n, OpLanczosOrth{q2, q1, d_a1, d_b1, 0.0}, "minres.orth");
+}
+
+struct OpPLanczosOrth {
+    double* t2; const double* t1; const double* a1p; double* q2; int pc; double omega; const double* d;
+    double* b1sq; double a1;
+    __device__ bool begin() { a1 = *a1p; return true; }
+    __device__ void elem(size_t i, dd* acc)
+    {
+        const double t = sub(t2[i], mul(a1, t1[i]));            // t2 -= a1*t1     :1000
+        t2[i] = t;
+        const double q = precond(pc, omega, t, d, i);           // M.Apply(A,q2,t2) :1001
+        q2[i] = q;
+        acc[0] = dd_add_prod(acc[0], q, t);                     // dot(q2,t2)      :1002
+    }
+    __device__ void finish(const dd* acc) { *b1sq = dd_round(acc[0]); }
+};
+int planczos_orth(size_t n, double* t2, const double* t1, const double* d_a1, double* q2, int pc,
+                  double omega, const double* d, double* d_b1sq)
+{
+    return launch_stream<1>(n, OpPLanczosOrth{t2, t1, d_a1, q2, pc, omega, d, d_b1sq, 0.0}, "minres.orth");
+}
+
+struct OpDivScalar {
+    double* out; const double* in; double s; int mode;
+    __device__ bool begin() { if (mode) s = dvd(1., s); return true; }
+    __device__ void elem(size_t i, dd*) { out[i] = mode ? mul(in[i], s) : dvd(in[i], s); }
+    __device__ void finish(const dd*) {}
+};
+int vec_div_scalar(size_t n, double* out, const double* in, double s, int mode)
+{
+    return launch_stream<0>(n, OpDivScalar{out, in, s, mode}, "vec");
+}
+
+struct OpMinresUpdate {
+    int mode; const double* q; const double* pm2; const double* pm1; double* p0; double* x;
+    double r0, r1, r2, f, inv;
+    __device__ bool begin() { inv = dvd(1, r2); return true; }
+    __device__ void elem(size_t i, dd*)
+    {
+        double p;
+        if (mode == 1) p = dvd(q[i], r0);                                        // :1097
+        else if (mode == 2) p = dvd(sub(q[i], mul(r0, pm1[i])), r1);             // :1110
+        else p = mul(sub(sub(q[i], mul(r0, pm2[i])), mul(r1, pm1[i])), inv);     // :1124
+        p0[i] = p;
+        x[i] = add(x[i], mul(f, p));                                             // :1128-1129
+    }
+    __device__ void finish(const dd*) {}
+};
+int minres_update(size_t n, int mode, const double* q, const double* pm2, const double* pm1, double* p0,
+                  double* x, double r0, double r1, double r2, double f)
+{
+    return launch_stream<0>(n, OpMinresUpdate{mode, q, pm2, pm1, p0, x, r0, r1, r2, f, 0.0}, "minres.update");
+}
+
+}  // namespace db200
+
+// ------------------------------------------------------------------------------------------
+// C ABI: vectors
+// ------------------------------------------------------------------------------------------
+using namespace db200;
+
+static int fetch_scalar(const double* d_s, double* out)
+{
+    Ctx& c = ctx();
+    DB_CUDA(cudaMemcpyAsync(c.h_scalars, d_s, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    DB_CUDA(cudaStreamSynchronize(c.stream));
+    *out = c.h_scalars[0];
+    return 0;
+}
+
+extern "C" {
+
+int drops_b200_vector_create(size_t n, drops_b200_vector_t* out)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(out != nullptr, "null out");
+    drops_b200_vector_s* v = new drops_b200_vector_s;
+    v->n = n;
+    int s = dev_alloc(&v->d, n);
+    if (s < 0) { delete v; *out = nullptr; return s; }
+    cudaError_t e = cudaMemsetAsync(v->d, 0, (n ? n : 1) * sizeof(double), ctx().stream);
+    if (e != cudaSuccess) { dev_free(v->d); delete v; *out = nullptr; return cuda_fail(e, "memset", __FILE__, __LINE__); }
+    *out = v;
+    return 0;
+}
+
+int drops_b200_vector_destroy(drops_b200_vector_t v)
+{
+    if (!v) return 0;
+    if (ctx().inited) cudaStreamSynchronize(ctx().stream);
+    if (v->owns) dev_free(v->d);
+    delete v;
+    return 0;
+}
+
+int drops_b200_vector_size(drops_b200_vector_t v, size_t* n)
+{
+    DB_ARG(v != nullptr && n != nullptr, "null argument");
+    *n = v->n;
+    return 0;
+}
+
+int drops_b200_vector_upload(drops_b200_vector_t v, const double* host)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(v != nullptr && (host != nullptr || v->n == 0), "null argument");
+    if (v->n) DB_CUDA(cudaMemcpyAsync(v->d, host, v->n * sizeof(double), cudaMemcpyHostToDevice, ctx().stream));
+    DB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return 0;
+}
+
+int drops_b200_vector_download(drops_b200_vector_t v, double* host)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(v != nullptr && (host != nullptr || v->n == 0), "null argument");
+    if (v->n) DB_CUDA(cudaMemcpyAsync(host, v->d, v->n * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+    DB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return 0;
+}
+
+int drops_b200_vector_fill(drops_b200_vector_t v, double value)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(v != nullptr, "null vector");
+    return vec_fill(v->n, v->d, value);
+}
+
+int drops_b200_vector_fill_hash(drops_b200_vector_t v)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(v != nullptr, "null vector");
+    return vec_fill_hash(v->n, v->d);
+}
+
+int drops_b200_vector_copy(drops_b200_vector_t dst, drops_b200_vector_t src)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(dst != nullptr && src != nullptr && dst->n == src->n, "size mismatch");
+    return vec_copy(dst->n, dst->d, src->d);
+}
+
+int drops_b200_vector_ptr(drops_b200_vector_t v, double** dptr)
+{
+    DB_ARG(v != nullptr && dptr != nullptr, "null argument");
+    *dptr = v->d;
+    return 0;
+}
+
+int drops_b200_dot(drops_b200_vector_t x, drops_b200_vector_t y, double* result)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(x && y && result && x->n == y->n, "dot: incompatible dimensions");
+    DB_CHECK(vec_dot(x->n, x->d, y->d, ctx().scratch_scalars));
+    return fetch_scalar(ctx().scratch_scalars, result);
+}
+
+int drops_b200_norm_sq(drops_b200_vector_t x, double* result) { return drops_b200_dot(x, x, result); }
+
+int drops_b200_norm(drops_b200_vector_t x, double* result)
+{
+    double s = 0.0;
+    DB_CHECK(drops_b200_dot(x, x, &s));
+    *result = sqrt(s);
+    return 0;
+}
+
+int drops_b200_supnorm(drops_b200_vector_t x, double* result)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(x && result, "null argument");
+    DB_CHECK(vec_supnorm(x->n, x->d, ctx().scratch_scalars));
+    return fetch_scalar(ctx().scratch_scalars, result);
+}
+
+int drops_b200_axpy(double a, drops_b200_vector_t x, drops_b200_vector_t y)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(x && y && x->n == y->n, "axpy: incompatible dimensions");
+    return vec_axpy(x->n, a, x->d, y->d);
+}
+
+int drops_b200_z_xpay(drops_b200_vector_t z, drops_b200_vector_t x, double a, drops_b200_vector_t y)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(z && x && y && z->n == x->n && z->n == y->n, "z_xpay: incompatible dimensions");
+    return vec_z_xpay(z->n, z->d, x->d, a, y->d);
+}
+
+int drops_b200_z_xpaypby2(drops_b200_vector_t z, drops_b200_vector_t x, double a, drops_b200_vector_t y,
+                          double b, drops_b200_vector_t y2)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(z && x && y && y2 && z->n == x->n && z->n == y->n && z->n == y2->n, "z_xpaypby2: incompatible dimensions");
+    return vec_z_xpaypby2(z->n, z->d, x->d, a, y->d, b, y2->d);
+}
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+// vecops.cuh -- streaming vector kernels with fused deterministic reductions (vecops.cu).
+#pragma once
+#include "common.cuh"
+
+namespace db200 {
+
+// Device-side scalar block shared by the kernels of one solver run.  Everything a later kernel
+// needs (alpha, beta, stop flag) is produced on the device by the last block of an earlier
+// kernel, so an iteration needs no host round trip.
+struct SolverScalars {
+    double rho, rho_1, lambda, rr, resid, normb, tol, bb;
+    double a1, b1, b0;           // Lanczos coefficients
+    double h[2];                 // scratch
+    double omega;
+    int iter, done, converged, relative, max_iter, pc, hist_cap, pad;
+};
+
+// ---- standalone reductions / updates (C ABI: dot, norm, axpy, ...) ---------------------------
+int vec_dot(size_t n, const double* x, const double* y, double* d_out);          // d_out: device scalar
+int vec_supnorm(size_t n, const double* x, double* d_out);
+int vec_axpy(size_t n, double a, const double* x, double* y);                    // y += a*x
+int vec_z_xpay(size_t n, double* z, const double* x, double a, const double* y); // z = x + a*y
+int vec_z_xpaypby2(size_t n, double* z, const double* x, double a, const double* y, double b, const double* y2);
+int vec_jacobi(size_t n, double omega, const double* d, const double* b, double* x);  // x = (omega*b)/d
+int vec_fill(size_t n, double* x, double v);
+int vec_fill_hash(size_t n, double* x);
+int vec_copy(size_t n, double* dst, const double* src);
+
+// ---- PCG (num/krylovsolver.h:107-179) ------------------------------------------------------------
+// setup: given r = b - A x: normb, resid, hist[0], z = M^-1 r, rho = z.r, p = z; may set done.
+int pcg_setup(size_t n, const double* r, const double* b, const double* d, double* p,
+              SolverScalars* S, double* hist);
+// update: alpha = rho/lambda; x += alpha p; r -= alpha q; resid = |r|/normb; rho_1 = rho;
+//         rho = (M^-1 r).r; ++iter; hist[iter] = resid; done if resid <= tol or iter == max_iter.
+int pcg_update(size_t n, double* x, double* r, const double* p, const double* q, const double* d,
+               SolverScalars* S, double* hist);
+// direction: p = M^-1 r + (rho/rho_1) p
+int pcg_direction(size_t n, double* p, const double* r, const double* d, SolverScalars* S);
+
+// ---- CG (num/krylovsolver.h:49-103) --------------------------------------------------------------
+int cg_setup(size_t n, const double* r, const double* b, double* dvec, SolverScalars* S, double* hist);
+int cg_update(size_t n, double* x, double* r, const double* dvec, const double* Ad, SolverScalars* S, double* hist);
+int cg_direction(size_t n, double* dvec, const double* r, SolverScalars* S);
+
+// ---- GMRES building blocks (num/krylovsolver.h:320-461) -------------------------------------------
+// out = in * (1/(*d_scale))                                                      :366, :384
+int vec_scale_inv(size_t n, double* out, const double* in, const double* d_scale);
+// if vprev: w -= (*d_hprev) * vprev.  Then *d_hout = dot(w, vk) (vk != null) or |w|_2 (vk == null).
+int mgs_step(size_t n, double* w, const double* vprev, const double* d_hprev, const double* vk,
+             double* d_hout, bool want_norm);
+// x_e = (((x_e + y0 v0_e) + y1 v1_e) + ...) for k vectors; y on device.         :282-297
+int multi_axpy(size_t n, double* x, const double* const* d_vptrs, const double* d_y, int k);
+
+// ---- MINRES building blocks (num/krylovsolver.h:926-1152) ----------------------------------------
+// q2 -= (*d_a1) * q1;  *d_b1 = |q2|_2                                           :933-934
+int lanczos_orth(size_t n, double* q2, const double* q1, const double* d_a1, double* d_b1);
+// PLanczos: t2 -= a1*t1 (t1 may differ from the dot partner), then q2 = M^-1 t2, b1sq = q2.t2
+int planczos_orth(size_t n, double* t2, const double* t1, const double* d_a1, double* q2,
+                  int pc, double omega, const double* d, double* d_b1sq);
+// out = in / s (mode 0, :941, :965)  or  out = in * (1/s) (mode 1, :1005-1006); out may alias in
+int vec_div_scalar(size_t n, double* out, const double* in, double s, int mode);
+// p0 = (q - r0*pm2 - r1*pm1) {/ r2 | * (1/r2)};  x += f*p0                        :1090-1131
+// mode 1: p0 = q/r0c (k = 1);  mode 2: p0 = (q - r0*pm1)/r1 (k = 2);  mode 3: general.
+int minres_update(size_t n, int mode, const double* q, const double* pm2, const double* pm1, double* p0,
+                  double* x, double r0, double r1, double r2, double f);
+// r = b - t  style helpers
+int vec_sub(size_t n, double* out, const double* a, const double* b);            // out = a - b
+
+}  // namespace db200

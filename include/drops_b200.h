@@ -1,0 +1,206 @@
+/* drops_b200.h -- C ABI of the B200-native DROPS sparse-solver hot path.
+ *
+ * One process drives one GPU.  Plain pointers and sizes only; no C++ / torch types cross this
+ * boundary and no exception ever does: every entry point returns an int status
+ * (>= 0 success, < 0 one of DROPS_B200_E_*; drops_b200_last_error() has the text).
+ * There is no CPU fallback: without a usable sm_100 device every compute entry point fails with
+ * DROPS_B200_E_NODEVICE.
+ *
+ * The DROPS reference (56th/drops) has no FFI; its boundary for this path is the header-template
+ * interface of src/num/spmat.h, src/num/krylovsolver.h, src/num/precond.h, src/num/solverbase.h
+ * and src/parallel/exchange.h.  drops_b200/hostxx/ re-creates those headers on top of this ABI
+ * (see INTEGRATION.md); each entry point below names the reference interface it replaces
+ * (paths relative to the reference's src/).
+ *
+ * Layout conventions (same as the reference):
+ *   matrices : CSR, rowbeg[rows+1], colind[nnz] ascending inside a row, val[nnz]; the host entry
+ *              points take the reference's own types (size_t indices, double values;
+ *              SparseMatBaseCL::raw_row/raw_col/raw_val, num/spmat.h:789-794);
+ *   vectors  : contiguous double (VectorBaseCL::raw(), num/spmat.h:131-132).
+ */
+#ifndef DROPS_B200_H
+#define DROPS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#  define DROPS_B200_API __attribute__((visibility("default")))
+#else
+#  define DROPS_B200_API
+#endif
+
+/* ---- status codes ------------------------------------------------------------------------ */
+#define DROPS_B200_OK            0
+#define DROPS_B200_E_ARG        -1   /* bad argument (null handle, size mismatch, ...)           */
+#define DROPS_B200_E_CUDA       -2   /* CUDA runtime error (text in drops_b200_last_error)      */
+#define DROPS_B200_E_NODEVICE   -3   /* no CUDA device / not sm_100: the product has no CPU path*/
+#define DROPS_B200_E_NOTINIT    -4   /* drops_b200_init has not been called                     */
+#define DROPS_B200_E_NODIAG     -5   /* Jacobi needs a stored diagonal entry in every row       */
+#define DROPS_B200_E_RANGE      -6   /* index does not fit the device index type                */
+#define DROPS_B200_E_COMM       -7   /* NCCL error                                              */
+#define DROPS_B200_E_NOMEM      -8   /* device or host allocation failed                        */
+
+/* preconditioner selector: the PC template argument of the reference solvers */
+#define DROPS_B200_PC_DUMMY      0   /* DummyPcCL, num/precond.h:1032-1065: x = b               */
+#define DROPS_B200_PC_JACOBI     1   /* JACPcCL,   num/precond.h:874 / :1155-1188: x = omega*b/a_ii */
+
+typedef struct drops_b200_matrix_s* drops_b200_matrix_t;
+typedef struct drops_b200_vector_s* drops_b200_vector_t;
+
+/* ---- process-wide context ---------------------------------------------------------------- */
+/* Bind this process to CUDA device `device` (cudaSetDevice), create the solver stream and the
+ * reduction workspace.  Idempotent for the same device. */
+DROPS_B200_API int drops_b200_init(int device);
+DROPS_B200_API int drops_b200_shutdown(void);
+DROPS_B200_API const char* drops_b200_last_error(void);
+/* Library/ABI version and the sm architecture the kernels were compiled for (100). */
+DROPS_B200_API int drops_b200_abi_version(void);
+DROPS_B200_API int drops_b200_compiled_arch(void);
+/* Device facts: sm count, compute capability major*10+minor, free/total bytes. */
+DROPS_B200_API int drops_b200_device_info(int* sm_count, int* cc, size_t* free_bytes, size_t* total_bytes);
+/* Tunables (documented in DESIGN.md): "spmv.kernel", "spmv.threads", "spmv.ctas_per_sm",
+ * "spmv.exact", "sell.sigma", "pcg.check_every", "pcg.graph", "timing". */
+DROPS_B200_API int drops_b200_set_option(const char* key, double value);
+DROPS_B200_API int drops_b200_get_option(const char* key, double* value);
+/* Accumulated CUDA-event time (ms) and launch count of a named kernel class since the last
+ * reset; only collected while option "timing" is 1.  Keys: "spmv", "pcg.update", "pcg.direction",
+ * "vec", ... */
+DROPS_B200_API int drops_b200_timing_get(const char* key, double* ms, long long* launches);
+DROPS_B200_API int drops_b200_timing_reset(void);
+/* Device stopwatch: CUDA events recorded on the solver stream.  timer_stop synchronises and
+ * returns the milliseconds since the matching timer_start (what bench.py reports). */
+DROPS_B200_API int drops_b200_timer_start(void);
+DROPS_B200_API int drops_b200_timer_stop(double* ms);
+/* Number of kernels this library launched since init (all streams). */
+DROPS_B200_API long long drops_b200_launch_count(void);
+DROPS_B200_API int drops_b200_synchronize(void);
+
+/* ---- matrices: SparseMatBaseCL<double>, num/spmat.h:682-879 -------------------------------- */
+/* Copies a host CSR matrix in the reference layout to the device: narrows colind to int32,
+ * extracts the diagonal (GetDiag, num/spmat.h:993-1002), builds the sliced-ELL operator.
+ * `version` is SparseMatBaseCL::Version() (num/spmat.h:807-808); the hostxx layer keys its
+ * handle cache on (address, version). */
+DROPS_B200_API int drops_b200_matrix_create(size_t rows, size_t cols, size_t nnz,
+                                            const size_t* rowbeg, const size_t* colind,
+                                            const double* val, uint64_t version,
+                                            drops_b200_matrix_t* out);
+/* Same, from CSR arrays already resident on this device (int64 row pointers, int32 columns).
+ * The arrays are consumed (copied or adopted) before the call returns. */
+DROPS_B200_API int drops_b200_matrix_create_device(size_t rows, size_t cols, size_t nnz,
+                                                   const int64_t* d_rowptr, const int32_t* d_colind,
+                                                   const double* d_val, uint64_t version,
+                                                   drops_b200_matrix_t* out);
+/* New values on the unchanged pattern (operator*=, LinComb results with equal pattern). */
+DROPS_B200_API int drops_b200_matrix_update_values(drops_b200_matrix_t A, const double* val, uint64_t version);
+DROPS_B200_API int drops_b200_matrix_destroy(drops_b200_matrix_t A);
+DROPS_B200_API int drops_b200_matrix_info(drops_b200_matrix_t A, size_t* rows, size_t* cols, size_t* nnz,
+                                          uint64_t* version, size_t* device_bytes, size_t* padded_nnz);
+/* Copies the device CSR back in the reference layout (for tests and the CPU baseline). */
+DROPS_B200_API int drops_b200_matrix_download(drops_b200_matrix_t A, size_t* rowbeg, size_t* colind, double* val);
+
+/* y = A*x      : operator*(SparseMatBaseCL, VectorBaseCL), num/spmat.h:1712-1724 (y_Ax :1682-1709).
+ * y = A^T*x    : transp_mul, num/spmat.h:1748-1760 (y_ATx :1729-1746).
+ * Host buffers; the copies are part of the call.  x has cols (rows) entries, y rows (cols). */
+DROPS_B200_API int drops_b200_spmv(drops_b200_matrix_t A, const double* x, double* y);
+DROPS_B200_API int drops_b200_spmv_transpose(drops_b200_matrix_t A, const double* x, double* y);
+/* A.GetDiag(), num/spmat.h:993-1002. */
+DROPS_B200_API int drops_b200_matrix_diag(drops_b200_matrix_t A, double* diag);
+
+/* ---- device-resident vectors: VectorBaseCL<double>, num/spmat.h:82-145 ---------------------- */
+DROPS_B200_API int drops_b200_vector_create(size_t n, drops_b200_vector_t* out);
+DROPS_B200_API int drops_b200_vector_destroy(drops_b200_vector_t v);
+DROPS_B200_API int drops_b200_vector_size(drops_b200_vector_t v, size_t* n);
+DROPS_B200_API int drops_b200_vector_upload(drops_b200_vector_t v, const double* host);
+DROPS_B200_API int drops_b200_vector_download(drops_b200_vector_t v, double* host);
+DROPS_B200_API int drops_b200_vector_fill(drops_b200_vector_t v, double value);
+DROPS_B200_API int drops_b200_vector_copy(drops_b200_vector_t dst, drops_b200_vector_t src);
+/* x_i = ((i*2654435761) mod 2^32)/2^32 - 0.5: the seedless SpMV input of SURVEY.md section 8(d). */
+DROPS_B200_API int drops_b200_vector_fill_hash(drops_b200_vector_t v);
+/* Raw device pointer (for callers that own CUDA code themselves). */
+DROPS_B200_API int drops_b200_vector_ptr(drops_b200_vector_t v, double** dptr);
+
+DROPS_B200_API int drops_b200_spmv_dev(drops_b200_matrix_t A, drops_b200_vector_t x, drops_b200_vector_t y);
+DROPS_B200_API int drops_b200_spmv_transpose_dev(drops_b200_matrix_t A, drops_b200_vector_t x, drops_b200_vector_t y);
+
+/* dot (num/spmat.h:164-170), norm_sq/norm (:180-196), supnorm (:198-210): one deterministic
+ * double-double tree reduction; DummyExchangeCL::ParDot/Norm (parallel/exchange.h:58-84, Kahan)
+ * map to the same kernels (error <= the reference's). */
+DROPS_B200_API int drops_b200_dot(drops_b200_vector_t x, drops_b200_vector_t y, double* result);
+DROPS_B200_API int drops_b200_norm_sq(drops_b200_vector_t x, double* result);
+DROPS_B200_API int drops_b200_norm(drops_b200_vector_t x, double* result);
+DROPS_B200_API int drops_b200_supnorm(drops_b200_vector_t x, double* result);
+/* axpy: y += a*x (num/spmat.h:212-218); z_xpay: z = x + a*y (:220-227);
+ * z_xpaypby2: z = x + a*y + b*y2 (:229-237).  Products are rounded before the add (no FMA),
+ * like the reference's valarray expressions. */
+DROPS_B200_API int drops_b200_axpy(double a, drops_b200_vector_t x, drops_b200_vector_t y);
+DROPS_B200_API int drops_b200_z_xpay(drops_b200_vector_t z, drops_b200_vector_t x, double a, drops_b200_vector_t y);
+DROPS_B200_API int drops_b200_z_xpaypby2(drops_b200_vector_t z, drops_b200_vector_t x, double a,
+                                         drops_b200_vector_t y, double b, drops_b200_vector_t y2);
+/* JACPcCL::Apply: x_i = omega*b_i/a_ii (num/precond.h:153-169, :1293-1311). */
+DROPS_B200_API int drops_b200_jacobi_apply(drops_b200_matrix_t A, double omega,
+                                           drops_b200_vector_t b, drops_b200_vector_t x);
+
+/* ---- Krylov solvers ------------------------------------------------------------------------
+ * Common contract (num/krylovsolver.h:50-59): x is in/out (initial guess -> solution), b is
+ * const; *max_iter IN: iteration limit, OUT: iterations used (unchanged when not converged);
+ * *tol IN: tolerance, OUT: final residual (relative iff `relative`).  Return value: 1 converged,
+ * 0 not converged within *max_iter, < 0 error.  hist (may be NULL) receives the residual the
+ * reference would print through SolverBaseCL::output_ after each iteration, hist[0] = initial.
+ *
+ * pcg    : PCG, num/krylovsolver.h:107-179 (PCGSolverCL<PC>::Solve :1818-1824) with
+ *          DummyExchangeCL; pc = DROPS_B200_PC_JACOBI gives PCGSolverCL<JACPcCL>.
+ * cg     : CG, :49-103 (CGSolverCL :1782-1802).
+ * gmres  : serial GMRES(m), :320-461 (GMResSolverCL<PC>::Solve :1946-1958), modified
+ *          Gram-Schmidt; left_precond = 1 is the driver's default (:1937).
+ * minres : MINRES :1155-1161 / PMINRES :1069-1152 (MResSolverCL :1868-1889); precond = 1 runs
+ *          the preconditioned Lanczos basis (PLanczosONBCL :1010-1052) with `pc`.
+ * Host-buffer forms copy x,b in and x out inside the call; *_dev forms work on device vectors. */
+DROPS_B200_API int drops_b200_pcg(drops_b200_matrix_t A, double* x, const double* b, int pc, double omega,
+                                  int* max_iter, double* tol, int relative, double* hist, int hist_cap);
+DROPS_B200_API int drops_b200_pcg_dev(drops_b200_matrix_t A, drops_b200_vector_t x, drops_b200_vector_t b,
+                                      int pc, double omega, int* max_iter, double* tol, int relative,
+                                      double* hist, int hist_cap);
+DROPS_B200_API int drops_b200_cg(drops_b200_matrix_t A, double* x, const double* b,
+                                 int* max_iter, double* tol, int relative, double* hist, int hist_cap);
+DROPS_B200_API int drops_b200_cg_dev(drops_b200_matrix_t A, drops_b200_vector_t x, drops_b200_vector_t b,
+                                     int* max_iter, double* tol, int relative, double* hist, int hist_cap);
+DROPS_B200_API int drops_b200_gmres(drops_b200_matrix_t A, double* x, const double* b, int pc, double omega,
+                                    int restart, int* max_iter, double* tol, int relative, int left_precond);
+DROPS_B200_API int drops_b200_gmres_dev(drops_b200_matrix_t A, drops_b200_vector_t x, drops_b200_vector_t b,
+                                        int pc, double omega, int restart, int* max_iter, double* tol,
+                                        int relative, int left_precond);
+DROPS_B200_API int drops_b200_minres(drops_b200_matrix_t A, double* x, const double* b, int precond, int pc,
+                                     double omega, int* max_iter, double* tol, int relative);
+DROPS_B200_API int drops_b200_minres_dev(drops_b200_matrix_t A, drops_b200_vector_t x, drops_b200_vector_t b,
+                                         int precond, int pc, double omega, int* max_iter, double* tol,
+                                         int relative);
+
+/* ---- synthetic brick systems ---------------------------------------
+ * Uniform Kuhn brick (BrickBuilderCL, geom/builder.cpp:99-180: 6 tetrahedra per cell sharing the
+ * main diagonal) on the unit cube with N cells per direction, homogeneous Dirichlet on all faces,
+ * alpha = 1.  fe = 1: P1 stiffness (poisson/poissonaccus.tpp:327), n = (N-1)^3, 15 stored
+ * couplings per interior row.  fe = 2: P2 stiffness (poisson/poisson.tpp:828-838, :898-917),
+ * n = (2N-1)^3, 65/27/27/19 stored couplings per interior row.  All couplings of DOFs sharing a
+ * tetrahedron are stored, numerically zero or not (poisson.tpp:912-917).
+ * numbering = 0: lexicographic over the DOF lattice; 1: vertices first, then edges
+ * (misc/problem.cpp:707-719).  upper_scale != 1 multiplies the strict upper triangle (the
+ * nonsymmetric GMRES stand-in).  z-slab [z0, z1) of lattice planes restricts the generated rows
+ * (multi-GPU); z0 = z1 = 0 means all rows. */
+DROPS_B200_API int drops_b200_brick_sizes(int fe, int N, size_t* n, size_t* nnz);
+DROPS_B200_API int drops_b200_brick_csr_host(int fe, int N, int numbering, double upper_scale,
+                                             size_t* rowbeg, size_t* colind, double* val);
+DROPS_B200_API int drops_b200_brick_matrix_device(int fe, int N, int numbering, double upper_scale,
+                                                  drops_b200_matrix_t* out);
+/* x*(p) = 64 xyz(1-x)(1-y)(1-z) sampled at the DOF positions (poissonsolverfactory.h:25-26). */
+DROPS_B200_API int drops_b200_brick_solution_host(int fe, int N, int numbering, double* xstar);
+DROPS_B200_API int drops_b200_brick_solution_device(int fe, int N, int numbering, drops_b200_vector_t xstar);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DROPS_B200_H */

@@ -1,0 +1,367 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against
+  * the golden fixtures produced by the compiled reference (tests/golden, oracle/make_golden.py),
+  * the oracle (oracle/drops_oracle.c) on seeded brick systems it finishes in seconds,
+  * size-independent properties at BASELINE.json's full size (C2: P2, N=185, 50.2 M rows).
+Tolerances (BASELINE.json north_star): SpMV 1e-14 relative per entry -- measured against
+(|A||x|)_i, and in the default exact mode the result is required to be BIT-IDENTICAL; Krylov
+iteration counts within +-1; solutions within 1e-10 relative.
+"""
+import numpy as np
+import pytest
+
+from conftest import absAx, golden_files, hash_vector, load_golden
+
+pytestmark = pytest.mark.gpu
+
+X_RTOL = 1e-10      # final solutions, relative 2-norm
+SPMV_RTOL = 1e-14   # per entry, relative to (|A||x|)_i
+
+
+def gmat(gpu, g):
+    return gpu.Matrix(int(g["rows"]), int(g["cols"]), g["rowbeg"], g["colind"], g["val"])
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+# ---------------------------------------------------------------------------------------------
+# SpMV, transpose, diagonal, Jacobi against the reference's outputs
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", golden_files("brick_*.npz") + golden_files("random_*.npz"),
+                         ids=lambda p: p.split("/")[-1][:-4])
+def test_spmv_bit_identical_to_reference(gpu, path):
+    g = dict(np.load(path))
+    A = gmat(gpu, g)
+    assert np.array_equal(A.spmv(g["x_in"]), g["y_Ax"])
+    xt = g["xt_in"] if "xt_in" in g else g["x_in"]
+    assert np.array_equal(A.spmv_transpose(xt), g["y_ATx"])
+    if "diag" in g:
+        assert np.array_equal(A.diag(), g["diag"])
+    if "jac_w07" in g:
+        assert np.array_equal(A.jacobi_apply(g["x_in"], 0.7), g["jac_w07"])
+        assert np.array_equal(A.jacobi_apply(g["x_in"], 1.0), g["jac_w1"])
+    rb, ci, va = A.download()
+    assert np.array_equal(rb, g["rowbeg"]) and np.array_equal(ci, g["colind"]) and np.array_equal(va, g["val"])
+
+
+@pytest.mark.parametrize("kernel,lanes,exact", [(0, 0, 0), (1, 2, 0), (1, 8, 0), (1, 32, 0)])
+def test_spmv_fast_modes_within_tolerance(gpu, kernel, lanes, exact):
+    """FMA / tree-summed variants: |y - y_ref|_i <= 1e-14 (|A||x|)_i."""
+    try:
+        gpu.set_option("spmv.kernel", kernel)
+        gpu.set_option("spmv.lanes", lanes or 8)
+        gpu.set_option("spmv.exact", exact)
+        for path in golden_files("brick_fe2_N6*.npz") + golden_files("random_ragged.npz"):
+            g = dict(np.load(path))
+            A = gmat(gpu, g)
+            y = A.spmv(g["x_in"])
+            scale = absAx(g["rowbeg"], g["colind"], g["val"], g["x_in"], int(g["rows"]))
+            assert np.all(np.abs(y - g["y_Ax"]) <= SPMV_RTOL * scale + 1e-300)
+    finally:
+        gpu.set_option("spmv.kernel", 0)
+        gpu.set_option("spmv.exact", 1)
+
+
+@pytest.mark.parametrize("sigma,threads,ctas", [(0, 64, 1), (64, 128, 0.25), (512, 1024, 2), (4096, 256, 64)])
+def test_spmv_layout_and_launch_options_do_not_change_results(gpu, sigma, threads, ctas):
+    g = load_golden("brick_fe2_N6_num1.npz")
+    try:
+        gpu.set_option("sell.sigma", sigma)
+        gpu.set_option("spmv.threads", threads)
+        gpu.set_option("spmv.ctas_per_sm", ctas)
+        A = gmat(gpu, g)
+        assert np.array_equal(A.spmv(g["x_in"]), g["y_Ax"])
+        assert np.array_equal(A.spmv_transpose(g["x_in"]), g["y_ATx"])
+    finally:
+        gpu.set_option("sell.sigma", 4096)
+        gpu.set_option("spmv.threads", 512)
+        gpu.set_option("spmv.ctas_per_sm", 4)
+
+
+def test_reference_kats_on_gpu(gpu):
+    """src/tests/minres.cpp + TestMinres.ref and src/tests/blockmat.cpp + Testblockmat.ref."""
+    g = load_golden("reference_kats.npz")
+    A2 = gpu.Matrix(2, 2, [0, 1, 2], [1, 0], [1., 1.])
+    conv, it, res, x = A2.minres(np.zeros(2), np.array([1., 2.]), 10, 1e-10)
+    assert conv and it == int(g["test2"][1]) and np.allclose(x, [2., 1.], atol=1e-12) and abs(res - 4.213e-16) < 1e-10
+    A4 = gpu.Matrix(4, 4, g["A4_rowbeg"], g["A4_colind"], g["A4_val"])
+    conv, it, res, x = A4.minres(np.zeros(4), g["b4"], 10, 1e-10)
+    assert conv and it == int(g["test3"][1]) and np.allclose(x, [0.25, 0.5, 0.75, 1.0], atol=1e-9)
+    assert abs(res - 2.87588e-11) < 1e-10                      # TestMinres.ref "Residual3"
+    conv, it, res, x = A4.pminres_dummy(np.zeros(4), g["b4"], 10, 1e-10)
+    assert conv and it == int(g["test5"][1]) and np.allclose(x, [0.25, 0.5, 0.75, 1.0], atol=1e-9)
+    assert abs(res - 2.87596e-11) < 1e-10                      # "Residual5"
+    B = gpu.Matrix(1, 2, [0, 2], [0, 1], [1., 1.])
+    assert np.array_equal(B.spmv_transpose(np.array([3.])), [3., 3.])   # transp_mul( B, b2): 3 3
+    b = np.array([1., 2., 3.])
+    Sb = np.concatenate([A2.spmv(b[:2]) + B.spmv_transpose(b[2:]), B.spmv(b[:2])])
+    assert np.array_equal(Sb, g["block_Sb"]) and np.array_equal(Sb, [5., 4., 3.])
+
+
+# ---------------------------------------------------------------------------------------------
+# vector kernels
+# ---------------------------------------------------------------------------------------------
+def test_vector_kernels_against_reference(gpu):
+    g = load_golden("vectors.npz")
+    x, y, y2 = gpu.Vector.from_host(g["x"]), gpu.Vector.from_host(g["y"]), gpu.Vector.from_host(g["y2"])
+    z = gpu.Vector(x.n)
+    # elementwise updates: bit-identical to the reference's valarray expressions
+    gpu.z_xpay(z, x, -1.25, y)
+    assert np.array_equal(z.download(), g["z_xpay"])
+    gpu.z_xpaypby2(z, x, 0.5, y, -3.0, y2)
+    assert np.array_equal(z.download(), g["z_xpaypby2"])
+    z.copy_from(y)
+    gpu.axpy(0.37, x, z)
+    assert np.array_equal(z.download(), g["axpy"])
+    # reductions: double-double tree, compared with the exactly rounded value and with the
+    # reference's Kahan sum; the tolerance is a few ulp of sum|x_i y_i|
+    import math
+    exact = math.fsum((g["x"] * g["y"]).tolist())
+    scale = float(np.abs(g["x"] * g["y"]).sum())
+    d = gpu.dot(x, y)
+    assert abs(d - exact) <= 4e-16 * scale
+    assert abs(d - float(g["kahan_dot"])) <= 4e-16 * scale
+    assert abs(gpu.norm(x) - float(g["kahan_norm"])) <= 4e-16 * float(g["kahan_norm"])
+    assert abs(gpu.norm_sq(x) - float(g["norm_sq"])) <= 1e-13 * float(g["norm_sq"])   # reference: plain sum
+    assert gpu.supnorm(x) == float(g["supnorm"])
+    h = gpu.Vector(1000)
+    h.fill_hash()
+    assert np.array_equal(h.download(), hash_vector(1000))
+
+
+def test_reductions_are_deterministic(gpu):
+    rng = np.random.default_rng(3)
+    a, b = rng.standard_normal(1 << 20), rng.standard_normal(1 << 20)
+    x, y = gpu.Vector.from_host(a), gpu.Vector.from_host(b)
+    vals = {gpu.dot(x, y) for _ in range(5)}
+    assert len(vals) == 1
+
+
+# ---------------------------------------------------------------------------------------------
+# Krylov solvers against the reference's outputs
+# ---------------------------------------------------------------------------------------------
+def check_solve(out, g, key, x_rtol=X_RTOL, res_rtol=1e-6):
+    conv, it, res = bool(g[key][0]), int(g[key][1]), float(g[key][2])
+    assert out[0] == conv, key
+    assert abs(out[1] - it) <= 1, (key, out[1], it)
+    if out[1] == it:
+        assert abs(out[2] - res) <= res_rtol * abs(res) + 1e-300, (key, out[2], res)
+        assert rel(out[3], g[key + "_x"]) <= x_rtol, (key, rel(out[3], g[key + "_x"]))
+
+
+@pytest.mark.parametrize("path", golden_files("brick_*.npz") + golden_files("random_spd*.npz"),
+                         ids=lambda p: p.split("/")[-1][:-4])
+def test_solvers_against_reference(gpu, path):
+    g = dict(np.load(path))
+    A = gmat(gpu, g)
+    b, x0 = g["b"], np.zeros(int(g["rows"]))
+    tag = "nonsym" if "nonsym" in path else "sym"
+    if tag == "sym":
+        out = A.pcg_jacobi(x0, b, 400, 1e-10, True, 1.0, hist=True)
+        check_solve(out, g, "sym_pcgjac")
+        it = min(out[1], int(g["sym_pcgjac"][1]))
+        ref_hist = g["sym_pcgjac_hist"]
+        assert np.allclose(out[4][1:it + 1], ref_hist[1:it + 1], rtol=1e-6, atol=0)
+        check_solve(A.pcg_jacobi(x0, b, 400, 1e-10, False, 0.8), g, "sym_pcgjac_w08")
+        check_solve(A.pcg_dummy(x0, b, 400, 1e-10, True), g, "sym_pcgdummy")
+        out = A.cg(x0, b, 400, 1e-10, True, hist=True)
+        check_solve(out, g, "sym_cg")
+        it = min(out[1], int(g["sym_cg"][1]))
+        assert np.allclose(out[4][1:it + 1], g["sym_cg_hist"][1:it + 1], rtol=1e-6, atol=0)
+        check_solve(A.minres(x0, b, 400, 1e-9), g, "sym_minres", x_rtol=1e-8)
+        check_solve(A.pminres_jacobi(x0, b, 400, 1e-9), g, "sym_pminresjac", x_rtol=1e-8)
+        # fixed work: exactly 7 iterations, not converged, max_iter left untouched
+        out = A.pcg_jacobi(x0, b, 7, 0.0, True, 1.0)
+        assert out[0] is False and out[1] == 7
+        assert abs(out[2] - g["sym_pcgjac_fixed7"][2]) <= 1e-9 * g["sym_pcgjac_fixed7"][2]
+        assert rel(out[3], g["sym_pcgjac_fixed7_x"]) <= 1e-12
+    check_solve(A.gmres_jacobi(x0, b, 20, 400, 1e-10, True, 1.0, True), g, f"{tag}_gmresjac_l1")
+    check_solve(A.gmres_jacobi(x0, b, 20, 400, 1e-10, True, 1.0, False), g, f"{tag}_gmresjac_l0")
+    check_solve(A.gmres_jacobi(x0, b, 5, 400, 1e-10, True, 1.0, True), g, f"{tag}_gmresjac_m5", x_rtol=1e-8)
+    check_solve(A.gmres_dummy(x0, b, 20, 400, 1e-10, False, True), g, f"{tag}_gmresdummy")
+
+
+def test_solver_edge_cases(gpu):
+    g = load_golden("brick_fe2_N4_num0.npz")
+    A = gmat(gpu, g)
+    n = A.rows
+    b = g["b"]
+    # zero right-hand side: normb == 0 -> 1 (krylovsolver.h:132), converged at iteration 0
+    conv, it, res, x = A.pcg_jacobi(np.zeros(n), np.zeros(n), 50, 1e-10, True)
+    assert conv and it == 0 and res == 0.0 and not x.any()
+    # exact initial guess
+    conv, it, res, x = A.pcg_jacobi(g["xstar"], b, 50, 1e-8, True)
+    assert conv and it == 0
+    # max_iter = 0: not converged, max_iter untouched, x untouched
+    conv, it, res, x = A.pcg_jacobi(np.zeros(n), b, 0, 1e-10, True)
+    assert not conv and it == 0 and not x.any()
+    # check_every = 1 and a chunk size that does not divide the iteration count
+    for ce in (1, 5):
+        gpu.set_option("pcg.check_every", ce)
+        out = A.pcg_jacobi(np.zeros(n), b, 400, 1e-10, True)
+        assert out[0] and out[1] == int(g["sym_pcgjac"][1])
+        assert rel(out[3], g["sym_pcgjac_x"]) <= 1e-12
+    gpu.set_option("pcg.check_every", 16)
+    # device-resident entry points give the same answer as the host-buffer ones
+    xv, bv = gpu.Vector(n), gpu.Vector.from_host(b)
+    conv, it, res = A.pcg_dev(xv, bv, 400, 1e-10, True)
+    assert conv and it == int(g["sym_pcgjac"][1]) and rel(xv.download(), g["sym_pcgjac_x"]) <= 1e-12
+    # 1x1 system
+    A1 = gpu.Matrix(1, 1, [0, 1], [0], [4.0])
+    conv, it, res, x = A1.pcg_jacobi(np.zeros(1), np.array([2.0]), 5, 1e-12, False)
+    assert conv and it == 1 and x[0] == 0.5
+    # a matrix with a missing diagonal entry: Jacobi refuses loudly (the reference reads past the row)
+    Z = gpu.Matrix(2, 2, [0, 1, 2], [1, 0], [1., 1.])
+    with pytest.raises(gpu.DropsB200Error) as ei:
+        Z.pcg_jacobi(np.zeros(2), np.ones(2), 5, 1e-10)
+    assert ei.value.code == -5
+    # dimension checks
+    with pytest.raises(gpu.DropsB200Error):
+        A.spmv_dev(gpu.Vector(n + 1), gpu.Vector(n))
+    # an empty matrix and rows without entries
+    E = gpu.Matrix(3, 3, [0, 0, 0, 0], [], [])
+    assert np.array_equal(E.spmv(np.ones(3)), np.zeros(3))
+    assert np.array_equal(E.spmv_transpose(np.ones(3)), np.zeros(3))
+
+
+def test_matrix_value_update_tracks_version(gpu):
+    g = load_golden("brick_fe2_N4_num1.npz")
+    A = gmat(gpu, g)
+    assert A.info()["version"] == 1
+    y1 = A.spmv(g["x_in"])
+    A.update_values(2.0 * g["val"], 2)           # SparseMatBaseCL::operator*=  bumps Version()
+    assert A.info()["version"] == 2
+    assert np.array_equal(A.spmv(g["x_in"]), 2.0 * y1)
+    assert np.array_equal(A.spmv_transpose(g["x_in"]), 2.0 * g["y_ATx"])
+    assert np.array_equal(A.diag(), 2.0 * g["diag"])
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle-sized brick systems, checked live against oracle/drops_oracle.c
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fe,N,numbering", [(1, 24, 0), (2, 16, 1), (2, 32, 1), (2, 32, 0)])
+def test_brick_parity_with_oracle(gpu, port, fe, N, numbering):
+    n, rb, ci, va = gpu.brick_csr_host(fe, N, numbering)
+    P = port.PortMatrix(n, n, rb, ci, va)
+    # device generator == host generator, bit for bit
+    G = gpu.Matrix.brick(fe, N, numbering)
+    rb2, ci2, va2 = G.download()
+    assert np.array_equal(rb2, rb) and np.array_equal(ci2, ci) and np.array_equal(va2, va)
+    xs = gpu.brick_solution_host(fe, N, numbering)
+    xv = gpu.Vector(n)
+    gpu.brick_solution_device(fe, N, numbering, xv)
+    assert np.array_equal(xv.download(), xs)
+    # SpMV: bit-identical
+    xin = hash_vector(n)
+    assert np.array_equal(G.spmv(xin), P.spmv(xin))
+    assert np.array_equal(G.spmv_transpose(xin), P.spmv_transpose(xin))
+    # PCG-Jacobi to convergence: iteration count +-1, solution 1e-10
+    b = P.spmv(xs)
+    ref = P.pcg_jacobi(np.zeros(n), b, 2000, 1e-10, True, hist=True)
+    out = G.pcg_jacobi(np.zeros(n), b, 2000, 1e-10, True, hist=True)
+    assert ref[0] and out[0]
+    assert abs(out[1] - ref[1]) <= 1, (out[1], ref[1])
+    assert rel(out[3], ref[3]) <= X_RTOL
+    assert rel(out[3], xs) <= 1e-8
+    it = min(out[1], ref[1])
+    assert np.allclose(out[4][:it + 1], ref[4][:it + 1], rtol=1e-5, atol=0)
+    if N <= 16:
+        r = P.gmres_jacobi(np.zeros(n), b, 30, 1000, 1e-9, True)
+        o = G.gmres_jacobi(np.zeros(n), b, 30, 1000, 1e-9, True)
+        assert r[0] and o[0] and abs(o[1] - r[1]) <= 1 and rel(o[3], r[3]) <= 1e-8
+        r = P.minres(np.zeros(n), b, 1000, 1e-8)
+        o = G.minres(np.zeros(n), b, 1000, 1e-8)
+        assert r[0] and o[0] and abs(o[1] - r[1]) <= 1 and rel(o[3], r[3]) <= 1e-7
+
+
+def test_nonsymmetric_gmres_parity_with_oracle(gpu, port):
+    """C3 stand-in (level-set advection system): P2 pattern, nonsymmetric values, GMRES(30)+Jacobi."""
+    n, rb, ci, va = gpu.brick_csr_host(2, 12, 1, 1.1)
+    P = port.PortMatrix(n, n, rb, ci, va)
+    G = gpu.Matrix(n, n, rb, ci, va)
+    xs = gpu.brick_solution_host(2, 12, 1)
+    b = P.spmv(xs)
+    for left in (True, False):
+        r = P.gmres_jacobi(np.zeros(n), b, 30, 2000, 1e-9, True, 1.0, left)
+        o = G.gmres_jacobi(np.zeros(n), b, 30, 2000, 1e-9, True, 1.0, left)
+        assert r[0] and o[0]
+        assert abs(o[1] - r[1]) <= 1, (o[1], r[1])
+        assert rel(o[3], r[3]) <= 1e-8
+
+
+def test_irregular_interface_system_parity(gpu, port):
+    """C4 stand-in (TraceFEM): keep only the P1 DOFs within 2h of the sphere |p-c| = 0.3; irregular
+    row lengths, CG + Jacobi."""
+    import scipy.sparse as sp
+    N = 28
+    n, rb, ci, va = gpu.brick_csr_host(1, N, 0)
+    A = sp.csr_matrix((va, ci.astype(np.int64), rb.astype(np.int64)), shape=(n, n))
+    M = N - 1
+    idx = np.arange(n)
+    p = np.stack([idx % M + 1, (idx // M) % M + 1, idx // (M * M) + 1], 1) / N
+    keep = np.abs(np.linalg.norm(p - 0.5, axis=1) - 0.3) < 2.0 / N
+    S = (A[keep][:, keep] + sp.identity(int(keep.sum())) * 1e-3).tocsr()
+    S.sort_indices()
+    m = S.shape[0]
+    assert len(set(np.diff(S.indptr))) > 5
+    P = port.PortMatrix(m, m, S.indptr, S.indices, S.data)
+    G = gpu.Matrix(m, m, S.indptr, S.indices, S.data)
+    xin = hash_vector(m)
+    assert np.array_equal(G.spmv(xin), P.spmv(xin))
+    b = P.spmv(np.ones(m))
+    r = P.pcg_jacobi(np.zeros(m), b, 1000, 1e-9, True)
+    o = G.pcg_jacobi(np.zeros(m), b, 1000, 1e-9, True)
+    assert r[0] and o[0] and abs(o[1] - r[1]) <= 1 and rel(o[3], r[3]) <= X_RTOL
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json full size (C2): properties that need no CPU copy of the 17 GB matrix
+# ---------------------------------------------------------------------------------------------
+def test_full_size_c2_properties(gpu):
+    fe, N, numbering = 2, 185, 1
+    n, nnz = gpu.brick_sizes(fe, N)
+    assert n == 50243409
+    A = gpu.Matrix.brick(fe, N, numbering)
+    info = A.info()
+    assert info["nnz"] == nnz
+    assert info["padded_nnz"] <= 1.02 * nnz                 # sigma-sorted slices: < 2 % padding
+    x, y, z, w = (gpu.Vector(n) for _ in range(4))
+    # (1) symmetry through the operator: x'Ay == y'Ax, and A^T x == A x bit for bit
+    x.fill_hash()
+    gpu.brick_solution_device(fe, N, numbering, y)
+    A.spmv_dev(x, z)
+    A.spmv_dev(y, w)
+    yAx, xAy = gpu.dot(y, z), gpu.dot(x, w)
+    assert abs(yAx - xAy) <= 1e-11 * abs(yAx)
+    A.spmv_transpose_dev(x, w)
+    gpu.axpy(-1.0, z, w)
+    assert gpu.supnorm(w) == 0.0
+    # (2) linearity: A(x + 3y) == Ax + 3Ay to rounding
+    gpu.z_xpay(w, x, 3.0, y)                                # w = x + 3y
+    v = gpu.Vector(n)
+    A.spmv_dev(w, v)                                        # v = A w
+    A.spmv_dev(y, w)                                        # w = A y
+    gpu.axpy(3.0, w, z)                                     # z = Ax + 3Ay
+    gpu.axpy(-1.0, z, v)
+    assert gpu.supnorm(v) <= 1e-12 * max(gpu.supnorm(z), 1.0)
+    # (3) stiffness rows annihilate constants: |A 1|_inf is tiny except next to the boundary, and
+    #     sum_i (A 1)_i = 1'A1 > 0 equals the boundary flux; check 1'A1 against x*-weighted identity
+    x.fill(1.0)
+    A.spmv_dev(x, z)
+    one_A_one = gpu.dot(x, z)
+    assert one_A_one > 0
+    # (4) PCG: the recurrence residual equals the true residual, and the error decreases
+    gpu.brick_solution_device(fe, N, numbering, y)          # y = x*
+    b = gpu.Vector(n)
+    A.spmv_dev(y, b)
+    normb = gpu.norm(b)
+    x.fill(0.0)
+    conv, it, res = A.pcg_dev(x, b, 60, 0.0, True)
+    assert not conv and it == 60
+    A.spmv_dev(x, z)
+    gpu.axpy(-1.0, b, z)                                    # z = Ax - b
+    true_res = gpu.norm(z) / normb
+    assert abs(true_res - res) <= 1e-8 * max(res, 1e-300) + 1e-13
+    gpu.axpy(-1.0, y, x)
+    assert gpu.norm(x) < gpu.norm(y)
