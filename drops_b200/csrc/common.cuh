@@ -199,6 +199,8 @@ int timing_flush();
 inline void count_launch(int n = 1) { ctx().launches += n; }
 
 constexpr int kMaxQ = 4;            // quantities per fused reduction
+constexpr int kPartialStride = 1 << 20;   // dd entries of reduction workspace per slot (>= NQ * grid)
+constexpr int kPartialSlots = 4;          // kernels that may overlap use different slots
 constexpr int kReduceThreads = 256;
 
 // Grid for streaming vector kernels: a multiple of the SM count.

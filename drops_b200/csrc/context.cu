@@ -148,8 +148,8 @@ int drops_b200_init(int device)
     c.sm_count = p.multiProcessorCount;
     DB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     DB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
-    c.max_grid = c.sm_count * 128;
-    DB_CHECK(dev_alloc(&c.partials, (size_t)kMaxQ * c.max_grid * 8));
+    c.max_grid = c.sm_count * 8;
+    DB_CHECK(dev_alloc(&c.partials, (size_t)kPartialStride * kPartialSlots));
     DB_CHECK(dev_alloc(&c.tickets, 64));
     DB_CUDA(cudaMemset(c.tickets, 0, 64 * sizeof(unsigned)));
     DB_CHECK(dev_alloc(&c.scratch_scalars, 64));

@@ -39,6 +39,7 @@ struct EpiArgs {
     const double* dotv;
     double* dot_out;
     const int* done;
+    int prefetch;
     dd* partials;
     unsigned* ticket;
 };
@@ -52,12 +53,18 @@ __device__ __forceinline__ double apply_epilogue(double s, int row, const EpiArg
     return s;
 }
 
-constexpr int kSellUnroll = 4;
+__device__ __forceinline__ void prefetch_l2(const void* p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
-template <int EPI, bool EXACT, bool DOT>
-__global__ void __launch_bounds__(1024)
+// U = entries per thread loaded before the first use (loads in flight), MINB = resident CTAs of
+// 512 threads the register allocation must allow (2: <= 64 regs, 3: <= 40, 4: <= 32).
+template <int EPI, bool EXACT, bool DOT, int U, int MINB>
+__global__ void __launch_bounds__(512, MINB)
 k_spmv_sell(SellView A, const double* __restrict__ x, double* __restrict__ y, EpiArgs e)
 {
+    constexpr int kSellUnroll = U;
     if (e.done != nullptr && *e.done != 0) return;
     __shared__ dd red_smem[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -71,6 +78,13 @@ k_spmv_sell(SellView A, const double* __restrict__ x, double* __restrict__ y, Ep
         const int width = (int)((A.slice_ptr[s + 1] - base) >> 5);
         const int32_t* cp = A.col + base + lane;
         const double* vp = A.val + base + lane;
+        if (e.prefetch && s + nwarp < s_end) {
+            // pull the slice this warp handles next into L2 while the current one is consumed
+            const int64_t nb = A.slice_ptr[s + nwarp];
+            const int nlines = (int)((A.slice_ptr[s + nwarp + 1] - nb) >> 5);   // = width: 128 B col lines
+            for (int l = lane; l < nlines; l += 32) prefetch_l2(A.col + nb + (int64_t)l * 32);
+            for (int l = lane; l < 2 * nlines; l += 32) prefetch_l2(A.val + nb + (int64_t)l * 16);
+        }
         double sum = 0.0;
         int j = 0;
         for (; j + kSellUnroll <= width; j += kSellUnroll) {
@@ -161,19 +175,39 @@ static EpiArgs make_epi(const SpmvArgs& a)
     e.dotv = a.dotv;
     e.dot_out = a.dot_out;
     e.done = a.done;
-    e.partials = c.partials + (size_t)a.slot * kMaxQ * c.max_grid;
+    e.prefetch = (int)opt("spmv.prefetch", 0.0);
+    e.partials = c.partials + (size_t)a.slot * kPartialStride;
     e.ticket = c.tickets + a.slot;
     return e;
 }
 
+template <int EPI, bool EXACT, int U, int MINB>
+static void launch_sell_v(const SellView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads,
+                          cudaStream_t st)
+{
+    if (a.dotv != nullptr)
+        k_spmv_sell<EPI, EXACT, true, U, MINB><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
+    else
+        k_spmv_sell<EPI, EXACT, false, U, MINB><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
+}
+
+// "spmv.variant": 0 = U4/<=64 regs (default), 1 = U8/<=64, 2 = U4/<=40, 3 = U4/<=32, 4 = U2/<=32,
+// 5 = U8/<=40.  Only the plain product (the PCG kernel) is built in all variants.
 template <int EPI, bool EXACT>
 static void launch_sell(const SellView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads,
                         cudaStream_t st)
 {
-    if (a.dotv != nullptr)
-        k_spmv_sell<EPI, EXACT, true><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
-    else
-        k_spmv_sell<EPI, EXACT, false><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
+    if (EPI == EPI_NONE) {
+        switch ((int)opt("spmv.variant", 0.0)) {
+            case 1: launch_sell_v<EPI_NONE, EXACT, 8, 2>(v, a, e, grid, threads, st); return;
+            case 2: launch_sell_v<EPI_NONE, EXACT, 4, 3>(v, a, e, grid, threads, st); return;
+            case 3: launch_sell_v<EPI_NONE, EXACT, 4, 4>(v, a, e, grid, threads, st); return;
+            case 4: launch_sell_v<EPI_NONE, EXACT, 2, 4>(v, a, e, grid, threads, st); return;
+            case 5: launch_sell_v<EPI_NONE, EXACT, 8, 3>(v, a, e, grid, threads, st); return;
+            default: break;
+        }
+    }
+    launch_sell_v<EPI, EXACT, 4, 2>(v, a, e, grid, threads, st);
 }
 
 template <bool EXACT>
@@ -196,15 +230,26 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a)
     DB_ARG(a.epilogue == EPI_NONE || a.aux != nullptr, "epilogue needs aux vector");
     DB_ARG(a.dotv == nullptr || a.dot_out != nullptr, "fused dot needs an output scalar");
     if (A.rows == 0) return 0;
-    int threads = (int)opt("spmv.threads", 512);
+    int threads = (int)opt("spmv.threads", 256);
     if (threads < 32) threads = 32;
-    if (threads > 1024) threads = 1024;
+    if (threads > 512) threads = 512;
     threads &= ~31;
-    const double per_sm = opt("spmv.ctas_per_sm", 4.0);
-    long long grid = (long long)(per_sm * c.sm_count + 0.5);
+    // Work decomposition: every CTA owns `slices_per_cta` consecutive slices, CTAs are launched in
+    // matrix order.  Measured on B200 (profiles/r01_spmv_sweep.md): many short ranges walked in
+    // order beat a persistent grid by 1.7x -- all resident CTAs then stream one compact window of
+    // the matrix and share one window of x in L2.  "spmv.ctas_per_sm" > 0 selects a persistent-style
+    // grid instead (kept for the comparison).
+    const double per_sm = opt("spmv.ctas_per_sm", 0.0);
+    long long grid;
+    if (per_sm > 0.0) grid = (long long)(per_sm * c.sm_count + 0.5);
+    else {
+        long long spc = (long long)opt("spmv.slices_per_cta", 64.0);
+        if (spc < 1) spc = 1;
+        grid = ((long long)A.nslices + spc - 1) / spc;
+    }
     const long long max_useful = ((long long)A.nslices * 32 + threads - 1) / threads;
     if (grid > max_useful) grid = max_useful;
-    if (grid > c.max_grid) grid = c.max_grid;
+    if (grid > kPartialStride) grid = kPartialStride;
     if (grid < 1) grid = 1;
     cudaStream_t st = a.stream ? a.stream : c.stream;
     SellView v{A.slice_ptr, A.col, A.val, A.perm, (long long)A.nslices};
