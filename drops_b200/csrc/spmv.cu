@@ -191,8 +191,9 @@ static void launch_sell_v(const SellView& v, const SpmvArgs& a, const EpiArgs& e
         k_spmv_sell<EPI, EXACT, false, U, MINB><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
 }
 
-// "spmv.variant": 0 = U4/<=64 regs (default), 1 = U8/<=64, 2 = U4/<=40, 3 = U4/<=32, 4 = U2/<=32,
-// 5 = U8/<=40.  Only the plain product (the PCG kernel) is built in all variants.
+// "spmv.variant": 0 = U4/<=40 regs (default: best in profiles/r01_sweep2_spmv.jsonl), 1 = U8/<=64,
+// 2 = U4/<=64, 3 = U4/<=32, 4 = U2/<=32, 5 = U8/<=40.  Only the plain product (the PCG kernel) is
+// built in all variants; the epilogue forms use the default.
 template <int EPI, bool EXACT>
 static void launch_sell(const SellView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads,
                         cudaStream_t st)
@@ -200,14 +201,14 @@ static void launch_sell(const SellView& v, const SpmvArgs& a, const EpiArgs& e, 
     if (EPI == EPI_NONE) {
         switch ((int)opt("spmv.variant", 0.0)) {
             case 1: launch_sell_v<EPI_NONE, EXACT, 8, 2>(v, a, e, grid, threads, st); return;
-            case 2: launch_sell_v<EPI_NONE, EXACT, 4, 3>(v, a, e, grid, threads, st); return;
+            case 2: launch_sell_v<EPI_NONE, EXACT, 4, 2>(v, a, e, grid, threads, st); return;
             case 3: launch_sell_v<EPI_NONE, EXACT, 4, 4>(v, a, e, grid, threads, st); return;
             case 4: launch_sell_v<EPI_NONE, EXACT, 2, 4>(v, a, e, grid, threads, st); return;
             case 5: launch_sell_v<EPI_NONE, EXACT, 8, 3>(v, a, e, grid, threads, st); return;
             default: break;
         }
     }
-    launch_sell_v<EPI, EXACT, 4, 2>(v, a, e, grid, threads, st);
+    launch_sell_v<EPI, EXACT, 4, 3>(v, a, e, grid, threads, st);
 }
 
 template <bool EXACT>
@@ -230,20 +231,21 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a)
     DB_ARG(a.epilogue == EPI_NONE || a.aux != nullptr, "epilogue needs aux vector");
     DB_ARG(a.dotv == nullptr || a.dot_out != nullptr, "fused dot needs an output scalar");
     if (A.rows == 0) return 0;
-    int threads = (int)opt("spmv.threads", 256);
+    int threads = (int)opt("spmv.threads", 128);
     if (threads < 32) threads = 32;
     if (threads > 512) threads = 512;
     threads &= ~31;
     // Work decomposition: every CTA owns `slices_per_cta` consecutive slices, CTAs are launched in
-    // matrix order.  Measured on B200 (profiles/r01_spmv_sweep.md): many short ranges walked in
-    // order beat a persistent grid by 1.7x -- all resident CTAs then stream one compact window of
-    // the matrix and share one window of x in L2.  "spmv.ctas_per_sm" > 0 selects a persistent-style
+    // matrix order.  Measured on B200 (profiles/r01_spmv.md): many short ranges walked in order
+    // (128 threads x 16 slices = 512 rows per CTA, 98 k CTAs at C2) reach 5.9 TB/s, a persistent
+    // grid of 4 CTAs/SM only 3.3 TB/s -- all resident CTAs then stream one compact window of the
+    // matrix and share one window of x in L2.  "spmv.ctas_per_sm" > 0 selects the persistent-style
     // grid instead (kept for the comparison).
     const double per_sm = opt("spmv.ctas_per_sm", 0.0);
     long long grid;
     if (per_sm > 0.0) grid = (long long)(per_sm * c.sm_count + 0.5);
     else {
-        long long spc = (long long)opt("spmv.slices_per_cta", 64.0);
+        long long spc = (long long)opt("spmv.slices_per_cta", 16.0);
         if (spc < 1) spc = 1;
         grid = ((long long)A.nslices + spc - 1) / spc;
     }

@@ -1,0 +1,352 @@
+// drops_b200/hostxx/num/krylovsolver.h
+//
+// B200 drop-in for the part of DROPS' src/num/krylovsolver.h named by the hot path: the free
+// functions CG (:49-103), PCG (:107-179), GMRES (:320-461), MINRES (:1155-1161), PMINRES
+// (:1069-1152), the orthonormal-basis classes LanczosONBCL (:945-979) / PLanczosONBCL
+// (:1010-1052) and the drivers CGSolverCL (:1782-1802), PCGSolverCL (:1805-1832), MResSolverCL
+// (:1868-1889), PMResSolverCL (:1892-1921), GMResSolverCL (:1924-1973).
+//
+// Signatures, in/out conventions and return values are the reference's: x is the start vector
+// on entry and the solution on exit, max_iter IN limit / OUT iterations used, tol IN tolerance /
+// OUT residual reached, the bool result says "converged"; the drivers record the outcome in
+// SolverBaseCL::iter_/res_.  The bodies do not iterate on the host: they hand the system to the
+// device solvers behind include/drops_b200.h (vectors are copied in and out once per Solve, the
+// matrix copy is cached on SparseMatBaseCL::Version()).  Only DummyExchangeCL-style serial
+// exchange objects are meaningful here; multi-GPU runs use the row-partitioned device solver.
+#ifndef DROPS_SOLVER_H
+#define DROPS_SOLVER_H
+
+#include <iostream>
+#include <vector>
+
+#include "misc/container.h"
+#include "num/precond.h"
+#include "num/solverbase.h"
+#include "num/spmat.h"
+
+namespace DROPS
+{
+
+namespace b200
+{
+/// Prints the residual history the way the reference's loops do ("PCG: 3 resid 1.2e-05").
+inline void print_history(std::ostream* out, const char* tag, const std::vector<double>& hist, int iters)
+{
+    if (!out) return;
+    for (int i = 1; i <= iters && i < static_cast<int>(hist.size()); ++i)
+        (*out) << tag << ": " << i << " resid " << hist[i] << std::endl;
+}
+
+template <typename Mat, typename Vec>
+inline void check_dims(const Mat& A, const Vec& x, const Vec& b, const char* who)
+{
+    if (A.num_rows() != A.num_cols() || x.size() != A.num_rows() || b.size() != A.num_rows())
+        throw DROPSErrCL(std::string(who) + ": incompatible dimensions");
+}
+}  // namespace b200
+
+//=============================================================================
+//  Free functions
+//=============================================================================
+
+/// Conjugate gradients without preconditioner.
+template <typename Mat, typename Vec, typename ExCL>
+bool CG(const Mat& A, Vec& x, const Vec& b, const ExCL&, int& max_iter, double& tol, bool measure_relative_tol,
+        std::ostream* output = 0)
+{
+    const MatrixCL& M = b200::finest(A);
+    b200::check_dims(M, x, b, "CG");
+    std::vector<double> hist(output ? max_iter + 1 : 0);
+    int it = max_iter;
+    const int r = drops_b200_cg(M.device(), &x[0], Addr(b), &it, &tol, measure_relative_tol ? 1 : 0,
+                                output ? hist.data() : 0, static_cast<int>(hist.size()));
+    b200::check(r);
+    if (r == 1) max_iter = it;
+    b200::print_history(output, "CG", hist, r == 1 ? it : max_iter);
+    return r == 1;
+}
+
+/// Preconditioned conjugate gradients; M is JACPcCL or DummyPcCL.
+template <typename Mat, typename Vec, typename PreCon, typename ExCL>
+bool PCG(const Mat& A, Vec& x, const Vec& b, const ExCL&, PreCon& M, int& max_iter, double& tol,
+         bool measure_relative_tol = false, std::ostream* output = 0)
+{
+    const MatrixCL& Mat0 = b200::finest(A);
+    b200::check_dims(Mat0, x, b, "PCG");
+    std::vector<double> hist(output ? max_iter + 1 : 0);
+    int it = max_iter;
+    const int r = drops_b200_pcg(Mat0.device(), &x[0], Addr(b), b200::PcTraits<PreCon>::kind(),
+                                 b200::PcTraits<PreCon>::omega(M), &it, &tol, measure_relative_tol ? 1 : 0,
+                                 output ? hist.data() : 0, static_cast<int>(hist.size()));
+    b200::check(r);
+    if (r == 1) max_iter = it;
+    b200::print_history(output, "PCG", hist, r == 1 ? it : max_iter);
+    return r == 1;
+}
+
+enum PreMethGMRES { RightPreconditioning, LeftPreconditioning };
+
+/// Restarted GMRES(m) with modified Gram-Schmidt; the residual is the preconditioned one for
+/// LeftPreconditioning.  calculate2norm (a debugging aid of the reference) is accepted and ignored.
+template <typename Mat, typename Vec, typename PreCon, typename ExT>
+bool GMRES(const Mat& A, Vec& x, const Vec& b, const ExT&, PreCon& M, int m, int& max_iter, double& tol,
+           bool measure_relative_tol = true, bool /*calculate2norm*/ = false,
+           PreMethGMRES method = RightPreconditioning, std::ostream* output = 0)
+{
+    const MatrixCL& Mat0 = b200::finest(A);
+    b200::check_dims(Mat0, x, b, "GMRES");
+    int it = max_iter;
+    const int r = drops_b200_gmres(Mat0.device(), &x[0], Addr(b), b200::PcTraits<PreCon>::kind(),
+                                   b200::PcTraits<PreCon>::omega(M), m, &it, &tol, measure_relative_tol ? 1 : 0,
+                                   method == LeftPreconditioning ? 1 : 0);
+    b200::check(r);
+    if (r == 1) max_iter = it;
+    if (output)
+        (*output) << (r == 1 ? "GMRES converged in " : "GMRES DIDN'T converge after ") << it
+                  << " iterations with residual: " << tol << std::endl;
+    return r == 1;
+}
+
+//-----------------------------------------------------------------------------
+// Lanczos bases.  They are usable on their own (new_basis / next walk the three-term recurrence
+// with the product on the GPU), and they select the MINRES flavour when handed to PMResSolverCL.
+//-----------------------------------------------------------------------------
+template <typename Mat, typename Vec>
+bool LanczosStep(const Mat& A, const Vec& q0, const Vec& q1, Vec& q2, double& a1, const double b0, double& b1)
+{
+    q2 = A * q1 - b0 * q0;
+    a1 = dot(q2, q1);
+    q2 -= a1 * q1;
+    b1 = norm(q2);
+    if (b1 < 1e-15) return false;   // lucky breakdown: the Krylov space is A-invariant
+    q2 /= b1;
+    return true;
+}
+
+template <typename Vec>
+class LanczosONBCL
+{
+  private:
+    bool nobreakdown_;
+    double norm_r0_;
+
+  public:
+    SBufferCL<Vec, 3> q;
+    double a0;
+    SBufferCL<double, 2> b;
+
+    LanczosONBCL() : nobreakdown_(true), norm_r0_(0.), a0(0.) {}
+
+    template <typename Mat, typename ExT>
+    void new_basis(const Mat& A, const Vec& r0, const ExT&)
+    {
+        q[-1].resize(r0.size(), 0.);
+        norm_r0_ = norm(r0);
+        q[0].resize(r0.size(), 0.); q[0] = r0 / norm_r0_;
+        q[1].resize(r0.size(), 0.);
+        b[-1] = 0.;
+        nobreakdown_ = LanczosStep(A, q[-1], q[0], q[1], a0, b[-1], b[0]);
+    }
+    double norm_r0() const { return norm_r0_; }
+    bool breakdown() const { return !nobreakdown_; }
+
+    template <typename Mat, typename ExT>
+    bool next(const Mat& A, const ExT&)
+    {
+        q.rotate(); b.rotate();
+        return (nobreakdown_ = LanczosStep(A, q[-1], q[0], q[1], a0, b[-1], b[0]));
+    }
+};
+
+template <typename Vec, typename PreCon>
+class PLanczosONBCL
+{
+  public:
+    const PreCon& M;
+    PLanczosONBCL(const PreCon& M_) : M(M_) {}
+};
+
+namespace b200
+{
+/// How a Lanczos type maps onto drops_b200_minres.
+template <typename L>
+struct LanczosTraits;
+template <typename Vec>
+struct LanczosTraits<LanczosONBCL<Vec> > {
+    static int precond() { return 0; }
+    static int kind(const LanczosONBCL<Vec>&) { return DROPS_B200_PC_DUMMY; }
+    static double omega(const LanczosONBCL<Vec>&) { return 1.0; }
+};
+template <typename Vec, typename PC>
+struct LanczosTraits<PLanczosONBCL<Vec, PC> > {
+    static int precond() { return 1; }
+    static int kind(const PLanczosONBCL<Vec, PC>&) { return PcTraits<PC>::kind(); }
+    static double omega(const PLanczosONBCL<Vec, PC>& q) { return PcTraits<PC>::omega(q.M); }
+};
+
+template <typename Mat, typename Vec>
+inline bool run_minres(const Mat& A, Vec& x, const Vec& rhs, int precond, int kind, double omega, int& max_iter,
+                       double& tol, bool rel)
+{
+    const MatrixCL& Mat0 = finest(A);
+    check_dims(Mat0, x, rhs, "MINRES");
+    int it = max_iter;
+    const int r = drops_b200_minres(Mat0.device(), &x[0], Addr(rhs), precond, kind, omega, &it, &tol, rel ? 1 : 0);
+    check(r);
+    if (r == 1) max_iter = it;
+    return r == 1;
+}
+}  // namespace b200
+
+/// (Preconditioned) MINRES driven by a Lanczos basis type; the basis object only selects the
+/// flavour, the recurrence itself runs on the device starting from rhs - A*x.
+template <typename Mat, typename Vec, typename Lanczos, typename ExT>
+bool PMINRES(const Mat& A, Vec& x, const Vec& rhs, const ExT&, Lanczos& q, int& max_iter, double& tol,
+             bool measure_relative_tol = false)
+{
+    typedef b200::LanczosTraits<Lanczos> LT;
+    return b200::run_minres(A, x, rhs, LT::precond(), LT::kind(q), LT::omega(q), max_iter, tol, measure_relative_tol);
+}
+
+template <typename Mat, typename Vec, typename ExT>
+bool MINRES(const Mat& A, Vec& x, const Vec& rhs, const ExT&, int& max_iter, double& tol,
+            bool measure_relative_tol = false)
+{
+    return b200::run_minres(A, x, rhs, 0, DROPS_B200_PC_DUMMY, 1.0, max_iter, tol, measure_relative_tol);
+}
+
+//=============================================================================
+//  Drivers
+//=============================================================================
+
+class CGSolverCL : public SolverBaseCL
+{
+  public:
+    CGSolverCL(int maxiter, double tol, bool rel = false, std::ostream* output = 0)
+        : SolverBaseCL(maxiter, tol, rel, output) {}
+
+    template <typename Mat, typename Vec, typename ExT>
+    void Solve(const Mat& A, Vec& x, const Vec& b, const ExT& ex)
+    {
+        res_ = tol_; iter_ = maxiter_;
+        CG(A, x, b, ex, iter_, res_, rel_, output_);
+    }
+    template <typename Mat, typename Vec, typename ExT>
+    void Solve(const Mat& A, Vec& x, const Vec& b, const ExT& ex, int& numIter, double& resid) const
+    {
+        resid = tol_; numIter = maxiter_;
+        CG(A, x, b, ex, numIter, resid, rel_, output_);
+    }
+};
+
+template <typename PC>
+class PCGSolverCL : public SolverBaseCL
+{
+  private:
+    PC& _pc;
+
+  public:
+    PCGSolverCL(PC& pc, int maxiter, double tol, bool rel = false, std::ostream* output = 0)
+        : SolverBaseCL(maxiter, tol, rel, output), _pc(pc) {}
+
+    PC&       GetPc()       { return _pc; }
+    const PC& GetPc() const { return _pc; }
+
+    template <typename Mat, typename Vec, typename ExT>
+    void Solve(const Mat& A, Vec& x, const Vec& b, const ExT& ex)
+    {
+        res_ = tol_; iter_ = maxiter_;
+        PCG(A, x, b, ex, _pc, iter_, res_, rel_, output_);
+    }
+    template <typename Mat, typename Vec, typename ExT>
+    void Solve(const Mat& A, Vec& x, const Vec& b, const ExT& ex, int& numIter, double& resid) const
+    {
+        resid = tol_; numIter = maxiter_;
+        PCG(A, x, b, ex, _pc, numIter, resid, rel_, output_);
+    }
+};
+
+class MResSolverCL : public SolverBaseCL
+{
+  public:
+    MResSolverCL(int maxiter, double tol, bool rel = false) : SolverBaseCL(maxiter, tol, rel) {}
+
+    template <typename Mat, typename Vec, typename ExT>
+    void Solve(const Mat& A, Vec& x, const Vec& b, const ExT& ex)
+    {
+        res_ = tol_; iter_ = maxiter_;
+        MINRES(A, x, b, ex, iter_, res_, rel_);
+    }
+    template <typename Mat, typename Vec, typename ExT>
+    void Solve(const Mat& A, Vec& x, const Vec& b, const ExT& ex, int& numIter, double& resid) const
+    {
+        resid = tol_; numIter = maxiter_;
+        MINRES(A, x, b, ex, numIter, resid, rel_);
+    }
+};
+
+template <typename Lanczos>
+class PMResSolverCL : public SolverBaseCL
+{
+  private:
+    Lanczos& q_;
+
+  public:
+    PMResSolverCL(Lanczos& q, int maxiter, double tol, bool rel = false) : SolverBaseCL(maxiter, tol, rel), q_(q) {}
+
+    Lanczos&       GetONB()       { return q_; }
+    const Lanczos& GetONB() const { return q_; }
+
+    template <typename Mat, typename Vec, typename ExT>
+    void Solve(const Mat& A, Vec& x, const Vec& b, const ExT& ex)
+    {
+        res_ = tol_; iter_ = maxiter_;
+        PMINRES(A, x, b, ex, q_, iter_, res_, rel_);
+    }
+    template <typename Mat, typename Vec, typename ExT>
+    void Solve(const Mat& A, Vec& x, const Vec& b, const ExT& ex, int& numIter, double& resid) const
+    {
+        resid = tol_; numIter = maxiter_;
+        PMINRES(A, x, b, ex, q_, numIter, resid, rel_);
+    }
+};
+
+template <typename PC>
+class GMResSolverCL : public SolverBaseCL
+{
+  private:
+    PC&          pc_;
+    int          restart_;
+    bool         calculate2norm_;
+    PreMethGMRES method_;
+
+  public:
+    /// mod / useModGS select Gram-Schmidt variants of the MPI build of DROPS; the serial path
+    /// (and this one) always runs modified Gram-Schmidt.
+    GMResSolverCL(PC& pc, int restart, int maxiter, double tol, bool relative = true, bool calculate2norm = false,
+                  PreMethGMRES method = LeftPreconditioning, bool /*mod*/ = true, bool /*useModGS*/ = false,
+                  std::ostream* output = 0)
+        : SolverBaseCL(maxiter, tol, relative, output), pc_(pc), restart_(restart),
+          calculate2norm_(calculate2norm), method_(method) {}
+
+    PC&       GetPc()       { return pc_; }
+    const PC& GetPc() const { return pc_; }
+    int       GetRestart() const { return restart_; }
+
+    template <typename Mat, typename Vec, typename ExT>
+    void Solve(const Mat& A, Vec& x, const Vec& b, const ExT& ex)
+    {
+        res_ = tol_; iter_ = maxiter_;
+        GMRES(A, x, b, ex, pc_, restart_, iter_, res_, rel_, calculate2norm_, method_, output_);
+    }
+    template <typename Mat, typename Vec, typename ExT>
+    void Solve(const Mat& A, Vec& x, const Vec& b, const ExT& ex, int& numIter, double& resid) const
+    {
+        resid = tol_; numIter = maxiter_;
+        GMRES(A, x, b, ex, pc_, restart_, numIter, resid, rel_, calculate2norm_, method_, output_);
+    }
+};
+
+}  // namespace DROPS
+
+#endif

@@ -398,7 +398,7 @@ class MLSparseMatBaseCL : public std::list<SparseMatBaseCL<T> >
 {
   public:
     typedef std::list<SparseMatBaseCL<T> > base_;
-    MLSparseMatBaseCL(size_t lvl = 1) : base_(lvl) {}
+    explicit MLSparseMatBaseCL(size_t lvl = 1) : base_(lvl) {}
     SparseMatBaseCL<T>&       GetFinest()       { return this->back(); }
     const SparseMatBaseCL<T>& GetFinest() const { return this->back(); }
     SparseMatBaseCL<T>*       GetFinestPtr()       { return &this->back(); }

@@ -82,9 +82,9 @@ def test_spmv_layout_and_launch_options_do_not_change_results(gpu, sigma, thread
         assert out[1] == int(g["sym_pcgjac"][1]) and rel(out[3], g["sym_pcgjac_x"]) <= 1e-12
     finally:
         gpu.set_option("sell.sigma", 4096)
-        gpu.set_option("spmv.threads", 256)
+        gpu.set_option("spmv.threads", 128)
         gpu.set_option("spmv.ctas_per_sm", 0)
-        gpu.set_option("spmv.slices_per_cta", 64)
+        gpu.set_option("spmv.slices_per_cta", 16)
         gpu.set_option("spmv.variant", 0)
         gpu.set_option("spmv.prefetch", 0)
 

@@ -1,0 +1,81 @@
+"""The C++ host side above the C ABI (drops_b200/hostxx = DROPS' header interface for the path).
+
+tests/cxx/hotpath_kats.cpp is compiled against the UNMODIFIED reference headers (expected output,
+committed as tests/golden/hotpath_kats.expected.txt) and against the drop-in headers +
+libdrops_b200.so.  CPU: the drop-in build compiles and links, and the committed expectation holds
+the reference's .ref values.  GPU: the drop-in binary reproduces the reference's output line by line.
+"""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CXX_DIR = os.path.join(ROOT, "tests", "cxx")
+EXPECTED = os.path.join(ROOT, "tests", "golden", "hotpath_kats.expected.txt")
+
+KEYS = ("LANCZOS", "MINRES2", "MINRES4", "PMINRES4", "PMINRES4D", "TRANSP_MUL", "B*c", "VECEXPR", "VECOPS",
+        "EXCHANGE", "LAPLACE", "PCGJAC", "PCGJAC08", "CG", "PCGJAC5", "JACAPPLY", "GMRESJAC", "GMRESJACR",
+        "VERSIONED", "hotpath_kats")
+
+
+def parse(text):
+    """{first token(s) before ':' -> list of numbers on the line} for the program's own lines."""
+    out = {}
+    for line in text.splitlines():
+        m = re.match(r"^([A-Za-z0-9_*]+(?: [A-Za-z\-]+)?):? ?(.*)$", line)
+        if not m or not line.startswith(KEYS):
+            continue
+        key = line.split(":")[0] if ":" in line else line
+        nums = [float(t) for t in re.findall(r"[-+]?\d+\.?\d*(?:[eE][-+]?\d+)?", line[len(key):])]
+        out[key] = nums
+    return out
+
+
+def build_b200(lib_built):
+    subprocess.check_call(["make", "-C", CXX_DIR, "b200"], stdout=subprocess.DEVNULL)
+    return os.path.join(CXX_DIR, "build", "kats_b200")
+
+
+def test_dropin_headers_compile_and_link(lib_built):
+    exe = build_b200(lib_built)
+    assert os.path.exists(exe)
+    out = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    assert "libdrops_b200.so" in out
+
+
+def test_expected_output_holds_the_reference_kats():
+    exp = parse(open(EXPECTED).read())
+    assert exp["LANCZOS vectors"] == [2]                               # "lucky breakdown after 2 vectors"
+    assert abs(exp["MINRES4 iterations"][1] - 2.87588e-11) < 1e-10      # TestMinres.ref Residual3
+    assert abs(exp["PMINRES4D iterations"][1] - 2.87596e-11) < 1e-10    # TestMinres.ref Residual5
+    assert exp["TRANSP_MUL"] == [3.0, 3.0]                              # Testblockmat.ref
+    assert exp["VECEXPR maxdiff"][0] <= 1e-16                           # Testvectest.ref
+    assert "hotpath_kats finished regularly" in open(EXPECTED).read()
+
+
+@pytest.mark.gpu
+def test_dropin_binary_matches_reference_output(lib_built):
+    exe = build_b200(lib_built)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got, exp = parse(r.stdout), parse(open(EXPECTED).read())
+    assert "hotpath_kats finished regularly" in r.stdout
+    missing = sorted(set(exp) - set(got))
+    assert not missing, missing
+    # exact lines: host-side vector code and bit-identical device products
+    for key in ("LANCZOS vectors", "TRANSP_MUL", "B*c", "VECEXPR maxdiff", "VECOPS dot", "EXCHANGE pardot",
+                "LAPLACE rows", "VERSIONED ratio", "JACAPPLY z7", "MINRES2 converged"):
+        assert got[key] == exp[key], (key, got[key], exp[key])
+    # solutions of the tiny systems
+    for key in ("MINRES2 x", "MINRES4 x", "PMINRES4 x", "PMINRES4D x"):
+        assert all(abs(a - b) <= 1e-9 * max(1.0, abs(b)) for a, b in zip(got[key], exp[key])), key
+    # iterations (+-1) and residuals (the .ref files use an absolute 1e-10)
+    for key in ("MINRES4 iterations", "PMINRES4 iterations", "PMINRES4D iterations"):
+        assert abs(got[key][0] - exp[key][0]) <= 1 and abs(got[key][1] - exp[key][1]) < 1e-10, key
+    for key in ("PCGJAC iterations", "CG iterations", "GMRESJAC iterations", "GMRESJACR iterations"):
+        assert abs(got[key][0] - exp[key][0]) <= 1, (key, got[key], exp[key])
+        assert got[key][1] <= 1e-10 and got[key][2] <= 1e-8, (key, got[key])
+    assert abs(got["PCGJAC08 converged"][1] - exp["PCGJAC08 converged"][1]) <= 1 and got["PCGJAC08 converged"][0] == 1
+    assert got["PCGJAC5 iterations"] == exp["PCGJAC5 iterations"] == [5.0, 0.0]
