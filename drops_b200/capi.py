@@ -65,6 +65,7 @@ SIGNATURES = {
     "drops_b200_vector_ptr": (_i, [_vp, _vpp]),
     "drops_b200_spmv_dev": (_i, [_vp, _vp, _vp]),
     "drops_b200_spmv_transpose_dev": (_i, [_vp, _vp, _vp]),
+    "drops_b200_spmv_dot_dev": (_i, [_vp, _vp, _vp, _vp, _dpp]),
     "drops_b200_dot": (_i, [_vp, _vp, _dpp]),
     "drops_b200_norm_sq": (_i, [_vp, _dpp]),
     "drops_b200_norm": (_i, [_vp, _dpp]),
@@ -351,6 +352,12 @@ class Matrix:
     # --- device-vector products ----------------------------------------------------------
     def spmv_dev(self, x, y):
         check(lib().drops_b200_spmv_dev(self.h, x.h, y.h))
+
+    def spmv_dot_dev(self, x, y, w):
+        """y = A x fused with dot(y, w); returns the dot product."""
+        r = C.c_double()
+        check(lib().drops_b200_spmv_dot_dev(self.h, x.h, y.h, w.h, C.byref(r)))
+        return r.value
 
     def spmv_transpose_dev(self, x, y):
         check(lib().drops_b200_spmv_transpose_dev(self.h, x.h, y.h))

@@ -114,37 +114,88 @@ __device__ __forceinline__ void block_reduce_dd(dd (&v)[NQ], dd* smem)
     __syncthreads();
 }
 
-// Grid-wide deterministic reduction.  Every block stores its NQ partials, takes a ticket, and
-// the block that draws the last ticket sums all partials in block-index order (independent of
-// which block happens to be last) and returns true in ALL its threads with the totals in
-// thread 0's v[].  `partials` holds NQ*gridDim.x dd, `ticket` is zero on entry and is reset.
+// Grid-wide deterministic reduction.  Every block stores its NQ partials and takes a ticket; the
+// block that draws the last ticket sums the partials in block-index order (independent of which
+// block happens to be last) and returns true in ALL its threads with the totals in thread 0's
+// v[].  Grids of more than kReduceFlat blocks (the SpMV launches ~10^5 short CTAs) are reduced in
+// two levels -- groups of kReduceGroup consecutive blocks, then the group sums -- so that the
+// serial tail executed by a single CTA stays a few loads per thread instead of gridDim/blockDim
+// (measured on B200: 0.8 ms of a 3.9 ms SpMV with the flat scheme, profiles/r01_notes.md).
+// `partials` holds kPartialStride dd (NQ*gridDim block partials, then NQ*ngroups group partials),
+// `ticket` kTicketStride counters that are zero on entry and are reset before the kernel ends.
+constexpr unsigned kReduceFlat = 2048;
+constexpr unsigned kReduceGroup = 256;
+
 template <int NQ>
-__device__ __forceinline__ bool grid_reduce_dd(dd (&v)[NQ], dd* smem, dd* partials, unsigned* ticket)
+__device__ __forceinline__ void sum_partials_dd(dd (&acc)[NQ], const dd* partials, unsigned stride,
+                                                unsigned begin, unsigned end, dd* smem)
 {
-    __shared__ bool is_last;
-    block_reduce_dd<NQ>(v, smem);
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) partials[q * gridDim.x + blockIdx.x] = v[q];
-        __threadfence();
-        const unsigned t = atomicAdd(ticket, 1u);
-        is_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return false;
-    __threadfence();
-    dd acc[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
         acc[q] = dd_zero();
         // fixed assignment of partials to threads, fixed order inside a thread
-        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
-            const volatile dd* p = partials + q * gridDim.x + b;
+        for (unsigned b = begin + threadIdx.x; b < end; b += blockDim.x) {
+            const volatile dd* p = partials + (size_t)q * stride + b;
             dd t; t.hi = p->hi; t.lo = p->lo;
             acc[q] = dd_add(acc[q], t);
         }
     }
     block_reduce_dd<NQ>(acc, smem);
+}
+
+template <int NQ>
+__device__ __forceinline__ bool grid_reduce_dd(dd (&v)[NQ], dd* smem, dd* partials, unsigned* ticket)
+{
+    __shared__ bool is_last;
+    block_reduce_dd<NQ>(v, smem);
+    const unsigned nblk = gridDim.x;
+    dd acc[NQ];
+    if (nblk <= kReduceFlat) {
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) partials[(size_t)q * nblk + blockIdx.x] = v[q];
+            __threadfence();
+            is_last = (atomicAdd(ticket, 1u) == nblk - 1);
+        }
+        __syncthreads();
+        if (!is_last) return false;
+        __threadfence();
+        sum_partials_dd<NQ>(acc, partials, nblk, 0u, nblk, smem);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) v[q] = acc[q];
+            *ticket = 0u;
+        }
+        return true;
+    }
+    // ---- level 1: the last block of each group sums the group's block partials ------------------
+    const unsigned ngroups = (nblk + kReduceGroup - 1) / kReduceGroup;
+    const unsigned group = blockIdx.x / kReduceGroup;
+    const unsigned gbegin = group * kReduceGroup;
+    const unsigned gend = gbegin + kReduceGroup < nblk ? gbegin + kReduceGroup : nblk;
+    dd* gpartials = partials + (size_t)NQ * nblk;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) partials[(size_t)q * nblk + blockIdx.x] = v[q];
+        __threadfence();
+        is_last = (atomicAdd(ticket + 1 + group, 1u) == gend - gbegin - 1);
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+    sum_partials_dd<NQ>(acc, partials, nblk, gbegin, gend, smem);
+    // ---- level 2: the last group finisher sums the group partials ------------------------------
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) gpartials[(size_t)q * ngroups + group] = acc[q];
+        ticket[1 + group] = 0u;
+        __threadfence();
+        is_last = (atomicAdd(ticket, 1u) == ngroups - 1);
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+    sum_partials_dd<NQ>(acc, gpartials, ngroups, 0u, ngroups, smem);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int q = 0; q < NQ; ++q) v[q] = acc[q];
@@ -172,7 +223,7 @@ struct Ctx {
     cudaStream_t copy_stream = nullptr; // staging copies
     // reduction workspace
     dd* partials = nullptr;             // MAX_Q * max_grid
-    unsigned* tickets = nullptr;        // a few independent tickets
+    unsigned* tickets = nullptr;        // kPartialSlots * kTicketStride counters
     double* scratch_scalars = nullptr;  // device doubles for standalone dot/norm results
     double* h_scalars = nullptr;        // pinned host mirror
     int max_grid = 0;
@@ -201,6 +252,8 @@ inline void count_launch(int n = 1) { ctx().launches += n; }
 constexpr int kMaxQ = 4;            // quantities per fused reduction
 constexpr int kPartialStride = 1 << 20;   // dd entries of reduction workspace per slot (>= NQ * grid)
 constexpr int kPartialSlots = 4;          // kernels that may overlap use different slots
+constexpr int kTicketStride = 8192;       // counters per slot: 1 + groups of the two-level grid reduction
+constexpr int kMaxReduceGrid = kPartialStride / 2;   // NQ = 1 kernels; fused NQ > 1 kernels use <= 8 CTAs/SM
 constexpr int kReduceThreads = 256;
 
 // Grid for streaming vector kernels: a multiple of the SM count.

@@ -150,8 +150,8 @@ int drops_b200_init(int device)
     DB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     c.max_grid = c.sm_count * 8;
     DB_CHECK(dev_alloc(&c.partials, (size_t)kPartialStride * kPartialSlots));
-    DB_CHECK(dev_alloc(&c.tickets, 64));
-    DB_CUDA(cudaMemset(c.tickets, 0, 64 * sizeof(unsigned)));
+    DB_CHECK(dev_alloc(&c.tickets, (size_t)kPartialSlots * kTicketStride));
+    DB_CUDA(cudaMemset(c.tickets, 0, (size_t)kPartialSlots * kTicketStride * sizeof(unsigned)));
     DB_CHECK(dev_alloc(&c.scratch_scalars, 64));
     DB_CUDA(cudaMallocHost((void**)&c.h_scalars, 64 * sizeof(double)));
     DB_CUDA(cudaDeviceSynchronize());   // the memsets above ran on the legacy stream

@@ -529,6 +529,19 @@ int drops_b200_spmv_dev(drops_b200_matrix_t A, drops_b200_vector_t x, drops_b200
     return spmv_apply(A, false, a);
 }
 
+int drops_b200_spmv_dot_dev(drops_b200_matrix_t A, drops_b200_vector_t x, drops_b200_vector_t y,
+                            drops_b200_vector_t w, double* result)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(A && x && y && w && result, "null argument");
+    DB_ARG(x->n == A->csr.cols && y->n == A->csr.rows && w->n == A->csr.rows,
+           "SparseMatBaseCL * VectorBaseCL: incompatible dimensions");
+    Ctx& c = ctx();
+    SpmvArgs a; a.x = x->d; a.y = y->d; a.dotv = w->d; a.dot_out = c.scratch_scalars;
+    DB_CHECK(spmv_apply(A, false, a));
+    return fetch(c.scratch_scalars, result, sizeof(double));
+}
+
 int drops_b200_spmv_transpose_dev(drops_b200_matrix_t A, drops_b200_vector_t x, drops_b200_vector_t y)
 {
     DB_CHECK(require_ctx());

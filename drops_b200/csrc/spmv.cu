@@ -177,7 +177,7 @@ static EpiArgs make_epi(const SpmvArgs& a)
     e.done = a.done;
     e.prefetch = (int)opt("spmv.prefetch", 0.0);
     e.partials = c.partials + (size_t)a.slot * kPartialStride;
-    e.ticket = c.tickets + a.slot;
+    e.ticket = c.tickets + (size_t)a.slot * kTicketStride;
     return e;
 }
 
@@ -251,7 +251,7 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a)
     }
     const long long max_useful = ((long long)A.nslices * 32 + threads - 1) / threads;
     if (grid > max_useful) grid = max_useful;
-    if (grid > kPartialStride) grid = kPartialStride;
+    if (grid > kMaxReduceGrid) grid = kMaxReduceGrid;
     if (grid < 1) grid = 1;
     cudaStream_t st = a.stream ? a.stream : c.stream;
     SellView v{A.slice_ptr, A.col, A.val, A.perm, (long long)A.nslices};

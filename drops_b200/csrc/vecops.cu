@@ -41,7 +41,7 @@ static int launch_stream(size_t n, const Op& op, const char* timing_key, int slo
     ScopedTiming t(timing_key);
     const int grid = vec_grid(n, kReduceThreads, 4);
     k_stream<NQ, Op><<<grid, kReduceThreads, 0, c.stream>>>(
-        n, op, c.partials + (size_t)slot * kPartialStride, c.tickets + slot);
+        n, op, c.partials + (size_t)slot * kPartialStride, c.tickets + (size_t)slot * kTicketStride);
     count_launch();
     DB_CUDA(cudaGetLastError());
     return 0;

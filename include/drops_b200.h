@@ -126,6 +126,10 @@ DROPS_B200_API int drops_b200_vector_ptr(drops_b200_vector_t v, double** dptr);
 
 DROPS_B200_API int drops_b200_spmv_dev(drops_b200_matrix_t A, drops_b200_vector_t x, drops_b200_vector_t y);
 DROPS_B200_API int drops_b200_spmv_transpose_dev(drops_b200_matrix_t A, drops_b200_vector_t x, drops_b200_vector_t y);
+/* y = A*x and *result = dot(y, w) in one kernel: the q = A*p; lambda = ParDot(q, p) pair of PCG
+ * (num/krylovsolver.h:149-151) as the solver runs it.  w may be x. */
+DROPS_B200_API int drops_b200_spmv_dot_dev(drops_b200_matrix_t A, drops_b200_vector_t x, drops_b200_vector_t y,
+                                           drops_b200_vector_t w, double* result);
 
 /* dot (num/spmat.h:164-170), norm_sq/norm (:180-196), supnorm (:198-210): one deterministic
  * double-double tree reduction; DummyExchangeCL::ParDot/Norm (parallel/exchange.h:58-84, Kahan)
