@@ -25,6 +25,8 @@ class DropsB200Error(RuntimeError):
 _szp = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 
+_i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 _vp, _sz, _d, _i = C.c_void_p, C.c_size_t, C.c_double, C.c_int
 _ip, _dpp, _szpp = C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_size_t)
 _vpp = C.POINTER(C.c_void_p)
@@ -87,6 +89,39 @@ SIGNATURES = {
     "drops_b200_brick_matrix_device": (_i, [_i, _i, _i, _d, _vpp]),
     "drops_b200_brick_solution_host": (_i, [_i, _i, _i, _dp]),
     "drops_b200_brick_solution_device": (_i, [_i, _i, _i, _vp]),
+    # row-partitioned systems
+    "drops_b200_exchange_create": (_i, [_i, _i, _sz, _i64p, _sz, _i64p, _i32p, _vpp]),
+    "drops_b200_exchange_destroy": (_i, [_vp]),
+    "drops_b200_exchange_sizes": (_i, [_vp, _szpp, _szpp, _szpp, _ip]),
+    "drops_b200_exchange_request": (_i, [_vp, _i, _szpp, _vp]),
+    "drops_b200_exchange_set_send": (_i, [_vp, _i, _sz, _i64p]),
+    "drops_b200_exchange_send_list": (_i, [_vp, _i, _szpp, _vp]),
+    "drops_b200_exchange_local_index": (_i, [_vp, _sz, _i64p, _i64p]),
+    "drops_b200_exchange_ready": (_i, [_vp]),
+    "drops_b200_find_ghosts": (_i, [_sz, _i64p, _sz, _szp, _vp, _sz, _szpp]),
+    "drops_b200_partition_rows": (_i, [_sz, _szp, _szp, _i, _i32p]),
+    "drops_b200_comm_unique_id": (_i, [_vp]),
+    "drops_b200_comm_create": (_i, [_i, _i, _vp, _vpp]),
+    "drops_b200_comm_create_local": (_i, [_i, _vpp]),
+    "drops_b200_comm_destroy": (_i, [_vp]),
+    "drops_b200_comm_info": (_i, [_vp, _ip, _ip, _ip]),
+    "drops_b200_comm_allreduce_max": (_i, [_vp, _dpp]),
+    "drops_b200_dist_matrix_create": (_i, [_vp, _vp, _sz, _szp, _szp, _dp, C.c_uint64, _vpp]),
+    "drops_b200_dist_matrix_create_device": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, C.c_uint64, _vpp]),
+    "drops_b200_dist_matrix_destroy": (_i, [_vp]),
+    "drops_b200_dist_matrix_info": (_i, [_vp, _szpp, _szpp, _szpp, _szpp, _szpp, _szpp, _szpp]),
+    "drops_b200_dist_matrix_diag": (_i, [_vp, _dp]),
+    "drops_b200_dist_spmv_dev": (_i, [_i, _vpp, _vpp, _vpp]),
+    "drops_b200_dist_dot": (_i, [_i, _vpp, _vpp, _vpp, _dpp]),
+    "drops_b200_dist_pcg_dev": (_i, [_i, _vpp, _vpp, _vpp, _i, _d, _ip, _dpp, _i, _vp, _i]),
+    "drops_b200_brick_slab_generate": (_i, [_i, _i, _i, _d, _i, _i, _vpp]),
+    "drops_b200_brick_slab_destroy": (_i, [_vp]),
+    "drops_b200_brick_slab_info": (_i, [_vp, _szpp, _szpp, _szpp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "drops_b200_brick_slab_owned": (_i, [_vp, _i64p]),
+    "drops_b200_brick_slab_ghosts": (_i, [_vp, _i64p, _i32p]),
+    "drops_b200_brick_slab_matrix": (_i, [_vp, _vp, _vp, _vpp]),
+    "drops_b200_brick_slab_solution": (_i, [_vp, _vp]),
+    "drops_b200_brick_owner": (_i, [_i, _i, _i, _i, _sz, _i64p, _i32p]),
 }
 
 
@@ -471,3 +506,245 @@ def brick_solution_host(fe, N, numbering=0):
 
 def brick_solution_device(fe, N, numbering, vec):
     check(lib().drops_b200_brick_solution_device(int(fe), int(N), int(numbering), vec.h))
+
+
+# --- row-partitioned systems ---------------------------------------------------------------------
+UNIQUE_ID_BYTES = 128
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def find_ghosts(owned_gid, colind):
+    """Sorted unique column ids of the local rows that are not owned (host)."""
+    owned_gid, colind = _i64(owned_gid), _u64(colind)
+    n = C.c_size_t()
+    check(lib().drops_b200_find_ghosts(owned_gid.size, _nonempty(owned_gid, np.int64), colind.size,
+                                       _nonempty(colind, np.uint64), None, 0, C.byref(n)))
+    out = np.zeros(max(n.value, 1), np.int64)
+    check(lib().drops_b200_find_ghosts(owned_gid.size, _nonempty(owned_gid, np.int64), colind.size,
+                                       _nonempty(colind, np.uint64), out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
+    return out[:n.value]
+
+
+def partition_rows(rowbeg, colind, nparts):
+    """part[row] in [0, nparts): level-structure row partitioner (host)."""
+    rowbeg, colind = _u64(rowbeg), _u64(colind)
+    part = np.zeros(max(rowbeg.size - 1, 1), np.int32)
+    check(lib().drops_b200_partition_rows(rowbeg.size - 1, rowbeg, _nonempty(colind, np.uint64), int(nparts), part))
+    return part[:rowbeg.size - 1]
+
+
+class Exchange:
+    """Halo plan of one rank (ExchangeCL stand-in); host only."""
+
+    def __init__(self, rank, world, owned_gid, ghost_gid, ghost_owner):
+        owned_gid, ghost_gid, ghost_owner = _i64(owned_gid), _i64(ghost_gid), _i32(ghost_owner)
+        h = C.c_void_p()
+        check(lib().drops_b200_exchange_create(int(rank), int(world), owned_gid.size, _nonempty(owned_gid, np.int64),
+                                               ghost_gid.size, _nonempty(ghost_gid, np.int64),
+                                               _nonempty(ghost_owner, np.int32), C.byref(h)))
+        self.h, self.rank, self.world = h, int(rank), int(world)
+        self.n_owned, self.n_ghost = int(owned_gid.size), int(ghost_gid.size)
+
+    def request(self, peer):
+        n = C.c_size_t()
+        check(lib().drops_b200_exchange_request(self.h, int(peer), C.byref(n), None))
+        out = np.zeros(max(n.value, 1), np.int64)
+        check(lib().drops_b200_exchange_request(self.h, int(peer), C.byref(n), out.ctypes.data_as(C.c_void_p)))
+        return out[:n.value]
+
+    def set_send(self, peer, gids):
+        gids = _i64(gids)
+        check(lib().drops_b200_exchange_set_send(self.h, int(peer), gids.size, _nonempty(gids, np.int64)))
+
+    def send_list(self, peer):
+        n = C.c_size_t()
+        check(lib().drops_b200_exchange_send_list(self.h, int(peer), C.byref(n), None))
+        out = np.zeros(max(n.value, 1), np.int64)
+        check(lib().drops_b200_exchange_send_list(self.h, int(peer), C.byref(n), out.ctypes.data_as(C.c_void_p)))
+        return out[:n.value]
+
+    def local_index(self, gids):
+        gids = _i64(gids)
+        out = np.zeros(max(gids.size, 1), np.int64)
+        check(lib().drops_b200_exchange_local_index(self.h, gids.size, _nonempty(gids, np.int64), out))
+        return out[:gids.size]
+
+    def sizes(self):
+        a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        nn = C.c_int()
+        check(lib().drops_b200_exchange_sizes(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(nn)))
+        return {"n_owned": a.value, "n_ghost": b.value, "n_send": c.value, "neighbours": nn.value}
+
+    def ready(self):
+        return bool(check(lib().drops_b200_exchange_ready(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().drops_b200_exchange_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Comm:
+    def __init__(self, h):
+        self.h = h
+        r, w, l = C.c_int(), C.c_int(), C.c_int()
+        check(lib().drops_b200_comm_info(h, C.byref(r), C.byref(w), C.byref(l)))
+        self.rank, self.world, self.is_local = r.value, w.value, bool(l.value)
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(UNIQUE_ID_BYTES)
+        check(lib().drops_b200_comm_unique_id(buf))
+        return buf.raw
+
+    @classmethod
+    def nccl(cls, rank, world, unique_id=None):
+        h = C.c_void_p()
+        check(lib().drops_b200_comm_create(int(rank), int(world), unique_id, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def local(cls, world):
+        h = C.c_void_p()
+        check(lib().drops_b200_comm_create_local(int(world), C.byref(h)))
+        return cls(h)
+
+    def allreduce_max(self, v):
+        d = C.c_double(float(v))
+        check(lib().drops_b200_comm_allreduce_max(self.h, C.byref(d)))
+        return d.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().drops_b200_comm_destroy(self.h)
+            self.h = None
+
+
+def _harr(objs):
+    return (C.c_void_p * len(objs))(*[o.h for o in objs])
+
+
+class DistMatrix:
+    """The rows of one rank of a row-partitioned MatrixCL."""
+
+    def __init__(self, comm, ex, rowbeg, colind_global, val, version=1):
+        rowbeg, colind_global, val = _u64(rowbeg), _u64(colind_global), _f64(val)
+        h = C.c_void_p()
+        check(lib().drops_b200_dist_matrix_create(comm.h, ex.h, val.size, rowbeg, _nonempty(colind_global, np.uint64),
+                                                  _nonempty(val, np.float64), int(version), C.byref(h)))
+        self.h, self.comm, self.ex = h, comm, ex
+
+    @classmethod
+    def _wrap(cls, h, comm, ex):
+        self = cls.__new__(cls)
+        self.h, self.comm, self.ex = h, comm, ex
+        return self
+
+    def info(self):
+        v = [C.c_size_t() for _ in range(7)]
+        check(lib().drops_b200_dist_matrix_info(self.h, *[C.byref(x) for x in v]))
+        keys = ["n_owned", "n_ghost", "nnz", "interior_rows", "boundary_rows", "n_send", "device_bytes"]
+        return dict(zip(keys, [x.value for x in v]))
+
+    def diag(self):
+        d = np.zeros(max(self.info()["n_owned"], 1))
+        check(lib().drops_b200_dist_matrix_diag(self.h, d))
+        return d[:self.info()["n_owned"]]
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().drops_b200_dist_matrix_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def dist_spmv(parts, xs, ys):
+    check(lib().drops_b200_dist_spmv_dev(len(parts), _harr(parts), _harr(xs), _harr(ys)))
+
+
+def dist_dot(parts, xs, ys):
+    r = C.c_double()
+    check(lib().drops_b200_dist_dot(len(parts), _harr(parts), _harr(xs), _harr(ys), C.byref(r)))
+    return r.value
+
+
+def dist_pcg(parts, xs, bs, max_iter, tol, relative=False, pc=PC_JACOBI, omega=1.0, hist=False):
+    it, res = C.c_int(int(max_iter)), C.c_double(float(tol))
+    h, hargs = Matrix._hist(max_iter, hist)
+    conv = check(lib().drops_b200_dist_pcg_dev(len(parts), _harr(parts), _harr(xs), _harr(bs), int(pc), float(omega),
+                                               C.byref(it), C.byref(res), int(relative), *hargs))
+    out = (bool(conv), it.value, res.value)
+    return out + (h,) if hist else out
+
+
+class BrickSlab:
+    """z-slab of the synthetic brick generated on the device (global column ids)."""
+
+    def __init__(self, fe, N, numbering, world, rank, upper_scale=1.0):
+        h = C.c_void_p()
+        check(lib().drops_b200_brick_slab_generate(int(fe), int(N), int(numbering), float(upper_scale), int(world),
+                                                   int(rank), C.byref(h)))
+        self.h = h
+        a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        k0, k1 = C.c_longlong(), C.c_longlong()
+        check(lib().drops_b200_brick_slab_info(h, C.byref(a), C.byref(b), C.byref(c), C.byref(k0), C.byref(k1)))
+        self.n_owned, self.nnz, self.n_ghost, self.k0, self.k1 = a.value, b.value, c.value, k0.value, k1.value
+        self.world, self.rank = int(world), int(rank)
+
+    def owned(self):
+        out = np.zeros(max(self.n_owned, 1), np.int64)
+        check(lib().drops_b200_brick_slab_owned(self.h, out))
+        return out[:self.n_owned]
+
+    def ghosts(self):
+        g, o = np.zeros(max(self.n_ghost, 1), np.int64), np.zeros(max(self.n_ghost, 1), np.int32)
+        check(lib().drops_b200_brick_slab_ghosts(self.h, g, o))
+        return g[:self.n_ghost], o[:self.n_ghost]
+
+    def exchange(self):
+        g, o = self.ghosts()
+        return Exchange(self.rank, self.world, self.owned(), g, o)
+
+    def matrix(self, comm, ex):
+        h = C.c_void_p()
+        check(lib().drops_b200_brick_slab_matrix(comm.h, ex.h, self.h, C.byref(h)))
+        return DistMatrix._wrap(h, comm, ex)
+
+    def solution(self, vec):
+        check(lib().drops_b200_brick_slab_solution(self.h, vec.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().drops_b200_brick_slab_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def brick_owner(fe, N, numbering, world, gids):
+    gids = _i64(gids)
+    out = np.zeros(max(gids.size, 1), np.int32)
+    check(lib().drops_b200_brick_owner(int(fe), int(N), int(numbering), int(world), gids.size, _nonempty(gids, np.int64), out))
+    return out[:gids.size]

@@ -17,8 +17,9 @@
 // matrix is generated from a small table (8 classes x <= 65 offsets) -- on the host for oracle
 // sized systems and by a kernel, directly into device CSR, for the 50 M / 400 M row systems.
 // Host and device use the same table and the same index functions, so they agree bit for bit.
-#include "common.cuh"
+#include "dist.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
@@ -262,6 +263,89 @@ __global__ void k_brick_xstar(BrickGeom g, long long n, double* __restrict__ x)
     x[dof_index(g, i, j, k)] = xstar_at(g, i, j, k);
 }
 
+
+// ---- z-slab partitions (multi-GPU) ---------------------------------------------------------------
+// Rank r of `world` owns the lattice planes [k0, k1): M planes split evenly.
+__host__ __device__ inline long long slab_begin(long long M, int world, int r) { return 1 + M * r / world; }
+
+__host__ __device__ inline int slab_owner(long long M, int world, long long k)
+{
+    int r = (int)(((k - 1) * world) / M);          // first guess, then fix the integer rounding
+    while (r > 0 && k < slab_begin(M, world, r)) --r;
+    while (r + 1 < world && k >= slab_begin(M, world, r + 1)) ++r;
+    return r;
+}
+
+// lattice plane k (1-based) of a global DOF id -- the inverse of dof_index as far as k goes
+__host__ __device__ inline long long plane_of_gid(const BrickGeom& g, long long gid)
+{
+    if (g.fe == 1 || g.numbering == 0) return gid / (g.M * g.M) + 1;
+    const long long nv3 = g.nv1 * g.nv1 * g.nv1;
+    if (gid < nv3) return 2 * (gid / (g.nv1 * g.nv1) + 1);
+    const long long e = gid - nv3;
+    const long long pair = 2 * g.M * g.M - g.nv1 * g.nv1;   // edge DOFs in an (odd, even) plane pair
+    const long long p = e / pair, rem = e % pair;
+    return rem < g.M * g.M ? 2 * p + 1 : 2 * p + 2;
+}
+
+__global__ void k_slab_gids(BrickGeom g, long long r0, long long n, int64_t* __restrict__ gid, int64_t* __restrict__ lat)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long long r = r0 + t;
+    const long long i = r % g.M + 1, j = (r / g.M) % g.M + 1, k = r / (g.M * g.M) + 1;
+    gid[t] = dof_index(g, i, j, k);
+    lat[t] = r;
+}
+
+__global__ void k_slab_count(BrickGeom g, const StencilTable* __restrict__ T, long long n, const int64_t* __restrict__ lat,
+                             int64_t* __restrict__ len)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long long r = lat[t];
+    const long long i = r % g.M + 1, j = (r / g.M) % g.M + 1, k = r / (g.M * g.M) + 1;
+    len[t] = emit_row<int64_t>(g, *T, i, j, k, 0, nullptr, nullptr);
+}
+
+__global__ void k_slab_fill(BrickGeom g, const StencilTable* __restrict__ T, long long n, const int64_t* __restrict__ lat,
+                            const int64_t* __restrict__ gid, const int64_t* __restrict__ rowptr,
+                            int64_t* __restrict__ col, double* __restrict__ val)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long long r = lat[t];
+    const long long i = r % g.M + 1, j = (r / g.M) % g.M + 1, k = r / (g.M * g.M) + 1;
+    const int64_t b = rowptr[t];
+    emit_row<int64_t>(g, *T, i, j, k, gid[t], col + b, val + b);
+}
+
+__global__ void k_slab_xstar(BrickGeom g, long long n, const int64_t* __restrict__ lat, double* __restrict__ x)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long long r = lat[t];
+    x[t] = xstar_at(g, r % g.M + 1, (r / g.M) % g.M + 1, r / (g.M * g.M) + 1);
+}
+
+}  // namespace db200
+
+struct drops_b200_brick_slab_s {
+    db200::BrickGeom g;
+    int world = 1, rank = 0;
+    long long k0 = 0, k1 = 0;
+    size_t n_owned = 0, nnz = 0;
+    int64_t* d_gid = nullptr;      // owned global ids, ascending
+    int64_t* d_lat = nullptr;      // lattice index of each owned row
+    int64_t* d_rowptr = nullptr;
+    int64_t* d_col = nullptr;      // global column ids
+    double* d_val = nullptr;
+    std::vector<int64_t> owned, ghost_gid;
+    std::vector<int32_t> ghost_owner;
+};
+
+namespace db200 {
+
 }  // namespace db200
 
 using namespace db200;
@@ -395,6 +479,153 @@ int drops_b200_brick_solution_device(int fe, int N, int numbering, drops_b200_ve
     k_brick_xstar<<<(int)((n + 255) / 256), 256, 0, ctx().stream>>>(g, n, xstar->d);
     count_launch();
     DB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int drops_b200_brick_slab_destroy(drops_b200_brick_slab_t S)
+{
+    if (!S) return 0;
+    if (ctx().inited) cudaStreamSynchronize(ctx().stream);
+    dev_free(S->d_gid); dev_free(S->d_lat); dev_free(S->d_rowptr); dev_free(S->d_col); dev_free(S->d_val);
+    delete S;
+    return 0;
+}
+
+int drops_b200_brick_slab_generate(int fe, int N, int numbering, double upper_scale, int world, int rank,
+                                   drops_b200_brick_slab_t* out)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(out != nullptr, "null out");
+    *out = nullptr;
+    DB_ARG(world >= 1 && rank >= 0 && rank < world, "rank/world out of range");
+    BrickGeom g;
+    DB_CHECK(make_geom(fe, N, numbering, upper_scale, &g));
+    DB_ARG(g.M >= world, "fewer lattice planes than ranks");
+    const StencilTable& T = stencil(fe);
+    cudaStream_t st = ctx().stream;
+    drops_b200_brick_slab_s* S = new drops_b200_brick_slab_s;
+    S->g = g; S->world = world; S->rank = rank;
+    S->k0 = slab_begin(g.M, world, rank);
+    S->k1 = rank + 1 == world ? g.M + 1 : slab_begin(g.M, world, rank + 1);
+    const long long n = (S->k1 - S->k0) * g.M * g.M;
+    S->n_owned = (size_t)n;
+    StencilTable* dT = nullptr; void* tmp = nullptr; int64_t* gid2 = nullptr; int64_t* lat2 = nullptr;
+    int s = 0;
+    auto cleanup = [&]() { dev_free(dT); dev_free(tmp); dev_free(gid2); dev_free(lat2); };
+#define SL_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); drops_b200_brick_slab_destroy(S); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
+#define SL_CHECK(call) do { s = (call); if (s < 0) { cleanup(); drops_b200_brick_slab_destroy(S); return s; } } while (0)
+    SL_CHECK(dev_alloc(&dT, 1));
+    SL_CUDA(cudaMemcpyAsync(dT, &T, sizeof T, cudaMemcpyHostToDevice, st));
+    SL_CHECK(dev_alloc(&S->d_gid, (size_t)n)); SL_CHECK(dev_alloc(&S->d_lat, (size_t)n));
+    const int threads = 256;
+    const int grid = (int)std::max<long long>(1, (n + threads - 1) / threads);
+    const long long r0 = (S->k0 - 1) * g.M * g.M;
+    k_slab_gids<<<grid, threads, 0, st>>>(g, r0, n, S->d_gid, S->d_lat);
+    count_launch();
+    if (fe == 2 && numbering == 1) {     // lattice order is not ascending in the DROPS numbering: sort
+        SL_CHECK(dev_alloc(&gid2, (size_t)n)); SL_CHECK(dev_alloc(&lat2, (size_t)n));
+        size_t tb = 0;
+        SL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, S->d_gid, gid2, S->d_lat, lat2, n, 0, 40, st));
+        SL_CHECK(dev_alloc((char**)&tmp, tb));
+        SL_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, S->d_gid, gid2, S->d_lat, lat2, n, 0, 40, st));
+        count_launch(4);
+        SL_CUDA(cudaStreamSynchronize(st));
+        std::swap(S->d_gid, gid2); std::swap(S->d_lat, lat2);
+        dev_free(gid2); gid2 = nullptr; dev_free(lat2); lat2 = nullptr; dev_free(tmp); tmp = nullptr;
+    }
+    SL_CHECK(dev_alloc(&S->d_rowptr, (size_t)n + 1));
+    SL_CUDA(cudaMemsetAsync(S->d_rowptr, 0, ((size_t)n + 1) * sizeof(int64_t), st));
+    k_slab_count<<<grid, threads, 0, st>>>(g, dT, n, S->d_lat, S->d_rowptr);
+    count_launch();
+    size_t tb = 0;
+    SL_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, S->d_rowptr, S->d_rowptr, n + 1, st));
+    SL_CHECK(dev_alloc((char**)&tmp, tb));
+    SL_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, S->d_rowptr, S->d_rowptr, n + 1, st));
+    count_launch(2);
+    int64_t nnz = 0;
+    SL_CUDA(cudaMemcpyAsync(&nnz, S->d_rowptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    SL_CUDA(cudaStreamSynchronize(st));
+    S->nnz = (size_t)nnz;
+    SL_CHECK(dev_alloc(&S->d_col, S->nnz)); SL_CHECK(dev_alloc(&S->d_val, S->nnz));
+    k_slab_fill<<<grid, threads, 0, st>>>(g, dT, n, S->d_lat, S->d_gid, S->d_rowptr, S->d_col, S->d_val);
+    count_launch();
+    SL_CUDA(cudaGetLastError());
+    S->owned.resize((size_t)n);
+    if (n) SL_CUDA(cudaMemcpyAsync(S->owned.data(), S->d_gid, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    SL_CUDA(cudaStreamSynchronize(st));
+    SL_CHECK(find_ghosts_device(S->n_owned, S->owned.data(), S->nnz, S->d_col, &S->ghost_gid));
+    S->ghost_owner.resize(S->ghost_gid.size());
+    for (size_t i = 0; i < S->ghost_gid.size(); ++i)
+        S->ghost_owner[i] = slab_owner(g.M, world, plane_of_gid(g, S->ghost_gid[i]));
+    cleanup();
+#undef SL_CUDA
+#undef SL_CHECK
+    *out = S;
+    return 0;
+}
+
+int drops_b200_brick_slab_info(drops_b200_brick_slab_t S, size_t* n_owned, size_t* nnz, size_t* n_ghost, long long* k0,
+                               long long* k1)
+{
+    DB_ARG(S != nullptr, "null slab");
+    if (n_owned) *n_owned = S->n_owned;
+    if (nnz) *nnz = S->nnz;
+    if (n_ghost) *n_ghost = S->ghost_gid.size();
+    if (k0) *k0 = S->k0;
+    if (k1) *k1 = S->k1;
+    return 0;
+}
+
+int drops_b200_brick_slab_owned(drops_b200_brick_slab_t S, int64_t* owned_gid)
+{
+    DB_ARG(S != nullptr && owned_gid != nullptr, "null argument");
+    std::copy(S->owned.begin(), S->owned.end(), owned_gid);
+    return 0;
+}
+
+int drops_b200_brick_slab_ghosts(drops_b200_brick_slab_t S, int64_t* ghost_gid, int32_t* ghost_owner)
+{
+    DB_ARG(S != nullptr, "null slab");
+    if (ghost_gid) std::copy(S->ghost_gid.begin(), S->ghost_gid.end(), ghost_gid);
+    if (ghost_owner) std::copy(S->ghost_owner.begin(), S->ghost_owner.end(), ghost_owner);
+    return 0;
+}
+
+int drops_b200_brick_slab_matrix(drops_b200_comm_t comm, drops_b200_exchange_t ex, drops_b200_brick_slab_t S,
+                                 drops_b200_dist_matrix_t* out)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(comm && ex && S && out, "null argument");
+    DB_ARG(S->d_col != nullptr, "the slab's rows were already consumed");
+    DB_ARG(ex->owned.size() == S->n_owned, "plan and slab disagree on the owned rows");
+    const int s = dist_matrix_build(comm, ex, S->nnz, S->d_rowptr, S->d_col, S->d_val, 1, out);
+    // the operator holds its own copy: release the 20 B/entry generator output
+    dev_free(S->d_rowptr); dev_free(S->d_col); dev_free(S->d_val);
+    S->d_rowptr = nullptr; S->d_col = nullptr; S->d_val = nullptr;
+    return s;
+}
+
+int drops_b200_brick_slab_solution(drops_b200_brick_slab_t S, drops_b200_vector_t xstar)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(S != nullptr && xstar != nullptr && xstar->n == S->n_owned, "vector size does not match the slab");
+    const long long n = (long long)S->n_owned;
+    if (n == 0) return 0;
+    k_slab_xstar<<<(int)((n + 255) / 256), 256, 0, ctx().stream>>>(S->g, n, S->d_lat, xstar->d);
+    count_launch();
+    DB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int drops_b200_brick_owner(int fe, int N, int numbering, int world, size_t count, const int64_t* gids, int32_t* owner)
+{
+    BrickGeom g;
+    DB_CHECK(make_geom(fe, N, numbering, 1.0, &g));
+    DB_ARG(world >= 1 && (count == 0 || (gids != nullptr && owner != nullptr)), "bad argument");
+    for (size_t i = 0; i < count; ++i) {
+        DB_ARG(gids[i] >= 0 && gids[i] < g.M * g.M * g.M, "global id outside the brick");
+        owner[i] = slab_owner(g.M, world, plane_of_gid(g, gids[i]));
+    }
     return 0;
 }
 

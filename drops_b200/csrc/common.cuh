@@ -337,4 +337,5 @@ double* work_vec(drops_b200_matrix_s* M, int i);
 void free_sell(SellOp& s);
 void free_csr(CsrDev& c);
 int build_transpose(drops_b200_matrix_s* M);
+int build_sell(const CsrDev& A, SellOp& S, size_t* bytes, const int32_t* rowmap, size_t nsub);
 }  // namespace db200

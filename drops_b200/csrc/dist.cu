@@ -1,0 +1,886 @@
+// dist.cu -- the row-partitioned hot path across the GPUs of one box.
+//
+// Per PCG iteration and rank (num/krylovsolver.h:149-176 on the partition):
+//   pack        boundary entries of p -> send buffer                         (k_pack, solver stream)
+//   halo        ncclSend/ncclRecv per neighbour, one group                   (comm stream)
+//   SpMV int.   rows that reference no ghost column, fused p.q partial       (solver stream, overlaps the halo)
+//   SpMV bnd.   rows with ghost columns, after the halo arrived; partial chained (dd, unrounded)
+//   allgather   1 double-double per rank; k_dist_scalars sums them in rank order -> lambda
+//   update      x += alpha p, r -= alpha q, partials of |r|^2 and z.r        (same kernel as on one GPU)
+//   allgather   2 double-doubles per rank; k_dist_scalars -> rho, resid, iter, stop flag
+//   direction   p = z + beta p
+// All scalars stay on the device; every rank sums the same partials in the same order, so the
+// stop decision is bit-identical on all ranks and no rank needs the host inside the loop.
+// The reference needs 3 MPI synchronisation points per iteration; this path
+// has 2 tiny all-gathers and 1 neighbour exchange.
+//
+// NCCL is bound at run time (dlopen of the libnccl.so.2 already in the process -- torch's -- or
+// the system one): libdrops_b200.so itself has no link-time dependency on it.
+#include "dist.cuh"
+#include "spmv.cuh"
+#include "vecops.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_reduce.cuh>
+#include <cub/device/device_select.cuh>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstring>
+
+namespace db200 {
+
+// ------------------------------------------------------------------------------------------
+// NCCL binding
+// ------------------------------------------------------------------------------------------
+struct NcclApi {
+    bool tried = false, ok = false;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+};
+
+static NcclApi& nccl()
+{
+    static NcclApi api;
+    if (api.tried) return api;
+    api.tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);   // already loaded (torch)?
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return api;
+#define DB_SYM(field, name) *(void**)(&api.field) = dlsym(h, name); if (!api.field) return api;
+    DB_SYM(GetUniqueId, "ncclGetUniqueId") DB_SYM(CommInitRank, "ncclCommInitRank") DB_SYM(CommDestroy, "ncclCommDestroy")
+    DB_SYM(GetErrorString, "ncclGetErrorString") DB_SYM(GroupStart, "ncclGroupStart") DB_SYM(GroupEnd, "ncclGroupEnd")
+    DB_SYM(Send, "ncclSend") DB_SYM(Recv, "ncclRecv") DB_SYM(AllGather, "ncclAllGather") DB_SYM(AllReduce, "ncclAllReduce")
+#undef DB_SYM
+    api.ok = true;
+    return api;
+}
+
+static int nccl_fail(ncclResult_t r, const char* what)
+{
+    set_error("NCCL error %d (%s) in %s", (int)r, nccl().GetErrorString ? nccl().GetErrorString(r) : "?", what);
+    return DROPS_B200_E_COMM;
+}
+#define DB_NCCL(call) do { ncclResult_t r__ = (call); if (r__ != ncclSuccess) return nccl_fail(r__, #call); } while (0)
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+struct OwnedRanges {            // device view of the plan's lookup tables
+    const int64_t* gid0; const int64_t* len; const int64_t* local0; int nranges;
+    const int64_t* ghost_sorted; const int32_t* ghost_slot; long long n_ghost;
+    long long n_owned;
+};
+
+__device__ __forceinline__ long long local_of(const OwnedRanges& R, int64_t gid)
+{
+    int lo = 0, hi = R.nranges;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (R.gid0[mid] + R.len[mid] <= gid) lo = mid + 1; else hi = mid;
+    }
+    if (lo < R.nranges && R.gid0[lo] <= gid) return R.local0[lo] + (gid - R.gid0[lo]);
+    long long a = 0, b = R.n_ghost;
+    while (a < b) {
+        const long long mid = (a + b) >> 1;
+        if (R.ghost_sorted[mid] < gid) a = mid + 1; else b = mid;
+    }
+    if (a < R.n_ghost && R.ghost_sorted[a] == gid) return R.n_owned + R.ghost_slot[a];
+    return -1;
+}
+
+// One thread per row: global column ids -> local int32 columns (entry order untouched), and the
+// row's class: interior (no ghost column) or boundary.
+__global__ void k_remap_rows(long long rows, const int64_t* __restrict__ rowptr, const int64_t* __restrict__ colgid,
+                             OwnedRanges R, int32_t* __restrict__ col, char* __restrict__ f_int,
+                             char* __restrict__ f_bnd, int* __restrict__ bad)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    bool bnd = false;
+    for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+        const long long l = local_of(R, colgid[k]);
+        if (l < 0) { atomicExch(bad, 1); col[k] = 0; continue; }
+        col[k] = (int32_t)l;
+        bnd |= (l >= R.n_owned);
+    }
+    f_int[i] = bnd ? 0 : 1;
+    f_bnd[i] = bnd ? 1 : 0;
+}
+
+__global__ void k_flag_not_owned(long long nnz, const int64_t* __restrict__ colgid, OwnedRanges R, char* __restrict__ flag)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nnz) return;
+    const int64_t gid = colgid[k];
+    int lo = 0, hi = R.nranges;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (R.gid0[mid] + R.len[mid] <= gid) lo = mid + 1; else hi = mid;
+    }
+    flag[k] = (lo < R.nranges && R.gid0[lo] <= gid) ? 0 : 1;
+}
+
+__global__ void k_iota32(long long n, int32_t* out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int32_t)i;
+}
+
+__global__ void k_pack(long long n, const int32_t* __restrict__ idx, const double* __restrict__ x, double* __restrict__ out,
+                       const int* done)
+{
+    if (done != nullptr && *done != 0) return;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = x[idx[i]];
+}
+
+enum ScalarPhase { PH_DOT = 0, PH_LAMBDA = 1, PH_SETUP = 2, PH_UPDATE = 3 };
+
+// Sums the ranks' partials in rank order (the same on every rank) and does the scalar bookkeeping
+// that the last block of the fused kernels does on a single GPU.
+__global__ void k_dist_scalars(int phase, SolverScalars* S, double* hist, const dd* __restrict__ gathered, int world,
+                               double* out)
+{
+    if (threadIdx.x != 0) return;
+    if ((phase == PH_LAMBDA || phase == PH_UPDATE) && S->done) return;
+    const int nq = phase == PH_SETUP ? 3 : (phase == PH_UPDATE ? 2 : 1);
+    dd acc[3] = {dd_zero(), dd_zero(), dd_zero()};
+    for (int r = 0; r < world; ++r)
+        for (int q = 0; q < nq; ++q) acc[q] = dd_add(acc[q], gathered[r * nq + q]);
+    if (phase == PH_DOT) *out = dd_round(acc[0]);
+    else if (phase == PH_LAMBDA) S->lambda = dd_round(acc[0]);
+    else if (phase == PH_SETUP) pcg_setup_finish(S, hist, dd_round(acc[0]), dd_round(acc[1]), dd_round(acc[2]));
+    else pcg_update_finish(S, hist, dd_round(acc[0]), dd_round(acc[1]));
+}
+
+__global__ void k_zero_dd(dd* p, int n)
+{
+    if (threadIdx.x < n) p[threadIdx.x] = dd_zero();
+}
+
+// ------------------------------------------------------------------------------------------
+// host helpers
+// ------------------------------------------------------------------------------------------
+static inline int blocks_for(long long n, int threads) { return (int)std::max<long long>(1, (n + threads - 1) / threads); }
+
+struct DevTables {     // device copies of the plan's lookup tables
+    int64_t *gid0 = nullptr, *len = nullptr, *local0 = nullptr, *ghost_sorted = nullptr;
+    int32_t* ghost_slot = nullptr;
+    OwnedRanges view{};
+    void release() { dev_free(gid0); dev_free(len); dev_free(local0); dev_free(ghost_sorted); dev_free(ghost_slot); }
+};
+
+static int upload_ranges(const std::vector<drops_b200_exchange_s::Range>& ranges, size_t n_owned,
+                         const std::vector<int64_t>* ghost_sorted, const std::vector<int32_t>* ghost_slot, DevTables* T)
+{
+    cudaStream_t st = ctx().stream;
+    const size_t nr = ranges.size();
+    std::vector<int64_t> a(nr), b(nr), c(nr);
+    for (size_t i = 0; i < nr; ++i) { a[i] = ranges[i].gid0; b[i] = ranges[i].len; c[i] = ranges[i].local0; }
+    DB_CHECK(dev_alloc(&T->gid0, nr)); DB_CHECK(dev_alloc(&T->len, nr)); DB_CHECK(dev_alloc(&T->local0, nr));
+    if (nr) {
+        DB_CUDA(cudaMemcpyAsync(T->gid0, a.data(), nr * 8, cudaMemcpyHostToDevice, st));
+        DB_CUDA(cudaMemcpyAsync(T->len, b.data(), nr * 8, cudaMemcpyHostToDevice, st));
+        DB_CUDA(cudaMemcpyAsync(T->local0, c.data(), nr * 8, cudaMemcpyHostToDevice, st));
+    }
+    const size_t ng = ghost_sorted ? ghost_sorted->size() : 0;
+    DB_CHECK(dev_alloc(&T->ghost_sorted, ng)); DB_CHECK(dev_alloc(&T->ghost_slot, ng));
+    if (ng) {
+        DB_CUDA(cudaMemcpyAsync(T->ghost_sorted, ghost_sorted->data(), ng * 8, cudaMemcpyHostToDevice, st));
+        DB_CUDA(cudaMemcpyAsync(T->ghost_slot, ghost_slot->data(), ng * 4, cudaMemcpyHostToDevice, st));
+    }
+    DB_CUDA(cudaStreamSynchronize(st));    // the host vectors above go out of scope
+    T->view = OwnedRanges{T->gid0, T->len, T->local0, (int)nr, T->ghost_sorted, T->ghost_slot, (long long)ng, (long long)n_owned};
+    return 0;
+}
+
+// Sorted unique non-owned column ids of device-resident rows (global ids) -> host vector.
+int find_ghosts_device(size_t n_owned, const int64_t* owned_host_sorted, size_t nnz, const int64_t* d_colgid,
+                       std::vector<int64_t>* out)
+{
+    out->clear();
+    if (nnz == 0) return 0;
+    cudaStream_t st = ctx().stream;
+    std::vector<drops_b200_exchange_s::Range> ranges;
+    for (size_t i = 0; i < n_owned;) {
+        size_t j = i + 1;
+        while (j < n_owned && owned_host_sorted[j] == owned_host_sorted[j - 1] + 1) ++j;
+        ranges.push_back({owned_host_sorted[i], (int64_t)(j - i), (int64_t)i});
+        i = j;
+    }
+    DevTables T;
+    int s = upload_ranges(ranges, n_owned, nullptr, nullptr, &T);
+    char* flag = nullptr; int64_t* cand = nullptr; int64_t* cand2 = nullptr; long long* d_cnt = nullptr; void* tmp = nullptr;
+    auto cleanup = [&]() { T.release(); dev_free(flag); dev_free(cand); dev_free(cand2); dev_free(d_cnt); dev_free(tmp); };
+#define FG_CHECK(call) do { s = (call); if (s < 0) { cleanup(); return s; } } while (0)
+#define FG_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
+    if (s < 0) { cleanup(); return s; }
+    FG_CHECK(dev_alloc(&flag, nnz));
+    FG_CHECK(dev_alloc(&d_cnt, 1));
+    k_flag_not_owned<<<blocks_for((long long)nnz, 256), 256, 0, st>>>((long long)nnz, d_colgid, T.view, flag);
+    count_launch();
+    // the candidates are a thin set (entries of boundary rows): count, then select exactly that many
+    long long ncand = 0;
+    size_t tb = 0;
+    FG_CUDA(cub::DeviceReduce::Sum(nullptr, tb, (const unsigned char*)flag, d_cnt, (long long)nnz, st));
+    FG_CHECK(dev_alloc((char**)&tmp, tb));
+    FG_CUDA(cub::DeviceReduce::Sum(tmp, tb, (const unsigned char*)flag, d_cnt, (long long)nnz, st));
+    FG_CUDA(cudaMemcpyAsync(&ncand, d_cnt, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    FG_CUDA(cudaStreamSynchronize(st));
+    dev_free(tmp); tmp = nullptr;
+    if (ncand > 0) {
+        FG_CHECK(dev_alloc(&cand, (size_t)ncand));
+        tb = 0;
+        FG_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, d_colgid, flag, cand, d_cnt, (long long)nnz, st));
+        FG_CHECK(dev_alloc((char**)&tmp, tb));
+        FG_CUDA(cub::DeviceSelect::Flagged(tmp, tb, d_colgid, flag, cand, d_cnt, (long long)nnz, st));
+        count_launch(2);
+        FG_CUDA(cudaStreamSynchronize(st));
+    }
+    dev_free(flag); flag = nullptr; dev_free(tmp); tmp = nullptr;
+    if (ncand > 0) {
+        FG_CHECK(dev_alloc(&cand2, (size_t)ncand));
+        tb = 0;
+        FG_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, cand, cand2, ncand, 0, 64, st));
+        FG_CHECK(dev_alloc((char**)&tmp, tb));
+        FG_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tb, cand, cand2, ncand, 0, 64, st));
+        dev_free(tmp); tmp = nullptr;
+        tb = 0;
+        FG_CUDA(cub::DeviceSelect::Unique(nullptr, tb, cand2, cand, d_cnt, ncand, st));
+        FG_CHECK(dev_alloc((char**)&tmp, tb));
+        FG_CUDA(cub::DeviceSelect::Unique(tmp, tb, cand2, cand, d_cnt, ncand, st));
+        count_launch(4);
+        long long nuniq = 0;
+        FG_CUDA(cudaMemcpyAsync(&nuniq, d_cnt, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        FG_CUDA(cudaStreamSynchronize(st));
+        out->resize((size_t)nuniq);
+        if (nuniq) FG_CUDA(cudaMemcpyAsync(out->data(), cand, (size_t)nuniq * 8, cudaMemcpyDeviceToHost, st));
+        FG_CUDA(cudaStreamSynchronize(st));
+    }
+    cleanup();
+#undef FG_CHECK
+#undef FG_CUDA
+    return 0;
+}
+
+static void free_dist_matrix(drops_b200_dist_matrix_s* M)
+{
+    if (!M) return;
+    if (ctx().inited) { cudaStreamSynchronize(ctx().stream); if (M->comm && M->comm->comm_stream) cudaStreamSynchronize(M->comm->comm_stream); }
+    if (M->comm && M->comm->kind == COMM_LOCAL && M->rank < (int)M->comm->parts.size() && M->comm->parts[(size_t)M->rank] == M)
+        M->comm->parts[(size_t)M->rank] = nullptr;
+    free_sell(M->sell_int); free_sell(M->sell_bnd);
+    dev_free(M->diag); dev_free(M->ghost); dev_free(M->sendbuf); dev_free(M->d_send_idx);
+    for (double* w : M->work) dev_free(w);
+    dev_free(M->d_scalars); dev_free(M->d_hist);
+    delete M;
+}
+
+static double* dwork(drops_b200_dist_matrix_s* M, int i)
+{
+    if ((int)M->work.size() <= i) M->work.resize((size_t)i + 1, nullptr);
+    if (!M->work[(size_t)i] && dev_alloc(&M->work[(size_t)i], M->n_owned) < 0) return nullptr;
+    return M->work[(size_t)i];
+}
+
+__global__ void k_extract_diag_local(long long rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                     const double* __restrict__ val, double* __restrict__ diag, int* __restrict__ missing)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    int64_t k = rowptr[i];
+    const int64_t e = rowptr[i + 1];
+    while (k < e && col[k] != (int32_t)i) ++k;
+    if (k < e) diag[i] = val[k];
+    else { diag[i] = 0.0; atomicExch(missing, 1); }
+}
+
+// Builds the partition operator from device-resident rows with global column ids.
+int dist_matrix_build(drops_b200_comm_s* comm, drops_b200_exchange_s* E, size_t nnz, const int64_t* d_rowptr,
+                      const int64_t* d_colgid, const double* d_val, uint64_t version, drops_b200_dist_matrix_s** out)
+{
+    *out = nullptr;
+    DB_ARG(comm != nullptr && E != nullptr, "null comm/exchange");
+    DB_ARG(E->world == comm->world, "plan and communicator disagree on the number of ranks");
+    DB_ARG(comm->kind == COMM_LOCAL || E->rank == comm->rank, "plan was built for another rank");
+    for (int q = 0; q < E->world; ++q)
+        DB_ARG(E->send_set[(size_t)q], "halo plan is not ready: exchange_set_send is missing for a peer");
+    cudaStream_t st = ctx().stream;
+    const size_t n = E->owned.size(), ng = E->ghost_gid.size();
+    drops_b200_dist_matrix_s* M = new drops_b200_dist_matrix_s;
+    M->comm = comm; M->rank = E->rank; M->world = E->world;
+    M->n_owned = n; M->n_ghost = ng; M->nnz = nnz; M->version = version;
+    DevTables T;
+    int32_t* col = nullptr; char* f_int = nullptr; char* f_bnd = nullptr; int* d_flag = nullptr;
+    int32_t *rows_all = nullptr, *rows_int = nullptr, *rows_bnd = nullptr; long long* d_cnt = nullptr; void* tmp = nullptr;
+    int s = 0;
+    auto cleanup = [&]() {
+        T.release(); dev_free(col); dev_free(f_int); dev_free(f_bnd); dev_free(d_flag); dev_free(rows_all);
+        dev_free(rows_int); dev_free(rows_bnd); dev_free(d_cnt); dev_free(tmp);
+    };
+#define DM_CHECK(call) do { s = (call); if (s < 0) { cleanup(); free_dist_matrix(M); return s; } } while (0)
+#define DM_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); free_dist_matrix(M); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
+    DM_CHECK(upload_ranges(E->ranges, n, &E->ghost_sorted, &E->ghost_sorted_slot, &T));
+    DM_CHECK(dev_alloc(&col, nnz));
+    DM_CHECK(dev_alloc(&f_int, n)); DM_CHECK(dev_alloc(&f_bnd, n));
+    DM_CHECK(dev_alloc(&d_flag, 2));
+    DM_CUDA(cudaMemsetAsync(d_flag, 0, 2 * sizeof(int), st));
+    if (n > 0) {
+        k_remap_rows<<<blocks_for((long long)n, 128), 128, 0, st>>>((long long)n, d_rowptr, d_colgid, T.view, col, f_int, f_bnd, d_flag);
+        count_launch();
+        DM_CUDA(cudaGetLastError());
+    }
+    // diagonal (local column of an owned DOF == its local row)
+    DM_CHECK(dev_alloc(&M->diag, n));
+    if (n > 0) {
+        k_extract_diag_local<<<blocks_for((long long)n, 256), 256, 0, st>>>((long long)n, d_rowptr, col, d_val, M->diag, d_flag + 1);
+        count_launch();
+    }
+    int hflag[2] = {0, 0};
+    DM_CUDA(cudaMemcpyAsync(hflag, d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    DM_CUDA(cudaStreamSynchronize(st));
+    if (hflag[0]) {
+        cleanup(); free_dist_matrix(M);
+        set_error("dist_matrix: a column id is neither owned nor in the plan's ghost list");
+        return DROPS_B200_E_ARG;
+    }
+    M->diag_ok = (hflag[1] == 0);
+    // interior / boundary row lists
+    DM_CHECK(dev_alloc(&rows_all, n)); DM_CHECK(dev_alloc(&rows_int, n)); DM_CHECK(dev_alloc(&rows_bnd, n));
+    DM_CHECK(dev_alloc(&d_cnt, 2));
+    long long cnt[2] = {0, 0};
+    if (n > 0) {
+        k_iota32<<<blocks_for((long long)n, 256), 256, 0, st>>>((long long)n, rows_all);
+        size_t tb = 0;
+        DM_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, rows_all, f_int, rows_int, d_cnt, (long long)n, st));
+        DM_CHECK(dev_alloc((char**)&tmp, tb));
+        DM_CUDA(cub::DeviceSelect::Flagged(tmp, tb, rows_all, f_int, rows_int, d_cnt, (long long)n, st));
+        DM_CUDA(cub::DeviceSelect::Flagged(tmp, tb, rows_all, f_bnd, rows_bnd, d_cnt + 1, (long long)n, st));
+        count_launch(3);
+        DM_CUDA(cudaMemcpyAsync(cnt, d_cnt, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        DM_CUDA(cudaStreamSynchronize(st));
+    }
+    M->n_int = (size_t)cnt[0]; M->n_bnd = (size_t)cnt[1];
+    CsrDev A;   // aliases the caller's arrays; only the int32 columns are ours
+    A.rows = n; A.cols = n + ng; A.nnz = nnz;
+    A.rowptr = const_cast<int64_t*>(d_rowptr); A.col = col; A.val = const_cast<double*>(d_val);
+    M->device_bytes = n * 8;
+    DM_CHECK(build_sell(A, M->sell_int, &M->device_bytes, rows_int, M->n_int));
+    DM_CHECK(build_sell(A, M->sell_bnd, &M->device_bytes, rows_bnd, M->n_bnd));
+    // halo buffers
+    M->recv_off = E->recv_off;
+    M->send_off.assign((size_t)E->world + 1, 0);
+    std::vector<int32_t> flat;
+    for (int q = 0; q < E->world; ++q) {
+        flat.insert(flat.end(), E->send_idx[(size_t)q].begin(), E->send_idx[(size_t)q].end());
+        M->send_off[(size_t)q + 1] = flat.size();
+    }
+    M->n_send = flat.size();
+    DM_CHECK(dev_alloc(&M->d_send_idx, M->n_send));
+    DM_CHECK(dev_alloc(&M->sendbuf, M->n_send));
+    DM_CHECK(dev_alloc(&M->ghost, ng));
+    if (M->n_send) DM_CUDA(cudaMemcpyAsync(M->d_send_idx, flat.data(), M->n_send * 4, cudaMemcpyHostToDevice, st));
+    DM_CUDA(cudaMemsetAsync(M->ghost, 0, std::max<size_t>(ng, 1) * 8, st));
+    DM_CUDA(cudaStreamSynchronize(st));
+    M->device_bytes += (M->n_send + ng) * 8 + M->n_send * 4;
+    cleanup();
+#undef DM_CHECK
+#undef DM_CUDA
+    if (comm->kind == COMM_LOCAL) {
+        if ((int)comm->parts.size() < comm->world) comm->parts.resize((size_t)comm->world, nullptr);
+        comm->parts[(size_t)M->rank] = M;
+    }
+    *out = M;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// collective building blocks
+// ------------------------------------------------------------------------------------------
+struct PartArgs {
+    const double* x = nullptr; double* y = nullptr;
+    int epilogue = EPI_NONE; const double* aux = nullptr; double omega = 1.0;
+    const double* dotv = nullptr;       // fused dot partner (local partial -> gathered slot)
+    const int* done = nullptr;
+};
+
+static int check_parts(int np, drops_b200_dist_matrix_s* const* P)
+{
+    DB_ARG(np >= 1 && P != nullptr && P[0] != nullptr, "no partitions");
+    drops_b200_comm_s* comm = P[0]->comm;
+    DB_ARG(comm != nullptr, "partition without communicator");
+    if (comm->kind == COMM_NCCL) DB_ARG(np == 1, "an NCCL communicator drives exactly one partition per process");
+    else DB_ARG(np == comm->world, "a local communicator drives all `world` partitions in one call");
+    for (int p = 0; p < np; ++p) {
+        DB_ARG(P[p] != nullptr && P[p]->comm == comm, "partitions of different communicators");
+        DB_ARG(comm->kind == COMM_NCCL || P[p]->rank == p, "partitions must be ordered by rank");
+    }
+    return 0;
+}
+
+// slot of partition p's reduction partials in the rank-major gather buffer
+static inline dd* gather_slot(drops_b200_dist_matrix_s* M, int nq) { return M->comm->gathered + (size_t)M->rank * nq; }
+
+static int allgather_partials(drops_b200_comm_s* comm, int nq)
+{
+    if (comm->kind == COMM_NCCL && comm->world > 1) {
+        ScopedTiming t("allgather");
+        DB_NCCL(nccl().AllGather(comm->gathered + (size_t)comm->rank * nq, comm->gathered, (size_t)nq * 2, ncclDouble,
+                                 (ncclComm_t)comm->nccl, ctx().stream));
+    }
+    return 0;
+}
+
+static int halo_exchange(int np, drops_b200_dist_matrix_s* const* P, const PartArgs* a)
+{
+    drops_b200_comm_s* comm = P[0]->comm;
+    if (comm->world == 1) return 0;
+    cudaStream_t st = ctx().stream, cs = comm->comm_stream;
+    {
+        ScopedTiming t("halo.pack");
+        for (int p = 0; p < np; ++p)
+            if (P[p]->n_send) {
+                k_pack<<<blocks_for((long long)P[p]->n_send, 256), 256, 0, st>>>((long long)P[p]->n_send, P[p]->d_send_idx,
+                                                                                a[p].x, P[p]->sendbuf, a[p].done);
+                count_launch();
+            }
+    }
+    DB_CUDA(cudaGetLastError());
+    DB_CUDA(cudaEventRecord(comm->ev_pack, st));
+    DB_CUDA(cudaStreamWaitEvent(cs, comm->ev_pack, 0));
+    if (comm->kind == COMM_NCCL) {
+        drops_b200_dist_matrix_s* M = P[0];
+        DB_NCCL(nccl().GroupStart());
+        for (int q = 0; q < comm->world; ++q) {
+            const size_t ns = M->send_off[(size_t)q + 1] - M->send_off[(size_t)q];
+            const size_t nr = M->recv_off[(size_t)q + 1] - M->recv_off[(size_t)q];
+            if (ns) DB_NCCL(nccl().Send(M->sendbuf + M->send_off[(size_t)q], ns, ncclDouble, q, (ncclComm_t)comm->nccl, cs));
+            if (nr) DB_NCCL(nccl().Recv(M->ghost + M->recv_off[(size_t)q], nr, ncclDouble, q, (ncclComm_t)comm->nccl, cs));
+        }
+        DB_NCCL(nccl().GroupEnd());
+    } else {
+        for (int r = 0; r < np; ++r)
+            for (int q = 0; q < np; ++q) {
+                const size_t nr = P[r]->recv_off[(size_t)q + 1] - P[r]->recv_off[(size_t)q];
+                if (!nr) continue;
+                const size_t ns = P[q]->send_off[(size_t)r + 1] - P[q]->send_off[(size_t)r];
+                DB_ARG(ns == nr, "send and receive lists of two partitions do not match");
+                DB_CUDA(cudaMemcpyAsync(P[r]->ghost + P[r]->recv_off[(size_t)q], P[q]->sendbuf + P[q]->send_off[(size_t)r],
+                                        nr * 8, cudaMemcpyDeviceToDevice, cs));
+            }
+    }
+    DB_CUDA(cudaEventRecord(comm->ev_halo, cs));
+    return 0;
+}
+
+// y = epilogue(A x) on every partition; with a[p].dotv the local partial of y.dotv goes to the
+// partition's gather slot (1 dd per rank) -- the caller all-gathers.
+static int dist_spmv_run(int np, drops_b200_dist_matrix_s* const* P, const PartArgs* a)
+{
+    drops_b200_comm_s* comm = P[0]->comm;
+    cudaStream_t st = ctx().stream;
+    DB_CHECK(halo_exchange(np, P, a));
+    for (int p = 0; p < np; ++p) {
+        drops_b200_dist_matrix_s* M = P[p];
+        if (a[p].dotv && M->n_int == 0 && M->n_bnd == 0) {
+            k_zero_dd<<<1, 32, 0, st>>>(gather_slot(M, 1), 1);
+            count_launch();
+        }
+        if (M->n_int == 0) continue;
+        ScopedTiming t("spmv");
+        SpmvArgs s;
+        s.x = a[p].x; s.y = a[p].y; s.epilogue = a[p].epilogue; s.aux = a[p].aux; s.omega = a[p].omega; s.done = a[p].done;
+        if (a[p].dotv) { s.dotv = a[p].dotv; s.dd_out = M->n_bnd ? (dd*)M->d_scalars + 32 : gather_slot(M, 1); }
+        DB_CHECK(spmv_sell(M->sell_int, s));
+    }
+    if (comm->world > 1) DB_CUDA(cudaStreamWaitEvent(st, comm->ev_halo, 0));
+    for (int p = 0; p < np; ++p) {
+        drops_b200_dist_matrix_s* M = P[p];
+        if (M->n_bnd == 0) continue;
+        ScopedTiming t("spmv.bnd");
+        SpmvArgs s;
+        s.x = a[p].x; s.y = a[p].y; s.epilogue = a[p].epilogue; s.aux = a[p].aux; s.omega = a[p].omega; s.done = a[p].done;
+        s.xghost = M->ghost; s.n_owned = (long long)M->n_owned;
+        if (a[p].dotv) { s.dotv = a[p].dotv; s.dd_in = M->n_int ? (dd*)M->d_scalars + 32 : nullptr; s.dd_out = gather_slot(M, 1); }
+        DB_CHECK(spmv_sell(M->sell_bnd, s));
+    }
+    return 0;
+}
+
+static int ensure_part_scalars(drops_b200_dist_matrix_s* M, int hist_cap)
+{
+    // SolverScalars followed by scratch: dd partial at +32 dd (chained interior/boundary dot)
+    if (!M->d_scalars) {
+        char* raw = nullptr;
+        DB_CHECK(dev_alloc(&raw, 4096));
+        DB_CUDA(cudaMemsetAsync(raw, 0, 4096, ctx().stream));
+        M->d_scalars = raw;
+    }
+    if (hist_cap > M->hist_alloc) {
+        dev_free(M->d_hist); M->d_hist = nullptr; M->hist_alloc = 0;
+        DB_CHECK(dev_alloc(&M->d_hist, (size_t)hist_cap));
+        M->hist_alloc = hist_cap;
+    }
+    return 0;
+}
+static_assert(sizeof(SolverScalars) <= 32 * sizeof(dd), "scratch offset inside the scalar block");
+
+static int scalars_kernel(int phase, drops_b200_dist_matrix_s* M, double* hist, double* out)
+{
+    k_dist_scalars<<<1, 32, 0, ctx().stream>>>(phase, (SolverScalars*)M->d_scalars, hist, M->comm->gathered, M->world, out);
+    count_launch();
+    DB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int dist_pcg(int np, drops_b200_dist_matrix_s* const* P, double* const* x, const double* const* b, int pc, double omega,
+             int* max_iter, double* tol, int relative, double* hist, int hist_cap)
+{
+    DB_CHECK(check_parts(np, P));
+    DB_ARG(max_iter && tol, "null max_iter/tol");
+    DB_ARG(pc == DROPS_B200_PC_DUMMY || pc == DROPS_B200_PC_JACOBI, "unknown preconditioner");
+    Ctx& c = ctx();
+    cudaStream_t st = c.stream;
+    drops_b200_comm_s* comm = P[0]->comm;
+    const int want_hist = hist ? std::max(hist_cap, 0) : 0;
+    std::vector<double*> r(np), pv(np), q(np);
+    std::vector<SolverScalars*> S(np);
+    SolverScalars h;
+    std::memset(&h, 0, sizeof h);
+    h.tol = *tol; h.relative = relative; h.max_iter = *max_iter; h.pc = pc; h.omega = omega; h.hist_cap = want_hist;
+    // Jacobi needs a stored diagonal on EVERY rank: agree through the gather buffer of a dot-like phase
+    int diag_bad = 0;
+    for (int p = 0; p < np; ++p) {
+        if (pc == DROPS_B200_PC_JACOBI && !P[p]->diag_ok) diag_bad = 1;
+        DB_CHECK(ensure_part_scalars(P[p], std::max(want_hist, 1)));
+        S[p] = (SolverScalars*)P[p]->d_scalars;
+        r[p] = dwork(P[p], 0); pv[p] = dwork(P[p], 1); q[p] = dwork(P[p], 2);
+        if (!r[p] || !pv[p] || !q[p]) return DROPS_B200_E_NOMEM;
+        DB_CUDA(cudaMemcpyAsync(S[p], &h, sizeof h, cudaMemcpyHostToDevice, st));
+    }
+    {
+        double flag = diag_bad;
+        DB_CHECK(drops_b200_comm_allreduce_max(comm, &flag));
+        if (flag != 0.0) {
+            set_error("JACPcCL: at least one row (on some rank) stores no diagonal entry");
+            return DROPS_B200_E_NODIAG;
+        }
+    }
+    double* dh = want_hist ? P[0]->d_hist : nullptr;
+    std::vector<PartArgs> a(np);
+
+    // r = b - A x; setup partials; scalars
+    for (int p = 0; p < np; ++p) { a[p] = PartArgs(); a[p].x = x[p]; a[p].y = r[p]; a[p].epilogue = EPI_RESID; a[p].aux = b[p]; }
+    DB_CHECK(dist_spmv_run(np, P, a.data()));
+    for (int p = 0; p < np; ++p)
+        DB_CHECK(pcg_setup(P[p]->n_owned, r[p], b[p], P[p]->diag, pv[p], S[p], nullptr, gather_slot(P[p], 3)));
+    DB_CHECK(allgather_partials(comm, 3));
+    for (int p = 0; p < np; ++p) DB_CHECK(scalars_kernel(PH_SETUP, P[p], p == 0 ? dh : nullptr, nullptr));
+
+    int check_every = (int)opt("pcg.check_every", 16.0);
+    if (check_every < 1) check_every = 1;
+    struct Flags { int iter, done, converged, pad; };
+    Flags* hflags = reinterpret_cast<Flags*>(c.h_scalars + 16);
+    cudaEvent_t ev[2];
+    DB_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    DB_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    int status = 0, launched = 0, chunk_id = 0;
+    bool finished = false;
+    const int total = std::max(*max_iter, 0);
+    auto enqueue_flag_read = [&](int slot) -> int {
+        DB_CUDA(cudaMemcpyAsync(&hflags[slot], &S[0]->iter, sizeof(Flags), cudaMemcpyDeviceToHost, st));
+        DB_CUDA(cudaEventRecord(ev[slot], st));
+        return 0;
+    };
+    auto iteration = [&]() -> int {
+        for (int p = 0; p < np; ++p) {
+            a[p] = PartArgs(); a[p].x = pv[p]; a[p].y = q[p]; a[p].dotv = pv[p]; a[p].done = &S[p]->done;
+        }
+        DB_CHECK(dist_spmv_run(np, P, a.data()));                                     // q = A p, partial p.q
+        DB_CHECK(allgather_partials(comm, 1));
+        for (int p = 0; p < np; ++p) DB_CHECK(scalars_kernel(PH_LAMBDA, P[p], nullptr, nullptr));
+        for (int p = 0; p < np; ++p)
+            DB_CHECK(pcg_update(P[p]->n_owned, x[p], r[p], pv[p], q[p], P[p]->diag, S[p], nullptr, gather_slot(P[p], 2)));
+        DB_CHECK(allgather_partials(comm, 2));
+        for (int p = 0; p < np; ++p) DB_CHECK(scalars_kernel(PH_UPDATE, P[p], p == 0 ? dh : nullptr, nullptr));
+        for (int p = 0; p < np; ++p) DB_CHECK(pcg_direction(P[p]->n_owned, pv[p], r[p], P[p]->diag, S[p]));
+        return 0;
+    };
+    status = enqueue_flag_read(0);
+    chunk_id = 1;
+    while (status == 0 && !finished) {
+        const int chunk = std::min(check_every, total - launched);
+        for (int k = 0; k < chunk && status == 0; ++k) status = iteration();
+        launched += chunk;
+        if (status != 0) break;
+        const int slot = chunk_id & 1;
+        status = enqueue_flag_read(slot);
+        if (status != 0) break;
+        const int prev = slot ^ 1;
+        cudaError_t e = cudaEventSynchronize(ev[prev]);
+        if (e != cudaSuccess) { status = cuda_fail(e, "event sync", __FILE__, __LINE__); break; }
+        if (hflags[prev].done || launched >= total) {
+            e = cudaEventSynchronize(ev[slot]);
+            if (e != cudaSuccess) { status = cuda_fail(e, "event sync", __FILE__, __LINE__); break; }
+            if (hflags[slot].done || launched >= total) finished = true;
+        }
+        ++chunk_id;
+    }
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    if (status != 0) { cudaStreamSynchronize(st); return status; }
+    DB_CUDA(cudaMemcpyAsync(&h, S[0], sizeof h, cudaMemcpyDeviceToHost, st));
+    DB_CUDA(cudaStreamSynchronize(st));
+    if (comm->comm_stream) DB_CUDA(cudaStreamSynchronize(comm->comm_stream));
+    if (hist && want_hist > 0) {
+        const int cnt = std::min(want_hist, h.iter + 1);
+        DB_CUDA(cudaMemcpyAsync(hist, P[0]->d_hist, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
+        DB_CUDA(cudaStreamSynchronize(st));
+    }
+    *tol = h.resid;
+    if (h.converged) *max_iter = h.iter;
+    return h.converged ? 1 : 0;
+}
+
+}  // namespace db200
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+using namespace db200;
+
+extern "C" {
+
+int drops_b200_comm_unique_id(void* id_bytes)
+{
+    DB_ARG(id_bytes != nullptr, "null id buffer");
+    static_assert(sizeof(ncclUniqueId) <= DROPS_B200_UNIQUE_ID_BYTES, "unique id size");
+    if (!nccl().ok) { set_error("libnccl.so.2 could not be loaded"); return DROPS_B200_E_COMM; }
+    ncclUniqueId id;
+    DB_NCCL(nccl().GetUniqueId(&id));
+    std::memset(id_bytes, 0, DROPS_B200_UNIQUE_ID_BYTES);
+    std::memcpy(id_bytes, &id, sizeof id);
+    return 0;
+}
+
+static int comm_common(drops_b200_comm_s* C)
+{
+    int prio_lo = 0, prio_hi = 0;      // the halo must not queue behind the interior-row SpMV
+    DB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    DB_CUDA(cudaStreamCreateWithPriority(&C->comm_stream, cudaStreamNonBlocking, prio_hi));
+    DB_CUDA(cudaEventCreateWithFlags(&C->ev_pack, cudaEventDisableTiming));
+    DB_CUDA(cudaEventCreateWithFlags(&C->ev_halo, cudaEventDisableTiming));
+    DB_CHECK(dev_alloc(&C->gathered, (size_t)C->world * kMaxQ));
+    DB_CUDA(cudaMemset(C->gathered, 0, (size_t)C->world * kMaxQ * sizeof(dd)));
+    return 0;
+}
+
+int drops_b200_comm_create(int rank, int world, const void* id_bytes, drops_b200_comm_t* out)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(out != nullptr, "null out");
+    *out = nullptr;
+    DB_ARG(world >= 1 && rank >= 0 && rank < world, "rank/world out of range");
+    drops_b200_comm_s* C = new drops_b200_comm_s;
+    C->kind = COMM_NCCL; C->rank = rank; C->world = world;
+    int s = comm_common(C);
+    if (s == 0 && world > 1) {
+        if (!id_bytes) { set_error("comm_create: unique id required for world > 1"); s = DROPS_B200_E_ARG; }
+        else if (!nccl().ok) { set_error("libnccl.so.2 could not be loaded"); s = DROPS_B200_E_COMM; }
+        else {
+            ncclUniqueId id;
+            std::memcpy(&id, id_bytes, sizeof id);
+            ncclComm_t nc = nullptr;
+            ncclResult_t r = nccl().CommInitRank(&nc, world, id, rank);
+            if (r != ncclSuccess) s = nccl_fail(r, "ncclCommInitRank");
+            C->nccl = nc;
+        }
+    }
+    if (s < 0) { drops_b200_comm_destroy(C); return s; }
+    *out = C;
+    return 0;
+}
+
+int drops_b200_comm_create_local(int world, drops_b200_comm_t* out)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(out != nullptr && world >= 1, "bad argument");
+    drops_b200_comm_s* C = new drops_b200_comm_s;
+    C->kind = COMM_LOCAL; C->rank = 0; C->world = world;
+    C->parts.assign((size_t)world, nullptr);
+    const int s = comm_common(C);
+    if (s < 0) { drops_b200_comm_destroy(C); *out = nullptr; return s; }
+    *out = C;
+    return 0;
+}
+
+int drops_b200_comm_destroy(drops_b200_comm_t C)
+{
+    if (!C) return 0;
+    if (ctx().inited) {
+        cudaStreamSynchronize(ctx().stream);
+        if (C->comm_stream) cudaStreamSynchronize(C->comm_stream);
+    }
+    if (C->nccl && nccl().ok) nccl().CommDestroy((ncclComm_t)C->nccl);
+    if (C->ev_pack) cudaEventDestroy(C->ev_pack);
+    if (C->ev_halo) cudaEventDestroy(C->ev_halo);
+    if (C->comm_stream) cudaStreamDestroy(C->comm_stream);
+    dev_free(C->gathered);
+    delete C;
+    return 0;
+}
+
+int drops_b200_comm_info(drops_b200_comm_t C, int* rank, int* world, int* is_local)
+{
+    DB_ARG(C != nullptr, "null comm");
+    if (rank) *rank = C->rank;
+    if (world) *world = C->world;
+    if (is_local) *is_local = C->kind == COMM_LOCAL;
+    return 0;
+}
+
+int drops_b200_comm_allreduce_max(drops_b200_comm_t C, double* value)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(C != nullptr && value != nullptr, "null argument");
+    Ctx& c = ctx();
+    DB_CUDA(cudaStreamSynchronize(c.stream));
+    if (C->kind == COMM_LOCAL || C->world == 1) return 0;
+    double* d = c.scratch_scalars + 8;
+    DB_CUDA(cudaMemcpyAsync(d, value, sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    DB_NCCL(nccl().AllReduce(d, d, 1, ncclDouble, ncclMax, (ncclComm_t)C->nccl, c.stream));
+    DB_CUDA(cudaMemcpyAsync(value, d, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    DB_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int drops_b200_dist_matrix_create_device(drops_b200_comm_t comm, drops_b200_exchange_t ex, size_t nnz,
+                                         const int64_t* d_rowptr, const int64_t* d_colind_global, const double* d_val,
+                                         uint64_t version, drops_b200_dist_matrix_t* out)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(out != nullptr && d_rowptr != nullptr, "null argument");
+    DB_ARG(nnz == 0 || (d_colind_global != nullptr && d_val != nullptr), "null colind/val");
+    return dist_matrix_build(comm, ex, nnz, d_rowptr, d_colind_global, d_val, version, out);
+}
+
+int drops_b200_dist_matrix_create(drops_b200_comm_t comm, drops_b200_exchange_t ex, size_t nnz, const size_t* rowbeg,
+                                  const size_t* colind_global, const double* val, uint64_t version,
+                                  drops_b200_dist_matrix_t* out)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(out != nullptr && ex != nullptr && rowbeg != nullptr, "null argument");
+    DB_ARG(nnz == 0 || (colind_global != nullptr && val != nullptr), "null colind/val");
+    const size_t n = ex->owned.size();
+    DB_ARG(rowbeg[0] == 0 && rowbeg[n] == nnz, "rowbeg[0] != 0 or rowbeg[n_owned] != nnz");
+    cudaStream_t st = ctx().stream;
+    int64_t *rp = nullptr, *cg = nullptr; double* v = nullptr;
+    int s;
+    if ((s = dev_alloc(&rp, n + 1)) < 0 || (s = dev_alloc(&cg, nnz)) < 0 || (s = dev_alloc(&v, nnz)) < 0) {
+        dev_free(rp); dev_free(cg); dev_free(v);
+        return s;
+    }
+    static_assert(sizeof(size_t) == sizeof(int64_t), "size_t must be 64 bit");
+    cudaError_t e = cudaMemcpyAsync(rp, rowbeg, (n + 1) * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(cg, colind_global, nnz * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(v, val, nnz * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) s = cuda_fail(e, "partition upload", __FILE__, __LINE__);
+    else s = dist_matrix_build(comm, ex, nnz, rp, cg, v, version, out);
+    dev_free(rp); dev_free(cg); dev_free(v);
+    return s;
+}
+
+int drops_b200_dist_matrix_destroy(drops_b200_dist_matrix_t A)
+{
+    free_dist_matrix(A);
+    return 0;
+}
+
+int drops_b200_dist_matrix_info(drops_b200_dist_matrix_t A, size_t* n_owned, size_t* n_ghost, size_t* nnz,
+                                size_t* interior_rows, size_t* boundary_rows, size_t* n_send, size_t* device_bytes)
+{
+    DB_ARG(A != nullptr, "null matrix");
+    if (n_owned) *n_owned = A->n_owned;
+    if (n_ghost) *n_ghost = A->n_ghost;
+    if (nnz) *nnz = A->nnz;
+    if (interior_rows) *interior_rows = A->n_int;
+    if (boundary_rows) *boundary_rows = A->n_bnd;
+    if (n_send) *n_send = A->n_send;
+    if (device_bytes) *device_bytes = A->device_bytes;
+    return 0;
+}
+
+int drops_b200_dist_matrix_diag(drops_b200_dist_matrix_t A, double* diag)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(A != nullptr && diag != nullptr, "null argument");
+    if (A->n_owned) DB_CUDA(cudaMemcpyAsync(diag, A->diag, A->n_owned * 8, cudaMemcpyDeviceToHost, ctx().stream));
+    DB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return 0;
+}
+
+int drops_b200_dist_spmv_dev(int nparts, const drops_b200_dist_matrix_t* A, const drops_b200_vector_t* x,
+                             const drops_b200_vector_t* y)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(A && x && y, "null argument");
+    DB_CHECK(check_parts(nparts, A));
+    std::vector<PartArgs> a((size_t)nparts);
+    for (int p = 0; p < nparts; ++p) {
+        DB_ARG(x[p] && y[p] && x[p]->n == A[p]->n_owned && y[p]->n == A[p]->n_owned, "vector size != owned rows of the partition");
+        DB_ARG(x[p]->d != y[p]->d, "x and y must not alias");
+        DB_CHECK(ensure_part_scalars(A[p], 1));
+        a[(size_t)p].x = x[p]->d; a[(size_t)p].y = y[p]->d;
+    }
+    return dist_spmv_run(nparts, A, a.data());
+}
+
+int drops_b200_dist_dot(int nparts, const drops_b200_dist_matrix_t* A, const drops_b200_vector_t* x,
+                        const drops_b200_vector_t* y, double* result)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(A && x && y && result, "null argument");
+    DB_CHECK(check_parts(nparts, A));
+    Ctx& c = ctx();
+    for (int p = 0; p < nparts; ++p) {
+        DB_ARG(x[p] && y[p] && x[p]->n == A[p]->n_owned && y[p]->n == A[p]->n_owned, "vector size != owned rows of the partition");
+        DB_CHECK(ensure_part_scalars(A[p], 1));
+        DB_CHECK(vec_dot_partial(A[p]->n_owned, x[p]->d, y[p]->d, gather_slot(A[p], 1)));
+    }
+    DB_CHECK(allgather_partials(A[0]->comm, 1));
+    DB_CHECK(scalars_kernel(PH_DOT, A[0], nullptr, c.scratch_scalars));
+    DB_CUDA(cudaMemcpyAsync(c.h_scalars, c.scratch_scalars, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    DB_CUDA(cudaStreamSynchronize(c.stream));
+    *result = c.h_scalars[0];
+    return 0;
+}
+
+int drops_b200_dist_pcg_dev(int nparts, const drops_b200_dist_matrix_t* A, const drops_b200_vector_t* x,
+                            const drops_b200_vector_t* b, int pc, double omega, int* max_iter, double* tol, int relative,
+                            double* hist, int hist_cap)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(A && x && b, "null argument");
+    DB_CHECK(check_parts(nparts, A));
+    std::vector<double*> xs((size_t)nparts);
+    std::vector<const double*> bs((size_t)nparts);
+    for (int p = 0; p < nparts; ++p) {
+        DB_ARG(x[p] && b[p] && x[p]->n == A[p]->n_owned && b[p]->n == A[p]->n_owned, "vector size != owned rows of the partition");
+        xs[(size_t)p] = x[p]->d; bs[(size_t)p] = b[p]->d;
+    }
+    return dist_pcg(nparts, A, xs.data(), bs.data(), pc, omega, max_iter, tol, relative, hist, hist_cap);
+}
+
+}  // extern "C"

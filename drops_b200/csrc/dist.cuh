@@ -1,0 +1,74 @@
+// dist.cuh -- row-partitioned systems across GPUs: halo plan, communicator, partition matrix.
+#pragma once
+#include "common.cuh"
+
+#include <vector>
+
+// Host-side halo plan (exchange.cu).
+struct drops_b200_exchange_s {
+    int rank = 0, world = 1;
+    std::vector<int64_t> owned;              // owned global ids, ascending; local index = position
+    struct Range { int64_t gid0, len, local0; };
+    std::vector<Range> ranges;               // the owned ids as contiguous runs
+    std::vector<int64_t> ghost_gid;          // by ghost slot: (owner, gid) ascending
+    std::vector<int32_t> ghost_owner;
+    std::vector<size_t> recv_off;            // world+1: slots received from rank q = [recv_off[q], recv_off[q+1])
+    std::vector<int64_t> ghost_sorted;       // ghost ids ascending + their slots (lookup)
+    std::vector<int32_t> ghost_sorted_slot;
+    std::vector<std::vector<int32_t>> send_idx;   // per peer: owned local indices in the peer's request order
+    std::vector<bool> send_set;
+};
+
+namespace db200 {
+
+int64_t exchange_local_of(const drops_b200_exchange_s* E, int64_t gid);
+
+enum CommKind { COMM_NCCL = 0, COMM_LOCAL = 1 };
+
+// Sorted unique non-owned column ids of device-resident rows (dist.cu).
+int find_ghosts_device(size_t n_owned, const int64_t* owned_host_sorted, size_t nnz, const int64_t* d_colgid,
+                       std::vector<int64_t>* out);
+
+}  // namespace db200
+
+struct drops_b200_dist_matrix_s;
+
+// One communicator per process.  COMM_NCCL: this process is rank `rank` of `world`, one GPU each,
+// ncclSend/ncclRecv for the halo and ncclAllGather for the reduction partials.  COMM_LOCAL: all
+// `world` partitions live in this process on this GPU (device-to-device copies); it exists so that
+// the whole partitioned path -- plan, remap, interior/boundary split, rank-ordered reductions --
+// is exercised by the single-GPU test suite.
+struct drops_b200_comm_s {
+    int kind = db200::COMM_NCCL;
+    int rank = 0, world = 1;
+    void* nccl = nullptr;                    // ncclComm_t
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_pack = nullptr, ev_halo = nullptr;
+    db200::dd* gathered = nullptr;           // world * kMaxQ reduction partials, rank-major
+    std::vector<drops_b200_dist_matrix_s*> parts;   // COMM_LOCAL: registered partitions by rank
+};
+
+struct drops_b200_dist_matrix_s {
+    drops_b200_comm_s* comm = nullptr;
+    int rank = 0, world = 1;
+    size_t n_owned = 0, n_ghost = 0, nnz = 0, n_int = 0, n_bnd = 0, n_send = 0;
+    db200::SellOp sell_int, sell_bnd;        // rows without / with ghost columns
+    double* diag = nullptr;
+    bool diag_ok = false;
+    double* ghost = nullptr;                 // n_ghost received x entries
+    double* sendbuf = nullptr;               // n_send packed x entries
+    int32_t* d_send_idx = nullptr;
+    std::vector<size_t> send_off, recv_off;  // world+1 each
+    uint64_t version = 0;
+    size_t device_bytes = 0;
+    std::vector<double*> work;               // solver vectors (n_owned)
+    void* d_scalars = nullptr;               // db200::SolverScalars
+    double* d_hist = nullptr;
+    int hist_alloc = 0;
+};
+
+namespace db200 {
+// Builds the partition operator from device-resident rows with global column ids (dist.cu).
+int dist_matrix_build(drops_b200_comm_s* comm, drops_b200_exchange_s* E, size_t nnz, const int64_t* d_rowptr,
+                      const int64_t* d_colgid, const double* d_val, uint64_t version, drops_b200_dist_matrix_s** out);
+}  // namespace db200

@@ -39,15 +39,17 @@ __global__ void k_extract_diag(long long rows, const int64_t* __restrict__ rowpt
 // network in shared memory and emits perm + per-slice widths (in stored entries, i.e. width*32).
 template <int SIGMA>
 __global__ void __launch_bounds__(1024)
-k_sell_sort(long long rows, const int64_t* __restrict__ rowptr, int32_t* __restrict__ perm,
-            int64_t* __restrict__ slice_entries)
+k_sell_sort(long long rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ rowmap,
+            int32_t* __restrict__ perm, int64_t* __restrict__ slice_entries)
 {
+    // rows = number of rows of the operator; rowmap (optional) = the CSR row behind each of them
     __shared__ unsigned long long key[SIGMA];
     const long long w0 = (long long)blockIdx.x * SIGMA;
     for (int t = threadIdx.x; t < SIGMA; t += blockDim.x) {
         const long long r = w0 + t;
         if (r < rows) {
-            const unsigned long long len = (unsigned long long)(rowptr[r + 1] - rowptr[r]);
+            const long long ra = rowmap ? rowmap[r] : r;
+            const unsigned long long len = (unsigned long long)(rowptr[ra + 1] - rowptr[ra]);
             const unsigned long long inv = 0x7fffffffULL - (len > 0x7fffffffULL ? 0x7fffffffULL : len);
             key[t] = (inv << 32) | (unsigned long long)(unsigned)t;
         } else {
@@ -71,7 +73,8 @@ k_sell_sort(long long rows, const int64_t* __restrict__ rowptr, int32_t* __restr
     for (int t = threadIdx.x; t < SIGMA; t += blockDim.x) {
         const unsigned long long kk = key[t];
         const bool pad = (kk == ~0ULL);
-        perm[w0 + t] = pad ? -1 : (int32_t)(w0 + (long long)(kk & 0xffffffffULL));
+        const long long r = w0 + (long long)(kk & 0xffffffffULL);
+        perm[w0 + t] = pad ? -1 : (rowmap ? rowmap[r] : (int32_t)r);
         if ((t & 31) == 0) {
             const long long len = pad ? 0 : (long long)(0x7fffffffULL - (kk >> 32));
             slice_entries[(w0 + t) >> 5] = len * 32;
@@ -81,12 +84,16 @@ k_sell_sort(long long rows, const int64_t* __restrict__ rowptr, int32_t* __restr
 
 // sigma = 0/1: identity order (no sorting), widths = max length inside each slice.
 __global__ void k_sell_identity(long long rows, long long padded_rows, const int64_t* __restrict__ rowptr,
-                                int32_t* __restrict__ perm, int64_t* __restrict__ slice_entries)
+                                const int32_t* __restrict__ rowmap, int32_t* __restrict__ perm,
+                                int64_t* __restrict__ slice_entries)
 {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= padded_rows) return;
     long long len = 0;
-    if (r < rows) { perm[r] = (int32_t)r; len = rowptr[r + 1] - rowptr[r]; }
+    if (r < rows) {
+        const long long ra = rowmap ? rowmap[r] : r;
+        perm[r] = (int32_t)ra; len = rowptr[ra + 1] - rowptr[ra];
+    }
     else perm[r] = -1;
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) {
@@ -226,12 +233,16 @@ void free_csr(CsrDev& c)
     c = CsrDev();
 }
 
-int build_sell(const CsrDev& A, SellOp& S, size_t* bytes)
+// Builds the sliced-ELL operator of all rows of A (rowmap == nullptr) or of the `nsub` rows
+// listed in rowmap (device array, ascending); perm then holds rows of A, so y, aux and the
+// fused dot are addressed by the full row index.
+int build_sell(const CsrDev& A, SellOp& S, size_t* bytes, const int32_t* rowmap, size_t nsub)
 {
     Ctx& c = ctx();
     cudaStream_t st = c.stream;
     free_sell(S);
-    S.rows = A.rows; S.cols = A.cols;
+    const size_t op_rows = rowmap ? nsub : A.rows;
+    S.rows = op_rows; S.cols = A.cols;
     int sigma = (int)opt("sell.sigma", 4096.0);
     const bool sorted = sigma >= 64;
     if (sorted) {
@@ -239,25 +250,25 @@ int build_sell(const CsrDev& A, SellOp& S, size_t* bytes)
         else if (sigma >= 1024) sigma = 1024; else if (sigma >= 512) sigma = 512;
         else if (sigma >= 256) sigma = 256; else if (sigma >= 128) sigma = 128; else sigma = 64;
     } else sigma = 32;
-    const size_t nwin = (A.rows + sigma - 1) / sigma;
+    const size_t nwin = (op_rows + sigma - 1) / sigma;
     const size_t padded_rows = std::max<size_t>(nwin * sigma, 32);
     S.nslices = padded_rows / 32;
     DB_CHECK(dev_alloc(&S.perm, padded_rows));
     DB_CHECK(dev_alloc(&S.slice_ptr, S.nslices + 1));
     DB_CUDA(cudaMemsetAsync(S.slice_ptr, 0, (S.nslices + 1) * sizeof(int64_t), st));
-    if (A.rows > 0) {
+    if (op_rows > 0) {
         if (!sorted) {
-            k_sell_identity<<<blocks_for(padded_rows, 256), 256, 0, st>>>((long long)A.rows, (long long)padded_rows, A.rowptr, S.perm, S.slice_ptr);
+            k_sell_identity<<<blocks_for(padded_rows, 256), 256, 0, st>>>((long long)op_rows, (long long)padded_rows, A.rowptr, rowmap, S.perm, S.slice_ptr);
         } else {
             const int g = (int)nwin;
             switch (sigma) {
-                case 4096: k_sell_sort<4096><<<g, 1024, 0, st>>>((long long)A.rows, A.rowptr, S.perm, S.slice_ptr); break;
-                case 2048: k_sell_sort<2048><<<g, 1024, 0, st>>>((long long)A.rows, A.rowptr, S.perm, S.slice_ptr); break;
-                case 1024: k_sell_sort<1024><<<g, 512, 0, st>>>((long long)A.rows, A.rowptr, S.perm, S.slice_ptr); break;
-                case 512:  k_sell_sort<512><<<g, 256, 0, st>>>((long long)A.rows, A.rowptr, S.perm, S.slice_ptr); break;
-                case 256:  k_sell_sort<256><<<g, 128, 0, st>>>((long long)A.rows, A.rowptr, S.perm, S.slice_ptr); break;
-                case 128:  k_sell_sort<128><<<g, 64, 0, st>>>((long long)A.rows, A.rowptr, S.perm, S.slice_ptr); break;
-                default:   k_sell_sort<64><<<g, 32, 0, st>>>((long long)A.rows, A.rowptr, S.perm, S.slice_ptr); break;
+                case 4096: k_sell_sort<4096><<<g, 1024, 0, st>>>((long long)op_rows, A.rowptr, rowmap, S.perm, S.slice_ptr); break;
+                case 2048: k_sell_sort<2048><<<g, 1024, 0, st>>>((long long)op_rows, A.rowptr, rowmap, S.perm, S.slice_ptr); break;
+                case 1024: k_sell_sort<1024><<<g, 512, 0, st>>>((long long)op_rows, A.rowptr, rowmap, S.perm, S.slice_ptr); break;
+                case 512:  k_sell_sort<512><<<g, 256, 0, st>>>((long long)op_rows, A.rowptr, rowmap, S.perm, S.slice_ptr); break;
+                case 256:  k_sell_sort<256><<<g, 128, 0, st>>>((long long)op_rows, A.rowptr, rowmap, S.perm, S.slice_ptr); break;
+                case 128:  k_sell_sort<128><<<g, 64, 0, st>>>((long long)op_rows, A.rowptr, rowmap, S.perm, S.slice_ptr); break;
+                default:   k_sell_sort<64><<<g, 32, 0, st>>>((long long)op_rows, A.rowptr, rowmap, S.perm, S.slice_ptr); break;
             }
         }
         count_launch();
@@ -348,7 +359,7 @@ int build_transpose(drops_b200_matrix_s* M)
     DB_CUDA(cudaStreamSynchronize(st));
     dev_free(cursor);
     size_t bytes = T.nnz * 12 + (T.rows + 1) * 8;
-    DB_CHECK(build_sell(T, M->sell_t, &bytes));
+    DB_CHECK(build_sell(T, M->sell_t, &bytes, nullptr, 0));
     M->device_bytes += bytes;
     M->has_t = true;
     return 0;
@@ -369,7 +380,7 @@ int finalize_matrix(drops_b200_matrix_s* M)
     M->device_bytes = M->csr.nnz * 12 + (M->csr.rows + 1) * 8;
     DB_CHECK(extract_diag(M));
     if (M->square) M->device_bytes += M->csr.rows * 8;
-    DB_CHECK(build_sell(M->csr, M->sell, &M->device_bytes));
+    DB_CHECK(build_sell(M->csr, M->sell, &M->device_bytes, nullptr, 0));
     return 0;
 }
 

@@ -39,6 +39,10 @@ struct EpiArgs {
     const double* dotv;
     double* dot_out;
     const int* done;
+    const dd* dd_in;
+    dd* dd_out;
+    const double* xghost;
+    int n_owned;
     int prefetch;
     dd* partials;
     unsigned* ticket;
@@ -60,7 +64,23 @@ __device__ __forceinline__ void prefetch_l2(const void* p)
 
 // U = entries per thread loaded before the first use (loads in flight), MINB = resident CTAs of
 // 512 threads the register allocation must allow (2: <= 64 regs, 3: <= 40, 4: <= 32).
-template <int EPI, bool EXACT, bool DOT, int U, int MINB>
+// Stores the grid-wide fused dot product: rounded to *dot_out, or -- chained launches of a
+// partitioned product -- unrounded (plus the earlier launches' *dd_in) to *dd_out.
+__device__ __forceinline__ void store_dot(const EpiArgs& e, dd total)
+{
+    if (e.dd_in != nullptr) total = dd_add(total, *e.dd_in);
+    if (e.dd_out != nullptr) *e.dd_out = total;
+    else *e.dot_out = dd_round(total);
+}
+
+template <bool SPLIT>
+__device__ __forceinline__ double load_x(const double* __restrict__ x, const EpiArgs& e, int c)
+{
+    if (SPLIT) return c < e.n_owned ? __ldg(x + c) : __ldg(e.xghost + (c - e.n_owned));
+    return __ldg(x + c);
+}
+
+template <int EPI, bool EXACT, bool DOT, int U, int MINB, bool SPLIT = false>
 __global__ void __launch_bounds__(512, MINB)
 k_spmv_sell(SellView A, const double* __restrict__ x, double* __restrict__ y, EpiArgs e)
 {
@@ -96,7 +116,7 @@ k_spmv_sell(SellView A, const double* __restrict__ x, double* __restrict__ y, Ep
                 v[u] = __ldcs(vp + (size_t)(j + u) * 32);
             }
 #pragma unroll
-            for (int u = 0; u < kSellUnroll; ++u) xv[u] = c[u] >= 0 ? __ldg(x + c[u]) : 0.0;
+            for (int u = 0; u < kSellUnroll; ++u) xv[u] = c[u] >= 0 ? load_x<SPLIT>(x, e, c[u]) : 0.0;
 #pragma unroll
             for (int u = 0; u < kSellUnroll; ++u) {
                 if (c[u] >= 0)
@@ -107,7 +127,7 @@ k_spmv_sell(SellView A, const double* __restrict__ x, double* __restrict__ y, Ep
             const int c = __ldcs(cp + (size_t)j * 32);
             const double v = __ldcs(vp + (size_t)j * 32);
             if (c >= 0) {
-                const double xv = __ldg(x + c);
+                const double xv = load_x<SPLIT>(x, e, c);
                 sum = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv)) : fma(v, xv, sum);
             }
         }
@@ -120,7 +140,7 @@ k_spmv_sell(SellView A, const double* __restrict__ x, double* __restrict__ y, Ep
     }
     if (DOT) {
         if (grid_reduce_dd<1>(acc, red_smem, e.partials, e.ticket)) {
-            if (threadIdx.x == 0) *e.dot_out = dd_round(acc[0]);
+            if (threadIdx.x == 0) store_dot(e, acc[0]);
         }
     }
 }
@@ -159,7 +179,7 @@ k_spmv_csr_vector(long long rows, const int64_t* __restrict__ rowptr, const int3
     }
     if (DOT) {
         if (grid_reduce_dd<1>(acc, red_smem, e.partials, e.ticket)) {
-            if (threadIdx.x == 0) *e.dot_out = dd_round(acc[0]);
+            if (threadIdx.x == 0) store_dot(e, acc[0]);
         }
     }
 }
@@ -175,20 +195,24 @@ static EpiArgs make_epi(const SpmvArgs& a)
     e.dotv = a.dotv;
     e.dot_out = a.dot_out;
     e.done = a.done;
+    e.dd_in = a.dd_in;
+    e.dd_out = a.dd_out;
+    e.xghost = a.xghost;
+    e.n_owned = (int)a.n_owned;
     e.prefetch = (int)opt("spmv.prefetch", 0.0);
     e.partials = c.partials + (size_t)a.slot * kPartialStride;
     e.ticket = c.tickets + (size_t)a.slot * kTicketStride;
     return e;
 }
 
-template <int EPI, bool EXACT, int U, int MINB>
+template <int EPI, bool EXACT, int U, int MINB, bool SPLIT = false>
 static void launch_sell_v(const SellView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads,
                           cudaStream_t st)
 {
     if (a.dotv != nullptr)
-        k_spmv_sell<EPI, EXACT, true, U, MINB><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
+        k_spmv_sell<EPI, EXACT, true, U, MINB, SPLIT><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
     else
-        k_spmv_sell<EPI, EXACT, false, U, MINB><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
+        k_spmv_sell<EPI, EXACT, false, U, MINB, SPLIT><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
 }
 
 // "spmv.variant": 0 = U4/<=40 regs (default: best in profiles/r01_sweep2_spmv.jsonl), 1 = U8/<=64,
@@ -198,6 +222,10 @@ template <int EPI, bool EXACT>
 static void launch_sell(const SellView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads,
                         cudaStream_t st)
 {
+    if (a.xghost != nullptr) {   // boundary rows of a partition: a thin operator, one variant
+        launch_sell_v<EPI, EXACT, 4, 3, true>(v, a, e, grid, threads, st);
+        return;
+    }
     if (EPI == EPI_NONE) {
         switch ((int)opt("spmv.variant", 0.0)) {
             case 1: launch_sell_v<EPI_NONE, EXACT, 8, 2>(v, a, e, grid, threads, st); return;
@@ -229,7 +257,7 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a)
     DB_ARG(a.x != nullptr && a.y != nullptr, "null vector");
     DB_ARG(a.x != a.y, "x and y must not alias");
     DB_ARG(a.epilogue == EPI_NONE || a.aux != nullptr, "epilogue needs aux vector");
-    DB_ARG(a.dotv == nullptr || a.dot_out != nullptr, "fused dot needs an output scalar");
+    DB_ARG(a.dotv == nullptr || a.dot_out != nullptr || a.dd_out != nullptr, "fused dot needs an output scalar");
     if (A.rows == 0) return 0;
     int threads = (int)opt("spmv.threads", 128);
     if (threads < 32) threads = 32;

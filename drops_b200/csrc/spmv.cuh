@@ -24,6 +24,13 @@ struct SpmvArgs {
     // optional fused reduction  sum_i y_i * dotv_i  -> *dot_out (device scalar)
     const double* dotv = nullptr;
     double* dot_out = nullptr;
+    // partitioned systems (dist.cu): a fused dot may be chained over several launches -- the result
+    // (plus *dd_in, if given) is stored unrounded to *dd_out instead of rounded to *dot_out
+    const dd* dd_in = nullptr;
+    dd* dd_out = nullptr;
+    // columns >= n_owned are read from xghost[col - n_owned] (received halo entries)
+    const double* xghost = nullptr;
+    long long n_owned = 0;
     const int* done = nullptr;     // optional device flag: kernel is a no-op when *done != 0
     int slot = 0;                  // reduction workspace slot (kernels that may overlap use different slots)
     cudaStream_t stream = nullptr; // default: ctx().stream

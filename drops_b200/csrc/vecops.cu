@@ -71,6 +71,16 @@ int vec_dot(size_t n, const double* x, const double* y, double* d_out)
 {
     return launch_stream<1>(n, OpDot{x, y, d_out}, "vec");
 }
+struct OpDotPartial {
+    const double* x; const double* y; dd* out;
+    __device__ bool begin() { return true; }
+    __device__ void elem(size_t i, dd* acc) { acc[0] = dd_add_prod(acc[0], x[i], y[i]); }
+    __device__ void finish(const dd* acc) { *out = acc[0]; }
+};
+int vec_dot_partial(size_t n, const double* x, const double* y, dd* part_out)
+{
+    return launch_stream<1>(n, OpDotPartial{x, y, part_out}, "vec");
+}
 
 __global__ void k_supnorm(size_t n, const double* __restrict__ x, double* partial)
 {
@@ -187,7 +197,7 @@ int vec_sub(size_t n, double* out, const double* a, const double* b) { return la
 // ------------------------------------------------------------------------------------------
 struct OpPcgSetup {
     const double* r; const double* b; const double* d; double* p; SolverScalars* S; double* hist;
-    int pc; double omega;
+    int pc; double omega; dd* part_out;
     __device__ bool begin() { pc = S->pc; omega = S->omega; return true; }
     __device__ void elem(size_t i, dd* acc)
     {
@@ -200,25 +210,19 @@ struct OpPcgSetup {
     }
     __device__ void finish(const dd* acc)
     {
-        double normb = sqrt(dd_round(acc[1]));                  // krylovsolver.h:130-133
-        if (normb == 0.0 || !S->relative) normb = 1.0;
-        const double resid = sqrt(dd_round(acc[0])) / normb;    // :129, :134
-        S->normb = normb; S->resid = resid; S->rr = dd_round(acc[0]);
-        S->rho = dd_round(acc[2]); S->rho_1 = 0.0;              // :144
-        S->iter = 0;
-        if (hist && S->hist_cap > 0) hist[0] = resid;
-        if (resid <= S->tol) { S->done = 1; S->converged = 1; } // :137-141
-        else if (S->max_iter <= 0) S->done = 1;
+        if (part_out) { part_out[0] = acc[0]; part_out[1] = acc[1]; part_out[2] = acc[2]; return; }
+        pcg_setup_finish(S, hist, dd_round(acc[0]), dd_round(acc[1]), dd_round(acc[2]));
     }
 };
-int pcg_setup(size_t n, const double* r, const double* b, const double* d, double* p, SolverScalars* S, double* hist)
+int pcg_setup(size_t n, const double* r, const double* b, const double* d, double* p, SolverScalars* S, double* hist,
+              dd* part_out)
 {
-    return launch_stream<3>(n, OpPcgSetup{r, b, d, p, S, hist, 0, 1.0}, "pcg.setup");
+    return launch_stream<3>(n, OpPcgSetup{r, b, d, p, S, hist, 0, 1.0, part_out}, "pcg.setup");
 }
 
 struct OpPcgUpdate {
     double* x; double* r; const double* p; const double* q; const double* d; SolverScalars* S; double* hist;
-    double alpha; int pc; double omega;
+    double alpha; int pc; double omega; dd* part_out;
     __device__ bool begin()
     {
         if (S->done) return false;
@@ -237,14 +241,8 @@ struct OpPcgUpdate {
     }
     __device__ void finish(const dd* acc)
     {
-        const double rr = dd_round(acc[0]);
-        const double resid = sqrt(rr) / S->normb;
-        const int it = S->iter + 1;
-        S->iter = it; S->rr = rr; S->resid = resid;
-        S->rho_1 = S->rho; S->rho = dd_round(acc[1]);
-        if (hist && it < S->hist_cap) hist[it] = resid;
-        if (resid <= S->tol) { S->done = 1; S->converged = 1; } // :164-168
-        else if (it >= S->max_iter) S->done = 1;
+        if (part_out) { part_out[0] = acc[0]; part_out[1] = acc[1]; return; }
+        pcg_update_finish(S, hist, dd_round(acc[0]), dd_round(acc[1]));
     }
 };
 // 16-byte vectorised form of the two per-iteration PCG kernels: every thread has 5 (update) or 3
@@ -261,10 +259,10 @@ static inline bool aligned16(const void* a, const void* b, const void* c, const 
 __global__ void __launch_bounds__(kReduceThreads)
 k_pcg_update2(size_t n, double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
               const double* __restrict__ q, const double* __restrict__ d, SolverScalars* S, double* hist,
-              dd* partials, unsigned* ticket)
+              dd* part_out, dd* partials, unsigned* ticket)
 {
     __shared__ dd red_smem[2 * 32];
-    OpPcgUpdate op{x, r, p, q, d, S, hist, 0.0, 0, 1.0};
+    OpPcgUpdate op{x, r, p, q, d, S, hist, 0.0, 0, 1.0, part_out};
     if (!op.begin()) return;
     const double alpha = op.alpha, omega = op.omega;
     const bool jac = op.pc == DROPS_B200_PC_JACOBI;
@@ -296,18 +294,18 @@ k_pcg_update2(size_t n, double* __restrict__ x, double* __restrict__ r, const do
 }
 
 int pcg_update(size_t n, double* x, double* r, const double* p, const double* q, const double* d,
-               SolverScalars* S, double* hist)
+               SolverScalars* S, double* hist, dd* part_out)
 {
     if (opt("vec.wide", 1.0) != 0.0 && aligned16(x, r, p, q, d)) {
         Ctx& c = ctx();
         ScopedTiming t("pcg.update");
         const int grid = vec_grid(n, kReduceThreads, 4);
-        k_pcg_update2<<<grid, kReduceThreads, 0, c.stream>>>(n, x, r, p, q, d, S, hist, c.partials, c.tickets);
+        k_pcg_update2<<<grid, kReduceThreads, 0, c.stream>>>(n, x, r, p, q, d, S, hist, part_out, c.partials, c.tickets);
         count_launch();
         DB_CUDA(cudaGetLastError());
         return 0;
     }
-    return launch_stream<2>(n, OpPcgUpdate{x, r, p, q, d, S, hist, 0.0, 0, 1.0}, "pcg.update");
+    return launch_stream<2>(n, OpPcgUpdate{x, r, p, q, d, S, hist, 0.0, 0, 1.0, part_out}, "pcg.update");
 }
 
 struct OpPcgDirection {

@@ -15,6 +15,33 @@ struct SolverScalars {
     int iter, done, converged, relative, max_iter, pc, hist_cap, pad;
 };
 
+#ifdef __CUDACC__
+// Scalar bookkeeping after the reductions of the PCG setup / update pass; run by one thread
+// (the last block of the fused kernel on one GPU, k_dist_scalars on a partitioned system).
+__device__ __forceinline__ void pcg_setup_finish(SolverScalars* S, double* hist, double rr, double bb, double rho)
+{
+    double normb = sqrt(bb);                                    // krylovsolver.h:130-133
+    if (normb == 0.0 || !S->relative) normb = 1.0;
+    const double resid = sqrt(rr) / normb;                      // :129, :134
+    S->normb = normb; S->resid = resid; S->rr = rr;
+    S->rho = rho; S->rho_1 = 0.0;                               // :144
+    S->iter = 0;
+    if (hist && S->hist_cap > 0) hist[0] = resid;
+    if (resid <= S->tol) { S->done = 1; S->converged = 1; }     // :137-141
+    else if (S->max_iter <= 0) S->done = 1;
+}
+__device__ __forceinline__ void pcg_update_finish(SolverScalars* S, double* hist, double rr, double rho)
+{
+    const double resid = sqrt(rr) / S->normb;
+    const int it = S->iter + 1;
+    S->iter = it; S->rr = rr; S->resid = resid;
+    S->rho_1 = S->rho; S->rho = rho;
+    if (hist && it < S->hist_cap) hist[it] = resid;
+    if (resid <= S->tol) { S->done = 1; S->converged = 1; }     // :164-168
+    else if (it >= S->max_iter) S->done = 1;
+}
+#endif
+
 // ---- standalone reductions / updates (C ABI: dot, norm, axpy, ...) ---------------------------
 int vec_dot(size_t n, const double* x, const double* y, double* d_out);          // d_out: device scalar
 int vec_supnorm(size_t n, const double* x, double* d_out);
@@ -28,12 +55,17 @@ int vec_copy(size_t n, double* dst, const double* src);
 
 // ---- PCG (num/krylovsolver.h:107-179) ------------------------------------------------------------
 // setup: given r = b - A x: normb, resid, hist[0], z = M^-1 r, rho = z.r, p = z; may set done.
+// part_out != nullptr (partitioned system): the reductions are stored unrounded to part_out[0..2]
+// (|r|^2, |b|^2, z.r) and the scalar bookkeeping is left to the caller.
 int pcg_setup(size_t n, const double* r, const double* b, const double* d, double* p,
-              SolverScalars* S, double* hist);
+              SolverScalars* S, double* hist, dd* part_out = nullptr);
 // update: alpha = rho/lambda; x += alpha p; r -= alpha q; resid = |r|/normb; rho_1 = rho;
 //         rho = (M^-1 r).r; ++iter; hist[iter] = resid; done if resid <= tol or iter == max_iter.
+// part_out != nullptr: partials (|r|^2, z.r) to part_out[0..1], no bookkeeping.
 int pcg_update(size_t n, double* x, double* r, const double* p, const double* q, const double* d,
-               SolverScalars* S, double* hist);
+               SolverScalars* S, double* hist, dd* part_out = nullptr);
+// local double-double partial of x.y -> *part_out (no rounding)
+int vec_dot_partial(size_t n, const double* x, const double* y, dd* part_out);
 // direction: p = M^-1 r + (rho/rho_1) p
 int pcg_direction(size_t n, double* p, const double* r, const double* d, SolverScalars* S);
 

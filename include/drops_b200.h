@@ -204,6 +204,110 @@ DROPS_B200_API int drops_b200_brick_matrix_device(int fe, int N, int numbering, 
 DROPS_B200_API int drops_b200_brick_solution_host(int fe, int N, int numbering, double* xstar);
 DROPS_B200_API int drops_b200_brick_solution_device(int fe, int N, int numbering, drops_b200_vector_t xstar);
 
+/* ---- row-partitioned systems across the GPUs of one box --------------------------------------
+ * Stand-in for the reference's distributed layer: ExchangeCL (parallel/exchange.h:194-243,
+ * Accumulate parallel/exchange.cpp:333-362, ParDot :449-462, Norm :487-495) over ProcCL/MPI
+ * (parallel/parallel.h:256-263), with ParMETIS deciding who owns what
+ * (parallel/partitioner.cpp:251-257).  DROPS partitions tetrahedra and duplicates interface DOFs;
+ * here the matrix is partitioned by ROWS (owner computes), so a vector has one form only, the
+ * product y = A x needs the neighbours' x entries of the referenced-but-not-owned columns
+ * ("ghosts": ncclSend/ncclRecv, overlapped with the rows that reference no ghost), and a dot
+ * product is a local double-double partial + one ncclAllGather summed in rank order on every rank
+ * (bit-identical everywhere, so all ranks take the same branches).  One process per GPU.
+ *
+ * Local numbering of a rank: [0, n_owned) owned DOFs by ascending global id, then the ghosts
+ * grouped by owner rank.  A distributed vector is a drops_b200_vector_t of n_owned entries. */
+typedef struct drops_b200_exchange_s*    drops_b200_exchange_t;
+typedef struct drops_b200_comm_s*        drops_b200_comm_t;
+typedef struct drops_b200_dist_matrix_s* drops_b200_dist_matrix_t;
+
+/* -- halo plan (host only; no device needed).  Built in two steps because the send side needs the
+ *    neighbours' requests: create -> request(q) for every q -> [caller transports the lists] ->
+ *    set_send(q, what q requested from us).  ghost_gid must be unique and not owned. */
+DROPS_B200_API int drops_b200_exchange_create(int rank, int world, size_t n_owned, const int64_t* owned_gid,
+                                              size_t n_ghost, const int64_t* ghost_gid, const int32_t* ghost_owner,
+                                              drops_b200_exchange_t* out);
+DROPS_B200_API int drops_b200_exchange_destroy(drops_b200_exchange_t ex);
+DROPS_B200_API int drops_b200_exchange_sizes(drops_b200_exchange_t ex, size_t* n_owned, size_t* n_ghost,
+                                             size_t* n_send, int* n_neighbours);
+/* Global ids this rank needs from `peer`, in the order they will be received (gids may be NULL). */
+DROPS_B200_API int drops_b200_exchange_request(drops_b200_exchange_t ex, int peer, size_t* count, int64_t* gids);
+/* The ids `peer` requested from this rank; all must be owned here. */
+DROPS_B200_API int drops_b200_exchange_set_send(drops_b200_exchange_t ex, int peer, size_t count, const int64_t* gids);
+DROPS_B200_API int drops_b200_exchange_send_list(drops_b200_exchange_t ex, int peer, size_t* count, int64_t* local_idx);
+/* local index of each global id (owned: position; ghost: n_owned + slot; else -1) */
+DROPS_B200_API int drops_b200_exchange_local_index(drops_b200_exchange_t ex, size_t count, const int64_t* gids,
+                                                   int64_t* local);
+/* 1 when every peer's send list has been set */
+DROPS_B200_API int drops_b200_exchange_ready(drops_b200_exchange_t ex);
+/* Sorted unique column ids of the local rows that are not in owned_gid.  Writes at most `cap` ids,
+ * *n_ghost receives the full count (call with cap = 0 first).  colind: reference layout (size_t). */
+DROPS_B200_API int drops_b200_find_ghosts(size_t n_owned, const int64_t* owned_gid, size_t nnz, const size_t* colind,
+                                          int64_t* ghost_out, size_t cap, size_t* n_ghost);
+/* Row partitioner on the matrix graph (breadth-first level structure cut into chunks of equal
+ * stored-entry count): part[row] in [0, nparts).  Host only. */
+DROPS_B200_API int drops_b200_partition_rows(size_t rows, const size_t* rowbeg, const size_t* colind, int nparts,
+                                             int32_t* part);
+
+/* -- communicator.  unique_id: rank 0 fills DROPS_B200_UNIQUE_ID_BYTES bytes (ncclGetUniqueId), the
+ *    caller broadcasts them (torch.distributed / MPI / files), every rank calls comm_create.
+ *    comm_create_local: all `world` partitions are held by THIS process on this GPU (device-to-
+ *    device copies instead of NCCL) -- the transport of the single-GPU parity tests. */
+#define DROPS_B200_UNIQUE_ID_BYTES 128
+DROPS_B200_API int drops_b200_comm_unique_id(void* id_bytes);
+DROPS_B200_API int drops_b200_comm_create(int rank, int world, const void* id_bytes, drops_b200_comm_t* out);
+DROPS_B200_API int drops_b200_comm_create_local(int world, drops_b200_comm_t* out);
+DROPS_B200_API int drops_b200_comm_destroy(drops_b200_comm_t comm);
+DROPS_B200_API int drops_b200_comm_info(drops_b200_comm_t comm, int* rank, int* world, int* is_local);
+/* Device-side barrier + max over ranks of a host double (timing plumbing for bench.py). */
+DROPS_B200_API int drops_b200_comm_allreduce_max(drops_b200_comm_t comm, double* value);
+
+/* -- the rows of one rank.  Rows in the order of the plan's owned ids, GLOBAL column ids, entries of
+ *    a row in the reference's order (ascending global column): the per-row summation order, hence
+ *    every y_i, is bit-identical to the single-GPU product.  The plan must be ready. */
+DROPS_B200_API int drops_b200_dist_matrix_create(drops_b200_comm_t comm, drops_b200_exchange_t ex, size_t nnz,
+                                                 const size_t* rowbeg, const size_t* colind_global, const double* val,
+                                                 uint64_t version, drops_b200_dist_matrix_t* out);
+DROPS_B200_API int drops_b200_dist_matrix_create_device(drops_b200_comm_t comm, drops_b200_exchange_t ex, size_t nnz,
+                                                        const int64_t* d_rowptr, const int64_t* d_colind_global,
+                                                        const double* d_val, uint64_t version,
+                                                        drops_b200_dist_matrix_t* out);
+DROPS_B200_API int drops_b200_dist_matrix_destroy(drops_b200_dist_matrix_t A);
+DROPS_B200_API int drops_b200_dist_matrix_info(drops_b200_dist_matrix_t A, size_t* n_owned, size_t* n_ghost, size_t* nnz,
+                                               size_t* interior_rows, size_t* boundary_rows, size_t* n_send,
+                                               size_t* device_bytes);
+DROPS_B200_API int drops_b200_dist_matrix_diag(drops_b200_dist_matrix_t A, double* diag);
+
+/* Collective operations.  `nparts` partitions driven by this process: 1 with an NCCL communicator
+ * (every rank makes the same call), `world` with a local communicator (arrays ordered by rank). */
+DROPS_B200_API int drops_b200_dist_spmv_dev(int nparts, const drops_b200_dist_matrix_t* A,
+                                            const drops_b200_vector_t* x, const drops_b200_vector_t* y);
+DROPS_B200_API int drops_b200_dist_dot(int nparts, const drops_b200_dist_matrix_t* A, const drops_b200_vector_t* x,
+                                       const drops_b200_vector_t* y, double* result);
+/* PCG (num/krylovsolver.h:107-179) on the partitioned system; contract as drops_b200_pcg_dev.
+ * Every rank returns the same iteration count and residual. */
+DROPS_B200_API int drops_b200_dist_pcg_dev(int nparts, const drops_b200_dist_matrix_t* A,
+                                           const drops_b200_vector_t* x, const drops_b200_vector_t* b, int pc,
+                                           double omega, int* max_iter, double* tol, int relative, double* hist,
+                                           int hist_cap);
+
+/* -- synthetic brick, z-slab partition: rank r owns the lattice planes [k0, k1) (1-based, M planes
+ *    split evenly), rows in ascending global id.  Generated on the device, global ids as above. */
+typedef struct drops_b200_brick_slab_s* drops_b200_brick_slab_t;
+DROPS_B200_API int drops_b200_brick_slab_generate(int fe, int N, int numbering, double upper_scale, int world, int rank,
+                                                  drops_b200_brick_slab_t* out);
+DROPS_B200_API int drops_b200_brick_slab_destroy(drops_b200_brick_slab_t slab);
+DROPS_B200_API int drops_b200_brick_slab_info(drops_b200_brick_slab_t slab, size_t* n_owned, size_t* nnz, size_t* n_ghost,
+                                              long long* k0, long long* k1);
+DROPS_B200_API int drops_b200_brick_slab_owned(drops_b200_brick_slab_t slab, int64_t* owned_gid);
+DROPS_B200_API int drops_b200_brick_slab_ghosts(drops_b200_brick_slab_t slab, int64_t* ghost_gid, int32_t* ghost_owner);
+DROPS_B200_API int drops_b200_brick_slab_matrix(drops_b200_comm_t comm, drops_b200_exchange_t ex,
+                                                drops_b200_brick_slab_t slab, drops_b200_dist_matrix_t* out);
+DROPS_B200_API int drops_b200_brick_slab_solution(drops_b200_brick_slab_t slab, drops_b200_vector_t xstar);
+/* Host helper: owner rank (z-slab) of global ids of the brick. */
+DROPS_B200_API int drops_b200_brick_owner(int fe, int N, int numbering, int world, size_t count, const int64_t* gids,
+                                          int32_t* owner);
+
 #ifdef __cplusplus
 }
 #endif

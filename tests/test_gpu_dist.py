@@ -1,0 +1,196 @@
+"""GPU parity of the row-partitioned path.  On one GPU all ranks are partitions of one process
+(local communicator: device-to-device copies instead of NCCL), which runs the whole partitioned
+machinery -- plan, column remap, interior/boundary split, chained double-double partials,
+rank-ordered reductions -- against the single-GPU path and the reference goldens.  With >= 2 GPUs
+the same checks run over NCCL, one process per GPU (tests/dist_worker_gpu.py).
+Bars: SpMV rows bit-identical to the single-GPU product; PCG iteration count identical (+-1
+allowed by north_star), solution within 1e-10 relative."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, hash_vector, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def build_parts(gpu, rb, ci, va, part, world):
+    from drops_b200 import partition
+    comm = gpu.Comm.local(world)
+    loc = [partition.local_system(rb, ci, va, part, r, world) for r in range(world)]
+    partition.connect_in_process([l[4] for l in loc])
+    mats = [gpu.DistMatrix(comm, l[4], l[1], l[2], l[3]) for l in loc]
+    return comm, loc, mats
+
+
+def scatter(gpu, loc, v):
+    return [gpu.Vector.from_host(v[l[0]]) for l in loc]
+
+
+def gather(loc, vecs, n):
+    out = np.full(n, np.nan)
+    for l, v in zip(loc, vecs):
+        out[l[0]] = v.download()
+    return out
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_partitioned_matches_reference_golden(gpu, world):
+    g = load_golden("brick_fe2_N6_num1.npz")
+    n = int(g["rows"])
+    rb, ci, va = g["rowbeg"], g["colind"], g["val"]
+    part = gpu.partition_rows(rb, ci, world)
+    comm, loc, mats = build_parts(gpu, rb, ci, va, part, world)
+    infos = [m.info() for m in mats]
+    assert sum(i["n_owned"] for i in infos) == n and sum(i["nnz"] for i in infos) == len(va)
+    for i in infos:
+        assert i["interior_rows"] + i["boundary_rows"] == i["n_owned"]
+        assert (i["boundary_rows"] > 0) == (world > 1)
+    # y = A x: every row bit-identical to the compiled reference
+    xs = scatter(gpu, loc, g["x_in"])
+    ys = [gpu.Vector(l[0].size) for l in loc]
+    gpu.dist_spmv(mats, xs, ys)
+    assert np.array_equal(gather(loc, ys, n), g["y_Ax"])
+    assert np.array_equal(np.concatenate([m.diag() for m in mats])[np.argsort(np.concatenate([l[0] for l in loc]))], g["diag"])
+    # dot: rank-ordered double-double sum == single-GPU reduction to the last bits
+    d = gpu.dist_dot(mats, xs, ys)
+    xv, yv = gpu.Vector.from_host(g["x_in"]), gpu.Vector.from_host(g["y_Ax"])
+    assert abs(d - gpu.dot(xv, yv)) <= 4e-16 * float(np.abs(g["x_in"] * g["y_Ax"]).sum())
+    # PCG + Jacobi to convergence: same iteration count as the reference run, same solution
+    bs = scatter(gpu, loc, g["b"])
+    x0 = [gpu.Vector(l[0].size) for l in loc]
+    conv, it, res, hist = gpu.dist_pcg(mats, x0, bs, 400, 1e-10, True, hist=True)
+    assert conv and abs(it - int(g["sym_pcgjac"][1])) <= 1
+    assert rel(gather(loc, x0, n), g["sym_pcgjac_x"]) <= 1e-10
+    k = min(it, int(g["sym_pcgjac"][1]))
+    assert np.allclose(hist[1:k + 1], g["sym_pcgjac_hist"][1:k + 1], rtol=1e-6, atol=1e-15)
+    # fixed work (tol = 0): exactly 7 iterations, not converged
+    for v in x0:
+        v.fill(0.0)
+    conv, it, res = gpu.dist_pcg(mats, x0, bs, 7, 0.0, True)
+    assert not conv and it == 7
+    assert abs(res - g["sym_pcgjac_fixed7"][2]) <= 1e-9 * g["sym_pcgjac_fixed7"][2]
+    assert rel(gather(loc, x0, n), g["sym_pcgjac_fixed7_x"]) <= 1e-12
+    # unpreconditioned (DummyPcCL) and omega != 1
+    for v in x0:
+        v.fill(0.0)
+    conv, it, res = gpu.dist_pcg(mats, x0, bs, 400, 1e-10, True, pc=gpu.PC_DUMMY)
+    assert conv and abs(it - int(g["sym_pcgdummy"][1])) <= 1 and rel(gather(loc, x0, n), g["sym_pcgdummy_x"]) <= 1e-10
+    for v in x0:
+        v.fill(0.0)
+    conv, it, res = gpu.dist_pcg(mats, x0, bs, 400, 1e-10, False, omega=0.8)
+    assert conv and abs(it - int(g["sym_pcgjac_w08"][1])) <= 1 and rel(gather(loc, x0, n), g["sym_pcgjac_w08_x"]) <= 1e-10
+
+
+@pytest.mark.parametrize("fe,N,numbering,world", [(2, 16, 1, 4), (2, 16, 0, 3), (1, 24, 0, 2), (2, 12, 1, 8)])
+def test_brick_slabs_match_single_gpu(gpu, fe, N, numbering, world):
+    """Device-generated z-slabs (the multi-GPU bench path) against the single-GPU operator."""
+    from drops_b200 import partition
+    n, nnz = gpu.brick_sizes(fe, N)
+    G = gpu.Matrix.brick(fe, N, numbering)
+    comm = gpu.Comm.local(world)
+    slabs, exs, mats = partition.brick_partition_in_process(fe, N, numbering, world, comm)
+    owned = [s.owned() for s in slabs]
+    assert sum(o.size for o in owned) == n and sum(m.info()["nnz"] for m in mats) == nnz
+    assert np.array_equal(np.sort(np.concatenate(owned)), np.arange(n))
+    for r, (s, o) in enumerate(zip(slabs, owned)):
+        assert np.all(np.diff(o) > 0)
+        assert np.all(gpu.brick_owner(fe, N, numbering, world, o) == r)
+        gg, go = s.ghosts()
+        assert np.array_equal(gpu.brick_owner(fe, N, numbering, world, gg), go)
+        assert set(np.abs(go - r)) <= {1}                       # slabs only talk to their neighbours
+    xin = hash_vector(n)
+    xs = [gpu.Vector.from_host(xin[o]) for o in owned]
+    ys = [gpu.Vector(o.size) for o in owned]
+    gpu.dist_spmv(mats, xs, ys)
+    y = np.full(n, np.nan)
+    for o, v in zip(owned, ys):
+        y[o] = v.download()
+    assert np.array_equal(y, G.spmv(xin))
+    # x* and b = A x*
+    xstar = gpu.brick_solution_host(fe, N, numbering)
+    xsv = [gpu.Vector(o.size) for o in owned]
+    for s, v, o in zip(slabs, xsv, owned):
+        s.solution(v)
+        assert np.array_equal(v.download(), xstar[o])
+    bs = [gpu.Vector(o.size) for o in owned]
+    gpu.dist_spmv(mats, xsv, bs)
+    b = G.spmv(xstar)
+    ref = G.pcg_jacobi(np.zeros(n), b, 2000, 1e-10, True, hist=True)
+    x0 = [gpu.Vector(o.size) for o in owned]
+    conv, it, res, hist = gpu.dist_pcg(mats, x0, bs, 2000, 1e-10, True, hist=True)
+    assert conv and ref[0] and abs(it - ref[1]) <= 1, (it, ref[1])
+    x = np.full(n, np.nan)
+    for o, v in zip(owned, x0):
+        x[o] = v.download()
+    assert rel(x, ref[3]) <= 1e-10
+    k = min(it, ref[1])
+    assert np.allclose(hist[:k + 1], ref[4][:k + 1], rtol=1e-6, atol=1e-15)
+
+
+def test_partition_with_empty_rank_and_nccl_world1(gpu):
+    g = load_golden("brick_fe1_N6_num0.npz")
+    n = int(g["rows"])
+    rb, ci, va = g["rowbeg"], g["colind"], g["val"]
+    part = np.zeros(n, np.int32)
+    part[n // 3:] = 2                                          # rank 1 owns nothing
+    comm, loc, mats = build_parts(gpu, rb, ci, va, part, 3)
+    xs = scatter(gpu, loc, g["x_in"])
+    ys = [gpu.Vector(l[0].size) for l in loc]
+    gpu.dist_spmv(mats, xs, ys)
+    assert np.array_equal(gather(loc, ys, n), g["y_Ax"])
+    bs = scatter(gpu, loc, g["b"])
+    x0 = [gpu.Vector(l[0].size) for l in loc]
+    conv, it, res = gpu.dist_pcg(mats, x0, bs, 400, 1e-10, True)
+    assert conv and abs(it - int(g["sym_pcgjac"][1])) <= 1 and rel(gather(loc, x0, n), g["sym_pcgjac_x"]) <= 1e-10
+    # an NCCL communicator of one rank needs no NCCL: same entry points, one partition
+    from drops_b200 import partition
+    c1 = gpu.Comm.nccl(0, 1)
+    owned, lrb, lci, lva, ex = partition.local_system(rb, ci, va, np.zeros(n, np.int32), 0, 1)
+    A = gpu.DistMatrix(c1, ex, lrb, lci, lva)
+    xv, yv = gpu.Vector.from_host(g["x_in"]), gpu.Vector(n)
+    gpu.dist_spmv([A], [xv], [yv])
+    assert np.array_equal(yv.download(), g["y_Ax"])
+    # wrong number of partitions for the communicator / missing diagonal
+    with pytest.raises(gpu.DropsB200Error):
+        gpu.dist_spmv(mats[:2], xs[:2], ys[:2])
+    Z = gpu.DistMatrix(c1, gpu.Exchange(0, 1, [0, 1], [], []), [0, 1, 2], [1, 0], [1., 1.])
+    with pytest.raises(gpu.DropsB200Error) as ei:
+        gpu.dist_pcg([Z], [gpu.Vector(2)], [gpu.Vector(2)], 5, 1e-10)
+    assert ei.value.code == -5
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gpu_count():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=30).stdout
+        return sum(1 for l in out.splitlines() if l.startswith("GPU "))
+    except Exception:
+        return 0
+
+
+def test_two_ranks_over_nccl(gpu):
+    """One process per GPU, NCCL halo + all-gather; needs >= 2 GPUs (skipped on the 1-GPU box)."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(ROOT, "tests", "dist_worker_gpu.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("WORKER_OK") == 2, r.stdout[-3000:] + r.stderr[-3000:]
