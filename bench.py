@@ -155,6 +155,16 @@ def dist_setup(n_gpus):
     return rank, world, local, dist
 
 
+C2_ROWS = 50243409          # rows of BASELINE.json configs[1]; the unit of `value` at every N
+WEAK_CELLS = {1: 185, 2: 233, 4: 294, 8: 369}   # cubic bricks with ~50 M rows per GPU; 8 -> C5 (400 M DOF)
+
+
+def cells_for(args, world):
+    if args.cells != 185:
+        return max(2, int(round(args.cells * world ** (1.0 / 3.0))))
+    return WEAK_CELLS.get(world, int(round(185 * world ** (1.0 / 3.0))))
+
+
 # ------------------------------------------------------------------------------------------------
 # reference arm
 # ------------------------------------------------------------------------------------------------
@@ -163,22 +173,23 @@ def run_reference(args):
     if rank != 0:
         return
     from drops_b200 import capi
-    n_full, nnz_full = capi.brick_sizes(args.fe, args.cells)
-    # grow with the device count like our weak-scaling arm (rows per GPU fixed)
-    n_total = n_full * max(args.gpus, 1)
+    N = cells_for(args, max(args.gpus, 1))
+    n_total, nnz_full = capi.brick_sizes(args.fe, N)
     r = cpu_reference_run(args.cpu_cells, args.cpu_iters, args.fe, args.numbering,
                           repeats=max(args.steps, 1), warm=max(args.warmup, 0))
-    scale = r["rows"] / n_total
-    value = scale / r["sec_per_iter"]
+    # same unit as our arm: C2-equivalent iterations/s = row-iterations/s / rows(C2); the host CPUs do
+    # not grow with --gpus, so this is the same number at every N
+    unit_rows = C2_ROWS if (args.fe == 2 and args.cells == 185) else capi.brick_sizes(args.fe, args.cells)[0]
+    value = (r["rows"] / unit_rows) / r["sec_per_iter"]
     sample = (f"P{args.fe} brick N={args.cpu_cells} ({r['rows']} rows, {r['nnz']} nnz), {args.cpu_iters} PCG-Jacobi "
-              f"iterations per step, iterations/s scaled by rows {r['rows']}/{n_total} to the full workload")
+              f"iterations per step; row-iterations/s divided by {unit_rows} rows (one C2-sized iteration)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(r["times"])),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C2: P{args.fe} Poisson, Kuhn brick N={args.cells} per GPU-count unit, "
-                               f"{n_total} rows, PCG + JACPcCL, tol=0", "numbering": args.numbering,
-                   "cpu_sample_cells": args.cpu_cells},
+        "config": {"workload": f"P{args.fe} Poisson, Kuhn brick N={N} ({n_total} rows) at {args.gpus} GPU(s), PCG + JACPcCL, "
+                               f"tol=0; value in C2-equivalent iterations/s ({unit_rows} rows per unit)",
+                   "numbering": args.numbering, "cpu_sample_cells": args.cpu_cells},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample,
                          "spmv_gbs_reference_layout": r["spmv_gbs_ref_layout"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -197,8 +208,7 @@ def run_ours(args):
         _build.build()
     capi.init(local)
     if world > 1:
-        from drops_b200 import dist_bench
-        return dist_bench.run(args, rank, world, local, dist)
+        return run_ours_dist(args, rank, world, local, dist)
 
     fe, N, numbering, iters = args.fe, args.cells, args.numbering, args.iters
     n, nnz = capi.brick_sizes(fe, N)
@@ -329,6 +339,139 @@ def run_ours(args):
         "final_relative_residual": resid,
     }
     print(json.dumps(line), flush=True)
+
+
+
+def run_ours_dist(args, rank, world, local, dist):
+    """N > 1: the brick grows with N (weak scaling, ~50 M rows per GPU; N = 8 is BASELINE config 5, the
+    400 M-DOF system), z-slab row partition, one process per GPU, halo + reductions over NCCL."""
+    import torch
+    from drops_b200 import capi, partition
+    fe, numbering, iters = args.fe, args.numbering, args.iters
+    N = cells_for(args, world)
+    n, nnz = capi.brick_sizes(fe, N)
+    unit_rows = C2_ROWS if (fe == 2 and args.cells == 185) else capi.brick_sizes(fe, args.cells)[0]
+    comm = partition.make_comm(dist, rank, world)
+    t0 = time.perf_counter()
+    slab, ex, A = partition.brick_partition(fe, N, numbering, rank, world, comm, dist)
+    capi.synchronize()
+    gen_s = time.perf_counter() - t0
+    info = A.info()
+    no = info["n_owned"]
+    xs, b, x = capi.Vector(no), capi.Vector(no), capi.Vector(no)
+    slab.solution(xs)
+    capi.dist_spmv([A], [xs], [b])
+
+    def solve_dev():
+        x.fill(0.0)
+        conv, it, res = capi.dist_pcg([A], [x], [b], iters, 0.0, True)
+        assert not conv and it == iters
+        return res
+
+    def tmax(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def tsum(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.item()
+
+    for _ in range(args.warmup):
+        solve_dev()
+    capi.set_option("timing", 1)
+    capi.timing_reset()
+    sampler = ClockSampler(local)
+    sampler.start()
+    capi.synchronize()
+    torch.cuda.synchronize()
+    dist.barrier()
+    l0 = capi.launch_count()
+    capi.timer_start()
+    for _ in range(args.steps):
+        resid = solve_dev()
+    ms_local = capi.timer_stop()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = tmax(ms_local)
+    launches = tsum(capi.launch_count() - l0)
+    clocks = sampler.stop()
+    t_int, c_int = capi.timing("spmv")
+    t_bnd, c_bnd = capi.timing("spmv.bnd")
+    t_upd, _ = capi.timing("pcg.update")
+    t_dir, _ = capi.timing("pcg.direction")
+    t_pack, _ = capi.timing("halo.pack")
+    t_ag, _ = capi.timing("allgather")
+    capi.set_option("timing", 0)
+    global_it_s = args.steps * iters / (ms / 1e3)
+    value = global_it_s * n / unit_rows
+
+    # roofline of the dominant kernel on rank 0: interior-row SpMV of the partition
+    peak, peak_src = measured_peaks()
+    frac_int = info["interior_rows"] / max(no, 1)
+    spmv_bytes = (12.0 * info["nnz"] + 4.0 * (no + 1) + 16.0 * no) * frac_int
+    spmv_avg_ms = t_int / max(c_int, 1)
+    achieved = spmv_bytes / (spmv_avg_ms / 1e3) / 1e9
+    iter_bytes = 12.0 * info["nnz"] + 4.0 * (no + 1) + 13.0 * 8.0 * no
+    roofline = {"bound": "hbm", "kernel": "k_spmv_sell<EPI_NONE,exact,dot> on the interior rows of rank 0's partition",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": None, "algorithmic_bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_avg_ms,
+                "launches": c_int,
+                "iteration": {"algorithmic_bytes_per_gpu": iter_bytes,
+                              "achieved_gbs_per_gpu": iter_bytes * args.steps * iters / (ms / 1e3) / 1e9,
+                              "frac": iter_bytes * args.steps * iters / (ms / 1e3) / 1e9 / peak,
+                              "kernel_ms_share_rank0": {"spmv.interior": t_int / ms_local, "spmv.boundary": t_bnd / ms_local,
+                                                        "pcg.update": t_upd / ms_local, "pcg.direction": t_dir / ms_local,
+                                                        "halo.pack": t_pack / ms_local, "allgather": t_ag / ms_local}}}
+
+    # end to end: host buffers of every rank's slice go up, the solution slice comes back, every step
+    hb = torch.empty(no, dtype=torch.float64).pin_memory()
+    hx = torch.zeros(no, dtype=torch.float64).pin_memory()
+    hb.numpy()[:] = b.download()
+
+    def solve_host():
+        b.upload(hb.numpy())
+        x.upload(np.zeros(no))
+        conv, it, res = capi.dist_pcg([A], [x], [b], iters, 0.0, True)
+        hx.numpy()[:] = x.download()
+        return res
+
+    solve_host()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res_host = solve_host()
+    torch.cuda.synchronize()
+    dist.barrier()
+    wall = tmax(time.perf_counter() - t0)
+    e2e = {"value": args.steps * iters / wall * n / unit_rows, "unit": UNIT, "h2d_bytes_per_step": 16 * n,
+           "d2h_bytes_per_step": 8 * n, "ms_per_step": 1e3 * wall / args.steps,
+           "note": "every rank uploads its slices of x and b and downloads its slice of x inside each Solve"}
+    ghosts = tsum(info["n_ghost"])
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"P{fe} Poisson on the Kuhn brick, N={N} cells/direction, {n} rows, {nnz} nnz "
+                                   f"({n / world:.0f} rows per GPU; N=369 at 8 GPUs is BASELINE config 5), z-slab row "
+                                   f"partition, PCGSolverCL<JACPcCL>, {iters} iterations per step, tol=0, relative",
+                       "value_unit": f"C2-equivalent iterations/s = global iterations/s x rows/{unit_rows}; equals plain "
+                                     "iterations/s on C2 at 1 GPU",
+                       "global_iterations_per_s": global_it_s,
+                       "numbering": "vertices-then-edges (DROPS order)" if numbering == 1 else "lexicographic",
+                       "cache": "per-GPU inputs (17 GB matrix, 0.4 GB vectors) far exceed the 126 MB L2; no flush needed",
+                       "partition": {"ghost_entries_total": ghosts, "rank0": info}, "generate_s": gen_s},
+            "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "final_relative_residual": resid,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    A.close()
+    comm.close()
+    dist.destroy_process_group()
 
 
 def main():

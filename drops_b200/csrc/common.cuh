@@ -65,14 +65,20 @@ __device__ __forceinline__ dd dd_add(dd a, dd b)
     s.lo = __dadd_rn(s.lo, __dadd_rn(a.lo, b.lo));
     return quick_two_sum(s.hi, s.lo);
 }
-// acc += a*b with the product taken exactly (FMA residual).
+// acc += a*b, compensated (the Dot2 step of Ogita/Rump/Oishi): exact product via the FMA residual,
+// error-free sum of the high parts, all error terms collected in acc.lo WITHOUT renormalising.
+// The loop-carried dependency is the single add on acc.hi; the error chain runs beside it.  (The
+// renormalising variant serialised ~10 fp64 operations per row at the tail of every SpMV slice,
+// profiles/r01_notes.md.)  The result is as accurate as a sum in twice the working precision,
+// i.e. better than the reference's Kahan sum of rounded products (num/spmat.h:317-333).
 __device__ __forceinline__ dd dd_add_prod(dd acc, double a, double b)
 {
-    const double p = __dmul_rn(a, b);
-    const double e = __fma_rn(a, b, -p);
-    dd s = two_sum(acc.hi, p);
-    s.lo = __dadd_rn(s.lo, __dadd_rn(acc.lo, e));
-    return quick_two_sum(s.hi, s.lo);
+    const double p  = __dmul_rn(a, b);
+    const double ep = __fma_rn(a, b, -p);
+    const double s  = __dadd_rn(acc.hi, p);
+    const double bb = __dsub_rn(s, acc.hi);
+    const double es = __dadd_rn(__dsub_rn(acc.hi, __dsub_rn(s, bb)), __dsub_rn(p, bb));
+    return dd{s, __dadd_rn(acc.lo, __dadd_rn(ep, es))};
 }
 __device__ __forceinline__ double dd_round(dd a) { return __dadd_rn(a.hi, a.lo); }
 

@@ -48,12 +48,13 @@ struct EpiArgs {
     unsigned* ticket;
 };
 
+// s = row sum, av = the row's aux entry (d_i, b_i or z_i)
 template <int EPI>
-__device__ __forceinline__ double apply_epilogue(double s, int row, const EpiArgs& e, double beta)
+__device__ __forceinline__ double apply_epilogue(double s, double av, const EpiArgs& e, double beta)
 {
-    if (EPI == EPI_JACOBI) return __ddiv_rn(__dmul_rn(e.omega, s), __ldg(e.aux + row));
-    if (EPI == EPI_RESID)  return __dsub_rn(__ldg(e.aux + row), s);
-    if (EPI == EPI_AXMBY)  return __dsub_rn(s, __dmul_rn(beta, __ldg(e.aux + row)));
+    if (EPI == EPI_JACOBI) return __ddiv_rn(__dmul_rn(e.omega, s), av);
+    if (EPI == EPI_RESID)  return __dsub_rn(av, s);
+    if (EPI == EPI_AXMBY)  return __dsub_rn(s, __dmul_rn(beta, av));
     return s;
 }
 
@@ -80,13 +81,16 @@ __device__ __forceinline__ double load_x(const double* __restrict__ x, const Epi
     return __ldg(x + c);
 }
 
-template <int EPI, bool EXACT, bool DOT, int U, int MINB, bool SPLIT = false>
-__global__ void __launch_bounds__(512, MINB)
+// DOT: 0 = none; 1 = fused dot finished in this kernel (block reduce + two-level grid reduce);
+// 2 = fused dot, every WARP stores its double-double partial and k_sum_warp_partials finishes it
+// (no block barrier and no atomics in the SpMV itself).
+template <int EPI, bool EXACT, int DOT, int U, int MAXT, int MINB, bool SPLIT = false>
+__global__ void __launch_bounds__(MAXT, MINB)
 k_spmv_sell(SellView A, const double* __restrict__ x, double* __restrict__ y, EpiArgs e)
 {
     constexpr int kSellUnroll = U;
     if (e.done != nullptr && *e.done != 0) return;
-    __shared__ dd red_smem[32];
+    __shared__ dd red_smem[DOT == 1 ? 32 : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const long long s_begin = A.nslices * (long long)blockIdx.x / gridDim.x;
     const long long s_end   = A.nslices * (long long)(blockIdx.x + 1) / gridDim.x;
@@ -104,6 +108,14 @@ k_spmv_sell(SellView A, const double* __restrict__ x, double* __restrict__ y, Ep
             const int nlines = (int)((A.slice_ptr[s + nwarp + 1] - nb) >> 5);   // = width: 128 B col lines
             for (int l = lane; l < nlines; l += 32) prefetch_l2(A.col + nb + (int64_t)l * 32);
             for (int l = lane; l < 2 * nlines; l += 32) prefetch_l2(A.val + nb + (int64_t)l * 16);
+        }
+        // the row index and the row's epilogue operands are fetched up front: their latency hides
+        // behind the matrix stream instead of trailing it (two dependent misses per slice otherwise)
+        const int row = A.perm[s * 32 + lane];
+        double dv = 0.0, av = 0.0;
+        if (row >= 0) {
+            if (DOT) dv = __ldg(e.dotv + row);
+            if (EPI != EPI_NONE) av = __ldg(e.aux + row);
         }
         double sum = 0.0;
         int j = 0;
@@ -131,17 +143,35 @@ k_spmv_sell(SellView A, const double* __restrict__ x, double* __restrict__ y, Ep
                 sum = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv)) : fma(v, xv, sum);
             }
         }
-        const int row = A.perm[s * 32 + lane];
         if (row >= 0) {
-            const double out = apply_epilogue<EPI>(sum, row, e, beta);
+            const double out = apply_epilogue<EPI>(sum, av, e, beta);
             y[row] = out;
-            if (DOT) acc[0] = dd_add_prod(acc[0], out, __ldg(e.dotv + row));
+            if (DOT) acc[0] = dd_add_prod(acc[0], out, dv);
         }
     }
-    if (DOT) {
+    if (DOT == 1) {
         if (grid_reduce_dd<1>(acc, red_smem, e.partials, e.ticket)) {
             if (threadIdx.x == 0) store_dot(e, acc[0]);
         }
+    }
+    if (DOT == 2) {
+        const dd w = warp_reduce_dd(acc[0]);
+        if (lane == 0) e.partials[(size_t)blockIdx.x * nwarp + warp] = w;
+    }
+}
+
+// Second half of DOT == 2: deterministic sum of the per-warp partials (fixed thread assignment,
+// fixed order, fixed tree).
+__global__ void __launch_bounds__(kReduceThreads)
+k_sum_warp_partials(long long count, const dd* __restrict__ in, EpiArgs e, dd* partials, unsigned* ticket)
+{
+    __shared__ dd red_smem[32];
+    if (e.done != nullptr && *e.done != 0) return;
+    dd acc[1] = {dd_zero()};
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) acc[0] = dd_add(acc[0], in[i]);
+    if (grid_reduce_dd<1>(acc, red_smem, partials, ticket)) {
+        if (threadIdx.x == 0) store_dot(e, acc[0]);
     }
 }
 
@@ -172,7 +202,7 @@ k_spmv_csr_vector(long long rows, const int64_t* __restrict__ rowptr, const int3
 #pragma unroll
         for (int m = LANES / 2; m >= 1; m >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, m);
         if (row < rows && sub == 0) {
-            const double out = apply_epilogue<EPI>(sum, (int)row, e, beta);
+            const double out = apply_epilogue<EPI>(sum, EPI != EPI_NONE ? __ldg(e.aux + row) : 0.0, e, beta);
             y[row] = out;
             if (DOT) acc[0] = dd_add_prod(acc[0], out, __ldg(e.dotv + row));
         }
@@ -205,38 +235,59 @@ static EpiArgs make_epi(const SpmvArgs& a)
     return e;
 }
 
-template <int EPI, bool EXACT, int U, int MINB, bool SPLIT = false>
+template <int EPI, bool EXACT, int U, int MAXT, int MINB, bool SPLIT = false>
 static void launch_sell_v(const SellView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads,
                           cudaStream_t st)
 {
-    if (a.dotv != nullptr)
-        k_spmv_sell<EPI, EXACT, true, U, MINB, SPLIT><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
-    else
-        k_spmv_sell<EPI, EXACT, false, U, MINB, SPLIT><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
+    if (threads > MAXT) threads = MAXT;
+    if (a.dotv == nullptr) {
+        k_spmv_sell<EPI, EXACT, 0, U, MAXT, MINB, SPLIT><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
+        return;
+    }
+    const long long nwarps = (long long)grid * (threads >> 5);
+    if (opt("spmv.dotmode", 2.0) == 2.0 && nwarps <= kPartialStride) {
+        k_spmv_sell<EPI, EXACT, 2, U, MAXT, MINB, SPLIT><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
+        Ctx& c = ctx();
+        const int g2 = vec_grid((size_t)nwarps, kReduceThreads, 2);
+        k_sum_warp_partials<<<g2, kReduceThreads, 0, st>>>(nwarps, e.partials, e, c.partials + (size_t)3 * kPartialStride,
+                                                         c.tickets + (size_t)3 * kTicketStride);
+        count_launch();
+    } else {
+        k_spmv_sell<EPI, EXACT, 1, U, MAXT, MINB, SPLIT><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
+    }
 }
 
-// "spmv.variant": 0 = U4/<=40 regs (default: best in profiles/r01_sweep2_spmv.jsonl), 1 = U8/<=64,
-// 2 = U4/<=64, 3 = U4/<=32, 4 = U2/<=32, 5 = U8/<=40.  Only the plain product (the PCG kernel) is
+// "spmv.variant": 0 = U4/<=40 regs (default), 1 = U8/<=64, 2 = U4/<=64, 3 = U4/<=32, 4 = U2/<=32,
+// 5 = U8/<=40, 6 = U4/<=48 (128-thread CTAs only), 7 = U4/<=56, 8 = U8/<=48.  Only the plain product (the PCG kernel) is
 // built in all variants; the epilogue forms use the default.
 template <int EPI, bool EXACT>
 static void launch_sell(const SellView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads,
                         cudaStream_t st)
 {
     if (a.xghost != nullptr) {   // boundary rows of a partition: a thin operator, one variant
-        launch_sell_v<EPI, EXACT, 4, 3, true>(v, a, e, grid, threads, st);
+        launch_sell_v<EPI, EXACT, 4, 512, 2, true>(v, a, e, grid, threads, st);
         return;
     }
+    // measured on B200 (profiles/r01_probe_dot.json): the plain product is fastest with U4 and <= 40
+    // registers (2.96 ms at C2), the product with the fused dot needs the room of U8 / <= 48
+    // registers (3.12 ms; 3.55 ms when squeezed into 40)
+    const int variant = (int)(a.dotv != nullptr ? opt("spmv.dotvariant", 8.0) : opt("spmv.variant", 0.0));
     if (EPI == EPI_NONE) {
-        switch ((int)opt("spmv.variant", 0.0)) {
-            case 1: launch_sell_v<EPI_NONE, EXACT, 8, 2>(v, a, e, grid, threads, st); return;
-            case 2: launch_sell_v<EPI_NONE, EXACT, 4, 2>(v, a, e, grid, threads, st); return;
-            case 3: launch_sell_v<EPI_NONE, EXACT, 4, 4>(v, a, e, grid, threads, st); return;
-            case 4: launch_sell_v<EPI_NONE, EXACT, 2, 4>(v, a, e, grid, threads, st); return;
-            case 5: launch_sell_v<EPI_NONE, EXACT, 8, 3>(v, a, e, grid, threads, st); return;
+        switch (variant) {
+            case 1: launch_sell_v<EPI_NONE, EXACT, 8, 512, 2>(v, a, e, grid, threads, st); return;
+            case 2: launch_sell_v<EPI_NONE, EXACT, 4, 512, 2>(v, a, e, grid, threads, st); return;
+            case 3: launch_sell_v<EPI_NONE, EXACT, 4, 512, 4>(v, a, e, grid, threads, st); return;
+            case 4: launch_sell_v<EPI_NONE, EXACT, 2, 512, 4>(v, a, e, grid, threads, st); return;
+            case 5: launch_sell_v<EPI_NONE, EXACT, 8, 512, 3>(v, a, e, grid, threads, st); return;
+            case 6: launch_sell_v<EPI_NONE, EXACT, 4, 128, 10>(v, a, e, grid, threads, st); return;   // <= 48 regs
+            case 7: launch_sell_v<EPI_NONE, EXACT, 4, 128, 9>(v, a, e, grid, threads, st); return;    // <= 56 regs
+            case 8: launch_sell_v<EPI_NONE, EXACT, 8, 128, 10>(v, a, e, grid, threads, st); return;
+            case 0: launch_sell_v<EPI_NONE, EXACT, 4, 512, 3>(v, a, e, grid, threads, st); return;
             default: break;
         }
     }
-    launch_sell_v<EPI, EXACT, 4, 3>(v, a, e, grid, threads, st);
+    if (a.dotv != nullptr) launch_sell_v<EPI, EXACT, 8, 128, 10>(v, a, e, grid, threads, st);
+    else launch_sell_v<EPI, EXACT, 4, 512, 3>(v, a, e, grid, threads, st);
 }
 
 template <bool EXACT>

@@ -77,7 +77,7 @@ def test_partitioned_matches_reference_golden(gpu, world):
         v.fill(0.0)
     conv, it, res = gpu.dist_pcg(mats, x0, bs, 7, 0.0, True)
     assert not conv and it == 7
-    assert abs(res - g["sym_pcgjac_fixed7"][2]) <= 1e-9 * g["sym_pcgjac_fixed7"][2]
+    assert abs(res - g["sym_pcgjac_fixed7"][2]) <= 1e-9 * g["sym_pcgjac_fixed7"][2] + 1e-15
     assert rel(gather(loc, x0, n), g["sym_pcgjac_fixed7_x"]) <= 1e-12
     # unpreconditioned (DummyPcCL) and omega != 1
     for v in x0:
