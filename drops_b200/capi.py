@@ -52,6 +52,7 @@ SIGNATURES = {
     "drops_b200_matrix_update_values": (_i, [_vp, _dp, C.c_uint64]),
     "drops_b200_matrix_destroy": (_i, [_vp]),
     "drops_b200_matrix_info": (_i, [_vp, _szpp, _szpp, _szpp, C.POINTER(C.c_uint64), _szpp, _szpp]),
+    "drops_b200_matrix_format": (_i, [_vp, _szpp, _szpp, _ip, _szpp]),
     "drops_b200_matrix_download": (_i, [_vp, _szp, _szp, _dp]),
     "drops_b200_spmv": (_i, [_vp, _dp, _dp]),
     "drops_b200_spmv_transpose": (_i, [_vp, _dp, _dp]),
@@ -335,6 +336,12 @@ class Matrix:
                                            C.byref(db), C.byref(pn)))
         return {"rows": r.value, "cols": c.value, "nnz": z.value, "version": v.value,
                 "device_bytes": db.value, "padded_nnz": pn.value}
+
+    def format(self):
+        ns, pn, ws = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        cmp_ = C.c_int()
+        check(lib().drops_b200_matrix_format(self.h, C.byref(ns), C.byref(pn), C.byref(cmp_), C.byref(ws)))
+        return {"nslices": ns.value, "padded_nnz": pn.value, "compressed": bool(cmp_.value), "wide_slices": ws.value}
 
     def download(self):
         rb = np.zeros(self.rows + 1, np.uint64)

@@ -304,6 +304,14 @@ struct SellOp {
     double*  val = nullptr;
     int32_t* perm = nullptr;         // sorted position -> original row, -1 beyond rows
     int max_width = 0;
+    // 16-bit column deltas ("sell.compress"): entry j of the 32 rows of a slice are neighbouring
+    // rows with the same stencil, so their columns lie within 2^16 of each other: col = cbase[slice
+    // entry j] + col16 (0xFFFF = padding).  Slices where that fails are flagged wide and keep using
+    // col.  10.1 instead of 12 bytes per stored entry on the stream that bounds the kernel.
+    uint16_t* col16 = nullptr;       // padded entries, or nullptr when compression is off
+    int32_t* cbase = nullptr;        // padded/32 entries
+    uint8_t* wide = nullptr;         // nslices flags
+    size_t nwide = 0;
 };
 
 struct CsrDev {

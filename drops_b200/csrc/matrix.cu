@@ -125,6 +125,36 @@ __global__ void k_sell_fill(long long nslices, const int64_t* __restrict__ slice
     }
 }
 
+// One warp per slice: column base per slice entry (minimum over the 32 rows) + 16-bit deltas.
+__global__ void k_sell_compress(long long nslices, const int64_t* __restrict__ slice_ptr,
+                                const int32_t* __restrict__ scol, uint16_t* __restrict__ col16,
+                                int32_t* __restrict__ cbase, uint8_t* __restrict__ wide,
+                                unsigned long long* __restrict__ nwide)
+{
+    const int lane = threadIdx.x & 31;
+    const long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= nslices) return;
+    const int64_t base = slice_ptr[s];
+    const int width = (int)((slice_ptr[s + 1] - base) >> 5);
+    bool ok = true;
+    for (int j = 0; j < width; ++j) {
+        const int32_t c = scol[base + (int64_t)j * 32 + lane];
+        int32_t mn = c >= 0 ? c : 0x7fffffff;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, m));
+        if (mn == 0x7fffffff) mn = 0;
+        const long long d = c >= 0 ? (long long)c - mn : 0xFFFF;
+        ok = ok && (c < 0 || d < 0xFFFF);
+        col16[base + (int64_t)j * 32 + lane] = (uint16_t)(c >= 0 && d < 0xFFFF ? d : 0xFFFF);
+        if (lane == 0) cbase[(base >> 5) + j] = mn;
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) {
+        wide[s] = ok ? 0 : 1;
+        if (!ok) atomicAdd(nwide, 1ULL);
+    }
+}
+
 // Only the values change (same pattern): refill sval from the CSR values.
 __global__ void k_sell_refill_values(long long nslices, const int64_t* __restrict__ slice_ptr,
                                      const int32_t* __restrict__ perm, const int64_t* __restrict__ rowptr,
@@ -224,6 +254,7 @@ double* work_vec(drops_b200_matrix_s* M, int i)
 void free_sell(SellOp& s)
 {
     dev_free(s.slice_ptr); dev_free(s.col); dev_free(s.val); dev_free(s.perm);
+    dev_free(s.col16); dev_free(s.cbase); dev_free(s.wide);
     s = SellOp();
 }
 
@@ -290,7 +321,29 @@ int build_sell(const CsrDev& A, SellOp& S, size_t* bytes, const int32_t* rowmap,
         DB_CUDA(cudaGetLastError());
     }
     DB_CUDA(cudaStreamSynchronize(st));
-    if (bytes) *bytes += S.padded * 12 + (S.nslices + 1) * 8 + padded_rows * 4;
+    size_t col_bytes = S.padded * 4;
+    if (S.padded > 0 && opt("sell.compress", 1.0) != 0.0) {
+        unsigned long long* d_nwide = nullptr;
+        DB_CHECK(dev_alloc(&S.col16, S.padded));
+        DB_CHECK(dev_alloc(&S.cbase, S.padded / 32));
+        DB_CHECK(dev_alloc(&S.wide, S.nslices));
+        DB_CHECK(dev_alloc(&d_nwide, 1));
+        DB_CUDA(cudaMemsetAsync(d_nwide, 0, sizeof(unsigned long long), st));
+        k_sell_compress<<<blocks_for((long long)S.nslices * 32, 256), 256, 0, st>>>(
+            (long long)S.nslices, S.slice_ptr, S.col, S.col16, S.cbase, S.wide, d_nwide);
+        count_launch();
+        unsigned long long nw = 0;
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&nw, d_nwide, sizeof nw, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        dev_free(d_nwide);
+        DB_CUDA(e);
+        S.nwide = (size_t)nw;
+        col_bytes = S.padded * 2 + S.padded / 32 * 4 + S.nslices;
+        if (S.nwide == 0) { dev_free(S.col); S.col = nullptr; }      // no slice needs the 32-bit columns
+        else col_bytes += S.padded * 4;
+    }
+    if (bytes) *bytes += S.padded * 8 + col_bytes + (S.nslices + 1) * 8 + padded_rows * 4;
     return 0;
 }
 
@@ -548,6 +601,17 @@ int drops_b200_matrix_info(drops_b200_matrix_t M, size_t* rows, size_t* cols, si
     if (version) *version = M->version;
     if (device_bytes) *device_bytes = M->device_bytes;
     if (padded_nnz) *padded_nnz = M->sell.padded;
+    return 0;
+}
+
+int drops_b200_matrix_format(drops_b200_matrix_t M, size_t* nslices, size_t* padded_nnz, int* compressed,
+                             size_t* wide_slices)
+{
+    DB_ARG(M != nullptr, "null matrix");
+    if (nslices) *nslices = M->sell.nslices;
+    if (padded_nnz) *padded_nnz = M->sell.padded;
+    if (compressed) *compressed = M->sell.col16 != nullptr;
+    if (wide_slices) *wide_slices = M->sell.nwide;
     return 0;
 }
 

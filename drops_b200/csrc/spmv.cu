@@ -29,6 +29,9 @@ struct SellView {
     const double* val;
     const int32_t* perm;
     long long nslices;
+    const uint16_t* col16;     // 16-bit column deltas (nullptr: not compressed)
+    const int32_t* cbase;
+    const uint8_t* wide;
 };
 
 struct EpiArgs {
@@ -81,6 +84,55 @@ __device__ __forceinline__ double load_x(const double* __restrict__ x, const Epi
     return __ldg(x + c);
 }
 
+// Sum of one row of a slice, left to right.  C16: columns as cbase[entry] + 16-bit delta.
+template <bool EXACT, int U, bool SPLIT, bool C16>
+__device__ __forceinline__ double slice_row_sum(const SellView& A, int64_t base, int width, int lane,
+                                                const double* __restrict__ x, const EpiArgs& e)
+{
+    const double* vp = A.val + base + lane;
+    const int32_t* cp = C16 ? nullptr : A.col + base + lane;
+    const uint16_t* dp = C16 ? A.col16 + base + lane : nullptr;
+    const int32_t* bp = C16 ? A.cbase + (base >> 5) : nullptr;
+    double sum = 0.0;
+    int j = 0;
+    for (; j + U <= width; j += U) {
+        int c[U];
+        double v[U], xv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (C16) {
+                const int d = (int)__ldcs(dp + (size_t)(j + u) * 32);
+                c[u] = d == 0xFFFF ? -1 : __ldg(bp + j + u) + d;
+            } else {
+                c[u] = __ldcs(cp + (size_t)(j + u) * 32);
+            }
+            v[u] = __ldcs(vp + (size_t)(j + u) * 32);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) xv[u] = c[u] >= 0 ? load_x<SPLIT>(x, e, c[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (c[u] >= 0)
+                sum = EXACT ? __dadd_rn(sum, __dmul_rn(v[u], xv[u])) : fma(v[u], xv[u], sum);
+        }
+    }
+    for (; j < width; ++j) {
+        int c;
+        if (C16) {
+            const int d = (int)__ldcs(dp + (size_t)j * 32);
+            c = d == 0xFFFF ? -1 : __ldg(bp + j) + d;
+        } else {
+            c = __ldcs(cp + (size_t)j * 32);
+        }
+        const double v = __ldcs(vp + (size_t)j * 32);
+        if (c >= 0) {
+            const double xv = load_x<SPLIT>(x, e, c);
+            sum = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv)) : fma(v, xv, sum);
+        }
+    }
+    return sum;
+}
+
 // DOT: 0 = none; 1 = fused dot finished in this kernel (block reduce + two-level grid reduce);
 // 2 = fused dot, every WARP stores its double-double partial and k_sum_warp_partials finishes it
 // (no block barrier and no atomics in the SpMV itself).
@@ -100,13 +152,10 @@ k_spmv_sell(SellView A, const double* __restrict__ x, double* __restrict__ y, Ep
     for (long long s = s_begin + warp; s < s_end; s += nwarp) {
         const int64_t base = A.slice_ptr[s];
         const int width = (int)((A.slice_ptr[s + 1] - base) >> 5);
-        const int32_t* cp = A.col + base + lane;
-        const double* vp = A.val + base + lane;
         if (e.prefetch && s + nwarp < s_end) {
-            // pull the slice this warp handles next into L2 while the current one is consumed
+            // pull the values of the slice this warp handles next into L2 while the current one is consumed
             const int64_t nb = A.slice_ptr[s + nwarp];
-            const int nlines = (int)((A.slice_ptr[s + nwarp + 1] - nb) >> 5);   // = width: 128 B col lines
-            for (int l = lane; l < nlines; l += 32) prefetch_l2(A.col + nb + (int64_t)l * 32);
+            const int nlines = (int)((A.slice_ptr[s + nwarp + 1] - nb) >> 5);
             for (int l = lane; l < 2 * nlines; l += 32) prefetch_l2(A.val + nb + (int64_t)l * 16);
         }
         // the row index and the row's epilogue operands are fetched up front: their latency hides
@@ -117,32 +166,9 @@ k_spmv_sell(SellView A, const double* __restrict__ x, double* __restrict__ y, Ep
             if (DOT) dv = __ldg(e.dotv + row);
             if (EPI != EPI_NONE) av = __ldg(e.aux + row);
         }
-        double sum = 0.0;
-        int j = 0;
-        for (; j + kSellUnroll <= width; j += kSellUnroll) {
-            int c[kSellUnroll];
-            double v[kSellUnroll], xv[kSellUnroll];
-#pragma unroll
-            for (int u = 0; u < kSellUnroll; ++u) {
-                c[u] = __ldcs(cp + (size_t)(j + u) * 32);
-                v[u] = __ldcs(vp + (size_t)(j + u) * 32);
-            }
-#pragma unroll
-            for (int u = 0; u < kSellUnroll; ++u) xv[u] = c[u] >= 0 ? load_x<SPLIT>(x, e, c[u]) : 0.0;
-#pragma unroll
-            for (int u = 0; u < kSellUnroll; ++u) {
-                if (c[u] >= 0)
-                    sum = EXACT ? __dadd_rn(sum, __dmul_rn(v[u], xv[u])) : fma(v[u], xv[u], sum);
-            }
-        }
-        for (; j < width; ++j) {
-            const int c = __ldcs(cp + (size_t)j * 32);
-            const double v = __ldcs(vp + (size_t)j * 32);
-            if (c >= 0) {
-                const double xv = load_x<SPLIT>(x, e, c);
-                sum = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv)) : fma(v, xv, sum);
-            }
-        }
+        const bool c16 = A.col16 != nullptr && A.wide[s] == 0;     // warp-uniform
+        const double sum = c16 ? slice_row_sum<EXACT, kSellUnroll, SPLIT, true>(A, base, width, lane, x, e)
+                               : slice_row_sum<EXACT, kSellUnroll, SPLIT, false>(A, base, width, lane, x, e);
         if (row >= 0) {
             const double out = apply_epilogue<EPI>(sum, av, e, beta);
             y[row] = out;
@@ -333,7 +359,7 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a)
     if (grid > kMaxReduceGrid) grid = kMaxReduceGrid;
     if (grid < 1) grid = 1;
     cudaStream_t st = a.stream ? a.stream : c.stream;
-    SellView v{A.slice_ptr, A.col, A.val, A.perm, (long long)A.nslices};
+    SellView v{A.slice_ptr, A.col, A.val, A.perm, (long long)A.nslices, A.col16, A.cbase, A.wide};
     EpiArgs e = make_epi(a);
     if (opt("spmv.exact", 1.0) != 0.0) launch_sell_epi<true>(v, a, e, (int)grid, threads, st);
     else launch_sell_epi<false>(v, a, e, (int)grid, threads, st);

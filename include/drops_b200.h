@@ -63,8 +63,9 @@ DROPS_B200_API int drops_b200_abi_version(void);
 DROPS_B200_API int drops_b200_compiled_arch(void);
 /* Device facts: sm count, compute capability major*10+minor, free/total bytes. */
 DROPS_B200_API int drops_b200_device_info(int* sm_count, int* cc, size_t* free_bytes, size_t* total_bytes);
-/* Tunables (documented in DESIGN.md): "spmv.kernel", "spmv.threads", "spmv.ctas_per_sm",
- * "spmv.exact", "sell.sigma", "pcg.check_every", "pcg.graph", "timing". */
+/* Tunables: "spmv.kernel", "spmv.threads", "spmv.slices_per_cta", "spmv.exact",
+ * "spmv.variant", "spmv.dotvariant", "spmv.dotmode", "sell.sigma", "sell.compress", "vec.wide",
+ * "pcg.check_every", "timing". */
 DROPS_B200_API int drops_b200_set_option(const char* key, double value);
 DROPS_B200_API int drops_b200_get_option(const char* key, double* value);
 /* Accumulated CUDA-event time (ms) and launch count of a named kernel class since the last
@@ -100,6 +101,11 @@ DROPS_B200_API int drops_b200_matrix_update_values(drops_b200_matrix_t A, const 
 DROPS_B200_API int drops_b200_matrix_destroy(drops_b200_matrix_t A);
 DROPS_B200_API int drops_b200_matrix_info(drops_b200_matrix_t A, size_t* rows, size_t* cols, size_t* nnz,
                                           uint64_t* version, size_t* device_bytes, size_t* padded_nnz);
+/* Storage facts of the sliced-ELL operator: slices of 32 rows, stored entries incl. padding, whether
+ * columns are stored as 16-bit deltas ("sell.compress", default on) and how many slices had to keep
+ * 32-bit columns because their columns spread over more than 2^16. */
+DROPS_B200_API int drops_b200_matrix_format(drops_b200_matrix_t A, size_t* nslices, size_t* padded_nnz,
+                                            int* compressed, size_t* wide_slices);
 /* Copies the device CSR back in the reference layout (for tests and the CPU baseline). */
 DROPS_B200_API int drops_b200_matrix_download(drops_b200_matrix_t A, size_t* rowbeg, size_t* colind, double* val);
 

@@ -91,6 +91,36 @@ def test_spmv_layout_and_launch_options_do_not_change_results(gpu, sigma, thread
         gpu.set_option("spmv.prefetch", 0)
 
 
+def test_column_compression_is_transparent(gpu):
+    """16-bit column deltas: brick slices compress completely, scattered columns fall back to 32 bit
+    per slice; results are bit-identical either way."""
+    g = load_golden("brick_fe2_N6_num1.npz")
+    r = load_golden("random_ragged.npz")
+    n, rb, ci, va = gpu.brick_csr_host(2, 24, 1)
+    xin = hash_vector(n)
+    outs = {}
+    try:
+        for comp in (1, 0):
+            gpu.set_option("sell.compress", comp)
+            A, R, B = gmat(gpu, g), gmat(gpu, r), gpu.Matrix(n, n, rb, ci, va)
+            assert A.format()["compressed"] == bool(comp)
+            assert np.array_equal(A.spmv(g["x_in"]), g["y_Ax"])
+            assert np.array_equal(R.spmv(r["x_in"]), r["y_Ax"])
+            assert np.array_equal(R.spmv_transpose(r["xt_in"] if "xt_in" in r else r["x_in"]), r["y_ATx"])
+            outs[comp] = B.spmv(xin)
+            if comp:
+                assert B.format()["wide_slices"] <= 0.02 * B.format()["nslices"]
+                # a matrix whose columns jump by more than 2^16 inside a slice must take the fallback
+                m = 70000
+                W = gpu.Matrix(64, m, np.arange(65) * 2, np.tile([0, m - 1], 64), np.ones(128))
+                assert W.format()["wide_slices"] > 0
+                xw = hash_vector(m)
+                assert np.array_equal(W.spmv(xw), np.full(64, xw[0] + xw[m - 1]))
+    finally:
+        gpu.set_option("sell.compress", 1)
+    assert np.array_equal(outs[0], outs[1])
+
+
 def test_wide_and_scalar_vector_kernels_agree(gpu):
     g = load_golden("brick_fe2_N6_num1.npz")
     A = gmat(gpu, g)
