@@ -47,6 +47,7 @@ SIGNATURES = {
     "drops_b200_timer_stop": (_i, [_dpp]),
     "drops_b200_launch_count": (C.c_longlong, []),
     "drops_b200_synchronize": (_i, []),
+    "drops_b200_spmv_tma_fault": (_i, []),
     "drops_b200_matrix_create": (_i, [_sz, _sz, _sz, _szp, _szp, _dp, C.c_uint64, _vpp]),
     "drops_b200_matrix_create_device": (_i, [_sz, _sz, _sz, _vp, _vp, _vp, C.c_uint64, _vpp]),
     "drops_b200_matrix_update_values": (_i, [_vp, _dp, C.c_uint64]),
@@ -194,6 +195,10 @@ def timer_stop():
 
 def launch_count():
     return int(lib().drops_b200_launch_count())
+
+
+def spmv_tma_fault():
+    return int(lib().drops_b200_spmv_tma_fault())
 
 
 def synchronize():

@@ -322,7 +322,7 @@ int build_sell(const CsrDev& A, SellOp& S, size_t* bytes, const int32_t* rowmap,
     }
     DB_CUDA(cudaStreamSynchronize(st));
     size_t col_bytes = S.padded * 4;
-    if (S.padded > 0 && opt("sell.compress", 1.0) != 0.0) {
+    if (S.padded > 0 && opt("sell.compress", 0.0) != 0.0) {
         unsigned long long* d_nwide = nullptr;
         DB_CHECK(dev_alloc(&S.col16, S.padded));
         DB_CHECK(dev_alloc(&S.cbase, S.padded / 32));

@@ -19,70 +19,9 @@
 //     second vector save whole passes over HBM in PCG / GMRES / MINRES.
 // k_spmv_csr_vector: LANES threads per row on plain CSR (FMA + shuffle tree); kept as the
 //   comparison point ("spmv.kernel" = 1) and for matrices where SELL padding would explode.
-#include "spmv.cuh"
+#include "spmv_impl.cuh"
 
 namespace db200 {
-
-struct SellView {
-    const int64_t* slice_ptr;
-    const int32_t* col;
-    const double* val;
-    const int32_t* perm;
-    long long nslices;
-    const uint16_t* col16;     // 16-bit column deltas (nullptr: not compressed)
-    const int32_t* cbase;
-    const uint8_t* wide;
-};
-
-struct EpiArgs {
-    const double* aux;
-    double omega;
-    const double* beta;
-    double beta_val;
-    const double* dotv;
-    double* dot_out;
-    const int* done;
-    const dd* dd_in;
-    dd* dd_out;
-    const double* xghost;
-    int n_owned;
-    int prefetch;
-    dd* partials;
-    unsigned* ticket;
-};
-
-// s = row sum, av = the row's aux entry (d_i, b_i or z_i)
-template <int EPI>
-__device__ __forceinline__ double apply_epilogue(double s, double av, const EpiArgs& e, double beta)
-{
-    if (EPI == EPI_JACOBI) return __ddiv_rn(__dmul_rn(e.omega, s), av);
-    if (EPI == EPI_RESID)  return __dsub_rn(av, s);
-    if (EPI == EPI_AXMBY)  return __dsub_rn(s, __dmul_rn(beta, av));
-    return s;
-}
-
-__device__ __forceinline__ void prefetch_l2(const void* p)
-{
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
-// U = entries per thread loaded before the first use (loads in flight), MINB = resident CTAs of
-// 512 threads the register allocation must allow (2: <= 64 regs, 3: <= 40, 4: <= 32).
-// Stores the grid-wide fused dot product: rounded to *dot_out, or -- chained launches of a
-// partitioned product -- unrounded (plus the earlier launches' *dd_in) to *dd_out.
-__device__ __forceinline__ void store_dot(const EpiArgs& e, dd total)
-{
-    if (e.dd_in != nullptr) total = dd_add(total, *e.dd_in);
-    if (e.dd_out != nullptr) *e.dd_out = total;
-    else *e.dot_out = dd_round(total);
-}
-
-template <bool SPLIT>
-__device__ __forceinline__ double load_x(const double* __restrict__ x, const EpiArgs& e, int c)
-{
-    if (SPLIT) return c < e.n_owned ? __ldg(x + c) : __ldg(e.xghost + (c - e.n_owned));
-    return __ldg(x + c);
-}
 
 // Sum of one row of a slice, left to right.  C16: columns as cbase[entry] + 16-bit delta.
 template <bool EXACT, int U, bool SPLIT, bool C16>
@@ -201,6 +140,15 @@ k_sum_warp_partials(long long count, const dd* __restrict__ in, EpiArgs e, dd* p
     }
 }
 
+void sum_warp_partials(long long nwarps, const EpiArgs& e, cudaStream_t st)
+{
+    Ctx& c = ctx();
+    const int g2 = vec_grid((size_t)nwarps, kReduceThreads, 2);
+    k_sum_warp_partials<<<g2, kReduceThreads, 0, st>>>(nwarps, e.partials, e, c.partials + (size_t)3 * kPartialStride,
+                                                     c.tickets + (size_t)3 * kTicketStride);
+    count_launch();
+}
+
 template <int LANES, int EPI, bool DOT>
 __global__ void __launch_bounds__(256)
 k_spmv_csr_vector(long long rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
@@ -240,7 +188,7 @@ k_spmv_csr_vector(long long rows, const int64_t* __restrict__ rowptr, const int3
     }
 }
 
-static EpiArgs make_epi(const SpmvArgs& a)
+EpiArgs make_epi(const SpmvArgs& a)
 {
     Ctx& c = ctx();
     EpiArgs e;
@@ -273,11 +221,7 @@ static void launch_sell_v(const SellView& v, const SpmvArgs& a, const EpiArgs& e
     const long long nwarps = (long long)grid * (threads >> 5);
     if (opt("spmv.dotmode", 2.0) == 2.0 && nwarps <= kPartialStride) {
         k_spmv_sell<EPI, EXACT, 2, U, MAXT, MINB, SPLIT><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
-        Ctx& c = ctx();
-        const int g2 = vec_grid((size_t)nwarps, kReduceThreads, 2);
-        k_sum_warp_partials<<<g2, kReduceThreads, 0, st>>>(nwarps, e.partials, e, c.partials + (size_t)3 * kPartialStride,
-                                                         c.tickets + (size_t)3 * kTicketStride);
-        count_launch();
+        sum_warp_partials(nwarps, e, st);
     } else {
         k_spmv_sell<EPI, EXACT, 1, U, MAXT, MINB, SPLIT><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
     }
@@ -421,6 +365,7 @@ int spmv_apply(const drops_b200_matrix_s* M, bool transposed, const SpmvArgs& a)
         const int lanes = (int)opt("spmv.lanes", 8.0);
         return spmv_csr_vector(transposed ? M->csr_t : M->csr, a, lanes);
     }
+    if (kind == 2 && a.xghost == nullptr) return spmv_sell_tma(transposed ? M->sell_t : M->sell, a);
     return spmv_sell(transposed ? M->sell_t : M->sell, a);
 }
 

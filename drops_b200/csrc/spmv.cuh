@@ -39,10 +39,13 @@ struct SpmvArgs {
 // y = A x through the sliced-ELL operator (exact reference summation order unless option
 // "spmv.exact" is 0, in which case FMA is used).
 int spmv_sell(const SellOp& A, const SpmvArgs& a);
+// Same operator, matrix stream staged through shared memory with TMA bulk copies (spmv_tma.cu).
+int spmv_sell_tma(const SellOp& A, const SpmvArgs& a);
+int spmv_tma_fault();
 // y = A x straight from CSR, LANES threads per row (FMA, shuffle tree): comparison kernel.
 int spmv_csr_vector(const CsrDev& A, const SpmvArgs& a, int lanes);
 
-// dispatch on option "spmv.kernel": 0 = sell (default), 1 = csr_vector
+// dispatch on option "spmv.kernel": 0 = sell (register-staged), 1 = csr_vector, 2 = sell with TMA staging
 int spmv_apply(const drops_b200_matrix_s* M, bool transposed, const SpmvArgs& a);
 
 }  // namespace db200

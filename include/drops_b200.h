@@ -80,6 +80,9 @@ DROPS_B200_API int drops_b200_timer_stop(double* ms);
 /* Number of kernels this library launched since init (all streams). */
 DROPS_B200_API long long drops_b200_launch_count(void);
 DROPS_B200_API int drops_b200_synchronize(void);
+/* 1 if a warp of the TMA-staged SpMV ("spmv.kernel" = 2) ever gave up waiting for a stage (the
+ * kernel never spins forever); results of that launch are invalid.  0 in a healthy process. */
+DROPS_B200_API int drops_b200_spmv_tma_fault(void);
 
 /* ---- matrices: SparseMatBaseCL<double>, num/spmat.h:682-879 -------------------------------- */
 /* Copies a host CSR matrix in the reference layout to the device: narrows colind to int32,

