@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cpu-iters", type=int, default=25)
     ap.add_argument("--no-host-matrix", action="store_true", help="skip the host CSR upload path in e2e")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-small", action="store_true", help="skip the side measurement of BASELINE configs[0]")
     return ap.parse_args()
 
 
@@ -326,6 +327,13 @@ def run_ours(args):
                "sample_iterations_per_s": 1.0 / r["sec_per_iter"],
                "spmv_gbs_reference_layout": r["spmv_gbs_ref_layout"]}
 
+    c1 = None
+    if not args.no_small:
+        try:
+            c1 = small_config_c1(args)
+        except Exception as exc:      # the headline line must survive a failure of the side measurement
+            c1 = {"error": repr(exc)}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -336,10 +344,48 @@ def run_ours(args):
                    "cache": "inputs (17 GB matrix, 0.4 GB vectors) far exceed the 126 MB L2; no flush needed",
                    "spmv_kernel": "sell-32-sigma exact", "generate_s": gen_s},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        "final_relative_residual": resid,
+        "final_relative_residual": resid, "other_configs": {"C1_p1_n64": c1},
     }
     print(json.dumps(line), flush=True)
 
+
+def small_config_c1(args):
+    """BASELINE configs[0]: P1 Poisson, BrickBuilderCL cube with 64 cells per direction (4 cells, 4
+    uniform refinements), PCG + JACPcCL, 200 iterations (cdrdrops Iter), host buffers.  250 047 rows: the
+    whole system fits in L2 and an iteration is launch-bound, which is what the CUDA-graph replay is for.
+    Same system, same iteration count on the compiled reference (all host cores)."""
+    from drops_b200 import capi
+    from oracle import ref as oref
+    fe, N, numbering, iters = 1, 64, 0, 200
+    n, rb, ci, va = capi.brick_csr_host(fe, N, numbering)
+    A = capi.Matrix(n, n, rb, ci, va)
+    xs = capi.brick_solution_host(fe, N, numbering)
+    b = A.spmv(xs)
+    out = {"rows": n, "nnz": int(len(va)), "iterations_per_solve": iters}
+    for graph in (1, 0):
+        capi.set_option("pcg.graph", graph)
+        for _ in range(3):
+            A.pcg_jacobi(np.zeros(n), b, iters, 0.0, True)
+        t0 = time.perf_counter()
+        reps = 10
+        for _ in range(reps):
+            A.pcg_jacobi(np.zeros(n), b, iters, 0.0, True)
+        dt = (time.perf_counter() - t0) / reps
+        out["graph" if graph else "eager"] = {"iterations_per_s": iters / dt, "ms_per_solve": 1e3 * dt,
+                                               "note": "host-buffer entry point, copies inside"}
+    capi.set_option("pcg.graph", 1)
+    conv = A.pcg_jacobi(np.zeros(n), b, 2000, 1e-10, True)
+    out["to_convergence"] = {"iterations": conv[1], "relative_residual": conv[2]}
+    if oref.available() and not args.no_cpu:
+        R = oref.RefMatrix(n, n, rb, ci, va)
+        R.pcg_jacobi_timed(np.zeros(n), b, 20, 0.0, True, 1.0)
+        t0 = time.perf_counter()
+        R.pcg_jacobi_timed(np.zeros(n), b, iters, 0.0, True, 1.0)
+        dt = time.perf_counter() - t0
+        out["reference_cpu"] = {"iterations_per_s": iters / dt, "ms_per_solve": 1e3 * dt, "cores": oref.num_threads()}
+        cref = R.pcg_jacobi_timed(np.zeros(n), b, 2000, 1e-10, True, 1.0)
+        out["to_convergence"]["reference_iterations"] = int(cref[1])
+    return out
 
 
 def run_ours_dist(args, rank, world, local, dist):

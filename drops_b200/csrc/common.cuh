@@ -234,6 +234,7 @@ struct Ctx {
     double* h_scalars = nullptr;        // pinned host mirror
     int max_grid = 0;
     long long launches = 0;
+    unsigned long long options_epoch = 0;   // bumped by every set_option: cached CUDA graphs are keyed on it
     std::map<std::string, double> options;
     std::map<std::string, TimingSlot> timing;
     std::vector<cudaEvent_t> event_pool;
@@ -343,6 +344,10 @@ struct drops_b200_matrix_s {
     int hist_alloc = 0;
     double* d_small = nullptr;       // small device arrays (Hessenberg column, y, pointers)
     size_t small_alloc = 0;
+    // CUDA graph of one chunk of PCG iterations (launch-bound systems: cdrdrops' 250 k unknowns)
+    cudaGraphExec_t pcg_graph = nullptr;
+    struct { const void* x; const void* b; int chunk; int cg; unsigned long long epoch; } pcg_graph_key = {nullptr, nullptr, 0, 0, 0};
+    long long pcg_graph_launches = 0;  // kernels inside the captured chunk
 };
 
 namespace db200 {

@@ -196,6 +196,7 @@ int drops_b200_set_option(const char* key, double value)
 {
     DB_ARG(key != nullptr, "null key");
     ctx().options[key] = value;
+    ctx().options_epoch += 1;
     return 0;
 }
 

@@ -112,20 +112,55 @@ int pcg_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, doubl
         DB_CUDA(cudaEventRecord(ev[slot], st));
         return 0;
     };
+    auto one_iteration = [&]() -> int {
+        SpmvArgs s;
+        s.x = p; s.y = q; s.dotv = p; s.dot_out = &S->lambda; s.done = &S->done;   // q = A p, lambda = q.p  :149-151
+        DB_CHECK(spmv_apply(M, false, s));
+        DB_CHECK(unpreconditioned_cg ? cg_update(n, x, r, p, q, S, dh) : pcg_update(n, x, r, p, q, M->diag, S, dh));
+        DB_CHECK(unpreconditioned_cg ? cg_direction(n, p, r, S) : pcg_direction(n, p, r, M->diag, S));
+        return 0;
+    };
+    // A chunk of iterations as ONE CUDA graph launch: on small systems (cdrdrops' example has 250 k
+    // unknowns: ~10 us of HBM time per iteration) the 4 kernel launches per iteration are the cost.
+    // All kernel arguments are pointers that stay fixed over the solve, so the graph is captured
+    // once per (matrix, x, b, options) and replayed.  Not used while per-kernel timing is on.
+    const bool use_graph = opt("pcg.graph", 1.0) != 0.0 && opt("timing", 0.0) == 0.0 && total >= check_every &&
+                           dh == nullptr;
+    if (use_graph) {
+        auto& key = M->pcg_graph_key;
+        if (!M->pcg_graph || key.x != x || key.b != b || key.chunk != check_every ||
+            key.cg != (int)unpreconditioned_cg + 2 * pc || key.epoch != c.options_epoch) {
+            if (M->pcg_graph) { cudaGraphExecDestroy(M->pcg_graph); M->pcg_graph = nullptr; }
+            const long long l0 = c.launches;
+            cudaGraph_t graph = nullptr;
+            cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+            if (ce != cudaSuccess) status = cuda_fail(ce, "begin capture", __FILE__, __LINE__);
+            for (int k = 0; k < check_every && status == 0; ++k) status = one_iteration();
+            ce = cudaStreamEndCapture(st, &graph);
+            if (status == 0 && ce != cudaSuccess) status = cuda_fail(ce, "end capture", __FILE__, __LINE__);
+            if (status == 0) {
+                ce = cudaGraphInstantiate(&M->pcg_graph, graph, 0);
+                if (ce != cudaSuccess) status = cuda_fail(ce, "graph instantiate", __FILE__, __LINE__);
+            }
+            if (graph) cudaGraphDestroy(graph);
+            M->pcg_graph_launches = c.launches - l0;
+            c.launches = l0;                                   // captured, not launched
+            key.x = x; key.b = b; key.chunk = check_every; key.cg = (int)unpreconditioned_cg + 2 * pc;
+            key.epoch = c.options_epoch;
+            if (status != 0 && M->pcg_graph) { cudaGraphExecDestroy(M->pcg_graph); M->pcg_graph = nullptr; }
+        }
+    }
     // the setup kernels may already have finished the solve (resid <= tol at iteration 0)
-    status = enqueue_flag_read(0);
+    if (status == 0) status = enqueue_flag_read(0);
     chunk_id = 1;
     while (status == 0 && !finished) {
         const int chunk = std::min(check_every, total - launched);
-        for (int k = 0; k < chunk && status == 0; ++k) {
-            SpmvArgs s;
-            s.x = p; s.y = q; s.dotv = p; s.dot_out = &S->lambda; s.done = &S->done;   // q = A p, lambda = q.p  :149-151
-            status = spmv_apply(M, false, s);
-            if (status == 0)
-                status = unpreconditioned_cg ? cg_update(n, x, r, p, q, S, dh)
-                                             : pcg_update(n, x, r, p, q, M->diag, S, dh);
-            if (status == 0)
-                status = unpreconditioned_cg ? cg_direction(n, p, r, S) : pcg_direction(n, p, r, M->diag, S);
+        if (use_graph && chunk == check_every && M->pcg_graph) {
+            cudaError_t ce = cudaGraphLaunch(M->pcg_graph, st);
+            if (ce != cudaSuccess) status = cuda_fail(ce, "graph launch", __FILE__, __LINE__);
+            c.launches += M->pcg_graph_launches;
+        } else {
+            for (int k = 0; k < chunk && status == 0; ++k) status = one_iteration();
         }
         launched += chunk;
         if (status != 0) break;

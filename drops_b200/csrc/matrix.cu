@@ -587,6 +587,7 @@ int drops_b200_matrix_destroy(drops_b200_matrix_t M)
     for (double* w : M->work) dev_free(w);
     dev_free(M->bridge[0]); dev_free(M->bridge[1]);
     dev_free(M->d_scalars); dev_free(M->d_hist); dev_free(M->d_small);
+    if (M->pcg_graph) cudaGraphExecDestroy(M->pcg_graph);
     delete M;
     return 0;
 }

@@ -354,6 +354,48 @@ def test_solver_edge_cases(gpu):
     assert np.array_equal(E.spmv_transpose(np.ones(3)), np.zeros(3))
 
 
+def test_pcg_graph_replay_matches_eager(gpu, port):
+    """Chunks of PCG iterations replayed as one CUDA graph (the launch-bound case: cdrdrops' 250 k
+    unknowns) give bit-identical results to eager launches, across option changes, new right-hand
+    sides, value updates and device / host entry points."""
+    fe, N, numbering = 1, 20, 0
+    n, rb, ci, va = gpu.brick_csr_host(fe, N, numbering)
+    A = gpu.Matrix(n, n, rb, ci, va)
+    P = port.PortMatrix(n, n, rb, ci, va)
+    xs = gpu.brick_solution_host(fe, N, numbering)
+    b = P.spmv(xs)
+    ref = P.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True)
+    outs = {}
+    try:
+        for graph in (1, 0, 1):
+            gpu.set_option("pcg.graph", graph)
+            for ce in (16, 4):
+                gpu.set_option("pcg.check_every", ce)
+                out = A.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True)
+                assert out[0] and out[1] == ref[1]
+                outs.setdefault("x", out[3])
+                assert np.array_equal(out[3], outs["x"])            # same kernels, same order: same bits
+                out = A.pcg_jacobi(np.zeros(n), 2.0 * b, 37, 0.0, True)   # fixed work, other rhs, same graph
+                assert not out[0] and out[1] == 37
+                outs.setdefault("x37", out[3])
+                assert np.array_equal(out[3], outs["x37"])
+        gpu.set_option("pcg.graph", 1)
+        gpu.set_option("pcg.check_every", 16)
+        xv, bv = gpu.Vector(n), gpu.Vector.from_host(b)
+        for _ in range(3):                                           # replay on device-resident vectors
+            xv.fill(0.0)
+            conv, it, res = A.pcg_dev(xv, bv, 500, 1e-10, True)
+            assert conv and it == ref[1] and np.array_equal(xv.download(), outs["x"])
+        A.update_values(3.0 * va, 2)                                 # values change behind the cached graph
+        out = A.pcg_jacobi(np.zeros(n), 3.0 * b, 500, 1e-10, True)
+        assert out[0] and out[1] == ref[1] and rel(out[3], ref[3]) <= 1e-10
+        out = A.cg(np.zeros(n), 3.0 * b, 500, 1e-10, True)           # CG shares the handle: graph is re-keyed
+        assert out[0] and rel(out[3], ref[3]) <= 1e-9
+    finally:
+        gpu.set_option("pcg.graph", 1)
+        gpu.set_option("pcg.check_every", 16)
+
+
 def test_matrix_value_update_tracks_version(gpu):
     g = load_golden("brick_fe2_N4_num1.npz")
     A = gmat(gpu, g)
