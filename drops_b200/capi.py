@@ -86,6 +86,10 @@ SIGNATURES = {
     "drops_b200_gmres_dev": (_i, [_vp, _vp, _vp, _i, _d, _i, _ip, _dpp, _i, _i]),
     "drops_b200_minres": (_i, [_vp, _dp, _dp, _i, _i, _d, _ip, _dpp, _i]),
     "drops_b200_minres_dev": (_i, [_vp, _vp, _vp, _i, _i, _d, _ip, _dpp, _i]),
+    "drops_b200_bicgstab": (_i, [_vp, _dp, _dp, _i, _d, _ip, _dpp, _i, _ip]),
+    "drops_b200_bicgstab_dev": (_i, [_vp, _vp, _vp, _i, _d, _ip, _dpp, _i, _ip]),
+    "drops_b200_gcr": (_i, [_vp, _dp, _dp, _i, _d, _i, _ip, _dpp, _i]),
+    "drops_b200_gcr_dev": (_i, [_vp, _vp, _vp, _i, _d, _i, _ip, _dpp, _i]),
     "drops_b200_brick_sizes": (_i, [_i, _i, _szpp, _szpp]),
     "drops_b200_brick_csr_host": (_i, [_i, _i, _i, _d, _szp, _szp, _dp]),
     "drops_b200_brick_matrix_device": (_i, [_i, _i, _i, _d, _vpp]),
@@ -467,6 +471,21 @@ class Matrix:
         conv = check(lib().drops_b200_gmres_dev(self.h, x.h, b.h, int(pc), float(omega), int(restart),
                                                 C.byref(it), C.byref(res), int(relative), int(left)))
         return bool(conv), it.value, res.value
+
+    def bicgstab(self, x0, b, max_iter, tol, relative=True, pc=PC_JACOBI, omega=1.0):
+        """(converged, iters, resid, x, breakdown)"""
+        x = _f64(x0).copy()
+        it, res, bd = C.c_int(int(max_iter)), C.c_double(float(tol)), C.c_int(0)
+        conv = check(lib().drops_b200_bicgstab(self.h, x, _f64(b), int(pc), float(omega), C.byref(it), C.byref(res),
+                                               int(relative), C.byref(bd)))
+        return bool(conv), it.value, res.value, x, bd.value
+
+    def gcr(self, x0, b, truncate, max_iter, tol, relative=True, pc=PC_JACOBI, omega=1.0):
+        x = _f64(x0).copy()
+        it, res = C.c_int(int(max_iter)), C.c_double(float(tol))
+        conv = check(lib().drops_b200_gcr(self.h, x, _f64(b), int(pc), float(omega), int(truncate), C.byref(it),
+                                          C.byref(res), int(relative)))
+        return bool(conv), it.value, res.value, x
 
     def _minres(self, precond, pc, omega, x0, b, max_iter, tol, relative):
         x = _f64(x0).copy()

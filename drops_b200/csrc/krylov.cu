@@ -517,6 +517,166 @@ int minres_device(drops_b200_matrix_s* M, double* x, const double* b, int precon
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// BiCGStab -- num/krylovsolver.h:1189-1258 (BiCGStabSolverCL :1978-2013, serial branch)
+// Returns 1 converged, 0 not converged or breakdown (the reference returns false for both and
+// leaves a message on std::cout); *breakdown tells them apart.
+// ------------------------------------------------------------------------------------------
+int bicgstab_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, double omega_pc, int* max_iter,
+                    double* tol, int relative, int* breakdown)
+{
+    DB_CHECK(check_system(M, pc));
+    DB_ARG(max_iter && tol, "null max_iter/tol");
+    Ctx& c = ctx();
+    const size_t n = M->csr.rows;
+    if (breakdown) *breakdown = 0;
+    double* w[8];
+    for (int i = 0; i < 8; ++i) { w[i] = work_vec(M, i); if (!w[i]) return DROPS_B200_E_NOMEM; }
+    double *r = w[0], *rtilde = w[1], *p = w[2], *phat = w[3], *sv = w[4], *shat = w[5], *t = w[6], *v = w[7];
+    DB_CHECK(ensure_small(M, 8));
+    double* d_s = M->d_small;
+    double* hs = c.h_scalars;
+    SpmvArgs a;
+    a.x = x; a.y = r; a.epilogue = EPI_RESID; a.aux = b;                       // r = b - A x          :1197
+    DB_CHECK(spmv_apply(M, false, a));
+    DB_CHECK(vec_copy(n, rtilde, r));                                          // rtilde = r           :1198
+    DB_CHECK(vec_dot(n, b, b, d_s + 0));
+    DB_CHECK(vec_dot(n, r, r, d_s + 1));
+    DB_CHECK(vec_dot(n, rtilde, r, d_s + 2));
+    DB_CHECK(fetch(d_s, hs, 3 * sizeof(double)));
+    double normb = std::sqrt(hs[0]);
+    if (normb == 0.0 || !relative) normb = 1.0;                                //                      :1200
+    double resid = std::sqrt(hs[1]) / normb, rr = hs[1];
+    if (resid <= *tol) { *tol = resid; *max_iter = 0; return 1; }
+    double rho_1 = hs[2], rho_2 = 0.0, alpha = 0.0, beta = 0.0, omega = 0.0;
+    for (int i = 1; i <= *max_iter; ++i) {
+        if (rho_1 == 0.0) {                                                    //                      :1210-1215
+            *tol = std::sqrt(rr) / normb; *max_iter = i;
+            if (breakdown) *breakdown = 1;
+            return 0;
+        }
+        if (i > 1) beta = (rho_1 / rho_2) * (alpha / omega);                   //                      :1219
+        DB_CHECK(bicg_p(n, i == 1, p, phat, r, v, beta, omega, pc, omega_pc, M->diag));
+        SpmvArgs av; av.x = phat; av.y = v; av.dotv = rtilde; av.dot_out = d_s + 0;   // v = A phat; rtilde.v  :1223-1224
+        DB_CHECK(spmv_apply(M, false, av));
+        DB_CHECK(fetch(d_s, hs, sizeof(double)));
+        alpha = rho_1 / hs[0];
+        DB_CHECK(bicg_s(n, sv, shat, r, v, alpha, pc, omega_pc, M->diag, d_s + 0));
+        DB_CHECK(fetch(d_s, hs, sizeof(double)));
+        if ((resid = std::sqrt(hs[0]) / normb) < *tol) {                       //                      :1226-1231
+            DB_CHECK(vec_axpy(n, alpha, phat, x));
+            *tol = resid; *max_iter = i;
+            return 1;
+        }
+        SpmvArgs at; at.x = shat; at.y = t;                                    // t = A shat           :1233
+        DB_CHECK(spmv_apply(M, false, at));
+        DB_CHECK(bicg_ts(n, t, sv, d_s + 0));
+        DB_CHECK(fetch(d_s, hs, 2 * sizeof(double)));
+        omega = hs[0] / hs[1];                                                 //                      :1234
+        DB_CHECK(bicg_x(n, x, r, phat, shat, sv, t, rtilde, alpha, omega, d_s + 0));
+        DB_CHECK(fetch(d_s, hs, 2 * sizeof(double)));
+        rr = hs[0];
+        rho_2 = rho_1;
+        rho_1 = hs[1];                                                         // next iteration's dot(rtilde, r)
+        if ((resid = std::sqrt(rr) / normb) < *tol) { *tol = resid; *max_iter = i; return 1; }
+        if (omega == 0.0) {                                                    //                      :1245-1250
+            *tol = std::sqrt(rr) / normb; *max_iter = i;
+            if (breakdown) *breakdown = 2;
+            return 0;
+        }
+    }
+    *tol = resid;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// GCR(m) -- num/krylovsolver.h:1410-1483 (GCRSolverCL :2017-2053) with DummyExchangeCL.
+// The reference keeps "accumulated" twins racc / vnacc / vacc[i] of r / vn / v[i]; serially they
+// are copies until the truncation branch (:1466-1477) replaces s[min] and v[min] but NOT vacc[min].
+// To give the reference's results the twins are reproduced -- lazily: they alias the originals
+// until the first truncation.
+// ------------------------------------------------------------------------------------------
+int gcr_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, double omega_pc, int m, int* max_iter,
+               double* tol, int relative)
+{
+    DB_CHECK(check_system(M, pc));
+    DB_ARG(max_iter && tol, "null max_iter/tol");
+    DB_ARG(m >= 1, "GCR: truncation parameter m must be >= 1");
+    Ctx& c = ctx();
+    const size_t n = M->csr.rows;
+    m = (m <= *max_iter) ? m : *max_iter;                                      //                      :1416
+    if (m < 1) m = 1;
+    // work: 0 r, 1 sn, 2 vn, 3 racc, 4 vnacc, 5.. s[i], v[i], vacc_own[i] interleaved
+    double* r = work_vec(M, 0); double* sn = work_vec(M, 1); double* vn = work_vec(M, 2);
+    if (!r || !sn || !vn) return DROPS_B200_E_NOMEM;
+    double *racc = nullptr, *vnacc = nullptr;                                  // twins: nullptr = alias
+    std::vector<double*> s((size_t)m, nullptr), v((size_t)m, nullptr), vacc_own((size_t)m, nullptr);
+    std::vector<double> a((size_t)m, 0.0);
+    DB_CHECK(ensure_small(M, (size_t)m + 8));
+    double* d_a = M->d_small;                                                  // a[m] | beta | gamma | rr | bb
+    double* d_beta = d_a + m; double* d_gamma = d_beta + 1; double* d_rr = d_gamma + 1; double* d_bb = d_rr + 1;
+    std::vector<double> h((size_t)m + 4);
+    SpmvArgs ar;
+    ar.x = x; ar.y = r; ar.epilogue = EPI_RESID; ar.aux = b;                   // r = b - A x          :1418
+    DB_CHECK(spmv_apply(M, false, ar));
+    DB_CHECK(vec_dot(n, b, b, d_bb));
+    DB_CHECK(vec_dot(n, r, r, d_rr));
+    DB_CHECK(fetch(d_rr, h.data(), 2 * sizeof(double)));
+    double normb = std::sqrt(h[1]);
+    if (normb == 0.0 || !relative) normb = 1.0;
+    double resid = std::sqrt(h[0]) / normb;
+    int stored = 0;
+    for (int k = 0; k < *max_iter; ++k) {
+        if (resid < *tol) { *tol = resid; *max_iter = k; return 1; }           //                      :1433-1437
+        if (pc == DROPS_B200_PC_JACOBI) DB_CHECK(vec_jacobi(n, omega_pc, M->diag, r, sn));
+        else DB_CHECK(vec_copy(n, sn, r));                                     // M.Apply(A, sn, r)    :1438
+        SpmvArgs av; av.x = sn; av.y = vn;                                     // vn = A sn            :1440
+        DB_CHECK(spmv_apply(M, false, av));
+        if (vnacc) DB_CHECK(vec_copy(n, vnacc, vn));                           // vnacc = GetAccumulate(vn)
+        const int nst = std::min(k, m);
+        auto vacc = [&](int i) -> const double* { return vacc_own[(size_t)i] ? vacc_own[(size_t)i] : v[(size_t)i]; };
+        for (int i = 0; i <= nst; ++i) {                                       // orthogonalise        :1442-1451
+            const bool prev = i > 0;
+            DB_CHECK(gcr_orth(n, vn, sn, vnacc, prev ? v[(size_t)i - 1] : nullptr, prev ? s[(size_t)i - 1] : nullptr,
+                              prev ? vacc(i - 1) : nullptr, prev ? d_a + (i - 1) : nullptr,
+                              i < nst ? vacc(i) : nullptr, i < nst ? d_a + i : d_beta));
+        }
+        DB_CHECK(gcr_scale(n, vn, sn, vnacc, racc ? racc : r, d_beta, d_gamma));      //               :1452-1455
+        DB_CHECK(gcr_update(n, x, r, racc, sn, vn, vnacc, d_gamma, d_rr));            //               :1456-1462
+        DB_CHECK(fetch(d_a, h.data(), ((size_t)m + 3) * sizeof(double)));
+        for (int i = 0; i < nst; ++i) a[(size_t)i] = h[(size_t)i];
+        resid = std::sqrt(h[(size_t)m + 2]) / normb;
+        if (k < m) {                                                           // keep the direction   :1463-1467
+            s[(size_t)stored] = work_vec(M, 5 + 3 * stored);
+            v[(size_t)stored] = work_vec(M, 6 + 3 * stored);
+            if (!s[(size_t)stored] || !v[(size_t)stored]) return DROPS_B200_E_NOMEM;
+            DB_CHECK(vec_copy(n, s[(size_t)stored], sn));
+            DB_CHECK(vec_copy(n, v[(size_t)stored], vn));
+            ++stored;
+        } else {                                                               // min-alpha truncation :1468-1480
+            int min_idx = 0;
+            double a_min = std::fabs(a[0]);
+            for (int i = 1; i < k && i < m; ++i)
+                if (std::fabs(a[(size_t)i]) < a_min) { min_idx = i; a_min = std::fabs(a[(size_t)i]); }
+            if (!racc) {                                                       // the twins part ways here
+                racc = work_vec(M, 3); vnacc = work_vec(M, 4);
+                if (!racc || !vnacc) return DROPS_B200_E_NOMEM;
+                DB_CHECK(vec_copy(n, racc, r));
+                DB_CHECK(vec_copy(n, vnacc, vn));
+            }
+            if (!vacc_own[(size_t)min_idx]) {                                  // vacc[min_idx] keeps the OLD vector
+                vacc_own[(size_t)min_idx] = work_vec(M, 7 + 3 * min_idx);
+                if (!vacc_own[(size_t)min_idx]) return DROPS_B200_E_NOMEM;
+                DB_CHECK(vec_copy(n, vacc_own[(size_t)min_idx], v[(size_t)min_idx]));
+            }
+            DB_CHECK(vec_copy(n, s[(size_t)min_idx], sn));
+            DB_CHECK(vec_copy(n, v[(size_t)min_idx], vn));
+        }
+    }
+    *tol = resid;
+    return 0;
+}
+
 }  // namespace db200
 
 // ------------------------------------------------------------------------------------------
@@ -721,6 +881,48 @@ int drops_b200_minres(drops_b200_matrix_t A, double* x, const double* b, int pre
     HostBridge hb(A);
     DB_CHECK(hb.up(A->csr.rows, x, b));
     const int r = minres_device(A, hb.dx, hb.db, precond, pc, omega, max_iter, tol, relative);
+    if (r < 0) return r;
+    DB_CHECK(hb.down(A->csr.rows, x));
+    return r;
+}
+
+int drops_b200_bicgstab_dev(drops_b200_matrix_t A, drops_b200_vector_t x, drops_b200_vector_t b, int pc, double omega,
+                            int* max_iter, double* tol, int relative, int* breakdown)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(A && x && b && x->n == A->csr.rows && b->n == A->csr.rows, "BICGSTAB: incompatible dimensions");
+    return bicgstab_device(A, x->d, b->d, pc, omega, max_iter, tol, relative, breakdown);
+}
+
+int drops_b200_bicgstab(drops_b200_matrix_t A, double* x, const double* b, int pc, double omega, int* max_iter,
+                        double* tol, int relative, int* breakdown)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(A && x && b, "null argument");
+    HostBridge hb(A);
+    DB_CHECK(hb.up(A->csr.rows, x, b));
+    const int r = bicgstab_device(A, hb.dx, hb.db, pc, omega, max_iter, tol, relative, breakdown);
+    if (r < 0) return r;
+    DB_CHECK(hb.down(A->csr.rows, x));
+    return r;
+}
+
+int drops_b200_gcr_dev(drops_b200_matrix_t A, drops_b200_vector_t x, drops_b200_vector_t b, int pc, double omega,
+                       int truncate, int* max_iter, double* tol, int relative)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(A && x && b && x->n == A->csr.rows && b->n == A->csr.rows, "GCR: incompatible dimensions");
+    return gcr_device(A, x->d, b->d, pc, omega, truncate, max_iter, tol, relative);
+}
+
+int drops_b200_gcr(drops_b200_matrix_t A, double* x, const double* b, int pc, double omega, int truncate,
+                   int* max_iter, double* tol, int relative)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(A && x && b, "null argument");
+    HostBridge hb(A);
+    DB_CHECK(hb.up(A->csr.rows, x, b));
+    const int r = gcr_device(A, hb.dx, hb.db, pc, omega, truncate, max_iter, tol, relative);
     if (r < 0) return r;
     DB_CHECK(hb.down(A->csr.rows, x));
     return r;

@@ -569,6 +569,144 @@ int minres_update(size_t n, int mode, const double* q, const double* pm2, const 
     return launch_stream<0>(n, OpMinresUpdate{mode, q, pm2, pm1, p0, x, r0, r1, r2, f, 0.0}, "minres.update");
 }
 
+// ------------------------------------------------------------------------------------------
+// BiCGStab pieces
+// ------------------------------------------------------------------------------------------
+struct OpBicgP {
+    bool first; double* p; double* phat; const double* r; const double* v; double beta, omega; int pc; double opc; const double* d;
+    __device__ bool begin() { return true; }
+    __device__ void elem(size_t i, dd*)
+    {
+        const double pi = first ? r[i] : add(r[i], mul(beta, sub(p[i], mul(omega, v[i]))));   // :1216-1220
+        p[i] = pi;
+        phat[i] = precond(pc, opc, pi, d, i);                                                  // :1222
+    }
+    __device__ void finish(const dd*) {}
+};
+int bicg_p(size_t n, bool first, double* p, double* phat, const double* r, const double* v, double beta, double omega,
+           int pc, double omega_pc, const double* d)
+{
+    return launch_stream<0>(n, OpBicgP{first, p, phat, r, v, beta, omega, pc, omega_pc, d}, "bicgstab.vec");
+}
+
+struct OpBicgS {
+    double* s; double* shat; const double* r; const double* v; double alpha; int pc; double opc; const double* d; double* out;
+    __device__ bool begin() { return true; }
+    __device__ void elem(size_t i, dd* acc)
+    {
+        const double si = sub(r[i], mul(alpha, v[i]));                                         // :1225
+        s[i] = si;
+        shat[i] = precond(pc, opc, si, d, i);                                                  // :1232
+        acc[0] = dd_add_prod(acc[0], si, si);
+    }
+    __device__ void finish(const dd* acc) { out[0] = dd_round(acc[0]); }
+};
+int bicg_s(size_t n, double* s, double* shat, const double* r, const double* v, double alpha, int pc, double omega_pc,
+           const double* d, double* d_out)
+{
+    return launch_stream<1>(n, OpBicgS{s, shat, r, v, alpha, pc, omega_pc, d, d_out}, "bicgstab.vec");
+}
+
+struct OpBicgTs {
+    const double* t; const double* s; double* out;
+    __device__ bool begin() { return true; }
+    __device__ void elem(size_t i, dd* acc)
+    {
+        acc[0] = dd_add_prod(acc[0], t[i], s[i]);
+        acc[1] = dd_add_prod(acc[1], t[i], t[i]);
+    }
+    __device__ void finish(const dd* acc) { out[0] = dd_round(acc[0]); out[1] = dd_round(acc[1]); }
+};
+int bicg_ts(size_t n, const double* t, const double* s, double* d_out)
+{
+    return launch_stream<2>(n, OpBicgTs{t, s, d_out}, "bicgstab.vec");
+}
+
+struct OpBicgX {
+    double* x; double* r; const double* phat; const double* shat; const double* s; const double* t; const double* rtilde;
+    double alpha, omega; double* out;
+    __device__ bool begin() { return true; }
+    __device__ void elem(size_t i, dd* acc)
+    {
+        x[i] = add(x[i], add(mul(alpha, phat[i]), mul(omega, shat[i])));                       // :1235
+        const double ri = sub(s[i], mul(omega, t[i]));                                         // :1236
+        r[i] = ri;
+        acc[0] = dd_add_prod(acc[0], ri, ri);
+        acc[1] = dd_add_prod(acc[1], rtilde[i], ri);
+    }
+    __device__ void finish(const dd* acc) { out[0] = dd_round(acc[0]); out[1] = dd_round(acc[1]); }
+};
+int bicg_x(size_t n, double* x, double* r, const double* phat, const double* shat, const double* s, const double* t,
+           const double* rtilde, double alpha, double omega, double* d_out)
+{
+    return launch_stream<2>(n, OpBicgX{x, r, phat, shat, s, t, rtilde, alpha, omega, d_out}, "bicgstab.vec");
+}
+
+// ------------------------------------------------------------------------------------------
+// GCR pieces
+// ------------------------------------------------------------------------------------------
+struct OpGcrOrth {
+    double* vn; double* sn; double* vnacc; const double* vprev; const double* sprev; const double* vaccprev;
+    const double* aprev; const double* vacc_cur; double* out; double a;
+    __device__ bool begin() { a = vprev ? *aprev : 0.0; return true; }
+    __device__ void elem(size_t i, dd* acc)
+    {
+        double vi = vn[i], wi = vnacc ? vnacc[i] : 0.0;
+        if (vprev) {                                                                           // :1445-1448
+            vi = sub(vi, mul(a, vprev[i])); vn[i] = vi;
+            if (vnacc) { wi = sub(wi, mul(a, vaccprev[i])); vnacc[i] = wi; }
+            sn[i] = sub(sn[i], mul(a, sprev[i]));
+        }
+        const double acc_v = vnacc ? wi : vi;
+        acc[0] = vacc_cur ? dd_add_prod(acc[0], acc_v, vacc_cur[i]) : dd_add_prod(acc[0], acc_v, acc_v);
+    }
+    __device__ void finish(const dd* acc) { *out = vacc_cur ? dd_round(acc[0]) : sqrt(dd_round(acc[0])); }
+};
+int gcr_orth(size_t n, double* vn, double* sn, double* vnacc, const double* vprev, const double* sprev,
+             const double* vaccprev, const double* d_aprev, const double* vacc_cur, double* d_out)
+{
+    return launch_stream<1>(n, OpGcrOrth{vn, sn, vnacc, vprev, sprev, vaccprev, d_aprev, vacc_cur, d_out, 0.0}, "gcr.vec");
+}
+
+struct OpGcrScale {
+    double* vn; double* sn; double* vnacc; const double* racc; const double* betap; double* out; double beta;
+    __device__ bool begin() { beta = *betap; return true; }
+    __device__ void elem(size_t i, dd* acc)
+    {
+        const double vi = dvd(vn[i], beta);                                                    // :1452-1454
+        vn[i] = vi;
+        double wi = vi;
+        if (vnacc) { wi = dvd(vnacc[i], beta); vnacc[i] = wi; }
+        sn[i] = dvd(sn[i], beta);
+        acc[0] = dd_add_prod(acc[0], racc[i], wi);                                             // :1455
+    }
+    __device__ void finish(const dd* acc) { *out = dd_round(acc[0]); }
+};
+int gcr_scale(size_t n, double* vn, double* sn, double* vnacc, const double* racc, const double* d_beta, double* d_gamma)
+{
+    return launch_stream<1>(n, OpGcrScale{vn, sn, vnacc, racc, d_beta, d_gamma, 0.0}, "gcr.vec");
+}
+
+struct OpGcrUpdate {
+    double* x; double* r; double* racc; const double* sn; const double* vn; const double* vnacc; const double* gp;
+    double* out; double g;
+    __device__ bool begin() { g = *gp; return true; }
+    __device__ void elem(size_t i, dd* acc)
+    {
+        x[i] = add(x[i], mul(g, sn[i]));                                                       // :1459
+        double ri = sub(r[i], mul(g, vn[i]));                                                  // :1460
+        r[i] = ri;
+        if (racc) { ri = sub(racc[i], mul(g, vnacc[i])); racc[i] = ri; }                       // :1461
+        acc[0] = dd_add_prod(acc[0], ri, ri);
+    }
+    __device__ void finish(const dd* acc) { *out = dd_round(acc[0]); }
+};
+int gcr_update(size_t n, double* x, double* r, double* racc, const double* sn, const double* vn, const double* vnacc,
+               const double* d_gamma, double* d_rr)
+{
+    return launch_stream<1>(n, OpGcrUpdate{x, r, racc, sn, vn, vnacc, d_gamma, d_rr, 0.0}, "gcr.vec");
+}
+
 }  // namespace db200
 
 // ------------------------------------------------------------------------------------------

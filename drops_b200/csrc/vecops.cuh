@@ -95,6 +95,31 @@ int vec_div_scalar(size_t n, double* out, const double* in, double s, int mode);
 // mode 1: p0 = q/r0c (k = 1);  mode 2: p0 = (q - r0*pm1)/r1 (k = 2);  mode 3: general.
 int minres_update(size_t n, int mode, const double* q, const double* pm2, const double* pm1, double* p0,
                   double* x, double r0, double r1, double r2, double f);
+// ---- BiCGStab building blocks (num/krylovsolver.h:1189-1258) ---------------------------------------
+// p = first ? r : r + beta*(p - omega*v);  phat = M^-1 p                                  :1216-1222
+int bicg_p(size_t n, bool first, double* p, double* phat, const double* r, const double* v, double beta, double omega,
+           int pc, double omega_pc, const double* d);
+// s = r - alpha*v;  shat = M^-1 s;  *d_out = s.s                                          :1225-1232
+int bicg_s(size_t n, double* s, double* shat, const double* r, const double* v, double alpha, int pc, double omega_pc,
+           const double* d, double* d_out);
+// d_out[0] = t.s, d_out[1] = t.t                                                          :1234
+int bicg_ts(size_t n, const double* t, const double* s, double* d_out);
+// x += alpha*phat + omega*shat;  r = s - omega*t;  d_out[0] = r.r, d_out[1] = rtilde.r     :1235-1239, :1209
+int bicg_x(size_t n, double* x, double* r, const double* phat, const double* shat, const double* s, const double* t,
+           const double* rtilde, double alpha, double omega, double* d_out);
+// x += a*y with the reference's rounding (x = x + a*y)
+// ---- GCR building blocks (num/krylovsolver.h:1410-1483) --------------------------------------------
+// One orthogonalisation step: if vprev: vn -= a*vprev, sn -= a*sprev, (vnacc -= a*vaccprev) with a = *d_aprev;
+// then *d_out = dot(vnacc, vacc_cur)  (or |vnacc|_2 when vacc_cur == nullptr).  vnacc == nullptr: the
+// accumulated twin is vn itself.
+int gcr_orth(size_t n, double* vn, double* sn, double* vnacc, const double* vprev, const double* sprev,
+             const double* vaccprev, const double* d_aprev, const double* vacc_cur, double* d_out);
+// vn /= beta, sn /= beta, (vnacc /= beta) with beta = *d_beta;  *d_gamma = dot(racc, vnacc)
+int gcr_scale(size_t n, double* vn, double* sn, double* vnacc, const double* racc, const double* d_beta, double* d_gamma);
+// x += g*sn, r -= g*vn, (racc -= g*vnacc) with g = *d_gamma;  *d_rr = racc.racc
+int gcr_update(size_t n, double* x, double* r, double* racc, const double* sn, const double* vn, const double* vnacc,
+               const double* d_gamma, double* d_rr);
+
 // r = b - t  style helpers
 int vec_sub(size_t n, double* out, const double* a, const double* b);            // out = a - b
 

@@ -107,6 +107,41 @@ bool GMRES(const Mat& A, Vec& x, const Vec& b, const ExT&, PreCon& M, int m, int
     return r == 1;
 }
 
+/// BiCGStab (src/num/krylovsolver.h:1189-1258).  On a breakdown the reference prints a message,
+/// sets max_iter to the iteration and returns false; so does this.
+template <class Mat, class Vec, class Preconditioner, class ExT>
+bool BICGSTAB(const Mat& A, Vec& x, const Vec& b, const ExT&, Preconditioner& M, int& max_iter, double& tol,
+              bool measure_relative_tol = true)
+{
+    const MatrixCL& Mat0 = b200::finest(A);
+    b200::check_dims(Mat0, x, b, "BICGSTAB");
+    int it = max_iter, breakdown = 0;
+    const int r = drops_b200_bicgstab(Mat0.device(), &x[0], Addr(b), b200::PcTraits<Preconditioner>::kind(),
+                                      b200::PcTraits<Preconditioner>::omega(M), &it, &tol,
+                                      measure_relative_tol ? 1 : 0, &breakdown);
+    b200::check(r);
+    if (breakdown == 1) std::cout << "BiCGSTAB: Breakdown with rho_1 = 0.\n";
+    if (breakdown == 2) std::cout << "BiCGSTAB: Breakdown with omega_ = 0.\n";
+    if (r == 1 || breakdown) max_iter = it;
+    return r == 1;
+}
+
+/// GCR(m) with min-alpha truncation (src/num/krylovsolver.h:1410-1483).
+template <typename Mat, typename Vec, typename PreCon, typename ExCL>
+bool GCR(const Mat& A, Vec& x, const Vec& b, const ExCL&, PreCon& M, int m, int& max_iter, double& tol,
+         bool measure_relative_tol = true, std::ostream* output = 0)
+{
+    const MatrixCL& Mat0 = b200::finest(A);
+    b200::check_dims(Mat0, x, b, "GCR");
+    int it = max_iter;
+    const int r = drops_b200_gcr(Mat0.device(), &x[0], Addr(b), b200::PcTraits<PreCon>::kind(),
+                                 b200::PcTraits<PreCon>::omega(M), m, &it, &tol, measure_relative_tol ? 1 : 0);
+    b200::check(r);
+    if (r == 1) max_iter = it;
+    if (output) (*output) << "GCR: k: " << it << "\tresidual: " << tol << std::endl;
+    return r == 1;
+}
+
 //-----------------------------------------------------------------------------
 // Lanczos bases.  They are usable on their own (new_basis / next walk the three-term recurrence
 // with the product on the GPU), and they select the MINRES flavour when handed to PMResSolverCL.
@@ -344,6 +379,67 @@ class GMResSolverCL : public SolverBaseCL
     {
         resid = tol_; numIter = maxiter_;
         GMRES(A, x, b, ex, pc_, restart_, numIter, resid, rel_, calculate2norm_, method_, output_);
+    }
+};
+
+/// BiCGStab driver (src/num/krylovsolver.h:1978-2013); `mod` selects ModBICGSTAB in MPI builds only.
+template <typename PC>
+class BiCGStabSolverCL : public SolverBaseCL
+{
+  private:
+    PC&  pc_;
+    bool mod_;
+
+  public:
+    BiCGStabSolverCL(PC& pc, int maxiter, double tol, bool relative = true, bool mod = true)
+        : SolverBaseCL(maxiter, tol, relative), pc_(pc), mod_(mod) {}
+
+    PC&       GetPc()       { return pc_; }
+    const PC& GetPc() const { return pc_; }
+
+    template <typename Mat, typename Vec, typename ExT>
+    void Solve(const Mat& A, Vec& x, const Vec& b, const ExT& ex)
+    {
+        res_ = tol_; iter_ = maxiter_;
+        BICGSTAB(A, x, b, ex, pc_, iter_, res_, rel_);
+    }
+    template <typename Mat, typename Vec, typename ExT>
+    void Solve(const Mat& A, Vec& x, const Vec& b, const ExT& ex, int& numIter, double& resid) const
+    {
+        resid = tol_; numIter = maxiter_;
+        BICGSTAB(A, x, b, ex, pc_, numIter, resid, rel_);
+    }
+};
+
+/// GCR driver (src/num/krylovsolver.h:2017-2053).
+template <typename PC>
+class GCRSolverCL : public SolverBaseCL
+{
+  private:
+    PC& pc_;
+    int truncate_;
+
+  public:
+    GCRSolverCL(PC& pc, int truncate, int maxiter, double tol, bool relative = true, std::ostream* output = 0)
+        : SolverBaseCL(maxiter, tol, relative, output), pc_(pc), truncate_(truncate) {}
+
+    PC&       GetPc()       { return pc_; }
+    const PC& GetPc() const { return pc_; }
+    int       GetTruncate() const { return truncate_; }
+
+    template <typename Mat, typename Vec, typename ExT>
+    void Solve(const Mat& A, Vec& x, const Vec& b, const ExT& ex)
+    {
+        res_ = tol_; iter_ = maxiter_;
+        GCR(A, x, b, ex, pc_, truncate_, iter_, res_, rel_, output_);
+        if (output_ != 0)
+            *output_ << "GCRSolverCL: iterations: " << GetIter() << "\tresidual: " << GetResid() << std::endl;
+    }
+    template <typename Mat, typename Vec, typename ExT>
+    void Solve(const Mat& A, Vec& x, const Vec& b, const ExT& ex, int& numIter, double& resid) const
+    {
+        resid = tol_; numIter = maxiter_;
+        GCR(A, x, b, ex, pc_, truncate_, numIter, resid, rel_, output_);
     }
 };
 

@@ -193,6 +193,23 @@ DROPS_B200_API int drops_b200_minres_dev(drops_b200_matrix_t A, drops_b200_vecto
                                          int precond, int pc, double omega, int* max_iter, double* tol,
                                          int relative);
 
+/* bicgstab : BICGSTAB, num/krylovsolver.h:1189-1258 (BiCGStabSolverCL<PC>::Solve :1978-2013, serial
+ *            branch).  Returns 0 for "not converged" and for a breakdown, as the reference does;
+ *            *breakdown (may be NULL) is then 1 (rho_1 == 0) or 2 (omega == 0).  Note the
+ *            reference's strict "< tol" inside the loop (:1226, :1240).
+ * gcr      : GCR(m), num/krylovsolver.h:1410-1483 (GCRSolverCL<PC>::Solve :2017-2053), min-alpha
+ *            truncation with `truncate` stored directions, including the reference's behaviour of not
+ *            refreshing vacc[min_idx] after a truncation. */
+DROPS_B200_API int drops_b200_bicgstab(drops_b200_matrix_t A, double* x, const double* b, int pc, double omega,
+                                       int* max_iter, double* tol, int relative, int* breakdown);
+DROPS_B200_API int drops_b200_bicgstab_dev(drops_b200_matrix_t A, drops_b200_vector_t x, drops_b200_vector_t b,
+                                           int pc, double omega, int* max_iter, double* tol, int relative,
+                                           int* breakdown);
+DROPS_B200_API int drops_b200_gcr(drops_b200_matrix_t A, double* x, const double* b, int pc, double omega,
+                                  int truncate, int* max_iter, double* tol, int relative);
+DROPS_B200_API int drops_b200_gcr_dev(drops_b200_matrix_t A, drops_b200_vector_t x, drops_b200_vector_t b,
+                                      int pc, double omega, int truncate, int* max_iter, double* tol, int relative);
+
 /* ---- synthetic brick systems ---------------------------------------
  * Uniform Kuhn brick (BrickBuilderCL, geom/builder.cpp:99-180: 6 tetrahedra per cell sharing the
  * main diagonal) on the unit cube with N cells per direction, homogeneous Dirichlet on all faces,

@@ -281,6 +281,133 @@ done:
 }
 
 /* ---------------------------------------------------------------------------------------
+ * BiCGStab -- num/krylovsolver.h:1189-1258 (BICGSTAB, serial).  Plain dot / norm
+ * (std::inner_product, spmat.h:164-196), not the Kahan sums of the exchange class.
+ * Returns 1 converged, 0 not converged, -1 breakdown (the reference prints a message and
+ * returns false with max_iter = i).
+ * ------------------------------------------------------------------------------------- */
+ORC_API int orc_bicgstab(size_t n, const double* Aval, const size_t* Arow, const size_t* Acol,
+                         int pc_kind, double omega_pc, double* x, const double* b,
+                         int* max_iter, double* tol, int relative)
+{
+    orc_sys S = { n, Aval, Arow, Acol, pc_kind, omega_pc };
+    double rho_1 = 0.0, rho_2 = 0.0, alpha = 0.0, beta = 0.0, omega = 0.0, normb, resid;
+    double *p = vec_new(n), *phat = vec_new(n), *s = vec_new(n), *shat = vec_new(n), *t = vec_new(n),
+           *v = vec_new(n), *r = vec_new(n), *rtilde = vec_new(n);
+    size_t k; int i, ret = 0;
+
+    normb = orc_norm(n, b);                                            /* :1196 */
+    orc_y_Ax(r, n, Aval, Arow, Acol, x);
+    for (k = 0; k < n; ++k) r[k] = b[k] - r[k];                        /* :1197 */
+    memcpy(rtilde, r, n * sizeof(double));
+    if (normb == 0.0 || !relative) normb = 1.0;
+    resid = orc_norm(n, r) / normb;
+    if (resid <= *tol) { *tol = resid; *max_iter = 0; ret = 1; goto done; }
+    for (i = 1; i <= *max_iter; ++i) {
+        rho_1 = orc_dot(n, rtilde, r);                                 /* :1209 */
+        if (rho_1 == 0.0) { *tol = orc_norm(n, r) / normb; *max_iter = i; ret = -1; goto done; }
+        if (i == 1) memcpy(p, r, n * sizeof(double));
+        else {
+            beta = (rho_1 / rho_2) * (alpha / omega);                  /* :1219 */
+            for (k = 0; k < n; ++k) p[k] = r[k] + beta * (p[k] - omega * v[k]);
+        }
+        pc_apply(&S, phat, p);
+        orc_y_Ax(v, n, Aval, Arow, Acol, phat);
+        alpha = rho_1 / orc_dot(n, rtilde, v);                         /* :1224 */
+        for (k = 0; k < n; ++k) s[k] = r[k] - alpha * v[k];
+        if ((resid = orc_norm(n, s) / normb) < *tol) {                 /* :1226 */
+            for (k = 0; k < n; ++k) x[k] += alpha * phat[k];
+            *tol = resid; *max_iter = i; ret = 1; goto done;
+        }
+        pc_apply(&S, shat, s);
+        orc_y_Ax(t, n, Aval, Arow, Acol, shat);
+        omega = orc_dot(n, t, s) / orc_dot(n, t, t);                   /* :1234 */
+        for (k = 0; k < n; ++k) x[k] += alpha * phat[k] + omega * shat[k];
+        for (k = 0; k < n; ++k) r[k] = s[k] - omega * t[k];
+        rho_2 = rho_1;
+        if ((resid = orc_norm(n, r) / normb) < *tol) { *tol = resid; *max_iter = i; ret = 1; goto done; }
+        if (omega == 0.0) { *tol = orc_norm(n, r) / normb; *max_iter = i; ret = -1; goto done; }
+    }
+    *tol = resid;
+done:
+    free(p); free(phat); free(s); free(shat); free(t); free(v); free(r); free(rtilde);
+    return ret;
+}
+
+/* ---------------------------------------------------------------------------------------
+ * GCR(m) -- num/krylovsolver.h:1410-1483 with DummyExchangeCL: Norm / ParDot are Kahan sums,
+ * GetAccumulate is a copy.  The reference carries "accumulated" twins (racc, vnacc, vacc[i])
+ * beside r, vn, v[i]; serially they hold the same values UNTIL the truncation branch
+ * (:1466-1477) replaces s[min_idx] and v[min_idx] but not vacc[min_idx].  From then on the
+ * twins differ, and the coefficients (computed from the acc twins) no longer match the vectors
+ * they are applied to.  This restatement keeps the twins, i.e. reproduces that behaviour.
+ * ------------------------------------------------------------------------------------- */
+ORC_API int orc_gcr(size_t n, const double* Aval, const size_t* Arow, const size_t* Acol,
+                    int pc_kind, double omega_pc, double* x, const double* b, int m,
+                    int* max_iter, double* tol, int relative)
+{
+    orc_sys S = { n, Aval, Arow, Acol, pc_kind, omega_pc };
+    double *r = vec_new(n), *racc = vec_new(n), *sn = vec_new(n), *vn = vec_new(n), *vnacc = vec_new(n);
+    double **s, **v, **vacc, *a;
+    double normb, resid;
+    size_t q; int k, i, stored = 0, ret = 0;
+
+    m = (m <= *max_iter) ? m : *max_iter;                              /* :1416 */
+    if (m < 1) m = 1;
+    s = (double**)calloc((size_t)m, sizeof(double*));
+    v = (double**)calloc((size_t)m, sizeof(double*));
+    vacc = (double**)calloc((size_t)m, sizeof(double*));
+    a = (double*)calloc((size_t)m, sizeof(double));
+    orc_y_Ax(r, n, Aval, Arow, Acol, x);
+    for (q = 0; q < n; ++q) r[q] = b[q] - r[q];                        /* :1418 */
+    normb = orc_kahan_norm(n, b);
+    if (normb == 0.0 || !relative) normb = 1.0;
+    resid = orc_kahan_norm(n, r) / normb;                              /* Norm(r, false, &racc) */
+    memcpy(racc, r, n * sizeof(double));
+    for (k = 0; k < *max_iter; ++k) {
+        double beta, gamma;
+        if (resid < *tol) { *tol = resid; *max_iter = k; ret = 1; goto done; }
+        pc_apply(&S, sn, r);
+        orc_y_Ax(vn, n, Aval, Arow, Acol, sn);                         /* vn = A*GetAccumulate(sn) */
+        memcpy(vnacc, vn, n * sizeof(double));
+        for (i = 0; i < k && i < m; ++i) {                             /* :1442-1449 */
+            const double alpha = orc_kahan_dot(n, vnacc, vacc[i]);
+            a[i] = alpha;
+            for (q = 0; q < n; ++q) vn[q] -= alpha * v[i][q];
+            for (q = 0; q < n; ++q) vnacc[q] -= alpha * vacc[i][q];
+            for (q = 0; q < n; ++q) sn[q] -= alpha * s[i][q];
+        }
+        beta = orc_kahan_norm(n, vnacc);
+        for (q = 0; q < n; ++q) vn[q] /= beta;
+        for (q = 0; q < n; ++q) vnacc[q] /= beta;
+        for (q = 0; q < n; ++q) sn[q] /= beta;
+        gamma = orc_kahan_dot(n, racc, vnacc);
+        for (q = 0; q < n; ++q) x[q] += gamma * sn[q];
+        for (q = 0; q < n; ++q) r[q] -= gamma * vn[q];
+        for (q = 0; q < n; ++q) racc[q] -= gamma * vnacc[q];
+        resid = orc_kahan_norm(n, racc) / normb;
+        if (k < m) {
+            s[stored] = vec_new(n); v[stored] = vec_new(n); vacc[stored] = vec_new(n);
+            memcpy(s[stored], sn, n * sizeof(double)); memcpy(v[stored], vn, n * sizeof(double));
+            memcpy(vacc[stored], vnacc, n * sizeof(double));
+            ++stored;
+        } else {
+            int min_idx = 0;
+            double a_min = fabs(a[0]);
+            for (i = 1; i < k && i < m; ++i)
+                if (fabs(a[i]) < a_min) { min_idx = i; a_min = fabs(a[i]); }
+            memcpy(s[min_idx], sn, n * sizeof(double)); memcpy(v[min_idx], vn, n * sizeof(double));
+            /* vacc[min_idx] keeps its old contents, as in the reference */
+        }
+    }
+    *tol = resid;
+done:
+    for (i = 0; i < stored; ++i) { free(s[i]); free(v[i]); free(vacc[i]); }
+    free(s); free(v); free(vacc); free(a); free(r); free(racc); free(sn); free(vn); free(vnacc);
+    return ret;
+}
+
+/* ---------------------------------------------------------------------------------------
  * GMRES (serial) -- num/krylovsolver.h:258-297 (rotations, update), :320-461 (driver).
  * H is stored column-major m x m like DMatrixCL (misc/container.h:44-74).
  * ------------------------------------------------------------------------------------- */

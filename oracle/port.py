@@ -50,6 +50,8 @@ def lib():
         "orc_cg": (i, [sz] + csr + [_dp, _dp, ip, dpp, i, vp, i]),
         "orc_pcg": (i, [sz] + csr + [i, d, _dp, _dp, ip, dpp, i, vp, i]),
         "orc_gmres": (i, [sz] + csr + [i, d, _dp, _dp, i, ip, dpp, i, i]),
+        "orc_bicgstab": (i, [sz] + csr + [i, d, _dp, _dp, ip, dpp, i]),
+        "orc_gcr": (i, [sz] + csr + [i, d, _dp, _dp, i, ip, dpp, i]),
         "orc_minres": (i, [sz] + csr + [i, i, d, _dp, _dp, ip, dpp, i]),
         "orc_lanczos_basis": (i, [sz] + csr + [_dp, i, _dp, _dp, _dp]),
     }
@@ -157,6 +159,21 @@ class PortMatrix:
 
     def gmres_dummy(self, x0, b, restart, max_iter, tol, relative=True, left=True):
         return self._gmres(0, 1.0, x0, b, restart, max_iter, tol, relative, left)
+
+    def bicgstab(self, x0, b, max_iter, tol, relative=True, pc=1, omega=1.0):
+        """(converged, iters, resid, x); a breakdown reports converged = False like the reference."""
+        x = _f64(x0).copy()
+        it, res = C.c_int(int(max_iter)), C.c_double(float(tol))
+        conv = lib().orc_bicgstab(self.rows, *self._csr, int(pc), float(omega), x, _f64(b),
+                                  C.byref(it), C.byref(res), int(relative))
+        return conv == 1, it.value, res.value, x
+
+    def gcr(self, x0, b, m, max_iter, tol, relative=True, pc=1, omega=1.0):
+        x = _f64(x0).copy()
+        it, res = C.c_int(int(max_iter)), C.c_double(float(tol))
+        conv = lib().orc_gcr(self.rows, *self._csr, int(pc), float(omega), x, _f64(b), int(m),
+                             C.byref(it), C.byref(res), int(relative))
+        return conv == 1, it.value, res.value, x
 
     def _minres(self, precond, pc_kind, omega, x0, b, max_iter, tol, relative):
         x = _f64(x0).copy()

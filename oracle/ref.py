@@ -65,6 +65,8 @@ def lib():
         "ref_cg": (i, [vp, _dp, _dp, ip, dpp, i, vp, i]),
         "ref_gmres_jacobi": (i, [vp, _dp, _dp, d, i, ip, dpp, i, i]),
         "ref_gmres_dummy": (i, [vp, _dp, _dp, i, ip, dpp, i, i]),
+        "ref_bicgstab": (i, [vp, _dp, _dp, i, d, ip, dpp, i]),
+        "ref_gcr": (i, [vp, _dp, _dp, i, d, i, ip, dpp, i]),
         "ref_minres": (i, [vp, _dp, _dp, ip, dpp, i]),
         "ref_pminres_jacobi": (i, [vp, _dp, _dp, d, ip, dpp, i]),
         "ref_pminres_dummy": (i, [vp, _dp, _dp, ip, dpp, i]),
@@ -191,6 +193,16 @@ class RefMatrix:
     def gmres_dummy(self, x0, b, restart, max_iter, tol, relative=True, left=True):
         return self._solve(lib().ref_gmres_dummy, x0, b, max_iter, tol,
                            pre=(int(restart),), post=(int(relative), int(left)), hist=None)
+
+    def bicgstab(self, x0, b, max_iter, tol, relative=True, pc=1, omega=1.0):
+        """BICGSTAB (krylovsolver.h:1189-1258); pc: 0 DummyPcCL, 1 JACPcCL.  (converged, iters, resid, x)"""
+        return self._solve(lib().ref_bicgstab, x0, b, max_iter, tol, pre=(int(pc), float(omega)),
+                           post=(int(relative),), hist=None)
+
+    def gcr(self, x0, b, m, max_iter, tol, relative=True, pc=1, omega=1.0):
+        """GCR(m) (krylovsolver.h:1410-1483)."""
+        return self._solve(lib().ref_gcr, x0, b, max_iter, tol, pre=(int(pc), float(omega), int(m)),
+                           post=(int(relative),), hist=None)
 
     def minres(self, x0, b, max_iter, tol, relative=False):
         return self._solve(lib().ref_minres, x0, b, max_iter, tol, post=(int(relative),), hist=None)

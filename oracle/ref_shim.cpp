@@ -70,6 +70,38 @@ void from_vec(const DROPS::VectorCL& v, double* p) { if (v.size()) std::memcpy(p
 
 } // namespace
 
+template <typename PC>
+static int run_bicgstab(const DROPS::MatrixCL& A, PC& pc, double* x, const double* b, int* max_iter, double* tol,
+                        int relative)
+{
+    const size_t n = A.num_rows();
+    DROPS::VectorCL xv(to_vec(x, n)), bv(to_vec(b, n));
+    bool ok;
+    {
+        CoutCapture cap;
+        ok = DROPS::BICGSTAB(A, xv, bv, DROPS::DummyExchangeCL(), pc, *max_iter, *tol, relative != 0);
+        g_last_log = cap.sink.str();
+    }
+    from_vec(xv, x);
+    return ok ? 1 : 0;
+}
+
+template <typename PC>
+static int run_gcr(const DROPS::MatrixCL& A, PC& pc, double* x, const double* b, int m, int* max_iter, double* tol,
+                   int relative)
+{
+    const size_t n = A.num_rows();
+    DROPS::VectorCL xv(to_vec(x, n)), bv(to_vec(b, n));
+    bool ok;
+    {
+        CoutCapture cap;
+        ok = DROPS::GCR(A, xv, bv, DROPS::DummyExchangeCL(), pc, m, *max_iter, *tol, relative != 0);
+        g_last_log = cap.sink.str();
+    }
+    from_vec(xv, x);
+    return ok ? 1 : 0;
+}
+
 extern "C" {
 
 int ref_num_threads()
@@ -294,6 +326,29 @@ int ref_gmres_jacobi(void* h, double* x, const double* b, double omega, int rest
     *max_iter = solver.GetIter();
     *tol = solver.GetResid();
     return solver.GetResid() <= tol_in ? 1 : 0;
+}
+
+// BiCGStabSolverCL<PC>::Solve (krylovsolver.h:1978-2013 -> serial BICGSTAB :1189-1258) and
+// GCRSolverCL<PC>::Solve (:2017-2053 -> GCR :1410-1483).  pc_kind 0 = DummyPcCL, 1 = JACPcCL.
+// Return: 1 converged, 0 not (a breakdown also returns 0; the message is in ref_last_log).
+
+int ref_bicgstab(void* h, double* x, const double* b, int pc_kind, double omega, int* max_iter, double* tol,
+                 int relative)
+{
+    const DROPS::MatrixCL& A = static_cast<RefMatrix*>(h)->A;
+    if (pc_kind == 1) { DROPS::JACPcCL pc(omega); return run_bicgstab(A, pc, x, b, max_iter, tol, relative); }
+    DROPS::DummyPcCL pc;
+    return run_bicgstab(A, pc, x, b, max_iter, tol, relative);
+}
+
+
+int ref_gcr(void* h, double* x, const double* b, int pc_kind, double omega, int m, int* max_iter, double* tol,
+            int relative)
+{
+    const DROPS::MatrixCL& A = static_cast<RefMatrix*>(h)->A;
+    if (pc_kind == 1) { DROPS::JACPcCL pc(omega); return run_gcr(A, pc, x, b, m, max_iter, tol, relative); }
+    DROPS::DummyPcCL pc;
+    return run_gcr(A, pc, x, b, m, max_iter, tol, relative);
 }
 
 int ref_gmres_dummy(void* h, double* x, const double* b, int restart,

@@ -114,6 +114,46 @@ int main()
             print_vec("PMINRES4D x", x);
         }
     }
+    // --- BiCGStab / GCR 2x2 and 4x4 (bicgstab.cpp + TestBiCGStab.ref, gcr.cpp + TestGCR.ref) ---------
+    {
+        MatrixCL A2;
+        MatrixBuilderCL AB(&A2, 2, 2);
+        AB(0, 1) = 1.; AB(1, 0) = 1.;
+        AB.Build();
+        VectorCL b2(2);
+        b2[0] = 1.; b2[1] = 2.;
+        MatrixCL A4; VectorCL b4;
+        fill_4x4(A4, b4);
+        DummyPcCL pc;
+        {
+            VectorCL x(0., 2);
+            int mi = 10; double tol = 1e-10;
+            BICGSTAB(A2, x, b2, ex, pc, mi, tol);
+            std::printf("BICGSTAB2 iterations: %d residual: %.6e\n", mi, tol);
+            print_vec("BICGSTAB2 x", x);
+        }
+        {
+            VectorCL x(0., 4);
+            int mi = 10; double tol = 1e-10;
+            BICGSTAB(A4, x, b4, ex, pc, mi, tol);
+            std::printf("BICGSTAB4 iterations: %d residual: %.6e\n", mi, tol);
+            print_vec("BICGSTAB4 x", x);
+        }
+        {
+            VectorCL x(3., 2);
+            int mi = 100; double tol = 1e-10;
+            GCR(A2, x, b2, ex, pc, 10, mi, tol, false);
+            std::printf("GCR2 iterations: %d residual: %.6e\n", mi, tol);
+            print_vec("GCR2 x", x);
+        }
+        {
+            VectorCL x(0., 4);
+            int mi = 100; double tol = 1e-10;
+            GCR(A4, x, b4, ex, pc, 10, mi, tol, false);
+            std::printf("GCR4 iterations: %d residual: %.6e\n", mi, tol);
+            print_vec("GCR4 x", x);
+        }
+    }
     // --- transp_mul (blockmat.cpp) -----------------------------------------------------------------
     {
         MatrixCL B;
@@ -204,6 +244,16 @@ int main()
             GMResSolverCL<JACPcCL> rsolver(pc, 20, 500, 1e-10, true, false, RightPreconditioning);
             rsolver.Solve(G, x, bg, ex);
             std::printf("GMRESJACR iterations: %d residual: %.3e error: %.3e\n", rsolver.GetIter(), rsolver.GetResid(),
+                        norm(VectorCL(x - xs)) / norm(xs));
+            x = 0.;
+            BiCGStabSolverCL<JACPcCL> bsolver(pc, 500, 1e-10);
+            bsolver.Solve(G, x, bg, ex);
+            std::printf("BICGSTABJAC iterations: %d residual: %.3e error: %.3e\n", bsolver.GetIter(), bsolver.GetResid(),
+                        norm(VectorCL(x - xs)) / norm(xs));
+            x = 0.;
+            GCRSolverCL<JACPcCL> gsolver(pc, 100, 500, 1e-10);
+            gsolver.Solve(G, x, bg, ex);
+            std::printf("GCRJAC iterations: %d residual: %.3e error: %.3e\n", gsolver.GetIter(), gsolver.GetResid(),
                         norm(VectorCL(x - xs)) / norm(xs));
             // matrix modified in place: Version() changes, the product must follow
             G *= 2.;

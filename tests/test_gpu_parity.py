@@ -311,6 +311,63 @@ def test_solvers_against_reference(gpu, path):
     check_solve(A.gmres_dummy(x0, b, 20, 400, 1e-10, False, True), g, f"{tag}_gmresdummy")
 
 
+def test_bicgstab_and_gcr_against_reference(gpu):
+    """BiCGStab (krylovsolver.h:1189-1258) and GCR(m) (:1410-1483) against the compiled reference's
+    results (tests/golden/krylov_extra.npz) and the reference's own known-answer systems."""
+    E = load_golden("krylov_extra.npz")
+    calls = {"bicgstab_jac": lambda A, x0, b: A.bicgstab(x0, b, 400, 1e-10, True, gpu.PC_JACOBI, 1.0),
+             "bicgstab_dummy": lambda A, x0, b: A.bicgstab(x0, b, 400, 1e-10, True, gpu.PC_DUMMY),
+             "bicgstab_jac_abs_w08": lambda A, x0, b: A.bicgstab(x0, b, 400, 1e-9, False, gpu.PC_JACOBI, 0.8),
+             "gcr_jac_m100": lambda A, x0, b: A.gcr(x0, b, 100, 400, 1e-10, True, gpu.PC_JACOBI, 1.0),
+             "gcr_dummy_m100": lambda A, x0, b: A.gcr(x0, b, 100, 400, 1e-10, True, gpu.PC_DUMMY)}
+    for path in golden_files("brick_*.npz") + golden_files("random_spd*.npz"):
+        g = dict(np.load(path))
+        name = path.split("/")[-1][:-4]
+        A = gmat(gpu, g)
+        n = A.rows
+        for key, fn in calls.items():
+            out = fn(A, np.zeros(n), g["b"])
+            exp, xe = E[f"{name}/{key}"], E[f"{name}/{key}_x"]
+            assert out[0] == bool(exp[0]) and abs(out[1] - int(exp[1])) <= 1, (name, key, out[:3], exp)
+            if out[1] == int(exp[1]):
+                # BiCGStab amplifies rounding differences of its dot products (the reference sums them
+                # left to right): compare the solutions at the level both reach (tol 1e-10 / 1e-9)
+                assert rel(out[3], xe) <= 1e-7, (name, key, rel(out[3], xe))
+        # truncated GCR: same (non-)convergence and residual level as the reference, stale vacc[] included
+        out = A.gcr(np.zeros(n), g["b"], 4, 60, 1e-10, True, gpu.PC_JACOBI, 1.0)
+        exp = E[f"{name}/gcr_jac_m4_trunc"]
+        assert out[0] == bool(exp[0])
+        if not out[0]:
+            assert out[1] == 60 and 0.2 <= out[2] / exp[2] <= 5.0, (name, out[:3], exp)
+    A2 = gpu.Matrix(2, 2, [0, 1, 2], [1, 0], [1., 1.])
+    M = np.array([[-249., -453, -397, -52], [-453, -731, -601, -78], [-397, -601, -648, -91], [-52, -78, -91, -13]])
+    A4 = gpu.Matrix(4, 4, np.arange(0, 17, 4), np.tile(np.arange(4), 4), M.reshape(-1))
+    b2, b4 = np.array([1., 2.]), np.array([-1277. / 2, -2015. / 2, -3907. / 4, -533. / 4])
+    out = A2.bicgstab(np.zeros(2), b2, 10, 1e-10, True, gpu.PC_DUMMY)       # bicgstab.cpp Test()
+    assert out[0] and out[1] == int(E["kat/bicgstab2"][1]) and abs(out[2]) < 1e-10 and np.allclose(out[3], [2., 1.])
+    out = A4.bicgstab(np.zeros(4), b4, 10, 1e-10, True, gpu.PC_DUMMY)       # Test2(): "Case 2 Residual" 0 +- 1e-10
+    assert out[0] and abs(out[1] - int(E["kat/bicgstab4"][1])) <= 1 and abs(out[2]) < 1e-10
+    assert np.allclose(out[3], [0.25, 0.5, 0.75, 1.0], atol=1e-5)
+    out = A2.gcr(np.full(2, 3.0), b2, 10, 100, 1e-10, False, gpu.PC_DUMMY)  # gcr.cpp Test()
+    assert out[0] and out[1] == int(E["kat/gcr2"][1]) and abs(out[2]) < 1e-10 and np.allclose(out[3], [2., 1.])
+    out = A4.gcr(np.zeros(4), b4, 10, 100, 1e-10, False, gpu.PC_DUMMY)      # Test2()
+    assert out[0] and abs(out[1] - int(E["kat/gcr4"][1])) <= 1 and abs(out[2]) < 1e-10
+    assert np.allclose(out[3], [0.25, 0.5, 0.75, 1.0], atol=1e-8)
+    # live against the oracle on a larger nonsymmetric system
+    n, rb, ci, va = gpu.brick_csr_host(2, 12, 1, 1.1)
+    rows = np.repeat(np.arange(n), np.diff(rb.astype(np.int64)))
+    va = va.copy()
+    va[ci.astype(np.int64) == rows] *= 1.25
+    from oracle import port as oport
+    P = oport.PortMatrix(n, n, rb, ci, va)
+    G = gpu.Matrix(n, n, rb, ci, va)
+    b = P.spmv(gpu.brick_solution_host(2, 12, 1))
+    r, o = P.bicgstab(np.zeros(n), b, 500, 1e-9, True, 1), G.bicgstab(np.zeros(n), b, 500, 1e-9, True, gpu.PC_JACOBI)
+    assert r[0] and o[0] and abs(o[1] - r[1]) <= 1 and rel(o[3], r[3]) <= 1e-7
+    r, o = P.gcr(np.zeros(n), b, 100, 500, 1e-9, True, 1), G.gcr(np.zeros(n), b, 100, 500, 1e-9, True, gpu.PC_JACOBI)
+    assert r[0] and o[0] and abs(o[1] - r[1]) <= 1 and rel(o[3], r[3]) <= 1e-8
+
+
 def test_solver_edge_cases(gpu):
     g = load_golden("brick_fe2_N4_num0.npz")
     A = gmat(gpu, g)

@@ -17,7 +17,7 @@ EXPECTED = os.path.join(ROOT, "tests", "golden", "hotpath_kats.expected.txt")
 
 KEYS = ("LANCZOS", "MINRES2", "MINRES4", "PMINRES4", "PMINRES4D", "TRANSP_MUL", "B*c", "VECEXPR", "VECOPS",
         "EXCHANGE", "LAPLACE", "PCGJAC", "PCGJAC08", "CG", "PCGJAC5", "JACAPPLY", "GMRESJAC", "GMRESJACR",
-        "VERSIONED", "hotpath_kats")
+        "VERSIONED", "hotpath_kats", "BICGSTAB2", "BICGSTAB4", "GCR2", "GCR4", "BICGSTABJAC", "GCRJAC")
 
 
 def parse(text):
@@ -52,6 +52,9 @@ def test_expected_output_holds_the_reference_kats():
     assert abs(exp["PMINRES4D iterations"][1] - 2.87596e-11) < 1e-10    # TestMinres.ref Residual5
     assert exp["TRANSP_MUL"] == [3.0, 3.0]                              # Testblockmat.ref
     assert exp["VECEXPR maxdiff"][0] <= 1e-16                           # Testvectest.ref
+    # bicgstab.cpp / TestBiCGStab.ref and gcr.cpp / TestGCR.ref: residuals 0 +- 1e-10
+    for key in ("BICGSTAB2 iterations", "BICGSTAB4 iterations", "GCR2 iterations", "GCR4 iterations"):
+        assert abs(exp[key][1]) < 1e-10, key
     assert "hotpath_kats finished regularly" in open(EXPECTED).read()
 
 
@@ -75,6 +78,15 @@ def test_dropin_binary_matches_reference_output(lib_built):
     for key in ("MINRES4 iterations", "PMINRES4 iterations", "PMINRES4D iterations"):
         assert abs(got[key][0] - exp[key][0]) <= 1 and abs(got[key][1] - exp[key][1]) < 1e-10, key
     for key in ("PCGJAC iterations", "CG iterations", "GMRESJAC iterations", "GMRESJACR iterations"):
+        assert abs(got[key][0] - exp[key][0]) <= 1, (key, got[key], exp[key])
+        assert got[key][1] <= 1e-10 and got[key][2] <= 1e-8, (key, got[key])
+    # BiCGStab / GCR known-answer systems (TestBiCGStab.ref, TestGCR.ref: residual 0 +- 1e-10)
+    for key in ("BICGSTAB2", "BICGSTAB4", "GCR2", "GCR4"):
+        assert abs(got[key + " iterations"][0] - exp[key + " iterations"][0]) <= 1, key
+        assert abs(got[key + " iterations"][1]) < 1e-10, key
+        tolx = 1e-6 if key == "BICGSTAB4" else 1e-9      # the reference itself stops at 6e-12 on the 4x4 system
+        assert all(abs(a - b) <= tolx * max(1.0, abs(b)) for a, b in zip(got[key + " x"], exp[key + " x"])), key
+    for key in ("BICGSTABJAC iterations", "GCRJAC iterations"):
         assert abs(got[key][0] - exp[key][0]) <= 1, (key, got[key], exp[key])
         assert got[key][1] <= 1e-10 and got[key][2] <= 1e-8, (key, got[key])
     assert abs(got["PCGJAC08 converged"][1] - exp["PCGJAC08 converged"][1]) <= 1 and got["PCGJAC08 converged"][0] == 1

@@ -194,3 +194,40 @@ def test_reference_kats_live(refmod):
     assert np.array_equal(B.spmv_transpose(np.array([3.])), [3., 3.])
     Sb, STb = refmod.blockmat_saddle(A2, B, np.array([1., 2., 3.]))
     assert np.array_equal(Sb, [5., 4., 3.]) and np.array_equal(STb, [5., 4., 3.])
+
+
+def test_oracle_bicgstab_and_gcr_match_reference_fixtures(port):
+    """oracle/drops_oracle.c BiCGStab (krylovsolver.h:1189-1258) and GCR (:1410-1483, including the
+    stale vacc[min_idx] of the truncation branch) against tests/golden/krylov_extra.npz, produced by
+    the compiled reference (oracle/make_golden_extra.py): bit-identical, and the reference's own
+    known-answer systems (src/tests/bicgstab.cpp + TestBiCGStab.ref, src/tests/gcr.cpp + TestGCR.ref)."""
+    E = load_golden("krylov_extra.npz")
+    systems = sorted({k.split("/")[0] for k in E if not k.startswith("kat/")})
+    assert len(systems) >= 6
+    calls = {"bicgstab_jac": lambda P, x0, b: P.bicgstab(x0, b, 400, 1e-10, True, 1, 1.0),
+             "bicgstab_dummy": lambda P, x0, b: P.bicgstab(x0, b, 400, 1e-10, True, 0),
+             "bicgstab_jac_abs_w08": lambda P, x0, b: P.bicgstab(x0, b, 400, 1e-9, False, 1, 0.8),
+             "gcr_jac_m100": lambda P, x0, b: P.gcr(x0, b, 100, 400, 1e-10, True, 1, 1.0),
+             "gcr_dummy_m100": lambda P, x0, b: P.gcr(x0, b, 100, 400, 1e-10, True, 0),
+             "gcr_jac_m4_trunc": lambda P, x0, b: P.gcr(x0, b, 4, 60, 1e-10, True, 1, 1.0)}
+    for name in systems:
+        g = load_golden(name + ".npz")
+        n = int(g["rows"])
+        P = port.PortMatrix(n, n, g["rowbeg"], g["colind"], g["val"])
+        for key, fn in calls.items():
+            c, it, res, x = fn(P, np.zeros(n), g["b"])
+            exp = E[f"{name}/{key}"]
+            assert (c, it) == (bool(exp[0]), int(exp[1])), (name, key)
+            assert res == exp[2] and np.array_equal(x, E[f"{name}/{key}_x"]), (name, key)
+    # reference test programs: residuals 0 +- 1e-10 (TestBiCGStab.ref, TestGCR.ref)
+    A2 = port.PortMatrix(2, 2, [0, 1, 2], [1, 0], [1., 1.])
+    M = np.array([[-249., -453, -397, -52], [-453, -731, -601, -78], [-397, -601, -648, -91], [-52, -78, -91, -13]])
+    A4 = port.PortMatrix(4, 4, np.arange(0, 17, 4), np.tile(np.arange(4), 4), M.reshape(-1))
+    b2, b4 = np.array([1., 2.]), np.array([-1277. / 2, -2015. / 2, -3907. / 4, -533. / 4])
+    for key, r in [("kat/bicgstab2", A2.bicgstab(np.zeros(2), b2, 10, 1e-10, True, 0)),
+                   ("kat/bicgstab4", A4.bicgstab(np.zeros(4), b4, 10, 1e-10, True, 0)),
+                   ("kat/gcr2", A2.gcr(np.full(2, 3.0), b2, 10, 100, 1e-10, False, 0)),
+                   ("kat/gcr4", A4.gcr(np.zeros(4), b4, 10, 100, 1e-10, False, 0))]:
+        assert r[0] and r[1] == int(E[key][1]) and r[2] == E[key][2] and abs(r[2]) < 1e-10, key
+        assert np.array_equal(r[3], E[key + "_x"]), key
+    assert np.allclose(E["kat/gcr2_x"], [2., 1.]) and np.allclose(E["kat/gcr4_x"], [0.25, 0.5, 0.75, 1.0])
