@@ -219,7 +219,11 @@ static void launch_sell_v(const SellView& v, const SpmvArgs& a, const EpiArgs& e
         return;
     }
     const long long nwarps = (long long)grid * (threads >> 5);
-    if (opt("spmv.dotmode", 2.0) == 2.0 && nwarps <= kPartialStride) {
+    // small grids: finish the dot inside the kernel (one launch less per iteration, which is what
+    // counts on launch-bound systems); large grids: per-warp partials + finishing kernel
+    const double mode = opt("spmv.dotmode", 0.0);
+    const bool two_kernels = mode == 2.0 || (mode == 0.0 && grid > (int)kReduceFlat);
+    if (two_kernels && nwarps <= kPartialStride) {
         k_spmv_sell<EPI, EXACT, 2, U, MAXT, MINB, SPLIT><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
         sum_warp_partials(nwarps, e, st);
     } else {

@@ -22,9 +22,12 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <fstream>
+#include <iostream>
 #include <list>
 #include <map>
 #include <numeric>
+#include <string>
 #include <type_traits>
 #include <valarray>
 #include <vector>
@@ -328,6 +331,8 @@ class SparseMatBaseCL
     }
     void clear() { resize(0, 0, 0); }
 
+    /// Writes the matrix in MatrixMarket coordinate format (src/num/spmat.h:1085-1089).
+    SparseMatBaseCL& exportMTX(const std::string& path);
     VectorBaseCL<T> GetDiag() const
     {
         Assert(num_rows() == num_cols(), "SparseMatBaseCL::GetDiag: no square Matrix", DebugParallelC);
@@ -418,6 +423,105 @@ template <typename _VecEntry>
 VectorBaseCL<_VecEntry> transp_mul(const MLSparseMatBaseCL<double>& A, const VectorBaseCL<_VecEntry>& x)
 {
     return transp_mul(A.GetFinest(), x);
+}
+
+//*****************************************************************************
+//  Matrix / vector text I/O (src/num/spmat.h:1196-1288): same formats as the reference, so matrices
+//  written by a DROPS run (exportMTX :1085-1089, out) replay through this path and vice versa.
+//*****************************************************************************
+/// MatrixMarket coordinate output, 1-based, 15 digits (:1213-1224).
+template <typename T>
+std::ostream& operator<<(std::ostream& os, const SparseMatBaseCL<T>& A)
+{
+    const size_t M = A.num_rows();
+    os << "%%MatrixMarket matrix coordinate real general\n" << A.num_rows() << ' ' << A.num_cols() << ' '
+       << A.num_nonzeros() << '\n';
+    os.precision(15);
+    for (size_t row = 0; row < M; ++row)
+        for (size_t col = A.row_beg(row), rowend = A.row_beg(row + 1); col < rowend; ++col)
+            os << row + 1 << ' ' << A.col_ind(col) + 1 << ' ' << std::scientific << A.val(col) << '\n';
+    return os << std::flush;
+}
+
+template <typename T>
+SparseMatBaseCL<T>& SparseMatBaseCL<T>::exportMTX(const std::string& path)
+{
+    std::ofstream out(path);
+    out << *this;
+    return *this;
+}
+
+/// Plain CSR dump, readable by in() (:1227-1238).  Uses the stream's current precision.
+template <typename T>
+void out(std::ostream& os, const SparseMatBaseCL<T>& A)
+{
+    os << A.num_rows() << ' ' << A.num_cols() << ' ' << A.num_nonzeros() << '\n';
+    for (size_t row = 0; row <= A.num_rows(); ++row) os << A.row_beg(row) << ' ';
+    os << '\n';
+    for (size_t nz = 0; nz < A.num_nonzeros(); ++nz) os << A.col_ind(nz) << ' ';
+    os << '\n';
+    for (size_t nz = 0; nz < A.num_nonzeros(); ++nz) os << A.val(nz) << ' ';
+    os << std::endl;
+}
+
+/// Reads the output of out() (:1241-1255).
+template <typename T>
+void in(std::istream& is, SparseMatBaseCL<T>& A)
+{
+    size_t numrows, numcols, numnz;
+    is >> numrows >> numcols >> numnz;
+    A.resize(numrows, numcols, numnz);
+    T* val = A.raw_val();
+    size_t* row_beg = A.raw_row();
+    size_t* col_ind = A.raw_col();
+    for (size_t row = 0; row <= numrows; ++row) is >> row_beg[row];
+    for (size_t nz = 0; nz < numnz; ++nz) is >> col_ind[nz];
+    for (size_t nz = 0; nz < numnz; ++nz) is >> val[nz];
+}
+
+/// Reads "% rows x cols nonzeros" + 1-based triplets (:1258-1288; the older DROPS text format --
+/// like the reference, it does NOT read the MatrixMarket header that operator<< writes today).
+template <typename T>
+std::istream& operator>>(std::istream& in, SparseMatBaseCL<T>& A)
+{
+    size_t numrows, numcols, numnz;
+    while (in && in.get() != '%') ;
+    in >> numrows;
+    while (in && in.get() != 'x') ;
+    in >> numcols >> numnz;
+    while (in && in.get() != '\n') ;
+    if (!in) throw DROPSErrCL("SparseMatBaseCL operator>>: Missing \"% rows cols nz\" comment.\n");
+    SparseMatBuilderCL<T> B(&A, numrows, numcols);
+    size_t r, c;
+    T v;
+    for (size_t nz = 0; nz < numnz; ++nz) {
+        in >> r >> c >> v;
+        if (!in) throw DROPSErrCL("SparseMatBaseCL operator>>: Stream corrupt.\n");
+        if (r > numrows || c > numcols) {
+            std::cout << "r: " << r << "\tc: " << c << "\tv: " << v << "\tnz: " << nz << '\n';
+            throw DROPSErrCL("SparseMatBaseCL operator>>: Inconsistent data.\n");
+        }
+        B(r - 1, c - 1) = v;
+    }
+    B.Build();
+    return in;
+}
+
+/// Vector I/O (:1196-1210).
+template <typename T>
+void out(std::ostream& os, const VectorBaseCL<T>& v)
+{
+    os << v.size() << '\n';
+    for (size_t i = 0; i < v.size(); ++i) os << v[i] << ' ';
+    os << std::endl;
+}
+template <typename T>
+void in(std::istream& is, VectorBaseCL<T>& v)
+{
+    size_t s;
+    is >> s;
+    v.resize(s);
+    for (size_t i = 0; i < s; ++i) is >> v[i];
 }
 
 typedef VectorBaseCL<double>       VectorCL;

@@ -66,6 +66,8 @@ def lib():
         "ref_gmres_jacobi": (i, [vp, _dp, _dp, d, i, ip, dpp, i, i]),
         "ref_gmres_dummy": (i, [vp, _dp, _dp, i, ip, dpp, i, i]),
         "ref_bicgstab": (i, [vp, _dp, _dp, i, d, ip, dpp, i]),
+        "ref_matrix_write": (i, [vp, C.c_char_p, i, i]),
+        "ref_matrix_read_text": (vp, [C.c_char_p]),
         "ref_gcr": (i, [vp, _dp, _dp, i, d, i, ip, dpp, i]),
         "ref_minres": (i, [vp, _dp, _dp, ip, dpp, i]),
         "ref_pminres_jacobi": (i, [vp, _dp, _dp, d, ip, dpp, i]),
@@ -109,6 +111,24 @@ class RefMatrix:
         ti, tj, tv = _u64(ti), _u64(tj), _f64(tv)
         self.h = L.ref_matrix_build_triplets(self.rows, self.cols, int(tv.size), ti, tj, tv)
         self.nnz = int(L.ref_matrix_nnz(self.h))
+        return self
+
+    def write(self, path, fmt="mtx", precision=17):
+        """The reference's own writers: fmt "mtx" = operator<< (spmat.h:1213-1224), "text" = out() (:1227-1238)."""
+        if lib().ref_matrix_write(self.h, str(path).encode(), 0 if fmt == "mtx" else 1, int(precision)) != 0:
+            raise IOError(f"reference could not write {path}")
+
+    @classmethod
+    def read_text(cls, path):
+        """The reference's in() (spmat.h:1241-1255)."""
+        L = lib()
+        h = L.ref_matrix_read_text(str(path).encode())
+        if not h:
+            raise IOError(f"reference could not read {path}")
+        self = cls.__new__(cls)
+        self.h = h
+        self.rows, self.cols = int(L.ref_matrix_rows(h)), int(L.ref_matrix_cols(h))
+        self.nnz = int(L.ref_matrix_nnz(h))
         return self
 
     def csr(self):

@@ -20,6 +20,7 @@
 #include "parallel/exchange.h"
 
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <sstream>
 #include <string>
@@ -463,6 +464,27 @@ void ref_blockmat_saddle(void* hA, void* hB, const double* b, double* Sb, double
     DROPS::VectorCL bv(to_vec(b, S.num_cols()));
     from_vec(DROPS::VectorCL(S*bv), Sb);
     from_vec(DROPS::VectorCL(transp_mul(S, to_vec(b, S.num_rows()))), STb);
+}
+
+// Matrix text I/O of the reference itself (src/num/spmat.h:1213-1255): operator<< (MatrixMarket),
+// out() / in() (CSR dump).  Used to check drops_b200/matrix_io.py and the drop-in headers' I/O.
+int ref_matrix_write(void* h, const char* path, int format, int precision)
+{
+    const DROPS::MatrixCL& A = static_cast<RefMatrix*>(h)->A;
+    std::ofstream f(path);
+    if (!f) return -1;
+    if (format == 0) f << A;
+    else { f.precision(precision); DROPS::out(f, A); }
+    return f ? 0 : -1;
+}
+
+void* ref_matrix_read_text(const char* path)
+{
+    std::ifstream f(path);
+    if (!f) return 0;
+    RefMatrix* M = new RefMatrix;
+    DROPS::in(f, M->A);
+    return M;
 }
 
 } // extern "C"

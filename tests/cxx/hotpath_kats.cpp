@@ -14,6 +14,8 @@
 #include "parallel/exchange.h"
 
 #include <cstdio>
+#include <sstream>
+#include <string>
 #include <iostream>
 
 using namespace DROPS;
@@ -166,6 +168,31 @@ int main()
         VectorCL c(2);
         c[0] = 1.; c[1] = 2.;
         print_vec("B*c", VectorCL(B * c));
+    }
+    // --- text I/O: out/in round trip, MatrixMarket header of operator<< (spmat.h:1213-1255) -------------
+    {
+        MatrixCL A; VectorCL b;
+        fill_4x4(A, b);
+        std::stringstream ss;
+        ss.precision(17);
+        out(ss, A);
+        MatrixCL B;
+        in(ss, B);
+        double maxdiff = 0.;
+        for (size_t k = 0; k < A.num_nonzeros(); ++k) maxdiff = std::max(maxdiff, std::abs(A.val(k) - B.val(k)));
+        std::printf("IO out/in rows: %zu nnz: %zu maxdiff: %.3e\n", B.num_rows(), B.num_nonzeros(), maxdiff);
+        std::stringstream mm;
+        mm << A;
+        std::string l1, l2, l3;
+        std::getline(mm, l1); std::getline(mm, l2); std::getline(mm, l3);
+        std::printf("IO mtx header ok: %d dims: %s first: %s\n", int(l1 == "%%MatrixMarket matrix coordinate real general"),
+                    l2.c_str(), l3.c_str());
+        std::stringstream vs;
+        vs.precision(17);
+        out(vs, b);
+        VectorCL c;
+        in(vs, c);
+        std::printf("IO vec size: %zu diff: %.3e\n", c.size(), norm(VectorCL(b - c)));
     }
     // --- vector expressions (vectest.cpp) ------------------------------------------------------------
     {

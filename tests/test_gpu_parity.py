@@ -248,7 +248,7 @@ def test_fused_spmv_dot_matches_separate_dot(gpu, spc, threads, mode):
     finally:
         gpu.set_option("spmv.slices_per_cta", 16)
         gpu.set_option("spmv.threads", 128)
-        gpu.set_option("spmv.dotmode", 2)
+        gpu.set_option("spmv.dotmode", 0)
     A.spmv_dev(x, y2)
     assert np.array_equal(y.download(), y2.download())
     assert len(vals) == 1                                  # deterministic

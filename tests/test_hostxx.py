@@ -17,7 +17,7 @@ EXPECTED = os.path.join(ROOT, "tests", "golden", "hotpath_kats.expected.txt")
 
 KEYS = ("LANCZOS", "MINRES2", "MINRES4", "PMINRES4", "PMINRES4D", "TRANSP_MUL", "B*c", "VECEXPR", "VECOPS",
         "EXCHANGE", "LAPLACE", "PCGJAC", "PCGJAC08", "CG", "PCGJAC5", "JACAPPLY", "GMRESJAC", "GMRESJACR",
-        "VERSIONED", "hotpath_kats", "BICGSTAB2", "BICGSTAB4", "GCR2", "GCR4", "BICGSTABJAC", "GCRJAC")
+        "VERSIONED", "hotpath_kats", "BICGSTAB2", "BICGSTAB4", "GCR2", "GCR4", "BICGSTABJAC", "GCRJAC", "IO out", "IO mtx", "IO vec")
 
 
 def parse(text):
