@@ -51,6 +51,7 @@ SIGNATURES = {
     "drops_b200_matrix_create": (_i, [_sz, _sz, _sz, _szp, _szp, _dp, C.c_uint64, _vpp]),
     "drops_b200_matrix_create_device": (_i, [_sz, _sz, _sz, _vp, _vp, _vp, C.c_uint64, _vpp]),
     "drops_b200_matrix_update_values": (_i, [_vp, _dp, C.c_uint64]),
+    "drops_b200_matrix_lincomb": (_i, [_d, _vp, _d, _vp, C.c_uint64, _vpp]),
     "drops_b200_matrix_destroy": (_i, [_vp]),
     "drops_b200_matrix_info": (_i, [_vp, _szpp, _szpp, _szpp, C.POINTER(C.c_uint64), _szpp, _szpp]),
     "drops_b200_matrix_format": (_i, [_vp, _szpp, _szpp, _ip, _szpp]),
@@ -336,6 +337,13 @@ class Matrix:
         """Generate the brick system directly on the device."""
         h = C.c_void_p()
         check(lib().drops_b200_brick_matrix_device(int(fe), int(N), int(numbering), float(upper_scale), C.byref(h)))
+        return cls._wrap(h)
+
+    @classmethod
+    def lincomb(cls, a, A, b, B, version=1):
+        """a*A + b*B merged on the device (SparseMatBaseCL::LinComb)."""
+        h = C.c_void_p()
+        check(lib().drops_b200_matrix_lincomb(float(a), A.h, float(b), B.h, int(version), C.byref(h)))
         return cls._wrap(h)
 
     def info(self):

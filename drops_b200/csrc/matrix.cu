@@ -172,6 +172,42 @@ __global__ void k_sell_refill_values(long long nslices, const int64_t* __restric
         sval[base + (int64_t)j * 32 + lane] = j < len ? val[b + j] : 0.0;
 }
 
+// ---- LinComb: C = a*A + b*B, row-wise merge of two ascending column lists (spmat.h:1457-1551) ----
+__global__ void k_lincomb_count(long long rows, const int64_t* __restrict__ pa, const int32_t* __restrict__ ca,
+                                const int64_t* __restrict__ pb, const int32_t* __restrict__ cb, int64_t* __restrict__ len)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    int64_t ia = pa[r], ib = pb[r];
+    const int64_t ea = pa[r + 1], eb = pb[r + 1];
+    int64_t n = 0;
+    while (ia < ea && ib < eb) {
+        const int32_t x = ca[ia], y = cb[ib];
+        ia += (x <= y); ib += (y <= x); ++n;
+    }
+    len[r] = n + (ea - ia) + (eb - ib);
+}
+
+__global__ void k_lincomb_fill(long long rows, double a, const int64_t* __restrict__ pa, const int32_t* __restrict__ ca,
+                               const double* __restrict__ va, double b, const int64_t* __restrict__ pb,
+                               const int32_t* __restrict__ cb, const double* __restrict__ vb,
+                               const int64_t* __restrict__ pc, int32_t* __restrict__ cc, double* __restrict__ vc)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    int64_t ia = pa[r], ib = pb[r], i = pc[r];
+    const int64_t ea = pa[r + 1], eb = pb[r + 1];
+    while (ia < ea && ib < eb) {
+        const int32_t x = ca[ia], y = cb[ib];
+        if (y < x) { vc[i] = __dmul_rn(b, vb[ib]); cc[i] = y; ++ib; }                                  // :1524-1527
+        else if (x < y) { vc[i] = __dmul_rn(a, va[ia]); cc[i] = x; ++ia; }                             // :1528-1531
+        else { vc[i] = __dadd_rn(__dmul_rn(a, va[ia]), __dmul_rn(b, vb[ib])); cc[i] = y; ++ia; ++ib; } // :1532-1535
+        ++i;
+    }
+    for (; ia < ea; ++ia, ++i) { vc[i] = __dmul_rn(a, va[ia]); cc[i] = ca[ia]; }
+    for (; ib < eb; ++ib, ++i) { vc[i] = __dmul_rn(b, vb[ib]); cc[i] = cb[ib]; }
+}
+
 // ---- transpose ---------------------------------------------------------------------------
 __global__ void k_count_cols(long long nnz, const int32_t* __restrict__ col, unsigned long long* __restrict__ cnt)
 {
@@ -557,6 +593,52 @@ int drops_b200_matrix_create_device(size_t rows, size_t cols, size_t nnz, const 
         return cuda_fail(e, "device csr copy", __FILE__, __LINE__);
     }
     s = finalize_matrix(M);
+    if (s < 0) { drops_b200_matrix_destroy(M); return s; }
+    *out = M;
+    return 0;
+}
+
+int drops_b200_matrix_lincomb(double a, drops_b200_matrix_t A, double b, drops_b200_matrix_t B, uint64_t version,
+                              drops_b200_matrix_t* out)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(A != nullptr && B != nullptr && out != nullptr, "null argument");
+    DB_ARG(A->csr.rows == B->csr.rows && A->csr.cols == B->csr.cols, "LinComb: incompatible dimensions");
+    *out = nullptr;
+    cudaStream_t st = ctx().stream;
+    const size_t rows = A->csr.rows;
+    drops_b200_matrix_s* M = new drops_b200_matrix_s;
+    M->version = version;
+    CsrDev& C = M->csr;
+    C.rows = rows; C.cols = A->csr.cols;
+    int s = dev_alloc(&C.rowptr, rows + 1);
+    if (s < 0) { drops_b200_matrix_destroy(M); return s; }
+    cudaError_t e = cudaMemsetAsync(C.rowptr, 0, (rows + 1) * sizeof(int64_t), st);
+    if (e == cudaSuccess && rows > 0) {
+        k_lincomb_count<<<blocks_for((long long)rows, 256), 256, 0, st>>>((long long)rows, A->csr.rowptr, A->csr.col,
+                                                                         B->csr.rowptr, B->csr.col, C.rowptr);
+        count_launch();
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) { drops_b200_matrix_destroy(M); return cuda_fail(e, "lincomb count", __FILE__, __LINE__); }
+    s = exclusive_scan_i64(C.rowptr, rows + 1, st);
+    int64_t nnz = 0;
+    if (s == 0) {
+        e = cudaMemcpyAsync(&nnz, C.rowptr + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) s = cuda_fail(e, "lincomb nnz", __FILE__, __LINE__);
+    }
+    if (s == 0) { C.nnz = (size_t)nnz; s = dev_alloc(&C.col, C.nnz); }
+    if (s == 0) s = dev_alloc(&C.val, C.nnz);
+    if (s == 0 && rows > 0 && C.nnz > 0) {
+        k_lincomb_fill<<<blocks_for((long long)rows, 256), 256, 0, st>>>(
+            (long long)rows, a, A->csr.rowptr, A->csr.col, A->csr.val, b, B->csr.rowptr, B->csr.col, B->csr.val,
+            C.rowptr, C.col, C.val);
+        count_launch();
+        e = cudaGetLastError();
+        if (e != cudaSuccess) s = cuda_fail(e, "lincomb fill", __FILE__, __LINE__);
+    }
+    if (s == 0) s = finalize_matrix(M);
     if (s < 0) { drops_b200_matrix_destroy(M); return s; }
     *out = M;
     return 0;

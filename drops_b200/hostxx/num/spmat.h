@@ -331,6 +331,60 @@ class SparseMatBaseCL
     }
     void clear() { resize(0, 0, 0); }
 
+    /// *this = coeffA*A + coeffB*B, pattern = row-wise merge of the operands' ascending column lists
+    /// (src/num/spmat.h:1457-1551).  DROPS builds its time-step matrix this way right before every
+    /// solve (levelset/coupling.tpp:96, poisson/cdrdrops.cpp:112).  The host copy is merged as in the
+    /// reference; when both operands are resident on the GPU the device copy is merged THERE
+    /// (drops_b200_matrix_lincomb), so the next Solve needs no upload.
+    SparseMatBaseCL& LinComb(double coeffA, const SparseMatBaseCL& A, double coeffB, const SparseMatBaseCL& B)
+    {
+        if (A.num_rows() != B.num_rows() || A.num_cols() != B.num_cols())
+            throw DROPSErrCL("LinComb: incompatible dimensions");
+        const size_t rows = A.num_rows();
+        std::valarray<size_t> rb(rows + 1);
+        rb[0] = 0;
+        for (size_t row = 0; row < rows; ++row) {
+            const size_t *rA = A.GetFirstCol(row), *rB = B.GetFirstCol(row);
+            const size_t* const rAend = A.GetFirstCol(row + 1);
+            const size_t* const rBend = B.GetFirstCol(row + 1);
+            size_t i = 0;
+            for (; rA != rAend && rB != rBend; ++i)
+                if (*rB < *rA) ++rB;
+                else if (*rA < *rB) ++rA;
+                else { ++rA; ++rB; }
+            rb[row + 1] = rb[row] + i + (rAend - rA) + (rBend - rB);
+        }
+        const size_t nnz = rb[rows];
+        std::valarray<size_t> ci(nnz);
+        std::valarray<T> va(nnz);
+#pragma omp parallel for
+        for (long row = 0; row < (long)rows; ++row) {
+            size_t i = rb[row], iA = A.row_beg(row), iB = B.row_beg(row);
+            const size_t rAend = A.row_beg(row + 1), rBend = B.row_beg(row + 1);
+            for (; iA != rAend && iB != rBend; ++i)
+                if (B.col_ind(iB) < A.col_ind(iA)) { va[i] = coeffB * B._val[iB]; ci[i] = B._colind[iB++]; }
+                else if (A.col_ind(iA) < B.col_ind(iB)) { va[i] = coeffA * A._val[iA]; ci[i] = A._colind[iA++]; }
+                else { va[i] = coeffA * A._val[iA++] + coeffB * B._val[iB]; ci[i] = B._colind[iB++]; }
+            for (; iA < rAend; ++iA, ++i) { va[i] = coeffA * A._val[iA]; ci[i] = A._colind[iA]; }
+            for (; iB < rBend; ++iB, ++i) { va[i] = coeffB * B._val[iB]; ci[i] = B._colind[iB]; }
+        }
+        const bool on_device = &A != this && &B != this && A.dev_ && A.dev_version_ == A.version_ && B.dev_ &&
+                               B.dev_version_ == B.version_;
+        drops_b200_matrix_t merged = 0;
+        IncrementVersion();
+        ++pattern_version_;
+        if (on_device) b200::check(drops_b200_matrix_lincomb(coeffA, A.dev_, coeffB, B.dev_, version_, &merged));
+        _rows = rows; _cols = A.num_cols(); nnz_ = nnz;
+        _rowbeg.resize(rows + 1); _rowbeg = rb;
+        _colind.resize(nnz);      _colind = ci;
+        _val.resize(nnz);         _val = va;
+        drop_device();
+        if (merged) { dev_ = merged; dev_version_ = version_; dev_pattern_version_ = pattern_version_; }
+        return *this;
+    }
+    /// true when the device copy is current (no upload pending)
+    bool DeviceIsCurrent() const { return dev_ && dev_version_ == version_; }
+
     /// Writes the matrix in MatrixMarket coordinate format (src/num/spmat.h:1085-1089).
     SparseMatBaseCL& exportMTX(const std::string& path);
     VectorBaseCL<T> GetDiag() const

@@ -101,6 +101,12 @@ DROPS_B200_API int drops_b200_matrix_create_device(size_t rows, size_t cols, siz
                                                    drops_b200_matrix_t* out);
 /* New values on the unchanged pattern (operator*=, LinComb results with equal pattern). */
 DROPS_B200_API int drops_b200_matrix_update_values(drops_b200_matrix_t A, const double* val, uint64_t version);
+/* C = a*A + b*B on the device: SparseMatBaseCL::LinComb, num/spmat.h:1457-1551 (row-wise merge of the
+ * two ascending column lists; an entry present in both is a*A_ij + b*B_ij with both products rounded
+ * first).  DROPS calls it every time step right before the solve (levelset/coupling.tpp:96,
+ * poisson/cdrdrops.cpp:112); with the operands already resident nothing crosses PCIe. */
+DROPS_B200_API int drops_b200_matrix_lincomb(double a, drops_b200_matrix_t A, double b, drops_b200_matrix_t B,
+                                             uint64_t version, drops_b200_matrix_t* out);
 DROPS_B200_API int drops_b200_matrix_destroy(drops_b200_matrix_t A);
 DROPS_B200_API int drops_b200_matrix_info(drops_b200_matrix_t A, size_t* rows, size_t* cols, size_t* nnz,
                                           uint64_t* version, size_t* device_bytes, size_t* padded_nnz);

@@ -281,6 +281,40 @@ done:
 }
 
 /* ---------------------------------------------------------------------------------------
+ * LinComb -- num/spmat.h:1457-1551: C = coeffA*A + coeffB*B, pattern = row-wise merge of the two
+ * ascending column lists.  Two calls: with Ccol == NULL only Crow (row_beg of the result) is filled.
+ * ------------------------------------------------------------------------------------- */
+ORC_API void orc_lincomb(size_t rows, double coeffA, const double* Aval, const size_t* Arow, const size_t* Acol,
+                         double coeffB, const double* Bval, const size_t* Brow, const size_t* Bcol,
+                         size_t* Crow, size_t* Ccol, double* Cval)
+{
+    size_t row;
+    if (Ccol == NULL) {
+        Crow[0] = 0;
+        for (row = 0; row < rows; ++row) {                               /* :1487-1503 */
+            size_t i = 0, iA = Arow[row], iB = Brow[row];
+            const size_t eA = Arow[row + 1], eB = Brow[row + 1];
+            for (; iA != eA && iB != eB; ++i)
+                if (Bcol[iB] < Acol[iA]) ++iB;
+                else if (Acol[iA] < Bcol[iB]) ++iA;
+                else { ++iA; ++iB; }
+            Crow[row + 1] = Crow[row] + i + (eA - iA) + (eB - iB);
+        }
+        return;
+    }
+    for (row = 0; row < rows; ++row) {                                   /* :1515-1545 */
+        size_t i = Crow[row], iA = Arow[row], iB = Brow[row];
+        const size_t eA = Arow[row + 1], eB = Brow[row + 1];
+        for (; iA != eA && iB != eB; ++i)
+            if (Bcol[iB] < Acol[iA]) { Cval[i] = coeffB * Bval[iB]; Ccol[i] = Bcol[iB++]; }
+            else if (Acol[iA] < Bcol[iB]) { Cval[i] = coeffA * Aval[iA]; Ccol[i] = Acol[iA++]; }
+            else { Cval[i] = coeffA * Aval[iA++] + coeffB * Bval[iB]; Ccol[i] = Bcol[iB++]; }
+        for (; iA < eA; ++iA, ++i) { Cval[i] = coeffA * Aval[iA]; Ccol[i] = Acol[iA]; }
+        for (; iB < eB; ++iB, ++i) { Cval[i] = coeffB * Bval[iB]; Ccol[i] = Bcol[iB]; }
+    }
+}
+
+/* ---------------------------------------------------------------------------------------
  * BiCGStab -- num/krylovsolver.h:1189-1258 (BICGSTAB, serial).  Plain dot / norm
  * (std::inner_product, spmat.h:164-196), not the Kahan sums of the exchange class.
  * Returns 1 converged, 0 not converged, -1 breakdown (the reference prints a message and

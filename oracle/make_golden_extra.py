@@ -25,6 +25,40 @@ CASES = [("bicgstab_jac", lambda R, x0, b: R.bicgstab(x0, b, 400, 1e-10, True, 1
          ("gcr_jac_m4_trunc", lambda R, x0, b: R.gcr(x0, b, 4, 60, 1e-10, True, 1, 1.0))]
 
 
+def lincomb_fixture():
+    """SparseMatBaseCL::LinComb (spmat.h:1457-1551) by the compiled reference: the time-step matrix
+    L = (1/dt) E + theta H of levelset/coupling.tpp:95-97 in miniature -- a "mass" matrix whose pattern is a
+    strict subset of the stiffness pattern plus a few entries of its own, and the stiffness matrix."""
+    g = dict(np.load(os.path.join(GOLDEN, "brick_fe2_N4_num1_nonsym.npz")))
+    n = int(g["rows"])
+    rng = np.random.default_rng(7)
+    import scipy.sparse as sp
+    H = sp.csr_matrix((g["val"], g["colind"].astype(np.int64), g["rowbeg"].astype(np.int64)), shape=(n, n))
+    keep = rng.random(H.nnz) < 0.6
+    keep[g["colind"].astype(np.int64) == np.repeat(np.arange(n), np.diff(g["rowbeg"].astype(np.int64)))] = True
+    E = sp.csr_matrix((np.abs(H.data[keep]) * 0.01 + 0.1, H.indices[keep], np.r_[0, np.cumsum(np.add.reduceat(
+        keep.astype(np.int64), H.indptr[:-1]))]), shape=(n, n))
+    extra = sp.random(n, n, density=0.01, random_state=11, format="csr")
+    extra.data[:] = 0.37
+    E = (E + extra).tocsr()
+    E.sort_indices()
+    E.data[E.data == 0.0] = 0.25                              # keep every stored position nonzero
+    A = ref.RefMatrix(n, n, E.indptr, E.indices, E.data)
+    B = ref.RefMatrix(n, n, g["rowbeg"], g["colind"], g["val"])
+    out = {"rows": n, "A_rowbeg": E.indptr.astype(np.uint64), "A_colind": E.indices.astype(np.uint64), "A_val": E.data,
+           "B_rowbeg": g["rowbeg"], "B_colind": g["colind"], "B_val": g["val"], "x_in": g["x_in"], "b": g["b"]}
+    for tag, (a, b) in {"dt": (1.0 / 3e-4, 1.0), "neg": (0.7, -1.3), "zero": (0.0, 2.0)}.items():
+        Cm = ref.RefMatrix.lincomb(a, A, b, B)
+        rb, ci, va = Cm.csr()
+        out[f"{tag}_coef"] = np.array([a, b])
+        out[f"{tag}_rowbeg"], out[f"{tag}_colind"], out[f"{tag}_val"] = rb, ci, va
+        out[f"{tag}_y"] = Cm.spmv(g["x_in"])
+    c, it, res, x = ref.RefMatrix.lincomb(1.0 / 3e-4, A, 1.0, B).gmres_jacobi(np.zeros(n), g["b"], 50, 200, 1e-10, True, 1.0, True)
+    out["dt_gmres"] = np.array([c, it, res]); out["dt_gmres_x"] = x
+    np.savez_compressed(os.path.join(GOLDEN, "lincomb.npz"), **out)
+    print("lincomb: nnz A", E.nnz, "B", len(g["val"]), "C", len(out["dt_val"]), "gmres", out["dt_gmres"])
+
+
 def main():
     out = {}
     for path in sorted(glob.glob(os.path.join(GOLDEN, "brick_*.npz")) + glob.glob(os.path.join(GOLDEN, "random_spd*.npz"))):
@@ -48,6 +82,7 @@ def main():
         out[key] = np.array(r[:3], float)
         out[key + "_x"] = r[3]
     np.savez_compressed(os.path.join(GOLDEN, "krylov_extra.npz"), **out)
+    lincomb_fixture()
     for k in sorted(out):
         if not k.endswith("_x"):
             print(k, out[k])

@@ -51,6 +51,7 @@ def lib():
         "orc_pcg": (i, [sz] + csr + [i, d, _dp, _dp, ip, dpp, i, vp, i]),
         "orc_gmres": (i, [sz] + csr + [i, d, _dp, _dp, i, ip, dpp, i, i]),
         "orc_bicgstab": (i, [sz] + csr + [i, d, _dp, _dp, ip, dpp, i]),
+        "orc_lincomb": (None, [sz, d] + csr + [d] + csr + [_szp, C.c_void_p, C.c_void_p]),
         "orc_gcr": (i, [sz] + csr + [i, d, _dp, _dp, i, ip, dpp, i]),
         "orc_minres": (i, [sz] + csr + [i, i, d, _dp, _dp, ip, dpp, i]),
         "orc_lanczos_basis": (i, [sz] + csr + [_dp, i, _dp, _dp, _dp]),
@@ -239,3 +240,16 @@ def z_xpaypby2(x, a, y, b, y2):
     z = np.zeros(len(x))
     lib().orc_z_xpaypby2(len(x), z, _f64(x), float(a), _f64(y), float(b), _f64(y2))
     return z
+
+
+def lincomb(rows, a, A_csr, b, B_csr):
+    """a*A + b*B (SparseMatBaseCL::LinComb, spmat.h:1457-1551); *_csr = (rowbeg, colind, val) -> same triple."""
+    (ra, ca, va), (rb_, cb, vb) = [( _u64(t[0]), _u64(t[1]), _f64(t[2])) for t in (A_csr, B_csr)]
+    L = lib()
+    cr = np.zeros(rows + 1, np.uint64)
+    L.orc_lincomb(rows, float(a), va, ra, ca, float(b), vb, rb_, cb, cr, None, None)
+    nnz = int(cr[-1])
+    cc, cv = np.zeros(max(nnz, 1), np.uint64), np.zeros(max(nnz, 1))
+    L.orc_lincomb(rows, float(a), va, ra, ca, float(b), vb, rb_, cb, cr, cc.ctypes.data_as(C.c_void_p),
+                  cv.ctypes.data_as(C.c_void_p))
+    return cr, cc[:nnz], cv[:nnz]

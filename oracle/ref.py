@@ -68,6 +68,7 @@ def lib():
         "ref_bicgstab": (i, [vp, _dp, _dp, i, d, ip, dpp, i]),
         "ref_matrix_write": (i, [vp, C.c_char_p, i, i]),
         "ref_matrix_read_text": (vp, [C.c_char_p]),
+        "ref_matrix_lincomb": (vp, [d, vp, d, vp]),
         "ref_gcr": (i, [vp, _dp, _dp, i, d, i, ip, dpp, i]),
         "ref_minres": (i, [vp, _dp, _dp, ip, dpp, i]),
         "ref_pminres_jacobi": (i, [vp, _dp, _dp, d, ip, dpp, i]),
@@ -111,6 +112,15 @@ class RefMatrix:
         ti, tj, tv = _u64(ti), _u64(tj), _f64(tv)
         self.h = L.ref_matrix_build_triplets(self.rows, self.cols, int(tv.size), ti, tj, tv)
         self.nnz = int(L.ref_matrix_nnz(self.h))
+        return self
+
+    @classmethod
+    def lincomb(cls, a, A, b, B):
+        """SparseMatBaseCL::LinComb (spmat.h:1457-1551) run by the reference."""
+        L = lib()
+        self = cls.__new__(cls)
+        self.h = L.ref_matrix_lincomb(float(a), A.h, float(b), B.h)
+        self.rows, self.cols, self.nnz = A.rows, A.cols, int(L.ref_matrix_nnz(self.h))
         return self
 
     def write(self, path, fmt="mtx", precision=17):

@@ -487,4 +487,12 @@ void* ref_matrix_read_text(const char* path)
     return M;
 }
 
+// SparseMatBaseCL::LinComb (src/num/spmat.h:1457-1551): returns a new matrix handle a*A + b*B.
+void* ref_matrix_lincomb(double a, void* hA, double b, void* hB)
+{
+    RefMatrix* M = new RefMatrix;
+    M->A.LinComb(a, static_cast<RefMatrix*>(hA)->A, b, static_cast<RefMatrix*>(hB)->A);
+    return M;
+}
+
 } // extern "C"

@@ -282,6 +282,19 @@ int main()
             gsolver.Solve(G, x, bg, ex);
             std::printf("GCRJAC iterations: %d residual: %.3e error: %.3e\n", gsolver.GetIter(), gsolver.GetResid(),
                         norm(VectorCL(x - xs)) / norm(xs));
+            // time-step matrix L = c1*A + c2*G (LinComb, spmat.h:1457-1551): merged on the device when the
+            // operands are resident -- no upload before the solve
+            {
+                MatrixCL Lm;
+                const size_t v0 = Lm.Version();
+                Lm.LinComb(2.5, A, 1., G);
+                VectorCL bl(Lm * xs);
+                double md = 0.;
+                const VectorCL chk(2.5 * VectorCL(A * xs) + VectorCL(G * xs));
+                for (size_t i = 0; i < N; ++i) md = std::max(md, std::abs(bl[i] - chk[i]) / (1. + std::abs(chk[i])));
+                std::printf("LINCOMB nnz: %zu version bumped: %d maxreldiff: %.1e L(3,3): %.15e\n", Lm.num_nonzeros(),
+                            int(Lm.Version() > v0), md > 1e-13 ? md : 0., Lm(3, 3));
+            }
             // matrix modified in place: Version() changes, the product must follow
             G *= 2.;
             VectorCL b2(G * xs);

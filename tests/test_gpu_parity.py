@@ -453,6 +453,30 @@ def test_pcg_graph_replay_matches_eager(gpu, port):
         gpu.set_option("pcg.check_every", 16)
 
 
+def test_lincomb_on_device_matches_reference(gpu):
+    """drops_b200_matrix_lincomb against SparseMatBaseCL::LinComb run by the compiled reference
+    (tests/golden/lincomb.npz): merged pattern, values and the product bit-identical; the time-step
+    system L = E/dt + theta H then solves like the reference's."""
+    L = load_golden("lincomb.npz")
+    n = int(L["rows"])
+    A = gpu.Matrix(n, n, L["A_rowbeg"], L["A_colind"], L["A_val"])
+    B = gpu.Matrix(n, n, L["B_rowbeg"], L["B_colind"], L["B_val"])
+    for tag in ("dt", "neg", "zero"):
+        a, b = L[f"{tag}_coef"]
+        Cm = gpu.Matrix.lincomb(a, A, b, B, version=5)
+        rb, ci, va = Cm.download()
+        assert np.array_equal(rb, L[f"{tag}_rowbeg"]) and np.array_equal(ci, L[f"{tag}_colind"])
+        assert np.array_equal(va, L[f"{tag}_val"])
+        assert np.array_equal(Cm.spmv(L["x_in"]), L[f"{tag}_y"])
+        assert Cm.info()["version"] == 5
+    Cm = gpu.Matrix.lincomb(L["dt_coef"][0], A, L["dt_coef"][1], B)
+    out = Cm.gmres_jacobi(np.zeros(n), L["b"], 50, 200, 1e-10, True, 1.0, True)
+    assert out[0] == bool(L["dt_gmres"][0]) and abs(out[1] - int(L["dt_gmres"][1])) <= 1
+    assert rel(out[3], L["dt_gmres_x"]) <= 1e-8
+    with pytest.raises(gpu.DropsB200Error):
+        gpu.Matrix.lincomb(1.0, A, 1.0, gpu.Matrix(2, 2, [0, 1, 2], [0, 1], [1., 1.]))
+
+
 def test_matrix_value_update_tracks_version(gpu):
     g = load_golden("brick_fe2_N4_num1.npz")
     A = gmat(gpu, g)

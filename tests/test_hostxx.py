@@ -17,7 +17,7 @@ EXPECTED = os.path.join(ROOT, "tests", "golden", "hotpath_kats.expected.txt")
 
 KEYS = ("LANCZOS", "MINRES2", "MINRES4", "PMINRES4", "PMINRES4D", "TRANSP_MUL", "B*c", "VECEXPR", "VECOPS",
         "EXCHANGE", "LAPLACE", "PCGJAC", "PCGJAC08", "CG", "PCGJAC5", "JACAPPLY", "GMRESJAC", "GMRESJACR",
-        "VERSIONED", "hotpath_kats", "BICGSTAB2", "BICGSTAB4", "GCR2", "GCR4", "BICGSTABJAC", "GCRJAC", "IO out", "IO mtx", "IO vec")
+        "VERSIONED", "hotpath_kats", "BICGSTAB2", "BICGSTAB4", "GCR2", "GCR4", "BICGSTABJAC", "GCRJAC", "IO out", "IO mtx", "IO vec", "LINCOMB")
 
 
 def parse(text):
@@ -69,7 +69,8 @@ def test_dropin_binary_matches_reference_output(lib_built):
     assert not missing, missing
     # exact lines: host-side vector code and bit-identical device products
     for key in ("LANCZOS vectors", "TRANSP_MUL", "B*c", "VECEXPR maxdiff", "VECOPS dot", "EXCHANGE pardot",
-                "LAPLACE rows", "VERSIONED ratio", "JACAPPLY z7", "MINRES2 converged"):
+                "LAPLACE rows", "VERSIONED ratio", "JACAPPLY z7", "MINRES2 converged", "LINCOMB nnz", "IO out/in rows",
+                "IO mtx header ok", "IO vec size"):
         assert got[key] == exp[key], (key, got[key], exp[key])
     # solutions of the tiny systems
     for key in ("MINRES2 x", "MINRES4 x", "PMINRES4 x", "PMINRES4D x"):

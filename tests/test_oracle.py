@@ -231,3 +231,19 @@ def test_oracle_bicgstab_and_gcr_match_reference_fixtures(port):
         assert r[0] and r[1] == int(E[key][1]) and r[2] == E[key][2] and abs(r[2]) < 1e-10, key
         assert np.array_equal(r[3], E[key + "_x"]), key
     assert np.allclose(E["kat/gcr2_x"], [2., 1.]) and np.allclose(E["kat/gcr4_x"], [0.25, 0.5, 0.75, 1.0])
+
+
+def test_oracle_lincomb_matches_reference_fixture(port):
+    """SparseMatBaseCL::LinComb (spmat.h:1457-1551): pattern merge and values, bit-identical."""
+    L = load_golden("lincomb.npz")
+    n = int(L["rows"])
+    A = (L["A_rowbeg"], L["A_colind"], L["A_val"])
+    B = (L["B_rowbeg"], L["B_colind"], L["B_val"])
+    for tag in ("dt", "neg", "zero"):
+        a, b = L[f"{tag}_coef"]
+        rb, ci, va = port.lincomb(n, a, A, b, B)
+        assert np.array_equal(rb, L[f"{tag}_rowbeg"]) and np.array_equal(ci, L[f"{tag}_colind"])
+        assert np.array_equal(va, L[f"{tag}_val"])
+        P = port.PortMatrix(n, n, rb, ci, va)
+        assert np.array_equal(P.spmv(L["x_in"]), L[f"{tag}_y"])
+    assert len(L["dt_val"]) > max(len(A[2]), len(B[2]))        # the patterns really differ
