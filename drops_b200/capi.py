@@ -11,7 +11,8 @@ import numpy as np
 
 from . import _build
 
-PC_DUMMY, PC_JACOBI = 0, 1
+PC_DUMMY, PC_JACOBI, PC_CHEBYSHEV = 0, 1, 2
+OP_MUL, OP_TRANSP_MUL = 0, 1
 
 _lib = None
 
@@ -91,6 +92,20 @@ SIGNATURES = {
     "drops_b200_bicgstab_dev": (_i, [_vp, _vp, _vp, _i, _d, _ip, _dpp, _i, _ip]),
     "drops_b200_gcr": (_i, [_vp, _dp, _dp, _i, _d, _i, _ip, _dpp, _i]),
     "drops_b200_gcr_dev": (_i, [_vp, _vp, _vp, _i, _d, _i, _ip, _dpp, _i]),
+    "drops_b200_matrix_set_chebyshev": (_i, [_vp, _i, _d, _i, _d]),
+    "drops_b200_chebyshev_lambda_max": (_i, [_vp, _i, _dpp]),
+    "drops_b200_matrix_bbt_diag": (_i, [_vp, _dp]),
+    "drops_b200_precond_apply_dev": (_i, [_vp, _i, _d, _i, _vp, _vp]),
+    "drops_b200_pcg_general_dev": (_i, [_vp, _vp, _vp, _i, _d, _ip, _dpp, _i, _vp, _i]),
+    "drops_b200_pcgne": (_i, [_vp, _dp, _dp, _i, _d, _ip, _dpp, _i, _vp, _i]),
+    "drops_b200_pcgne_dev": (_i, [_vp, _vp, _vp, _i, _d, _ip, _dpp, _i, _vp, _i]),
+    "drops_b200_idrs": (_i, [_vp, _dp, _dp, _i, _d, _i, _d, _vp, _ip, _dpp, _i]),
+    "drops_b200_idrs_dev": (_i, [_vp, _vp, _vp, _i, _d, _i, _d, _vp, _ip, _dpp, _i]),
+    "drops_b200_block_dims": (_i, [_vp, _ip, _szpp, _szpp]),
+    "drops_b200_block_spmv": (_i, [_vp, _ip, _dp, _dp]),
+    "drops_b200_block_spmv_dev": (_i, [_vp, _ip, _vp, _vp]),
+    "drops_b200_composite_spmv": (_i, [_vp, _i, _vp, _i, _dp, _dp]),
+    "drops_b200_composite_spmv_dev": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "drops_b200_brick_sizes": (_i, [_i, _i, _szpp, _szpp]),
     "drops_b200_brick_csr_host": (_i, [_i, _i, _i, _d, _szp, _szp, _dp]),
     "drops_b200_brick_matrix_device": (_i, [_i, _i, _i, _d, _vpp]),
@@ -516,6 +531,96 @@ class Matrix:
         conv = check(lib().drops_b200_minres_dev(self.h, x.h, b.h, int(precond), int(pc), float(omega),
                                                  C.byref(it), C.byref(res), int(relative)))
         return bool(conv), it.value, res.value
+
+
+    # --- Chebyshev, PCGNE, IDR(s) ----------------------------------------
+    def set_chebyshev(self, normal_eq=False, lambda_scale=None, degree=3, ratio=30.0):
+        """Constructor arguments of ChebyshevPcCL (normal_eq False) / ChebyshevBBTPcCL (True)."""
+        if lambda_scale is None:
+            lambda_scale = 1.0 if normal_eq else 1.1
+        check(lib().drops_b200_matrix_set_chebyshev(self.h, int(normal_eq), float(lambda_scale), int(degree),
+                                                    float(ratio)))
+
+    def chebyshev_lambda_max(self, normal_eq=False):
+        r = C.c_double()
+        check(lib().drops_b200_chebyshev_lambda_max(self.h, int(normal_eq), C.byref(r)))
+        return r.value
+
+    def bbt_diag(self):
+        d = np.zeros(max(self.rows, 1))
+        check(lib().drops_b200_matrix_bbt_diag(self.h, d))
+        return d[:self.rows]
+
+    def precond_apply(self, b, pc, omega=1.0, normal_eq=False):
+        bv, xv = Vector.from_host(b), Vector(self.rows)
+        check(lib().drops_b200_precond_apply_dev(self.h, int(pc), float(omega), int(normal_eq), bv.h, xv.h))
+        return xv.download()
+
+    def pcg_general(self, x0, b, max_iter, tol, relative=False, pc=PC_JACOBI, omega=1.0, hist=False):
+        xv, bv = Vector.from_host(x0), Vector.from_host(b)
+        it, res = C.c_int(int(max_iter)), C.c_double(float(tol))
+        h, hargs = self._hist(max_iter, hist)
+        conv = lib().drops_b200_pcg_general_dev(self.h, xv.h, bv.h, int(pc), float(omega), C.byref(it), C.byref(res),
+                                                int(relative), *hargs)
+        return self._finish(conv, it, res, xv.download(), h, hist)
+
+    def pcgne(self, u0, b, max_iter, tol, relative=False, pc=PC_DUMMY, omega=1.0, hist=False):
+        u = _f64(u0).copy()
+        it, res = C.c_int(int(max_iter)), C.c_double(float(tol))
+        h, hargs = self._hist(max_iter, hist)
+        conv = lib().drops_b200_pcgne(self.h, u, _f64(b), int(pc), float(omega), C.byref(it), C.byref(res),
+                                      int(relative), *hargs)
+        return self._finish(conv, it, res, u, h, hist)
+
+    def idrs(self, x0, b, max_iter, tol, shadow=None, relative=False, s=4, omega_bound=0.7, pc=PC_JACOBI, omega=1.0):
+        """(ret, iters, resid, x) with the reference's return convention (include/drops_b200.h)."""
+        x = _f64(x0).copy()
+        sp_ = None
+        if shadow is not None:
+            shadow = _f64(shadow).reshape(-1)
+            assert shadow.size == s * self.rows
+            sp_ = shadow.ctypes.data_as(C.c_void_p)
+        it, res = C.c_int(int(max_iter)), C.c_double(float(tol))
+        ret = check(lib().drops_b200_idrs(self.h, x, _f64(b), int(pc), float(omega), int(s), float(omega_bound), sp_,
+                                          C.byref(it), C.byref(res), int(relative)))
+        return ret, it.value, res.value, x
+
+
+def _block_args(blocks, ops):
+    hb = (C.c_void_p * 4)(*[b.h if b is not None else None for b in blocks])
+    return C.cast(hb, C.c_void_p), (C.c_int * 4)(*[int(o) for o in ops]), hb
+
+
+def block_dims(blocks, ops):
+    r, c = C.c_size_t(), C.c_size_t()
+    hb, ob, _keep = _block_args(blocks, ops)
+    check(lib().drops_b200_block_dims(hb, ob, C.byref(r), C.byref(c)))
+    return r.value, c.value
+
+
+def block_spmv(blocks, ops, x, transposed=False):
+    """BlockMatrixBaseCL * x; blocks = [A, B, C, D] (Matrix or None), ops OP_MUL / OP_TRANSP_MUL.
+    transposed: transp_mul(S, x) = GetTranspose() * x (spblockmat.h:194-201)."""
+    if transposed:
+        blocks = [blocks[0], blocks[2], blocks[1], blocks[3]]
+        ops = [1 - ops[0], 1 - ops[2], 1 - ops[1], 1 - ops[3]]
+    rows, cols = block_dims(blocks, ops)
+    x = _f64(x)
+    assert x.size == cols
+    y = np.zeros(max(rows, 1))
+    hb, ob, _keep = _block_args(blocks, ops)
+    check(lib().drops_b200_block_spmv(hb, ob, _nonempty(x, np.float64), y))
+    return y[:rows]
+
+
+def composite_spmv(A0, op0, A1, op1, x, transposed=False):
+    """CompositeMatrixBaseCL * x = op1(A1) * (op0(A0) * x); transposed: GetTranspose() * x (spblockmat.h:364-370)."""
+    if transposed:
+        A0, op0, A1, op1 = A1, 1 - op1, A0, 1 - op0
+    ny = A1.rows if op1 == 0 else A1.cols
+    y = np.zeros(max(ny, 1))
+    check(lib().drops_b200_composite_spmv(A0.h, int(op0), A1.h, int(op1), _nonempty(_f64(x), np.float64), y))
+    return y[:ny]
 
 
 # --- synthetic brick systems (host side: no GPU needed) -----------------------------------------

@@ -348,6 +348,17 @@ struct drops_b200_matrix_s {
     cudaGraphExec_t pcg_graph = nullptr;
     struct { const void* x; const void* b; int chunk; int cg; unsigned long long epoch; } pcg_graph_key = {nullptr, nullptr, 0, 0, 0};
     long long pcg_graph_launches = 0;  // kernels inside the captured chunk
+    // ChebyshevPcCL [0] / ChebyshevBBTPcCL [1] (num/precond.h:1463-1567): constructor arguments,
+    // lambda_max cached like SetDiag does (keyed on the values epoch instead of Version())
+    double cheb_scale[2] = {1.1, 1.0};
+    int cheb_degree[2] = {3, 3};
+    double cheb_ratio[2] = {30.0, 30.0};
+    double cheb_lambda[2] = {0.0, 0.0};
+    double cheb_lambda_scale[2] = {0.0, 0.0};
+    uint64_t cheb_lambda_epoch[2] = {0, 0};
+    double* bbt_diag = nullptr;      // diag(A A^T), BBTDiag num/precond.h:56-75
+    uint64_t bbt_epoch = 0;
+    uint64_t values_epoch = 1;       // bumped whenever the stored values change
 };
 
 namespace db200 {

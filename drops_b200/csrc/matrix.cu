@@ -655,6 +655,7 @@ int drops_b200_matrix_update_values(drops_b200_matrix_t M, const double* val, ui
     DB_CHECK(extract_diag(M));
     drop_transpose(M);
     M->version = version;
+    ++M->values_epoch;
     DB_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
@@ -665,7 +666,7 @@ int drops_b200_matrix_destroy(drops_b200_matrix_t M)
     if (ctx().inited) cudaStreamSynchronize(ctx().stream);
     free_csr(M->csr); free_sell(M->sell);
     free_csr(M->csr_t); free_sell(M->sell_t);
-    dev_free(M->diag); dev_free(M->diag_missing);
+    dev_free(M->diag); dev_free(M->diag_missing); dev_free(M->bbt_diag);
     for (double* w : M->work) dev_free(w);
     dev_free(M->bridge[0]); dev_free(M->bridge[1]);
     dev_free(M->d_scalars); dev_free(M->d_hist); dev_free(M->d_small);

@@ -366,6 +366,111 @@ int pcg_direction(size_t n, double* p, const double* r, const double* d, SolverS
 }
 
 // ------------------------------------------------------------------------------------------
+// PCG with an external preconditioner, Chebyshev, IDR(s) helpers
+// ------------------------------------------------------------------------------------------
+struct OpPcgSetRho {
+    const double* z; const double* r; SolverScalars* S;
+    __device__ bool begin() { return true; }
+    __device__ void elem(size_t i, dd* acc) { acc[0] = dd_add_prod(acc[0], z[i], r[i]); }
+    __device__ void finish(const dd* acc) { S->rho = dd_round(acc[0]); }
+};
+int pcg_set_rho(size_t n, const double* z, const double* r, SolverScalars* S)
+{
+    return launch_stream<1>(n, OpPcgSetRho{z, r, S}, "pcg.rho");
+}
+
+struct OpPcgDirectionZ {
+    double* p; const double* z; SolverScalars* S; double beta;
+    __device__ bool begin()
+    {
+        if (S->done) return false;
+        beta = dvd(S->rho, S->rho_1);
+        return true;
+    }
+    __device__ void elem(size_t i, dd*) { p[i] = add(z[i], mul(beta, p[i])); }
+    __device__ void finish(const dd*) {}
+};
+int pcg_direction_z(size_t n, double* p, const double* z, SolverScalars* S)
+{
+    return launch_stream<0>(n, OpPcgDirectionZ{p, z, S, 0.0}, "pcg.direction");
+}
+
+struct OpChebFirst {
+    double* W; double* x; const double* res; const double* d; double oot;
+    __device__ bool begin() { return true; }
+    __device__ void elem(size_t i, dd*)
+    {
+        const double w = mul(mul(dvd(1.0, d[i]), res[i]), oot);
+        W[i] = w; x[i] = w;
+    }
+    __device__ void finish(const dd*) {}
+};
+int cheb_first(size_t n, double* W, double* x, const double* res, const double* d, double one_over_theta)
+{
+    return launch_stream<0>(n, OpChebFirst{W, x, res, d, one_over_theta}, "cheb");
+}
+
+struct OpChebStep {
+    double* W; double* x; const double* res; const double* d; double dt1, dt2;
+    __device__ bool begin() { return true; }
+    __device__ void elem(size_t i, dd*)
+    {
+        const double w = add(mul(W[i], dt1), mul(mul(dt2, dvd(1.0, d[i])), res[i]));
+        W[i] = w;
+        x[i] = add(x[i], w);
+    }
+    __device__ void finish(const dd*) {}
+};
+int cheb_step(size_t n, double* W, double* x, const double* res, const double* d, double dt1, double dt2)
+{
+    return launch_stream<0>(n, OpChebStep{W, x, res, d, dt1, dt2}, "cheb");
+}
+
+struct OpAxpby {
+    double a; double* y; double b; const double* x;
+    __device__ bool begin() { return true; }
+    __device__ void elem(size_t i, dd*) { y[i] = add(mul(a, y[i]), mul(b, x[i])); }
+    __device__ void finish(const dd*) {}
+};
+int vec_axpby(size_t n, double a, double* y, double b, const double* x)
+{
+    return launch_stream<0>(n, OpAxpby{a, y, b, x}, "vec");
+}
+
+template <int K>
+struct OpMultiDot {
+    const double* x; const double* v[K]; double* out;
+    __device__ bool begin() { return true; }
+    __device__ void elem(size_t i, dd* acc)
+    {
+        const double xi = x[i];
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc[j] = dd_add_prod(acc[j], v[j][i], xi);
+    }
+    __device__ void finish(const dd* acc)
+    {
+#pragma unroll
+        for (int j = 0; j < K; ++j) out[j] = dd_round(acc[j]);
+    }
+};
+int multi_dot(size_t n, const double* x, const double* const* h_vptrs, int k, double* d_out)
+{
+    for (int j0 = 0; j0 < k; j0 += 4) {
+        const int m = k - j0 < 4 ? k - j0 : 4;
+        const double* const* v = h_vptrs + j0;
+        int s = 0;
+        switch (m) {
+            case 1: s = launch_stream<1>(n, OpMultiDot<1>{x, {v[0]}, d_out + j0}, "vec"); break;
+            case 2: s = launch_stream<2>(n, OpMultiDot<2>{x, {v[0], v[1]}, d_out + j0}, "vec"); break;
+            case 3: s = launch_stream<3>(n, OpMultiDot<3>{x, {v[0], v[1], v[2]}, d_out + j0}, "vec"); break;
+            default: s = launch_stream<4>(n, OpMultiDot<4>{x, {v[0], v[1], v[2], v[3]}, d_out + j0}, "vec"); break;
+        }
+        if (s < 0) return s;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // CG (sign convention of the reference: r = A x - b, d = -r)
 // ------------------------------------------------------------------------------------------
 struct OpCgSetup {

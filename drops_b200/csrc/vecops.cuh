@@ -120,6 +120,25 @@ int gcr_scale(size_t n, double* vn, double* sn, double* vnacc, const double* rac
 int gcr_update(size_t n, double* x, double* r, double* racc, const double* sn, const double* vn, const double* vnacc,
                const double* d_gamma, double* d_rr);
 
+// ---- generic-preconditioner PCG (PCG / PCGNE with a preconditioner that is not an elementwise
+//      formula: ChebyshevPcCL) ----------------------------------------------------------------------
+// S->rho = z.r   (run after pcg_setup / pcg_update executed with pc = DUMMY, which left rho = r.r)
+int pcg_set_rho(size_t n, const double* z, const double* r, SolverScalars* S);
+// p = z + (rho/rho_1) p                                               krylovsolver.h:173-174, :246
+int pcg_direction_z(size_t n, double* p, const double* z, SolverScalars* S);
+
+// ---- Chebyshev polynomial preconditioner (num/precond.h:1359-1408) --------------------------------
+// W = ((1/d)*res)*one_over_theta;  x = W                                       precond.h:1383-1389
+int cheb_first(size_t n, double* W, double* x, const double* res, const double* d, double one_over_theta);
+// W = W*dt1 + ((dt2*(1/d))*res);  x += W                                       precond.h:1402-1405
+int cheb_step(size_t n, double* W, double* x, const double* res, const double* d, double dt1, double dt2);
+// y = (a*y) + (b*x)                                          IDR(s): U[k] = c[0]*U[k] + omega*v  :1630
+int vec_axpby(size_t n, double a, double* y, double b, const double* x);
+// d_out[j] = dot(v_j, x), j < k <= 4: one pass over x for k reductions
+int multi_dot(size_t n, const double* x, const double* const* h_vptrs, int k, double* d_out);
+// x *= (1/s) style helpers are vec_div_scalar; d_out[0] = |t|^2, d_out[1] = t.r       IDR(s) :1676
+// (bicg_ts(n, t, r, d_out) gives d_out[0] = t.r, d_out[1] = t.t)
+
 // r = b - t  style helpers
 int vec_sub(size_t n, double* out, const double* a, const double* b);            // out = a - b
 

@@ -48,6 +48,11 @@ extern "C" {
 /* preconditioner selector: the PC template argument of the reference solvers */
 #define DROPS_B200_PC_DUMMY      0   /* DummyPcCL, num/precond.h:1032-1065: x = b               */
 #define DROPS_B200_PC_JACOBI     1   /* JACPcCL,   num/precond.h:874 / :1155-1188: x = omega*b/a_ii */
+#define DROPS_B200_PC_CHEBYSHEV  2   /* ChebyshevPcCL num/precond.h:1463-1529 (PCG); ChebyshevBBTPcCL :1531-1567
+                                      * (PCGNE).  Parameters: drops_b200_matrix_set_chebyshev.              */
+/* BlockMatrixOperationT of num/spblockmat.h:40 */
+#define DROPS_B200_OP_MUL        0
+#define DROPS_B200_OP_TRANSP_MUL 1
 
 typedef struct drops_b200_matrix_s* drops_b200_matrix_t;
 typedef struct drops_b200_vector_s* drops_b200_vector_t;
@@ -215,6 +220,64 @@ DROPS_B200_API int drops_b200_gcr(drops_b200_matrix_t A, double* x, const double
                                   int truncate, int* max_iter, double* tol, int relative);
 DROPS_B200_API int drops_b200_gcr_dev(drops_b200_matrix_t A, drops_b200_vector_t x, drops_b200_vector_t b,
                                       int pc, double omega, int truncate, int* max_iter, double* tol, int relative);
+
+/* ---- the callers next to the core path --------------------------------
+ * Chebyshev polynomial preconditioner: ChebyshevPcCL(lambda_scale = 1.1, degree = 3, ratio = 30) for
+ * a square A (num/precond.h:1474) and ChebyshevBBTPcCL(lambda_scale = 1, degree = 3, ratio = 30) for
+ * the normal equations A A^T (:1533); normal_eq selects which parameter set is changed.  The
+ * defaults are the reference's constructor defaults. */
+DROPS_B200_API int drops_b200_matrix_set_chebyshev(drops_b200_matrix_t A, int normal_eq, double lambda_scale,
+                                                   int degree, double eig_ratio);
+/* What SetDiag computes (num/precond.h:1481-1491, :1537-1553): lambda_scale * MaxEigenvalueScaledMatrix
+ * (:1080-1096, 10 power iterations on D^-1 A or D^-1 A A^T with D = BBTDiag).  Cached on the handle. */
+DROPS_B200_API int drops_b200_chebyshev_lambda_max(drops_b200_matrix_t A, int normal_eq, double* lambda_max);
+/* BBTDiag, num/precond.h:56-75: diag(A A^T). */
+DROPS_B200_API int drops_b200_matrix_bbt_diag(drops_b200_matrix_t A, double* diag);
+/* x = M^-1 b: PC::Apply(A, x, b, ex) (normal_eq = 0) or PC::Apply(A, x, b, rowex, colex) on A A^T
+ * (normal_eq = 1; Jacobi then divides by BBTDiag).  x must not alias b for Chebyshev. */
+DROPS_B200_API int drops_b200_precond_apply_dev(drops_b200_matrix_t A, int pc, double omega, int normal_eq,
+                                                drops_b200_vector_t b, drops_b200_vector_t x);
+/* PCG through the generic-preconditioner driver (what drops_b200_pcg uses for PC_CHEBYSHEV; with
+ * PC_DUMMY / PC_JACOBI it gives the results of drops_b200_pcg_dev without CUDA graphs). */
+DROPS_B200_API int drops_b200_pcg_general_dev(drops_b200_matrix_t A, drops_b200_vector_t x, drops_b200_vector_t b,
+                                              int pc, double omega, int* max_iter, double* tol, int relative,
+                                              double* hist, int hist_cap);
+/* pcgne : PCGNE, num/krylovsolver.h:199-252 (PCGNESolverCL<PC>::Solve :1851-1864): CG on A A^T u = b
+ *         for a rectangular A (rows x cols), u and b have rows entries.  Contract as drops_b200_pcg. */
+DROPS_B200_API int drops_b200_pcgne(drops_b200_matrix_t A, double* u, const double* b, int pc, double omega,
+                                    int* max_iter, double* tol, int relative, double* hist, int hist_cap);
+DROPS_B200_API int drops_b200_pcgne_dev(drops_b200_matrix_t A, drops_b200_vector_t u, drops_b200_vector_t b,
+                                        int pc, double omega, int* max_iter, double* tol, int relative,
+                                        double* hist, int hist_cap);
+/* idrs  : IDRS, num/krylovsolver.h:1579-1698 (IDRsSolverCL<PC>::Solve :2112-2126).  shadow: the s
+ *         vectors P BEFORE orthonormalisation (host, s*n doubles, vector i at shadow + i*n), or NULL to
+ *         draw them as the reference does (srand(time(0)), 2*rand()/RAND_MAX - 1).  Outputs follow the
+ *         reference literally: *tol OUT is the ABSOLUTE residual norm, *max_iter OUT the iteration
+ *         count in every case, and the return value is 0 when tol_in > |r|/normb at exit (:1689-1693,
+ *         i.e. on convergence inside the loop) and 1 otherwise.  A zero pivot / omega (DROPSErrCL in
+ *         the reference) returns DROPS_B200_E_ARG. */
+DROPS_B200_API int drops_b200_idrs(drops_b200_matrix_t A, double* x, const double* b, int pc, double omega, int s,
+                                   double omega_bound, const double* shadow, int* max_iter, double* tol,
+                                   int relative);
+DROPS_B200_API int drops_b200_idrs_dev(drops_b200_matrix_t A, drops_b200_vector_t x, drops_b200_vector_t b, int pc,
+                                       double omega, int s, double omega_bound, const double* shadow,
+                                       int* max_iter, double* tol, int relative);
+/* BlockMatrixBaseCL operator* (num/spblockmat.h:225-267): blocks[4] = {A, B, C, D} of ( A B ; C D ),
+ * any of them may be NULL, ops[i] = DROPS_B200_OP_MUL / _TRANSP_MUL says how block i is applied.
+ * r0 = op(A) x0 [+ op(B) x1], r1 = op(C) x0 [+ op(D) x1], each "+=" a rounded elementwise add as in
+ * the reference.  transp_mul(BlockMatrix, x) (:269-273) is the same call on {A, C, B, D} with the
+ * operations flipped.  block_dims: num_rows() / num_cols() (:112-190). */
+DROPS_B200_API int drops_b200_block_dims(const drops_b200_matrix_t blocks[4], const int ops[4], size_t* rows,
+                                         size_t* cols);
+DROPS_B200_API int drops_b200_block_spmv(const drops_b200_matrix_t blocks[4], const int ops[4], const double* x,
+                                         double* y);
+DROPS_B200_API int drops_b200_block_spmv_dev(const drops_b200_matrix_t blocks[4], const int ops[4],
+                                             drops_b200_vector_t x, drops_b200_vector_t y);
+/* CompositeMatrixBaseCL operator* (num/spblockmat.h:376-397): y = op1(A1) * (op0(A0) * x). */
+DROPS_B200_API int drops_b200_composite_spmv(drops_b200_matrix_t A0, int op0, drops_b200_matrix_t A1, int op1,
+                                             const double* x, double* y);
+DROPS_B200_API int drops_b200_composite_spmv_dev(drops_b200_matrix_t A0, int op0, drops_b200_matrix_t A1, int op1,
+                                                 drops_b200_vector_t x, drops_b200_vector_t y);
 
 /* ---- synthetic brick systems ---------------------------------------
  * Uniform Kuhn brick (BrickBuilderCL, geom/builder.cpp:99-180: 6 tetrahedra per cell sharing the

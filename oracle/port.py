@@ -19,8 +19,8 @@ _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "drops_oracle.c")
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("drops_oracle.c", "drops_oracle_ext.c")]
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "port"], stdout=subprocess.DEVNULL)
 
 
@@ -55,6 +55,13 @@ def lib():
         "orc_gcr": (i, [sz] + csr + [i, d, _dp, _dp, i, ip, dpp, i]),
         "orc_minres": (i, [sz] + csr + [i, i, d, _dp, _dp, ip, dpp, i]),
         "orc_lanczos_basis": (i, [sz] + csr + [_dp, i, _dp, _dp, _dp]),
+        # drops_oracle_ext.c
+        "orc_bbt_diag": (None, [sz, _dp, _szp, _dp]),
+        "orc_max_eig_scaled": (d, [sz, sz] + csr + [i, _dp, i]),
+        "orc_chebyshev": (None, [sz, sz] + csr + [i, _dp, _dp, _dp, i, d, d]),
+        "orc_pcg_ext": (i, [sz, sz] + csr + [i, i, d, d, i, d, _dp, _dp, ip, dpp, i, vp, i, dpp]),
+        "orc_idrs": (i, [sz] + csr + [i, d, i, d, _dp, _dp, _dp, ip, dpp, i]),
+        "orc_block_mul": (None, [vp, vp, vp, _szp, _szp, C.POINTER(C.c_int), _szp, _szp, _dp, _dp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -192,6 +199,51 @@ class PortMatrix:
     def pminres_dummy(self, x0, b, max_iter, tol, relative=False):
         return self._minres(1, 0, 1.0, x0, b, max_iter, tol, relative)
 
+    # --- drops_oracle_ext.c: PCGNE, Chebyshev, IDR(s) ------------------------------------------
+    def bbt_diag(self):
+        d = np.zeros(self.rows)
+        lib().orc_bbt_diag(self.rows, self.val, self.rowbeg, d)
+        return d
+
+    def max_eig_scaled(self, D, ne=False, iters=10):
+        return lib().orc_max_eig_scaled(self.rows, self.cols, *self._csr, int(ne), _f64(D), int(iters))
+
+    def chebyshev_apply(self, b, ne=False, scale=None, degree=3, ratio=30.0):
+        """(x, lambda_max): SetDiag + Apply of ChebyshevPcCL (ne False) / ChebyshevBBTPcCL (ne True)."""
+        scale = (1.0 if ne else 1.1) if scale is None else scale
+        D = self.bbt_diag() if ne else self.diag()
+        lmax = scale * self.max_eig_scaled(D, ne)
+        x = np.zeros(self.rows)
+        lib().orc_chebyshev(self.rows, self.cols, *self._csr, int(ne), x, _f64(b), D, int(degree), float(lmax), float(ratio))
+        return x, lmax
+
+    def _pcg_ext(self, ne, pc, omega, scale, degree, ratio, x0, b, max_iter, tol, relative, hist):
+        x = _f64(x0).copy()
+        it, res, lam = C.c_int(int(max_iter)), C.c_double(float(tol)), C.c_double(0.0)
+        h, hargs = self._hist(max_iter, hist)
+        conv = lib().orc_pcg_ext(self.rows, self.cols, *self._csr, int(ne), int(pc), float(omega), float(scale),
+                                 int(degree), float(ratio), x, _f64(b), C.byref(it), C.byref(res), int(relative),
+                                 *hargs, C.byref(lam))
+        out = (bool(conv), it.value, res.value, x)
+        return out + (h,) if hist else out
+
+    def pcg_chebyshev(self, x0, b, max_iter, tol, relative=False, scale=1.1, degree=3, ratio=30.0, hist=False):
+        return self._pcg_ext(0, 2, 1.0, scale, degree, ratio, x0, b, max_iter, tol, relative, hist)
+
+    def pcgne(self, u0, b, max_iter, tol, relative=False, pc=0, omega=1.0, scale=1.0, degree=3, ratio=30.0, hist=False):
+        """pc 0 identity, 1 Jacobi on BBTDiag, 2 ChebyshevBBTPcCL."""
+        return self._pcg_ext(1, pc, omega, scale, degree, ratio, u0, b, max_iter, tol, relative, hist)
+
+    def idrs(self, x0, b, max_iter, tol, P, relative=False, s=4, omega_bound=0.7, pc=1, omega=1.0):
+        """(ret, iters, resid, x); ret is the reference's return value (see krylovsolver.h:1689-1696), -1 = it threw."""
+        x = _f64(x0).copy()
+        P = _f64(P).reshape(-1)
+        assert P.size == s * self.rows
+        it, res = C.c_int(int(max_iter)), C.c_double(float(tol))
+        ret = lib().orc_idrs(self.rows, *self._csr, int(pc), float(omega), int(s), float(omega_bound), P, x, _f64(b),
+                             C.byref(it), C.byref(res), int(relative))
+        return ret, it.value, res.value, x
+
     def lanczos_basis(self, r0, max_vecs=8):
         n = self.rows
         Q = np.zeros((max_vecs, n))
@@ -253,3 +305,54 @@ def lincomb(rows, a, A_csr, b, B_csr):
     L.orc_lincomb(rows, float(a), va, ra, ca, float(b), vb, rb_, cb, cr, cc.ctypes.data_as(C.c_void_p),
                   cv.ctypes.data_as(C.c_void_p))
     return cr, cc[:nnz], cv[:nnz]
+
+
+def block_dims(blocks, ops):
+    """num_rows()/num_cols() bookkeeping of BlockMatrixBaseCL (spblockmat.h:112-190): per block row / column."""
+    def orows(b, o):
+        return b.rows if o == 0 else b.cols
+
+    def ocols(b, o):
+        return b.cols if o == 0 else b.rows
+    nr = [None, None]
+    nc = [None, None]
+    for br in range(2):
+        for b in (2 * br, 2 * br + 1):
+            if blocks[b] is not None and nr[br] is None:
+                nr[br] = orows(blocks[b], ops[b])
+    for bc in range(2):
+        for b in (bc, bc + 2):
+            if blocks[b] is not None and nc[bc] is None:
+                nc[bc] = ocols(blocks[b], ops[b])
+    return nr, nc
+
+
+def block_mul(blocks, ops, x, transposed=False):
+    """BlockMatrixBaseCL * x (spblockmat.h:225-267); blocks = [A, B, C, D] PortMatrix or None, ops 0 MUL / 1 TRANSP_MUL.
+    transposed: transp_mul = GetTranspose()*x (:194-201, :269-273)."""
+    if transposed:
+        blocks = [blocks[0], blocks[2], blocks[1], blocks[3]]
+        ops = [1 - ops[0], 1 - ops[2], 1 - ops[1], 1 - ops[3]]
+    nr, nc = block_dims(blocks, ops)
+    PD, PS = C.POINTER(C.c_double), C.POINTER(C.c_size_t)
+    val, row, col = (PD * 4)(), (PS * 4)(), (PS * 4)()
+    brows, bcols = np.zeros(4, np.uint64), np.zeros(4, np.uint64)
+    for k, b in enumerate(blocks):
+        if b is None:
+            continue
+        val[k] = b.val.ctypes.data_as(PD)
+        row[k] = b.rowbeg.ctypes.data_as(PS)
+        col[k] = b.colind.ctypes.data_as(PS)
+        brows[k], bcols[k] = b.rows, b.cols
+    y = np.zeros(sum(nr))
+    lib().orc_block_mul(C.cast(val, C.c_void_p), C.cast(row, C.c_void_p), C.cast(col, C.c_void_p), brows, bcols,
+                        (C.c_int * 4)(*ops), np.array(nr, np.uint64), np.array(nc, np.uint64), _f64(x), y)
+    return y
+
+
+def composite_mul(A0, op0, A1, op1, x, transposed=False):
+    """CompositeMatrixBaseCL * x = op1(A1) * (op0(A0) * x) (spblockmat.h:376-397); transposed: GetTranspose()*x."""
+    if transposed:
+        A0, op0, A1, op1 = A1, 1 - op1, A0, 1 - op0
+    t = A0.spmv(x) if op0 == 0 else A0.spmv_transpose(x)
+    return A1.spmv(t) if op1 == 0 else A1.spmv_transpose(t)

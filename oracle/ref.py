@@ -75,6 +75,16 @@ def lib():
         "ref_pminres_dummy": (i, [vp, _dp, _dp, ip, dpp, i]),
         "ref_lanczos_basis": (i, [vp, _dp, i, _dp, _dp, _dp]),
         "ref_blockmat_saddle": (None, [vp, vp, _dp, _dp, _dp]),
+        "ref_bbt_diag": (None, [vp, _dp]),
+        "ref_max_eig_scaled": (d, [vp, i, _dp, i]),
+        "ref_chebyshev_apply": (d, [vp, i, d, i, d, _dp, _dp]),
+        "ref_pcg_chebyshev": (i, [vp, _dp, _dp, d, i, d, ip, dpp, i]),
+        "ref_pcgne": (i, [vp, _dp, _dp, i, d, d, i, d, ip, dpp, i]),
+        "ref_idrs": (i, [vp, _dp, _dp, i, d, i, d, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS"), sz,
+                         ip, dpp, i]),
+        "ref_block_dims": (None, [vp, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+        "ref_block_mul": (None, [vp, C.POINTER(C.c_int), i, _dp, _dp]),
+        "ref_composite_mul": (None, [vp, i, vp, i, i, _dp, _dp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -245,6 +255,45 @@ class RefMatrix:
         return self._solve(lib().ref_pminres_dummy, x0, b, max_iter, tol,
                            post=(int(relative),), hist=None)
 
+    # --- section 8(f) callers -------------------------------------------------------------------
+    def bbt_diag(self):
+        d = np.zeros(self.rows)
+        lib().ref_bbt_diag(self.h, d)
+        return d
+
+    def max_eig_scaled(self, D, ne=False, iters=10):
+        return lib().ref_max_eig_scaled(self.h, int(ne), _f64(D), int(iters))
+
+    def chebyshev_apply(self, b, ne=False, scale=None, degree=3, ratio=30.0):
+        scale = (1.0 if ne else 1.1) if scale is None else scale
+        x = np.zeros(self.rows)
+        lam_printed = lib().ref_chebyshev_apply(self.h, int(ne), float(scale), int(degree), float(ratio), _f64(b), x)
+        return x, lam_printed
+
+    def pcg_chebyshev(self, x0, b, max_iter, tol, relative=False, scale=1.1, degree=3, ratio=30.0):
+        x = _f64(x0).copy()
+        it, res = C.c_int(int(max_iter)), C.c_double(float(tol))
+        conv = lib().ref_pcg_chebyshev(self.h, x, _f64(b), float(scale), int(degree), float(ratio),
+                                       C.byref(it), C.byref(res), int(relative))
+        return bool(conv), it.value, res.value, x
+
+    def pcgne(self, u0, b, max_iter, tol, relative=False, pc=0, omega=1.0, scale=1.0, degree=3, ratio=30.0):
+        u = _f64(u0).copy()
+        it, res = C.c_int(int(max_iter)), C.c_double(float(tol))
+        conv = lib().ref_pcgne(self.h, u, _f64(b), int(pc), float(omega), float(scale), int(degree), float(ratio),
+                               C.byref(it), C.byref(res), int(relative))
+        return bool(conv), it.value, res.value, u
+
+    def idrs(self, x0, b, max_iter, tol, draws, relative=False, s=4, omega_bound=0.7, pc=1, omega=1.0):
+        """draws: the s*n ints rand() returns; the shadow vectors are shadow_from_draws(draws)."""
+        x = _f64(x0).copy()
+        draws = np.ascontiguousarray(draws, dtype=np.int32).reshape(-1)
+        assert draws.size == s * self.rows
+        it, res = C.c_int(int(max_iter)), C.c_double(float(tol))
+        ret = lib().ref_idrs(self.h, x, _f64(b), int(pc), float(omega), int(s), float(omega_bound), draws, draws.size,
+                             C.byref(it), C.byref(res), int(relative))
+        return ret, it.value, res.value, x
+
     def lanczos_basis(self, r0, max_vecs=8):
         n = self.rows
         Q = np.zeros((max_vecs, n))
@@ -300,6 +349,40 @@ def blockmat_saddle(A, B, b):
     Sb, STb = np.zeros(n), np.zeros(n)
     lib().ref_blockmat_saddle(A.h, B.h, _f64(b), Sb, STb)
     return Sb, STb
+
+
+RAND_MAX = 2147483647
+
+
+def shadow_from_draws(draws, s):
+    """IDRS :1613: P[i][j] = (double)(2.0*rand())/RAND_MAX - 1.0 for the s*n draws in call order."""
+    r = np.asarray(draws, dtype=np.float64).reshape(s, -1)
+    return (2.0 * r) / float(RAND_MAX) - 1.0
+
+
+def _handles(blocks):
+    return (C.c_void_p * 4)(*[b.h if b is not None else None for b in blocks])
+
+
+def block_mul(blocks, ops, x, transposed=False):
+    """BlockMatrixCL(A, opA, B, opB, C, opC, D, opD) * x or transp_mul, run by the reference."""
+    rows, cols = C.c_size_t(), C.c_size_t()
+    hb, ob = _handles(blocks), (C.c_int * 4)(*ops)
+    lib().ref_block_dims(C.cast(hb, C.c_void_p), ob, C.byref(rows), C.byref(cols))
+    y = np.zeros(cols.value if transposed else rows.value)
+    x = _f64(x)
+    assert x.size == (rows.value if transposed else cols.value)
+    lib().ref_block_mul(C.cast(hb, C.c_void_p), ob, int(transposed), x, y)
+    return y
+
+
+def composite_mul(A0, op0, A1, op1, x, transposed=False):
+    n_out = (A1.rows if op1 == 0 else A1.cols) if not transposed else (A0.cols if op0 == 0 else A0.rows)
+    n_in = (A0.cols if op0 == 0 else A0.rows) if not transposed else (A1.rows if op1 == 0 else A1.cols)
+    assert len(x) == n_in, (len(x), n_in)
+    y = np.zeros(n_out)
+    lib().ref_composite_mul(A0.h, int(op0), A1.h, int(op1), int(transposed), _f64(x), y)
+    return y
 
 
 def num_threads():

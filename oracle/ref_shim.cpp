@@ -14,6 +14,35 @@
 //   GMRES          -> src/num/krylovsolver.h:320-461, driver :1924-1973
 //   MINRES/PMINRES -> src/num/krylovsolver.h:926-1161, drivers :1868-1921
 //   DummyExchangeCL-> src/parallel/exchange.h:45-85
+// IDRS (krylovsolver.h:1610-1613) draws its shadow space with srand(time(NULL)) / rand().  To make a
+// reference run repeatable the two calls are redirected -- by macro, after every standard header that
+// could mention them has been included, so the reference sources stay untouched -- to a queue the test
+// fills (ref_idrs); with an empty queue rand() is the C library's.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <fstream>
+#include <iostream>
+#include <list>
+#include <map>
+#include <numeric>
+#include <random>
+#include <set>
+#include <sstream>
+#include <string>
+#include <valarray>
+#include <vector>
+namespace shimrand {
+static std::vector<int> queue;
+static size_t pos = 0;
+inline int next() { return pos < queue.size() ? queue[pos++] : std::rand(); }
+inline void seed(unsigned) {}
+}
+#define rand() shimrand::next()
+#define srand(x) shimrand::seed(x)
+
 #include "num/krylovsolver.h"
 #include "num/precond.h"
 #include "num/spblockmat.h"
@@ -493,6 +522,200 @@ void* ref_matrix_lincomb(double a, void* hA, double b, void* hB)
     RefMatrix* M = new RefMatrix;
     M->A.LinComb(a, static_cast<RefMatrix*>(hA)->A, b, static_cast<RefMatrix*>(hB)->A);
     return M;
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// PCGNE, Chebyshev, IDR(s), block / composite products.
+// ---------------------------------------------------------------------------------------------
+namespace {
+// PCGNE needs M.SetDiag(A, ex, ex) and M.Apply(A, x, b, ex, ex) (krylovsolver.h:204, :218).  Of the
+// serial preconditioners only NEGSPcCL and ChebyshevBBTPcCL have both; these two adapters give the
+// reference PCGNE an identity and a Jacobi (diag(A A^T) = BBTDiag, the _PAR ParJacNEG0CL of
+// precond.h:1190-1229, applied with the reference's own Jacobi0 :1293-1311).
+struct ShimIdentityNEPc {
+    bool RetAcc() const { return false; }
+    bool NeedDiag() const { return false; }
+    template <typename Mat, typename ExT> void SetDiag(const Mat&, const ExT&, const ExT&) {}
+    template <typename Mat, typename Vec, typename ExT>
+    void Apply(const Mat&, Vec& x, const Vec& b, const ExT&, const ExT&) const { x = b; }
+};
+struct ShimJacobiNEPc {
+    DROPS::VectorCL diag_;
+    double omega_;
+    explicit ShimJacobiNEPc(double omega) : omega_(omega) {}
+    bool RetAcc() const { return false; }
+    bool NeedDiag() const { return true; }
+    template <typename Mat, typename ExT> void SetDiag(const Mat& A, const ExT& rowex, const ExT& colex)
+    {
+        diag_.resize(A.num_rows());
+        diag_ = DROPS::BBTDiag(A, rowex, colex);
+    }
+    template <typename Mat, typename Vec, typename ExT>
+    void Apply(const Mat& A, Vec& x, const Vec& b, const ExT&, const ExT&) const
+    {
+        DROPS::Jacobi0(A, diag_, x, b, omega_, std::fabs(omega_ - 1.) > DROPS::DoubleEpsC);
+    }
+};
+
+template <typename PC>
+int run_pcgne(const DROPS::MatrixCL& A, PC& pc, double* u, const double* b, int* max_iter, double* tol, int relative)
+{
+    const size_t n = A.num_rows();
+    DROPS::VectorCL uv(to_vec(u, n)), bv(to_vec(b, n));
+    DROPS::DummyExchangeCL ex;
+    bool ok;
+    {
+        CoutCapture cap;
+        ok = DROPS::PCGNE(A, uv, bv, ex, ex, pc, *max_iter, *tol, relative != 0);
+        g_last_log = cap.sink.str();
+    }
+    from_vec(uv, u);
+    return ok ? 1 : 0;
+}
+} // namespace
+
+extern "C" {
+
+void ref_bbt_diag(void* h, double* d)
+{
+    const DROPS::MatrixCL& A = static_cast<RefMatrix*>(h)->A;
+    from_vec(DROPS::BBTDiag(A, DROPS::DummyExchangeCL(), DROPS::DummyExchangeCL()), d);
+}
+
+// MaxEigenvalueScaledMatrix (precond.h:1080-1096) on A (ne = 0) or on the composite A A^T (ne = 1)
+double ref_max_eig_scaled(void* h, int ne, const double* D, int iter)
+{
+    const DROPS::MatrixCL& A = static_cast<RefMatrix*>(h)->A;
+    DROPS::DummyExchangeCL ex;
+    DROPS::VectorCL d(to_vec(D, A.num_rows()));
+    if (!ne) return DROPS::MaxEigenvalueScaledMatrix(A, d, ex, iter);
+    DROPS::CompositeMatrixBaseCL<DROPS::MatrixCL, DROPS::MatrixCL, DROPS::DummyExchangeCL>
+        mat(&A, DROPS::TRANSP_MUL, ex, &A, DROPS::MUL, ex);
+    return DROPS::MaxEigenvalueScaledMatrix(mat, d, ex, iter);
+}
+
+// ChebyshevPcCL (ne = 0, precond.h:1463-1529) / ChebyshevBBTPcCL (ne = 1, :1531-1567): SetDiag + Apply.
+// Returns lambda_max as printed by SetDiag.
+double ref_chebyshev_apply(void* h, int ne, double scale, int degree, double ratio, const double* b, double* x)
+{
+    const DROPS::MatrixCL& A = static_cast<RefMatrix*>(h)->A;
+    const size_t n = A.num_rows();
+    DROPS::DummyExchangeCL ex;
+    DROPS::VectorCL bv(to_vec(b, n)), xv(n);
+    CoutCapture cap;
+    if (!ne) {
+        DROPS::ChebyshevPcCL pc(scale, degree, ratio);
+        pc.SetDiag(A, ex);
+        pc.Apply(A, xv, bv, ex);
+    } else {
+        DROPS::ChebyshevBBTPcCL pc(scale, degree, ratio);
+        pc.SetDiag(A, ex, ex);
+        pc.Apply(A, xv, bv, ex, ex);
+    }
+    g_last_log = cap.sink.str();
+    from_vec(xv, x);
+    const size_t p = g_last_log.rfind("lambda_max = ");
+    return p == std::string::npos ? 0.0 : std::atof(g_last_log.c_str() + p + 13);
+}
+
+// PCGSolverCL<ChebyshevPcCL>
+int ref_pcg_chebyshev(void* h, double* x, const double* b, double scale, int degree, double ratio,
+                      int* max_iter, double* tol, int relative)
+{
+    const DROPS::MatrixCL& A = static_cast<RefMatrix*>(h)->A;
+    const size_t n = A.num_rows();
+    DROPS::VectorCL xv(to_vec(x, n)), bv(to_vec(b, n));
+    DROPS::ChebyshevPcCL pc(scale, degree, ratio);
+    bool ok;
+    {
+        CoutCapture cap;
+        ok = DROPS::PCG(A, xv, bv, DROPS::DummyExchangeCL(), pc, *max_iter, *tol, relative != 0);
+        g_last_log = cap.sink.str();
+    }
+    from_vec(xv, x);
+    return ok ? 1 : 0;
+}
+
+// PCGNE (krylovsolver.h:199-252).  pc_kind 0: identity adapter, 1: Jacobi-on-BBTDiag adapter,
+// 2: the reference's ChebyshevBBTPcCL(scale, degree, ratio).
+int ref_pcgne(void* h, double* u, const double* b, int pc_kind, double omega, double scale, int degree, double ratio,
+              int* max_iter, double* tol, int relative)
+{
+    const DROPS::MatrixCL& A = static_cast<RefMatrix*>(h)->A;
+    if (pc_kind == 2) { DROPS::ChebyshevBBTPcCL pc(scale, degree, ratio); return run_pcgne(A, pc, u, b, max_iter, tol, relative); }
+    if (pc_kind == 1) { ShimJacobiNEPc pc(omega); return run_pcgne(A, pc, u, b, max_iter, tol, relative); }
+    ShimIdentityNEPc pc;
+    return run_pcgne(A, pc, u, b, max_iter, tol, relative);
+}
+
+// IDRS (krylovsolver.h:1579-1698).  draws: the s*n values rand() returns at :1613, in call order.
+// Returns the reference's bool, -1 when it throws (M(k,k) == 0 / omega == 0).
+int ref_idrs(void* h, double* x, const double* b, int pc_kind, double omega_pc, int s, double omega_bound,
+             const int* draws, size_t ndraws, int* max_iter, double* tol, int relative)
+{
+    const DROPS::MatrixCL& A = static_cast<RefMatrix*>(h)->A;
+    const size_t n = A.num_rows();
+    DROPS::VectorCL xv(to_vec(x, n)), bv(to_vec(b, n));
+    shimrand::queue.assign(draws, draws + ndraws);
+    shimrand::pos = 0;
+    // The reference reads uninitialised memory here: DMatrixCL M(s,s) is a bare new T[] (misc/container.h:51)
+    // and the first cycle solves with the strictly lower triangle of M before any of it was written
+    // (krylovsolver.h:1620-1636).  The values do not matter as long as they are finite (G and U are still
+    // zero), but recycled heap chunks can hold NaN bit patterns.  Park a few zeroed chunks of exactly that
+    // size in the allocator's free list so that M starts from finite memory and the run is repeatable.
+    {
+        double* park[6];
+        for (int i = 0; i < 6; ++i) { park[i] = new double[(size_t)s * s]; std::memset(park[i], 0, sizeof(double) * s * s); }
+        for (int i = 0; i < 6; ++i) delete[] park[i];
+    }
+    int ret;
+    try {
+        CoutCapture cap;
+        bool ok;
+        if (pc_kind == 1) { DROPS::JACPcCL pc(omega_pc); ok = DROPS::IDRS(A, xv, bv, DROPS::DummyExchangeCL(), pc, *max_iter, *tol, relative != 0, s, omega_bound); }
+        else { DROPS::DummyPcCL pc; ok = DROPS::IDRS(A, xv, bv, DROPS::DummyExchangeCL(), pc, *max_iter, *tol, relative != 0, s, omega_bound); }
+        ret = ok ? 1 : 0;
+    } catch (DROPS::DROPSErrCL&) {
+        ret = -1;
+    }
+    shimrand::queue.clear();
+    shimrand::pos = 0;
+    from_vec(xv, x);
+    return ret;
+}
+
+// BlockMatrixCL(A, opA, B, opB, C, opC, D, opD) * x and transp_mul (spblockmat.h:225-273); null handles
+// are absent blocks.  rows/cols: num_rows()/num_cols() of the block matrix.
+void ref_block_dims(void* const* hb, const int* ops, size_t* rows, size_t* cols)
+{
+    const DROPS::MatrixCL* m[4];
+    for (int i = 0; i < 4; ++i) m[i] = hb[i] ? &static_cast<RefMatrix*>(hb[i])->A : 0;
+    DROPS::BlockMatrixCL S(m[0], (DROPS::BlockMatrixOperationT)ops[0], m[1], (DROPS::BlockMatrixOperationT)ops[1],
+                           m[2], (DROPS::BlockMatrixOperationT)ops[2], m[3], (DROPS::BlockMatrixOperationT)ops[3]);
+    *rows = S.num_rows(); *cols = S.num_cols();
+}
+
+void ref_block_mul(void* const* hb, const int* ops, int transposed, const double* x, double* y)
+{
+    const DROPS::MatrixCL* m[4];
+    for (int i = 0; i < 4; ++i) m[i] = hb[i] ? &static_cast<RefMatrix*>(hb[i])->A : 0;
+    DROPS::BlockMatrixCL S(m[0], (DROPS::BlockMatrixOperationT)ops[0], m[1], (DROPS::BlockMatrixOperationT)ops[1],
+                           m[2], (DROPS::BlockMatrixOperationT)ops[2], m[3], (DROPS::BlockMatrixOperationT)ops[3]);
+    if (!transposed) from_vec(DROPS::VectorCL(S * to_vec(x, S.num_cols())), y);
+    else from_vec(DROPS::VectorCL(transp_mul(S, to_vec(x, S.num_rows()))), y);
+}
+
+// CompositeMatrixCL(A0, op0, ex, A1, op1, ex) * x (spblockmat.h:376-397)
+void ref_composite_mul(void* h0, int op0, void* h1, int op1, int transposed, const double* x, double* y)
+{
+    const DROPS::MatrixCL& A0 = static_cast<RefMatrix*>(h0)->A;
+    const DROPS::MatrixCL& A1 = static_cast<RefMatrix*>(h1)->A;
+    DROPS::DummyExchangeCL ex;
+    DROPS::CompositeMatrixCL Cm(&A0, (DROPS::BlockMatrixOperationT)op0, ex, &A1, (DROPS::BlockMatrixOperationT)op1, ex);
+    if (!transposed) from_vec(DROPS::VectorCL(Cm * to_vec(x, Cm.num_cols())), y);
+    else from_vec(DROPS::VectorCL(transp_mul(Cm, to_vec(x, Cm.num_rows()))), y);
 }
 
 } // extern "C"
