@@ -4,7 +4,8 @@
 // functions CG (:49-103), PCG (:107-179), GMRES (:320-461), MINRES (:1155-1161), PMINRES
 // (:1069-1152), the orthonormal-basis classes LanczosONBCL (:945-979) / PLanczosONBCL
 // (:1010-1052) and the drivers CGSolverCL (:1782-1802), PCGSolverCL (:1805-1832), MResSolverCL
-// (:1868-1889), PMResSolverCL (:1892-1921), GMResSolverCL (:1924-1973).
+// (:1868-1889), PMResSolverCL (:1892-1921), GMResSolverCL (:1924-1973); next to them PCGNE (:199-252,
+// PCGNESolverCL :1836-1865), BICGSTAB, GCR and IDRS (:1579-1698, IDRsSolverCL :2095-2135).
 //
 // Signatures, in/out conventions and return values are the reference's: x is the start vector
 // on entry and the solution on exit, max_iter IN limit / OUT iterations used, tol IN tolerance /
@@ -68,19 +69,47 @@ bool CG(const Mat& A, Vec& x, const Vec& b, const ExCL&, int& max_iter, double& 
 
 /// Preconditioned conjugate gradients; M is JACPcCL or DummyPcCL.
 template <typename Mat, typename Vec, typename PreCon, typename ExCL>
-bool PCG(const Mat& A, Vec& x, const Vec& b, const ExCL&, PreCon& M, int& max_iter, double& tol,
+bool PCG(const Mat& A, Vec& x, const Vec& b, const ExCL& ex, PreCon& M, int& max_iter, double& tol,
          bool measure_relative_tol = false, std::ostream* output = 0)
 {
     const MatrixCL& Mat0 = b200::finest(A);
     b200::check_dims(Mat0, x, b, "PCG");
     std::vector<double> hist(output ? max_iter + 1 : 0);
     int it = max_iter;
+    if (M.NeedDiag()) M.SetDiag(A, ex);                 // krylovsolver.h:123-124 (Chebyshev: lambda_max, printed)
+    b200::PcTraits<PreCon>::prepare(M, Mat0.device(), false);
     const int r = drops_b200_pcg(Mat0.device(), &x[0], Addr(b), b200::PcTraits<PreCon>::kind(),
                                  b200::PcTraits<PreCon>::omega(M), &it, &tol, measure_relative_tol ? 1 : 0,
                                  output ? hist.data() : 0, static_cast<int>(hist.size()));
     b200::check(r);
     if (r == 1) max_iter = it;
     b200::print_history(output, "PCG", hist, r == 1 ? it : max_iter);
+    return r == 1;
+}
+
+/// PCG for the normal equations A A^T u = b of a rectangular A (src/num/krylovsolver.h:199-252); M is
+/// ChebyshevBBTPcCL or DummyPcCL, or JACPcCL (then Jacobi on diag(A A^T), what the MPI build's
+/// ParJacNEG0CL does).  The residual log follows the reference: iteration 0 and every tenth.
+template <typename Mat, typename Vec, typename PreCon, typename ExACL, typename ExATranspCL>
+bool PCGNE(const Mat& A, Vec& u, const Vec& b, const ExACL& ExAX, const ExATranspCL& ExATranspX, PreCon& M, int& max_iter, double& tol,
+           bool measure_relative_tol = false, std::ostream* output = 0)
+{
+    const MatrixCL& Mat0 = b200::finest(A);
+    if (u.size() != Mat0.num_rows() || b.size() != Mat0.num_rows()) throw DROPSErrCL("PCGNE: incompatible dimensions");
+    std::vector<double> hist(output ? max_iter + 1 : 0);
+    int it = max_iter;
+    M.SetDiag(A, ExATranspX, ExAX);                      // krylovsolver.h:204
+    b200::PcTraits<PreCon>::prepare(M, Mat0.device(), true);
+    const int r = drops_b200_pcgne(Mat0.device(), &u[0], Addr(b), b200::PcTraits<PreCon>::kind(),
+                                   b200::PcTraits<PreCon>::omega(M), &it, &tol, measure_relative_tol ? 1 : 0,
+                                   output ? hist.data() : 0, static_cast<int>(hist.size()));
+    b200::check(r);
+    if (r == 1) max_iter = it;
+    if (output) {
+        const int last = r == 1 ? it : max_iter;
+        for (int i = 0; i <= last && i < static_cast<int>(hist.size()); ++i)
+            if (i == 0 || i % 10 == 0) (*output) << "PCGNE: iter: " << i << " resid: " << hist[i] << '\n';
+    }
     return r == 1;
 }
 
@@ -123,6 +152,22 @@ bool BICGSTAB(const Mat& A, Vec& x, const Vec& b, const ExT&, Preconditioner& M,
     if (breakdown == 1) std::cout << "BiCGSTAB: Breakdown with rho_1 = 0.\n";
     if (breakdown == 2) std::cout << "BiCGSTAB: Breakdown with omega_ = 0.\n";
     if (r == 1 || breakdown) max_iter = it;
+    return r == 1;
+}
+
+/// IDR(s) (src/num/krylovsolver.h:1579-1698).  The shadow space is drawn like the reference draws it
+/// (srand(time(0)), rand()); outputs follow the reference literally: tol returns the ABSOLUTE residual
+/// norm, max_iter the iterations done, and the bool is false when the tolerance was beaten inside the
+/// loop (:1689-1693) -- callers in DROPS ignore it and read GetResid().
+template <class Mat, class Vec, class PC, class ExT>
+bool IDRS(const Mat& A, Vec& x, const Vec& rhs, const ExT&, PC& pc, int& max_iter, double& tol,
+          bool measure_relative_tol = false, const int s = 4, typename Vec::value_type omega_bound = 0.7)
+{
+    const MatrixCL& Mat0 = b200::finest(A);
+    b200::check_dims(Mat0, x, rhs, "IDRS");
+    const int r = drops_b200_idrs(Mat0.device(), &x[0], Addr(rhs), b200::PcTraits<PC>::kind(), b200::PcTraits<PC>::omega(pc),
+                                  s, omega_bound, 0, &max_iter, &tol, measure_relative_tol ? 1 : 0);
+    if (r < 0) throw DROPSErrCL(std::string(drops_b200_last_error()));     // "IDR(s): M(k,k) ==0" / "omega ==0"
     return r == 1;
 }
 
@@ -301,6 +346,34 @@ class PCGSolverCL : public SolverBaseCL
     }
 };
 
+/// PCG for A A^T; note that A, not A A^T, is handed to Solve (src/num/krylovsolver.h:1836-1865).
+template <typename PC>
+class PCGNESolverCL : public SolverBaseCL
+{
+  private:
+    PC& pc_;
+
+  public:
+    PCGNESolverCL(PC& pc, int maxiter, double tol, bool rel = false, std::ostream* output = 0)
+        : SolverBaseCL(maxiter, tol, rel, output), pc_(pc) {}
+
+    PC&       GetPc()       { return pc_; }
+    const PC& GetPc() const { return pc_; }
+
+    template <typename Mat, typename Vec, typename ExT>
+    void Solve(const Mat& A, Vec& x, const Vec& b, const ExT& ex, const ExT& ex_transp)
+    {
+        res_ = tol_; iter_ = maxiter_;
+        PCGNE(A, x, b, ex, ex_transp, pc_, iter_, res_, rel_, output_);
+    }
+    template <typename Mat, typename Vec, typename ExT>
+    void Solve(const Mat& A, Vec& x, const Vec& b, const ExT& ex, const ExT& ex_transp, int& numIter, double& resid) const
+    {
+        resid = tol_; numIter = maxiter_;
+        PCGNE(A, x, b, ex, ex_transp, pc_, numIter, resid, rel_, output_);
+    }
+};
+
 class MResSolverCL : public SolverBaseCL
 {
   public:
@@ -408,6 +481,39 @@ class BiCGStabSolverCL : public SolverBaseCL
     {
         resid = tol_; numIter = maxiter_;
         BICGSTAB(A, x, b, ex, pc_, numIter, resid, rel_);
+    }
+};
+
+/// IDR(s) driver (src/num/krylovsolver.h:2095-2135).
+template <typename PC>
+class IDRsSolverCL : public SolverBaseCL
+{
+  private:
+    PC&          pc_;
+    const int    s_;
+    const double omega_bound_;
+
+  public:
+    IDRsSolverCL(PC& pc, int maxiter, double tol, bool relative = true, const int s = 4, const double omega_bound = 0.7,
+                 std::ostream* output = 0)
+        : SolverBaseCL(maxiter, tol, relative, output), pc_(pc), s_(s), omega_bound_(omega_bound) {}
+
+    PC&       GetPc()       { return pc_; }
+    const PC& GetPc() const { return pc_; }
+
+    template <typename Mat, typename Vec, typename ExT>
+    void Solve(const Mat& A, Vec& x, const Vec& b, const ExT& ex)
+    {
+        res_ = tol_; iter_ = maxiter_;
+        IDRS(A, x, b, ex, pc_, iter_, res_, rel_, s_, omega_bound_);
+        if (output_ != 0)
+            *output_ << "IDRsSolverCL: iterations: " << GetIter() << "\tresidual: " << GetResid() << std::endl;
+    }
+    template <typename Mat, typename Vec, typename ExT>
+    void Solve(const Mat& A, Vec& x, const Vec& b, const ExT& ex, int& numIter, double& resid) const
+    {
+        resid = tol_; numIter = maxiter_;
+        IDRS(A, x, b, ex, pc_, numIter, resid, rel_, s_, omega_bound_);
     }
 };
 

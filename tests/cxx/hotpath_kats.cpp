@@ -10,10 +10,12 @@
 // Laplacian for PCG/GMRES with JACPcCL, which the reference never tests.
 #include "num/krylovsolver.h"
 #include "num/precond.h"
+#include "num/spblockmat.h"
 #include "num/spmat.h"
 #include "parallel/exchange.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <sstream>
 #include <string>
 #include <iostream>
@@ -169,6 +171,38 @@ int main()
         c[0] = 1.; c[1] = 2.;
         print_vec("B*c", VectorCL(B * c));
     }
+    // --- BlockMatrixCL / CompositeMatrixCL (blockmat.cpp + Testblockmat.ref) ------------------------------
+    {
+        MatrixCL A, B;
+        MatrixBuilderCL AB(&A, 2, 2);
+        AB(0, 1) = 1.; AB(1, 0) = 1.;
+        AB.Build();
+        MatrixBuilderCL BB(&B, 1, 2);
+        BB(0, 0) = 1.; BB(0, 1) = 1.;
+        BB.Build();
+        BlockMatrixCL S(&A, MUL, &B, TRANSP_MUL, &B, MUL);
+        VectorCL b(3);
+        b[0] = 1.; b[1] = 2.; b[2] = 3.;
+        std::printf("BLOCK dims: %zu %zu %zu %zu %zu %zu\n", S.num_rows(0), S.num_rows(1), S.num_cols(0), S.num_cols(1),
+                    S.num_rows(), S.num_cols());
+        print_vec("BLOCK S*b", VectorCL(S * b));
+        print_vec("BLOCK transp_mul", VectorCL(transp_mul(S, b)));
+        BlockMatrixCL S2(0, MUL, &B, TRANSP_MUL, &B, MUL, 0, MUL);            // no diagonal blocks
+        print_vec("BLOCK nodiag", VectorCL(S2 * b));
+        MatrixCL Sfull(BuildMatrix(S));
+        print_vec("BLOCK built", VectorCL(Sfull * b));
+        DummyExchangeCL dex;
+        CompositeMatrixCL BBt(&B, TRANSP_MUL, dex, &B, MUL, dex);             // B * B^T  (1x1)
+        VectorCL one(1);
+        one[0] = 2.;
+        std::printf("COMPOSITE dims: %zu %zu %zu\n", BBt.num_rows(), BBt.num_cols(), BBt.intermediate_dim());
+        print_vec("COMPOSITE BBt", VectorCL(BBt * one));
+        CompositeMatrixCL AtB(&B, TRANSP_MUL, dex, &A, MUL, dex);             // A * B^T  (2x1)
+        print_vec("COMPOSITE ABt", VectorCL(AtB * one));
+        VectorCL two(2);
+        two[0] = 1.; two[1] = -3.;
+        print_vec("COMPOSITE ABt_T", VectorCL(transp_mul(AtB, two)));
+    }
     // --- text I/O: out/in round trip, MatrixMarket header of operator<< (spmat.h:1213-1255) -------------
     {
         MatrixCL A; VectorCL b;
@@ -258,6 +292,45 @@ int main()
             std::printf("JACAPPLY z7: %.15e z100: %.15e\n", z[7], z[100]);
         }
         {
+            // PCG with the Chebyshev polynomial preconditioner (precond.h:1463-1529); SetDiag prints lambda_max
+            x = 0.;
+            ChebyshevPcCL cpc(1.1, 3, 30.0);
+            PCGSolverCL<ChebyshevPcCL> solver(cpc, 500, 1e-10, true);
+            std::ostringstream sink;
+            std::streambuf* oldbuf = std::cout.rdbuf(sink.rdbuf());
+            solver.Solve(A, x, b, ex);
+            std::cout.rdbuf(oldbuf);
+            std::printf("PCGCHEB iterations: %d residual: %.3e error: %.3e\n", solver.GetIter(), solver.GetResid(),
+                        norm(VectorCL(x - xs)) / norm(xs));
+            const std::string log = sink.str();
+            const size_t pos = log.find("lambda_max = ");
+            std::printf("PCGCHEB lambda_max: %.5g\n", pos == std::string::npos ? -1. : std::atof(log.c_str() + pos + 13));
+            // PCGNE with ChebyshevBBTPcCL on B = every second row of A (krylovsolver.h:199-252, precond.h:1531-1567)
+            MatrixCL Bh;
+            {
+                MatrixBuilderCL BB(&Bh, (N + 1) / 2, N);
+                for (size_t i = 0; i < N; i += 2)
+                    for (size_t nz = A.row_beg(i); nz < A.row_beg(i + 1); ++nz) BB(i / 2, A.col_ind(nz)) = A.val(nz);
+                BB.Build();
+            }
+            VectorCL us(Bh.num_rows());
+            for (size_t i = 0; i < us.size(); ++i) us[i] = 1. + 0.01 * double(i % 17);
+            const VectorCL bu(Bh * VectorCL(transp_mul(Bh, us)));
+            VectorCL u(Bh.num_rows());
+            ChebyshevBBTPcCL bpc(1., 3, 30.0);
+            PCGNESolverCL<ChebyshevBBTPcCL> nesolver(bpc, 500, 1e-10, true);
+            oldbuf = std::cout.rdbuf(sink.rdbuf());
+            nesolver.Solve(Bh, u, bu, ex, ex);
+            std::cout.rdbuf(oldbuf);
+            std::printf("PCGNE iterations: %d residual: %.3e error: %.3e\n", nesolver.GetIter(), nesolver.GetResid(),
+                        norm(VectorCL(u - us)) / norm(us));
+            const VectorCL bbt(BBTDiag(Bh, ex, ex));
+            std::printf("BBTDIAG d0: %.15e d9: %.15e\n", bbt[0], bbt[9]);
+            VectorCL zc(N);
+            cpc.Apply(A, zc, b, ex);
+            std::printf("CHEBAPPLY z7: %.12e z100: %.12e\n", zc[7], zc[100]);
+        }
+        {
             MatrixCL G;
             fill_laplace3d(G, n, 0.5, 1.1);         // nonsymmetric
             VectorCL bg(G * xs);
@@ -282,6 +355,11 @@ int main()
             gsolver.Solve(G, x, bg, ex);
             std::printf("GCRJAC iterations: %d residual: %.3e error: %.3e\n", gsolver.GetIter(), gsolver.GetResid(),
                         norm(VectorCL(x - xs)) / norm(xs));
+            x = 0.;
+            IDRsSolverCL<JACPcCL> isolver(pc, 500, 1e-10, true, 4, 0.7);      // random shadow space: only the
+            isolver.Solve(G, x, bg, ex);                                       // outcome is comparable
+            std::printf("IDRS solved: %d error ok: %d\n", int(isolver.GetResid() / norm(bg) <= 1e-10),
+                        int(norm(VectorCL(x - xs)) / norm(xs) <= 1e-8));
             // time-step matrix L = c1*A + c2*G (LinComb, spmat.h:1457-1551): merged on the device when the
             // operands are resident -- no upload before the solve
             {

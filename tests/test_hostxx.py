@@ -17,7 +17,8 @@ EXPECTED = os.path.join(ROOT, "tests", "golden", "hotpath_kats.expected.txt")
 
 KEYS = ("LANCZOS", "MINRES2", "MINRES4", "PMINRES4", "PMINRES4D", "TRANSP_MUL", "B*c", "VECEXPR", "VECOPS",
         "EXCHANGE", "LAPLACE", "PCGJAC", "PCGJAC08", "CG", "PCGJAC5", "JACAPPLY", "GMRESJAC", "GMRESJACR",
-        "VERSIONED", "hotpath_kats", "BICGSTAB2", "BICGSTAB4", "GCR2", "GCR4", "BICGSTABJAC", "GCRJAC", "IO out", "IO mtx", "IO vec", "LINCOMB")
+        "VERSIONED", "hotpath_kats", "BICGSTAB2", "BICGSTAB4", "GCR2", "GCR4", "BICGSTABJAC", "GCRJAC", "IO out", "IO mtx", "IO vec", "LINCOMB", "BLOCK", "COMPOSITE", "PCGCHEB", "PCGNE",
+        "BBTDIAG", "CHEBAPPLY", "IDRS")
 
 
 def parse(text):
@@ -55,6 +56,8 @@ def test_expected_output_holds_the_reference_kats():
     # bicgstab.cpp / TestBiCGStab.ref and gcr.cpp / TestGCR.ref: residuals 0 +- 1e-10
     for key in ("BICGSTAB2 iterations", "BICGSTAB4 iterations", "GCR2 iterations", "GCR4 iterations"):
         assert abs(exp[key][1]) < 1e-10, key
+    assert exp["BLOCK S*b"] == [5.0, 4.0, 3.0] and exp["BLOCK transp_mul"] == [5.0, 4.0, 3.0]   # Testblockmat.ref
+    assert exp["IDRS solved"] == [1.0, 1.0]
     assert "hotpath_kats finished regularly" in open(EXPECTED).read()
 
 
@@ -90,5 +93,14 @@ def test_dropin_binary_matches_reference_output(lib_built):
     for key in ("BICGSTABJAC iterations", "GCRJAC iterations"):
         assert abs(got[key][0] - exp[key][0]) <= 1, (key, got[key], exp[key])
         assert got[key][1] <= 1e-10 and got[key][2] <= 1e-8, (key, got[key])
+    # section 8(f) callers: block / composite products exact, Chebyshev-preconditioned solvers +-1 iteration
+    for key in ("BLOCK dims", "BLOCK S*b", "BLOCK transp_mul", "BLOCK nodiag", "BLOCK built", "COMPOSITE dims",
+                "COMPOSITE BBt", "COMPOSITE ABt", "COMPOSITE ABt_T", "BBTDIAG d0", "IDRS solved"):
+        assert got[key] == exp[key], (key, got[key], exp[key])
+    for key in ("PCGCHEB iterations", "PCGNE iterations"):
+        assert abs(got[key][0] - exp[key][0]) <= 1, (key, got[key], exp[key])
+        assert got[key][1] <= 1e-10 and got[key][2] <= 1e-8, (key, got[key])
+    assert got["PCGCHEB lambda_max"] == exp["PCGCHEB lambda_max"]              # as printed by SetDiag (6 digits)
+    assert all(abs(a - b) <= 1e-11 * abs(b) for a, b in zip(got["CHEBAPPLY z7"], exp["CHEBAPPLY z7"]))
     assert abs(got["PCGJAC08 converged"][1] - exp["PCGJAC08 converged"][1]) <= 1 and got["PCGJAC08 converged"][0] == 1
     assert got["PCGJAC5 iterations"] == exp["PCGJAC5 iterations"] == [5.0, 0.0]
