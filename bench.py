@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--no-host-matrix", action="store_true", help="skip the host CSR upload path in e2e")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-small", action="store_true", help="skip the side measurement of BASELINE configs[0]")
+    ap.add_argument("--no-pk", action="store_true", help="12-byte SELL stream only (value dictionary off)")
+    ap.add_argument("--no-general", action="store_true", help="skip the side measurement of the 12-byte stream")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (repeatable)")
     return ap.parse_args()
 
 
@@ -213,6 +216,11 @@ def run_ours(args):
 
     fe, N, numbering, iters = args.fe, args.cells, args.numbering, args.iters
     n, nnz = capi.brick_sizes(fe, N)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        capi.set_option(k, float(v))
+    if args.no_pk:
+        capi.set_option("sell.valdict", 0)
     t0 = time.perf_counter()
     A = capi.Matrix.brick(fe, N, numbering)
     capi.synchronize()
@@ -228,47 +236,85 @@ def run_ours(args):
         return res
 
     # ---- device-resident steps: `value` ------------------------------------------------------
-    for _ in range(args.warmup):
-        solve_dev()
-    capi.set_option("timing", 1)
-    capi.timing_reset()
-    sampler = ClockSampler(local)
-    sampler.start()
-    capi.synchronize()
-    l0 = capi.launch_count()
-    capi.timer_start()
-    for _ in range(args.steps):
-        resid = solve_dev()
-    ms = capi.timer_stop()
-    launches = capi.launch_count() - l0
-    clocks = sampler.stop()
-    spmv_ms, spmv_cnt = capi.timing("spmv")
-    upd_ms, upd_cnt = capi.timing("pcg.update")
-    dir_ms, dir_cnt = capi.timing("pcg.direction")
-    capi.set_option("timing", 0)
+    def timed_steps(warmup, steps, with_clocks):
+        for _ in range(warmup):
+            solve_dev()
+        capi.set_option("timing", 1)
+        capi.timing_reset()
+        sampler = ClockSampler(local) if with_clocks else None
+        if sampler:
+            sampler.start()
+        capi.synchronize()
+        l0 = capi.launch_count()
+        capi.timer_start()
+        for _ in range(steps):
+            res = solve_dev()
+        ms_ = capi.timer_stop()
+        out = {"ms": ms_, "launches": capi.launch_count() - l0, "clocks": sampler.stop() if sampler else None,
+               "resid": res, "spmv": capi.timing("spmv"), "vec": capi.timing("vec"),
+               "upd": capi.timing("pcg.update"), "dir": capi.timing("pcg.direction")}
+        capi.set_option("timing", 0)
+        return out
+
+    T = timed_steps(args.warmup, args.steps, True)
+    ms, launches, clocks, resid = T["ms"], T["launches"], T["clocks"], T["resid"]
+    (spmv_ms, spmv_cnt), (upd_ms, _), (dir_ms, _), (vec_ms, _) = T["spmv"], T["upd"], T["dir"], T["vec"]
     value = args.steps * iters / (ms / 1e3)
 
     # ---- roofline of the dominant kernel --------------------------------------------------------
+    # Bytes the SpMV has to move in the format it actually streams: the dictionary-packed stream holds
+    # 4 B per stored entry (one word: value index + column), the general stream 12 B
+    # (int32 column + fp64 value, the SURVEY.md 8(d) figure).  Vector passes per iteration: p gathered
+    # and q written by the SpMV (2), r/q/d read + r written (4), x/p/r/d read + x/p written (6) = 12
+    # with the deferred x update, 13 without; a separate dot kernel re-reads p and q (+2).
     peak, peak_src = measured_peaks()
-    spmv_bytes = 12.0 * nnz + 4.0 * (n + 1) + 16.0 * n
-    iter_bytes = 12.0 * nnz + 4.0 * (n + 1) + 13.0 * 8.0 * n
+    packed = A.value_dictionary()["packed"] and capi.get_option("spmv.pk", 1.0) != 0.0
+    entry_bytes = 4.0 if packed else 12.0
+    passes = (12.0 if capi.get_option("pcg.defer_x", 1.0) != 0.0 else 13.0) + \
+             (0.0 if capi.get_option("pcg.fused_dot", 1.0) != 0.0 else 2.0)
+    spmv_bytes = entry_bytes * nnz + 4.0 * (n + 1) + 16.0 * n
+    iter_bytes = entry_bytes * nnz + 4.0 * (n + 1) + passes * 8.0 * n
+    survey_spmv_bytes = 12.0 * nnz + 4.0 * (n + 1) + 16.0 * n
+    survey_iter_bytes = 12.0 * nnz + 4.0 * (n + 1) + 13.0 * 8.0 * n
     spmv_avg_ms = spmv_ms / max(spmv_cnt, 1)
     achieved = spmv_bytes / (spmv_avg_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_spmv_sell<EPI_NONE,exact,dot> (q = A p fused with p.q)",
+    kernel_name = ("k_spmv_sell_pk<EPI_NONE,exact,dot> (q = A p fused with p.q, dictionary-packed 4-byte stream)"
+                   if packed else "k_spmv_sell<EPI_NONE,exact,dot> (q = A p fused with p.q)")
+    roofline = {"bound": "hbm", "kernel": kernel_name,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "traffic": None,
-                "algorithmic_bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_avg_ms, "launches": spmv_cnt,
-                "iteration": {"algorithmic_bytes": iter_bytes,
+                "algorithmic_bytes_per_launch": spmv_bytes, "bytes_per_stored_entry": entry_bytes,
+                "avg_launch_ms": spmv_avg_ms, "launches": spmv_cnt,
+                "survey_12B_layout": {"algorithmic_bytes_per_launch": survey_spmv_bytes,
+                                      "equivalent_gbs": survey_spmv_bytes / (spmv_avg_ms / 1e3) / 1e9,
+                                      "note": "what a 12 B/entry stream would have to sustain to match this launch time"},
+                "iteration": {"algorithmic_bytes": iter_bytes, "vector_passes": passes,
                               "achieved_gbs": iter_bytes * args.steps * iters / (ms / 1e3) / 1e9,
                               "frac": iter_bytes * args.steps * iters / (ms / 1e3) / 1e9 / peak,
+                              "survey_12B_13pass_equivalent_gbs": survey_iter_bytes * args.steps * iters / (ms / 1e3) / 1e9,
                               "kernel_ms_share": {"spmv": spmv_ms / ms, "pcg.update": upd_ms / ms,
-                                                  "pcg.direction": dir_ms / ms}}}
+                                                  "pcg.direction": dir_ms / ms, "dot": vec_ms / ms}}}
     prof = os.path.join(ROOT, "profiles", "spmv_traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            tr = json.load(open(prof))
+            roofline["traffic"] = tr.get("dram_bytes_per_launch_pk" if packed else "dram_bytes_per_launch")
         except Exception:
             pass
+
+    # ---- the same solve on the general 12-byte stream (what a matrix without a value dictionary runs)
+    general = None
+    if packed and not args.no_general:
+        capi.set_option("spmv.pk", 0)
+        G = timed_steps(1, 1, False)
+        capi.set_option("spmv.pk", 1)
+        g_spmv_ms = G["spmv"][0] / max(G["spmv"][1], 1)
+        general = {"iterations_per_s": iters / (G["ms"] / 1e3), "spmv_avg_launch_ms": g_spmv_ms,
+                   "spmv_achieved_gbs": survey_spmv_bytes / (g_spmv_ms / 1e3) / 1e9,
+                   "spmv_frac": survey_spmv_bytes / (g_spmv_ms / 1e3) / 1e9 / peak,
+                   "iteration_frac": (12.0 * nnz + 4.0 * (n + 1) + passes * 8.0 * n) * iters / (G["ms"] / 1e3) / 1e9 / peak,
+                   "note": "spmv.pk = 0: int32 column + fp64 value per entry, 1 step after 1 warm-up"}
+        assert G["resid"] == resid, (G["resid"], resid)     # bit-identical products -> identical solve
 
     # ---- end to end through the host-buffer C ABI ----------------------------------------------
     import torch
@@ -342,9 +388,10 @@ def run_ours(args):
                                f"PCGSolverCL<JACPcCL>, {iters} iterations per step, tol=0, relative",
                    "numbering": "vertices-then-edges (DROPS order)" if numbering == 1 else "lexicographic",
                    "cache": "inputs (17 GB matrix, 0.4 GB vectors) far exceed the 126 MB L2; no flush needed",
-                   "spmv_kernel": "sell-32-sigma exact", "generate_s": gen_s},
+                   "spmv_kernel": "sell-32-sigma exact" + (", value dictionary (%d values), 4 B/entry" % A.value_dictionary()["n_distinct"] if packed else ", 12 B/entry"),
+                   "generate_s": gen_s},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        "final_relative_residual": resid, "other_configs": {"C1_p1_n64": c1},
+        "final_relative_residual": resid, "general_12B_stream": general, "other_configs": {"C1_p1_n64": c1},
     }
     print(json.dumps(line), flush=True)
 

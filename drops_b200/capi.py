@@ -56,6 +56,7 @@ SIGNATURES = {
     "drops_b200_matrix_destroy": (_i, [_vp]),
     "drops_b200_matrix_info": (_i, [_vp, _szpp, _szpp, _szpp, C.POINTER(C.c_uint64), _szpp, _szpp]),
     "drops_b200_matrix_format": (_i, [_vp, _szpp, _szpp, _ip, _szpp]),
+    "drops_b200_matrix_value_dictionary": (_i, [_vp, _i, _ip, _ip, _ip]),
     "drops_b200_matrix_download": (_i, [_vp, _szp, _szp, _dp]),
     "drops_b200_spmv": (_i, [_vp, _dp, _dp]),
     "drops_b200_spmv_transpose": (_i, [_vp, _dp, _dp]),
@@ -191,6 +192,17 @@ def shutdown():
 
 def set_option(key, value):
     check(lib().drops_b200_set_option(key.encode(), float(value)))
+
+
+def get_option(key, default=None):
+    """Value of a library option; `default` when it was never set (the library then uses its own default)."""
+    v = C.c_double()
+    r = lib().drops_b200_get_option(key.encode(), C.byref(v))
+    if r < 0:
+        if default is None:
+            check(r)
+        return default
+    return v.value
 
 
 def timing(key):
@@ -374,6 +386,11 @@ class Matrix:
         cmp_ = C.c_int()
         check(lib().drops_b200_matrix_format(self.h, C.byref(ns), C.byref(pn), C.byref(cmp_), C.byref(ws)))
         return {"nslices": ns.value, "padded_nnz": pn.value, "compressed": bool(cmp_.value), "wide_slices": ws.value}
+
+    def value_dictionary(self, transposed=False):
+        nd, pk, cb = C.c_int(), C.c_int(), C.c_int()
+        check(lib().drops_b200_matrix_value_dictionary(self.h, int(transposed), C.byref(nd), C.byref(pk), C.byref(cb)))
+        return {"n_distinct": nd.value, "packed": bool(pk.value), "column_bits": cb.value}
 
     def download(self):
         rb = np.zeros(self.rows + 1, np.uint64)

@@ -313,6 +313,16 @@ struct SellOp {
     int32_t* cbase = nullptr;        // padded/32 entries
     uint8_t* wide = nullptr;         // nslices flags
     size_t nwide = 0;
+    // Value dictionary ("sell.valdict"): constant-coefficient systems on uniform meshes hold a handful
+    // of distinct fp64 values (15 on the P2 Kuhn brick).  When the matrix has at most 65535 distinct
+    // bit patterns, `dict` lists them (sorted by bit pattern) and every stored entry becomes one
+    // 32-bit word  pk = (dict index << cbits) | column  (padding: index ndict = 0.0, column 0) -- lossless, so the
+    // product stays bit-identical, at 4 instead of 12 bytes per entry on the stream that bounds
+    // the kernel.  pk is nullptr when column bits + index bits do not fit 32 (then col/val are used).
+    uint32_t* pk = nullptr;          // padded entries
+    double* dict = nullptr;          // ndict distinct values + one 0.0 (the padding slot)
+    int ndict = 0;
+    int cbits = 0;                   // low bits of pk that hold the column
 };
 
 struct CsrDev {
@@ -368,4 +378,6 @@ void free_sell(SellOp& s);
 void free_csr(CsrDev& c);
 int build_transpose(drops_b200_matrix_s* M);
 int build_sell(const CsrDev& A, SellOp& S, size_t* bytes, const int32_t* rowmap, size_t nsub);
+// (re)builds S.dict / S.pk from S.col / S.val; leaves them null when the matrix does not qualify
+int build_value_dictionary(SellOp& S, size_t* bytes);
 }  // namespace db200

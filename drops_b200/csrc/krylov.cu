@@ -113,10 +113,23 @@ int pcg_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, doubl
         DB_CUDA(cudaEventRecord(ev[slot], st));
         return 0;
     };
+    // "pcg.fused_dot" = 0: q = A p and p.q as two kernels (the dot re-reads p and q from HBM);
+    // "pcg.defer_x" = 1: x += alpha p moves into the direction kernel (10 instead of 11 vector passes)
+    const bool fused_dot = opt("pcg.fused_dot", 1.0) != 0.0;
+    const bool defer_x = !unpreconditioned_cg && opt("pcg.defer_x", 1.0) != 0.0 && opt("vec.wide", 1.0) != 0.0 &&
+                         ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(r) |
+                           reinterpret_cast<uintptr_t>(M->diag)) & 15u) == 0;
     auto one_iteration = [&]() -> int {
         SpmvArgs s;
-        s.x = p; s.y = q; s.dotv = p; s.dot_out = &S->lambda; s.done = &S->done;   // q = A p, lambda = q.p  :149-151
+        s.x = p; s.y = q; s.done = &S->done;                                       // q = A p, lambda = q.p  :149-151
+        if (fused_dot) { s.dotv = p; s.dot_out = &S->lambda; }
         DB_CHECK(spmv_apply(M, false, s));
+        if (!fused_dot) DB_CHECK(vec_dot_unless(n, q, p, &S->lambda, &S->done));
+        if (defer_x) {
+            DB_CHECK(pcg_update_r(n, r, q, M->diag, S, dh));
+            DB_CHECK(pcg_direction_x(n, x, p, r, M->diag, S));
+            return 0;
+        }
         DB_CHECK(unpreconditioned_cg ? cg_update(n, x, r, p, q, S, dh) : pcg_update(n, x, r, p, q, M->diag, S, dh));
         DB_CHECK(unpreconditioned_cg ? cg_direction(n, p, r, S) : pcg_direction(n, p, r, M->diag, S));
         return 0;

@@ -125,6 +125,71 @@ __global__ void k_sell_fill(long long nslices, const int64_t* __restrict__ slice
     }
 }
 
+
+// ---- value dictionary -----------------------------------------------------------------------
+// Distinct bit patterns of the stored values, collected in an open-addressing hash set.  Lanes of
+// a warp that hold the same pattern elect one leader; a slot that already holds the key costs one
+// cached read and no atomic, so the pass runs at the speed of reading `val` once.
+constexpr unsigned long long kDictEmpty = ~0ULL;          // (a NaN payload; a matrix holding it is not compressed)
+constexpr int kDictTableBits = 17;
+constexpr int kDictMax = 65535;
+
+__device__ __forceinline__ unsigned dict_hash(unsigned long long k)
+{
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+    return (unsigned)k & ((1u << kDictTableBits) - 1u);
+}
+
+__global__ void __launch_bounds__(256)
+k_dict_collect(long long n, const int32_t* __restrict__ col, const double* __restrict__ val,
+               unsigned long long* table, int* count)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < n; i0 += stride) {
+        int over = 0;                                                 // too many: give up early (warp-uniform)
+        if ((threadIdx.x & 31) == 0) over = *(volatile int*)count > kDictMax;
+        if (__shfl_sync(0xffffffffu, over, 0)) return;
+        const long long i = i0 + threadIdx.x;
+        const bool live = i < n && __ldcs(col + i) >= 0;               // padding holds no value
+        const unsigned long long key = live ? (unsigned long long)__double_as_longlong(__ldcs(val + i)) : 0ULL;
+        const unsigned act = __ballot_sync(0xffffffffu, live);
+        if (!live) continue;
+        const unsigned same = __match_any_sync(act, key);
+        if ((threadIdx.x & 31) != __ffs(same) - 1) continue;           // not the leader of its value
+        if (key == kDictEmpty) { atomicAdd(count, kDictMax + 1); continue; }
+        unsigned slot = dict_hash(key);
+        for (int probe = 0; probe < (1 << kDictTableBits); ++probe) {
+            unsigned long long cur = *(volatile unsigned long long*)(table + slot);
+            if (cur == key) break;
+            if (cur == kDictEmpty) {
+                cur = atomicCAS(table + slot, kDictEmpty, key);
+                if (cur == kDictEmpty) { atomicAdd(count, 1); break; }
+                if (cur == key) break;
+            }
+            slot = (slot + 1) & ((1u << kDictTableBits) - 1u);
+        }
+    }
+}
+
+// pk = (index of val in the sorted dictionary << cbits) | col; padding = (ndict << cbits), i.e. column 0
+// and the extra dictionary slot that holds 0.0 (spmv_pk.cu drops the padded product with a select).
+__global__ void __launch_bounds__(256)
+k_dict_pack(long long n, const int32_t* __restrict__ col, const double* __restrict__ val,
+            const unsigned long long* __restrict__ keys, int ndict, int cbits, uint32_t* __restrict__ pk)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t c = __ldcs(col + i);
+    if (c < 0) { pk[i] = (uint32_t)ndict << cbits; return; }
+    const unsigned long long key = (unsigned long long)__double_as_longlong(__ldcs(val + i));
+    int lo = 0, hi = ndict;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(keys + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    pk[i] = ((uint32_t)lo << cbits) | (uint32_t)c;
+}
+
 // One warp per slice: column base per slice entry (minimum over the 32 rows) + 16-bit deltas.
 __global__ void k_sell_compress(long long nslices, const int64_t* __restrict__ slice_ptr,
                                 const int32_t* __restrict__ scol, uint16_t* __restrict__ col16,
@@ -291,6 +356,7 @@ void free_sell(SellOp& s)
 {
     dev_free(s.slice_ptr); dev_free(s.col); dev_free(s.val); dev_free(s.perm);
     dev_free(s.col16); dev_free(s.cbase); dev_free(s.wide);
+    dev_free(s.pk); dev_free(s.dict);
     s = SellOp();
 }
 
@@ -380,7 +446,82 @@ int build_sell(const CsrDev& A, SellOp& S, size_t* bytes, const int32_t* rowmap,
         else col_bytes += S.padded * 4;
     }
     if (bytes) *bytes += S.padded * 8 + col_bytes + (S.nslices + 1) * 8 + padded_rows * 4;
-    return 0;
+    return build_value_dictionary(S, bytes);
+}
+
+static int bits_for(unsigned long long count)      // bits that distinguish `count` codes 0..count-1
+{
+    int b = 0;
+    while ((1ULL << b) < count) ++b;
+    return b;
+}
+
+int build_value_dictionary(SellOp& S, size_t* bytes)
+{
+    cudaStream_t st = ctx().stream;
+    dev_free(S.pk); dev_free(S.dict);
+    S.pk = nullptr; S.dict = nullptr; S.ndict = 0; S.cbits = 0;
+    if (S.padded == 0 || S.col == nullptr || S.val == nullptr || opt("sell.valdict", 1.0) == 0.0) return 0;
+    const int cbits = std::max(1, bits_for((unsigned long long)std::max<size_t>(S.cols, 1)));
+    if (cbits > 31) return 0;
+    unsigned long long* table = nullptr; int* d_count = nullptr;
+    const size_t cap = (size_t)1 << kDictTableBits;
+    DB_CHECK(dev_alloc(&table, cap));
+    if (dev_alloc(&d_count, 1) < 0) { dev_free(table); return DROPS_B200_E_NOMEM; }
+    int status = 0, count = 0;
+    std::vector<unsigned long long> keys;
+    auto fail = [&](cudaError_t e, const char* what) { status = cuda_fail(e, what, __FILE__, __LINE__); };
+    cudaError_t e = cudaMemsetAsync(table, 0xff, cap * sizeof(unsigned long long), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_count, 0, sizeof(int), st);
+    if (e == cudaSuccess) {
+        const int grid = (int)std::min<long long>(((long long)S.padded + 255) / 256, (long long)ctx().sm_count * 16);
+        k_dict_collect<<<grid, 256, 0, st>>>((long long)S.padded, S.col, S.val, table, d_count);
+        count_launch();
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&count, d_count, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) fail(e, "value dictionary: collect");
+    // index field: one code more than ndict -- slot ndict (0.0) belongs to the padding word
+    if (status == 0 && count >= 1 && count <= kDictMax && cbits + bits_for((unsigned long long)count + 1) <= 32) {
+        std::vector<unsigned long long> host(cap);
+        e = cudaMemcpyAsync(host.data(), table, cap * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) fail(e, "value dictionary: download");
+        else {
+            for (unsigned long long k : host) if (k != kDictEmpty) keys.push_back(k);
+            std::sort(keys.begin(), keys.end());
+            if ((int)keys.size() != count) { set_error("value dictionary: %zu keys in the table, %d counted", keys.size(), count); status = DROPS_B200_E_CUDA; }
+        }
+    } else count = 0;
+    dev_free(d_count);
+    if (status == 0 && count > 0) {
+        // the hash table's storage doubles as the sorted key list for the packing pass
+        e = cudaMemcpyAsync(table, keys.data(), keys.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) fail(e, "value dictionary: upload");
+        std::vector<double> dict_host(keys.size() + 1, 0.0);
+        std::memcpy(dict_host.data(), keys.data(), keys.size() * sizeof(double));
+        if (status == 0) status = dev_alloc(&S.dict, dict_host.size());
+        if (status == 0) status = dev_alloc(&S.pk, S.padded);
+        if (status == 0) {
+            e = cudaMemcpyAsync(S.dict, dict_host.data(), dict_host.size() * sizeof(double), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) {
+                k_dict_pack<<<blocks_for((long long)S.padded, 256), 256, 0, st>>>((long long)S.padded, S.col, S.val, table, count, cbits, S.pk);
+                count_launch();
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) fail(e, "value dictionary: pack");
+        }
+        if (status == 0) {
+            S.ndict = count; S.cbits = cbits;
+            if (bytes) *bytes += S.padded * 4 + keys.size() * 8;
+        } else {
+            dev_free(S.pk); dev_free(S.dict); S.pk = nullptr; S.dict = nullptr;
+        }
+    }
+    dev_free(table);
+    return status;
 }
 
 int refill_sell_values(const CsrDev& A, SellOp& S)
@@ -391,7 +532,7 @@ int refill_sell_values(const CsrDev& A, SellOp& S)
         (long long)S.nslices, S.slice_ptr, S.perm, A.rowptr, A.val, S.val);
     count_launch();
     DB_CUDA(cudaGetLastError());
-    return 0;
+    return build_value_dictionary(S, nullptr);      // new values, new dictionary
 }
 
 int extract_diag(drops_b200_matrix_s* M)
@@ -685,6 +826,17 @@ int drops_b200_matrix_info(drops_b200_matrix_t M, size_t* rows, size_t* cols, si
     if (version) *version = M->version;
     if (device_bytes) *device_bytes = M->device_bytes;
     if (padded_nnz) *padded_nnz = M->sell.padded;
+    return 0;
+}
+
+int drops_b200_matrix_value_dictionary(drops_b200_matrix_t M, int transposed, int* n_distinct, int* packed,
+                                       int* column_bits)
+{
+    DB_ARG(M != nullptr, "null matrix");
+    const SellOp& S = transposed ? M->sell_t : M->sell;
+    if (n_distinct) *n_distinct = S.ndict;
+    if (packed) *packed = S.pk != nullptr;
+    if (column_bits) *column_bits = S.cbits;
     return 0;
 }
 

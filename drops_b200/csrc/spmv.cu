@@ -284,6 +284,8 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a)
     DB_ARG(a.epilogue == EPI_NONE || a.aux != nullptr, "epilogue needs aux vector");
     DB_ARG(a.dotv == nullptr || a.dot_out != nullptr || a.dd_out != nullptr, "fused dot needs an output scalar");
     if (A.rows == 0) return 0;
+    // dictionary-packed stream (4 B per entry, spmv_pk.cu) when the operator has one
+    if (A.pk != nullptr && a.xghost == nullptr && opt("spmv.pk", 1.0) != 0.0) return spmv_sell_pk(A, a);
     int threads = (int)opt("spmv.threads", 128);
     if (threads < 32) threads = 32;
     if (threads > 512) threads = 512;

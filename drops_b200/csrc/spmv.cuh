@@ -39,6 +39,9 @@ struct SpmvArgs {
 // y = A x through the sliced-ELL operator (exact reference summation order unless option
 // "spmv.exact" is 0, in which case FMA is used).
 int spmv_sell(const SellOp& A, const SpmvArgs& a);
+// Same operator on its dictionary-packed stream (SellOp::pk, 4 B per entry; spmv_pk.cu); spmv_sell
+// dispatches to it when the operator has one and option "spmv.pk" is not 0.
+int spmv_sell_pk(const SellOp& A, const SpmvArgs& a);
 // Same operator, matrix stream staged through shared memory with TMA bulk copies (spmv_tma.cu).
 int spmv_sell_tma(const SellOp& A, const SpmvArgs& a);
 int spmv_tma_fault();

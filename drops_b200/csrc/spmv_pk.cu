@@ -1,0 +1,246 @@
+// spmv_pk.cu -- y = A x on the dictionary-packed sliced-ELL stream (SellOp::pk, common.cuh).
+//
+// Same operator, same slices, same per-row left-to-right summation as k_spmv_sell (spmv.cu), but
+// every stored entry is ONE 32-bit word  (dict index << cbits) | column : 4 bytes instead of 12 on
+// the stream that bounds the kernel.  The dictionary holds the matrix' distinct fp64 bit patterns,
+// so a_ij is recovered exactly and y stays bit-identical to y_Ax (num/spmat.h:1682-1709).  It
+// applies to constant-coefficient systems on uniform meshes (the Poisson configs: 15 distinct
+// values on the P2 Kuhn brick, 3 on P1); matrices that do not qualify have no pk and run spmv.cu.
+//   * one coalesced 128 B load per entry-row of a warp, U of them in flight per thread before the
+//     first gather -- at one register per staged entry (three in the 12-byte format);
+//   * the dictionary sits in shared memory (<= kPkDictSmem values, copied by every CTA at start) or
+//     is read through the read-only L1 path; lanes of a slice hold neighbouring rows of the same
+//     stencil, so a lookup is mostly one broadcast wavefront;
+//   * x through ld.global.nc; epilogues and the fused dot exactly as in spmv.cu.
+#include "spmv_impl.cuh"
+
+namespace db200 {
+
+constexpr int kPkDictSmem = 512;
+
+struct PkView {
+    const int64_t* slice_ptr;
+    const uint32_t* pk;
+    const double* dict;
+    const int32_t* perm;
+    long long nslices;
+    int ndict;
+    int cbits;
+};
+
+// Padding is the word (ndict << cbits): column 0 and the extra dictionary slot ndict (0.0), so every
+// load of the unrolled body is unconditional and straight-line; the padded product is computed and
+// then dropped by a select (adding it could turn a -0.0 sum into +0.0, or poison it when x_0 is
+// not finite), which keeps the row sum bit-identical.
+template <bool EXACT, int U, bool SMEM>
+__device__ __forceinline__ double pk_row_sum(const PkView& A, int64_t base, int width, int lane,
+                                             const double* __restrict__ x)
+{
+    extern __shared__ double sdict[];      // the CTA's copy of the dictionary (SMEM)
+    const uint32_t* pp = A.pk + base + lane;
+    const int cbits = A.cbits;
+    const uint32_t cmask = (1u << cbits) - 1u;
+    const uint32_t wpad = (uint32_t)A.ndict << cbits;
+    double sum = 0.0;
+    int j = 0;
+    for (; j + U <= width; j += U) {
+        uint32_t w[U];
+        double xv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) w[u] = __ldcs(pp + (size_t)(j + u) * 32);
+#pragma unroll
+        for (int u = 0; u < U; ++u) xv[u] = __ldg(x + (w[u] & cmask));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double v = SMEM ? sdict[w[u] >> cbits] : __ldg(A.dict + (w[u] >> cbits));
+            const double t = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv[u])) : fma(v, xv[u], sum);
+            sum = w[u] < wpad ? t : sum;
+        }
+    }
+    for (; j < width; ++j) {
+        const uint32_t w = __ldcs(pp + (size_t)j * 32);
+        const double xv = __ldg(x + (w & cmask));
+        const double v = SMEM ? sdict[w >> cbits] : __ldg(A.dict + (w >> cbits));
+        const double t = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv)) : fma(v, xv, sum);
+        sum = w < wpad ? t : sum;
+    }
+    return sum;
+}
+
+// DOT as in k_spmv_sell: 0 none, 1 finished in this kernel, 2 per-warp partials + finishing kernel.
+// DF, the form of the fused dot (same per-thread order of the same products: bit-identical results):
+//   0 = in the slice loop, partner fetched at slice start, accumulator in registers -- at <= 40
+//       registers the compiler can then no longer keep the U loads of the row sum in flight
+//       (2.2 instead of 1.5 ms at C2);
+//   1 = a second pass over the warp's own slices (y_i re-read from L2, the partner from L1);
+//   2 = in the slice loop, but the partner is fetched AFTER the row sum (an L1 hit: the diagonal
+//       entry just gathered it) and the accumulator is parked in shared memory between slices, so
+//       the row sum runs with the registers of the plain product.
+template <int EPI, bool EXACT, int DOT, int U, int MAXT, int MINB, bool SMEM, int DF>
+__global__ void __launch_bounds__(MAXT, MINB)
+k_spmv_sell_pk(PkView A, const double* __restrict__ x, double* __restrict__ y, EpiArgs e)
+{
+    if (e.done != nullptr && *e.done != 0) return;
+    extern __shared__ double sdict[];
+    __shared__ dd red_smem[DOT == 1 ? 32 : 1];
+    __shared__ dd acc_smem[(DOT != 0 && DF == 2) ? MAXT : 1];
+    if (DOT != 0 && DF == 2) acc_smem[threadIdx.x] = dd_zero();     // the thread's own slot: no barrier needed
+    if (SMEM) {
+        for (int i = threadIdx.x; i <= A.ndict; i += blockDim.x) sdict[i] = A.dict[i];
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const long long s_begin = A.nslices * (long long)blockIdx.x / gridDim.x;
+    const long long s_end   = A.nslices * (long long)(blockIdx.x + 1) / gridDim.x;
+    const double beta = (EPI == EPI_AXMBY) ? (e.beta != nullptr ? *e.beta : e.beta_val) : 0.0;
+    dd acc[1] = {dd_zero()};
+
+    for (long long s = s_begin + warp; s < s_end; s += nwarp) {
+        const int64_t base = A.slice_ptr[s];
+        const int width = (int)((A.slice_ptr[s + 1] - base) >> 5);
+        const int row = A.perm[s * 32 + lane];
+        double dv = 0.0, av = 0.0;
+        if (row >= 0) {
+            if (DOT && DF == 0) dv = __ldg(e.dotv + row);
+            if (EPI != EPI_NONE) av = __ldg(e.aux + row);
+        }
+        const double sum = pk_row_sum<EXACT, U, SMEM>(A, base, width, lane, x);
+        if (row >= 0) {
+            const double out = apply_epilogue<EPI>(sum, av, e, beta);
+            y[row] = out;
+            if (DOT && DF == 0) acc[0] = dd_add_prod(acc[0], out, dv);
+            if (DOT && DF == 2) acc_smem[threadIdx.x] = dd_add_prod(acc_smem[threadIdx.x], out, __ldg(e.dotv + row));
+        }
+    }
+    if (DOT && DF == 2) acc[0] = acc_smem[threadIdx.x];
+    if (DOT && DF == 1) {
+        for (long long s = s_begin + warp; s < s_end; s += nwarp) {
+            const int row = A.perm[s * 32 + lane];
+            if (row >= 0) acc[0] = dd_add_prod(acc[0], __ldcg(y + row), __ldg(e.dotv + row));
+        }
+    }
+    if (DOT == 1) {
+        if (grid_reduce_dd<1>(acc, red_smem, e.partials, e.ticket)) {
+            if (threadIdx.x == 0) store_dot(e, acc[0]);
+        }
+    }
+    if (DOT == 2) {
+        const dd w = warp_reduce_dd(acc[0]);
+        if (lane == 0) e.partials[(size_t)blockIdx.x * nwarp + warp] = w;
+    }
+}
+
+template <int EPI, bool EXACT, int U, int MAXT, int MINB, bool SMEM, int DF>
+static void launch_pk_d(const PkView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads, cudaStream_t st)
+{
+    if (threads > MAXT) threads = MAXT;
+    const size_t sh = SMEM ? ((size_t)v.ndict + 1) * sizeof(double) : 0;
+    if (a.dotv == nullptr) {
+        k_spmv_sell_pk<EPI, EXACT, 0, U, MAXT, MINB, SMEM, 0><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
+        return;
+    }
+    const long long nwarps = (long long)grid * (threads >> 5);
+    const double mode = opt("spmv.dotmode", 0.0);
+    const bool two_kernels = mode == 2.0 || (mode == 0.0 && grid > (int)kReduceFlat);
+    if (two_kernels && nwarps <= kPartialStride) {
+        k_spmv_sell_pk<EPI, EXACT, 2, U, MAXT, MINB, SMEM, DF><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
+        sum_warp_partials(nwarps, e, st);
+    } else {
+        k_spmv_sell_pk<EPI, EXACT, 1, U, MAXT, MINB, SMEM, DF><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
+    }
+}
+
+template <int EPI, bool EXACT, int U, int MAXT, int MINB, bool BOTH_DICTS>
+static void launch_pk_v(const PkView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads, cudaStream_t st)
+{
+    const bool smem = v.ndict <= kPkDictSmem && opt("spmv.pkdict", 0.0) == 0.0;
+    const int df = a.dotv != nullptr ? (int)opt("spmv.pkdotform", 2.0) : 0;
+    if constexpr (BOTH_DICTS) {
+        if (!smem) { launch_pk_d<EPI, EXACT, U, MAXT, MINB, false, 2>(v, a, e, grid, threads, st); return; }
+    }
+    if (df == 1) launch_pk_d<EPI, EXACT, U, MAXT, MINB, true, 1>(v, a, e, grid, threads, st);
+    else if (df == 0) launch_pk_d<EPI, EXACT, U, MAXT, MINB, true, 0>(v, a, e, grid, threads, st);
+    else launch_pk_d<EPI, EXACT, U, MAXT, MINB, true, 2>(v, a, e, grid, threads, st);
+}
+
+// "spmv.pkvariant" (plain product) / "spmv.pkdotvariant" (fused dot): unroll x register cap.
+//   0 = U8/<=40 regs, 1 = U8/<=48, 2 = U4/<=32, 3 = U16/<=64, 4 = U16/<=48, 5 = U8/256 threads/<=40,
+//   6 = U12/<=48, 7 = U4/<=40, 8 = U8/CTAs up to 1024 threads/<=64, 9 = U8/<=512 threads/<=40,
+//   10 = U16/<=512 threads/<=64
+constexpr int kPkDefaultVariant = 0;
+
+template <int EPI, bool EXACT>
+static bool launch_pk(const PkView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads, cudaStream_t st)
+{
+    const bool smem_ok = v.ndict <= kPkDictSmem && opt("spmv.pkdict", 0.0) == 0.0;
+    const int variant = (int)(a.dotv != nullptr ? opt("spmv.pkdotvariant", (double)kPkDefaultVariant)
+                                                : opt("spmv.pkvariant", (double)kPkDefaultVariant));
+    if (EPI == EPI_NONE && EXACT && smem_ok) {
+        switch (variant) {
+            case 1: launch_pk_v<EPI_NONE, true, 8, 128, 10, false>(v, a, e, grid, threads, st); return true;
+            case 2: launch_pk_v<EPI_NONE, true, 4, 128, 16, false>(v, a, e, grid, threads, st); return true;
+            case 3: launch_pk_v<EPI_NONE, true, 16, 128, 8, false>(v, a, e, grid, threads, st); return true;
+            case 4: launch_pk_v<EPI_NONE, true, 16, 128, 10, false>(v, a, e, grid, threads, st); return true;
+            case 5: launch_pk_v<EPI_NONE, true, 8, 256, 6, false>(v, a, e, grid, threads, st); return true;
+            case 6: launch_pk_v<EPI_NONE, true, 12, 128, 10, false>(v, a, e, grid, threads, st); return true;
+            case 7: launch_pk_v<EPI_NONE, true, 4, 128, 12, false>(v, a, e, grid, threads, st); return true;
+            case 8: launch_pk_v<EPI_NONE, true, 8, 1024, 1, false>(v, a, e, grid, threads, st); return true;
+            case 9: launch_pk_v<EPI_NONE, true, 8, 512, 3, false>(v, a, e, grid, threads, st); return true;
+            case 10: launch_pk_v<EPI_NONE, true, 16, 512, 2, false>(v, a, e, grid, threads, st); return true;
+            default: break;
+        }
+    }
+    launch_pk_v<EPI, EXACT, 8, 128, 12, true>(v, a, e, grid, threads, st);
+    return true;
+}
+
+template <bool EXACT>
+static void launch_pk_epi(const PkView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads, cudaStream_t st)
+{
+    switch (a.epilogue) {
+        case EPI_JACOBI: launch_pk<EPI_JACOBI, EXACT>(v, a, e, grid, threads, st); break;
+        case EPI_RESID:  launch_pk<EPI_RESID, EXACT>(v, a, e, grid, threads, st); break;
+        case EPI_AXMBY:  launch_pk<EPI_AXMBY, EXACT>(v, a, e, grid, threads, st); break;
+        default:         launch_pk<EPI_NONE, EXACT>(v, a, e, grid, threads, st); break;
+    }
+}
+
+int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
+{
+    Ctx& c = ctx();
+    DB_ARG(A.pk != nullptr && A.dict != nullptr, "operator holds no packed stream");
+    DB_ARG(a.x != nullptr && a.y != nullptr, "null vector");
+    DB_ARG(a.x != a.y, "x and y must not alias");
+    DB_ARG(a.xghost == nullptr, "the packed stream has no split-x form");
+    DB_ARG(a.epilogue == EPI_NONE || a.aux != nullptr, "epilogue needs aux vector");
+    DB_ARG(a.dotv == nullptr || a.dot_out != nullptr || a.dd_out != nullptr, "fused dot needs an output scalar");
+    DB_ARG(a.dotv != a.y, "the partner of the fused dot must not be the output vector");   // the tail pass re-reads y
+    if (A.rows == 0) return 0;
+    int threads = (int)opt("spmv.pk_threads", 128);
+    if (threads < 32) threads = 32;
+    if (threads > 1024) threads = 1024;
+    threads &= ~31;
+    // same decomposition as spmv_sell: CTAs own consecutive slices and are launched in matrix order
+    const double per_sm = opt("spmv.ctas_per_sm", 0.0);
+    long long grid;
+    if (per_sm > 0.0) grid = (long long)(per_sm * c.sm_count + 0.5);
+    else {
+        long long spc = (long long)opt("spmv.pk_slices_per_cta", 16.0);
+        if (spc < 1) spc = 1;
+        grid = ((long long)A.nslices + spc - 1) / spc;
+    }
+    const long long max_useful = ((long long)A.nslices * 32 + threads - 1) / threads;
+    if (grid > max_useful) grid = max_useful;
+    if (grid > kMaxReduceGrid) grid = kMaxReduceGrid;
+    if (grid < 1) grid = 1;
+    cudaStream_t st = a.stream ? a.stream : c.stream;
+    PkView v{A.slice_ptr, A.pk, A.dict, A.perm, (long long)A.nslices, A.ndict, A.cbits};
+    EpiArgs e = make_epi(a);
+    if (opt("spmv.exact", 1.0) != 0.0) launch_pk_epi<true>(v, a, e, (int)grid, threads, st);
+    else launch_pk_epi<false>(v, a, e, (int)grid, threads, st);
+    count_launch();
+    DB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace db200

@@ -71,6 +71,16 @@ int vec_dot(size_t n, const double* x, const double* y, double* d_out)
 {
     return launch_stream<1>(n, OpDot{x, y, d_out}, "vec");
 }
+struct OpDotUnless {
+    const double* x; const double* y; double* out; const int* done;
+    __device__ bool begin() { return *done == 0; }
+    __device__ void elem(size_t i, dd* acc) { acc[0] = dd_add_prod(acc[0], x[i], y[i]); }
+    __device__ void finish(const dd* acc) { *out = dd_round(acc[0]); }
+};
+int vec_dot_unless(size_t n, const double* x, const double* y, double* d_out, const int* done)
+{
+    return launch_stream<1>(n, OpDotUnless{x, y, d_out, done}, "vec");
+}
 struct OpDotPartial {
     const double* x; const double* y; dd* out;
     __device__ bool begin() { return true; }
@@ -363,6 +373,136 @@ int pcg_direction(size_t n, double* p, const double* r, const double* d, SolverS
         return 0;
     }
     return launch_stream<0>(n, OpPcgDirection{p, r, d, S, 0.0, 0, 1.0}, "pcg.direction");
+}
+
+// ---- deferred x update: 4 + 6 vector passes instead of 7 + 4 ---------------------------------------
+struct OpPcgUpdateR {
+    double* r; const double* q; const double* d; SolverScalars* S; double* hist;
+    double alpha; int pc; double omega;
+    __device__ bool begin()
+    {
+        if (S->done) return false;
+        alpha = dvd(S->rho, S->lambda);                         // :152
+        pc = S->pc; omega = S->omega;
+        return true;
+    }
+    __device__ void elem(size_t i, dd* acc)
+    {
+        const double ri = add(r[i], mul(-alpha, q[i]));         // :155
+        r[i] = ri;
+        const double z = precond(pc, omega, ri, d, i);          // :170
+        acc[0] = dd_add_prod(acc[0], ri, ri);                   // :158
+        acc[1] = dd_add_prod(acc[1], z, ri);                    // :172
+    }
+    __device__ void finish(const dd* acc) { pcg_update_finish(S, hist, dd_round(acc[0]), dd_round(acc[1])); }
+};
+
+__global__ void __launch_bounds__(kReduceThreads)
+k_pcg_update_r(size_t n, double* __restrict__ r, const double* __restrict__ q, const double* __restrict__ d,
+               SolverScalars* S, double* hist, dd* partials, unsigned* ticket)
+{
+    __shared__ dd red_smem[2 * 32];
+    OpPcgUpdateR op{r, q, d, S, hist, 0.0, 0, 1.0};
+    if (!op.begin()) return;
+    const double alpha = op.alpha, omega = op.omega;
+    const bool jac = op.pc == DROPS_B200_PC_JACOBI;
+    dd acc[2] = {dd_zero(), dd_zero()};
+    const size_t n2 = n >> 1;
+    double2* r2 = reinterpret_cast<double2*>(r);
+    const double2* q2 = reinterpret_cast<const double2*>(q);
+    const double2* d2 = reinterpret_cast<const double2*>(d);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        double2 rv = r2[i];
+        const double2 qv = __ldcs(q2 + i);                      // q is dead after this kernel
+        double2 dv = make_double2(1.0, 1.0);
+        if (jac) dv = d2[i];
+        rv.x = add(rv.x, mul(-alpha, qv.x)); rv.y = add(rv.y, mul(-alpha, qv.y));
+        r2[i] = rv;
+        const double zx = jac ? dvd(mul(omega, rv.x), dv.x) : rv.x;
+        const double zy = jac ? dvd(mul(omega, rv.y), dv.y) : rv.y;
+        acc[0] = dd_add_prod(acc[0], rv.x, rv.x); acc[0] = dd_add_prod(acc[0], rv.y, rv.y);
+        acc[1] = dd_add_prod(acc[1], zx, rv.x);   acc[1] = dd_add_prod(acc[1], zy, rv.y);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) op.elem(n - 1, acc);
+    if (grid_reduce_dd<2>(acc, red_smem, partials, ticket)) {
+        if (threadIdx.x == 0) op.finish(acc);
+    }
+}
+
+int pcg_update_r(size_t n, double* r, const double* q, const double* d, SolverScalars* S, double* hist)
+{
+    if (opt("vec.wide", 1.0) != 0.0 && aligned16(r, q, d)) {
+        Ctx& c = ctx();
+        ScopedTiming t("pcg.update");
+        const int grid = vec_grid(n, kReduceThreads, 4);
+        k_pcg_update_r<<<grid, kReduceThreads, 0, c.stream>>>(n, r, q, d, S, hist, c.partials, c.tickets);
+        count_launch();
+        DB_CUDA(cudaGetLastError());
+        return 0;
+    }
+    return launch_stream<2>(n, OpPcgUpdateR{r, q, d, S, hist, 0.0, 0, 1.0}, "pcg.update");
+}
+
+// x += alpha p for the iteration pcg_update_r just completed (S->iter counts it, S->x_iter does not
+// yet); then, unless that iteration ended the solve, p = z + beta p.  After the rotation in
+// pcg_update_finish the iteration's rho sits in rho_1, so alpha = rho_1 / lambda is the quotient the
+// update kernel used (:152).  The block that finishes last marks the x update as applied; kernels of
+// iterations that are skipped after the stop see x_iter == iter and do nothing.
+__global__ void __launch_bounds__(kReduceThreads)
+k_pcg_direction_x(size_t n, double* __restrict__ x, double* __restrict__ p, const double* __restrict__ r,
+                  const double* __restrict__ d, SolverScalars* S, unsigned* ticket)
+{
+    const int it = S->iter;
+    if (S->x_iter == it) return;
+    const bool more = S->done == 0;
+    const double alpha = dvd(S->rho_1, S->lambda);
+    const double beta = more ? dvd(S->rho, S->rho_1) : 0.0;     // :173
+    const double omega = S->omega;
+    const bool jac = S->pc == DROPS_B200_PC_JACOBI;
+    const size_t n2 = n >> 1;
+    double2* x2 = reinterpret_cast<double2*>(x);
+    double2* p2 = reinterpret_cast<double2*>(p);
+    const double2* r2 = reinterpret_cast<const double2*>(r);
+    const double2* d2 = reinterpret_cast<const double2*>(d);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        double2 xv = x2[i], pv = p2[i];
+        xv.x = add(xv.x, mul(alpha, pv.x)); xv.y = add(xv.y, mul(alpha, pv.y));   // :154
+        x2[i] = xv;
+        if (more) {
+            const double2 rv = r2[i];
+            double2 dv = make_double2(1.0, 1.0);
+            if (jac) dv = d2[i];
+            const double zx = jac ? dvd(mul(omega, rv.x), dv.x) : rv.x;
+            const double zy = jac ? dvd(mul(omega, rv.y), dv.y) : rv.y;
+            pv.x = add(zx, mul(beta, pv.x)); pv.y = add(zy, mul(beta, pv.y));     // :174
+            p2[i] = pv;
+        }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const size_t i = n - 1;
+        const double pi = p[i];
+        x[i] = add(x[i], mul(alpha, pi));
+        if (more) p[i] = add(precond(S->pc, omega, r[i], d, i), mul(beta, pi));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) { S->x_iter = it; *ticket = 0u; }
+    }
+}
+
+int pcg_direction_x(size_t n, double* x, double* p, const double* r, const double* d, SolverScalars* S)
+{
+    Ctx& c = ctx();
+    DB_ARG(aligned16(x, p, r, d), "pcg_direction_x needs 16-byte aligned vectors");
+    ScopedTiming t("pcg.direction");
+    const int grid = vec_grid(n, kReduceThreads, 4);
+    k_pcg_direction_x<<<grid, kReduceThreads, 0, c.stream>>>(n, x, p, r, d, S, c.tickets + (size_t)2 * kTicketStride);
+    count_launch();
+    DB_CUDA(cudaGetLastError());
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------

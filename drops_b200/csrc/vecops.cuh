@@ -12,7 +12,8 @@ struct SolverScalars {
     double a1, b1, b0;           // Lanczos coefficients
     double h[2];                 // scratch
     double omega;
-    int iter, done, converged, relative, max_iter, pc, hist_cap, pad;
+    int iter, done, converged, relative, max_iter, pc, hist_cap;
+    int x_iter;                  // PCG with the deferred x update: iterations whose alpha*p is already in x
 };
 
 #ifdef __CUDACC__
@@ -68,6 +69,14 @@ int pcg_update(size_t n, double* x, double* r, const double* p, const double* q,
 int vec_dot_partial(size_t n, const double* x, const double* y, dd* part_out);
 // direction: p = M^-1 r + (rho/rho_1) p
 int pcg_direction(size_t n, double* p, const double* r, const double* d, SolverScalars* S);
+// The same iteration with the x update moved from the update into the direction kernel (10 instead of
+// 11 vector passes: p is read once): pcg_update_r does r -= alpha q, z, the two reductions and the
+// scalar bookkeeping; pcg_direction_x does x += alpha p for the iteration that just ran (also when it
+// was the last one) and then p = z + beta p unless the solve is done.  Element arithmetic unchanged.
+int pcg_update_r(size_t n, double* r, const double* q, const double* d, SolverScalars* S, double* hist);
+int pcg_direction_x(size_t n, double* x, double* p, const double* r, const double* d, SolverScalars* S);
+// dot product into a device scalar, skipped while *done != 0
+int vec_dot_unless(size_t n, const double* x, const double* y, double* d_out, const int* done);
 
 // ---- CG (num/krylovsolver.h:49-103) --------------------------------------------------------------
 int cg_setup(size_t n, const double* r, const double* b, double* dvec, SolverScalars* S, double* hist);

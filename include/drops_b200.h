@@ -120,6 +120,13 @@ DROPS_B200_API int drops_b200_matrix_info(drops_b200_matrix_t A, size_t* rows, s
  * 32-bit columns because their columns spread over more than 2^16. */
 DROPS_B200_API int drops_b200_matrix_format(drops_b200_matrix_t A, size_t* nslices, size_t* padded_nnz,
                                             int* compressed, size_t* wide_slices);
+/* Value dictionary of the sliced-ELL operator ("sell.valdict", default on): a matrix with at most
+ * 65535 distinct fp64 bit patterns whose column and dictionary-index bits fit 32 is ALSO stored as one
+ * 32-bit word per entry (lossless; products stay bit-identical).  n_distinct = 0 and packed = 0 when
+ * the matrix does not qualify; column_bits = low bits of a word that hold the column.  `transposed`
+ * != 0 asks about the A^T operator (0/0 until the first transp_mul built it). */
+DROPS_B200_API int drops_b200_matrix_value_dictionary(drops_b200_matrix_t A, int transposed, int* n_distinct,
+                                                      int* packed, int* column_bits);
 /* Copies the device CSR back in the reference layout (for tests and the CPU baseline). */
 DROPS_B200_API int drops_b200_matrix_download(drops_b200_matrix_t A, size_t* rowbeg, size_t* colind, double* val);
 

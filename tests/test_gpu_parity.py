@@ -69,6 +69,7 @@ def test_spmv_fast_modes_within_tolerance(gpu, kernel, lanes, exact):
 def test_spmv_layout_and_launch_options_do_not_change_results(gpu, sigma, threads, ctas, spc, variant, prefetch):
     g = load_golden("brick_fe2_N6_num1.npz")
     try:
+        gpu.set_option("spmv.pk", 0)       # the 12-byte stream; the packed one: test_value_dictionary_*
         gpu.set_option("sell.sigma", sigma)
         gpu.set_option("spmv.threads", threads)
         gpu.set_option("spmv.ctas_per_sm", ctas)
@@ -82,6 +83,7 @@ def test_spmv_layout_and_launch_options_do_not_change_results(gpu, sigma, thread
         out = A.pcg_jacobi(np.zeros(A.rows), g["b"], 400, 1e-10, True)
         assert out[1] == int(g["sym_pcgjac"][1]) and rel(out[3], g["sym_pcgjac_x"]) <= 1e-12
     finally:
+        gpu.set_option("spmv.pk", 1)
         gpu.set_option("sell.sigma", 4096)
         gpu.set_option("spmv.threads", 128)
         gpu.set_option("spmv.ctas_per_sm", 0)
@@ -89,6 +91,135 @@ def test_spmv_layout_and_launch_options_do_not_change_results(gpu, sigma, thread
         gpu.set_option("spmv.variant", 0)
         gpu.set_option("spmv.dotvariant", 8)
         gpu.set_option("spmv.prefetch", 0)
+
+
+PK_DEFAULTS = {"spmv.pk": 1, "spmv.pkdotform": 2, "spmv.pkvariant": 0, "spmv.pkdotvariant": 0, "spmv.pk_threads": 128,
+               "spmv.pk_slices_per_cta": 16, "spmv.pkdict": 0, "spmv.dotmode": 0, "sell.sigma": 4096,
+               "sell.valdict": 1, "spmv.exact": 1}
+
+
+def _restore_pk(gpu):
+    for k, v in PK_DEFAULTS.items():
+        gpu.set_option(k, v)
+
+
+def test_value_dictionary_qualifies_only_when_lossless_packing_fits(gpu):
+    """Brick systems hold a handful of distinct values and get the packed 4-byte stream; matrices with
+    too many distinct values, or whose column + index bits exceed 32, keep the 12-byte stream only."""
+    g = load_golden("brick_fe2_N6_num1.npz")
+    A = gmat(gpu, g)
+    d = A.value_dictionary()
+    assert d["packed"] and d["n_distinct"] == len(np.unique(g["val"].view(np.uint64)))
+    assert (1 << d["column_bits"]) >= A.cols
+    r = load_golden("random_ragged.npz")
+    R = gmat(gpu, r)
+    nd = len(np.unique(r["val"].view(np.uint64)))
+    assert R.value_dictionary()["packed"] == (nd <= 65535) and (not R.value_dictionary()["packed"] or R.value_dictionary()["n_distinct"] == nd)
+    # 70 000 distinct values: no dictionary
+    m = 70000
+    W = gpu.Matrix(m, m, np.arange(m + 1), np.arange(m), np.arange(1, m + 1, dtype=np.float64))
+    assert W.value_dictionary() == {"n_distinct": 0, "packed": False, "column_bits": 0}
+    xw = hash_vector(m)
+    assert np.array_equal(W.spmv(xw), np.arange(1, m + 1, dtype=np.float64) * xw)
+    # 2^20 columns (20 bits) and 5000 values (13 bits) do not fit one word together
+    cols = 1 << 20
+    rows = 5000
+    V = gpu.Matrix(rows, cols, np.arange(rows + 1), (np.arange(rows) * 209) % cols, np.arange(1, rows + 1) / 7.0)
+    assert not V.value_dictionary()["packed"]
+    try:
+        gpu.set_option("sell.valdict", 0)
+        assert not gmat(gpu, g).value_dictionary()["packed"]
+    finally:
+        _restore_pk(gpu)
+
+
+@pytest.mark.parametrize("variant,threads,spc,dictmode,dotmode,sigma",
+                         [(0, 128, 16, 0, 0, 4096), (1, 128, 1, 1, 1, 4096), (2, 64, 7, 0, 2, 64), (3, 128, 1000000, 0, 1, 0),
+                          (4, 32, 3, 0, 2, 512), (5, 256, 16, 0, 0, 4096), (6, 128, 2, 1, 2, 1024), (7, 96, 5, 0, 1, 128)])
+def test_value_dictionary_stream_is_bit_identical(gpu, variant, threads, spc, dictmode, dotmode, sigma):
+    """The packed stream reproduces every product, transpose product, fused dot and solve of the 12-byte
+    stream bit for bit, under every launch geometry."""
+    g = load_golden("brick_fe2_N6_num1.npz")
+    n, rb, ci, va = gpu.brick_csr_host(2, 14, 1)
+    xin = hash_vector(n)
+    try:
+        gpu.set_option("spmv.pk", 0)
+        B0 = gpu.Matrix(n, n, rb, ci, va)
+        y0, yt0 = B0.spmv(xin), B0.spmv_transpose(xin)
+        X, Y = gpu.Vector.from_host(xin), gpu.Vector(n)
+        d0 = B0.spmv_dot_dev(X, Y, X)
+        s0 = B0.pcg_jacobi(np.zeros(n), y0, 60, 1e-10, True)
+        gpu.set_option("spmv.pk", 1)
+        gpu.set_option("spmv.pkvariant", variant)
+        gpu.set_option("spmv.pkdotvariant", variant)
+        gpu.set_option("spmv.pk_threads", threads)
+        gpu.set_option("spmv.pk_slices_per_cta", spc)
+        gpu.set_option("spmv.pkdict", dictmode)
+        gpu.set_option("spmv.dotmode", dotmode)
+        gpu.set_option("spmv.pkdotform", variant % 3)
+        gpu.set_option("sell.sigma", sigma)
+        A = gmat(gpu, g)
+        assert A.value_dictionary()["packed"]
+        assert np.array_equal(A.spmv(g["x_in"]), g["y_Ax"])
+        assert np.array_equal(A.spmv_transpose(g["x_in"]), g["y_ATx"])
+        assert A.value_dictionary(transposed=True)["packed"]
+        out = A.pcg_jacobi(np.zeros(A.rows), g["b"], 400, 1e-10, True)
+        assert out[1] == int(g["sym_pcgjac"][1]) and rel(out[3], g["sym_pcgjac_x"]) <= 1e-12
+        B = gpu.Matrix(n, n, rb, ci, va)
+        assert np.array_equal(B.spmv(xin), y0) and np.array_equal(B.spmv_transpose(xin), yt0)
+        assert B.spmv_dot_dev(X, Y, X) == d0 and np.array_equal(Y.download(), y0)
+        s1 = B.pcg_jacobi(np.zeros(n), y0, 60, 1e-10, True)
+        assert s1[1] == s0[1] and s1[2] == s0[2] and np.array_equal(s1[3], s0[3])
+    finally:
+        _restore_pk(gpu)
+
+
+def test_value_dictionary_padding_and_special_values(gpu):
+    """Ragged rows (padding inside slices), +0.0 / -0.0 / denormal entries, a non-finite x_0 (padding
+    points at column 0) and new values on the old pattern: always the bits of the 12-byte stream."""
+    rng = np.random.default_rng(7)
+    rows, cols = 3000, 2500
+    lens = rng.integers(0, 40, rows)
+    lens[::97] = 0
+    rb = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    ci = np.concatenate([np.sort(rng.choice(cols, l, replace=False)) for l in lens]).astype(np.uint64)
+    pool = np.array([0.0, -0.0, 1.0, -1.0, 0.1, 1e-310, -2.5, 3.0e200, 7.0 / 3.0])
+    va = pool[rng.integers(0, len(pool), len(ci))]
+    x = rng.standard_normal(cols)
+    try:
+        for x0 in (x[0], np.inf, np.nan, -0.0):
+            x[0] = x0
+            gpu.set_option("spmv.pk", 0)
+            A0 = gpu.Matrix(rows, cols, rb, ci, va)
+            y0 = A0.spmv(x)
+            gpu.set_option("spmv.pk", 1)
+            A = gpu.Matrix(rows, cols, rb, ci, va)
+            assert A.value_dictionary()["packed"] and A.value_dictionary()["n_distinct"] == len(pool)
+            y = A.spmv(x)
+            assert np.array_equal(y.view(np.uint64), y0.view(np.uint64))
+        x[0] = 0.25
+        xt = rng.standard_normal(rows)
+        gpu.set_option("spmv.pk", 0)
+        yt0 = A0.spmv_transpose(xt)
+        gpu.set_option("spmv.pk", 1)
+        assert np.array_equal(A.spmv_transpose(xt).view(np.uint64), yt0.view(np.uint64))
+        # new values on the old pattern: the dictionary is rebuilt; values that no longer compress drop it
+        va2 = pool[::-1][rng.integers(0, len(pool), len(ci))] * 3.0
+        A.update_values(va2, 2)
+        A0.update_values(va2, 2)
+        assert A.value_dictionary()["packed"]
+        gpu.set_option("spmv.pk", 0)
+        y0 = A0.spmv(x)
+        gpu.set_option("spmv.pk", 1)
+        assert np.array_equal(A.spmv(x).view(np.uint64), y0.view(np.uint64))
+        va3 = rng.standard_normal(len(ci)) if len(ci) > 65535 else np.arange(len(ci), dtype=np.float64)
+        A.update_values(va3, 3)
+        if len(np.unique(va3)) > 65535:
+            assert not A.value_dictionary()["packed"]
+        A0.update_values(va3, 3)
+        assert np.array_equal(A.spmv(x), A0.spmv(x))
+    finally:
+        _restore_pk(gpu)
 
 
 def test_column_compression_is_transparent(gpu):
