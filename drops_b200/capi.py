@@ -57,6 +57,7 @@ SIGNATURES = {
     "drops_b200_matrix_info": (_i, [_vp, _szpp, _szpp, _szpp, C.POINTER(C.c_uint64), _szpp, _szpp]),
     "drops_b200_matrix_format": (_i, [_vp, _szpp, _szpp, _ip, _szpp]),
     "drops_b200_matrix_value_dictionary": (_i, [_vp, _i, _ip, _ip, _ip]),
+    "drops_b200_matrix_layout": (_i, [_vp, _ip, _ip]),
     "drops_b200_matrix_download": (_i, [_vp, _szp, _szp, _dp]),
     "drops_b200_spmv": (_i, [_vp, _dp, _dp]),
     "drops_b200_spmv_transpose": (_i, [_vp, _dp, _dp]),
@@ -386,6 +387,11 @@ class Matrix:
         cmp_ = C.c_int()
         check(lib().drops_b200_matrix_format(self.h, C.byref(ns), C.byref(pn), C.byref(cmp_), C.byref(ws)))
         return {"nslices": ns.value, "padded_nnz": pn.value, "compressed": bool(cmp_.value), "wide_slices": ws.value}
+
+    def layout(self):
+        bo, ro = C.c_int(), C.c_int()
+        check(lib().drops_b200_matrix_layout(self.h, C.byref(bo), C.byref(ro)))
+        return {"block_ordered": bool(bo.value), "row_ordered_stream": bool(ro.value)}
 
     def value_dictionary(self, transposed=False):
         nd, pk, cb = C.c_int(), C.c_int(), C.c_int()

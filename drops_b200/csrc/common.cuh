@@ -305,6 +305,7 @@ struct SellOp {
     double*  val = nullptr;
     int32_t* perm = nullptr;         // sorted position -> original row, -1 beyond rows
     int max_width = 0;
+    bool full_rows = true;           // built over all rows of the CSR (false: a row subset, dist.cu)
     // 16-bit column deltas ("sell.compress"): entry j of the 32 rows of a slice are neighbouring
     // rows with the same stencil, so their columns lie within 2^16 of each other: col = cbase[slice
     // entry j] + col16 (0xFFFF = padding).  Slices where that fails are flagged wide and keep using
@@ -323,6 +324,14 @@ struct SellOp {
     double* dict = nullptr;          // ndict distinct values + one 0.0 (the padding slot)
     int ndict = 0;
     int cbits = 0;                   // low bits of pk that hold the column
+    // Row-ordered twin of pk (square operators over all rows): the unknowns renumbered by the
+    // operator's own slice order -- position s*32+lane of the sorted windows -- so that row `pos`
+    // IS y[pos] (no perm load, coalesced stores) and the neighbours of 32 rows of equal shape are
+    // neighbours in x (a gather touches 8-9 sectors instead of ~14 on the P2 brick, where DOF classes
+    // alternate along a mesh line).  Vectors of that numbering have npos = 32*nslices entries
+    // (padding positions hold 0); the entries of a row keep their order, so every y_i keeps its bits.
+    uint32_t* pkp = nullptr;         // padded entries: (dict index << cbits) | position of the column
+    size_t npos = 0;
 };
 
 struct CsrDev {
@@ -344,11 +353,14 @@ struct drops_b200_matrix_s {
     int* diag_missing = nullptr;     // device flag
     bool diag_ok = false;
     bool square = false;
+    bool block_ordered = false;      // sell was built over the block order of reorder.cu
     uint64_t version = 0;
     size_t device_bytes = 0;
     // solver workspace cached with the matrix: vectors of max(rows, cols) doubles, grown on demand
     std::vector<double*> work;
     double* bridge[2] = {nullptr, nullptr};   // device copies of host x / b (host-buffer entry points)
+    std::vector<double*> ro_work;    // vectors in the row-ordered numbering (sell.npos doubles)
+    uint64_t ro_diag_epoch = 0;      // values epoch ro_work[0] (the permuted diagonal) was gathered at
     void* d_scalars = nullptr;       // db200::SolverScalars
     double* d_hist = nullptr;
     int hist_alloc = 0;
@@ -377,7 +389,10 @@ double* work_vec(drops_b200_matrix_s* M, int i);
 void free_sell(SellOp& s);
 void free_csr(CsrDev& c);
 int build_transpose(drops_b200_matrix_s* M);
-int build_sell(const CsrDev& A, SellOp& S, size_t* bytes, const int32_t* rowmap, size_t nsub);
+int build_sell(const CsrDev& A, SellOp& S, size_t* bytes, const int32_t* rowmap, size_t nsub,
+               bool rowmap_is_permutation = false);
+// block order of the rows of a square operator from its graph (reorder.cu); *d_order = nullptr: keep the caller's order
+int compute_block_order(const CsrDev& A, int32_t** d_order);
 // (re)builds S.dict / S.pk from S.col / S.val; leaves them null when the matrix does not qualify
 int build_value_dictionary(SellOp& S, size_t* bytes);
 }  // namespace db200

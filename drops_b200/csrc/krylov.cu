@@ -73,7 +73,32 @@ int pcg_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, doubl
     const int want_hist = hist ? std::max(hist_cap, 0) : 0;
     DB_CHECK(ensure_scalars(M, std::max(want_hist, 1)));
     SolverScalars* S = (SolverScalars*)M->d_scalars;
-    double* r = work_vec(M, 0); double* p = work_vec(M, 1); double* q = work_vec(M, 2);
+    // Row-ordered solve ("pcg.reorder", operators with a row-ordered packed stream): the whole
+    // iteration runs on vectors renumbered by the operator's slice order -- x, b and the diagonal are
+    // gathered once, x is scattered back at the end.  Every row sum keeps its bits (entry order is
+    // untouched); the reductions visit the same products in another order, which the double-double
+    // accumulation absorbs.  Padding positions hold 0 (diagonal 1) and stay 0.
+    const bool ro = !unpreconditioned_cg && M->sell.pkp != nullptr && opt("pcg.reorder", 1.0) != 0.0 &&
+                    opt("spmv.pk", 1.0) != 0.0 && opt("spmv.kernel", 0.0) == 0.0;
+    double* x_user = x;
+    const double* diag = M->diag;
+    if (ro) {
+        const size_t npos = M->sell.npos;
+        if (M->ro_work.size() < 6) M->ro_work.resize(6, nullptr);
+        for (double*& w : M->ro_work) if (!w) DB_CHECK(dev_alloc(&w, npos));
+        double* dp = M->ro_work[0]; double* xp = M->ro_work[1]; double* bp = M->ro_work[2];
+        if (M->ro_diag_epoch != M->values_epoch) {
+            DB_CHECK(vec_gather_perm(npos, M->sell.perm, M->diag, dp, 1.0));
+            M->ro_diag_epoch = M->values_epoch;
+        }
+        DB_CHECK(vec_gather_perm(npos, M->sell.perm, x, xp, 0.0));
+        DB_CHECK(vec_gather_perm(npos, M->sell.perm, b, bp, 0.0));
+        x = xp; b = bp; diag = dp;
+    }
+    const size_t nv = ro ? M->sell.npos : n;      // length of the vectors the iteration works on
+    double* r = ro ? M->ro_work[3] : work_vec(M, 0);
+    double* p = ro ? M->ro_work[4] : work_vec(M, 1);
+    double* q = ro ? M->ro_work[5] : work_vec(M, 2);
     if (!r || !p || !q) return DROPS_B200_E_NOMEM;
 
     SolverScalars h;
@@ -86,9 +111,9 @@ int pcg_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, doubl
     SpmvArgs a;
     if (!unpreconditioned_cg) {
         // r = b - A x                                                           :125
-        a.x = x; a.y = r; a.epilogue = EPI_RESID; a.aux = b;
+        a.x = x; a.y = r; a.epilogue = EPI_RESID; a.aux = b; a.row_ordered = ro;
         DB_CHECK(spmv_apply(M, false, a));
-        DB_CHECK(pcg_setup(n, r, b, M->diag, p, S, dh));
+        DB_CHECK(pcg_setup(nv, r, b, diag, p, S, dh));
     } else {
         // r = A x - b  (CG :61): q = A x, r = q - b
         a.x = x; a.y = q;
@@ -118,20 +143,20 @@ int pcg_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, doubl
     const bool fused_dot = opt("pcg.fused_dot", 1.0) != 0.0;
     const bool defer_x = !unpreconditioned_cg && opt("pcg.defer_x", 1.0) != 0.0 && opt("vec.wide", 1.0) != 0.0 &&
                          ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(r) |
-                           reinterpret_cast<uintptr_t>(M->diag)) & 15u) == 0;
+                           reinterpret_cast<uintptr_t>(diag)) & 15u) == 0;
     auto one_iteration = [&]() -> int {
         SpmvArgs s;
-        s.x = p; s.y = q; s.done = &S->done;                                       // q = A p, lambda = q.p  :149-151
+        s.x = p; s.y = q; s.done = &S->done; s.row_ordered = ro;                    // q = A p, lambda = q.p  :149-151
         if (fused_dot) { s.dotv = p; s.dot_out = &S->lambda; }
         DB_CHECK(spmv_apply(M, false, s));
-        if (!fused_dot) DB_CHECK(vec_dot_unless(n, q, p, &S->lambda, &S->done));
+        if (!fused_dot) DB_CHECK(vec_dot_unless(nv, q, p, &S->lambda, &S->done));
         if (defer_x) {
-            DB_CHECK(pcg_update_r(n, r, q, M->diag, S, dh));
-            DB_CHECK(pcg_direction_x(n, x, p, r, M->diag, S));
+            DB_CHECK(pcg_update_r(nv, r, q, diag, S, dh));
+            DB_CHECK(pcg_direction_x(nv, x, p, r, diag, S));
             return 0;
         }
-        DB_CHECK(unpreconditioned_cg ? cg_update(n, x, r, p, q, S, dh) : pcg_update(n, x, r, p, q, M->diag, S, dh));
-        DB_CHECK(unpreconditioned_cg ? cg_direction(n, p, r, S) : pcg_direction(n, p, r, M->diag, S));
+        DB_CHECK(unpreconditioned_cg ? cg_update(n, x, r, p, q, S, dh) : pcg_update(nv, x, r, p, q, diag, S, dh));
+        DB_CHECK(unpreconditioned_cg ? cg_direction(n, p, r, S) : pcg_direction(nv, p, r, diag, S));
         return 0;
     };
     // A chunk of iterations as ONE CUDA graph launch: on small systems (cdrdrops' example has 250 k
@@ -196,6 +221,7 @@ int pcg_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, doubl
     cudaEventDestroy(ev[1]);
     if (status != 0) { cudaStreamSynchronize(st); return status; }
 
+    if (ro) DB_CHECK(vec_scatter_perm(M->sell.npos, M->sell.perm, x, x_user));
     DB_CHECK(fetch(S, &h, sizeof h));
     if (hist && want_hist > 0) {
         const int cnt = std::min(want_hist, h.iter + 1);

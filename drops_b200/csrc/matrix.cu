@@ -356,7 +356,7 @@ void free_sell(SellOp& s)
 {
     dev_free(s.slice_ptr); dev_free(s.col); dev_free(s.val); dev_free(s.perm);
     dev_free(s.col16); dev_free(s.cbase); dev_free(s.wide);
-    dev_free(s.pk); dev_free(s.dict);
+    dev_free(s.pk); dev_free(s.dict); dev_free(s.pkp);
     s = SellOp();
 }
 
@@ -369,13 +369,14 @@ void free_csr(CsrDev& c)
 // Builds the sliced-ELL operator of all rows of A (rowmap == nullptr) or of the `nsub` rows
 // listed in rowmap (device array, ascending); perm then holds rows of A, so y, aux and the
 // fused dot are addressed by the full row index.
-int build_sell(const CsrDev& A, SellOp& S, size_t* bytes, const int32_t* rowmap, size_t nsub)
+int build_sell(const CsrDev& A, SellOp& S, size_t* bytes, const int32_t* rowmap, size_t nsub, bool rowmap_is_permutation)
 {
     Ctx& c = ctx();
     cudaStream_t st = c.stream;
     free_sell(S);
     const size_t op_rows = rowmap ? nsub : A.rows;
     S.rows = op_rows; S.cols = A.cols;
+    S.full_rows = rowmap == nullptr || (rowmap_is_permutation && nsub == A.rows);
     int sigma = (int)opt("sell.sigma", 4096.0);
     const bool sorted = sigma >= 64;
     if (sorted) {
@@ -449,6 +450,27 @@ int build_sell(const CsrDev& A, SellOp& S, size_t* bytes, const int32_t* rowmap,
     return build_value_dictionary(S, bytes);
 }
 
+__global__ void k_inverse_perm(long long npos, const int32_t* __restrict__ perm, int32_t* __restrict__ iperm)
+{
+    const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= npos) return;
+    const int32_t r = perm[pos];
+    if (r >= 0) iperm[r] = (int32_t)pos;
+}
+
+// the packed stream with every column replaced by its position in the operator's row order
+__global__ void __launch_bounds__(256)
+k_pack_reorder(long long n, const uint32_t* __restrict__ pk, const int32_t* __restrict__ iperm, int cbits, uint32_t wpad,
+               uint32_t* __restrict__ pkp)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t w = __ldcs(pk + i);
+    if (w >= wpad) { pkp[i] = w; return; }
+    const uint32_t cmask = (1u << cbits) - 1u;
+    pkp[i] = (w & ~cmask) | (uint32_t)__ldg(iperm + (w & cmask));
+}
+
 static int bits_for(unsigned long long count)      // bits that distinguish `count` codes 0..count-1
 {
     int b = 0;
@@ -459,10 +481,11 @@ static int bits_for(unsigned long long count)      // bits that distinguish `cou
 int build_value_dictionary(SellOp& S, size_t* bytes)
 {
     cudaStream_t st = ctx().stream;
-    dev_free(S.pk); dev_free(S.dict);
-    S.pk = nullptr; S.dict = nullptr; S.ndict = 0; S.cbits = 0;
+    dev_free(S.pk); dev_free(S.dict); dev_free(S.pkp);
+    S.pk = nullptr; S.dict = nullptr; S.pkp = nullptr; S.ndict = 0; S.cbits = 0; S.npos = 0;
     if (S.padded == 0 || S.col == nullptr || S.val == nullptr || opt("sell.valdict", 1.0) == 0.0) return 0;
-    const int cbits = std::max(1, bits_for((unsigned long long)std::max<size_t>(S.cols, 1)));
+    // columns and, for the row-ordered twin, positions (32 * nslices >= rows) share the low bits
+    const int cbits = std::max(1, bits_for((unsigned long long)std::max<size_t>(std::max(S.cols, S.nslices * 32), 1)));
     if (cbits > 31) return 0;
     unsigned long long* table = nullptr; int* d_count = nullptr;
     const size_t cap = (size_t)1 << kDictTableBits;
@@ -516,7 +539,27 @@ int build_value_dictionary(SellOp& S, size_t* bytes)
         if (status == 0) {
             S.ndict = count; S.cbits = cbits;
             if (bytes) *bytes += S.padded * 4 + keys.size() * 8;
-        } else {
+        }
+        // row-ordered twin: square operator over all its rows (perm is a permutation of 0..rows-1)
+        if (status == 0 && S.full_rows && S.rows == S.cols && opt("sell.reorder", 1.0) != 0.0) {
+            int32_t* iperm = nullptr;
+            const long long npos = (long long)S.nslices * 32;
+            status = dev_alloc(&iperm, S.cols);
+            if (status == 0) status = dev_alloc(&S.pkp, S.padded);
+            if (status == 0) {
+                k_inverse_perm<<<blocks_for(npos, 256), 256, 0, st>>>(npos, S.perm, iperm);
+                k_pack_reorder<<<blocks_for((long long)S.padded, 256), 256, 0, st>>>((long long)S.padded, S.pk, iperm, cbits,
+                                                                                   (uint32_t)count << cbits, S.pkp);
+                count_launch(2);
+                e = cudaGetLastError();
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                if (e != cudaSuccess) fail(e, "value dictionary: reorder");
+            }
+            dev_free(iperm);
+            if (status == 0) { S.npos = (size_t)npos; if (bytes) *bytes += S.padded * 4; }
+            else { dev_free(S.pkp); S.pkp = nullptr; }
+        }
+        if (status != 0) {
             dev_free(S.pk); dev_free(S.dict); S.pk = nullptr; S.dict = nullptr;
         }
     }
@@ -610,8 +653,13 @@ int finalize_matrix(drops_b200_matrix_s* M)
     M->device_bytes = M->csr.nnz * 12 + (M->csr.rows + 1) * 8;
     DB_CHECK(extract_diag(M));
     if (M->square) M->device_bytes += M->csr.rows * 8;
-    DB_CHECK(build_sell(M->csr, M->sell, &M->device_bytes, nullptr, 0));
-    return 0;
+    // rows in compact blocks of the matrix graph (reorder.cu) when the operator is large enough to profit
+    int32_t* order = nullptr;
+    DB_CHECK(compute_block_order(M->csr, &order));
+    const int s = build_sell(M->csr, M->sell, &M->device_bytes, order, order ? M->csr.rows : 0, order != nullptr);
+    dev_free(order);
+    M->block_ordered = s == 0 && order != nullptr;
+    return s;
 }
 
 }  // namespace db200
@@ -809,6 +857,7 @@ int drops_b200_matrix_destroy(drops_b200_matrix_t M)
     free_csr(M->csr_t); free_sell(M->sell_t);
     dev_free(M->diag); dev_free(M->diag_missing); dev_free(M->bbt_diag);
     for (double* w : M->work) dev_free(w);
+    for (double* w : M->ro_work) dev_free(w);
     dev_free(M->bridge[0]); dev_free(M->bridge[1]);
     dev_free(M->d_scalars); dev_free(M->d_hist); dev_free(M->d_small);
     if (M->pcg_graph) cudaGraphExecDestroy(M->pcg_graph);
@@ -837,6 +886,14 @@ int drops_b200_matrix_value_dictionary(drops_b200_matrix_t M, int transposed, in
     if (n_distinct) *n_distinct = S.ndict;
     if (packed) *packed = S.pk != nullptr;
     if (column_bits) *column_bits = S.cbits;
+    return 0;
+}
+
+int drops_b200_matrix_layout(drops_b200_matrix_t M, int* block_ordered, int* row_ordered_stream)
+{
+    DB_ARG(M != nullptr, "null matrix");
+    if (block_ordered) *block_ordered = M->block_ordered;
+    if (row_ordered_stream) *row_ordered_stream = M->sell.pkp != nullptr;
     return 0;
 }
 

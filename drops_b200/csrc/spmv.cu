@@ -285,7 +285,12 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a)
     DB_ARG(a.dotv == nullptr || a.dot_out != nullptr || a.dd_out != nullptr, "fused dot needs an output scalar");
     if (A.rows == 0) return 0;
     // dictionary-packed stream (4 B per entry, spmv_pk.cu) when the operator has one
-    if (A.pk != nullptr && a.xghost == nullptr && opt("spmv.pk", 1.0) != 0.0) return spmv_sell_pk(A, a);
+    if (A.pk != nullptr && a.xghost == nullptr && (a.row_ordered || opt("spmv.pk", 1.0) != 0.0)) {
+        // stream staged by TMA ("spmv.pktma") when the dictionary fits shared memory
+        if (opt("spmv.pktma", 0.0) != 0.0 && A.ndict <= 512) return spmv_sell_pk_tma(A, a);
+        return spmv_sell_pk(A, a);
+    }
+    DB_ARG(!a.row_ordered, "row-ordered vectors need the operator's row-ordered stream");
     int threads = (int)opt("spmv.threads", 128);
     if (threads < 32) threads = 32;
     if (threads > 512) threads = 512;
@@ -366,7 +371,7 @@ int spmv_csr_vector(const CsrDev& A, const SpmvArgs& a, int lanes)
 int spmv_apply(const drops_b200_matrix_s* M, bool transposed, const SpmvArgs& a)
 {
     ScopedTiming t(transposed ? "spmv_t" : "spmv");
-    const int kind = (int)opt("spmv.kernel", 0.0);
+    const int kind = a.row_ordered ? 0 : (int)opt("spmv.kernel", 0.0);
     if (kind == 1) {
         const int lanes = (int)opt("spmv.lanes", 8.0);
         return spmv_csr_vector(transposed ? M->csr_t : M->csr, a, lanes);

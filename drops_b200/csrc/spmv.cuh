@@ -31,6 +31,8 @@ struct SpmvArgs {
     // columns >= n_owned are read from xghost[col - n_owned] (received halo entries)
     const double* xghost = nullptr;
     long long n_owned = 0;
+    // x, y, aux and dotv are vectors in the operator's row-ordered numbering (SellOp::pkp, npos entries)
+    bool row_ordered = false;
     const int* done = nullptr;     // optional device flag: kernel is a no-op when *done != 0
     int slot = 0;                  // reduction workspace slot (kernels that may overlap use different slots)
     cudaStream_t stream = nullptr; // default: ctx().stream
@@ -42,6 +44,9 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a);
 // Same operator on its dictionary-packed stream (SellOp::pk, 4 B per entry; spmv_pk.cu); spmv_sell
 // dispatches to it when the operator has one and option "spmv.pk" is not 0.
 int spmv_sell_pk(const SellOp& A, const SpmvArgs& a);
+// ... with the packed stream staged through shared memory by TMA bulk copies (spmv_pk_tma.cu)
+int spmv_sell_pk_tma(const SellOp& A, const SpmvArgs& a);
+int spmv_pk_tma_fault();
 // Same operator, matrix stream staged through shared memory with TMA bulk copies (spmv_tma.cu).
 int spmv_sell_tma(const SellOp& A, const SpmvArgs& a);
 int spmv_tma_fault();

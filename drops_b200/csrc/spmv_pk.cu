@@ -68,6 +68,55 @@ __device__ __forceinline__ double pk_row_sum(const PkView& A, int64_t base, int 
 }
 
 // DOT as in k_spmv_sell: 0 none, 1 finished in this kernel, 2 per-warp partials + finishing kernel.
+// Software-pipelined form: the words of batch k+1 are requested before the gathers of batch k are
+// consumed, so a warp always has U matrix loads AND U gathers in flight (the plain form alternates).
+template <bool EXACT, int U, bool SMEM>
+__device__ __forceinline__ double pk_row_sum_pipe(const PkView& A, int64_t base, int width, int lane,
+                                                  const double* __restrict__ x)
+{
+    extern __shared__ double sdict[];
+    const uint32_t* pp = A.pk + base + lane;
+    const int cbits = A.cbits;
+    const uint32_t cmask = (1u << cbits) - 1u;
+    const uint32_t wpad = (uint32_t)A.ndict << cbits;
+    double sum = 0.0;
+    int j = 0;
+    uint32_t w[U];
+    if (U <= width) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) w[u] = __ldcs(pp + (size_t)u * 32);
+    }
+    for (; j + U <= width; j += U) {
+        uint32_t wn[U];
+        double xv[U];
+        const bool more = j + 2 * U <= width;
+        if (more) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) wn[u] = __ldcs(pp + (size_t)(j + U + u) * 32);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) xv[u] = __ldg(x + (w[u] & cmask));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double v = SMEM ? sdict[w[u] >> cbits] : __ldg(A.dict + (w[u] >> cbits));
+            const double t = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv[u])) : fma(v, xv[u], sum);
+            sum = w[u] < wpad ? t : sum;
+        }
+        if (more) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) w[u] = wn[u];
+        }
+    }
+    for (; j < width; ++j) {
+        const uint32_t ww = __ldcs(pp + (size_t)j * 32);
+        const double xv = __ldg(x + (ww & cmask));
+        const double v = SMEM ? sdict[ww >> cbits] : __ldg(A.dict + (ww >> cbits));
+        const double t = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv)) : fma(v, xv, sum);
+        sum = ww < wpad ? t : sum;
+    }
+    return sum;
+}
+
 // DF, the form of the fused dot (same per-thread order of the same products: bit-identical results):
 //   0 = in the slice loop, partner fetched at slice start, accumulator in registers -- at <= 40
 //       registers the compiler can then no longer keep the U loads of the row sum in flight
@@ -98,13 +147,23 @@ k_spmv_sell_pk(PkView A, const double* __restrict__ x, double* __restrict__ y, E
     for (long long s = s_begin + warp; s < s_end; s += nwarp) {
         const int64_t base = A.slice_ptr[s];
         const int width = (int)((A.slice_ptr[s + 1] - base) >> 5);
-        const int row = A.perm[s * 32 + lane];
+        // row-ordered twin (perm == nullptr): position s*32+lane IS the row of y, aux and the dot partner
+        const int row = A.perm != nullptr ? A.perm[s * 32 + lane] : (int)(s * 32 + lane);
         double dv = 0.0, av = 0.0;
         if (row >= 0) {
             if (DOT && DF == 0) dv = __ldg(e.dotv + row);
             if (EPI != EPI_NONE) av = __ldg(e.aux + row);
         }
-        const double sum = pk_row_sum<EXACT, U, SMEM>(A, base, width, lane, x);
+        if (e.prefetch > 0 && s + (long long)e.prefetch * nwarp < A.nslices) {
+            // request the words of a slice this warp (or the next CTA) reaches soon into L2: the stream
+            // is perfectly predictable, and the kernel waits on latency, not on DRAM bytes
+            const long long sp = s + (long long)e.prefetch * nwarp;
+            const int64_t nb = A.slice_ptr[sp];
+            const int nlines = (int)((A.slice_ptr[sp + 1] - nb) >> 5);
+            for (int l = lane; l < nlines; l += 32) prefetch_l2(A.pk + nb + (int64_t)l * 32);
+        }
+        const double sum = U > 0 ? pk_row_sum<EXACT, (U > 0 ? U : -U), SMEM>(A, base, width, lane, x)
+                                 : pk_row_sum_pipe<EXACT, (U > 0 ? U : -U), SMEM>(A, base, width, lane, x);
         if (row >= 0) {
             const double out = apply_epilogue<EPI>(sum, av, e, beta);
             y[row] = out;
@@ -115,7 +174,7 @@ k_spmv_sell_pk(PkView A, const double* __restrict__ x, double* __restrict__ y, E
     if (DOT && DF == 2) acc[0] = acc_smem[threadIdx.x];
     if (DOT && DF == 1) {
         for (long long s = s_begin + warp; s < s_end; s += nwarp) {
-            const int row = A.perm[s * 32 + lane];
+            const int row = A.perm != nullptr ? A.perm[s * 32 + lane] : (int)(s * 32 + lane);
             if (row >= 0) acc[0] = dd_add_prod(acc[0], __ldcg(y + row), __ldg(e.dotv + row));
         }
     }
@@ -166,8 +225,8 @@ static void launch_pk_v(const PkView& v, const SpmvArgs& a, const EpiArgs& e, in
 // "spmv.pkvariant" (plain product) / "spmv.pkdotvariant" (fused dot): unroll x register cap.
 //   0 = U8/<=40 regs, 1 = U8/<=48, 2 = U4/<=32, 3 = U16/<=64, 4 = U16/<=48, 5 = U8/256 threads/<=40,
 //   6 = U12/<=48, 7 = U4/<=40, 8 = U8/CTAs up to 1024 threads/<=64, 9 = U8/<=512 threads/<=40,
-//   10 = U16/<=512 threads/<=64
-constexpr int kPkDefaultVariant = 0;
+//   10 = U16/<=512 threads/<=64; software-pipelined: 11 = U4/<=40, 12 = U8/<=48, 13 = U6/<=40, 14 = U4/<=512 threads/<=40
+constexpr int kPkDefaultVariant = 9;   // measured on C2 (profiles/r01_probe_blockorder.json): 512-thread CTAs x 128 slices
 
 template <int EPI, bool EXACT>
 static bool launch_pk(const PkView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads, cudaStream_t st)
@@ -185,12 +244,16 @@ static bool launch_pk(const PkView& v, const SpmvArgs& a, const EpiArgs& e, int 
             case 6: launch_pk_v<EPI_NONE, true, 12, 128, 10, false>(v, a, e, grid, threads, st); return true;
             case 7: launch_pk_v<EPI_NONE, true, 4, 128, 12, false>(v, a, e, grid, threads, st); return true;
             case 8: launch_pk_v<EPI_NONE, true, 8, 1024, 1, false>(v, a, e, grid, threads, st); return true;
-            case 9: launch_pk_v<EPI_NONE, true, 8, 512, 3, false>(v, a, e, grid, threads, st); return true;
+            case 0: launch_pk_v<EPI_NONE, true, 8, 128, 12, false>(v, a, e, grid, threads, st); return true;
             case 10: launch_pk_v<EPI_NONE, true, 16, 512, 2, false>(v, a, e, grid, threads, st); return true;
+            case 11: launch_pk_v<EPI_NONE, true, -4, 128, 12, false>(v, a, e, grid, threads, st); return true;
+            case 12: launch_pk_v<EPI_NONE, true, -8, 128, 10, false>(v, a, e, grid, threads, st); return true;
+            case 13: launch_pk_v<EPI_NONE, true, -6, 128, 12, false>(v, a, e, grid, threads, st); return true;
+            case 14: launch_pk_v<EPI_NONE, true, -4, 512, 3, false>(v, a, e, grid, threads, st); return true;
             default: break;
         }
     }
-    launch_pk_v<EPI, EXACT, 8, 128, 12, true>(v, a, e, grid, threads, st);
+    launch_pk_v<EPI, EXACT, 8, 512, 3, true>(v, a, e, grid, threads, st);
     return true;
 }
 
@@ -209,6 +272,7 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
 {
     Ctx& c = ctx();
     DB_ARG(A.pk != nullptr && A.dict != nullptr, "operator holds no packed stream");
+    DB_ARG(!a.row_ordered || A.pkp != nullptr, "operator holds no row-ordered stream");
     DB_ARG(a.x != nullptr && a.y != nullptr, "null vector");
     DB_ARG(a.x != a.y, "x and y must not alias");
     DB_ARG(a.xghost == nullptr, "the packed stream has no split-x form");
@@ -216,7 +280,7 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
     DB_ARG(a.dotv == nullptr || a.dot_out != nullptr || a.dd_out != nullptr, "fused dot needs an output scalar");
     DB_ARG(a.dotv != a.y, "the partner of the fused dot must not be the output vector");   // the tail pass re-reads y
     if (A.rows == 0) return 0;
-    int threads = (int)opt("spmv.pk_threads", 128);
+    int threads = (int)opt("spmv.pk_threads", 512);
     if (threads < 32) threads = 32;
     if (threads > 1024) threads = 1024;
     threads &= ~31;
@@ -225,7 +289,7 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
     long long grid;
     if (per_sm > 0.0) grid = (long long)(per_sm * c.sm_count + 0.5);
     else {
-        long long spc = (long long)opt("spmv.pk_slices_per_cta", 16.0);
+        long long spc = (long long)opt("spmv.pk_slices_per_cta", 128.0);
         if (spc < 1) spc = 1;
         grid = ((long long)A.nslices + spc - 1) / spc;
     }
@@ -234,8 +298,10 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
     if (grid > kMaxReduceGrid) grid = kMaxReduceGrid;
     if (grid < 1) grid = 1;
     cudaStream_t st = a.stream ? a.stream : c.stream;
-    PkView v{A.slice_ptr, A.pk, A.dict, A.perm, (long long)A.nslices, A.ndict, A.cbits};
+    PkView v{A.slice_ptr, a.row_ordered ? A.pkp : A.pk, A.dict, a.row_ordered ? nullptr : A.perm, (long long)A.nslices,
+             A.ndict, A.cbits};
     EpiArgs e = make_epi(a);
+    e.prefetch = (int)opt("spmv.pk_prefetch", 0.0);        // slices ahead (in units of the CTA's warp count)
     if (opt("spmv.exact", 1.0) != 0.0) launch_pk_epi<true>(v, a, e, (int)grid, threads, st);
     else launch_pk_epi<false>(v, a, e, (int)grid, threads, st);
     count_launch();

@@ -126,6 +126,39 @@ int vec_supnorm(size_t n, const double* x, double* d_out)
     return 0;
 }
 
+__global__ void k_gather_perm(size_t npos, const int32_t* __restrict__ perm, const double* __restrict__ src,
+                              double* __restrict__ dst, double fill)
+{
+    const size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= npos) return;
+    const int32_t r = perm[pos];
+    dst[pos] = r >= 0 ? src[r] : fill;
+}
+__global__ void k_scatter_perm(size_t npos, const int32_t* __restrict__ perm, const double* __restrict__ src,
+                               double* __restrict__ dst)
+{
+    const size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= npos) return;
+    const int32_t r = perm[pos];
+    if (r >= 0) dst[r] = src[pos];
+}
+int vec_gather_perm(size_t npos, const int32_t* perm, const double* src, double* dst, double fill)
+{
+    if (npos == 0) return 0;
+    k_gather_perm<<<(unsigned)((npos + 255) / 256), 256, 0, ctx().stream>>>(npos, perm, src, dst, fill);
+    count_launch();
+    DB_CUDA(cudaGetLastError());
+    return 0;
+}
+int vec_scatter_perm(size_t npos, const int32_t* perm, const double* src, double* dst)
+{
+    if (npos == 0) return 0;
+    k_scatter_perm<<<(unsigned)((npos + 255) / 256), 256, 0, ctx().stream>>>(npos, perm, src, dst);
+    count_launch();
+    DB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 struct OpAxpy {
     double a; const double* x; double* y;
     __device__ bool begin() { return true; }

@@ -53,6 +53,9 @@ int vec_jacobi(size_t n, double omega, const double* d, const double* b, double*
 int vec_fill(size_t n, double* x, double v);
 int vec_fill_hash(size_t n, double* x);
 int vec_copy(size_t n, double* dst, const double* src);
+// dst[pos] = perm[pos] >= 0 ? src[perm[pos]] : fill   /   dst[perm[pos]] = src[pos]   (row-ordered numbering)
+int vec_gather_perm(size_t npos, const int32_t* perm, const double* src, double* dst, double fill);
+int vec_scatter_perm(size_t npos, const int32_t* perm, const double* src, double* dst);
 
 // ---- PCG (num/krylovsolver.h:107-179) ------------------------------------------------------------
 // setup: given r = b - A x: normb, resid, hist[0], z = M^-1 r, rho = z.r, p = z; may set done.

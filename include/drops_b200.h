@@ -127,6 +127,12 @@ DROPS_B200_API int drops_b200_matrix_format(drops_b200_matrix_t A, size_t* nslic
  * != 0 asks about the A^T operator (0/0 until the first transp_mul built it). */
 DROPS_B200_API int drops_b200_matrix_value_dictionary(drops_b200_matrix_t A, int transposed, int* n_distinct,
                                                       int* packed, int* column_bits);
+/* Row order of the sliced-ELL operator: block_ordered != 0 when the slices were cut from the block
+ * order of the matrix graph ("sell.block_order", operators of at least "sell.block_min_rows" rows:
+ * three breadth-first distance fields as pseudo-coordinates, rows sorted by the Morton code of their
+ * cell); row_ordered_stream != 0 when the packed stream has its row-ordered twin, which is what
+ * PCG iterates on ("pcg.reorder").  Both only change who shares a cache, never a result bit of A*x. */
+DROPS_B200_API int drops_b200_matrix_layout(drops_b200_matrix_t A, int* block_ordered, int* row_ordered_stream);
 /* Copies the device CSR back in the reference layout (for tests and the CPU baseline). */
 DROPS_B200_API int drops_b200_matrix_download(drops_b200_matrix_t A, size_t* rowbeg, size_t* colind, double* val);
 

@@ -93,14 +93,63 @@ def test_spmv_layout_and_launch_options_do_not_change_results(gpu, sigma, thread
         gpu.set_option("spmv.prefetch", 0)
 
 
-PK_DEFAULTS = {"spmv.pk": 1, "spmv.pkdotform": 2, "spmv.pkvariant": 0, "spmv.pkdotvariant": 0, "spmv.pk_threads": 128,
+PK_DEFAULTS = {"spmv.pktma": None, "spmv.pktma_geometry": 0, "spmv.pktma_slices_per_cta": None, "spmv.pk": 1, "spmv.pkdotform": 2, "pcg.reorder": 1, "pcg.defer_x": 1, "pcg.fused_dot": 1, "spmv.pkvariant": 0, "spmv.pkdotvariant": 0, "spmv.pk_threads": 128,
                "spmv.pk_slices_per_cta": 16, "spmv.pkdict": 0, "spmv.dotmode": 0, "sell.sigma": 4096,
                "sell.valdict": 1, "spmv.exact": 1}
 
 
+PKTMA_DEFAULT = 0     # library default of "spmv.pktma"
+
+
 def _restore_pk(gpu):
     for k, v in PK_DEFAULTS.items():
+        if k == "spmv.pktma":
+            v = PKTMA_DEFAULT
+        elif k == "spmv.pktma_slices_per_cta":
+            v = 16
         gpu.set_option(k, v)
+
+
+@pytest.mark.parametrize("geometry,spc,dotmode", [(0, 16, 0), (1, 1, 0), (2, 3, 0), (3, 1000000, 0), (4, 32, 0), (5, 7, 0),
+                                                  (6, 16, 0), (7, 2, 0), (8, 5, 0)])
+def test_value_dictionary_tma_stream_is_bit_identical(gpu, geometry, spc, dotmode):
+    """"spmv.pktma" = 1: the packed words reach the SM through cp.async.bulk + mbarrier rings; same
+    arithmetic, so every product, fused dot and solve keeps its bits under every ring geometry."""
+    g = load_golden("brick_fe2_N6_num1.npz")
+    r = load_golden("random_ragged.npz")
+    n, rb, ci, va = gpu.brick_csr_host(2, 14, 1)
+    xin = hash_vector(n)
+    try:
+        gpu.set_option("spmv.pktma", 0)
+        B0 = gpu.Matrix(n, n, rb, ci, va)
+        y0, yt0 = B0.spmv(xin), B0.spmv_transpose(xin)
+        X, Y = gpu.Vector.from_host(xin), gpu.Vector(n)
+        d0 = B0.spmv_dot_dev(X, Y, X)
+        s0 = B0.pcg_jacobi(np.zeros(n), y0, 60, 1e-10, True)
+        gpu.set_option("spmv.pktma", 1)
+        gpu.set_option("spmv.pktma_geometry", geometry)
+        gpu.set_option("spmv.pktma_slices_per_cta", spc)
+        A = gmat(gpu, g)
+        assert np.array_equal(A.spmv(g["x_in"]), g["y_Ax"])
+        assert np.array_equal(A.spmv_transpose(g["x_in"]), g["y_ATx"])
+        out = A.pcg_jacobi(np.zeros(A.rows), g["b"], 400, 1e-10, True)
+        assert out[1] == int(g["sym_pcgjac"][1]) and rel(out[3], g["sym_pcgjac_x"]) <= 1e-12
+        if gmat(gpu, r).value_dictionary()["packed"]:
+            R = gmat(gpu, r)
+            assert np.array_equal(R.spmv(r["x_in"]), r["y_Ax"])
+            assert np.array_equal(R.spmv_transpose(r["xt_in"] if "xt_in" in r else r["x_in"]), r["y_ATx"])
+        B = gpu.Matrix(n, n, rb, ci, va)
+        assert np.array_equal(B.spmv(xin), y0) and np.array_equal(B.spmv_transpose(xin), yt0)
+        assert B.spmv_dot_dev(X, Y, X) == d0 and np.array_equal(Y.download(), y0)
+        s1 = B.pcg_jacobi(np.zeros(n), y0, 60, 1e-10, True)
+        assert s1[1] == s0[1] and s1[2] == s0[2] and np.array_equal(s1[3], s0[3])
+        check_solve_like = B.gmres_jacobi(np.zeros(n), y0, 20, 200, 1e-10, True, 1.0, True)
+        gpu.set_option("spmv.pktma", 0)
+        ref = B.gmres_jacobi(np.zeros(n), y0, 20, 200, 1e-10, True, 1.0, True)
+        assert check_solve_like[1] == ref[1] and np.array_equal(check_solve_like[3], ref[3])
+        assert gpu.lib().drops_b200_spmv_tma_fault() == 0
+    finally:
+        _restore_pk(gpu)
 
 
 def test_value_dictionary_qualifies_only_when_lossless_packing_fits(gpu):
@@ -169,8 +218,109 @@ def test_value_dictionary_stream_is_bit_identical(gpu, variant, threads, spc, di
         assert np.array_equal(B.spmv(xin), y0) and np.array_equal(B.spmv_transpose(xin), yt0)
         assert B.spmv_dot_dev(X, Y, X) == d0 and np.array_equal(Y.download(), y0)
         s1 = B.pcg_jacobi(np.zeros(n), y0, 60, 1e-10, True)
-        assert s1[1] == s0[1] and s1[2] == s0[2] and np.array_equal(s1[3], s0[3])
+        # the packed solve runs in the row-ordered numbering: same products, reductions in another order
+        assert s1[1] == s0[1] and abs(s1[2] - s0[2]) <= 1e-9 * abs(s0[2]) and rel(s1[3], s0[3]) <= 1e-12
+        gpu.set_option("pcg.reorder", 0)
+        s2 = B.pcg_jacobi(np.zeros(n), y0, 60, 1e-10, True)
+        assert s2[1] == s0[1] and s2[2] == s0[2] and np.array_equal(s2[3], s0[3])
     finally:
+        _restore_pk(gpu)
+
+
+@pytest.mark.parametrize("reorder,defer_x,fused_dot,graph", [(1, 1, 1, 1), (1, 0, 0, 0), (0, 1, 0, 1), (0, 0, 1, 0), (1, 1, 0, 0)])
+def test_pcg_forms_agree_with_reference(gpu, reorder, defer_x, fused_dot, graph):
+    """Row-ordered solve, deferred x update, separate dot kernel, graph replay: every combination gives
+    the reference's iteration count and solution, also when the solve stops inside a chunk, at
+    max_iter, or before the first iteration."""
+    g = load_golden("brick_fe2_N6_num1.npz")
+    n, rb, ci, va = gpu.brick_csr_host(2, 10, 1)
+    try:
+        gpu.set_option("pcg.reorder", reorder)
+        gpu.set_option("pcg.defer_x", defer_x)
+        gpu.set_option("pcg.fused_dot", fused_dot)
+        gpu.set_option("pcg.graph", graph)
+        A = gmat(gpu, g)
+        out = A.pcg_jacobi(np.zeros(A.rows), g["b"], 400, 1e-10, True)
+        assert out[0] and out[1] == int(g["sym_pcgjac"][1]) and rel(out[3], g["sym_pcgjac_x"]) <= 1e-12
+        out = A.pcg_jacobi(np.zeros(A.rows), g["b"], 7, 1e-30, True)          # stops at max_iter
+        assert not out[0] and rel(out[3], g["sym_pcgjac_fixed7_x"]) <= 1e-12
+        out = A.pcg_jacobi(g["sym_pcgjac_x"].copy(), g["b"], 50, 1e-6, True)  # converged at iteration 0 or 1
+        assert out[0] and out[1] <= 1
+        for check_every in (1, 3, 16):
+            gpu.set_option("pcg.check_every", check_every)
+            B = gpu.Matrix(n, n, rb, ci, va)
+            xs = gpu.brick_solution_host(2, 10, 1)
+            b = B.spmv(xs)
+            out = B.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True)
+            gpu.set_option("pcg.reorder", 0); gpu.set_option("pcg.defer_x", 0); gpu.set_option("pcg.fused_dot", 1)
+            ref = B.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True)
+            gpu.set_option("pcg.reorder", reorder); gpu.set_option("pcg.defer_x", defer_x); gpu.set_option("pcg.fused_dot", fused_dot)
+            assert out[0] and out[1] == ref[1] and rel(out[3], ref[3]) <= 1e-12 and rel(out[3], xs) <= 1e-8
+    finally:
+        gpu.set_option("pcg.check_every", 16)
+        gpu.set_option("pcg.graph", 1)
+        _restore_pk(gpu)
+
+
+@pytest.mark.parametrize("tile,sigma", [(1, 4096), (2, 64), (8, 4096), (3, 0)])
+def test_block_order_is_transparent(gpu, tile, sigma):
+    """Rows cut into blocks of the matrix graph (reorder.cu): any tile size, also on graphs with isolated
+    rows and several components -- products keep their bits, solves their iteration counts."""
+    g = load_golden("brick_fe2_N6_num1.npz")
+    n, rb, ci, va = gpu.brick_csr_host(2, 12, 1)
+    xin = hash_vector(n)
+    xs = gpu.brick_solution_host(2, 12, 1)
+    try:
+        gpu.set_option("sell.block_order", 0)
+        B0 = gpu.Matrix(n, n, rb, ci, va)
+        assert not B0.layout()["block_ordered"]
+        y0, yt0 = B0.spmv(xin), B0.spmv_transpose(xin)
+        b = B0.spmv(xs)
+        s0 = B0.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True)
+        gm0 = B0.gmres_jacobi(np.zeros(n), b, 20, 300, 1e-10, True, 1.0, True)
+        gpu.set_option("sell.block_order", 1)
+        gpu.set_option("sell.block_min_rows", 0)
+        gpu.set_option("sell.block_tile", tile)
+        gpu.set_option("sell.sigma", sigma)
+        A = gmat(gpu, g)
+        assert A.layout()["block_ordered"]
+        assert np.array_equal(A.spmv(g["x_in"]), g["y_Ax"]) and np.array_equal(A.spmv_transpose(g["x_in"]), g["y_ATx"])
+        assert np.array_equal(A.diag(), g["diag"])
+        out = A.pcg_jacobi(np.zeros(A.rows), g["b"], 400, 1e-10, True)
+        assert out[1] == int(g["sym_pcgjac"][1]) and rel(out[3], g["sym_pcgjac_x"]) <= 1e-12
+        B = gpu.Matrix(n, n, rb, ci, va)
+        assert B.layout()["block_ordered"]
+        assert np.array_equal(B.spmv(xin), y0) and np.array_equal(B.spmv_transpose(xin), yt0)
+        s1 = B.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True)
+        assert s1[0] and s1[1] == s0[1] and rel(s1[3], s0[3]) <= 1e-12
+        gm1 = B.gmres_jacobi(np.zeros(n), b, 20, 300, 1e-10, True, 1.0, True)
+        assert gm1[1] == gm0[1] and rel(gm1[3], gm0[3]) <= 1e-10
+        rb2, ci2, va2 = B.download()
+        assert np.array_equal(rb2, rb) and np.array_equal(ci2, ci) and np.array_equal(va2, va)
+        # two components, isolated rows (reachable from nowhere), an empty row
+        m = 600
+        rows = []
+        for i in range(m):
+            if i % 50 == 7:
+                rows.append([])                                   # empty row
+            elif i % 50 == 9:
+                rows.append([i])                                  # isolated
+            else:
+                half = 0 if i < m // 2 else m // 2
+                rows.append(sorted({i, half + (i - half + 1) % (m // 2), half + (i - half + 17) % (m // 2)}))
+        rbd = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.uint64)
+        cid = np.array([c for r in rows for c in r], dtype=np.uint64)
+        vad = 1.0 + (np.arange(len(cid)) % 7) * 0.25
+        xd = hash_vector(m)
+        gpu.set_option("sell.block_order", 0)
+        yd0 = gpu.Matrix(m, m, rbd, cid, vad).spmv(xd)
+        gpu.set_option("sell.block_order", 1)
+        D = gpu.Matrix(m, m, rbd, cid, vad)
+        assert D.layout()["block_ordered"] and np.array_equal(D.spmv(xd), yd0)
+    finally:
+        gpu.set_option("sell.block_order", 1)
+        gpu.set_option("sell.block_min_rows", 2.0e6)
+        gpu.set_option("sell.block_tile", 8)
         _restore_pk(gpu)
 
 
@@ -195,8 +345,11 @@ def test_value_dictionary_padding_and_special_values(gpu):
             gpu.set_option("spmv.pk", 1)
             A = gpu.Matrix(rows, cols, rb, ci, va)
             assert A.value_dictionary()["packed"] and A.value_dictionary()["n_distinct"] == len(pool)
-            y = A.spmv(x)
-            assert np.array_equal(y.view(np.uint64), y0.view(np.uint64))
+            for tma in (0, 1):
+                gpu.set_option("spmv.pktma", tma)
+                y = A.spmv(x)
+                assert np.array_equal(y.view(np.uint64), y0.view(np.uint64))
+            gpu.set_option("spmv.pktma", PKTMA_DEFAULT)
         x[0] = 0.25
         xt = rng.standard_normal(rows)
         gpu.set_option("spmv.pk", 0)
