@@ -202,6 +202,7 @@ EpiArgs make_epi(const SpmvArgs& a)
     e.dd_in = a.dd_in;
     e.dd_out = a.dd_out;
     e.xghost = a.xghost;
+    e.xu = a.xu; e.xu_p = a.xu_p; e.xu_alpha = a.xu_alpha; e.xu_iter = a.xu_iter; e.xu_applied = a.xu_applied;
     e.n_owned = (int)a.n_owned;
     e.prefetch = (int)opt("spmv.prefetch", 0.0);
     e.partials = c.partials + (size_t)a.slot * kPartialStride;
@@ -287,10 +288,11 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a)
     // dictionary-packed stream (4 B per entry, spmv_pk.cu) when the operator has one
     if (A.pk != nullptr && a.xghost == nullptr && (a.row_ordered || opt("spmv.pk", 1.0) != 0.0)) {
         // stream staged by TMA ("spmv.pktma") when the dictionary fits shared memory
-        if (opt("spmv.pktma", 0.0) != 0.0 && A.ndict <= 512) return spmv_sell_pk_tma(A, a);
+        if (opt("spmv.pktma", 0.0) != 0.0 && A.ndict <= 512 && a.xu == nullptr) return spmv_sell_pk_tma(A, a);
         return spmv_sell_pk(A, a);
     }
     DB_ARG(!a.row_ordered, "row-ordered vectors need the operator's row-ordered stream");
+    DB_ARG(a.xu == nullptr, "only the packed stream carries the PCG x update");
     int threads = (int)opt("spmv.threads", 128);
     if (threads < 32) threads = 32;
     if (threads > 512) threads = 512;

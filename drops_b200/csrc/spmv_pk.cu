@@ -143,6 +143,10 @@ k_spmv_sell_pk(PkView A, const double* __restrict__ x, double* __restrict__ y, E
     const long long s_end   = A.nslices * (long long)(blockIdx.x + 1) / gridDim.x;
     const double beta = (EPI == EPI_AXMBY) ? (e.beta != nullptr ? *e.beta : e.beta_val) : 0.0;
     dd acc[1] = {dd_zero()};
+    // PCG: x += alpha p of the previous iteration rides on this product (DRAM has the headroom, the
+    // kernel is bound by the L2 -> L1 path), 3 vector passes less in the direction kernel
+    const bool xupd = DOT != 0 && e.xu != nullptr && *e.xu_applied != *e.xu_iter;
+    const double xalpha = xupd ? *e.xu_alpha : 0.0;
 
     for (long long s = s_begin + warp; s < s_end; s += nwarp) {
         const int64_t base = A.slice_ptr[s];
@@ -169,6 +173,7 @@ k_spmv_sell_pk(PkView A, const double* __restrict__ x, double* __restrict__ y, E
             y[row] = out;
             if (DOT && DF == 0) acc[0] = dd_add_prod(acc[0], out, dv);
             if (DOT && DF == 2) acc_smem[threadIdx.x] = dd_add_prod(acc_smem[threadIdx.x], out, __ldg(e.dotv + row));
+            if (xupd) e.xu[row] = __dadd_rn(e.xu[row], __dmul_rn(xalpha, __ldcs(e.xu_p + row)));
         }
     }
     if (DOT && DF == 2) acc[0] = acc_smem[threadIdx.x];
@@ -279,6 +284,8 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
     DB_ARG(a.epilogue == EPI_NONE || a.aux != nullptr, "epilogue needs aux vector");
     DB_ARG(a.dotv == nullptr || a.dot_out != nullptr || a.dd_out != nullptr, "fused dot needs an output scalar");
     DB_ARG(a.dotv != a.y, "the partner of the fused dot must not be the output vector");   // the tail pass re-reads y
+    DB_ARG(a.xu == nullptr || (a.dotv != nullptr && a.xu_p && a.xu_alpha && a.xu_iter && a.xu_applied),
+           "the carried x update needs the fused dot and its scalars");
     if (A.rows == 0) return 0;
     int threads = (int)opt("spmv.pk_threads", 512);
     if (threads < 32) threads = 32;
@@ -292,6 +299,12 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
         long long spc = (long long)opt("spmv.pk_slices_per_cta", 128.0);
         if (spc < 1) spc = 1;
         grid = ((long long)A.nslices + spc - 1) / spc;
+    }
+    // small operators: shrink the CTAs until the grid fills the machine a few times over
+    if (per_sm <= 0.0) {
+        while (threads > 128 && grid < 8LL * c.sm_count) { threads >>= 1; grid <<= 1; }
+        while (grid < 8LL * c.sm_count && grid * 2 * (threads >> 5) <= (long long)A.nslices) grid <<= 1;
+        threads &= ~31;
     }
     const long long max_useful = ((long long)A.nslices * 32 + threads - 1) / threads;
     if (grid > max_useful) grid = max_useful;

@@ -12,6 +12,7 @@ struct SolverScalars {
     double a1, b1, b0;           // Lanczos coefficients
     double h[2];                 // scratch
     double omega;
+    double alpha_prev;           // alpha of the last completed PCG iteration (x update carried by the next SpMV)
     int iter, done, converged, relative, max_iter, pc, hist_cap;
     int x_iter;                  // PCG with the deferred x update: iterations whose alpha*p is already in x
 };
@@ -78,6 +79,12 @@ int pcg_direction(size_t n, double* p, const double* r, const double* d, SolverS
 // was the last one) and then p = z + beta p unless the solve is done.  Element arithmetic unchanged.
 int pcg_update_r(size_t n, double* r, const double* q, const double* d, SolverScalars* S, double* hist);
 int pcg_direction_x(size_t n, double* x, double* p, const double* r, const double* d, SolverScalars* S);
+// x update carried by the SpMV of the NEXT iteration (SpmvArgs::xu, packed stream): the direction is then
+// written out of place, p_new = z + beta p_old (4 passes), because the SpMV that follows still reads
+// p_old for x += alpha p_old; pcg_flush_x applies the update of the last completed iteration after the
+// loop (p_even / p_odd: the two direction buffers, iteration j uses buffer j & 1).
+int pcg_direction_oop(size_t n, double* p_new, const double* p_old, const double* r, const double* d, SolverScalars* S);
+int pcg_flush_x(size_t n, double* x, const double* p_even, const double* p_odd, SolverScalars* S);
 // dot product into a device scalar, skipped while *done != 0
 int vec_dot_unless(size_t n, const double* x, const double* y, double* d_out, const int* done);
 

@@ -93,8 +93,8 @@ def test_spmv_layout_and_launch_options_do_not_change_results(gpu, sigma, thread
         gpu.set_option("spmv.prefetch", 0)
 
 
-PK_DEFAULTS = {"spmv.pktma": None, "spmv.pktma_geometry": 0, "spmv.pktma_slices_per_cta": None, "spmv.pk": 1, "spmv.pkdotform": 2, "pcg.reorder": 1, "pcg.defer_x": 1, "pcg.fused_dot": 1, "spmv.pkvariant": 0, "spmv.pkdotvariant": 0, "spmv.pk_threads": 128,
-               "spmv.pk_slices_per_cta": 16, "spmv.pkdict": 0, "spmv.dotmode": 0, "sell.sigma": 4096,
+PK_DEFAULTS = {"spmv.pktma": None, "spmv.pktma_geometry": 0, "spmv.pktma_slices_per_cta": None, "spmv.pk": 1, "spmv.pkdotform": 2, "pcg.reorder": 1, "pcg.defer_x": 1, "pcg.fused_dot": 1, "pcg.fuse_x": 0, "spmv.pk_threads": 512,
+               "spmv.pk_slices_per_cta": 128, "spmv.pkvariant": 9, "spmv.pkdotvariant": 9, "spmv.pkdict": 0, "spmv.dotmode": 0, "sell.sigma": 4096,
                "sell.valdict": 1, "spmv.exact": 1}
 
 
@@ -227,8 +227,9 @@ def test_value_dictionary_stream_is_bit_identical(gpu, variant, threads, spc, di
         _restore_pk(gpu)
 
 
-@pytest.mark.parametrize("reorder,defer_x,fused_dot,graph", [(1, 1, 1, 1), (1, 0, 0, 0), (0, 1, 0, 1), (0, 0, 1, 0), (1, 1, 0, 0)])
-def test_pcg_forms_agree_with_reference(gpu, reorder, defer_x, fused_dot, graph):
+@pytest.mark.parametrize("reorder,defer_x,fused_dot,graph,fuse_x",
+                         [(1, 1, 1, 1, 1), (1, 1, 1, 0, 1), (1, 1, 1, 1, 0), (1, 0, 0, 0, 0), (0, 1, 0, 1, 1), (0, 0, 1, 0, 0), (1, 1, 0, 0, 1)])
+def test_pcg_forms_agree_with_reference(gpu, reorder, defer_x, fused_dot, graph, fuse_x):
     """Row-ordered solve, deferred x update, separate dot kernel, graph replay: every combination gives
     the reference's iteration count and solution, also when the solve stops inside a chunk, at
     max_iter, or before the first iteration."""
@@ -239,6 +240,7 @@ def test_pcg_forms_agree_with_reference(gpu, reorder, defer_x, fused_dot, graph)
         gpu.set_option("pcg.defer_x", defer_x)
         gpu.set_option("pcg.fused_dot", fused_dot)
         gpu.set_option("pcg.graph", graph)
+        gpu.set_option("pcg.fuse_x", fuse_x)
         A = gmat(gpu, g)
         out = A.pcg_jacobi(np.zeros(A.rows), g["b"], 400, 1e-10, True)
         assert out[0] and out[1] == int(g["sym_pcgjac"][1]) and rel(out[3], g["sym_pcgjac_x"]) <= 1e-12
@@ -246,15 +248,23 @@ def test_pcg_forms_agree_with_reference(gpu, reorder, defer_x, fused_dot, graph)
         assert not out[0] and rel(out[3], g["sym_pcgjac_fixed7_x"]) <= 1e-12
         out = A.pcg_jacobi(g["sym_pcgjac_x"].copy(), g["b"], 50, 1e-6, True)  # converged at iteration 0 or 1
         assert out[0] and out[1] <= 1
-        for check_every in (1, 3, 16):
+        for maxit in (1, 2, 5, 16, 17, 33):                                    # x = the reference's iterate after maxit steps
+            gpu.set_option("pcg.reorder", reorder); gpu.set_option("pcg.defer_x", defer_x); gpu.set_option("pcg.fuse_x", fuse_x)
+            out = A.pcg_jacobi(np.zeros(A.rows), g["b"], maxit, 1e-30, True)
+            gpu.set_option("pcg.reorder", 0); gpu.set_option("pcg.defer_x", 0); gpu.set_option("pcg.fuse_x", 0)
+            ref = A.pcg_jacobi(np.zeros(A.rows), g["b"], maxit, 1e-30, True)
+            assert not out[0] and out[1] == ref[1] and rel(out[3], ref[3]) <= 1e-12 and abs(out[2] - ref[2]) <= 1e-9 * ref[2]
+        gpu.set_option("pcg.reorder", reorder); gpu.set_option("pcg.defer_x", defer_x); gpu.set_option("pcg.fuse_x", fuse_x)
+        for check_every in (1, 2, 3, 16):
             gpu.set_option("pcg.check_every", check_every)
             B = gpu.Matrix(n, n, rb, ci, va)
             xs = gpu.brick_solution_host(2, 10, 1)
             b = B.spmv(xs)
             out = B.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True)
-            gpu.set_option("pcg.reorder", 0); gpu.set_option("pcg.defer_x", 0); gpu.set_option("pcg.fused_dot", 1)
+            gpu.set_option("pcg.reorder", 0); gpu.set_option("pcg.defer_x", 0); gpu.set_option("pcg.fused_dot", 1); gpu.set_option("pcg.fuse_x", 0)
             ref = B.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True)
             gpu.set_option("pcg.reorder", reorder); gpu.set_option("pcg.defer_x", defer_x); gpu.set_option("pcg.fused_dot", fused_dot)
+            gpu.set_option("pcg.fuse_x", fuse_x)
             assert out[0] and out[1] == ref[1] and rel(out[3], ref[3]) <= 1e-12 and rel(out[3], xs) <= 1e-8
     finally:
         gpu.set_option("pcg.check_every", 16)
