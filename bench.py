@@ -211,16 +211,16 @@ def run_ours(args):
     if not os.path.exists(_build.LIB_PATH):
         _build.build()
     capi.init(local)
-    if world > 1:
-        return run_ours_dist(args, rank, world, local, dist)
-
-    fe, N, numbering, iters = args.fe, args.cells, args.numbering, args.iters
-    n, nnz = capi.brick_sizes(fe, N)
     for kv in args.opt:
         k, v = kv.split("=")
         capi.set_option(k, float(v))
     if args.no_pk:
         capi.set_option("sell.valdict", 0)
+    if world > 1:
+        return run_ours_dist(args, rank, world, local, dist)
+
+    fe, N, numbering, iters = args.fe, args.cells, args.numbering, args.iters
+    n, nnz = capi.brick_sizes(fe, N)
     t0 = time.perf_counter()
     A = capi.Matrix.brick(fe, N, numbering)
     capi.synchronize()
@@ -268,7 +268,9 @@ def run_ours(args):
     # and q written by the SpMV (2), r/q/d read + r written (4), x/p/r/d read + x/p written (6) = 12
     # with the deferred x update, 13 without; a separate dot kernel re-reads p and q (+2).
     peak, peak_src = measured_peaks()
-    packed = A.value_dictionary()["packed"] and capi.get_option("spmv.pk", 1.0) != 0.0
+    vdict = A.value_dictionary()
+    layout = A.layout()
+    packed = vdict["packed"] and capi.get_option("spmv.pk", 1.0) != 0.0
     entry_bytes = 4.0 if packed else 12.0
     passes = (12.0 if capi.get_option("pcg.defer_x", 1.0) != 0.0 else 13.0) + \
              (0.0 if capi.get_option("pcg.fused_dot", 1.0) != 0.0 else 2.0)
@@ -388,7 +390,9 @@ def run_ours(args):
                                f"PCGSolverCL<JACPcCL>, {iters} iterations per step, tol=0, relative",
                    "numbering": "vertices-then-edges (DROPS order)" if numbering == 1 else "lexicographic",
                    "cache": "inputs (17 GB matrix, 0.4 GB vectors) far exceed the 126 MB L2; no flush needed",
-                   "spmv_kernel": "sell-32-sigma exact" + (", value dictionary (%d values), 4 B/entry" % A.value_dictionary()["n_distinct"] if packed else ", 12 B/entry"),
+                   "spmv_kernel": "sell-32-sigma exact" + (", value dictionary (%d values), 4 B/entry" % vdict["n_distinct"] if packed else ", 12 B/entry"),
+                   "row_order": ("blocks of the matrix graph" if layout["block_ordered"] else "caller's order") +
+                                (", PCG on row-ordered vectors" if layout["row_ordered_stream"] and capi.get_option("pcg.reorder", 1.0) != 0.0 else ""),
                    "generate_s": gen_s},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "final_relative_residual": resid, "general_12B_stream": general, "other_configs": {"C1_p1_n64": c1},
@@ -503,11 +507,16 @@ def run_ours_dist(args, rank, world, local, dist):
     # roofline of the dominant kernel on rank 0: interior-row SpMV of the partition
     peak, peak_src = measured_peaks()
     frac_int = info["interior_rows"] / max(no, 1)
-    spmv_bytes = (12.0 * info["nnz"] + 4.0 * (no + 1) + 16.0 * no) * frac_int
+    packed = A.format()["interior_packed"] and capi.get_option("spmv.pk", 1.0) != 0.0
+    entry_bytes = 4.0 if packed else 12.0          # bytes per stored entry of the stream the kernel reads
+    passes = 12.0 if capi.get_option("pcg.defer_x", 1.0) != 0.0 else 13.0
+    spmv_bytes = (entry_bytes * info["nnz"] + 4.0 * (no + 1) + 16.0 * no) * frac_int
     spmv_avg_ms = t_int / max(c_int, 1)
     achieved = spmv_bytes / (spmv_avg_ms / 1e3) / 1e9
-    iter_bytes = 12.0 * info["nnz"] + 4.0 * (no + 1) + 13.0 * 8.0 * no
-    roofline = {"bound": "hbm", "kernel": "k_spmv_sell<EPI_NONE,exact,dot> on the interior rows of rank 0's partition",
+    iter_bytes = entry_bytes * info["nnz"] + 4.0 * (no + 1) + passes * 8.0 * no
+    roofline = {"bound": "hbm", "kernel": ("k_spmv_sell_pk" if packed else "k_spmv_sell") +
+                "<EPI_NONE,exact,dot> on the interior rows of rank 0's partition",
+                "bytes_per_stored_entry": entry_bytes,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "traffic": None, "algorithmic_bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_avg_ms,
                 "launches": c_int,

@@ -134,6 +134,7 @@ SIGNATURES = {
     "drops_b200_dist_matrix_create_device": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, C.c_uint64, _vpp]),
     "drops_b200_dist_matrix_destroy": (_i, [_vp]),
     "drops_b200_dist_matrix_info": (_i, [_vp, _szpp, _szpp, _szpp, _szpp, _szpp, _szpp, _szpp]),
+    "drops_b200_dist_matrix_format": (_i, [_vp, _ip, _ip]),
     "drops_b200_dist_matrix_diag": (_i, [_vp, _dp]),
     "drops_b200_dist_spmv_dev": (_i, [_i, _vpp, _vpp, _vpp]),
     "drops_b200_dist_dot": (_i, [_i, _vpp, _vpp, _vpp, _dpp]),
@@ -825,6 +826,11 @@ class DistMatrix:
         check(lib().drops_b200_dist_matrix_info(self.h, *[C.byref(x) for x in v]))
         keys = ["n_owned", "n_ghost", "nnz", "interior_rows", "boundary_rows", "n_send", "device_bytes"]
         return dict(zip(keys, [x.value for x in v]))
+
+    def format(self):
+        pk, nd = C.c_int(), C.c_int()
+        check(lib().drops_b200_dist_matrix_format(self.h, C.byref(pk), C.byref(nd)))
+        return {"interior_packed": bool(pk.value), "n_distinct": nd.value}
 
     def diag(self):
         d = np.zeros(max(self.info()["n_owned"], 1))

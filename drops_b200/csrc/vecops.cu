@@ -410,7 +410,7 @@ int pcg_direction(size_t n, double* p, const double* r, const double* d, SolverS
 
 // ---- deferred x update: 4 + 6 vector passes instead of 7 + 4 ---------------------------------------
 struct OpPcgUpdateR {
-    double* r; const double* q; const double* d; SolverScalars* S; double* hist;
+    double* r; const double* q; const double* d; SolverScalars* S; double* hist; dd* part_out;
     double alpha; int pc; double omega;
     __device__ bool begin()
     {
@@ -430,16 +430,17 @@ struct OpPcgUpdateR {
     __device__ void finish(const dd* acc)
     {
         S->alpha_prev = alpha;
+        if (part_out) { part_out[0] = acc[0]; part_out[1] = acc[1]; return; }      // partitioned: k_dist_scalars finishes
         pcg_update_finish(S, hist, dd_round(acc[0]), dd_round(acc[1]));
     }
 };
 
 __global__ void __launch_bounds__(kReduceThreads)
 k_pcg_update_r(size_t n, double* __restrict__ r, const double* __restrict__ q, const double* __restrict__ d,
-               SolverScalars* S, double* hist, dd* partials, unsigned* ticket)
+               SolverScalars* S, double* hist, dd* part_out, dd* partials, unsigned* ticket)
 {
     __shared__ dd red_smem[2 * 32];
-    OpPcgUpdateR op{r, q, d, S, hist, 0.0, 0, 1.0};
+    OpPcgUpdateR op{r, q, d, S, hist, part_out, 0.0, 0, 1.0};
     if (!op.begin()) return;
     const double alpha = op.alpha, omega = op.omega;
     const bool jac = op.pc == DROPS_B200_PC_JACOBI;
@@ -467,18 +468,18 @@ k_pcg_update_r(size_t n, double* __restrict__ r, const double* __restrict__ q, c
     }
 }
 
-int pcg_update_r(size_t n, double* r, const double* q, const double* d, SolverScalars* S, double* hist)
+int pcg_update_r(size_t n, double* r, const double* q, const double* d, SolverScalars* S, double* hist, dd* part_out)
 {
     if (opt("vec.wide", 1.0) != 0.0 && aligned16(r, q, d)) {
         Ctx& c = ctx();
         ScopedTiming t("pcg.update");
         const int grid = vec_grid(n, kReduceThreads, 4);
-        k_pcg_update_r<<<grid, kReduceThreads, 0, c.stream>>>(n, r, q, d, S, hist, c.partials, c.tickets);
+        k_pcg_update_r<<<grid, kReduceThreads, 0, c.stream>>>(n, r, q, d, S, hist, part_out, c.partials, c.tickets);
         count_launch();
         DB_CUDA(cudaGetLastError());
         return 0;
     }
-    return launch_stream<2>(n, OpPcgUpdateR{r, q, d, S, hist, 0.0, 0, 1.0}, "pcg.update");
+    return launch_stream<2>(n, OpPcgUpdateR{r, q, d, S, hist, part_out, 0.0, 0, 1.0}, "pcg.update");
 }
 
 // x += alpha p for the iteration pcg_update_r just completed (S->iter counts it, S->x_iter does not

@@ -384,6 +384,9 @@ DROPS_B200_API int drops_b200_dist_matrix_destroy(drops_b200_dist_matrix_t A);
 DROPS_B200_API int drops_b200_dist_matrix_info(drops_b200_dist_matrix_t A, size_t* n_owned, size_t* n_ghost, size_t* nnz,
                                                size_t* interior_rows, size_t* boundary_rows, size_t* n_send,
                                                size_t* device_bytes);
+/* Whether the interior-row operator of the partition has the dictionary-packed 4-byte stream, and the
+ * number of distinct values of its dictionary (drops_b200_matrix_value_dictionary for a partition). */
+DROPS_B200_API int drops_b200_dist_matrix_format(drops_b200_dist_matrix_t A, int* interior_packed, int* n_distinct);
 DROPS_B200_API int drops_b200_dist_matrix_diag(drops_b200_dist_matrix_t A, double* diag);
 
 /* Collective operations.  `nparts` partitions driven by this process: 1 with an NCCL communicator
