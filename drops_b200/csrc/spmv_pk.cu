@@ -28,11 +28,23 @@ struct PkView {
     int cbits;
 };
 
+// matrix-stream load: LD = 0 ld.global.cs (evict-first in L1 and L2), 1 = L1::no_allocate + L2 evict-first
+template <int LD>
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t* p)
+{
+    if (LD == 0) return __ldcs(p);
+    uint32_t v;
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
 // Padding is the word (ndict << cbits): column 0 and the extra dictionary slot ndict (0.0), so every
 // load of the unrolled body is unconditional and straight-line; the padded product is computed and
 // then dropped by a select (adding it could turn a -0.0 sum into +0.0, or poison it when x_0 is
 // not finite), which keeps the row sum bit-identical.
-template <bool EXACT, int U, bool SMEM>
+template <bool EXACT, int U, bool SMEM, int LD>
 __device__ __forceinline__ double pk_row_sum(const PkView& A, int64_t base, int width, int lane,
                                              const double* __restrict__ x)
 {
@@ -47,7 +59,7 @@ __device__ __forceinline__ double pk_row_sum(const PkView& A, int64_t base, int 
         uint32_t w[U];
         double xv[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) w[u] = __ldcs(pp + (size_t)(j + u) * 32);
+        for (int u = 0; u < U; ++u) w[u] = ld_stream<LD>(pp + (size_t)(j + u) * 32);
 #pragma unroll
         for (int u = 0; u < U; ++u) xv[u] = __ldg(x + (w[u] & cmask));
 #pragma unroll
@@ -58,7 +70,7 @@ __device__ __forceinline__ double pk_row_sum(const PkView& A, int64_t base, int 
         }
     }
     for (; j < width; ++j) {
-        const uint32_t w = __ldcs(pp + (size_t)j * 32);
+        const uint32_t w = ld_stream<LD>(pp + (size_t)j * 32);
         const double xv = __ldg(x + (w & cmask));
         const double v = SMEM ? sdict[w >> cbits] : __ldg(A.dict + (w >> cbits));
         const double t = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv)) : fma(v, xv, sum);
@@ -166,8 +178,10 @@ k_spmv_sell_pk(PkView A, const double* __restrict__ x, double* __restrict__ y, E
             const int nlines = (int)((A.slice_ptr[sp + 1] - nb) >> 5);
             for (int l = lane; l < nlines; l += 32) prefetch_l2(A.pk + nb + (int64_t)l * 32);
         }
-        const double sum = U > 0 ? pk_row_sum<EXACT, (U > 0 ? U : -U), SMEM>(A, base, width, lane, x)
-                                 : pk_row_sum_pipe<EXACT, (U > 0 ? U : -U), SMEM>(A, base, width, lane, x);
+        // U < 0: software-pipelined form; U >= 100: U - 100 words in flight, stream loaded with L1::no_allocate
+        constexpr int UU = U < 0 ? -U : (U >= 100 ? U - 100 : U);
+        const double sum = U > 0 ? pk_row_sum<EXACT, UU, SMEM, (U >= 100 ? 1 : 0)>(A, base, width, lane, x)
+                                 : pk_row_sum_pipe<EXACT, UU, SMEM>(A, base, width, lane, x);
         if (row >= 0) {
             const double out = apply_epilogue<EPI>(sum, av, e, beta);
             y[row] = out;
@@ -230,7 +244,7 @@ static void launch_pk_v(const PkView& v, const SpmvArgs& a, const EpiArgs& e, in
 // "spmv.pkvariant" (plain product) / "spmv.pkdotvariant" (fused dot): unroll x register cap.
 //   0 = U8/<=40 regs, 1 = U8/<=48, 2 = U4/<=32, 3 = U16/<=64, 4 = U16/<=48, 5 = U8/256 threads/<=40,
 //   6 = U12/<=48, 7 = U4/<=40, 8 = U8/CTAs up to 1024 threads/<=64, 9 = U8/<=512 threads/<=40,
-//   10 = U16/<=512 threads/<=64; software-pipelined: 11 = U4/<=40, 12 = U8/<=48, 13 = U6/<=40, 14 = U4/<=512 threads/<=40
+//   10 = U16/<=512 threads/<=64; software-pipelined: 11 = U4/<=40, 12 = U8/<=48, 13 = U6/<=40, 14 = U4/<=512 threads/<=40; 15 = variant 9 with the stream loaded L1::no_allocate
 constexpr int kPkDefaultVariant = 9;   // measured on C2 (profiles/r01_probe_blockorder.json): 512-thread CTAs x 128 slices
 
 template <int EPI, bool EXACT>
@@ -255,6 +269,7 @@ static bool launch_pk(const PkView& v, const SpmvArgs& a, const EpiArgs& e, int 
             case 12: launch_pk_v<EPI_NONE, true, -8, 128, 10, false>(v, a, e, grid, threads, st); return true;
             case 13: launch_pk_v<EPI_NONE, true, -6, 128, 12, false>(v, a, e, grid, threads, st); return true;
             case 14: launch_pk_v<EPI_NONE, true, -4, 512, 3, false>(v, a, e, grid, threads, st); return true;
+            case 15: launch_pk_v<EPI_NONE, true, 108, 512, 3, false>(v, a, e, grid, threads, st); return true;
             default: break;
         }
     }
