@@ -139,6 +139,7 @@ SIGNATURES = {
     "drops_b200_dist_spmv_dev": (_i, [_i, _vpp, _vpp, _vpp]),
     "drops_b200_dist_dot": (_i, [_i, _vpp, _vpp, _vpp, _dpp]),
     "drops_b200_dist_pcg_dev": (_i, [_i, _vpp, _vpp, _vpp, _i, _d, _ip, _dpp, _i, _vp, _i]),
+    "drops_b200_dist_gmres_dev": (_i, [_i, _vpp, _vpp, _vpp, _i, _d, _i, _ip, _dpp, _i, _i]),
     "drops_b200_brick_slab_generate": (_i, [_i, _i, _i, _d, _i, _i, _vpp]),
     "drops_b200_brick_slab_destroy": (_i, [_vp]),
     "drops_b200_brick_slab_info": (_i, [_vp, _szpp, _szpp, _szpp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
@@ -866,6 +867,13 @@ def dist_pcg(parts, xs, bs, max_iter, tol, relative=False, pc=PC_JACOBI, omega=1
                                                C.byref(it), C.byref(res), int(relative), *hargs))
     out = (bool(conv), it.value, res.value)
     return out + (h,) if hist else out
+
+
+def dist_gmres(parts, xs, bs, restart, max_iter, tol, relative=True, pc=PC_JACOBI, omega=1.0, left=True):
+    it, res = C.c_int(int(max_iter)), C.c_double(float(tol))
+    conv = check(lib().drops_b200_dist_gmres_dev(len(parts), _harr(parts), _harr(xs), _harr(bs), int(pc), float(omega),
+                                                 int(restart), C.byref(it), C.byref(res), int(relative), int(left)))
+    return bool(conv), it.value, res.value
 
 
 class BrickSlab:

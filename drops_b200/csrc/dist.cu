@@ -27,6 +27,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 namespace db200 {
@@ -145,7 +146,7 @@ __global__ void k_pack(long long n, const int32_t* __restrict__ idx, const doubl
     if (i < n) out[i] = x[idx[i]];
 }
 
-enum ScalarPhase { PH_DOT = 0, PH_LAMBDA = 1, PH_SETUP = 2, PH_UPDATE = 3 };
+enum ScalarPhase { PH_DOT = 0, PH_LAMBDA = 1, PH_SETUP = 2, PH_UPDATE = 3, PH_NORM = 4 };
 
 // Sums the ranks' partials in rank order (the same on every rank) and does the scalar bookkeeping
 // that the last block of the fused kernels does on a single GPU.
@@ -159,6 +160,7 @@ __global__ void k_dist_scalars(int phase, SolverScalars* S, double* hist, const 
     for (int r = 0; r < world; ++r)
         for (int q = 0; q < nq; ++q) acc[q] = dd_add(acc[q], gathered[r * nq + q]);
     if (phase == PH_DOT) *out = dd_round(acc[0]);
+    else if (phase == PH_NORM) *out = sqrt(dd_round(acc[0]));
     else if (phase == PH_LAMBDA) S->lambda = dd_round(acc[0]);
     else if (phase == PH_SETUP) pcg_setup_finish(S, hist, dd_round(acc[0]), dd_round(acc[1]), dd_round(acc[2]));
     else pcg_update_finish(S, hist, dd_round(acc[0]), dd_round(acc[1]));
@@ -283,7 +285,7 @@ static void free_dist_matrix(drops_b200_dist_matrix_s* M)
     free_sell(M->sell_int); free_sell(M->sell_bnd);
     dev_free(M->diag); dev_free(M->ghost); dev_free(M->sendbuf); dev_free(M->d_send_idx);
     for (double* w : M->work) dev_free(w);
-    dev_free(M->d_scalars); dev_free(M->d_hist);
+    dev_free(M->d_scalars); dev_free(M->d_hist); dev_free(M->d_small);
     delete M;
 }
 
@@ -664,6 +666,196 @@ int dist_pcg(int np, drops_b200_dist_matrix_s* const* P, double* const* x, const
     return h.converged ? 1 : 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// GMRES(m) on the partitioned system -- the serial driver of num/krylovsolver.h:320-461 (modified
+// Gram-Schmidt, Givens rotations on the host) with every reduction summed over the ranks in rank
+// order: partial -> all-gather -> k_dist_scalars, result left on the device for the fused axpy of the
+// next Gram-Schmidt step (no host round trip inside a column; one fetch of the column at its end).
+// All ranks hold bit-identical Hessenberg columns, so they rotate, stop and restart in step.
+// The reference's own distributed variants (krylovsolver.h:528-916) need one GlobalSum per
+// Gram-Schmidt step as well (or one per column with classical Gram-Schmidt).
+// ------------------------------------------------------------------------------------------
+static void gm_gen_rot(double& dx, double& dy, double& cs, double& sn)     // :258-271
+{
+    if (dy == 0.0) { cs = 1.0; sn = 0.0; }
+    else { const double r = std::sqrt(dx * dx + dy * dy); cs = dx / r; sn = dy / r; }
+}
+static void gm_app_rot(double& dx, double& dy, double cs, double sn)       // :274-279
+{
+    const double tmp = cs * dx + sn * dy;
+    dy = -sn * dx + cs * dy;
+    dx = tmp;
+}
+
+int dist_gmres(int np, drops_b200_dist_matrix_s* const* P, double* const* x, const double* const* b, int pc, double omega,
+               int restart, int* max_iter, double* tol, int relative, int left)
+{
+    DB_CHECK(check_parts(np, P));
+    DB_ARG(max_iter && tol, "null max_iter/tol");
+    DB_ARG(pc == DROPS_B200_PC_DUMMY || pc == DROPS_B200_PC_JACOBI, "unknown preconditioner");
+    Ctx& c = ctx();
+    cudaStream_t st = c.stream;
+    drops_b200_comm_s* comm = P[0]->comm;
+    const int m = restart <= *max_iter ? restart : *max_iter;                  // :327
+    DB_ARG(m >= 2, "GMRES needs restart >= 2 and max_iter >= 2");
+    const bool jac = pc == DROPS_B200_PC_JACOBI;
+    {
+        double flag = 0.0;
+        for (int p = 0; p < np; ++p) if (jac && !P[p]->diag_ok) flag = 1.0;
+        DB_CHECK(drops_b200_comm_allreduce_max(comm, &flag));
+        if (flag != 0.0) { set_error("JACPcCL: at least one row (on some rank) stores no diagonal entry"); return DROPS_B200_E_NODIAG; }
+    }
+    // per partition: r, w, tmp, z, basis v[0..m-1]; small device block h[m+1] | y[m] | vptrs[m] | scal[4]
+    struct Part { double *r, *w, *tmp, *z; std::vector<double*> v; double *d_h, *d_y, *d_scal; const double** d_vptrs; size_t n; };
+    std::vector<Part> W((size_t)np);
+    for (int p = 0; p < np; ++p) {
+        Part& w = W[(size_t)p];
+        w.n = P[p]->n_owned;
+        DB_CHECK(ensure_part_scalars(P[p], 1));
+        w.r = dwork(P[p], 0); w.w = dwork(P[p], 1); w.tmp = dwork(P[p], 2); w.z = dwork(P[p], 3);
+        if (!w.r || !w.w || !w.tmp || !w.z) return DROPS_B200_E_NOMEM;
+        w.v.resize((size_t)m);
+        for (int i = 0; i < m; ++i) { w.v[(size_t)i] = dwork(P[p], 4 + i); if (!w.v[(size_t)i]) return DROPS_B200_E_NOMEM; }
+        const size_t need = (size_t)3 * m + 8;
+        if (need > P[p]->small_alloc) {
+            dev_free(P[p]->d_small); P[p]->d_small = nullptr; P[p]->small_alloc = 0;
+            DB_CHECK(dev_alloc(&P[p]->d_small, need));
+            P[p]->small_alloc = need;
+        }
+        w.d_h = P[p]->d_small; w.d_y = w.d_h + (m + 1);
+        w.d_vptrs = reinterpret_cast<const double**>(w.d_y + m);
+        w.d_scal = reinterpret_cast<double*>(w.d_vptrs + m);
+        DB_CUDA(cudaMemcpyAsync(w.d_vptrs, w.v.data(), (size_t)m * sizeof(double*), cudaMemcpyHostToDevice, st));
+    }
+    std::vector<double> H((size_t)m * m, 0.0), s(m, 0.0), cs(m, 0.0), sn(m, 0.0), y(m, 0.0), hcol(m + 1, 0.0);
+    auto Hat = [&](int i, int j) -> double& { return H[(size_t)j * m + i]; };
+    std::vector<PartArgs> a((size_t)np);
+
+    auto apply_pc = [&](int p, double* out, const double* in) -> int {
+        if (jac) return vec_jacobi(W[(size_t)p].n, omega, P[p]->diag, in, out);
+        return vec_copy(W[(size_t)p].n, out, in);
+    };
+    // global reduction: local partials are in the gather slots; result -> out_of(p) on every partition
+    auto reduce_to = [&](int phase, double* (*slot)(Part&, int), int idx) -> int {
+        DB_CHECK(allgather_partials(comm, 1));
+        for (int p = 0; p < np; ++p) DB_CHECK(scalars_kernel(phase, P[p], nullptr, slot(W[(size_t)p], idx)));
+        return 0;
+    };
+    auto h_slot = [](Part& w, int k) -> double* { return w.d_h + k; };
+    auto scal_slot = [](Part& w, int k) -> double* { return w.d_scal + k; };
+    auto norm_of = [&](double* Part::*vec, int scal_idx) -> int {            // scal[idx] = |vec|_2 over all ranks
+        for (int p = 0; p < np; ++p)
+            DB_CHECK(mgs_step(W[(size_t)p].n, W[(size_t)p].*vec, nullptr, nullptr, nullptr, nullptr, true, gather_slot(P[p], 1)));
+        return reduce_to(PH_NORM, scal_slot, scal_idx);
+    };
+    auto residual = [&]() -> int {                                            // r = [M^-1](b - A x)
+        for (int p = 0; p < np; ++p) {
+            a[(size_t)p] = PartArgs(); a[(size_t)p].x = x[p]; a[(size_t)p].epilogue = EPI_RESID; a[(size_t)p].aux = b[p];
+            a[(size_t)p].y = (left && jac) ? W[(size_t)p].tmp : W[(size_t)p].r;
+        }
+        DB_CHECK(dist_spmv_run(np, P, a.data()));
+        if (left && jac) for (int p = 0; p < np; ++p) DB_CHECK(apply_pc(p, W[(size_t)p].r, W[(size_t)p].tmp));
+        return 0;
+    };
+    auto fetch_host = [&](const double* d, double* h, size_t cnt) -> int {
+        DB_CUDA(cudaMemcpyAsync(h, d, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
+        DB_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    };
+    auto update_x = [&](int k) -> int {                                       // GMRES_Update :282-297
+        if (k < 0) return 0;
+        y = s;
+        for (int i = k; i >= 0; --i) {
+            y[(size_t)i] /= Hat(i, i);
+            for (int j = i - 1; j >= 0; --j) y[(size_t)j] -= Hat(j, i) * y[(size_t)i];
+        }
+        for (int p = 0; p < np; ++p) {
+            Part& w = W[(size_t)p];
+            DB_CUDA(cudaMemcpyAsync(w.d_y, y.data(), (size_t)(k + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
+            if (left) DB_CHECK(multi_axpy(w.n, x[p], w.d_vptrs, w.d_y, k + 1));
+            else {                                                            // :416-421
+                DB_CHECK(vec_fill(w.n, w.z, 0.0));
+                DB_CHECK(multi_axpy(w.n, w.z, w.d_vptrs, w.d_y, k + 1));
+                DB_CHECK(apply_pc(p, w.tmp, w.z));
+                DB_CHECK(vec_axpy(w.n, 1.0, w.tmp, x[p]));
+            }
+        }
+        DB_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    };
+
+    double beta, normb, resid;
+    DB_CHECK(residual());
+    DB_CHECK(norm_of(&Part::r, 0));                                            // beta = |r|
+    for (int p = 0; p < np; ++p) {
+        if (left) DB_CHECK(apply_pc(p, W[(size_t)p].w, b[p]));                 // normb = |M^-1 b|  :346-347
+        else DB_CHECK(vec_copy(W[(size_t)p].n, W[(size_t)p].w, b[p]));         // normb = |b|       :340
+    }
+    DB_CHECK(norm_of(&Part::w, 1));
+    DB_CHECK(fetch_host(W[0].d_scal, c.h_scalars, 2));
+    beta = c.h_scalars[0]; normb = c.h_scalars[1];
+    if (normb == 0.0 || !relative) normb = 1.0;
+    resid = beta / normb;
+    if (resid <= *tol) { *tol = resid; *max_iter = 0; return 1; }
+
+    int j = 1;
+    while (j <= *max_iter) {
+        for (int p = 0; p < np; ++p) DB_CHECK(vec_scale_inv(W[(size_t)p].n, W[(size_t)p].v[0], W[(size_t)p].r, W[(size_t)p].d_scal + 0));
+        std::fill(s.begin(), s.end(), 0.0);
+        s[0] = beta;
+        int i;
+        for (i = 0; i < m - 1 && j <= *max_iter; ++i, ++j) {
+            for (int p = 0; p < np; ++p) {
+                Part& w = W[(size_t)p];
+                a[(size_t)p] = PartArgs();
+                if (left) {                                                   // w = M^-1 (A v[i])  :377
+                    a[(size_t)p].x = w.v[(size_t)i]; a[(size_t)p].y = w.w;
+                    if (jac) { a[(size_t)p].epilogue = EPI_JACOBI; a[(size_t)p].aux = P[p]->diag; a[(size_t)p].omega = omega; }
+                } else {                                                      // w = A (M^-1 v[i])  :372-376
+                    DB_CHECK(apply_pc(p, w.tmp, w.v[(size_t)i]));
+                    a[(size_t)p].x = w.tmp; a[(size_t)p].y = w.w;
+                }
+            }
+            DB_CHECK(dist_spmv_run(np, P, a.data()));
+            for (int k = 0; k <= i; ++k) {                                    // modified Gram-Schmidt  :378-381
+                for (int p = 0; p < np; ++p) {
+                    Part& w = W[(size_t)p];
+                    DB_CHECK(mgs_step(w.n, w.w, k > 0 ? w.v[(size_t)k - 1] : nullptr, w.d_h + (k - 1), w.v[(size_t)k], nullptr, false,
+                                      gather_slot(P[p], 1)));
+                }
+                DB_CHECK(reduce_to(PH_DOT, h_slot, k));
+            }
+            for (int p = 0; p < np; ++p) {
+                Part& w = W[(size_t)p];
+                DB_CHECK(mgs_step(w.n, w.w, w.v[(size_t)i], w.d_h + i, nullptr, nullptr, true, gather_slot(P[p], 1)));   // H(i+1,i) = |w|  :383
+            }
+            DB_CHECK(reduce_to(PH_NORM, h_slot, i + 1));
+            for (int p = 0; p < np; ++p) DB_CHECK(vec_scale_inv(W[(size_t)p].n, W[(size_t)p].v[(size_t)i + 1], W[(size_t)p].w, W[(size_t)p].d_h + i + 1));
+            DB_CHECK(fetch_host(W[0].d_h, hcol.data(), (size_t)(i + 2)));
+            for (int k = 0; k <= i + 1; ++k) Hat(k, i) = hcol[(size_t)k];
+            for (int k = 0; k < i; ++k) gm_app_rot(Hat(k, i), Hat(k + 1, i), cs[(size_t)k], sn[(size_t)k]);
+            gm_gen_rot(Hat(i, i), Hat(i + 1, i), cs[(size_t)i], sn[(size_t)i]);
+            gm_app_rot(Hat(i, i), Hat(i + 1, i), cs[(size_t)i], sn[(size_t)i]);
+            gm_app_rot(s[(size_t)i], s[(size_t)i + 1], cs[(size_t)i], sn[(size_t)i]);
+            resid = std::abs(s[(size_t)i + 1]) / normb;                       // :393
+            if (resid <= *tol) {                                              // :413-429
+                DB_CHECK(update_x(i));
+                *tol = resid; *max_iter = j;
+                return 1;
+            }
+        }
+        DB_CHECK(update_x(i - 1));                                            // :431-444
+        DB_CHECK(residual());
+        DB_CHECK(norm_of(&Part::r, 0));
+        DB_CHECK(fetch_host(W[0].d_scal, c.h_scalars, 1));
+        beta = c.h_scalars[0];
+        resid = beta / normb;
+        if (resid <= *tol) { *tol = resid; *max_iter = j; return 1; }         // :449-456
+    }
+    *tol = resid;
+    return 0;
+}
+
 }  // namespace db200
 
 // ------------------------------------------------------------------------------------------
@@ -884,6 +1076,22 @@ int drops_b200_dist_dot(int nparts, const drops_b200_dist_matrix_t* A, const dro
     DB_CUDA(cudaStreamSynchronize(c.stream));
     *result = c.h_scalars[0];
     return 0;
+}
+
+int drops_b200_dist_gmres_dev(int nparts, const drops_b200_dist_matrix_t* A, const drops_b200_vector_t* x,
+                              const drops_b200_vector_t* b, int pc, double omega, int restart, int* max_iter, double* tol,
+                              int relative, int left_precond)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(A && x && b, "null argument");
+    DB_CHECK(check_parts(nparts, A));
+    std::vector<double*> xs((size_t)nparts);
+    std::vector<const double*> bs((size_t)nparts);
+    for (int p = 0; p < nparts; ++p) {
+        DB_ARG(x[p] && b[p] && x[p]->n == A[p]->n_owned && b[p]->n == A[p]->n_owned, "vector size != owned rows of the partition");
+        xs[(size_t)p] = x[p]->d; bs[(size_t)p] = b[p]->d;
+    }
+    return dist_gmres(nparts, A, xs.data(), bs.data(), pc, omega, restart, max_iter, tol, relative, left_precond);
 }
 
 int drops_b200_dist_pcg_dev(int nparts, const drops_b200_dist_matrix_t* A, const drops_b200_vector_t* x,

@@ -65,6 +65,8 @@ struct drops_b200_dist_matrix_s {
     void* d_scalars = nullptr;               // db200::SolverScalars
     double* d_hist = nullptr;
     int hist_alloc = 0;
+    double* d_small = nullptr;               // GMRES: Hessenberg column, y, basis pointers, scalars
+    size_t small_alloc = 0;
 };
 
 namespace db200 {

@@ -809,7 +809,7 @@ int vec_scale_inv(size_t n, double* out, const double* in, const double* d_scale
 
 template <bool PREV, bool NORM>
 struct OpMgs {
-    double* w; const double* vprev; const double* hprev; const double* vk; double* hout; double h;
+    double* w; const double* vprev; const double* hprev; const double* vk; double* hout; double h; dd* part_out;
     __device__ bool begin() { h = PREV ? *hprev : 0.0; return true; }
     __device__ void elem(size_t i, dd* acc)
     {
@@ -817,17 +817,21 @@ struct OpMgs {
         if (PREV) { wi = sub(wi, mul(h, vprev[i])); w[i] = wi; }   // w -= H(k,i)*v[k]  :380
         acc[0] = NORM ? dd_add_prod(acc[0], wi, wi) : dd_add_prod(acc[0], wi, vk[i]);
     }
-    __device__ void finish(const dd* acc) { *hout = NORM ? sqrt(dd_round(acc[0])) : dd_round(acc[0]); }
+    __device__ void finish(const dd* acc)
+    {
+        if (part_out) { *part_out = acc[0]; return; }      // partitioned: the sum over ranks (and the sqrt) come later
+        *hout = NORM ? sqrt(dd_round(acc[0])) : dd_round(acc[0]);
+    }
 };
 int mgs_step(size_t n, double* w, const double* vprev, const double* d_hprev, const double* vk,
-             double* d_hout, bool want_norm)
+             double* d_hout, bool want_norm, dd* part_out)
 {
     if (vprev) {
-        if (want_norm) return launch_stream<1>(n, OpMgs<true, true>{w, vprev, d_hprev, vk, d_hout, 0.0}, "gmres.mgs");
-        return launch_stream<1>(n, OpMgs<true, false>{w, vprev, d_hprev, vk, d_hout, 0.0}, "gmres.mgs");
+        if (want_norm) return launch_stream<1>(n, OpMgs<true, true>{w, vprev, d_hprev, vk, d_hout, 0.0, part_out}, "gmres.mgs");
+        return launch_stream<1>(n, OpMgs<true, false>{w, vprev, d_hprev, vk, d_hout, 0.0, part_out}, "gmres.mgs");
     }
-    if (want_norm) return launch_stream<1>(n, OpMgs<false, true>{w, vprev, d_hprev, vk, d_hout, 0.0}, "gmres.mgs");
-    return launch_stream<1>(n, OpMgs<false, false>{w, vprev, d_hprev, vk, d_hout, 0.0}, "gmres.mgs");
+    if (want_norm) return launch_stream<1>(n, OpMgs<false, true>{w, vprev, d_hprev, vk, d_hout, 0.0, part_out}, "gmres.mgs");
+    return launch_stream<1>(n, OpMgs<false, false>{w, vprev, d_hprev, vk, d_hout, 0.0, part_out}, "gmres.mgs");
 }
 
 struct OpMultiAxpy {

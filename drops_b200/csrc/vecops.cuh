@@ -98,8 +98,10 @@ int cg_direction(size_t n, double* dvec, const double* r, SolverScalars* S);
 // out = in * (1/(*d_scale))                                                      :366, :384
 int vec_scale_inv(size_t n, double* out, const double* in, const double* d_scale);
 // if vprev: w -= (*d_hprev) * vprev.  Then *d_hout = dot(w, vk) (vk != null) or |w|_2 (vk == null).
+// part_out != nullptr (partitioned system): the local double-double partial of the reduction goes to
+// *part_out unrounded (for the norm: of w.w, without the sqrt) and d_hout is not written.
 int mgs_step(size_t n, double* w, const double* vprev, const double* d_hprev, const double* vk,
-             double* d_hout, bool want_norm);
+             double* d_hout, bool want_norm, dd* part_out = nullptr);
 // x_e = (((x_e + y0 v0_e) + y1 v1_e) + ...) for k vectors; y on device.         :282-297
 int multi_axpy(size_t n, double* x, const double* const* d_vptrs, const double* d_y, int k);
 

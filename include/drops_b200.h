@@ -401,6 +401,14 @@ DROPS_B200_API int drops_b200_dist_pcg_dev(int nparts, const drops_b200_dist_mat
                                            const drops_b200_vector_t* x, const drops_b200_vector_t* b, int pc,
                                            double omega, int* max_iter, double* tol, int relative, double* hist,
                                            int hist_cap);
+/* GMRES(m) on the partitioned system: the serial driver of num/krylovsolver.h:320-461 (modified Gram-Schmidt,
+ * left or right preconditioning with JACPcCL / DummyPcCL), every dot product summed over the ranks in rank
+ * order (one small all-gather per Gram-Schmidt step -- what the reference's distributed variants,
+ * krylovsolver.h:528-916, do with GlobalSum).  All ranks compute identical Hessenberg columns and stop in the
+ * same iteration.  Arguments and return value as drops_b200_gmres_dev. */
+DROPS_B200_API int drops_b200_dist_gmres_dev(int nparts, const drops_b200_dist_matrix_t* A, const drops_b200_vector_t* x,
+                                             const drops_b200_vector_t* b, int pc, double omega, int restart,
+                                             int* max_iter, double* tol, int relative, int left_precond);
 
 /* -- synthetic brick, z-slab partition: rank r owns the lattice planes [k0, k1) (1-based, M planes
  *    split evenly), rows in ascending global id.  Generated on the device, global ids as above. */

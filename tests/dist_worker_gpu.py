@@ -53,9 +53,21 @@ def main():
         tl = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(tl, t)
         assert all(torch.equal(a, t) for a in tl)
+        # GMRES(20) + Jacobi over NCCL against the single-GPU driver
+        gref = G.gmres_jacobi(np.zeros(n), bref, 20, 3000, 1e-10, True, 1.0, True)
+        xg = capi.Vector(owned.size)
+        gconv, git, gres = capi.dist_gmres([A], [xg], [b], 20, 3000, 1e-10, True)
+        assert gconv and gref[0] and abs(git - gref[1]) <= 1, (git, gref[1])
+        gerr = np.linalg.norm(xg.download() - gref[3][owned]) / np.linalg.norm(gref[3][owned])
+        assert gerr <= 1e-8, gerr
+        t = torch.tensor([float(git), gres], dtype=torch.float64, device="cuda")
+        tl = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(tl, t)
+        assert all(torch.equal(a, t) for a in tl)
         if rank == 0:
             print(f"P{fe} N={N} numbering={numbering} world={world}: iters {it} (single GPU {ref[1]}), "
-                  f"rel.diff {err:.2e}, ghosts {ex.n_ghost}, info {A.info()}", flush=True)
+                  f"rel.diff {err:.2e}, gmres iters {git} (single GPU {gref[1]}), rel.diff {gerr:.2e}, "
+                  f"ghosts {ex.n_ghost}, info {A.info()}", flush=True)
     dist.barrier()
     print("WORKER_OK", rank, flush=True)
     dist.destroy_process_group()

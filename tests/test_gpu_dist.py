@@ -90,6 +90,41 @@ def test_partitioned_matches_reference_golden(gpu, world):
     assert conv and abs(it - int(g["sym_pcgjac_w08"][1])) <= 1 and rel(gather(loc, x0, n), g["sym_pcgjac_w08_x"]) <= 1e-10
 
 
+@pytest.mark.parametrize("name,tag,world", [("brick_fe2_N6_num1.npz", "sym", 1), ("brick_fe2_N6_num1.npz", "sym", 3),
+                                            ("brick_fe2_N4_num1_nonsym.npz", "nonsym", 2), ("brick_fe2_N4_num1_nonsym.npz", "nonsym", 4)])
+def test_partitioned_gmres_matches_reference_golden(gpu, name, tag, world):
+    """GMRES(m) on the partitioned system (rank-ordered reductions, Givens rotations on the host of every
+    rank) against the compiled reference's serial GMRES: iteration counts +-1, solutions 1e-10 / 1e-8."""
+    g = load_golden(name)
+    n = int(g["rows"])
+    rb, ci, va = g["rowbeg"], g["colind"], g["val"]
+    part = gpu.partition_rows(rb, ci, world)
+    comm, loc, mats = build_parts(gpu, rb, ci, va, part, world)
+    bs = scatter(gpu, loc, g["b"])
+    single = gpu.Matrix(n, n, rb, ci, va)
+    for key, restart, left, x_rtol in ((f"{tag}_gmresjac_l1", 20, True, 1e-10), (f"{tag}_gmresjac_l0", 20, False, 1e-10),
+                                       (f"{tag}_gmresjac_m5", 5, True, 1e-8)):
+        x0 = [gpu.Vector(l[0].size) for l in loc]
+        conv, it, res = gpu.dist_gmres(mats, x0, bs, restart, 400, 1e-10, True, left=left)
+        rconv, rit, rres = bool(g[key][0]), int(g[key][1]), float(g[key][2])
+        assert conv == rconv and abs(it - rit) <= 1, (key, it, rit)
+        xg = gather(loc, x0, n)
+        if it == rit:
+            assert abs(res - rres) <= 1e-3 * abs(rres) + 1e-15
+            assert rel(xg, g[key + "_x"]) <= x_rtol, (key, rel(xg, g[key + "_x"]))
+        one = single.gmres_jacobi(np.zeros(n), g["b"], restart, 400, 1e-10, True, 1.0, left)
+        assert one[1] == it and rel(xg, one[3]) <= 1e-9
+    if tag == "sym":
+        x0 = [gpu.Vector(l[0].size) for l in loc]
+        conv, it, res = gpu.dist_gmres(mats, x0, bs, 20, 400, 1e-10, False, pc=gpu.PC_DUMMY)
+        assert conv and abs(it - int(g["sym_gmresdummy"][1])) <= 1
+        assert rel(gather(loc, x0, n), g["sym_gmresdummy_x"]) <= 1e-9
+    # max_iter reached: not converged, iteration budget untouched
+    x0 = [gpu.Vector(l[0].size) for l in loc]
+    conv, it, res = gpu.dist_gmres(mats, x0, bs, 4, 6, 1e-30, True)
+    assert not conv and it == 6
+
+
 @pytest.mark.parametrize("fe,N,numbering,world", [(2, 16, 1, 4), (2, 16, 0, 3), (1, 24, 0, 2), (2, 12, 1, 8)])
 def test_brick_slabs_match_single_gpu(gpu, fe, N, numbering, world):
     """Device-generated z-slabs (the multi-GPU bench path) against the single-GPU operator."""
