@@ -270,8 +270,8 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     vdict = A.value_dictionary()
     layout = A.layout()
-    packed = vdict["packed"] and capi.get_option("spmv.pk", 1.0) != 0.0
-    entry_bytes = 4.0 if packed else 12.0
+    packed = (vdict["packed"] or vdict["six_byte"]) and capi.get_option("spmv.pk", 1.0) != 0.0
+    entry_bytes = (4.0 if vdict["packed"] else 6.0) if packed else 12.0
     passes = (12.0 if capi.get_option("pcg.defer_x", 1.0) != 0.0 else 13.0) + \
              (0.0 if capi.get_option("pcg.fused_dot", 1.0) != 0.0 else 2.0)
     spmv_bytes = entry_bytes * nnz + 4.0 * (n + 1) + 16.0 * n
@@ -280,7 +280,7 @@ def run_ours(args):
     survey_iter_bytes = 12.0 * nnz + 4.0 * (n + 1) + 13.0 * 8.0 * n
     spmv_avg_ms = spmv_ms / max(spmv_cnt, 1)
     achieved = spmv_bytes / (spmv_avg_ms / 1e3) / 1e9
-    kernel_name = ("k_spmv_sell_pk<EPI_NONE,exact,dot> (q = A p fused with p.q, dictionary-packed 4-byte stream)"
+    kernel_name = ("k_spmv_sell_pk<EPI_NONE,exact,dot> (q = A p fused with p.q, dictionary-packed %d-byte stream)" % int(entry_bytes)
                    if packed else "k_spmv_sell<EPI_NONE,exact,dot> (q = A p fused with p.q)")
     roofline = {"bound": "hbm", "kernel": kernel_name,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -390,7 +390,7 @@ def run_ours(args):
                                f"PCGSolverCL<JACPcCL>, {iters} iterations per step, tol=0, relative",
                    "numbering": "vertices-then-edges (DROPS order)" if numbering == 1 else "lexicographic",
                    "cache": "inputs (17 GB matrix, 0.4 GB vectors) far exceed the 126 MB L2; no flush needed",
-                   "spmv_kernel": "sell-32-sigma exact" + (", value dictionary (%d values), 4 B/entry" % vdict["n_distinct"] if packed else ", 12 B/entry"),
+                   "spmv_kernel": "sell-32-sigma exact" + (", value dictionary (%d values), %d B/entry" % (vdict["n_distinct"], int(entry_bytes)) if packed else ", 12 B/entry"),
                    "row_order": ("blocks of the matrix graph" if layout["block_ordered"] else "caller's order") +
                                 (", PCG on row-ordered vectors" if layout["row_ordered_stream"] and capi.get_option("pcg.reorder", 1.0) != 0.0 else ""),
                    "generate_s": gen_s},

@@ -398,7 +398,7 @@ class Matrix:
     def value_dictionary(self, transposed=False):
         nd, pk, cb = C.c_int(), C.c_int(), C.c_int()
         check(lib().drops_b200_matrix_value_dictionary(self.h, int(transposed), C.byref(nd), C.byref(pk), C.byref(cb)))
-        return {"n_distinct": nd.value, "packed": bool(pk.value), "column_bits": cb.value}
+        return {"n_distinct": nd.value, "packed": pk.value == 1, "six_byte": pk.value == 2, "column_bits": cb.value}
 
     def download(self):
         rb = np.zeros(self.rows + 1, np.uint64)

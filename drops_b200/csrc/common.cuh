@@ -330,6 +330,7 @@ struct SellOp {
     // neighbours in x (a gather touches 8-9 sectors instead of ~14 on the P2 brick, where DOF classes
     // alternate along a mesh line).  Vectors of that numbering have npos = 32*nslices entries
     // (padding positions hold 0); the entries of a row keep their order, so every y_i keeps its bits.
+    uint16_t* vidx = nullptr;        // instead of pk when the bits do not fit one word: 16-bit dictionary index beside col (6 B / entry)
     uint32_t* pkp = nullptr;         // padded entries: (dict index << cbits) | position of the column
     size_t npos = 0;
 };

@@ -356,7 +356,7 @@ void free_sell(SellOp& s)
 {
     dev_free(s.slice_ptr); dev_free(s.col); dev_free(s.val); dev_free(s.perm);
     dev_free(s.col16); dev_free(s.cbase); dev_free(s.wide);
-    dev_free(s.pk); dev_free(s.dict); dev_free(s.pkp);
+    dev_free(s.pk); dev_free(s.dict); dev_free(s.pkp); dev_free(s.vidx);
     s = SellOp();
 }
 
@@ -450,6 +450,23 @@ int build_sell(const CsrDev& A, SellOp& S, size_t* bytes, const int32_t* rowmap,
     return build_value_dictionary(S, bytes);
 }
 
+// vidx = index of val in the sorted dictionary (16 bit); padding (col < 0) gets slot ndict = 0.0
+__global__ void __launch_bounds__(256)
+k_dict_index16(long long n, const int32_t* __restrict__ col, const double* __restrict__ val,
+               const unsigned long long* __restrict__ keys, int ndict, uint16_t* __restrict__ vidx)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (__ldcs(col + i) < 0) { vidx[i] = (uint16_t)ndict; return; }
+    const unsigned long long key = (unsigned long long)__double_as_longlong(__ldcs(val + i));
+    int lo = 0, hi = ndict;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(keys + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    vidx[i] = (uint16_t)lo;
+}
+
 __global__ void k_inverse_perm(long long npos, const int32_t* __restrict__ perm, int32_t* __restrict__ iperm)
 {
     const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -481,8 +498,8 @@ static int bits_for(unsigned long long count)      // bits that distinguish `cou
 int build_value_dictionary(SellOp& S, size_t* bytes)
 {
     cudaStream_t st = ctx().stream;
-    dev_free(S.pk); dev_free(S.dict); dev_free(S.pkp);
-    S.pk = nullptr; S.dict = nullptr; S.pkp = nullptr; S.ndict = 0; S.cbits = 0; S.npos = 0;
+    dev_free(S.pk); dev_free(S.dict); dev_free(S.pkp); dev_free(S.vidx);
+    S.pk = nullptr; S.dict = nullptr; S.pkp = nullptr; S.vidx = nullptr; S.ndict = 0; S.cbits = 0; S.npos = 0;
     if (S.padded == 0 || S.col == nullptr || S.val == nullptr || opt("sell.valdict", 1.0) == 0.0) return 0;
     // columns and, for the row-ordered twin, positions (32 * nslices >= rows) share the low bits
     const int cbits = std::max(1, bits_for((unsigned long long)std::max<size_t>(std::max(S.cols, S.nslices * 32), 1)));
@@ -505,8 +522,11 @@ int build_value_dictionary(SellOp& S, size_t* bytes)
     if (e == cudaSuccess) e = cudaMemcpyAsync(&count, d_count, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) fail(e, "value dictionary: collect");
-    // index field: one code more than ndict -- slot ndict (0.0) belongs to the padding word
-    if (status == 0 && count >= 1 && count <= kDictMax && cbits + bits_for((unsigned long long)count + 1) <= 32) {
+    // one word per entry when column bits + index bits fit ("sell.pack_bits", 32; the index field has one
+    // code more than ndict: slot ndict (0.0) belongs to the padding word); otherwise the dictionary still
+    // pays as a 16-bit index beside the int32 column: 6 instead of 12 bytes per entry
+    const bool one_word = cbits + bits_for((unsigned long long)count + 1) <= (int)opt("sell.pack_bits", 32.0);
+    if (status == 0 && count >= 1 && count <= kDictMax) {
         std::vector<unsigned long long> host(cap);
         e = cudaMemcpyAsync(host.data(), table, cap * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -525,11 +545,14 @@ int build_value_dictionary(SellOp& S, size_t* bytes)
         std::vector<double> dict_host(keys.size() + 1, 0.0);
         std::memcpy(dict_host.data(), keys.data(), keys.size() * sizeof(double));
         if (status == 0) status = dev_alloc(&S.dict, dict_host.size());
-        if (status == 0) status = dev_alloc(&S.pk, S.padded);
+        if (status == 0) status = one_word ? dev_alloc(&S.pk, S.padded) : dev_alloc(&S.vidx, S.padded);
         if (status == 0) {
             e = cudaMemcpyAsync(S.dict, dict_host.data(), dict_host.size() * sizeof(double), cudaMemcpyHostToDevice, st);
             if (e == cudaSuccess) {
-                k_dict_pack<<<blocks_for((long long)S.padded, 256), 256, 0, st>>>((long long)S.padded, S.col, S.val, table, count, cbits, S.pk);
+                if (one_word)
+                    k_dict_pack<<<blocks_for((long long)S.padded, 256), 256, 0, st>>>((long long)S.padded, S.col, S.val, table, count, cbits, S.pk);
+                else
+                    k_dict_index16<<<blocks_for((long long)S.padded, 256), 256, 0, st>>>((long long)S.padded, S.col, S.val, table, count, S.vidx);
                 count_launch();
                 e = cudaGetLastError();
             }
@@ -537,11 +560,11 @@ int build_value_dictionary(SellOp& S, size_t* bytes)
             if (e != cudaSuccess) fail(e, "value dictionary: pack");
         }
         if (status == 0) {
-            S.ndict = count; S.cbits = cbits;
-            if (bytes) *bytes += S.padded * 4 + keys.size() * 8;
+            S.ndict = count; S.cbits = one_word ? cbits : 0;
+            if (bytes) *bytes += S.padded * (one_word ? 4 : 2) + keys.size() * 8;
         }
         // row-ordered twin: square operator over all its rows (perm is a permutation of 0..rows-1)
-        if (status == 0 && S.full_rows && S.rows == S.cols && opt("sell.reorder", 1.0) != 0.0) {
+        if (status == 0 && one_word && S.full_rows && S.rows == S.cols && opt("sell.reorder", 1.0) != 0.0) {
             int32_t* iperm = nullptr;
             const long long npos = (long long)S.nslices * 32;
             status = dev_alloc(&iperm, S.cols);
@@ -560,7 +583,7 @@ int build_value_dictionary(SellOp& S, size_t* bytes)
             else { dev_free(S.pkp); S.pkp = nullptr; }
         }
         if (status != 0) {
-            dev_free(S.pk); dev_free(S.dict); S.pk = nullptr; S.dict = nullptr;
+            dev_free(S.pk); dev_free(S.dict); dev_free(S.vidx); S.pk = nullptr; S.dict = nullptr; S.vidx = nullptr; S.ndict = 0;
         }
     }
     dev_free(table);
@@ -884,7 +907,7 @@ int drops_b200_matrix_value_dictionary(drops_b200_matrix_t M, int transposed, in
     DB_ARG(M != nullptr, "null matrix");
     const SellOp& S = transposed ? M->sell_t : M->sell;
     if (n_distinct) *n_distinct = S.ndict;
-    if (packed) *packed = S.pk != nullptr;
+    if (packed) *packed = S.pk != nullptr ? 1 : (S.vidx != nullptr ? 2 : 0);
     if (column_bits) *column_bits = S.cbits;
     return 0;
 }

@@ -286,9 +286,9 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a)
     DB_ARG(a.dotv == nullptr || a.dot_out != nullptr || a.dd_out != nullptr, "fused dot needs an output scalar");
     if (A.rows == 0) return 0;
     // dictionary-packed stream (4 B per entry, spmv_pk.cu) when the operator has one
-    if (A.pk != nullptr && a.xghost == nullptr && (a.row_ordered || opt("spmv.pk", 1.0) != 0.0)) {
+    if ((A.pk != nullptr || A.vidx != nullptr) && a.xghost == nullptr && (a.row_ordered || opt("spmv.pk", 1.0) != 0.0)) {
         // stream staged by TMA ("spmv.pktma") when the dictionary fits shared memory
-        if (opt("spmv.pktma", 0.0) != 0.0 && A.ndict <= 512 && a.xu == nullptr) return spmv_sell_pk_tma(A, a);
+        if (opt("spmv.pktma", 0.0) != 0.0 && A.pk != nullptr && A.ndict <= 512 && a.xu == nullptr) return spmv_sell_pk_tma(A, a);
         return spmv_sell_pk(A, a);
     }
     DB_ARG(!a.row_ordered, "row-ordered vectors need the operator's row-ordered stream");

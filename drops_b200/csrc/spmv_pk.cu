@@ -20,6 +20,8 @@ constexpr int kPkDictSmem = 512;
 
 struct PkView {
     const int64_t* slice_ptr;
+    const int32_t* col;         // six-byte form: int32 column (-1 = padding) ...
+    const uint16_t* vidx;       // ... + 16-bit dictionary index (slot ndict = 0.0 for padding)
     const uint32_t* pk;
     const double* dict;
     const int32_t* perm;
@@ -80,6 +82,43 @@ __device__ __forceinline__ double pk_row_sum(const PkView& A, int64_t base, int 
 }
 
 // DOT as in k_spmv_sell: 0 none, 1 finished in this kernel, 2 per-warp partials + finishing kernel.
+// Six-byte form (V6): matrices whose column bits + index bits exceed one word keep the int32 column
+// of the general stream and replace the fp64 value by a 16-bit dictionary index.
+template <bool EXACT, int U, bool SMEM>
+__device__ __forceinline__ double pk6_row_sum(const PkView& A, int64_t base, int width, int lane,
+                                              const double* __restrict__ x)
+{
+    extern __shared__ double sdict[];
+    const int32_t* cp = A.col + base + lane;
+    const uint16_t* ip = A.vidx + base + lane;
+    double sum = 0.0;
+    int j = 0;
+    for (; j + U <= width; j += U) {
+        int c[U];
+        unsigned vi[U];
+        double xv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { c[u] = __ldcs(cp + (size_t)(j + u) * 32); vi[u] = __ldcs(ip + (size_t)(j + u) * 32); }
+#pragma unroll
+        for (int u = 0; u < U; ++u) xv[u] = c[u] >= 0 ? __ldg(x + c[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double v = SMEM ? sdict[vi[u]] : __ldg(A.dict + vi[u]);
+            const double t = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv[u])) : fma(v, xv[u], sum);
+            sum = c[u] >= 0 ? t : sum;
+        }
+    }
+    for (; j < width; ++j) {
+        const int c = __ldcs(cp + (size_t)j * 32);
+        const unsigned vi = __ldcs(ip + (size_t)j * 32);
+        const double xv = c >= 0 ? __ldg(x + c) : 0.0;
+        const double v = SMEM ? sdict[vi] : __ldg(A.dict + vi);
+        const double t = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv)) : fma(v, xv, sum);
+        sum = c >= 0 ? t : sum;
+    }
+    return sum;
+}
+
 // Software-pipelined form: the words of batch k+1 are requested before the gathers of batch k are
 // consumed, so a warp always has U matrix loads AND U gathers in flight (the plain form alternates).
 template <bool EXACT, int U, bool SMEM>
@@ -137,7 +176,7 @@ __device__ __forceinline__ double pk_row_sum_pipe(const PkView& A, int64_t base,
 //   2 = in the slice loop, but the partner is fetched AFTER the row sum (an L1 hit: the diagonal
 //       entry just gathered it) and the accumulator is parked in shared memory between slices, so
 //       the row sum runs with the registers of the plain product.
-template <int EPI, bool EXACT, int DOT, int U, int MAXT, int MINB, bool SMEM, int DF>
+template <int EPI, bool EXACT, int DOT, int U, int MAXT, int MINB, bool SMEM, int DF, bool V6 = false>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_spmv_sell_pk(PkView A, const double* __restrict__ x, double* __restrict__ y, EpiArgs e)
 {
@@ -180,7 +219,8 @@ k_spmv_sell_pk(PkView A, const double* __restrict__ x, double* __restrict__ y, E
         }
         // U < 0: software-pipelined form; U >= 100: U - 100 words in flight, stream loaded with L1::no_allocate
         constexpr int UU = U < 0 ? -U : (U >= 100 ? U - 100 : U);
-        const double sum = U > 0 ? pk_row_sum<EXACT, UU, SMEM, (U >= 100 ? 1 : 0)>(A, base, width, lane, x)
+        const double sum = V6 ? pk6_row_sum<EXACT, UU, SMEM>(A, base, width, lane, x)
+                         : U > 0 ? pk_row_sum<EXACT, UU, SMEM, (U >= 100 ? 1 : 0)>(A, base, width, lane, x)
                                  : pk_row_sum_pipe<EXACT, UU, SMEM>(A, base, width, lane, x);
         if (row >= 0) {
             const double out = apply_epilogue<EPI>(sum, av, e, beta);
@@ -208,23 +248,23 @@ k_spmv_sell_pk(PkView A, const double* __restrict__ x, double* __restrict__ y, E
     }
 }
 
-template <int EPI, bool EXACT, int U, int MAXT, int MINB, bool SMEM, int DF>
+template <int EPI, bool EXACT, int U, int MAXT, int MINB, bool SMEM, int DF, bool V6 = false>
 static void launch_pk_d(const PkView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads, cudaStream_t st)
 {
     if (threads > MAXT) threads = MAXT;
     const size_t sh = SMEM ? ((size_t)v.ndict + 1) * sizeof(double) : 0;
     if (a.dotv == nullptr) {
-        k_spmv_sell_pk<EPI, EXACT, 0, U, MAXT, MINB, SMEM, 0><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
+        k_spmv_sell_pk<EPI, EXACT, 0, U, MAXT, MINB, SMEM, 0, V6><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
         return;
     }
     const long long nwarps = (long long)grid * (threads >> 5);
     const double mode = opt("spmv.dotmode", 0.0);
     const bool two_kernels = mode == 2.0 || (mode == 0.0 && grid > (int)kReduceFlat);
     if (two_kernels && nwarps <= kPartialStride) {
-        k_spmv_sell_pk<EPI, EXACT, 2, U, MAXT, MINB, SMEM, DF><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
+        k_spmv_sell_pk<EPI, EXACT, 2, U, MAXT, MINB, SMEM, DF, V6><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
         sum_warp_partials(nwarps, e, st);
     } else {
-        k_spmv_sell_pk<EPI, EXACT, 1, U, MAXT, MINB, SMEM, DF><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
+        k_spmv_sell_pk<EPI, EXACT, 1, U, MAXT, MINB, SMEM, DF, V6><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
     }
 }
 
@@ -250,6 +290,11 @@ constexpr int kPkDefaultVariant = 9;   // measured on C2 (profiles/r01_probe_blo
 template <int EPI, bool EXACT>
 static bool launch_pk(const PkView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads, cudaStream_t st)
 {
+    if (v.vidx != nullptr) {       // six-byte form: one geometry, dictionary in shared memory or through L1
+        if (v.ndict <= kPkDictSmem && opt("spmv.pkdict", 0.0) == 0.0) launch_pk_d<EPI, EXACT, 8, 512, 3, true, 2, true>(v, a, e, grid, threads, st);
+        else launch_pk_d<EPI, EXACT, 8, 512, 3, false, 2, true>(v, a, e, grid, threads, st);
+        return true;
+    }
     const bool smem_ok = v.ndict <= kPkDictSmem && opt("spmv.pkdict", 0.0) == 0.0;
     const int variant = (int)(a.dotv != nullptr ? opt("spmv.pkdotvariant", (double)kPkDefaultVariant)
                                                 : opt("spmv.pkvariant", (double)kPkDefaultVariant));
@@ -291,7 +336,7 @@ static void launch_pk_epi(const PkView& v, const SpmvArgs& a, const EpiArgs& e, 
 int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
 {
     Ctx& c = ctx();
-    DB_ARG(A.pk != nullptr && A.dict != nullptr, "operator holds no packed stream");
+    DB_ARG((A.pk != nullptr || A.vidx != nullptr) && A.dict != nullptr, "operator holds no packed stream");
     DB_ARG(!a.row_ordered || A.pkp != nullptr, "operator holds no row-ordered stream");
     DB_ARG(a.x != nullptr && a.y != nullptr, "null vector");
     DB_ARG(a.x != a.y, "x and y must not alias");
@@ -326,7 +371,7 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
     if (grid > kMaxReduceGrid) grid = kMaxReduceGrid;
     if (grid < 1) grid = 1;
     cudaStream_t st = a.stream ? a.stream : c.stream;
-    PkView v{A.slice_ptr, a.row_ordered ? A.pkp : A.pk, A.dict, a.row_ordered ? nullptr : A.perm, (long long)A.nslices,
+    PkView v{A.slice_ptr, A.col, A.pk != nullptr ? nullptr : A.vidx, a.row_ordered ? A.pkp : A.pk, A.dict, a.row_ordered ? nullptr : A.perm, (long long)A.nslices,
              A.ndict, A.cbits};
     EpiArgs e = make_epi(a);
     e.prefetch = (int)opt("spmv.pk_prefetch", 0.0);        // slices ahead (in units of the CTA's warp count)

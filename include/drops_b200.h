@@ -123,7 +123,9 @@ DROPS_B200_API int drops_b200_matrix_format(drops_b200_matrix_t A, size_t* nslic
 /* Value dictionary of the sliced-ELL operator ("sell.valdict", default on): a matrix with at most
  * 65535 distinct fp64 bit patterns whose column and dictionary-index bits fit 32 is ALSO stored as one
  * 32-bit word per entry (lossless; products stay bit-identical).  n_distinct = 0 and packed = 0 when
- * the matrix does not qualify; column_bits = low bits of a word that hold the column.  `transposed`
+ * the matrix does not qualify; column_bits = low bits of a word that hold the column.  packed = 2: the
+ * dictionary is used as a 16-bit index beside the int32 column (6 bytes per entry) because column bits +
+ * index bits exceed one word ("sell.pack_bits", 32).  `transposed`
  * != 0 asks about the A^T operator (0/0 until the first transp_mul built it). */
 DROPS_B200_API int drops_b200_matrix_value_dictionary(drops_b200_matrix_t A, int transposed, int* n_distinct,
                                                       int* packed, int* column_bits);

@@ -167,14 +167,16 @@ def test_value_dictionary_qualifies_only_when_lossless_packing_fits(gpu):
     # 70 000 distinct values: no dictionary
     m = 70000
     W = gpu.Matrix(m, m, np.arange(m + 1), np.arange(m), np.arange(1, m + 1, dtype=np.float64))
-    assert W.value_dictionary() == {"n_distinct": 0, "packed": False, "column_bits": 0}
+    assert W.value_dictionary() == {"n_distinct": 0, "packed": False, "six_byte": False, "column_bits": 0}
     xw = hash_vector(m)
     assert np.array_equal(W.spmv(xw), np.arange(1, m + 1, dtype=np.float64) * xw)
     # 2^20 columns (20 bits) and 5000 values (13 bits) do not fit one word together
     cols = 1 << 20
     rows = 5000
     V = gpu.Matrix(rows, cols, np.arange(rows + 1), (np.arange(rows) * 209) % cols, np.arange(1, rows + 1) / 7.0)
-    assert not V.value_dictionary()["packed"]
+    assert not V.value_dictionary()["packed"] and V.value_dictionary()["six_byte"] and V.value_dictionary()["n_distinct"] == rows
+    xv = hash_vector(cols)
+    assert np.array_equal(V.spmv(xv), (np.arange(1, rows + 1) / 7.0) * xv[(np.arange(rows) * 209) % cols])
     try:
         gpu.set_option("sell.valdict", 0)
         assert not gmat(gpu, g).value_dictionary()["packed"]
@@ -334,6 +336,52 @@ def test_block_order_is_transparent(gpu, tile, sigma):
         _restore_pk(gpu)
 
 
+@pytest.mark.parametrize("dictmode,dotmode,sigma,threads,spc", [(0, 0, 4096, 512, 128), (1, 1, 64, 128, 3), (0, 2, 0, 64, 1000000)])
+def test_value_dictionary_six_byte_form_is_bit_identical(gpu, dictmode, dotmode, sigma, threads, spc):
+    """"sell.pack_bits" = 0 forces the form large systems with many distinct values get: int32 column +
+    16-bit dictionary index.  Same bits as the 12-byte stream in products, fused dots and solves."""
+    g = load_golden("brick_fe2_N6_num1.npz")
+    r = load_golden("random_ragged.npz")
+    n, rb, ci, va = gpu.brick_csr_host(2, 14, 1)
+    xin = hash_vector(n)
+    try:
+        gpu.set_option("spmv.pk", 0)
+        B0 = gpu.Matrix(n, n, rb, ci, va)
+        y0, yt0 = B0.spmv(xin), B0.spmv_transpose(xin)
+        X, Y = gpu.Vector.from_host(xin), gpu.Vector(n)
+        d0 = B0.spmv_dot_dev(X, Y, X)
+        s0 = B0.pcg_jacobi(np.zeros(n), y0, 60, 1e-10, True)
+        gm0 = B0.gmres_jacobi(np.zeros(n), y0, 20, 200, 1e-10, True, 1.0, True)
+        gpu.set_option("spmv.pk", 1)
+        gpu.set_option("sell.pack_bits", 0)
+        gpu.set_option("spmv.pkdict", dictmode)
+        gpu.set_option("spmv.dotmode", dotmode)
+        gpu.set_option("sell.sigma", sigma)
+        gpu.set_option("spmv.pk_threads", threads)
+        gpu.set_option("spmv.pk_slices_per_cta", spc)
+        A = gmat(gpu, g)
+        d = A.value_dictionary()
+        assert d["six_byte"] and not d["packed"] and not A.layout()["row_ordered_stream"]
+        assert np.array_equal(A.spmv(g["x_in"]), g["y_Ax"]) and np.array_equal(A.spmv_transpose(g["x_in"]), g["y_ATx"])
+        out = A.pcg_jacobi(np.zeros(A.rows), g["b"], 400, 1e-10, True)
+        assert out[1] == int(g["sym_pcgjac"][1]) and rel(out[3], g["sym_pcgjac_x"]) <= 1e-12
+        R = gmat(gpu, r)
+        if R.value_dictionary()["six_byte"]:
+            assert np.array_equal(R.spmv(r["x_in"]), r["y_Ax"])
+            assert np.array_equal(R.spmv_transpose(r["xt_in"] if "xt_in" in r else r["x_in"]), r["y_ATx"])
+        B = gpu.Matrix(n, n, rb, ci, va)
+        assert B.value_dictionary()["six_byte"]
+        assert np.array_equal(B.spmv(xin), y0) and np.array_equal(B.spmv_transpose(xin), yt0)
+        assert B.spmv_dot_dev(X, Y, X) == d0 and np.array_equal(Y.download(), y0)
+        s1 = B.pcg_jacobi(np.zeros(n), y0, 60, 1e-10, True)
+        assert s1[1] == s0[1] and s1[2] == s0[2] and np.array_equal(s1[3], s0[3])      # caller order: same reductions
+        gm1 = B.gmres_jacobi(np.zeros(n), y0, 20, 200, 1e-10, True, 1.0, True)
+        assert gm1[1] == gm0[1] and np.array_equal(gm1[3], gm0[3])
+    finally:
+        gpu.set_option("sell.pack_bits", 32)
+        _restore_pk(gpu)
+
+
 def test_value_dictionary_padding_and_special_values(gpu):
     """Ragged rows (padding inside slices), +0.0 / -0.0 / denormal entries, a non-finite x_0 (padding
     points at column 0) and new values on the old pattern: always the bits of the 12-byte stream."""
@@ -360,6 +408,11 @@ def test_value_dictionary_padding_and_special_values(gpu):
                 y = A.spmv(x)
                 assert np.array_equal(y.view(np.uint64), y0.view(np.uint64))
             gpu.set_option("spmv.pktma", PKTMA_DEFAULT)
+            gpu.set_option("sell.pack_bits", 0)
+            A6 = gpu.Matrix(rows, cols, rb, ci, va)
+            gpu.set_option("sell.pack_bits", 32)
+            assert A6.value_dictionary()["six_byte"]
+            assert np.array_equal(A6.spmv(x).view(np.uint64), y0.view(np.uint64))
         x[0] = 0.25
         xt = rng.standard_normal(rows)
         gpu.set_option("spmv.pk", 0)
