@@ -285,6 +285,12 @@ class Vector:
         check(lib().drops_b200_vector_download(self.h, out))
         return out[:self.n]
 
+    def download_into(self, out):
+        """Copy into a caller-supplied contiguous float64 array (e.g. a pinned buffer): no intermediate array."""
+        assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"] and out.size == self.n
+        check(lib().drops_b200_vector_download(self.h, out))
+        return out
+
     def fill(self, v):
         check(lib().drops_b200_vector_fill(self.h, float(v)))
 
@@ -831,7 +837,8 @@ class DistMatrix:
     def format(self):
         pk, nd = C.c_int(), C.c_int()
         check(lib().drops_b200_dist_matrix_format(self.h, C.byref(pk), C.byref(nd)))
-        return {"interior_packed": bool(pk.value), "n_distinct": nd.value}
+        return {"interior_packed": bool(pk.value & 1), "six_byte": bool(pk.value & 2), "row_ordered": bool(pk.value & 4),
+                "block_ordered": bool(pk.value & 8), "n_distinct": nd.value}
 
     def diag(self):
         d = np.zeros(max(self.info()["n_owned"], 1))

@@ -396,4 +396,6 @@ int build_sell(const CsrDev& A, SellOp& S, size_t* bytes, const int32_t* rowmap,
 int compute_block_order(const CsrDev& A, int32_t** d_order);
 // (re)builds S.dict / S.pk from S.col / S.val; leaves them null when the matrix does not qualify
 int build_value_dictionary(SellOp& S, size_t* bytes);
+// row-ordered twin of S.pk under a caller-supplied numbering iperm[column] = position (< npos)
+int pack_reorder(SellOp& S, const int32_t* iperm, size_t npos);
 }  // namespace db200

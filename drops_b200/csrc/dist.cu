@@ -146,6 +146,42 @@ __global__ void k_pack(long long n, const int32_t* __restrict__ idx, const doubl
     if (i < n) out[i] = x[idx[i]];
 }
 
+// position numbering of a partition: iperm[owned row] = base + pos, ro_perm[base + pos] = owned row
+__global__ void k_ro_positions(long long npos, const int32_t* __restrict__ perm, int base, int32_t* __restrict__ iperm,
+                               int32_t* __restrict__ ro_perm)
+{
+    const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= npos) return;
+    const int32_t r = perm[pos];
+    ro_perm[base + pos] = r;
+    if (r >= 0) iperm[r] = (int32_t)(base + pos);
+}
+// boundary operator twin: owned columns -> positions, ghost columns -> npos + slot; rows -> positions
+__global__ void k_ro_boundary(long long padded, const int32_t* __restrict__ col, const int32_t* __restrict__ iperm,
+                              int n_owned, int npos, int32_t* __restrict__ col_ro)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= padded) return;
+    const int32_t c = col[i];
+    col_ro[i] = c < 0 ? -1 : (c < n_owned ? iperm[c] : npos + (c - n_owned));
+}
+__global__ void k_ro_perm_shift(long long npos, const int32_t* __restrict__ perm, int base, int32_t* __restrict__ out)
+{
+    const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos < npos) out[pos] = perm[pos] >= 0 ? (int32_t)(base + pos) : -1;
+}
+__global__ void k_gather_i32(long long n, const int32_t* __restrict__ idx, const int32_t* __restrict__ src, int32_t* __restrict__ dst)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+__global__ void k_gather_flags(long long n, const int32_t* __restrict__ order, const char* __restrict__ a, const char* __restrict__ b,
+                               char* __restrict__ ao, char* __restrict__ bo)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { ao[i] = a[order[i]]; bo[i] = b[order[i]]; }
+}
+
 enum ScalarPhase { PH_DOT = 0, PH_LAMBDA = 1, PH_SETUP = 2, PH_UPDATE = 3, PH_NORM = 4 };
 
 // Sums the ranks' partials in rank order (the same on every rank) and does the scalar bookkeeping
@@ -282,7 +318,8 @@ static void free_dist_matrix(drops_b200_dist_matrix_s* M)
     if (ctx().inited) { cudaStreamSynchronize(ctx().stream); if (M->comm && M->comm->comm_stream) cudaStreamSynchronize(M->comm->comm_stream); }
     if (M->comm && M->comm->kind == COMM_LOCAL && M->rank < (int)M->comm->parts.size() && M->comm->parts[(size_t)M->rank] == M)
         M->comm->parts[(size_t)M->rank] = nullptr;
-    free_sell(M->sell_int); free_sell(M->sell_bnd);
+    free_sell(M->sell_int); free_sell(M->sell_bnd); free_sell(M->sell_bnd_ro);
+    dev_free(M->ro_perm); dev_free(M->diag_ro); dev_free(M->d_send_idx_ro);
     dev_free(M->diag); dev_free(M->ghost); dev_free(M->sendbuf); dev_free(M->d_send_idx);
     for (double* w : M->work) dev_free(w);
     dev_free(M->d_scalars); dev_free(M->d_hist); dev_free(M->d_small);
@@ -292,7 +329,7 @@ static void free_dist_matrix(drops_b200_dist_matrix_s* M)
 static double* dwork(drops_b200_dist_matrix_s* M, int i)
 {
     if ((int)M->work.size() <= i) M->work.resize((size_t)i + 1, nullptr);
-    if (!M->work[(size_t)i] && dev_alloc(&M->work[(size_t)i], M->n_owned) < 0) return nullptr;
+    if (!M->work[(size_t)i] && dev_alloc(&M->work[(size_t)i], std::max(M->n_owned, M->npos)) < 0) return nullptr;
     return M->work[(size_t)i];
 }
 
@@ -363,7 +400,32 @@ int dist_matrix_build(drops_b200_comm_s* comm, drops_b200_exchange_s* E, size_t 
     DM_CHECK(dev_alloc(&d_cnt, 2));
     long long cnt[2] = {0, 0};
     if (n > 0) {
-        k_iota32<<<blocks_for((long long)n, 256), 256, 0, st>>>((long long)n, rows_all);
+        // rows in blocks of the partition's own graph (reorder.cu) when it is large enough to profit
+        int32_t* order = nullptr;
+        {
+            CsrDev L;
+            L.rows = n; L.cols = n + ng; L.nnz = nnz;
+            L.rowptr = const_cast<int64_t*>(d_rowptr); L.col = col; L.val = const_cast<double*>(d_val);
+            DM_CHECK(compute_block_order(L, &order));
+        }
+        if (order) {
+            char *fi = nullptr, *fb = nullptr;
+            int s2 = dev_alloc(&fi, n);
+            if (s2 == 0) s2 = dev_alloc(&fb, n);
+            if (s2 == 0) {
+                k_gather_flags<<<blocks_for((long long)n, 256), 256, 0, st>>>((long long)n, order, f_int, f_bnd, fi, fb);
+                cudaMemcpyAsync(rows_all, order, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
+                cudaMemcpyAsync(f_int, fi, n, cudaMemcpyDeviceToDevice, st);
+                cudaMemcpyAsync(f_bnd, fb, n, cudaMemcpyDeviceToDevice, st);
+                cudaStreamSynchronize(st);
+                M->block_ordered = true;
+                count_launch();
+            }
+            dev_free(fi); dev_free(fb); dev_free(order);
+            DM_CHECK(s2);
+        } else {
+            k_iota32<<<blocks_for((long long)n, 256), 256, 0, st>>>((long long)n, rows_all);
+        }
         size_t tb = 0;
         DM_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, rows_all, f_int, rows_int, d_cnt, (long long)n, st));
         DM_CHECK(dev_alloc((char**)&tmp, tb));
@@ -378,7 +440,14 @@ int dist_matrix_build(drops_b200_comm_s* comm, drops_b200_exchange_s* E, size_t 
     A.rows = n; A.cols = n + ng; A.nnz = nnz;
     A.rowptr = const_cast<int64_t*>(d_rowptr); A.col = col; A.val = const_cast<double*>(d_val);
     M->device_bytes = n * 8;
-    DM_CHECK(build_sell(A, M->sell_int, &M->device_bytes, rows_int, M->n_int));
+    {
+        // head room in the column field of the packed words: the row-ordered twin stores positions, and the
+        // positions of a partition run up to (windows of the interior + windows of the boundary operator)
+        CsrDev Ai = A;
+        Ai.cols = n + ng + 2 * 4096 + 64;
+        DM_CHECK(build_sell(Ai, M->sell_int, &M->device_bytes, rows_int, M->n_int));
+        M->sell_int.cols = A.cols;
+    }
     DM_CHECK(build_sell(A, M->sell_bnd, &M->device_bytes, rows_bnd, M->n_bnd));
     // halo buffers
     M->recv_off = E->recv_off;
@@ -396,6 +465,54 @@ int dist_matrix_build(drops_b200_comm_s* comm, drops_b200_exchange_s* E, size_t 
     DM_CUDA(cudaMemsetAsync(M->ghost, 0, std::max<size_t>(ng, 1) * 8, st));
     DM_CUDA(cudaStreamSynchronize(st));
     M->device_bytes += (M->n_send + ng) * 8 + M->n_send * 4;
+    // ---- row-ordered twins: PCG iterates in the numbering of the operators' own slices ----
+    if (opt("dist.reorder", 1.0) != 0.0 && n > 0 && M->sell_int.pk != nullptr && M->n_int > 0) {
+        const size_t npi = M->sell_int.nslices * 32, npb = M->sell_bnd.nslices * 32, npos = npi + npb;
+        int32_t* iperm = nullptr;
+        DM_CHECK(dev_alloc(&iperm, n));
+        int s3 = dev_alloc(&M->ro_perm, npos);
+        if (s3 == 0) {
+            k_ro_positions<<<blocks_for((long long)npi, 256), 256, 0, st>>>((long long)npi, M->sell_int.perm, 0, iperm, M->ro_perm);
+            k_ro_positions<<<blocks_for((long long)npb, 256), 256, 0, st>>>((long long)npb, M->sell_bnd.perm, (int)npi, iperm, M->ro_perm);
+            count_launch(2);
+            s3 = pack_reorder(M->sell_int, iperm, npos);
+        }
+        if (s3 == 0 && M->sell_int.pkp != nullptr) {
+            SellOp& B = M->sell_bnd; SellOp& R = M->sell_bnd_ro;
+            R.rows = B.rows; R.cols = npos + ng; R.nslices = B.nslices; R.padded = B.padded; R.full_rows = false;
+            s3 = dev_alloc(&R.slice_ptr, B.nslices + 1);
+            if (s3 == 0) s3 = dev_alloc(&R.col, B.padded);
+            if (s3 == 0) s3 = dev_alloc(&R.val, B.padded);
+            if (s3 == 0) s3 = dev_alloc(&R.perm, npb);
+            if (s3 == 0) s3 = dev_alloc(&M->diag_ro, npos);
+            if (s3 == 0) s3 = dev_alloc(&M->d_send_idx_ro, M->n_send);
+            if (s3 == 0) {
+                cudaMemcpyAsync(R.slice_ptr, B.slice_ptr, (B.nslices + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st);
+                if (B.padded) {
+                    cudaMemcpyAsync(R.val, B.val, B.padded * sizeof(double), cudaMemcpyDeviceToDevice, st);
+                    k_ro_boundary<<<blocks_for((long long)B.padded, 256), 256, 0, st>>>((long long)B.padded, B.col, iperm, (int)n, (int)npos, R.col);
+                }
+                k_ro_perm_shift<<<blocks_for((long long)npb, 256), 256, 0, st>>>((long long)npb, B.perm, (int)npi, R.perm);
+                if (M->n_send) k_gather_i32<<<blocks_for((long long)M->n_send, 256), 256, 0, st>>>((long long)M->n_send, M->d_send_idx, iperm, M->d_send_idx_ro);
+                count_launch(3);
+                s3 = vec_gather_perm(npos, M->ro_perm, M->diag, M->diag_ro, 1.0);
+            }
+            if (s3 == 0) {
+                cudaError_t e3 = cudaStreamSynchronize(st);
+                if (e3 != cudaSuccess) s3 = cuda_fail(e3, "row-ordered twins", __FILE__, __LINE__);
+            }
+            if (s3 == 0) {
+                M->npos = npos; M->npos_int = npi;
+                M->device_bytes += M->sell_int.padded * 4 + B.padded * 12 + npos * 12 + M->n_send * 4;
+            }
+        }
+        dev_free(iperm);
+        if (s3 < 0) { cleanup(); free_dist_matrix(M); return s3; }
+        if (M->npos == 0) {      // twins incomplete (bits do not fit): drop them
+            dev_free(M->sell_int.pkp); M->sell_int.pkp = nullptr; M->sell_int.npos = 0;
+            free_sell(M->sell_bnd_ro); dev_free(M->ro_perm); M->ro_perm = nullptr;
+        }
+    }
     cleanup();
 #undef DM_CHECK
 #undef DM_CUDA
@@ -415,6 +532,7 @@ struct PartArgs {
     int epilogue = EPI_NONE; const double* aux = nullptr; double omega = 1.0;
     const double* dotv = nullptr;       // fused dot partner (local partial -> gathered slot)
     const int* done = nullptr;
+    bool ro = false;                    // x, y, aux, dotv are in the partition's row-ordered numbering (npos entries)
 };
 
 static int check_parts(int np, drops_b200_dist_matrix_s* const* P)
@@ -453,7 +571,8 @@ static int halo_exchange(int np, drops_b200_dist_matrix_s* const* P, const PartA
         ScopedTiming t("halo.pack");
         for (int p = 0; p < np; ++p)
             if (P[p]->n_send) {
-                k_pack<<<blocks_for((long long)P[p]->n_send, 256), 256, 0, st>>>((long long)P[p]->n_send, P[p]->d_send_idx,
+                k_pack<<<blocks_for((long long)P[p]->n_send, 256), 256, 0, st>>>((long long)P[p]->n_send,
+                                                                                a[p].ro ? P[p]->d_send_idx_ro : P[p]->d_send_idx,
                                                                                 a[p].x, P[p]->sendbuf, a[p].done);
                 count_launch();
             }
@@ -504,6 +623,7 @@ static int dist_spmv_run(int np, drops_b200_dist_matrix_s* const* P, const PartA
         SpmvArgs s;
         s.x = a[p].x; s.y = a[p].y; s.epilogue = a[p].epilogue; s.aux = a[p].aux; s.omega = a[p].omega; s.done = a[p].done;
         if (a[p].dotv) { s.dotv = a[p].dotv; s.dd_out = M->n_bnd ? (dd*)M->d_scalars + 32 : gather_slot(M, 1); }
+        s.row_ordered = a[p].ro;
         DB_CHECK(spmv_sell(M->sell_int, s));
     }
     if (comm->world > 1) DB_CUDA(cudaStreamWaitEvent(st, comm->ev_halo, 0));
@@ -513,9 +633,9 @@ static int dist_spmv_run(int np, drops_b200_dist_matrix_s* const* P, const PartA
         ScopedTiming t("spmv.bnd");
         SpmvArgs s;
         s.x = a[p].x; s.y = a[p].y; s.epilogue = a[p].epilogue; s.aux = a[p].aux; s.omega = a[p].omega; s.done = a[p].done;
-        s.xghost = M->ghost; s.n_owned = (long long)M->n_owned;
+        s.xghost = M->ghost; s.n_owned = a[p].ro ? (long long)M->npos : (long long)M->n_owned;
         if (a[p].dotv) { s.dotv = a[p].dotv; s.dd_in = M->n_int ? (dd*)M->d_scalars + 32 : nullptr; s.dd_out = gather_slot(M, 1); }
-        DB_CHECK(spmv_sell(M->sell_bnd, s));
+        DB_CHECK(spmv_sell(a[p].ro ? M->sell_bnd_ro : M->sell_bnd, s));
     }
     return 0;
 }
@@ -558,6 +678,29 @@ int dist_pcg(int np, drops_b200_dist_matrix_s* const* P, double* const* x, const
     const int want_hist = hist ? std::max(hist_cap, 0) : 0;
     std::vector<double*> r(np), pv(np), q(np);
     std::vector<SolverScalars*> S(np);
+    // row-ordered solve: every partition iterates on vectors in the numbering of its own slices; x and b are
+    // gathered once and x is scattered back at the end (same products in every row, dist.cuh)
+    bool ro = opt("dist.reorder", 1.0) != 0.0 && opt("spmv.pk", 1.0) != 0.0 && opt("spmv.kernel", 0.0) == 0.0;
+    for (int p = 0; p < np; ++p) ro = ro && P[p]->npos > 0;
+    {
+        double flag = ro ? 0.0 : 1.0;                         // all ranks or none
+        DB_CHECK(drops_b200_comm_allreduce_max(comm, &flag));
+        ro = flag == 0.0;
+    }
+    std::vector<double*> x_user(x, x + np);
+    std::vector<double*> xv(x, x + np);
+    std::vector<const double*> bv(b, b + np), dg(np);
+    std::vector<size_t> nv(np);
+    for (int p = 0; p < np; ++p) {
+        dg[p] = P[p]->diag; nv[p] = P[p]->n_owned;
+        if (ro) {
+            double* xp = dwork(P[p], 3); double* bp = dwork(P[p], 4);
+            if (!xp || !bp) return DROPS_B200_E_NOMEM;
+            DB_CHECK(vec_gather_perm(P[p]->npos, P[p]->ro_perm, x[p], xp, 0.0));
+            DB_CHECK(vec_gather_perm(P[p]->npos, P[p]->ro_perm, b[p], bp, 0.0));
+            xv[p] = xp; bv[p] = bp; dg[p] = P[p]->diag_ro; nv[p] = P[p]->npos;
+        }
+    }
     SolverScalars h;
     std::memset(&h, 0, sizeof h);
     h.tol = *tol; h.relative = relative; h.max_iter = *max_iter; h.pc = pc; h.omega = omega; h.hist_cap = want_hist;
@@ -569,6 +712,13 @@ int dist_pcg(int np, drops_b200_dist_matrix_s* const* P, double* const* x, const
         S[p] = (SolverScalars*)P[p]->d_scalars;
         r[p] = dwork(P[p], 0); pv[p] = dwork(P[p], 1); q[p] = dwork(P[p], 2);
         if (!r[p] || !pv[p] || !q[p]) return DROPS_B200_E_NOMEM;
+        if (ro) {
+            // the boundary operator skips its padding rows (the tail of the position range): r and q must hold
+            // zeros there, the vector kernels run over all npos positions
+            const size_t tail0 = P[p]->npos_int + P[p]->n_bnd, tail = P[p]->npos - tail0;
+            DB_CUDA(cudaMemsetAsync(r[p] + tail0, 0, tail * sizeof(double), st));
+            DB_CUDA(cudaMemsetAsync(q[p] + tail0, 0, tail * sizeof(double), st));
+        }
         DB_CUDA(cudaMemcpyAsync(S[p], &h, sizeof h, cudaMemcpyHostToDevice, st));
     }
     {
@@ -583,15 +733,15 @@ int dist_pcg(int np, drops_b200_dist_matrix_s* const* P, double* const* x, const
     std::vector<PartArgs> a(np);
     std::vector<char> defer_x(np);
     for (int p = 0; p < np; ++p)
-        defer_x[p] = opt("pcg.defer_x", 1.0) != 0.0 && opt("vec.wide", 1.0) != 0.0 && P[p]->n_owned > 0 &&
-                     ((reinterpret_cast<uintptr_t>(x[p]) | reinterpret_cast<uintptr_t>(pv[p]) | reinterpret_cast<uintptr_t>(r[p]) |
-                       reinterpret_cast<uintptr_t>(P[p]->diag)) & 15u) == 0;
+        defer_x[p] = opt("pcg.defer_x", 1.0) != 0.0 && opt("vec.wide", 1.0) != 0.0 && nv[p] > 0 &&
+                     ((reinterpret_cast<uintptr_t>(xv[p]) | reinterpret_cast<uintptr_t>(pv[p]) | reinterpret_cast<uintptr_t>(r[p]) |
+                       reinterpret_cast<uintptr_t>(dg[p])) & 15u) == 0;
 
     // r = b - A x; setup partials; scalars
-    for (int p = 0; p < np; ++p) { a[p] = PartArgs(); a[p].x = x[p]; a[p].y = r[p]; a[p].epilogue = EPI_RESID; a[p].aux = b[p]; }
+    for (int p = 0; p < np; ++p) { a[p] = PartArgs(); a[p].x = xv[p]; a[p].y = r[p]; a[p].epilogue = EPI_RESID; a[p].aux = bv[p]; a[p].ro = ro; }
     DB_CHECK(dist_spmv_run(np, P, a.data()));
     for (int p = 0; p < np; ++p)
-        DB_CHECK(pcg_setup(P[p]->n_owned, r[p], b[p], P[p]->diag, pv[p], S[p], nullptr, gather_slot(P[p], 3)));
+        DB_CHECK(pcg_setup(nv[p], r[p], bv[p], dg[p], pv[p], S[p], nullptr, gather_slot(P[p], 3)));
     DB_CHECK(allgather_partials(comm, 3));
     for (int p = 0; p < np; ++p) DB_CHECK(scalars_kernel(PH_SETUP, P[p], p == 0 ? dh : nullptr, nullptr));
 
@@ -612,21 +762,21 @@ int dist_pcg(int np, drops_b200_dist_matrix_s* const* P, double* const* x, const
     };
     auto iteration = [&]() -> int {
         for (int p = 0; p < np; ++p) {
-            a[p] = PartArgs(); a[p].x = pv[p]; a[p].y = q[p]; a[p].dotv = pv[p]; a[p].done = &S[p]->done;
+            a[p] = PartArgs(); a[p].x = pv[p]; a[p].y = q[p]; a[p].dotv = pv[p]; a[p].done = &S[p]->done; a[p].ro = ro;
         }
         DB_CHECK(dist_spmv_run(np, P, a.data()));                                     // q = A p, partial p.q
         DB_CHECK(allgather_partials(comm, 1));
         for (int p = 0; p < np; ++p) DB_CHECK(scalars_kernel(PH_LAMBDA, P[p], nullptr, nullptr));
         // x += alpha p rides in the direction kernel (10 instead of 11 vector passes, vecops.cuh)
         for (int p = 0; p < np; ++p) {
-            if (defer_x[p]) DB_CHECK(pcg_update_r(P[p]->n_owned, r[p], q[p], P[p]->diag, S[p], nullptr, gather_slot(P[p], 2)));
-            else DB_CHECK(pcg_update(P[p]->n_owned, x[p], r[p], pv[p], q[p], P[p]->diag, S[p], nullptr, gather_slot(P[p], 2)));
+            if (defer_x[p]) DB_CHECK(pcg_update_r(nv[p], r[p], q[p], dg[p], S[p], nullptr, gather_slot(P[p], 2)));
+            else DB_CHECK(pcg_update(nv[p], xv[p], r[p], pv[p], q[p], dg[p], S[p], nullptr, gather_slot(P[p], 2)));
         }
         DB_CHECK(allgather_partials(comm, 2));
         for (int p = 0; p < np; ++p) DB_CHECK(scalars_kernel(PH_UPDATE, P[p], p == 0 ? dh : nullptr, nullptr));
         for (int p = 0; p < np; ++p) {
-            if (defer_x[p]) DB_CHECK(pcg_direction_x(P[p]->n_owned, x[p], pv[p], r[p], P[p]->diag, S[p]));
-            else DB_CHECK(pcg_direction(P[p]->n_owned, pv[p], r[p], P[p]->diag, S[p]));
+            if (defer_x[p]) DB_CHECK(pcg_direction_x(nv[p], xv[p], pv[p], r[p], dg[p], S[p]));
+            else DB_CHECK(pcg_direction(nv[p], pv[p], r[p], dg[p], S[p]));
         }
         return 0;
     };
@@ -653,6 +803,7 @@ int dist_pcg(int np, drops_b200_dist_matrix_s* const* P, double* const* x, const
     cudaEventDestroy(ev[0]);
     cudaEventDestroy(ev[1]);
     if (status != 0) { cudaStreamSynchronize(st); return status; }
+    if (ro) for (int p = 0; p < np; ++p) DB_CHECK(vec_scatter_perm(P[p]->npos, P[p]->ro_perm, xv[p], x_user[p]));
     DB_CUDA(cudaMemcpyAsync(&h, S[0], sizeof h, cudaMemcpyDeviceToHost, st));
     DB_CUDA(cudaStreamSynchronize(st));
     if (comm->comm_stream) DB_CUDA(cudaStreamSynchronize(comm->comm_stream));
@@ -1028,7 +1179,9 @@ int drops_b200_dist_matrix_info(drops_b200_dist_matrix_t A, size_t* n_owned, siz
 int drops_b200_dist_matrix_format(drops_b200_dist_matrix_t A, int* interior_packed, int* n_distinct)
 {
     DB_ARG(A != nullptr, "null matrix");
-    if (interior_packed) *interior_packed = A->sell_int.pk != nullptr;
+    if (interior_packed)
+        *interior_packed = (A->sell_int.pk != nullptr ? 1 : 0) | (A->sell_int.vidx != nullptr ? 2 : 0) | (A->npos > 0 ? 4 : 0) |
+                           (A->block_ordered ? 8 : 0);
     if (n_distinct) *n_distinct = A->sell_int.ndict;
     return 0;
 }

@@ -67,6 +67,14 @@ struct drops_b200_dist_matrix_s {
     int hist_alloc = 0;
     double* d_small = nullptr;               // GMRES: Hessenberg column, y, basis pointers, scalars
     size_t small_alloc = 0;
+    // Row-ordered numbering of the partition ("dist.reorder"): positions of the interior operator, then of
+    // the boundary operator; PCG iterates on vectors of npos entries (padding positions hold 0).
+    size_t npos = 0, npos_int = 0;           // npos == 0: no row-ordered twins
+    int32_t* ro_perm = nullptr;              // position -> owned row (-1 = padding)
+    db200::SellOp sell_bnd_ro;               // boundary rows with columns = positions / npos + ghost slot
+    double* diag_ro = nullptr;
+    int32_t* d_send_idx_ro = nullptr;
+    bool block_ordered = false;
 };
 
 namespace db200 {

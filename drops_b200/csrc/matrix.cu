@@ -590,6 +590,22 @@ int build_value_dictionary(SellOp& S, size_t* bytes)
     return status;
 }
 
+// Row-ordered twin of S.pk for a caller-supplied numbering: iperm[column] = position (dist.cu: the
+// positions of a partition run over its interior and its boundary operator).
+int pack_reorder(SellOp& S, const int32_t* iperm, size_t npos)
+{
+    dev_free(S.pkp); S.pkp = nullptr; S.npos = 0;
+    if (S.pk == nullptr || S.padded == 0 || npos > ((size_t)1 << S.cbits)) return 0;
+    cudaStream_t st = ctx().stream;
+    DB_CHECK(dev_alloc(&S.pkp, S.padded));
+    k_pack_reorder<<<blocks_for((long long)S.padded, 256), 256, 0, st>>>((long long)S.padded, S.pk, iperm, S.cbits,
+                                                                       (uint32_t)S.ndict << S.cbits, S.pkp);
+    count_launch();
+    DB_CUDA(cudaGetLastError());
+    S.npos = npos;
+    return 0;
+}
+
 int refill_sell_values(const CsrDev& A, SellOp& S)
 {
     if (S.padded == 0) return 0;

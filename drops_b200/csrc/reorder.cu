@@ -130,11 +130,12 @@ static int argmax_i32(const int32_t* d, int n, int* out, void** tmp, size_t* tmp
 }
 
 // *d_order (rows entries, caller frees) lists the rows in block order; nullptr when the option is off,
-// the operator is not square or too small to profit ("sell.block_min_rows").
+// the operator has more rows than columns or is too small to profit ("sell.block_min_rows").
 int compute_block_order(const CsrDev& A, int32_t** d_order)
 {
     *d_order = nullptr;
-    if (opt("sell.block_order", 1.0) == 0.0 || A.rows != A.cols || A.nnz == 0) return 0;
+    // columns >= rows (the ghost columns of a partition) are no graph vertices: k_bfs_expand skips them
+    if (opt("sell.block_order", 1.0) == 0.0 || A.rows > A.cols || A.rows == 0 || A.nnz == 0) return 0;
     if ((double)A.rows < opt("sell.block_min_rows", 2.0e6)) return 0;
     int tile = (int)opt("sell.block_tile", 8.0);
     if (tile < 1) tile = 1;

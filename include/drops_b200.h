@@ -386,8 +386,10 @@ DROPS_B200_API int drops_b200_dist_matrix_destroy(drops_b200_dist_matrix_t A);
 DROPS_B200_API int drops_b200_dist_matrix_info(drops_b200_dist_matrix_t A, size_t* n_owned, size_t* n_ghost, size_t* nnz,
                                                size_t* interior_rows, size_t* boundary_rows, size_t* n_send,
                                                size_t* device_bytes);
-/* Whether the interior-row operator of the partition has the dictionary-packed 4-byte stream, and the
- * number of distinct values of its dictionary (drops_b200_matrix_value_dictionary for a partition). */
+/* Storage facts of a partition: interior_packed is a bit set -- 1: the interior-row operator has the
+ * dictionary-packed 4-byte stream, 2: the six-byte form, 4: the partition has its row-ordered twins (PCG
+ * iterates in the numbering of the operators' own slices, "dist.reorder"), 8: rows were cut in blocks of the
+ * partition's graph; n_distinct = size of the interior operator's dictionary. */
 DROPS_B200_API int drops_b200_dist_matrix_format(drops_b200_dist_matrix_t A, int* interior_packed, int* n_distinct);
 DROPS_B200_API int drops_b200_dist_matrix_diag(drops_b200_dist_matrix_t A, double* diag);
 

@@ -64,6 +64,10 @@ def test_partitioned_matches_reference_golden(gpu, world):
     d = gpu.dist_dot(mats, xs, ys)
     xv, yv = gpu.Vector.from_host(g["x_in"]), gpu.Vector.from_host(g["y_Ax"])
     assert abs(d - gpu.dot(xv, yv)) <= 4e-16 * float(np.abs(g["x_in"] * g["y_Ax"]).sum())
+    # the brick qualifies for the packed stream, so every partition with interior rows has its row-ordered twins
+    for m, i in zip(mats, infos):
+        f = m.format()
+        assert f["interior_packed"] == (i["interior_rows"] > 0) and f["row_ordered"] == (i["interior_rows"] > 0)
     # PCG + Jacobi to convergence: same iteration count as the reference run, same solution
     bs = scatter(gpu, loc, g["b"])
     x0 = [gpu.Vector(l[0].size) for l in loc]
@@ -79,6 +83,14 @@ def test_partitioned_matches_reference_golden(gpu, world):
     assert not conv and it == 7
     assert abs(res - g["sym_pcgjac_fixed7"][2]) <= 1e-9 * g["sym_pcgjac_fixed7"][2] + 1e-15
     assert rel(gather(loc, x0, n), g["sym_pcgjac_fixed7_x"]) <= 1e-12
+    # the same solve in the owned numbering ("dist.reorder" = 0 at solve time): same count, same solution
+    try:
+        gpu.set_option("dist.reorder", 0)
+        x1 = [gpu.Vector(l[0].size) for l in loc]
+        conv1, it1, res1 = gpu.dist_pcg(mats, x1, bs, 7, 0.0, True)
+        assert not conv1 and it1 == 7 and abs(res1 - res) <= 1e-9 * res and rel(gather(loc, x1, n), gather(loc, x0, n)) <= 1e-12
+    finally:
+        gpu.set_option("dist.reorder", 1)
     # unpreconditioned (DummyPcCL) and omega != 1
     for v in x0:
         v.fill(0.0)
@@ -88,6 +100,35 @@ def test_partitioned_matches_reference_golden(gpu, world):
         v.fill(0.0)
     conv, it, res = gpu.dist_pcg(mats, x0, bs, 400, 1e-10, False, omega=0.8)
     assert conv and abs(it - int(g["sym_pcgjac_w08"][1])) <= 1 and rel(gather(loc, x0, n), g["sym_pcgjac_w08_x"]) <= 1e-10
+
+
+@pytest.mark.parametrize("world,tile", [(2, 2), (3, 8)])
+def test_partition_rows_in_graph_blocks(gpu, world, tile):
+    """Partitions whose rows are cut in blocks of their own graph (reorder.cu on the owned x owned part) and
+    iterate on row-ordered vectors: products keep their bits, the solve its count and solution."""
+    g = load_golden("brick_fe2_N6_num1.npz")
+    n = int(g["rows"])
+    rb, ci, va = g["rowbeg"], g["colind"], g["val"]
+    part = gpu.partition_rows(rb, ci, world)
+    try:
+        gpu.set_option("sell.block_min_rows", 0)
+        gpu.set_option("sell.block_tile", tile)
+        comm, loc, mats = build_parts(gpu, rb, ci, va, part, world)
+        assert all(m.format()["block_ordered"] and m.format()["row_ordered"] for m in mats)
+        xs = scatter(gpu, loc, g["x_in"])
+        ys = [gpu.Vector(l[0].size) for l in loc]
+        gpu.dist_spmv(mats, xs, ys)
+        assert np.array_equal(gather(loc, ys, n), g["y_Ax"])
+        bs = scatter(gpu, loc, g["b"])
+        x0 = [gpu.Vector(l[0].size) for l in loc]
+        conv, it, res = gpu.dist_pcg(mats, x0, bs, 400, 1e-10, True)
+        assert conv and abs(it - int(g["sym_pcgjac"][1])) <= 1 and rel(gather(loc, x0, n), g["sym_pcgjac_x"]) <= 1e-10
+        x1 = [gpu.Vector(l[0].size) for l in loc]
+        conv, it, res = gpu.dist_gmres(mats, x1, bs, 20, 400, 1e-10, True)
+        assert conv and abs(it - int(g["sym_gmresjac_l1"][1])) <= 1 and rel(gather(loc, x1, n), g["sym_gmresjac_l1_x"]) <= 1e-10
+    finally:
+        gpu.set_option("sell.block_min_rows", 2.0e6)
+        gpu.set_option("sell.block_tile", 8)
 
 
 @pytest.mark.parametrize("name,tag,world", [("brick_fe2_N6_num1.npz", "sym", 1), ("brick_fe2_N6_num1.npz", "sym", 3),
