@@ -182,6 +182,49 @@ __global__ void k_gather_flags(long long n, const int32_t* __restrict__ order, c
     if (i < n) { ao[i] = a[order[i]]; bo[i] = b[order[i]]; }
 }
 
+// ---- peer-to-peer halo ------------------------------------------------------------------------
+// pack + push: entry i of my send list goes straight into the ghost buffer of the rank that needs it.
+// Every block fences its stores system-wide and takes a ticket; the block that draws the last ticket
+// raises my sequence number in the flag arrays of the receivers -- by then all entries are visible.
+__global__ void __launch_bounds__(256)
+k_pack_push(long long n_send, const int32_t* __restrict__ idx, const double* __restrict__ x,
+            const size_t* __restrict__ send_off, int world, double* const* __restrict__ peer_dst,
+            unsigned* const* __restrict__ peer_flag, unsigned seq, unsigned* ticket, const int* done)
+{
+    if (done != nullptr && *done != 0) return;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_send) {
+        int q = 0;
+        while (q + 1 < world && (long long)send_off[q + 1] <= i) ++q;
+        peer_dst[q][i - (long long)send_off[q]] = x[idx[i]];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(ticket, 1u) == gridDim.x - 1) {
+        *ticket = 0u;
+        __threadfence_system();
+        for (int q = 0; q < world; ++q)
+            if (send_off[q + 1] > send_off[q]) *(volatile unsigned*)peer_flag[q] = seq;
+        __threadfence_system();
+    }
+}
+
+// Consumer side: one lane per sender spins (bounded) until that sender's sequence number has arrived.
+__global__ void k_halo_wait(int world, const unsigned* flags, const unsigned char* __restrict__ expect, unsigned seq,
+                            const int* done, int* fault)
+{
+    if (done != nullptr && *done != 0) return;
+    const int q = threadIdx.x;
+    if (q < world && expect[q]) {
+        unsigned long long spins = 0;
+        while ((int)(*(volatile const unsigned*)(flags + q) - seq) < 0) {
+            __nanosleep(64);
+            if (++spins > (1ull << 26)) { atomicExch(fault, 1); break; }       // never hang the GPU
+        }
+    }
+    __threadfence_system();
+}
+
 enum ScalarPhase { PH_DOT = 0, PH_LAMBDA = 1, PH_SETUP = 2, PH_UPDATE = 3, PH_NORM = 4 };
 
 // Sums the ranks' partials in rank order (the same on every rank) and does the scalar bookkeeping
@@ -312,6 +355,8 @@ int find_ghosts_device(size_t n_owned, const int64_t* owned_host_sorted, size_t 
     return 0;
 }
 
+static int p2p_setup_nccl(drops_b200_dist_matrix_s* M);
+
 static void free_dist_matrix(drops_b200_dist_matrix_s* M)
 {
     if (!M) return;
@@ -320,6 +365,9 @@ static void free_dist_matrix(drops_b200_dist_matrix_s* M)
         M->comm->parts[(size_t)M->rank] = nullptr;
     free_sell(M->sell_int); free_sell(M->sell_bnd); free_sell(M->sell_bnd_ro);
     dev_free(M->ro_perm); dev_free(M->diag_ro); dev_free(M->d_send_idx_ro);
+    for (void* m : M->ipc_mapped) cudaIpcCloseMemHandle(m);
+    dev_free(M->p2p_ticket); dev_free(M->p2p_fault); dev_free(M->d_peer_dst); dev_free(M->d_peer_flag);
+    dev_free(M->d_send_off); dev_free(M->d_expect);
     dev_free(M->diag); dev_free(M->ghost); dev_free(M->sendbuf); dev_free(M->d_send_idx);
     for (double* w : M->work) dev_free(w);
     dev_free(M->d_scalars); dev_free(M->d_hist); dev_free(M->d_small);
@@ -460,7 +508,18 @@ int dist_matrix_build(drops_b200_comm_s* comm, drops_b200_exchange_s* E, size_t 
     M->n_send = flat.size();
     DM_CHECK(dev_alloc(&M->d_send_idx, M->n_send));
     DM_CHECK(dev_alloc(&M->sendbuf, M->n_send));
-    DM_CHECK(dev_alloc(&M->ghost, ng));
+    {
+        // ghost entries and, behind them, the arrival flags of the peer-to-peer halo: ONE allocation of at
+        // least 2 MB, so that it is a block of its own and one CUDA IPC handle maps both into the peers
+        const size_t flag_off = (ng * sizeof(double) + 255) / 256 * 256;
+        const size_t bytes = std::max<size_t>(flag_off + (size_t)std::max(E->world, 1) * sizeof(unsigned), (size_t)2 << 20);
+        char* raw = nullptr;
+        DM_CHECK(dev_alloc(&raw, bytes));
+        M->ghost = reinterpret_cast<double*>(raw);
+        M->halo_flags = reinterpret_cast<unsigned*>(raw + flag_off);
+        M->halo_flag_offset = flag_off;
+        DM_CUDA(cudaMemsetAsync(M->halo_flags, 0, (size_t)std::max(E->world, 1) * sizeof(unsigned), st));
+    }
     if (M->n_send) DM_CUDA(cudaMemcpyAsync(M->d_send_idx, flat.data(), M->n_send * 4, cudaMemcpyHostToDevice, st));
     DM_CUDA(cudaMemsetAsync(M->ghost, 0, std::max<size_t>(ng, 1) * 8, st));
     DM_CUDA(cudaStreamSynchronize(st));
@@ -519,6 +578,9 @@ int dist_matrix_build(drops_b200_comm_s* comm, drops_b200_exchange_s* E, size_t 
     if (comm->kind == COMM_LOCAL) {
         if ((int)comm->parts.size() < comm->world) comm->parts.resize((size_t)comm->world, nullptr);
         comm->parts[(size_t)M->rank] = M;
+    } else {
+        const int ps = p2p_setup_nccl(M);          // collective; failure to map peers is not an error
+        if (ps < 0) { free_dist_matrix(M); return ps; }
     }
     *out = M;
     return 0;
@@ -533,6 +595,7 @@ struct PartArgs {
     const double* dotv = nullptr;       // fused dot partner (local partial -> gathered slot)
     const int* done = nullptr;
     bool ro = false;                    // x, y, aux, dotv are in the partition's row-ordered numbering (npos entries)
+    bool p2p = false;                   // the exchange may use the peer path (solver loops only, see halo_exchange)
 };
 
 static int check_parts(int np, drops_b200_dist_matrix_s* const* P)
@@ -562,11 +625,150 @@ static int allgather_partials(drops_b200_comm_s* comm, int nq)
     return 0;
 }
 
+// Peer mappings of one partition.  NCCL transport: IPC handles of every rank's ghost buffer and flag
+// array travel through one all-gather (collective: every rank builds its partition); in-process
+// transport: the peers are the other partitions of this process.  Any failure leaves p2p = -1 on
+// ALL ranks and the exchange stays on ncclSend/ncclRecv.
+static int p2p_finish(drops_b200_dist_matrix_s* M, const std::vector<double*>& ghost_of, const std::vector<unsigned*>& flags_of,
+                      const std::vector<std::vector<size_t>>& recv_off_of)
+{
+    const int world = M->world, me = M->rank;
+    cudaStream_t st = ctx().stream;
+    std::vector<double*> dst((size_t)world, nullptr);
+    std::vector<unsigned*> flg((size_t)world, nullptr);
+    std::vector<unsigned char> expect((size_t)world, 0);
+    for (int q = 0; q < world; ++q) {
+        if (M->send_off[(size_t)q + 1] > M->send_off[(size_t)q]) {
+            dst[(size_t)q] = ghost_of[(size_t)q] + recv_off_of[(size_t)q][(size_t)me];
+            flg[(size_t)q] = flags_of[(size_t)q] + me;
+        }
+        expect[(size_t)q] = M->recv_off[(size_t)q + 1] > M->recv_off[(size_t)q] ? 1 : 0;
+    }
+    DB_CHECK(dev_alloc(&M->d_peer_dst, (size_t)world)); DB_CHECK(dev_alloc(&M->d_peer_flag, (size_t)world));
+    DB_CHECK(dev_alloc(&M->d_send_off, (size_t)world + 1)); DB_CHECK(dev_alloc(&M->d_expect, (size_t)world));
+    DB_CHECK(dev_alloc(&M->p2p_ticket, 1)); DB_CHECK(dev_alloc(&M->p2p_fault, 1));
+    DB_CUDA(cudaMemcpyAsync(M->d_peer_dst, dst.data(), (size_t)world * sizeof(double*), cudaMemcpyHostToDevice, st));
+    DB_CUDA(cudaMemcpyAsync(M->d_peer_flag, flg.data(), (size_t)world * sizeof(unsigned*), cudaMemcpyHostToDevice, st));
+    DB_CUDA(cudaMemcpyAsync(M->d_send_off, M->send_off.data(), ((size_t)world + 1) * sizeof(size_t), cudaMemcpyHostToDevice, st));
+    DB_CUDA(cudaMemcpyAsync(M->d_expect, expect.data(), (size_t)world, cudaMemcpyHostToDevice, st));
+    DB_CUDA(cudaMemsetAsync(M->p2p_ticket, 0, sizeof(unsigned), st));
+    DB_CUDA(cudaMemsetAsync(M->p2p_fault, 0, sizeof(int), st));
+    DB_CUDA(cudaStreamSynchronize(st));
+    M->p2p = 1;
+    return 0;
+}
+
+static int p2p_setup_nccl(drops_b200_dist_matrix_s* M)
+{
+    drops_b200_comm_s* comm = M->comm;
+    const int world = M->world, me = M->rank;
+    Ctx& c = ctx();
+    cudaStream_t st = c.stream;
+    M->p2p = -1;
+    if (opt("dist.p2p", 1.0) == 0.0 || world < 2 || !nccl().ok || comm->nccl == nullptr) return 0;
+    // blob per rank: handle of the ghost + flags allocation | offset of the flags in it | status | recv_off[world + 1]
+    const size_t blob = 2 * sizeof(cudaIpcMemHandle_t) + 8 + ((size_t)world + 1) * sizeof(size_t);
+    std::vector<unsigned char> mine(blob, 0), all(blob * (size_t)world, 0);
+    cudaIpcMemHandle_t hg, hf;
+    long long ok = 1;
+    std::memset(&hg, 0, sizeof hg); std::memset(&hf, 0, sizeof hf);
+    if (cudaIpcGetMemHandle(&hg, M->ghost) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+        std::memset(&hg, 0, sizeof hg);
+    }
+    const unsigned long long foff = M->halo_flag_offset;
+    std::memcpy(&hf, &foff, sizeof foff);                  // second slot carries the flag offset
+    std::memcpy(mine.data(), &hg, sizeof hg);
+    std::memcpy(mine.data() + sizeof hg, &hf, sizeof hf);
+    std::memcpy(mine.data() + 2 * sizeof hg, &ok, 8);
+    std::memcpy(mine.data() + 2 * sizeof hg + 8, M->recv_off.data(), ((size_t)world + 1) * sizeof(size_t));
+    unsigned char* d_all = nullptr;
+    DB_CHECK(dev_alloc(&d_all, blob * (size_t)world));
+    cudaError_t e = cudaMemcpyAsync(d_all + blob * (size_t)me, mine.data(), blob, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { dev_free(d_all); return cuda_fail(e, "p2p setup", __FILE__, __LINE__); }
+    ncclResult_t nr = nccl().AllGather(d_all + blob * (size_t)me, d_all, blob, ncclChar, (ncclComm_t)comm->nccl, st);
+    if (nr != ncclSuccess) { dev_free(d_all); return nccl_fail(nr, "p2p handle all-gather"); }
+    e = cudaMemcpyAsync(all.data(), d_all, blob * (size_t)world, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    dev_free(d_all);
+    if (e != cudaSuccess) return cuda_fail(e, "p2p setup", __FILE__, __LINE__);
+    std::vector<double*> ghost_of((size_t)world, nullptr);
+    std::vector<unsigned*> flags_of((size_t)world, nullptr);
+    std::vector<std::vector<size_t>> roff((size_t)world, std::vector<size_t>((size_t)world + 1, 0));
+    bool good = true;
+    for (int q = 0; q < world; ++q) {
+        const unsigned char* b = all.data() + blob * (size_t)q;
+        long long okq = 0;
+        std::memcpy(&okq, b + 2 * sizeof hg, 8);
+        std::memcpy(roff[(size_t)q].data(), b + 2 * sizeof hg + 8, ((size_t)world + 1) * sizeof(size_t));
+        if (!okq) good = false;
+    }
+    for (int q = 0; q < world && good; ++q) {
+        if (q == me) { ghost_of[(size_t)q] = M->ghost; flags_of[(size_t)q] = M->halo_flags; continue; }
+        if (M->send_off[(size_t)q + 1] == M->send_off[(size_t)q]) continue;      // nothing goes to q
+        const unsigned char* b = all.data() + blob * (size_t)q;
+        std::memcpy(&hg, b, sizeof hg); std::memcpy(&hf, b + sizeof hg, sizeof hf);
+        void* pg = nullptr;
+        if (cudaIpcOpenMemHandle(&pg, hg, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); good = false; break; }
+        M->ipc_mapped.push_back(pg);
+        unsigned long long foff_q = 0;
+        std::memcpy(&foff_q, &hf, sizeof foff_q);
+        ghost_of[(size_t)q] = (double*)pg; flags_of[(size_t)q] = (unsigned*)((char*)pg + foff_q);
+    }
+    double bad = good ? 0.0 : 1.0;                         // all ranks or none
+    DB_CHECK(drops_b200_comm_allreduce_max(comm, &bad));
+    if (bad != 0.0) {
+        for (void* m : M->ipc_mapped) cudaIpcCloseMemHandle(m);
+        M->ipc_mapped.clear();
+        return 0;
+    }
+    return p2p_finish(M, ghost_of, flags_of, roff);
+}
+
+static int p2p_setup_local(int np, drops_b200_dist_matrix_s* const* P)
+{
+    std::vector<double*> ghost_of((size_t)np);
+    std::vector<unsigned*> flags_of((size_t)np);
+    std::vector<std::vector<size_t>> roff((size_t)np);
+    for (int p = 0; p < np; ++p) { ghost_of[(size_t)p] = P[p]->ghost; flags_of[(size_t)p] = P[p]->halo_flags; roff[(size_t)p] = P[p]->recv_off; }
+    for (int p = 0; p < np; ++p) {
+        if (P[p]->p2p != 0) continue;
+        P[p]->p2p = -1;
+        if (opt("dist.p2p", 1.0) == 0.0 || np < 2) continue;
+        DB_CHECK(p2p_finish(P[p], ghost_of, flags_of, roff));
+    }
+    return 0;
+}
+
 static int halo_exchange(int np, drops_b200_dist_matrix_s* const* P, const PartArgs* a)
 {
     drops_b200_comm_s* comm = P[0]->comm;
     if (comm->world == 1) return 0;
     cudaStream_t st = ctx().stream, cs = comm->comm_stream;
+    if (comm->kind == COMM_LOCAL && P[0]->p2p == 0) DB_CHECK(p2p_setup_local(np, P));
+    // peer path: only inside solver loops (a[p].p2p) -- there two reductions over all ranks separate one
+    // exchange from the next, so a ghost buffer is never overwritten while its owner still reads it
+    bool peer = a[0].p2p && opt("dist.p2p", 1.0) != 0.0;
+    for (int p = 0; p < np; ++p) peer = peer && P[p]->p2p == 1;
+    if (peer) {
+        // on the communication stream, beside the interior rows (as the NCCL exchange below)
+        DB_CUDA(cudaEventRecord(comm->ev_pack, st));
+        DB_CUDA(cudaStreamWaitEvent(cs, comm->ev_pack, 0));
+        for (int p = 0; p < np; ++p) {
+            drops_b200_dist_matrix_s* M = P[p];
+            ++M->p2p_seq;
+            if (M->n_send) {
+                k_pack_push<<<blocks_for((long long)M->n_send, 256), 256, 0, cs>>>(
+                    (long long)M->n_send, a[p].ro ? M->d_send_idx_ro : M->d_send_idx, a[p].x, M->d_send_off, M->world,
+                    M->d_peer_dst, M->d_peer_flag, M->p2p_seq, M->p2p_ticket, a[p].done);
+                count_launch();
+            }
+        }
+        DB_CUDA(cudaGetLastError());
+        DB_CUDA(cudaEventRecord(comm->ev_halo, cs));
+        return 1;                                  // the caller waits with k_halo_wait before the boundary rows
+    }
     {
         ScopedTiming t("halo.pack");
         for (int p = 0; p < np; ++p)
@@ -611,7 +813,9 @@ static int dist_spmv_run(int np, drops_b200_dist_matrix_s* const* P, const PartA
 {
     drops_b200_comm_s* comm = P[0]->comm;
     cudaStream_t st = ctx().stream;
-    DB_CHECK(halo_exchange(np, P, a));
+    const int hx = halo_exchange(np, P, a);
+    if (hx < 0) return hx;
+    const bool peer = hx == 1;
     for (int p = 0; p < np; ++p) {
         drops_b200_dist_matrix_s* M = P[p];
         if (a[p].dotv && M->n_int == 0 && M->n_bnd == 0) {
@@ -626,7 +830,18 @@ static int dist_spmv_run(int np, drops_b200_dist_matrix_s* const* P, const PartA
         s.row_ordered = a[p].ro;
         DB_CHECK(spmv_sell(M->sell_int, s));
     }
-    if (comm->world > 1) DB_CUDA(cudaStreamWaitEvent(st, comm->ev_halo, 0));
+    if (comm->world > 1) DB_CUDA(cudaStreamWaitEvent(st, comm->ev_halo, 0));     // my sends / pushes have left
+    if (peer) {
+        ScopedTiming t("halo.wait");
+        for (int p = 0; p < np; ++p) {
+            drops_b200_dist_matrix_s* M = P[p];
+            if (M->n_ghost == 0) continue;
+            k_halo_wait<<<1, std::max(32, (M->world + 31) / 32 * 32), 0, st>>>(M->world, M->halo_flags, M->d_expect, M->p2p_seq,
+                                                                             a[p].done, M->p2p_fault);
+            count_launch();
+        }
+        DB_CUDA(cudaGetLastError());
+    }
     for (int p = 0; p < np; ++p) {
         drops_b200_dist_matrix_s* M = P[p];
         if (M->n_bnd == 0) continue;
@@ -762,7 +977,7 @@ int dist_pcg(int np, drops_b200_dist_matrix_s* const* P, double* const* x, const
     };
     auto iteration = [&]() -> int {
         for (int p = 0; p < np; ++p) {
-            a[p] = PartArgs(); a[p].x = pv[p]; a[p].y = q[p]; a[p].dotv = pv[p]; a[p].done = &S[p]->done; a[p].ro = ro;
+            a[p] = PartArgs(); a[p].x = pv[p]; a[p].y = q[p]; a[p].dotv = pv[p]; a[p].done = &S[p]->done; a[p].ro = ro; a[p].p2p = true;
         }
         DB_CHECK(dist_spmv_run(np, P, a.data()));                                     // q = A p, partial p.q
         DB_CHECK(allgather_partials(comm, 1));
@@ -959,6 +1174,7 @@ int dist_gmres(int np, drops_b200_dist_matrix_s* const* P, double* const* x, con
             for (int p = 0; p < np; ++p) {
                 Part& w = W[(size_t)p];
                 a[(size_t)p] = PartArgs();
+                a[(size_t)p].p2p = true;                                      // reductions over all ranks separate the exchanges
                 if (left) {                                                   // w = M^-1 (A v[i])  :377
                     a[(size_t)p].x = w.v[(size_t)i]; a[(size_t)p].y = w.w;
                     if (jac) { a[(size_t)p].epilogue = EPI_JACOBI; a[(size_t)p].aux = P[p]->diag; a[(size_t)p].omega = omega; }
@@ -1181,7 +1397,13 @@ int drops_b200_dist_matrix_format(drops_b200_dist_matrix_t A, int* interior_pack
     DB_ARG(A != nullptr, "null matrix");
     if (interior_packed)
         *interior_packed = (A->sell_int.pk != nullptr ? 1 : 0) | (A->sell_int.vidx != nullptr ? 2 : 0) | (A->npos > 0 ? 4 : 0) |
-                           (A->block_ordered ? 8 : 0);
+                           (A->block_ordered ? 8 : 0) | (A->p2p == 1 ? 16 : 0);
+    if (interior_packed && A->p2p == 1 && A->p2p_fault && ctx().inited) {
+        int f = 0;
+        cudaStreamSynchronize(ctx().stream);
+        cudaMemcpy(&f, A->p2p_fault, sizeof(int), cudaMemcpyDeviceToHost);
+        if (f) *interior_packed |= 32;
+    }
     if (n_distinct) *n_distinct = A->sell_int.ndict;
     return 0;
 }

@@ -75,6 +75,20 @@ struct drops_b200_dist_matrix_s {
     double* diag_ro = nullptr;
     int32_t* d_send_idx_ro = nullptr;
     bool block_ordered = false;
+    // Peer-to-peer halo ("dist.p2p"): the pack kernel stores the boundary entries of x straight into the
+    // neighbours' ghost buffers (NVLink peer stores through CUDA IPC mappings; plain pointers for the
+    // in-process transport) and raises a sequence flag there; no send buffer, no NCCL call per exchange.
+    int p2p = 0;                             // 0 not set up, 1 ready, -1 unavailable (NCCL send/recv is used)
+    unsigned p2p_seq = 0;                    // exchanges done through the peer path (same on every rank)
+    unsigned* halo_flags = nullptr;          // world entries in MY memory (behind the ghost entries): flags[q] = last sequence pushed by q
+    size_t halo_flag_offset = 0;             // byte offset of halo_flags inside the ghost allocation
+    unsigned* p2p_ticket = nullptr;
+    int* p2p_fault = nullptr;                // a wait timed out
+    double** d_peer_dst = nullptr;           // world entries: where my entries for q land (q's ghost + offset)
+    unsigned** d_peer_flag = nullptr;        // world entries: my slot in q's flag array
+    size_t* d_send_off = nullptr;            // world + 1
+    unsigned char* d_expect = nullptr;       // world entries: 1 = q sends to me
+    std::vector<void*> ipc_mapped;           // pointers opened with cudaIpcOpenMemHandle
 };
 
 namespace db200 {
