@@ -225,19 +225,55 @@ __global__ void k_halo_wait(int world, const unsigned* flags, const unsigned cha
     __threadfence_system();
 }
 
+// peer-to-peer all-gather of reduction partials: my nq partials go into slot `me` of the current parity half
+// of EVERY rank's buffer, then my sequence number into every rank's flag array
+__global__ void k_push_partials(int nq, int me, int world, const dd* __restrict__ local, dd* const* __restrict__ peer_buf,
+                                unsigned* const* __restrict__ peer_flag, unsigned seq, const int* done)
+{
+    if (done != nullptr && *done != 0) return;
+    const int t = threadIdx.x;
+    if (t < world * nq) {
+        const int q = t / nq, j = t - q * nq;
+        dd v = local[j];
+        dd* dst = peer_buf[q] + (size_t)(seq & 1u) * world * kMaxQ + (size_t)me * nq + j;
+        *(volatile double*)&dst->hi = v.hi;
+        *(volatile double*)&dst->lo = v.lo;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < world) { *(volatile unsigned*)(peer_flag[t] + me) = seq; }
+    __threadfence_system();
+}
+
 enum ScalarPhase { PH_DOT = 0, PH_LAMBDA = 1, PH_SETUP = 2, PH_UPDATE = 3, PH_NORM = 4 };
 
 // Sums the ranks' partials in rank order (the same on every rank) and does the scalar bookkeeping
 // that the last block of the fused kernels does on a single GPU.
-__global__ void k_dist_scalars(int phase, SolverScalars* S, double* hist, const dd* __restrict__ gathered, int world,
-                               double* out)
+__global__ void k_dist_scalars(int phase, SolverScalars* S, double* hist, const dd* gathered, int world,
+                               double* out, const unsigned* flags, unsigned seq, int* fault)
 {
-    if (threadIdx.x != 0) return;
     if ((phase == PH_LAMBDA || phase == PH_UPDATE) && S->done) return;
+    if (flags != nullptr) {                          // peer path: wait (bounded) for every rank's sequence number
+        const int q = threadIdx.x;
+        if (q < world) {
+            unsigned long long spins = 0;
+            while ((int)(*(volatile const unsigned*)(flags + q) - seq) < 0) {
+                __nanosleep(32);
+                if (++spins > (1ull << 26)) { atomicExch(fault, 1); break; }
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
     const int nq = phase == PH_SETUP ? 3 : (phase == PH_UPDATE ? 2 : 1);
     dd acc[3] = {dd_zero(), dd_zero(), dd_zero()};
     for (int r = 0; r < world; ++r)
-        for (int q = 0; q < nq; ++q) acc[q] = dd_add(acc[q], gathered[r * nq + q]);
+        for (int q = 0; q < nq; ++q) {
+            const volatile dd* g = gathered + r * nq + q;
+            dd t; t.hi = g->hi; t.lo = g->lo;
+            acc[q] = dd_add(acc[q], t);
+        }
     if (phase == PH_DOT) *out = dd_round(acc[0]);
     else if (phase == PH_NORM) *out = sqrt(dd_round(acc[0]));
     else if (phase == PH_LAMBDA) S->lambda = dd_round(acc[0]);
@@ -615,8 +651,24 @@ static int check_parts(int np, drops_b200_dist_matrix_s* const* P)
 // slot of partition p's reduction partials in the rank-major gather buffer
 static inline dd* gather_slot(drops_b200_dist_matrix_s* M, int nq) { return M->comm->gathered + (size_t)M->rank * nq; }
 
-static int allgather_partials(drops_b200_comm_s* comm, int nq)
+static int allgather_partials(drops_b200_comm_s* comm, int nq, const int* const* done_of = nullptr)
 {
+    comm->red_last_p2p = false;
+    if (comm->world > 1 && comm->p2p == 1 && opt("dist.p2p_reduce", 1.0) != 0.0 && comm->world * nq <= 1024) {
+        ScopedTiming t("allgather");
+        ++comm->red_seq;
+        const int threads = std::max(32, (comm->world * nq + 31) / 32 * 32);
+        const int first = comm->kind == COMM_LOCAL ? 0 : comm->rank, last = comm->kind == COMM_LOCAL ? comm->world : comm->rank + 1;
+        for (int me = first; me < last; ++me) {
+            const int* done = done_of ? done_of[comm->kind == COMM_LOCAL ? me : 0] : nullptr;
+            k_push_partials<<<1, threads, 0, ctx().stream>>>(nq, me, comm->world, comm->gathered + (size_t)me * nq, comm->d_peer_red,
+                                                             comm->d_peer_redflag, comm->red_seq, done);
+            count_launch();
+        }
+        DB_CUDA(cudaGetLastError());
+        comm->red_last_p2p = true;
+        return 0;
+    }
     if (comm->kind == COMM_NCCL && comm->world > 1) {
         ScopedTiming t("allgather");
         DB_NCCL(nccl().AllGather(comm->gathered + (size_t)comm->rank * nq, comm->gathered, (size_t)nq * 2, ncclDouble,
@@ -875,7 +927,13 @@ static_assert(sizeof(SolverScalars) <= 32 * sizeof(dd), "scratch offset inside t
 
 static int scalars_kernel(int phase, drops_b200_dist_matrix_s* M, double* hist, double* out)
 {
-    k_dist_scalars<<<1, 32, 0, ctx().stream>>>(phase, (SolverScalars*)M->d_scalars, hist, M->comm->gathered, M->world, out);
+    drops_b200_comm_s* C = M->comm;
+    if (C->red_last_p2p)
+        k_dist_scalars<<<1, std::max(32, (M->world + 31) / 32 * 32), 0, ctx().stream>>>(
+            phase, (SolverScalars*)M->d_scalars, hist, C->red_buf + (size_t)(C->red_seq & 1u) * M->world * kMaxQ, M->world, out,
+            C->red_flags, C->red_seq, C->red_fault);
+    else
+        k_dist_scalars<<<1, 32, 0, ctx().stream>>>(phase, (SolverScalars*)M->d_scalars, hist, C->gathered, M->world, out, nullptr, 0u, nullptr);
     count_launch();
     DB_CUDA(cudaGetLastError());
     return 0;
@@ -975,19 +1033,21 @@ int dist_pcg(int np, drops_b200_dist_matrix_s* const* P, double* const* x, const
         DB_CUDA(cudaEventRecord(ev[slot], st));
         return 0;
     };
+    std::vector<const int*> done_ptrs(np);       // skipped iterations skip their reductions on every rank alike
+    for (int p = 0; p < np; ++p) done_ptrs[p] = &S[p]->done;
     auto iteration = [&]() -> int {
         for (int p = 0; p < np; ++p) {
             a[p] = PartArgs(); a[p].x = pv[p]; a[p].y = q[p]; a[p].dotv = pv[p]; a[p].done = &S[p]->done; a[p].ro = ro; a[p].p2p = true;
         }
         DB_CHECK(dist_spmv_run(np, P, a.data()));                                     // q = A p, partial p.q
-        DB_CHECK(allgather_partials(comm, 1));
+        DB_CHECK(allgather_partials(comm, 1, done_ptrs.data()));
         for (int p = 0; p < np; ++p) DB_CHECK(scalars_kernel(PH_LAMBDA, P[p], nullptr, nullptr));
         // x += alpha p rides in the direction kernel (10 instead of 11 vector passes, vecops.cuh)
         for (int p = 0; p < np; ++p) {
             if (defer_x[p]) DB_CHECK(pcg_update_r(nv[p], r[p], q[p], dg[p], S[p], nullptr, gather_slot(P[p], 2)));
             else DB_CHECK(pcg_update(nv[p], xv[p], r[p], pv[p], q[p], dg[p], S[p], nullptr, gather_slot(P[p], 2)));
         }
-        DB_CHECK(allgather_partials(comm, 2));
+        DB_CHECK(allgather_partials(comm, 2, done_ptrs.data()));
         for (int p = 0; p < np; ++p) DB_CHECK(scalars_kernel(PH_UPDATE, P[p], p == 0 ? dh : nullptr, nullptr));
         for (int p = 0; p < np; ++p) {
             if (defer_x[p]) DB_CHECK(pcg_direction_x(nv[p], xv[p], pv[p], r[p], dg[p], S[p]));
@@ -1253,7 +1313,81 @@ static int comm_common(drops_b200_comm_s* C)
     DB_CUDA(cudaEventCreateWithFlags(&C->ev_halo, cudaEventDisableTiming));
     DB_CHECK(dev_alloc(&C->gathered, (size_t)C->world * kMaxQ));
     DB_CUDA(cudaMemset(C->gathered, 0, (size_t)C->world * kMaxQ * sizeof(dd)));
+    // buffer of the peer-to-peer reductions: 2 parity halves of world x kMaxQ partials, then world flags; one
+    // allocation of >= 2 MB so that a single CUDA IPC handle maps it into the peers
+    {
+        const size_t flag_off = ((size_t)2 * C->world * kMaxQ * sizeof(dd) + 255) / 256 * 256;
+        const size_t bytes = std::max<size_t>(flag_off + (size_t)C->world * sizeof(unsigned), (size_t)2 << 20);
+        char* raw = nullptr;
+        DB_CHECK(dev_alloc(&raw, bytes));
+        DB_CUDA(cudaMemset(raw, 0, bytes));
+        C->red_buf = reinterpret_cast<dd*>(raw);
+        C->red_flags = reinterpret_cast<unsigned*>(raw + flag_off);
+        DB_CHECK(dev_alloc(&C->red_fault, 1));
+        DB_CUDA(cudaMemset(C->red_fault, 0, sizeof(int)));
+    }
     return 0;
+}
+
+// peer tables of the reductions: bufs[q] / flags[q] = rank q's buffer and flag array in MY address space
+static int comm_p2p_finish(drops_b200_comm_s* C, const std::vector<dd*>& bufs, const std::vector<unsigned*>& flags)
+{
+    DB_CHECK(dev_alloc(&C->d_peer_red, (size_t)C->world));
+    DB_CHECK(dev_alloc(&C->d_peer_redflag, (size_t)C->world));
+    DB_CUDA(cudaMemcpy(C->d_peer_red, bufs.data(), (size_t)C->world * sizeof(dd*), cudaMemcpyHostToDevice));
+    DB_CUDA(cudaMemcpy(C->d_peer_redflag, flags.data(), (size_t)C->world * sizeof(unsigned*), cudaMemcpyHostToDevice));
+    C->p2p = 1;
+    return 0;
+}
+
+static int comm_p2p_setup_nccl(drops_b200_comm_s* C)
+{
+    C->p2p = -1;
+    if (opt("dist.p2p", 1.0) == 0.0 || C->world < 2 || !nccl().ok || C->nccl == nullptr) return 0;
+    Ctx& c = ctx();
+    cudaStream_t st = c.stream;
+    const int world = C->world, me = C->rank;
+    const size_t blob = sizeof(cudaIpcMemHandle_t) + 16;      // handle | flag offset | status
+    std::vector<unsigned char> mine(blob, 0), all(blob * (size_t)world, 0);
+    cudaIpcMemHandle_t h;
+    long long ok = 1;
+    if (cudaIpcGetMemHandle(&h, C->red_buf) != cudaSuccess) { cudaGetLastError(); ok = 0; std::memset(&h, 0, sizeof h); }
+    const unsigned long long foff = (unsigned long long)((char*)C->red_flags - (char*)C->red_buf);
+    std::memcpy(mine.data(), &h, sizeof h);
+    std::memcpy(mine.data() + sizeof h, &foff, 8);
+    std::memcpy(mine.data() + sizeof h + 8, &ok, 8);
+    unsigned char* d_all = nullptr;
+    DB_CHECK(dev_alloc(&d_all, blob * (size_t)world));
+    cudaError_t e = cudaMemcpyAsync(d_all + blob * (size_t)me, mine.data(), blob, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { dev_free(d_all); return cuda_fail(e, "p2p reduce setup", __FILE__, __LINE__); }
+    ncclResult_t nr = nccl().AllGather(d_all + blob * (size_t)me, d_all, blob, ncclChar, (ncclComm_t)C->nccl, st);
+    if (nr != ncclSuccess) { dev_free(d_all); return nccl_fail(nr, "p2p reduce handle all-gather"); }
+    e = cudaMemcpyAsync(all.data(), d_all, blob * (size_t)world, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    dev_free(d_all);
+    if (e != cudaSuccess) return cuda_fail(e, "p2p reduce setup", __FILE__, __LINE__);
+    std::vector<dd*> bufs((size_t)world, nullptr);
+    std::vector<unsigned*> flags((size_t)world, nullptr);
+    bool good = true;
+    for (int q = 0; q < world && good; ++q) {
+        const unsigned char* b = all.data() + blob * (size_t)q;
+        long long okq = 0; unsigned long long fq = 0;
+        std::memcpy(&h, b, sizeof h); std::memcpy(&fq, b + sizeof h, 8); std::memcpy(&okq, b + sizeof h + 8, 8);
+        if (!okq) { good = false; break; }
+        if (q == me) { bufs[(size_t)q] = C->red_buf; flags[(size_t)q] = C->red_flags; continue; }
+        void* pm = nullptr;
+        if (cudaIpcOpenMemHandle(&pm, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); good = false; break; }
+        C->ipc_mapped.push_back(pm);
+        bufs[(size_t)q] = (dd*)pm; flags[(size_t)q] = (unsigned*)((char*)pm + fq);
+    }
+    double bad = good ? 0.0 : 1.0;                         // all ranks or none
+    DB_CHECK(drops_b200_comm_allreduce_max(C, &bad));
+    if (bad != 0.0) {
+        for (void* m : C->ipc_mapped) cudaIpcCloseMemHandle(m);
+        C->ipc_mapped.clear();
+        return 0;
+    }
+    return comm_p2p_finish(C, bufs, flags);
 }
 
 int drops_b200_comm_create(int rank, int world, const void* id_bytes, drops_b200_comm_t* out)
@@ -1275,6 +1409,7 @@ int drops_b200_comm_create(int rank, int world, const void* id_bytes, drops_b200
             ncclResult_t r = nccl().CommInitRank(&nc, world, id, rank);
             if (r != ncclSuccess) s = nccl_fail(r, "ncclCommInitRank");
             C->nccl = nc;
+            if (s == 0) s = comm_p2p_setup_nccl(C);          // collective; failing to map peers is not an error
         }
     }
     if (s < 0) { drops_b200_comm_destroy(C); return s; }
@@ -1289,7 +1424,12 @@ int drops_b200_comm_create_local(int world, drops_b200_comm_t* out)
     drops_b200_comm_s* C = new drops_b200_comm_s;
     C->kind = COMM_LOCAL; C->rank = 0; C->world = world;
     C->parts.assign((size_t)world, nullptr);
-    const int s = comm_common(C);
+    int s = comm_common(C);
+    if (s == 0 && world > 1 && opt("dist.p2p", 1.0) != 0.0) {     // all ranks live here: every "peer" buffer is this one
+        std::vector<dd*> bufs((size_t)world, C->red_buf);
+        std::vector<unsigned*> flags((size_t)world, C->red_flags);
+        s = comm_p2p_finish(C, bufs, flags);
+    }
     if (s < 0) { drops_b200_comm_destroy(C); *out = nullptr; return s; }
     *out = C;
     return 0;
@@ -1307,6 +1447,8 @@ int drops_b200_comm_destroy(drops_b200_comm_t C)
     if (C->ev_halo) cudaEventDestroy(C->ev_halo);
     if (C->comm_stream) cudaStreamDestroy(C->comm_stream);
     dev_free(C->gathered);
+    for (void* m : C->ipc_mapped) cudaIpcCloseMemHandle(m);
+    dev_free(C->red_buf); dev_free(C->red_fault); dev_free(C->d_peer_red); dev_free(C->d_peer_redflag);
     delete C;
     return 0;
 }
@@ -1402,6 +1544,13 @@ int drops_b200_dist_matrix_format(drops_b200_dist_matrix_t A, int* interior_pack
         int f = 0;
         cudaStreamSynchronize(ctx().stream);
         cudaMemcpy(&f, A->p2p_fault, sizeof(int), cudaMemcpyDeviceToHost);
+        if (f) *interior_packed |= 32;
+    }
+    if (interior_packed && A->comm && A->comm->p2p == 1 && ctx().inited) {
+        int f = 0;
+        cudaStreamSynchronize(ctx().stream);
+        cudaMemcpy(&f, A->comm->red_fault, sizeof(int), cudaMemcpyDeviceToHost);
+        *interior_packed |= 64;                      // reductions go peer to peer as well
         if (f) *interior_packed |= 32;
     }
     if (n_distinct) *n_distinct = A->sell_int.ndict;

@@ -46,6 +46,18 @@ struct drops_b200_comm_s {
     cudaEvent_t ev_pack = nullptr, ev_halo = nullptr;
     db200::dd* gathered = nullptr;           // world * kMaxQ reduction partials, rank-major
     std::vector<drops_b200_dist_matrix_s*> parts;   // COMM_LOCAL: registered partitions by rank
+    // Peer-to-peer reductions ("dist.p2p_reduce"): every rank stores its partials straight into all ranks'
+    // buffers (CUDA IPC mappings over NVLink) and raises its sequence number there; k_dist_scalars waits for
+    // all sequence numbers.  Two parity halves: a rank can be at most one reduction ahead of another.
+    int p2p = 0;                             // 1 ready, -1 unavailable (ncclAllGather is used)
+    db200::dd* red_buf = nullptr;            // 2 x world x kMaxQ partials, then world flags (one >= 2 MB allocation)
+    unsigned* red_flags = nullptr;
+    db200::dd** d_peer_red = nullptr;        // world entries: base of every rank's red_buf (mapped)
+    unsigned** d_peer_redflag = nullptr;     // world entries: base of every rank's flag array
+    unsigned red_seq = 0;
+    bool red_last_p2p = false;               // the reduction just gathered went through the peer path
+    int* red_fault = nullptr;
+    std::vector<void*> ipc_mapped;
 };
 
 struct drops_b200_dist_matrix_s {

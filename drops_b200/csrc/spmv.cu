@@ -297,6 +297,7 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a)
     if (threads < 32) threads = 32;
     if (threads > 512) threads = 512;
     threads &= ~31;
+    if (a.xghost != nullptr) threads = 64;       // thin boundary operator: one slice per warp (see below)
     // Work decomposition: every CTA owns `slices_per_cta` consecutive slices, CTAs are launched in
     // matrix order.  Measured on B200 (profiles/r01_spmv.md): many short ranges walked in order
     // (128 threads x 16 slices = 512 rows per CTA, 98 k CTAs at C2) reach 5.9 TB/s, a persistent
@@ -307,7 +308,9 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a)
     long long grid;
     if (per_sm > 0.0) grid = (long long)(per_sm * c.sm_count + 0.5);
     else {
-        long long spc = (long long)opt("spmv.slices_per_cta", 16.0);
+        // boundary rows of a partition are a thin operator (0.4 % of the rows at C5): short CTAs, or the
+        // launch does not even fill the machine once
+        long long spc = (long long)(a.xghost != nullptr ? opt("spmv.bnd_slices_per_cta", 2.0) : opt("spmv.slices_per_cta", 16.0));
         if (spc < 1) spc = 1;
         grid = ((long long)A.nslices + spc - 1) / spc;
     }

@@ -390,7 +390,8 @@ DROPS_B200_API int drops_b200_dist_matrix_info(drops_b200_dist_matrix_t A, size_
  * dictionary-packed 4-byte stream, 2: the six-byte form, 4: the partition has its row-ordered twins (PCG
  * iterates in the numbering of the operators' own slices, "dist.reorder"), 8: rows were cut in blocks of the
  * partition's graph, 16: the peer-to-peer halo is set up (the pack kernel stores into the neighbours' ghost
- * buffers over NVLink, "dist.p2p"; otherwise ncclSend/ncclRecv), 32: a peer-to-peer wait timed out;
+ * buffers over NVLink, "dist.p2p"; otherwise ncclSend/ncclRecv), 32: a peer-to-peer wait timed out, 64: the
+ * reduction partials travel peer to peer as well ("dist.p2p_reduce"; otherwise ncclAllGather);
  * n_distinct = size of the interior operator's dictionary. */
 DROPS_B200_API int drops_b200_dist_matrix_format(drops_b200_dist_matrix_t A, int* interior_packed, int* n_distinct);
 DROPS_B200_API int drops_b200_dist_matrix_diag(drops_b200_dist_matrix_t A, double* diag);

@@ -67,13 +67,13 @@ def main():
         fmt = A.format()
         assert not fmt["p2p_fault"]
         if fmt["p2p"]:                          # the same solve with the halo over ncclSend/ncclRecv: same bits
-            capi.set_option("dist.p2p", 0)
+            capi.set_option("dist.p2p", 0); capi.set_option("dist.p2p_reduce", 0)
             x1 = capi.Vector(owned.size)
             c1, it1, res1 = capi.dist_pcg([A], [x1], [b], 3000, 1e-10, True)
-            capi.set_option("dist.p2p", 1)
+            capi.set_option("dist.p2p", 1); capi.set_option("dist.p2p_reduce", 1)
             assert it1 == it and res1 == res and np.array_equal(x1.download(), x0.download())
         if rank == 0:
-            print(f"P{fe} N={N} numbering={numbering} world={world} p2p={fmt['p2p']}: iters {it} (single GPU {ref[1]}), "
+            print(f"P{fe} N={N} numbering={numbering} world={world} p2p={fmt['p2p']} p2p_reduce={fmt['p2p_reduce']}: iters {it} (single GPU {ref[1]}), "
                   f"rel.diff {err:.2e}, gmres iters {git} (single GPU {gref[1]}), rel.diff {gerr:.2e}, "
                   f"ghosts {ex.n_ghost}, info {A.info()}", flush=True)
     dist.barrier()

@@ -93,14 +93,16 @@ def test_partitioned_matches_reference_golden(gpu, world):
         gpu.set_option("dist.reorder", 1)
     # halo through peer stores (default inside the solver loops) vs copies: the same bits
     if world > 1:
-        assert all(m.format()["p2p"] and not m.format()["p2p_fault"] for m in mats)
+        assert all(m.format()["p2p"] and m.format()["p2p_reduce"] and not m.format()["p2p_fault"] for m in mats)
         try:
             gpu.set_option("dist.p2p", 0)
+            gpu.set_option("dist.p2p_reduce", 0)
             x2 = [gpu.Vector(l[0].size) for l in loc]
             conv2, it2, res2 = gpu.dist_pcg(mats, x2, bs, 7, 0.0, True)
             assert it2 == 7 and res2 == res and np.array_equal(gather(loc, x2, n), gather(loc, x0, n))
         finally:
             gpu.set_option("dist.p2p", 1)
+            gpu.set_option("dist.p2p_reduce", 1)
     # unpreconditioned (DummyPcCL) and omega != 1
     for v in x0:
         v.fill(0.0)

@@ -8,7 +8,7 @@ timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --mast
 echo "worker exit $?"; grep -E "WORKER_OK|iters|Error|error|assert" gpurun_out/worker2_2c.log | head -20 | cut -c1-330
 echo "=== 2-rank pytest"
 timeout 300 python -m pytest tests/test_gpu_dist.py -m gpu -q -k two_ranks > gpurun_out/pytest_2c.log 2>&1; tail -3 gpurun_out/pytest_2c.log
-for o in "" "--opt dist.p2p=0"; do
+for o in "" "--opt dist.p2p=0 --opt dist.p2p_reduce=0" "--opt dist.p2p_reduce=0"; do
 echo "=== bench N=2 $o"
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 \
     bench.py --gpus 2 --steps 3 --warmup 3 $o > gpurun_out/bench_2c_n2.json 2> gpurun_out/bench_2c_n2.err
