@@ -498,12 +498,13 @@ int dist_matrix_build(drops_b200_comm_s* comm, drops_b200_exchange_s* E, size_t 
             if (s2 == 0) s2 = dev_alloc(&fb, n);
             if (s2 == 0) {
                 k_gather_flags<<<blocks_for((long long)n, 256), 256, 0, st>>>((long long)n, order, f_int, f_bnd, fi, fb);
-                cudaMemcpyAsync(rows_all, order, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
-                cudaMemcpyAsync(f_int, fi, n, cudaMemcpyDeviceToDevice, st);
-                cudaMemcpyAsync(f_bnd, fb, n, cudaMemcpyDeviceToDevice, st);
-                cudaStreamSynchronize(st);
-                M->block_ordered = true;
                 count_launch();
+                cudaError_t e2 = cudaMemcpyAsync(rows_all, order, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
+                if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(f_int, fi, n, cudaMemcpyDeviceToDevice, st);
+                if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(f_bnd, fb, n, cudaMemcpyDeviceToDevice, st);
+                if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(st);
+                if (e2 != cudaSuccess) s2 = cuda_fail(e2, "block order of a partition", __FILE__, __LINE__);
+                else M->block_ordered = true;
             }
             dev_free(fi); dev_free(fb); dev_free(order);
             DM_CHECK(s2);
