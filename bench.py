@@ -304,19 +304,25 @@ def run_ours(args):
         except Exception:
             pass
 
-    # ---- the same solve on the general 12-byte stream (what a matrix without a value dictionary runs)
+    # ---- the same solve on the general 12-byte stream (what a matrix without a value dictionary runs):
+    #      a second handle built with the dictionary switched off -- caller's row order, int32 column + fp64 value
     general = None
     if packed and not args.no_general:
-        capi.set_option("spmv.pk", 0)
+        capi.set_option("sell.valdict", 0)
+        G12 = capi.Matrix.brick(fe, N, numbering)
+        capi.set_option("sell.valdict", 1)
+        A_main = A
+        A = G12
         G = timed_steps(1, 1, False)
-        capi.set_option("spmv.pk", 1)
+        A = A_main
+        G12.close()
         g_spmv_ms = G["spmv"][0] / max(G["spmv"][1], 1)
         general = {"iterations_per_s": iters / (G["ms"] / 1e3), "spmv_avg_launch_ms": g_spmv_ms,
                    "spmv_achieved_gbs": survey_spmv_bytes / (g_spmv_ms / 1e3) / 1e9,
                    "spmv_frac": survey_spmv_bytes / (g_spmv_ms / 1e3) / 1e9 / peak,
                    "iteration_frac": (12.0 * nnz + 4.0 * (n + 1) + passes * 8.0 * n) * iters / (G["ms"] / 1e3) / 1e9 / peak,
-                   "note": "spmv.pk = 0: int32 column + fp64 value per entry, 1 step after 1 warm-up"}
-        assert G["resid"] == resid, (G["resid"], resid)     # bit-identical products -> identical solve
+                   "note": "sell.valdict = 0: int32 column + fp64 value per entry, caller's row order, 1 step after 1 warm-up"}
+        assert abs(G["resid"] - resid) <= 1e-9 * abs(resid), (G["resid"], resid)     # same system, same 200 iterations
 
     # ---- end to end through the host-buffer C ABI ----------------------------------------------
     import torch

@@ -331,6 +331,7 @@ struct SellOp {
     // alternate along a mesh line).  Vectors of that numbering have npos = 32*nslices entries
     // (padding positions hold 0); the entries of a row keep their order, so every y_i keeps its bits.
     uint16_t* vidx = nullptr;        // instead of pk when the bits do not fit one word: 16-bit dictionary index beside col (6 B / entry)
+    uint8_t* pk_nopad = nullptr;     // per slice: 1 = no padding word in the slice (the kernel then skips the selects)
     uint32_t* pkp = nullptr;         // padded entries: (dict index << cbits) | position of the column
     size_t npos = 0;
 };
@@ -369,7 +370,7 @@ struct drops_b200_matrix_s {
     size_t small_alloc = 0;
     // CUDA graph of one chunk of PCG iterations (launch-bound systems: cdrdrops' 250 k unknowns)
     cudaGraphExec_t pcg_graph = nullptr;
-    struct { const void* x; const void* b; int chunk; int cg; unsigned long long epoch; } pcg_graph_key = {nullptr, nullptr, 0, 0, 0};
+    struct { const void* x; const void* b; int chunk; int cg; unsigned long long epoch; uint64_t values; } pcg_graph_key = {nullptr, nullptr, 0, 0, 0, 0};
     long long pcg_graph_launches = 0;  // kernels inside the captured chunk
     // ChebyshevPcCL [0] / ChebyshevBBTPcCL [1] (num/precond.h:1463-1567): constructor arguments,
     // lambda_max cached like SetDiag does (keyed on the values epoch instead of Version())
@@ -394,6 +395,8 @@ int build_sell(const CsrDev& A, SellOp& S, size_t* bytes, const int32_t* rowmap,
                bool rowmap_is_permutation = false);
 // block order of the rows of a square operator from its graph (reorder.cu); *d_order = nullptr: keep the caller's order
 int compute_block_order(const CsrDev& A, int32_t** d_order);
+// one pass over the values: will this operator get the one-word packed stream (and with it the row-ordered twin)?
+int will_pack_one_word(const double* d_val, size_t nnz, size_t cols_and_positions, bool* yes);
 // (re)builds S.dict / S.pk from S.col / S.val; leaves them null when the matrix does not qualify
 int build_value_dictionary(SellOp& S, size_t* bytes);
 // row-ordered twin of S.pk under a caller-supplied numbering iperm[column] = position (< npos)

@@ -490,7 +490,9 @@ int dist_matrix_build(drops_b200_comm_s* comm, drops_b200_exchange_s* E, size_t 
             CsrDev L;
             L.rows = n; L.cols = n + ng; L.nnz = nnz;
             L.rowptr = const_cast<int64_t*>(d_rowptr); L.col = col; L.val = const_cast<double*>(d_val);
-            DM_CHECK(compute_block_order(L, &order));
+            bool packs = false;          // graph blocks only pay together with the row-ordered twins
+            DM_CHECK(will_pack_one_word(d_val, nnz, n + ng + 2 * 4096 + 64, &packs));
+            if (packs && opt("dist.reorder", 1.0) != 0.0) DM_CHECK(compute_block_order(L, &order));
         }
         if (order) {
             char *fi = nullptr, *fb = nullptr;

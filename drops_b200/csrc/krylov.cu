@@ -185,7 +185,8 @@ int pcg_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, doubl
     if (use_graph) {
         auto& key = M->pcg_graph_key;
         if (!M->pcg_graph || key.x != x || key.b != b || key.chunk != check_every ||
-            key.cg != (int)unpreconditioned_cg + 2 * pc || key.epoch != c.options_epoch) {
+            key.cg != (int)unpreconditioned_cg + 2 * pc || key.epoch != c.options_epoch || key.values != M->values_epoch) {
+            // (a value update rebuilds the packed streams and the dictionary: new device addresses)
             if (M->pcg_graph) { cudaGraphExecDestroy(M->pcg_graph); M->pcg_graph = nullptr; }
             const long long l0 = c.launches;
             cudaGraph_t graph = nullptr;
@@ -203,7 +204,7 @@ int pcg_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, doubl
             M->pcg_graph_launches = c.launches - l0;
             c.launches = l0;                                   // captured, not launched
             key.x = x; key.b = b; key.chunk = check_every; key.cg = (int)unpreconditioned_cg + 2 * pc;
-            key.epoch = c.options_epoch;
+            key.epoch = c.options_epoch; key.values = M->values_epoch;
             if (status != 0 && M->pcg_graph) { cudaGraphExecDestroy(M->pcg_graph); M->pcg_graph = nullptr; }
         }
     }

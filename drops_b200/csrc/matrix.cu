@@ -150,7 +150,7 @@ k_dict_collect(long long n, const int32_t* __restrict__ col, const double* __res
         if ((threadIdx.x & 31) == 0) over = *(volatile int*)count > kDictMax;
         if (__shfl_sync(0xffffffffu, over, 0)) return;
         const long long i = i0 + threadIdx.x;
-        const bool live = i < n && __ldcs(col + i) >= 0;               // padding holds no value
+        const bool live = i < n && (col == nullptr || __ldcs(col + i) >= 0);   // padding holds no value
         const unsigned long long key = live ? (unsigned long long)__double_as_longlong(__ldcs(val + i)) : 0ULL;
         const unsigned act = __ballot_sync(0xffffffffu, live);
         if (!live) continue;
@@ -356,7 +356,7 @@ void free_sell(SellOp& s)
 {
     dev_free(s.slice_ptr); dev_free(s.col); dev_free(s.val); dev_free(s.perm);
     dev_free(s.col16); dev_free(s.cbase); dev_free(s.wide);
-    dev_free(s.pk); dev_free(s.dict); dev_free(s.pkp); dev_free(s.vidx);
+    dev_free(s.pk); dev_free(s.dict); dev_free(s.pkp); dev_free(s.vidx); dev_free(s.pk_nopad);
     s = SellOp();
 }
 
@@ -467,6 +467,22 @@ k_dict_index16(long long n, const int32_t* __restrict__ col, const double* __res
     vidx[i] = (uint16_t)lo;
 }
 
+// one warp per slice: does the slice hold a padding word?  (rows are sorted by length inside a window, so
+// only the last entry-row can differ between the lanes; slices of padding rows are all padding)
+__global__ void k_slice_nopad(long long nslices, const int64_t* __restrict__ slice_ptr, const uint32_t* __restrict__ pk,
+                              uint32_t wpad, uint8_t* __restrict__ nopad)
+{
+    const int lane = threadIdx.x & 31;
+    const long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= nslices) return;
+    const int64_t base = slice_ptr[s];
+    const int width = (int)((slice_ptr[s + 1] - base) >> 5);
+    bool pad = false;
+    for (int j = 0; j < width; ++j) pad |= pk[base + (int64_t)j * 32 + lane] >= wpad;
+    const unsigned any = __ballot_sync(0xffffffffu, pad);
+    if (lane == 0) nopad[s] = any == 0u ? 1 : 0;
+}
+
 __global__ void k_inverse_perm(long long npos, const int32_t* __restrict__ perm, int32_t* __restrict__ iperm)
 {
     const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -495,11 +511,42 @@ static int bits_for(unsigned long long count)      // bits that distinguish `cou
     return b;
 }
 
+// Will an operator with these values and `cols` columns (positions: up to cols + slack) get the one-word
+// packed stream?  One pass over val; decides up front whether the rows are cut in graph blocks (reorder.cu),
+// which only pays together with the row-ordered twin of that stream.
+int will_pack_one_word(const double* d_val, size_t nnz, size_t cols_and_positions, bool* yes)
+{
+    *yes = false;
+    if (nnz == 0 || opt("sell.valdict", 1.0) == 0.0) return 0;
+    cudaStream_t st = ctx().stream;
+    unsigned long long* table = nullptr; int* d_count = nullptr;
+    const size_t cap = (size_t)1 << kDictTableBits;
+    DB_CHECK(dev_alloc(&table, cap));
+    if (dev_alloc(&d_count, 1) < 0) { dev_free(table); return DROPS_B200_E_NOMEM; }
+    int count = 0;
+    cudaError_t e = cudaMemsetAsync(table, 0xff, cap * sizeof(unsigned long long), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_count, 0, sizeof(int), st);
+    if (e == cudaSuccess) {
+        const int grid = (int)std::min<long long>(((long long)nnz + 255) / 256, (long long)ctx().sm_count * 16);
+        k_dict_collect<<<grid, 256, 0, st>>>((long long)nnz, nullptr, d_val, table, d_count);
+        count_launch();
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&count, d_count, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    dev_free(table); dev_free(d_count);
+    if (e != cudaSuccess) return cuda_fail(e, "value dictionary: count", __FILE__, __LINE__);
+    const int cbits = std::max(1, bits_for((unsigned long long)std::max<size_t>(cols_and_positions, 1)));
+    // (+1: padding may add the value 0.0; +1: the padding slot)
+    *yes = count >= 1 && count + 1 <= kDictMax && cbits + bits_for((unsigned long long)count + 2) <= (int)opt("sell.pack_bits", 32.0);
+    return 0;
+}
+
 int build_value_dictionary(SellOp& S, size_t* bytes)
 {
     cudaStream_t st = ctx().stream;
-    dev_free(S.pk); dev_free(S.dict); dev_free(S.pkp); dev_free(S.vidx);
-    S.pk = nullptr; S.dict = nullptr; S.pkp = nullptr; S.vidx = nullptr; S.ndict = 0; S.cbits = 0; S.npos = 0;
+    dev_free(S.pk); dev_free(S.dict); dev_free(S.pkp); dev_free(S.vidx); dev_free(S.pk_nopad);
+    S.pk_nopad = nullptr; S.pk = nullptr; S.dict = nullptr; S.pkp = nullptr; S.vidx = nullptr; S.ndict = 0; S.cbits = 0; S.npos = 0;
     if (S.padded == 0 || S.col == nullptr || S.val == nullptr || opt("sell.valdict", 1.0) == 0.0) return 0;
     // columns and, for the row-ordered twin, positions (32 * nslices >= rows) share the low bits
     const int cbits = std::max(1, bits_for((unsigned long long)std::max<size_t>(std::max(S.cols, S.nslices * 32), 1)));
@@ -559,6 +606,17 @@ int build_value_dictionary(SellOp& S, size_t* bytes)
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);
             if (e != cudaSuccess) fail(e, "value dictionary: pack");
         }
+        if (status == 0 && one_word) {
+            status = dev_alloc(&S.pk_nopad, S.nslices);
+            if (status == 0) {
+                k_slice_nopad<<<blocks_for((long long)S.nslices * 32, 256), 256, 0, st>>>((long long)S.nslices, S.slice_ptr, S.pk,
+                                                                                         (uint32_t)count << cbits, S.pk_nopad);
+                count_launch();
+                e = cudaGetLastError();
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                if (e != cudaSuccess) fail(e, "value dictionary: padding flags");
+            }
+        }
         if (status == 0) {
             S.ndict = count; S.cbits = one_word ? cbits : 0;
             if (bytes) *bytes += S.padded * (one_word ? 4 : 2) + keys.size() * 8;
@@ -583,7 +641,8 @@ int build_value_dictionary(SellOp& S, size_t* bytes)
             else { dev_free(S.pkp); S.pkp = nullptr; }
         }
         if (status != 0) {
-            dev_free(S.pk); dev_free(S.dict); dev_free(S.vidx); S.pk = nullptr; S.dict = nullptr; S.vidx = nullptr; S.ndict = 0;
+            dev_free(S.pk); dev_free(S.dict); dev_free(S.vidx); dev_free(S.pk_nopad);
+            S.pk = nullptr; S.dict = nullptr; S.vidx = nullptr; S.pk_nopad = nullptr; S.ndict = 0;
         }
     }
     dev_free(table);
@@ -694,7 +753,9 @@ int finalize_matrix(drops_b200_matrix_s* M)
     if (M->square) M->device_bytes += M->csr.rows * 8;
     // rows in compact blocks of the matrix graph (reorder.cu) when the operator is large enough to profit
     int32_t* order = nullptr;
-    DB_CHECK(compute_block_order(M->csr, &order));
+    bool packs = false;
+    DB_CHECK(will_pack_one_word(M->csr.val, M->csr.nnz, std::max(M->csr.cols, M->csr.rows + 4096), &packs));
+    if (packs && M->square && opt("sell.reorder", 1.0) != 0.0) DB_CHECK(compute_block_order(M->csr, &order));
     const int s = build_sell(M->csr, M->sell, &M->device_bytes, order, order ? M->csr.rows : 0, order != nullptr);
     dev_free(order);
     M->block_ordered = s == 0 && order != nullptr;

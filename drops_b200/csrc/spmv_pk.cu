@@ -28,6 +28,7 @@ struct PkView {
     long long nslices;
     int ndict;
     int cbits;
+    const uint8_t* nopad;       // per slice: 1 = no padding word (nullptr: unknown, keep the selects)
 };
 
 // matrix-stream load: LD = 0 ld.global.cs (evict-first in L1 and L2), 1 = L1::no_allocate + L2 evict-first
@@ -46,7 +47,7 @@ __device__ __forceinline__ uint32_t ld_stream(const uint32_t* p)
 // load of the unrolled body is unconditional and straight-line; the padded product is computed and
 // then dropped by a select (adding it could turn a -0.0 sum into +0.0, or poison it when x_0 is
 // not finite), which keeps the row sum bit-identical.
-template <bool EXACT, int U, bool SMEM, int LD>
+template <bool EXACT, int U, bool SMEM, int LD, bool NOPAD = false>
 __device__ __forceinline__ double pk_row_sum(const PkView& A, int64_t base, int width, int lane,
                                              const double* __restrict__ x)
 {
@@ -68,7 +69,7 @@ __device__ __forceinline__ double pk_row_sum(const PkView& A, int64_t base, int 
         for (int u = 0; u < U; ++u) {
             const double v = SMEM ? sdict[w[u] >> cbits] : __ldg(A.dict + (w[u] >> cbits));
             const double t = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv[u])) : fma(v, xv[u], sum);
-            sum = w[u] < wpad ? t : sum;
+            sum = (NOPAD || w[u] < wpad) ? t : sum;
         }
     }
     for (; j < width; ++j) {
@@ -76,7 +77,7 @@ __device__ __forceinline__ double pk_row_sum(const PkView& A, int64_t base, int 
         const double xv = __ldg(x + (w & cmask));
         const double v = SMEM ? sdict[w >> cbits] : __ldg(A.dict + (w >> cbits));
         const double t = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv)) : fma(v, xv, sum);
-        sum = w < wpad ? t : sum;
+        sum = (NOPAD || w < wpad) ? t : sum;
     }
     return sum;
 }
@@ -219,9 +220,12 @@ k_spmv_sell_pk(PkView A, const double* __restrict__ x, double* __restrict__ y, E
         }
         // U < 0: software-pipelined form; U >= 100: U - 100 words in flight, stream loaded with L1::no_allocate
         constexpr int UU = U < 0 ? -U : (U >= 100 ? U - 100 : U);
+        // 99.8 % of the slices of a sorted operator hold no padding word: their row sum needs no selects
+        const bool nopad = !V6 && U > 0 && A.nopad != nullptr && A.nopad[s] != 0;      // warp-uniform
         const double sum = V6 ? pk6_row_sum<EXACT, UU, SMEM>(A, base, width, lane, x)
-                         : U > 0 ? pk_row_sum<EXACT, UU, SMEM, (U >= 100 ? 1 : 0)>(A, base, width, lane, x)
-                                 : pk_row_sum_pipe<EXACT, UU, SMEM>(A, base, width, lane, x);
+                         : U <= 0 ? pk_row_sum_pipe<EXACT, UU, SMEM>(A, base, width, lane, x)
+                         : nopad ? pk_row_sum<EXACT, UU, SMEM, (U >= 100 ? 1 : 0), true>(A, base, width, lane, x)
+                                 : pk_row_sum<EXACT, UU, SMEM, (U >= 100 ? 1 : 0), false>(A, base, width, lane, x);
         if (row >= 0) {
             const double out = apply_epilogue<EPI>(sum, av, e, beta);
             y[row] = out;
@@ -372,7 +376,7 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
     if (grid < 1) grid = 1;
     cudaStream_t st = a.stream ? a.stream : c.stream;
     PkView v{A.slice_ptr, A.col, A.pk != nullptr ? nullptr : A.vidx, a.row_ordered ? A.pkp : A.pk, A.dict, a.row_ordered ? nullptr : A.perm, (long long)A.nslices,
-             A.ndict, A.cbits};
+             A.ndict, A.cbits, opt("spmv.pk_nopad", 1.0) != 0.0 ? A.pk_nopad : nullptr};
     EpiArgs e = make_epi(a);
     e.prefetch = (int)opt("spmv.pk_prefetch", 0.0);        // slices ahead (in units of the CTA's warp count)
     if (opt("spmv.exact", 1.0) != 0.0) launch_pk_epi<true>(v, a, e, (int)grid, threads, st);

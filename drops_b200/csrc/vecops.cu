@@ -435,6 +435,7 @@ struct OpPcgUpdateR {
     }
 };
 
+template <int STEP>
 __global__ void __launch_bounds__(kReduceThreads)
 k_pcg_update_r(size_t n, double* __restrict__ r, const double* __restrict__ q, const double* __restrict__ d,
                SolverScalars* S, double* hist, dd* part_out, dd* partials, unsigned* ticket)
@@ -450,17 +451,26 @@ k_pcg_update_r(size_t n, double* __restrict__ r, const double* __restrict__ q, c
     const double2* q2 = reinterpret_cast<const double2*>(q);
     const double2* d2 = reinterpret_cast<const double2*>(d);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
-        double2 rv = r2[i];
-        const double2 qv = __ldcs(q2 + i);                      // q is dead after this kernel
-        double2 dv = make_double2(1.0, 1.0);
-        if (jac) dv = d2[i];
+    // two elements of the grid-stride sequence per trip: 6 independent 16 B loads in flight per thread; the
+    // per-thread order of the accumulated products is unchanged (i, i + stride, i + 2 stride, ...)
+    auto body = [&](size_t i, double2 rv, const double2 qv, const double2 dv) {
         rv.x = add(rv.x, mul(-alpha, qv.x)); rv.y = add(rv.y, mul(-alpha, qv.y));
         r2[i] = rv;
         const double zx = jac ? dvd(mul(omega, rv.x), dv.x) : rv.x;
         const double zy = jac ? dvd(mul(omega, rv.y), dv.y) : rv.y;
         acc[0] = dd_add_prod(acc[0], rv.x, rv.x); acc[0] = dd_add_prod(acc[0], rv.y, rv.y);
         acc[1] = dd_add_prod(acc[1], zx, rv.x);   acc[1] = dd_add_prod(acc[1], zy, rv.y);
+    };
+    const double2 one2 = make_double2(1.0, 1.0);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += STEP * stride) {
+        const size_t j = i + stride;
+        const bool two = STEP == 2 && j < n2;
+        const double2 rv0 = r2[i], qv0 = __ldcs(q2 + i);            // q is dead after this kernel
+        const double2 dv0 = jac ? d2[i] : one2;
+        double2 rv1 = one2, qv1 = one2, dv1 = one2;
+        if (two) { rv1 = r2[j]; qv1 = __ldcs(q2 + j); dv1 = jac ? d2[j] : one2; }
+        body(i, rv0, qv0, dv0);
+        if (two) body(j, rv1, qv1, dv1);
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) op.elem(n - 1, acc);
     if (grid_reduce_dd<2>(acc, red_smem, partials, ticket)) {
@@ -474,7 +484,12 @@ int pcg_update_r(size_t n, double* r, const double* q, const double* d, SolverSc
         Ctx& c = ctx();
         ScopedTiming t("pcg.update");
         const int grid = vec_grid(n, kReduceThreads, 4);
-        k_pcg_update_r<<<grid, kReduceThreads, 0, c.stream>>>(n, r, q, d, S, hist, part_out, c.partials, c.tickets);
+        // measured on C2: two elements per trip help the direction kernel (0.375 -> 0.362 ms) and hurt this
+        // one (0.282 -> 0.306 ms: 74 registers), so the default differs ("vec.unroll2_update")
+        if (opt("vec.unroll2_update", 0.0) != 0.0)
+            k_pcg_update_r<2><<<grid, kReduceThreads, 0, c.stream>>>(n, r, q, d, S, hist, part_out, c.partials, c.tickets);
+        else
+            k_pcg_update_r<1><<<grid, kReduceThreads, 0, c.stream>>>(n, r, q, d, S, hist, part_out, c.partials, c.tickets);
         count_launch();
         DB_CUDA(cudaGetLastError());
         return 0;
@@ -487,6 +502,7 @@ int pcg_update_r(size_t n, double* r, const double* q, const double* d, SolverSc
 // pcg_update_finish the iteration's rho sits in rho_1, so alpha = rho_1 / lambda is the quotient the
 // update kernel used (:152).  The block that finishes last marks the x update as applied; kernels of
 // iterations that are skipped after the stop see x_iter == iter and do nothing.
+template <int STEP>
 __global__ void __launch_bounds__(kReduceThreads)
 k_pcg_direction_x(size_t n, double* __restrict__ x, double* __restrict__ p, const double* __restrict__ r,
                   const double* __restrict__ d, SolverScalars* S, unsigned* ticket)
@@ -504,19 +520,26 @@ k_pcg_direction_x(size_t n, double* __restrict__ x, double* __restrict__ p, cons
     const double2* r2 = reinterpret_cast<const double2*>(r);
     const double2* d2 = reinterpret_cast<const double2*>(d);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
-        double2 xv = x2[i], pv = p2[i];
+    auto body = [&](size_t i, double2 xv, double2 pv, const double2 rv, const double2 dv) {
         xv.x = add(xv.x, mul(alpha, pv.x)); xv.y = add(xv.y, mul(alpha, pv.y));   // :154
         x2[i] = xv;
         if (more) {
-            const double2 rv = r2[i];
-            double2 dv = make_double2(1.0, 1.0);
-            if (jac) dv = d2[i];
             const double zx = jac ? dvd(mul(omega, rv.x), dv.x) : rv.x;
             const double zy = jac ? dvd(mul(omega, rv.y), dv.y) : rv.y;
             pv.x = add(zx, mul(beta, pv.x)); pv.y = add(zy, mul(beta, pv.y));     // :174
             p2[i] = pv;
         }
+    };
+    const double2 one2 = make_double2(1.0, 1.0);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += STEP * stride) {    // STEP elements per trip
+        const size_t j = i + stride;
+        const bool two = STEP == 2 && j < n2;
+        const double2 xv0 = x2[i], pv0 = p2[i];
+        const double2 rv0 = more ? r2[i] : one2, dv0 = (more && jac) ? d2[i] : one2;
+        double2 xv1 = one2, pv1 = one2, rv1 = one2, dv1 = one2;
+        if (two) { xv1 = x2[j]; pv1 = p2[j]; if (more) { rv1 = r2[j]; if (jac) dv1 = d2[j]; } }
+        body(i, xv0, pv0, rv0, dv0);
+        if (two) body(j, xv1, pv1, rv1, dv1);
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const size_t i = n - 1;
@@ -537,7 +560,10 @@ int pcg_direction_x(size_t n, double* x, double* p, const double* r, const doubl
     DB_ARG(aligned16(x, p, r, d), "pcg_direction_x needs 16-byte aligned vectors");
     ScopedTiming t("pcg.direction");
     const int grid = vec_grid(n, kReduceThreads, 4);
-    k_pcg_direction_x<<<grid, kReduceThreads, 0, c.stream>>>(n, x, p, r, d, S, c.tickets + (size_t)2 * kTicketStride);
+    if (opt("vec.unroll2", 1.0) != 0.0)
+        k_pcg_direction_x<2><<<grid, kReduceThreads, 0, c.stream>>>(n, x, p, r, d, S, c.tickets + (size_t)2 * kTicketStride);
+    else
+        k_pcg_direction_x<1><<<grid, kReduceThreads, 0, c.stream>>>(n, x, p, r, d, S, c.tickets + (size_t)2 * kTicketStride);
     count_launch();
     DB_CUDA(cudaGetLastError());
     return 0;
