@@ -280,7 +280,7 @@ def run_ours(args):
     survey_iter_bytes = 12.0 * nnz + 4.0 * (n + 1) + 13.0 * 8.0 * n
     spmv_avg_ms = spmv_ms / max(spmv_cnt, 1)
     achieved = spmv_bytes / (spmv_avg_ms / 1e3) / 1e9
-    kernel_name = ("k_spmv_sell_pk<EPI_NONE,exact,dot> (q = A p fused with p.q, dictionary-packed %d-byte stream)" % int(entry_bytes)
+    kernel_name = ("k_spmv_sell_pk<EPI_NONE,exact,dot> (q = A p fused with p.q, dictionary-packed %d-byte stream, dictionary in the kernel's parameter block)" % int(entry_bytes)
                    if packed else "k_spmv_sell<EPI_NONE,exact,dot> (q = A p fused with p.q)")
     roofline = {"bound": "hbm", "kernel": kernel_name,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

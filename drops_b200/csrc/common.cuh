@@ -296,6 +296,8 @@ struct drops_b200_vector_s {
 namespace db200 {
 
 // Sliced-ELL (C = 32, sigma-sorted) operator + the CSR it was built from.
+constexpr int kDictConst = 48;       // dictionary entries (values + the padding slot) a kernel parameter block carries
+
 struct SellOp {
     size_t rows = 0, cols = 0;
     size_t nslices = 0;
@@ -323,6 +325,8 @@ struct SellOp {
     uint32_t* pk = nullptr;          // padded entries
     double* dict = nullptr;          // ndict distinct values + one 0.0 (the padding slot)
     int ndict = 0;
+    double dict_host[kDictConst] = {};   // the same list on the host when it fits: travels as a kernel parameter
+    int ndict_host = 0;                  // (constant bank: lookups leave the L1 data pipe, spmv_pk.cu "spmv.pk_cdict")
     int cbits = 0;                   // low bits of pk that hold the column
     // Row-ordered twin of pk (square operators over all rows): the unknowns renumbered by the
     // operator's own slice order -- position s*32+lane of the sorted windows -- so that row `pos`

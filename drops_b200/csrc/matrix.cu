@@ -546,7 +546,7 @@ int build_value_dictionary(SellOp& S, size_t* bytes)
 {
     cudaStream_t st = ctx().stream;
     dev_free(S.pk); dev_free(S.dict); dev_free(S.pkp); dev_free(S.vidx); dev_free(S.pk_nopad);
-    S.pk_nopad = nullptr; S.pk = nullptr; S.dict = nullptr; S.pkp = nullptr; S.vidx = nullptr; S.ndict = 0; S.cbits = 0; S.npos = 0;
+    S.pk_nopad = nullptr; S.pk = nullptr; S.dict = nullptr; S.pkp = nullptr; S.vidx = nullptr; S.ndict = 0; S.ndict_host = 0; S.cbits = 0; S.npos = 0;
     if (S.padded == 0 || S.col == nullptr || S.val == nullptr || opt("sell.valdict", 1.0) == 0.0) return 0;
     // columns and, for the row-ordered twin, positions (32 * nslices >= rows) share the low bits
     const int cbits = std::max(1, bits_for((unsigned long long)std::max<size_t>(std::max(S.cols, S.nslices * 32), 1)));
@@ -618,6 +618,11 @@ int build_value_dictionary(SellOp& S, size_t* bytes)
             }
         }
         if (status == 0) {
+            S.ndict_host = 0;
+            if (dict_host.size() <= (size_t)kDictConst) {
+                std::memcpy(S.dict_host, dict_host.data(), dict_host.size() * sizeof(double));
+                S.ndict_host = count;
+            }
             S.ndict = count; S.cbits = one_word ? cbits : 0;
             if (bytes) *bytes += S.padded * (one_word ? 4 : 2) + keys.size() * 8;
         }

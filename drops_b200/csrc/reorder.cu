@@ -74,14 +74,15 @@ __device__ __forceinline__ unsigned spread3(unsigned v)     // 10 bits -> every 
 }
 
 __global__ void k_block_keys(long long n, const int32_t* __restrict__ da, const int32_t* __restrict__ db,
-                             const int32_t* __restrict__ dc, int tile, unsigned* __restrict__ key, int32_t* __restrict__ row)
+                             const int32_t* __restrict__ dc, int ta, int tb, int tc, unsigned* __restrict__ key,
+                             int32_t* __restrict__ row)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     row[i] = (int32_t)i;
     const int a = da[i], b = db[i], c = dc[i];
     if (a < 0 || b < 0 || c < 0) { key[i] = 0x3fffffffu; return; }      // not reachable: after everything else
-    const unsigned ca = min(a / tile, 1022), cb = min(b / tile, 1022), cc = min(c / tile, 1022);
+    const unsigned ca = min(a / ta, 1022), cb = min(b / tb, 1022), cc = min(c / tc, 1022);
     key[i] = spread3(ca) | (spread3(cb) << 1) | (spread3(cc) << 2);
 }
 
@@ -139,6 +140,10 @@ int compute_block_order(const CsrDev& A, int32_t** d_order)
     if ((double)A.rows < opt("sell.block_min_rows", 2.0e6)) return 0;
     int tile = (int)opt("sell.block_tile", 8.0);
     if (tile < 1) tile = 1;
+    // per-field tiles ("sell.block_tile_a/b/c", 0 = block_tile): cells need not be cubes
+    const int ta = std::max(1, (int)opt("sell.block_tile_a", 0.0) > 0 ? (int)opt("sell.block_tile_a", 0.0) : tile);
+    const int tb = std::max(1, (int)opt("sell.block_tile_b", 0.0) > 0 ? (int)opt("sell.block_tile_b", 0.0) : tile);
+    const int tc = std::max(1, (int)opt("sell.block_tile_c", 0.0) > 0 ? (int)opt("sell.block_tile_c", 0.0) : tile);
     cudaStream_t st = ctx().stream;
     const int n = (int)A.rows;
     int32_t *da = nullptr, *db = nullptr, *dc = nullptr, *q0 = nullptr, *q1 = nullptr, *rows_in = nullptr, *rows_out = nullptr;
@@ -170,7 +175,7 @@ int compute_block_order(const CsrDev& A, int32_t** d_order)
     dev_free(q0); q0 = nullptr; dev_free(q1); q1 = nullptr;
     RO_CHECK(dev_alloc(&key_in, (size_t)n)); RO_CHECK(dev_alloc(&key_out, (size_t)n));
     RO_CHECK(dev_alloc(&rows_in, (size_t)n)); RO_CHECK(dev_alloc(&rows_out, (size_t)n));
-    k_block_keys<<<blocks_of(n, 256), 256, 0, st>>>(n, da, db, dc, tile, key_in, rows_in);
+    k_block_keys<<<blocks_of(n, 256), 256, 0, st>>>(n, da, db, dc, ta, tb, tc, key_in, rows_in);
     count_launch();
     size_t need = 0;
     RO_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, key_in, key_out, rows_in, rows_out, n, 0, 30, st));

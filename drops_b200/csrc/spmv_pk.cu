@@ -14,9 +14,12 @@
 //   * x through ld.global.nc; epilogues and the fused dot exactly as in spmv.cu.
 #include "spmv_impl.cuh"
 
+#include <cstring>
+
 namespace db200 {
 
 constexpr int kPkDictSmem = 512;
+constexpr size_t kXwMaxSmem = 100 * 1024;      // x window + dictionary per CTA
 
 struct PkView {
     const int64_t* slice_ptr;
@@ -29,7 +32,20 @@ struct PkView {
     int ndict;
     int cbits;
     const uint8_t* nopad;       // per slice: 1 = no padding word (nullptr: unknown, keep the selects)
+    int xw_halo;                // XW kernels: slices of x staged either side of the CTA's own rows
+    int cdict_n;                // > 0: cdict holds the dictionary (values + padding slot)
+    double cdict[kDictConst];   // CD kernels: the dictionary inside the parameter block (constant bank)
 };
+
+// a_ij from its dictionary index: shared memory (SMEM), the kernel's parameter block (CD: an indexed
+// constant load, which does not pass through the L1 data pipe the x gathers saturate), or global memory
+template <bool SMEM, bool CD>
+__device__ __forceinline__ double pk_value(const PkView& A, uint32_t idx)
+{
+    extern __shared__ double sdict[];
+    if (CD) return A.cdict[idx];
+    return SMEM ? sdict[idx] : __ldg(A.dict + idx);
+}
 
 // matrix-stream load: LD = 0 ld.global.cs (evict-first in L1 and L2), 1 = L1::no_allocate + L2 evict-first
 template <int LD>
@@ -43,13 +59,36 @@ __device__ __forceinline__ uint32_t ld_stream(const uint32_t* p)
     return v;
 }
 
+// x window (XW, option "spmv.pk_xwin", off): with row-ordered vectors a CTA's own rows are the positions
+// [32 s_begin, 32 s_end) of x, and on a block-ordered operator (reorder.cu) most of the columns of those rows
+// are positions of the same block.  The CTA copies that stretch of x (plus `halo` slices either side) into
+// shared memory with coalesced loads and gathers from there; only columns outside the window go through L1.
+// Measured on C2 inside PCG (profiles/r01_probe_xw.json): bit-identical and SLOWER in every geometry -- 1.68 ms
+// without the window, 2.06-2.9 ms with it (the window costs L1 capacity and every gather becomes a predicated
+// LDS + LDG pair).  Kept as a measured option.
+struct XWin {
+    uint32_t off;               // sdict[off + k] = x[base + k], k < len
+    uint32_t base, len;
+};
+
+template <bool XW>
+__device__ __forceinline__ double pk_gather(const double* __restrict__ x, const XWin& xw, uint32_t pos)
+{
+    if (XW) {
+        extern __shared__ double sdict[];
+        const uint32_t rel = pos - xw.base;
+        return rel < xw.len ? sdict[xw.off + rel] : __ldg(x + pos);
+    }
+    return __ldg(x + pos);
+}
+
 // Padding is the word (ndict << cbits): column 0 and the extra dictionary slot ndict (0.0), so every
 // load of the unrolled body is unconditional and straight-line; the padded product is computed and
 // then dropped by a select (adding it could turn a -0.0 sum into +0.0, or poison it when x_0 is
 // not finite), which keeps the row sum bit-identical.
-template <bool EXACT, int U, bool SMEM, int LD, bool NOPAD = false>
+template <bool EXACT, int U, bool SMEM, int LD, bool NOPAD = false, bool XW = false, bool CD = false>
 __device__ __forceinline__ double pk_row_sum(const PkView& A, int64_t base, int width, int lane,
-                                             const double* __restrict__ x)
+                                             const double* __restrict__ x, const XWin& xw = XWin())
 {
     extern __shared__ double sdict[];      // the CTA's copy of the dictionary (SMEM)
     const uint32_t* pp = A.pk + base + lane;
@@ -64,18 +103,18 @@ __device__ __forceinline__ double pk_row_sum(const PkView& A, int64_t base, int 
 #pragma unroll
         for (int u = 0; u < U; ++u) w[u] = ld_stream<LD>(pp + (size_t)(j + u) * 32);
 #pragma unroll
-        for (int u = 0; u < U; ++u) xv[u] = __ldg(x + (w[u] & cmask));
+        for (int u = 0; u < U; ++u) xv[u] = pk_gather<XW>(x, xw, w[u] & cmask);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const double v = SMEM ? sdict[w[u] >> cbits] : __ldg(A.dict + (w[u] >> cbits));
+            const double v = pk_value<SMEM, CD>(A, w[u] >> cbits);
             const double t = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv[u])) : fma(v, xv[u], sum);
             sum = (NOPAD || w[u] < wpad) ? t : sum;
         }
     }
     for (; j < width; ++j) {
         const uint32_t w = ld_stream<LD>(pp + (size_t)j * 32);
-        const double xv = __ldg(x + (w & cmask));
-        const double v = SMEM ? sdict[w >> cbits] : __ldg(A.dict + (w >> cbits));
+        const double xv = pk_gather<XW>(x, xw, w & cmask);
+        const double v = pk_value<SMEM, CD>(A, w >> cbits);
         const double t = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv)) : fma(v, xv, sum);
         sum = (NOPAD || w < wpad) ? t : sum;
     }
@@ -177,22 +216,33 @@ __device__ __forceinline__ double pk_row_sum_pipe(const PkView& A, int64_t base,
 //   2 = in the slice loop, but the partner is fetched AFTER the row sum (an L1 hit: the diagonal
 //       entry just gathered it) and the accumulator is parked in shared memory between slices, so
 //       the row sum runs with the registers of the plain product.
-template <int EPI, bool EXACT, int DOT, int U, int MAXT, int MINB, bool SMEM, int DF, bool V6 = false>
+template <int EPI, bool EXACT, int DOT, int U, int MAXT, int MINB, bool SMEM, int DF, bool V6 = false, bool XW = false, bool CD = false>
 __global__ void __launch_bounds__(MAXT, MINB)
-k_spmv_sell_pk(PkView A, const double* __restrict__ x, double* __restrict__ y, EpiArgs e)
+k_spmv_sell_pk(const __grid_constant__ PkView A, const double* __restrict__ x, double* __restrict__ y, EpiArgs e)
 {
     if (e.done != nullptr && *e.done != 0) return;
     extern __shared__ double sdict[];
     __shared__ dd red_smem[DOT == 1 ? 32 : 1];
     __shared__ dd acc_smem[(DOT != 0 && DF == 2) ? MAXT : 1];
     if (DOT != 0 && DF == 2) acc_smem[threadIdx.x] = dd_zero();     // the thread's own slot: no barrier needed
-    if (SMEM) {
-        for (int i = threadIdx.x; i <= A.ndict; i += blockDim.x) sdict[i] = A.dict[i];
-        __syncthreads();
-    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const long long s_begin = A.nslices * (long long)blockIdx.x / gridDim.x;
     const long long s_end   = A.nslices * (long long)(blockIdx.x + 1) / gridDim.x;
+    XWin xw{0u, 0u, 0u};
+    if (SMEM) {
+        for (int i = threadIdx.x; i <= A.ndict; i += blockDim.x) sdict[i] = A.dict[i];
+    }
+    if (XW) {
+        // the window sits behind the dictionary (16-byte aligned); positions are multiples of 32 doubles
+        double* swin = sdict + ((A.ndict + 2) & ~1);
+        const long long lo = s_begin - A.xw_halo > 0 ? s_begin - A.xw_halo : 0;
+        const long long hi = s_end + A.xw_halo < A.nslices ? s_end + A.xw_halo : A.nslices;
+        xw.off = (uint32_t)((A.ndict + 2) & ~1); xw.base = (uint32_t)(lo * 32); xw.len = (uint32_t)((hi - lo) * 32);
+        const double2* src = reinterpret_cast<const double2*>(x + lo * 32);
+        double2* dst = reinterpret_cast<double2*>(swin);
+        for (uint32_t i = threadIdx.x; i < xw.len / 2; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    if (SMEM || XW) __syncthreads();
     const double beta = (EPI == EPI_AXMBY) ? (e.beta != nullptr ? *e.beta : e.beta_val) : 0.0;
     dd acc[1] = {dd_zero()};
     // PCG: x += alpha p of the previous iteration rides on this product (DRAM has the headroom, the
@@ -224,8 +274,8 @@ k_spmv_sell_pk(PkView A, const double* __restrict__ x, double* __restrict__ y, E
         const bool nopad = !V6 && U > 0 && A.nopad != nullptr && A.nopad[s] != 0;      // warp-uniform
         const double sum = V6 ? pk6_row_sum<EXACT, UU, SMEM>(A, base, width, lane, x)
                          : U <= 0 ? pk_row_sum_pipe<EXACT, UU, SMEM>(A, base, width, lane, x)
-                         : nopad ? pk_row_sum<EXACT, UU, SMEM, (U >= 100 ? 1 : 0), true>(A, base, width, lane, x)
-                                 : pk_row_sum<EXACT, UU, SMEM, (U >= 100 ? 1 : 0), false>(A, base, width, lane, x);
+                         : nopad ? pk_row_sum<EXACT, UU, SMEM, (U >= 100 ? 1 : 0), true, XW, CD>(A, base, width, lane, x, xw)
+                                 : pk_row_sum<EXACT, UU, SMEM, (U >= 100 ? 1 : 0), false, XW, CD>(A, base, width, lane, x, xw);
         if (row >= 0) {
             const double out = apply_epilogue<EPI>(sum, av, e, beta);
             y[row] = out;
@@ -252,23 +302,39 @@ k_spmv_sell_pk(PkView A, const double* __restrict__ x, double* __restrict__ y, E
     }
 }
 
-template <int EPI, bool EXACT, int U, int MAXT, int MINB, bool SMEM, int DF, bool V6 = false>
+// shared memory of an XW launch: dictionary + the widest window a CTA of this grid can own
+static size_t xw_smem_bytes(const PkView& v, int grid)
+{
+    const long long own = (v.nslices + grid - 1) / grid;
+    return ((size_t)((v.ndict + 2) & ~1) + (size_t)(own + 2 * v.xw_halo) * 32) * sizeof(double);
+}
+
+template <typename K>
+static void allow_smem(K kernel, size_t sh)
+{
+    if (sh > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+}
+
+template <int EPI, bool EXACT, int U, int MAXT, int MINB, bool SMEM, int DF, bool V6 = false, bool XW = false, bool CD = false>
 static void launch_pk_d(const PkView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads, cudaStream_t st)
 {
     if (threads > MAXT) threads = MAXT;
-    const size_t sh = SMEM ? ((size_t)v.ndict + 1) * sizeof(double) : 0;
+    const size_t sh = XW ? xw_smem_bytes(v, grid) : SMEM ? ((size_t)v.ndict + 1) * sizeof(double) : 0;
     if (a.dotv == nullptr) {
-        k_spmv_sell_pk<EPI, EXACT, 0, U, MAXT, MINB, SMEM, 0, V6><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
+        if (XW) allow_smem(k_spmv_sell_pk<EPI, EXACT, 0, U, MAXT, MINB, SMEM, 0, V6, XW, CD>, sh);
+        k_spmv_sell_pk<EPI, EXACT, 0, U, MAXT, MINB, SMEM, 0, V6, XW, CD><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
         return;
     }
     const long long nwarps = (long long)grid * (threads >> 5);
     const double mode = opt("spmv.dotmode", 0.0);
     const bool two_kernels = mode == 2.0 || (mode == 0.0 && grid > (int)kReduceFlat);
     if (two_kernels && nwarps <= kPartialStride) {
-        k_spmv_sell_pk<EPI, EXACT, 2, U, MAXT, MINB, SMEM, DF, V6><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
+        if (XW) allow_smem(k_spmv_sell_pk<EPI, EXACT, 2, U, MAXT, MINB, SMEM, DF, V6, XW, CD>, sh);
+        k_spmv_sell_pk<EPI, EXACT, 2, U, MAXT, MINB, SMEM, DF, V6, XW, CD><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
         sum_warp_partials(nwarps, e, st);
     } else {
-        k_spmv_sell_pk<EPI, EXACT, 1, U, MAXT, MINB, SMEM, DF, V6><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
+        if (XW) allow_smem(k_spmv_sell_pk<EPI, EXACT, 1, U, MAXT, MINB, SMEM, DF, V6, XW, CD>, sh);
+        k_spmv_sell_pk<EPI, EXACT, 1, U, MAXT, MINB, SMEM, DF, V6, XW, CD><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
     }
 }
 
@@ -289,6 +355,7 @@ static void launch_pk_v(const PkView& v, const SpmvArgs& a, const EpiArgs& e, in
 //   0 = U8/<=40 regs, 1 = U8/<=48, 2 = U4/<=32, 3 = U16/<=64, 4 = U16/<=48, 5 = U8/256 threads/<=40,
 //   6 = U12/<=48, 7 = U4/<=40, 8 = U8/CTAs up to 1024 threads/<=64, 9 = U8/<=512 threads/<=40,
 //   10 = U16/<=512 threads/<=64; software-pipelined: 11 = U4/<=40, 12 = U8/<=48, 13 = U6/<=40, 14 = U4/<=512 threads/<=40; 15 = variant 9 with the stream loaded L1::no_allocate
+constexpr int kPkCdictDotVariant = 8;  // measured on C2 inside PCG (profiles/r01_probe_cdict.json): U14, 384-thread CTAs, <= 56 registers
 constexpr int kPkDefaultVariant = 9;   // measured on C2 (profiles/r01_probe_blockorder.json): 512-thread CTAs x 128 slices
 
 template <int EPI, bool EXACT>
@@ -300,6 +367,45 @@ static bool launch_pk(const PkView& v, const SpmvArgs& a, const EpiArgs& e, int 
         return true;
     }
     const bool smem_ok = v.ndict <= kPkDictSmem && opt("spmv.pkdict", 0.0) == 0.0;
+    // x window in shared memory: row-ordered vectors only (the CTA's rows are then a stretch of x), at most
+    // kXwMaxSmem bytes per CTA, and not with the carried x update (it would need the window of xu as well)
+    if (a.row_ordered && smem_ok && a.xu == nullptr && opt("spmv.pk_xwin", 0.0) != 0.0 &&
+        xw_smem_bytes(v, grid) <= kXwMaxSmem) {
+        const int xv = (int)opt("spmv.pk_xwin", 0.0);
+        if (xv == 2) launch_pk_d<EPI, EXACT, 8, 512, 2, true, 2, false, true>(v, a, e, grid, threads, st);
+        else if (xv == 3) launch_pk_d<EPI, EXACT, 8, 1024, 1, true, 2, false, true>(v, a, e, grid, threads, st);
+        else if (xv == 4) launch_pk_d<EPI, EXACT, 4, 512, 3, true, 2, false, true>(v, a, e, grid, threads, st);
+        else if (xv == 5) launch_pk_d<EPI, EXACT, 6, 512, 3, true, 2, false, true>(v, a, e, grid, threads, st);
+        else launch_pk_d<EPI, EXACT, 8, 512, 3, true, 2, false, true>(v, a, e, grid, threads, st);
+        return true;
+    }
+    // dictionary in the parameter block (CD): default geometry only
+    // (measured on C2, profiles/r01_notes.md third part: fused-dot product 1.90 -> 1.73 ms, PCG +6.8 %)
+    // "spmv.pk_cdict" (plain product) / "spmv.pk_cdict_dot" (fused dot): 0 = off, else unroll x CTA size x resident CTAs
+    const int cv = (int)(a.dotv != nullptr ? opt("spmv.pk_cdict_dot", (double)kPkCdictDotVariant) : opt("spmv.pk_cdict", 1.0));
+    if (smem_ok && v.cdict_n > 0 && cv != 0) {
+        if (EPI == EPI_NONE && EXACT) {
+#define DB_CD(U_, T_, B_) launch_pk_d<EPI_NONE, true, U_, T_, B_, false, 2, false, false, true>(v, a, e, grid, threads, st); return true
+            switch (cv) {
+                case 2: DB_CD(16, 512, 2);
+                case 3: DB_CD(10, 512, 3);
+                case 4: DB_CD(8, 256, 6);
+                case 5: DB_CD(16, 1024, 1);
+                case 6: DB_CD(12, 256, 5);
+                case 7: DB_CD(16, 256, 4);
+                case 8: DB_CD(14, 384, 3);
+                case 9: DB_CD(12, 384, 3);
+                case 10: DB_CD(20, 256, 3);
+                case 11: DB_CD(32, 512, 1);
+                case 12: DB_CD(24, 128, 5);
+                case 13: DB_CD(14, 192, 6);
+                default: break;
+            }
+#undef DB_CD
+        }
+        launch_pk_d<EPI, EXACT, 8, 512, 3, false, 2, false, false, true>(v, a, e, grid, threads, st);
+        return true;
+    }
     const int variant = (int)(a.dotv != nullptr ? opt("spmv.pkdotvariant", (double)kPkDefaultVariant)
                                                 : opt("spmv.pkvariant", (double)kPkDefaultVariant));
     if (EPI == EPI_NONE && EXACT && smem_ok) {
@@ -351,7 +457,12 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
     DB_ARG(a.xu == nullptr || (a.dotv != nullptr && a.xu_p && a.xu_alpha && a.xu_iter && a.xu_applied),
            "the carried x update needs the fused dot and its scalars");
     if (A.rows == 0) return 0;
-    int threads = (int)opt("spmv.pk_threads", 512);
+    // the fused-dot product with the dictionary in the parameter block has its own geometry (measured on C2 inside
+    // PCG: 14 words in flight x 384-thread CTAs x 192 slices, 3 CTAs of <= 56 registers per SM)
+    const bool dot_geometry = a.dotv != nullptr && A.pk != nullptr && A.ndict_host > 0 && A.ndict_host == A.ndict &&
+                              A.ndict <= kPkDictSmem && opt("spmv.pkdict", 0.0) == 0.0 &&
+                              opt("spmv.pk_cdict_dot", (double)kPkCdictDotVariant) != 0.0;
+    int threads = dot_geometry ? (int)opt("spmv.pk_dot_threads", 384) : (int)opt("spmv.pk_threads", 512);
     if (threads < 32) threads = 32;
     if (threads > 1024) threads = 1024;
     threads &= ~31;
@@ -360,7 +471,7 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
     long long grid;
     if (per_sm > 0.0) grid = (long long)(per_sm * c.sm_count + 0.5);
     else {
-        long long spc = (long long)opt("spmv.pk_slices_per_cta", 128.0);
+        long long spc = dot_geometry ? (long long)opt("spmv.pk_dot_slices_per_cta", 192.0) : (long long)opt("spmv.pk_slices_per_cta", 128.0);
         if (spc < 1) spc = 1;
         grid = ((long long)A.nslices + spc - 1) / spc;
     }
@@ -376,7 +487,9 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
     if (grid < 1) grid = 1;
     cudaStream_t st = a.stream ? a.stream : c.stream;
     PkView v{A.slice_ptr, A.col, A.pk != nullptr ? nullptr : A.vidx, a.row_ordered ? A.pkp : A.pk, A.dict, a.row_ordered ? nullptr : A.perm, (long long)A.nslices,
-             A.ndict, A.cbits, opt("spmv.pk_nopad", 1.0) != 0.0 ? A.pk_nopad : nullptr};
+             A.ndict, A.cbits, opt("spmv.pk_nopad", 1.0) != 0.0 ? A.pk_nopad : nullptr,
+             std::max(0, (int)opt("spmv.pk_xwin_halo", 0.0)), A.ndict_host == A.ndict ? A.ndict_host : 0, {}};
+    if (v.cdict_n > 0) std::memcpy(v.cdict, A.dict_host, sizeof(double) * ((size_t)A.ndict_host + 1));
     EpiArgs e = make_epi(a);
     e.prefetch = (int)opt("spmv.pk_prefetch", 0.0);        // slices ahead (in units of the CTA's warp count)
     if (opt("spmv.exact", 1.0) != 0.0) launch_pk_epi<true>(v, a, e, (int)grid, threads, st);

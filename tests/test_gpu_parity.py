@@ -93,9 +93,16 @@ def test_spmv_layout_and_launch_options_do_not_change_results(gpu, sigma, thread
         gpu.set_option("spmv.prefetch", 0)
 
 
+CDICT_DOT_DEFAULT = 8 # library default of "spmv.pk_cdict_dot"
+CDICT_DEFAULT = 1     # library default of "spmv.pk_cdict"
+XWIN_DEFAULT = 0      # library default of "spmv.pk_xwin"
+
+
 PK_DEFAULTS = {"spmv.pktma": None, "spmv.pktma_geometry": 0, "spmv.pktma_slices_per_cta": None, "spmv.pk": 1, "spmv.pkdotform": 2, "pcg.reorder": 1, "pcg.defer_x": 1, "pcg.fused_dot": 1, "pcg.fuse_x": 0, "spmv.pk_threads": 512,
                "spmv.pk_slices_per_cta": 128, "spmv.pkvariant": 9, "spmv.pkdotvariant": 9, "spmv.pkdict": 0, "spmv.dotmode": 0, "sell.sigma": 4096,
-               "sell.valdict": 1, "spmv.exact": 1}
+               "sell.valdict": 1, "spmv.exact": 1, "spmv.pk_xwin": XWIN_DEFAULT, "spmv.pk_xwin_halo": 0,
+               "spmv.pk_cdict": CDICT_DEFAULT, "spmv.pk_cdict_dot": CDICT_DOT_DEFAULT,
+               "spmv.pk_dot_threads": 384, "spmv.pk_dot_slices_per_cta": 192}
 
 
 PKTMA_DEFAULT = 0     # library default of "spmv.pktma"
@@ -205,6 +212,8 @@ def test_value_dictionary_stream_is_bit_identical(gpu, variant, threads, spc, di
         gpu.set_option("spmv.pkdotvariant", variant)
         gpu.set_option("spmv.pk_threads", threads)
         gpu.set_option("spmv.pk_slices_per_cta", spc)
+        gpu.set_option("spmv.pk_dot_threads", threads)
+        gpu.set_option("spmv.pk_dot_slices_per_cta", spc)
         gpu.set_option("spmv.pkdict", dictmode)
         gpu.set_option("spmv.dotmode", dotmode)
         gpu.set_option("spmv.pkdotform", variant % 3)
@@ -270,6 +279,89 @@ def test_pcg_forms_agree_with_reference(gpu, reorder, defer_x, fused_dot, graph,
             assert out[0] and out[1] == ref[1] and rel(out[3], ref[3]) <= 1e-12 and rel(out[3], xs) <= 1e-8
     finally:
         gpu.set_option("pcg.check_every", 16)
+        gpu.set_option("pcg.graph", 1)
+        _restore_pk(gpu)
+
+
+@pytest.mark.parametrize("xwin,halo,threads,spc,tile,graph", [(1, 0, 512, 128, 8, 1), (2, 1, 64, 2, 2, 0), (3, 3, 1024, 256, 8, 1),
+                                                               (4, 0, 32, 1, 1, 0), (5, 7, 96, 5, 3, 1), (1, 100000, 128, 16, 8, 0)])
+def test_x_window_in_shared_memory_keeps_every_bit(gpu, xwin, halo, threads, spc, tile, graph):
+    """"spmv.pk_xwin": the row-ordered packed product gathers the x entries of the CTA's own stretch of rows
+    (+ halo slices) from shared memory and the others through L1.  Same operands, same order: the PCG iterates,
+    residuals and iteration counts are the bits of the solve without the window, for every CTA geometry
+    (windows of one slice, windows larger than the vector, windows cut at both ends)."""
+    g = load_golden("brick_fe2_N6_num1.npz")
+    n, rb, ci, va = gpu.brick_csr_host(2, 12, 1)
+    xs = gpu.brick_solution_host(2, 12, 1)
+    try:
+        gpu.set_option("sell.block_order", 1)
+        gpu.set_option("sell.block_min_rows", 0)
+        gpu.set_option("sell.block_tile", tile)
+        gpu.set_option("pcg.graph", graph)
+        gpu.set_option("spmv.pk_threads", threads)
+        gpu.set_option("spmv.pk_slices_per_cta", spc)
+        gpu.set_option("spmv.pk_dot_threads", threads)
+        gpu.set_option("spmv.pk_dot_slices_per_cta", spc)
+        B = gpu.Matrix(n, n, rb, ci, va)
+        assert B.layout()["row_ordered_stream"]
+        b = B.spmv(xs)
+        A = gmat(gpu, g)
+        res = {}
+        for w in (0, xwin):
+            gpu.set_option("spmv.pk_xwin", w)
+            gpu.set_option("spmv.pk_xwin_halo", halo if w else 0)
+            res[w] = (B.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True), B.pcg_jacobi(np.zeros(n), b, 9, 1e-30, True),
+                      A.pcg_jacobi(np.zeros(A.rows), g["b"], 400, 1e-10, True))
+        for r0, r1 in zip(res[0], res[xwin]):
+            assert r0[0] == r1[0] and r0[1] == r1[1] and r0[2] == r1[2] and np.array_equal(r0[3], r1[3])
+        assert res[xwin][2][1] == int(g["sym_pcgjac"][1]) and rel(res[xwin][2][3], g["sym_pcgjac_x"]) <= 1e-12
+        assert res[xwin][0][0] and rel(res[xwin][0][3], xs) <= 1e-8
+    finally:
+        gpu.set_option("sell.block_order", 1)
+        gpu.set_option("sell.block_min_rows", 2.0e6)
+        gpu.set_option("sell.block_tile", 8)
+        gpu.set_option("pcg.graph", 1)
+        _restore_pk(gpu)
+
+
+@pytest.mark.parametrize("threads,spc,dotmode,graph", [(512, 128, 0, 1), (64, 3, 1, 0), (1024, 1000000, 2, 1)])
+def test_dictionary_in_the_parameter_block_keeps_every_bit(gpu, threads, spc, dotmode, graph):
+    """"spmv.pk_cdict": dictionaries of <= 47 values ride in the kernel's parameter block and a_ij comes from an
+    indexed constant load instead of shared memory.  Same values, same order: products, transposed products,
+    fused dots and whole solves keep their bits; matrices with more values stay on the shared-memory path."""
+    g = load_golden("brick_fe2_N6_num1.npz")
+    r = load_golden("random_ragged.npz")
+    n, rb, ci, va = gpu.brick_csr_host(2, 12, 1)
+    xin = hash_vector(n)
+    xs = gpu.brick_solution_host(2, 12, 1)
+    try:
+        gpu.set_option("sell.block_min_rows", 0)
+        gpu.set_option("pcg.graph", graph)
+        gpu.set_option("spmv.pk_threads", threads)
+        gpu.set_option("spmv.pk_slices_per_cta", spc)
+        gpu.set_option("spmv.pk_dot_threads", threads)
+        gpu.set_option("spmv.pk_dot_slices_per_cta", spc)
+        gpu.set_option("spmv.dotmode", dotmode)
+        B = gpu.Matrix(n, n, rb, ci, va)
+        assert B.value_dictionary()["packed"] and B.value_dictionary()["n_distinct"] <= 47
+        b = B.spmv(xs)
+        X, Y = gpu.Vector.from_host(xin), gpu.Vector(n)
+        A, R = gmat(gpu, g), gmat(gpu, r)
+        res = {}
+        for cd in range(14):
+            gpu.set_option("spmv.pk_cdict", cd)
+            gpu.set_option("spmv.pk_cdict_dot", cd)
+            d = B.spmv_dot_dev(X, Y, X)
+            res[cd] = (B.spmv(xin), B.spmv_transpose(xin), np.float64(d), Y.download(),
+                       B.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True)[3], np.float64(B.pcg_jacobi(np.zeros(n), b, 9, 1e-30, True)[2]),
+                       B.gmres_jacobi(np.zeros(n), b, 20, 300, 1e-10, True, 1.0, True)[3],
+                       A.spmv(g["x_in"]), A.spmv_transpose(g["x_in"]), R.spmv(r["x_in"]))
+        for cd in range(1, 14):
+            for u, v in zip(res[0], res[cd]):
+                assert np.array_equal(u, v)
+        assert np.array_equal(res[1][7], g["y_Ax"]) and np.array_equal(res[1][8], g["y_ATx"]) and np.array_equal(res[1][9], r["y_Ax"])
+    finally:
+        gpu.set_option("sell.block_min_rows", 2.0e6)
         gpu.set_option("pcg.graph", 1)
         _restore_pk(gpu)
 
@@ -359,6 +451,8 @@ def test_value_dictionary_six_byte_form_is_bit_identical(gpu, dictmode, dotmode,
         gpu.set_option("sell.sigma", sigma)
         gpu.set_option("spmv.pk_threads", threads)
         gpu.set_option("spmv.pk_slices_per_cta", spc)
+        gpu.set_option("spmv.pk_dot_threads", threads)
+        gpu.set_option("spmv.pk_dot_slices_per_cta", spc)
         A = gmat(gpu, g)
         d = A.value_dictionary()
         assert d["six_byte"] and not d["packed"] and not A.layout()["row_ordered_stream"]
