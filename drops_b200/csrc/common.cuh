@@ -396,7 +396,7 @@ void free_sell(SellOp& s);
 void free_csr(CsrDev& c);
 int build_transpose(drops_b200_matrix_s* M);
 int build_sell(const CsrDev& A, SellOp& S, size_t* bytes, const int32_t* rowmap, size_t nsub,
-               bool rowmap_is_permutation = false);
+               bool rowmap_is_permutation = false, bool type_sort = false);
 // block order of the rows of a square operator from its graph (reorder.cu); *d_order = nullptr: keep the caller's order
 int compute_block_order(const CsrDev& A, int32_t** d_order);
 // one pass over the values: will this operator get the one-word packed stream (and with it the row-ordered twin)?

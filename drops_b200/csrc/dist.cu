@@ -483,6 +483,7 @@ int dist_matrix_build(drops_b200_comm_s* comm, drops_b200_exchange_s* E, size_t 
     DM_CHECK(dev_alloc(&rows_all, n)); DM_CHECK(dev_alloc(&rows_int, n)); DM_CHECK(dev_alloc(&rows_bnd, n));
     DM_CHECK(dev_alloc(&d_cnt, 2));
     long long cnt[2] = {0, 0};
+    bool packs = false;
     if (n > 0) {
         // rows in blocks of the partition's own graph (reorder.cu) when it is large enough to profit
         int32_t* order = nullptr;
@@ -490,7 +491,7 @@ int dist_matrix_build(drops_b200_comm_s* comm, drops_b200_exchange_s* E, size_t 
             CsrDev L;
             L.rows = n; L.cols = n + ng; L.nnz = nnz;
             L.rowptr = const_cast<int64_t*>(d_rowptr); L.col = col; L.val = const_cast<double*>(d_val);
-            bool packs = false;          // graph blocks only pay together with the row-ordered twins
+            packs = false;               // graph blocks only pay together with the row-ordered twins
             DM_CHECK(will_pack_one_word(d_val, nnz, n + ng + 2 * 4096 + 64, &packs));
             if (packs && opt("dist.reorder", 1.0) != 0.0) DM_CHECK(compute_block_order(L, &order));
         }
@@ -532,7 +533,7 @@ int dist_matrix_build(drops_b200_comm_s* comm, drops_b200_exchange_s* E, size_t 
         // positions of a partition run up to (windows of the interior + windows of the boundary operator)
         CsrDev Ai = A;
         Ai.cols = n + ng + 2 * 4096 + 64;
-        DM_CHECK(build_sell(Ai, M->sell_int, &M->device_bytes, rows_int, M->n_int));
+        DM_CHECK(build_sell(Ai, M->sell_int, &M->device_bytes, rows_int, M->n_int, false, packs));
         M->sell_int.cols = A.cols;
     }
     DM_CHECK(build_sell(A, M->sell_bnd, &M->device_bytes, rows_bnd, M->n_bnd));

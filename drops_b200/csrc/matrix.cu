@@ -35,12 +35,18 @@ __global__ void k_extract_diag(long long rows, const int64_t* __restrict__ rowpt
     else { diag[i] = 0.0; atomicExch(missing, 1); }
 }
 
-// One CTA sorts one window of SIGMA rows by (length descending, row ascending) with a bitonic
-// network in shared memory and emits perm + per-slice widths (in stored entries, i.e. width*32).
+// One CTA sorts one window of SIGMA rows by (length descending, [stencil type,] row ascending) with a
+// bitonic network in shared memory and emits perm + per-slice widths (in stored entries, i.e. width*32).
+// type_val != nullptr ("sell.type_sort", operators that get the packed stream): rows of one length are
+// grouped by a 20-bit hash of their value sequence.  On a constant-coefficient mesh operator that is the
+// stencil class (x-, y-, z-edge ... rows), so the 32 rows of a slice hold the same stencil: their j-th
+// columns are one run of the row-ordered x (fewer 128-byte lines per gather) and their j-th dictionary
+// index is one address.  Any order inside a window is valid; colliding hashes only merge two groups.
+// Measured on C2 (profiles/r01_probe_type.json): no gain (fused-dot product 1.474 -> 1.492 ms), off by default.
 template <int SIGMA>
 __global__ void __launch_bounds__(1024)
 k_sell_sort(long long rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ rowmap,
-            int32_t* __restrict__ perm, int64_t* __restrict__ slice_entries)
+            int32_t* __restrict__ perm, int64_t* __restrict__ slice_entries, const double* __restrict__ type_val)
 {
     // rows = number of rows of the operator; rowmap (optional) = the CSR row behind each of them
     __shared__ unsigned long long key[SIGMA];
@@ -51,7 +57,17 @@ k_sell_sort(long long rows, const int64_t* __restrict__ rowptr, const int32_t* _
             const long long ra = rowmap ? rowmap[r] : r;
             const unsigned long long len = (unsigned long long)(rowptr[ra + 1] - rowptr[ra]);
             const unsigned long long inv = 0x7fffffffULL - (len > 0x7fffffffULL ? 0x7fffffffULL : len);
-            key[t] = (inv << 32) | (unsigned long long)(unsigned)t;
+            unsigned long long type = 0;
+            if (type_val != nullptr) {
+                unsigned h = 2166136261u;
+                for (int64_t k = rowptr[ra]; k < rowptr[ra + 1]; ++k) {
+                    const unsigned long long bits = (unsigned long long)__double_as_longlong(__ldg(type_val + k));
+                    h = (h ^ (unsigned)bits) * 16777619u;
+                    h = (h ^ (unsigned)(bits >> 32)) * 16777619u;
+                }
+                type = (h ^ (h >> 20)) & 0xfffffu;
+            }
+            key[t] = (inv << 32) | (type << 12) | (unsigned long long)(unsigned)t;      // t < SIGMA <= 4096
         } else {
             key[t] = ~0ULL;
         }
@@ -73,7 +89,7 @@ k_sell_sort(long long rows, const int64_t* __restrict__ rowptr, const int32_t* _
     for (int t = threadIdx.x; t < SIGMA; t += blockDim.x) {
         const unsigned long long kk = key[t];
         const bool pad = (kk == ~0ULL);
-        const long long r = w0 + (long long)(kk & 0xffffffffULL);
+        const long long r = w0 + (long long)(kk & 0xfffULL);
         perm[w0 + t] = pad ? -1 : (rowmap ? rowmap[r] : (int32_t)r);
         if ((t & 31) == 0) {
             const long long len = pad ? 0 : (long long)(0x7fffffffULL - (kk >> 32));
@@ -369,7 +385,8 @@ void free_csr(CsrDev& c)
 // Builds the sliced-ELL operator of all rows of A (rowmap == nullptr) or of the `nsub` rows
 // listed in rowmap (device array, ascending); perm then holds rows of A, so y, aux and the
 // fused dot are addressed by the full row index.
-int build_sell(const CsrDev& A, SellOp& S, size_t* bytes, const int32_t* rowmap, size_t nsub, bool rowmap_is_permutation)
+int build_sell(const CsrDev& A, SellOp& S, size_t* bytes, const int32_t* rowmap, size_t nsub, bool rowmap_is_permutation,
+               bool type_sort)
 {
     Ctx& c = ctx();
     cudaStream_t st = c.stream;
@@ -395,14 +412,15 @@ int build_sell(const CsrDev& A, SellOp& S, size_t* bytes, const int32_t* rowmap,
             k_sell_identity<<<blocks_for(padded_rows, 256), 256, 0, st>>>((long long)op_rows, (long long)padded_rows, A.rowptr, rowmap, S.perm, S.slice_ptr);
         } else {
             const int g = (int)nwin;
+            const double* tv = (type_sort && opt("sell.type_sort", 0.0) != 0.0) ? A.val : nullptr;
             switch (sigma) {
-                case 4096: k_sell_sort<4096><<<g, 1024, 0, st>>>((long long)op_rows, A.rowptr, rowmap, S.perm, S.slice_ptr); break;
-                case 2048: k_sell_sort<2048><<<g, 1024, 0, st>>>((long long)op_rows, A.rowptr, rowmap, S.perm, S.slice_ptr); break;
-                case 1024: k_sell_sort<1024><<<g, 512, 0, st>>>((long long)op_rows, A.rowptr, rowmap, S.perm, S.slice_ptr); break;
-                case 512:  k_sell_sort<512><<<g, 256, 0, st>>>((long long)op_rows, A.rowptr, rowmap, S.perm, S.slice_ptr); break;
-                case 256:  k_sell_sort<256><<<g, 128, 0, st>>>((long long)op_rows, A.rowptr, rowmap, S.perm, S.slice_ptr); break;
-                case 128:  k_sell_sort<128><<<g, 64, 0, st>>>((long long)op_rows, A.rowptr, rowmap, S.perm, S.slice_ptr); break;
-                default:   k_sell_sort<64><<<g, 32, 0, st>>>((long long)op_rows, A.rowptr, rowmap, S.perm, S.slice_ptr); break;
+                case 4096: k_sell_sort<4096><<<g, 1024, 0, st>>>((long long)op_rows, A.rowptr, rowmap, S.perm, S.slice_ptr, tv); break;
+                case 2048: k_sell_sort<2048><<<g, 1024, 0, st>>>((long long)op_rows, A.rowptr, rowmap, S.perm, S.slice_ptr, tv); break;
+                case 1024: k_sell_sort<1024><<<g, 512, 0, st>>>((long long)op_rows, A.rowptr, rowmap, S.perm, S.slice_ptr, tv); break;
+                case 512:  k_sell_sort<512><<<g, 256, 0, st>>>((long long)op_rows, A.rowptr, rowmap, S.perm, S.slice_ptr, tv); break;
+                case 256:  k_sell_sort<256><<<g, 128, 0, st>>>((long long)op_rows, A.rowptr, rowmap, S.perm, S.slice_ptr, tv); break;
+                case 128:  k_sell_sort<128><<<g, 64, 0, st>>>((long long)op_rows, A.rowptr, rowmap, S.perm, S.slice_ptr, tv); break;
+                default:   k_sell_sort<64><<<g, 32, 0, st>>>((long long)op_rows, A.rowptr, rowmap, S.perm, S.slice_ptr, tv); break;
             }
         }
         count_launch();
@@ -761,7 +779,7 @@ int finalize_matrix(drops_b200_matrix_s* M)
     bool packs = false;
     DB_CHECK(will_pack_one_word(M->csr.val, M->csr.nnz, std::max(M->csr.cols, M->csr.rows + 4096), &packs));
     if (packs && M->square && opt("sell.reorder", 1.0) != 0.0) DB_CHECK(compute_block_order(M->csr, &order));
-    const int s = build_sell(M->csr, M->sell, &M->device_bytes, order, order ? M->csr.rows : 0, order != nullptr);
+    const int s = build_sell(M->csr, M->sell, &M->device_bytes, order, order ? M->csr.rows : 0, order != nullptr, packs);
     dev_free(order);
     M->block_ordered = s == 0 && order != nullptr;
     return s;
