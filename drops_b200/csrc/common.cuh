@@ -367,6 +367,11 @@ struct drops_b200_matrix_s {
     double* bridge[2] = {nullptr, nullptr};   // device copies of host x / b (host-buffer entry points)
     std::vector<double*> ro_work;    // vectors in the row-ordered numbering (sell.npos doubles)
     uint64_t ro_diag_epoch = 0;      // values epoch ro_work[0] (the permuted diagonal) was gathered at
+    // the permuted diagonal as one byte per position + its distinct values, when there are at most kDiagDict
+    // of them (constant-coefficient operators): the PCG vector kernels read 1 instead of 8 bytes of d ("pcg.diag_index")
+    uint8_t* ro_diag_idx = nullptr;
+    int ro_diag_count = 0;
+    double ro_diag_values[32] = {};
     void* d_scalars = nullptr;       // db200::SolverScalars
     double* d_hist = nullptr;
     int hist_alloc = 0;
@@ -399,6 +404,8 @@ int build_sell(const CsrDev& A, SellOp& S, size_t* bytes, const int32_t* rowmap,
                bool rowmap_is_permutation = false, bool type_sort = false);
 // block order of the rows of a square operator from its graph (reorder.cu); *d_order = nullptr: keep the caller's order
 int compute_block_order(const CsrDev& A, int32_t** d_order);
+// a vector of <= max_values distinct bit patterns as one byte per entry + the sorted value list (matrix.cu)
+int build_value_index8(const double* d_val, size_t n, int max_values, uint8_t** d_idx, double* host_values, int* count);
 // one pass over the values: will this operator get the one-word packed stream (and with it the row-ordered twin)?
 int will_pack_one_word(const double* d_val, size_t nnz, size_t cols_and_positions, bool* yes);
 // (re)builds S.dict / S.pk from S.col / S.val; leaves them null when the matrix does not qualify

@@ -89,6 +89,10 @@ int pcg_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, doubl
         double* dp = M->ro_work[0]; double* xp = M->ro_work[1]; double* bp = M->ro_work[2];
         if (M->ro_diag_epoch != M->values_epoch) {
             DB_CHECK(vec_gather_perm(npos, M->sell.perm, M->diag, dp, 1.0));
+            // constant-coefficient operators: a handful of distinct diagonal values -> one byte per position
+            dev_free(M->ro_diag_idx); M->ro_diag_idx = nullptr; M->ro_diag_count = 0;
+            if (pc == DROPS_B200_PC_JACOBI && M->sell.ndict_host > 0)
+                DB_CHECK(build_value_index8(dp, npos, kDiagDict, &M->ro_diag_idx, M->ro_diag_values, &M->ro_diag_count));
             M->ro_diag_epoch = M->values_epoch;
         }
         DB_CHECK(vec_gather_perm(npos, M->sell.perm, x, xp, 0.0));
@@ -96,6 +100,13 @@ int pcg_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, doubl
         x = xp; b = bp; diag = dp;
     }
     const size_t nv = ro ? M->sell.npos : n;      // length of the vectors the iteration works on
+    DiagIndex dix;
+    const bool use_dix = ro && M->ro_diag_idx != nullptr && M->ro_diag_count > 0 && opt("pcg.diag_index", 1.0) != 0.0;
+    if (use_dix) {
+        dix.idx = M->ro_diag_idx;
+        std::memcpy(dix.dict.v, M->ro_diag_values, sizeof(double) * (size_t)M->ro_diag_count);
+    }
+    const DiagIndex* di = use_dix ? &dix : nullptr;
     double* r = ro ? M->ro_work[3] : work_vec(M, 0);
     double* p = ro ? M->ro_work[4] : work_vec(M, 1);
     double* q = ro ? M->ro_work[5] : work_vec(M, 2);
@@ -168,8 +179,8 @@ int pcg_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, doubl
         DB_CHECK(spmv_apply(M, false, s));
         if (!fused_dot) DB_CHECK(vec_dot_unless(nv, q, p, &S->lambda, &S->done));
         if (defer_x) {
-            DB_CHECK(pcg_update_r(nv, r, q, diag, S, dh));
-            DB_CHECK(pcg_direction_x(nv, x, p, r, diag, S));
+            DB_CHECK(pcg_update_r(nv, r, q, diag, S, dh, nullptr, di));
+            DB_CHECK(pcg_direction_x(nv, x, p, r, diag, S, di));
             return 0;
         }
         DB_CHECK(unpreconditioned_cg ? cg_update(n, x, r, p, q, S, dh) : pcg_update(nv, x, r, p, q, diag, S, dh));

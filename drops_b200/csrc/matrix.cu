@@ -485,6 +485,77 @@ k_dict_index16(long long n, const int32_t* __restrict__ col, const double* __res
     vidx[i] = (uint16_t)lo;
 }
 
+// idx = index of val in the sorted list of distinct values (8 bit)
+__global__ void __launch_bounds__(256)
+k_value_index8(long long n, const double* __restrict__ val, const unsigned long long* __restrict__ keys, int nkeys,
+               uint8_t* __restrict__ idx)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long key = (unsigned long long)__double_as_longlong(__ldcs(val + i));
+    int lo = 0, hi = nkeys;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(keys + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    idx[i] = (uint8_t)lo;
+}
+
+// A vector with at most max_values (<= 256) distinct bit patterns as one byte per entry + the list of values
+// (host_values, sorted by bit pattern).  *count = 0 and *d_idx = nullptr when the vector holds more.
+// Used for the Jacobi diagonal of constant-coefficient operators (krylov.cu): the PCG vector kernels then
+// read 1 instead of 8 bytes per entry of d.
+int build_value_index8(const double* d_val, size_t n, int max_values, uint8_t** d_idx, double* host_values, int* count)
+{
+    *d_idx = nullptr; *count = 0;
+    if (n == 0 || max_values < 1) return 0;
+    if (max_values > 256) max_values = 256;
+    cudaStream_t st = ctx().stream;
+    unsigned long long* table = nullptr; int* d_count = nullptr;
+    const size_t cap = (size_t)1 << kDictTableBits;
+    DB_CHECK(dev_alloc(&table, cap));
+    if (dev_alloc(&d_count, 1) < 0) { dev_free(table); return DROPS_B200_E_NOMEM; }
+    int status = 0, cnt = 0;
+    cudaError_t e = cudaMemsetAsync(table, 0xff, cap * sizeof(unsigned long long), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_count, 0, sizeof(int), st);
+    if (e == cudaSuccess) {
+        const int grid = (int)std::min<long long>(((long long)n + 255) / 256, (long long)ctx().sm_count * 16);
+        k_dict_collect<<<grid, 256, 0, st>>>((long long)n, nullptr, d_val, table, d_count);
+        count_launch();
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&cnt, d_count, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && cnt >= 1 && cnt <= max_values) {
+        std::vector<unsigned long long> host(cap), keys;
+        e = cudaMemcpyAsync(host.data(), table, cap * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) {
+            for (unsigned long long k : host) if (k != kDictEmpty) keys.push_back(k);
+            std::sort(keys.begin(), keys.end());
+            if ((int)keys.size() != cnt) { set_error("value index: %zu keys in the table, %d counted", keys.size(), cnt); status = DROPS_B200_E_CUDA; }
+        }
+        if (e == cudaSuccess && status == 0) {
+            e = cudaMemcpyAsync(table, keys.data(), keys.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) status = dev_alloc(d_idx, n);
+            if (e == cudaSuccess && status == 0) {
+                k_value_index8<<<blocks_for((long long)n, 256), 256, 0, st>>>((long long)n, d_val, table, cnt, *d_idx);
+                count_launch();
+                e = cudaGetLastError();
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            }
+            if (e == cudaSuccess && status == 0) {
+                std::memcpy(host_values, keys.data(), keys.size() * sizeof(double));
+                *count = cnt;
+            }
+        }
+    }
+    dev_free(table); dev_free(d_count);
+    if (e != cudaSuccess) status = cuda_fail(e, "value index", __FILE__, __LINE__);
+    if (status != 0) { dev_free(*d_idx); *d_idx = nullptr; *count = 0; }
+    return status;
+}
+
 // one warp per slice: does the slice hold a padding word?  (rows are sorted by length inside a window, so
 // only the last entry-row can differ between the lanes; slices of padding rows are all padding)
 __global__ void k_slice_nopad(long long nslices, const int64_t* __restrict__ slice_ptr, const uint32_t* __restrict__ pk,
@@ -981,6 +1052,7 @@ int drops_b200_matrix_destroy(drops_b200_matrix_t M)
     dev_free(M->diag); dev_free(M->diag_missing); dev_free(M->bbt_diag);
     for (double* w : M->work) dev_free(w);
     for (double* w : M->ro_work) dev_free(w);
+    dev_free(M->ro_diag_idx);
     dev_free(M->bridge[0]); dev_free(M->bridge[1]);
     dev_free(M->d_scalars); dev_free(M->d_hist); dev_free(M->d_small);
     if (M->pcg_graph) cudaGraphExecDestroy(M->pcg_graph);

@@ -435,10 +435,23 @@ struct OpPcgUpdateR {
     }
 };
 
-template <int STEP>
+// d_i of the element pair i: from the vector, or (DIDX) from the byte index + the dictionary in the parameter block
+template <bool DIDX>
+__device__ __forceinline__ double2 load_diag2(const double2* __restrict__ d2, const uint8_t* __restrict__ didx,
+                                              const DiagDict& dict, size_t i)
+{
+    if (DIDX) {
+        const uchar2 k = __ldg(reinterpret_cast<const uchar2*>(didx) + i);
+        return make_double2(dict.v[k.x], dict.v[k.y]);
+    }
+    return d2[i];
+}
+
+template <int STEP, bool DIDX>
 __global__ void __launch_bounds__(kReduceThreads)
 k_pcg_update_r(size_t n, double* __restrict__ r, const double* __restrict__ q, const double* __restrict__ d,
-               SolverScalars* S, double* hist, dd* part_out, dd* partials, unsigned* ticket)
+               SolverScalars* S, double* hist, dd* part_out, dd* partials, unsigned* ticket,
+               const uint8_t* __restrict__ didx, const __grid_constant__ DiagDict dict)
 {
     __shared__ dd red_smem[2 * 32];
     OpPcgUpdateR op{r, q, d, S, hist, part_out, 0.0, 0, 1.0};
@@ -466,9 +479,9 @@ k_pcg_update_r(size_t n, double* __restrict__ r, const double* __restrict__ q, c
         const size_t j = i + stride;
         const bool two = STEP == 2 && j < n2;
         const double2 rv0 = r2[i], qv0 = __ldcs(q2 + i);            // q is dead after this kernel
-        const double2 dv0 = jac ? d2[i] : one2;
+        const double2 dv0 = jac ? load_diag2<DIDX>(d2, didx, dict, i) : one2;
         double2 rv1 = one2, qv1 = one2, dv1 = one2;
-        if (two) { rv1 = r2[j]; qv1 = __ldcs(q2 + j); dv1 = jac ? d2[j] : one2; }
+        if (two) { rv1 = r2[j]; qv1 = __ldcs(q2 + j); dv1 = jac ? load_diag2<DIDX>(d2, didx, dict, j) : one2; }
         body(i, rv0, qv0, dv0);
         if (two) body(j, rv1, qv1, dv1);
     }
@@ -478,18 +491,32 @@ k_pcg_update_r(size_t n, double* __restrict__ r, const double* __restrict__ q, c
     }
 }
 
-int pcg_update_r(size_t n, double* r, const double* q, const double* d, SolverScalars* S, double* hist, dd* part_out)
+int pcg_update_r(size_t n, double* r, const double* q, const double* d, SolverScalars* S, double* hist, dd* part_out,
+                 const DiagIndex* di)
 {
+    if (di != nullptr && di->idx != nullptr && (n & 1) == 0 && opt("vec.wide", 1.0) != 0.0 && aligned16(r, q, d)) {
+        Ctx& c = ctx();
+        ScopedTiming t("pcg.update");
+        const int grid = vec_grid(n, kReduceThreads, 4);
+        if (opt("vec.unroll2_update", 0.0) != 0.0)
+            k_pcg_update_r<2, true><<<grid, kReduceThreads, 0, c.stream>>>(n, r, q, d, S, hist, part_out, c.partials, c.tickets, di->idx, di->dict);
+        else
+            k_pcg_update_r<1, true><<<grid, kReduceThreads, 0, c.stream>>>(n, r, q, d, S, hist, part_out, c.partials, c.tickets, di->idx, di->dict);
+        count_launch();
+        DB_CUDA(cudaGetLastError());
+        return 0;
+    }
     if (opt("vec.wide", 1.0) != 0.0 && aligned16(r, q, d)) {
         Ctx& c = ctx();
         ScopedTiming t("pcg.update");
         const int grid = vec_grid(n, kReduceThreads, 4);
+        static const DiagDict no_dict = {};
         // measured on C2: two elements per trip help the direction kernel (0.375 -> 0.362 ms) and hurt this
         // one (0.282 -> 0.306 ms: 74 registers), so the default differs ("vec.unroll2_update")
         if (opt("vec.unroll2_update", 0.0) != 0.0)
-            k_pcg_update_r<2><<<grid, kReduceThreads, 0, c.stream>>>(n, r, q, d, S, hist, part_out, c.partials, c.tickets);
+            k_pcg_update_r<2, false><<<grid, kReduceThreads, 0, c.stream>>>(n, r, q, d, S, hist, part_out, c.partials, c.tickets, nullptr, no_dict);
         else
-            k_pcg_update_r<1><<<grid, kReduceThreads, 0, c.stream>>>(n, r, q, d, S, hist, part_out, c.partials, c.tickets);
+            k_pcg_update_r<1, false><<<grid, kReduceThreads, 0, c.stream>>>(n, r, q, d, S, hist, part_out, c.partials, c.tickets, nullptr, no_dict);
         count_launch();
         DB_CUDA(cudaGetLastError());
         return 0;
@@ -502,10 +529,11 @@ int pcg_update_r(size_t n, double* r, const double* q, const double* d, SolverSc
 // pcg_update_finish the iteration's rho sits in rho_1, so alpha = rho_1 / lambda is the quotient the
 // update kernel used (:152).  The block that finishes last marks the x update as applied; kernels of
 // iterations that are skipped after the stop see x_iter == iter and do nothing.
-template <int STEP>
+template <int STEP, bool DIDX>
 __global__ void __launch_bounds__(kReduceThreads)
 k_pcg_direction_x(size_t n, double* __restrict__ x, double* __restrict__ p, const double* __restrict__ r,
-                  const double* __restrict__ d, SolverScalars* S, unsigned* ticket)
+                  const double* __restrict__ d, SolverScalars* S, unsigned* ticket,
+                  const uint8_t* __restrict__ didx, const __grid_constant__ DiagDict dict)
 {
     const int it = S->iter;
     if (S->x_iter == it) return;
@@ -535,9 +563,9 @@ k_pcg_direction_x(size_t n, double* __restrict__ x, double* __restrict__ p, cons
         const size_t j = i + stride;
         const bool two = STEP == 2 && j < n2;
         const double2 xv0 = x2[i], pv0 = p2[i];
-        const double2 rv0 = more ? r2[i] : one2, dv0 = (more && jac) ? d2[i] : one2;
+        const double2 rv0 = more ? r2[i] : one2, dv0 = (more && jac) ? load_diag2<DIDX>(d2, didx, dict, i) : one2;
         double2 xv1 = one2, pv1 = one2, rv1 = one2, dv1 = one2;
-        if (two) { xv1 = x2[j]; pv1 = p2[j]; if (more) { rv1 = r2[j]; if (jac) dv1 = d2[j]; } }
+        if (two) { xv1 = x2[j]; pv1 = p2[j]; if (more) { rv1 = r2[j]; if (jac) dv1 = load_diag2<DIDX>(d2, didx, dict, j); } }
         body(i, xv0, pv0, rv0, dv0);
         if (two) body(j, xv1, pv1, rv1, dv1);
     }
@@ -554,16 +582,22 @@ k_pcg_direction_x(size_t n, double* __restrict__ x, double* __restrict__ p, cons
     }
 }
 
-int pcg_direction_x(size_t n, double* x, double* p, const double* r, const double* d, SolverScalars* S)
+int pcg_direction_x(size_t n, double* x, double* p, const double* r, const double* d, SolverScalars* S, const DiagIndex* di)
 {
     Ctx& c = ctx();
     DB_ARG(aligned16(x, p, r, d), "pcg_direction_x needs 16-byte aligned vectors");
     ScopedTiming t("pcg.direction");
     const int grid = vec_grid(n, kReduceThreads, 4);
-    if (opt("vec.unroll2", 1.0) != 0.0)
-        k_pcg_direction_x<2><<<grid, kReduceThreads, 0, c.stream>>>(n, x, p, r, d, S, c.tickets + (size_t)2 * kTicketStride);
+    unsigned* ticket = c.tickets + (size_t)2 * kTicketStride;
+    static const DiagDict no_dict = {};
+    const bool two = opt("vec.unroll2", 1.0) != 0.0;
+    if (di != nullptr && di->idx != nullptr && (n & 1) == 0) {
+        if (two) k_pcg_direction_x<2, true><<<grid, kReduceThreads, 0, c.stream>>>(n, x, p, r, d, S, ticket, di->idx, di->dict);
+        else k_pcg_direction_x<1, true><<<grid, kReduceThreads, 0, c.stream>>>(n, x, p, r, d, S, ticket, di->idx, di->dict);
+    } else if (two)
+        k_pcg_direction_x<2, false><<<grid, kReduceThreads, 0, c.stream>>>(n, x, p, r, d, S, ticket, nullptr, no_dict);
     else
-        k_pcg_direction_x<1><<<grid, kReduceThreads, 0, c.stream>>>(n, x, p, r, d, S, c.tickets + (size_t)2 * kTicketStride);
+        k_pcg_direction_x<1, false><<<grid, kReduceThreads, 0, c.stream>>>(n, x, p, r, d, S, ticket, nullptr, no_dict);
     count_launch();
     DB_CUDA(cudaGetLastError());
     return 0;

@@ -77,9 +77,15 @@ int pcg_direction(size_t n, double* p, const double* r, const double* d, SolverS
 // 11 vector passes: p is read once): pcg_update_r does r -= alpha q, z, the two reductions and the
 // scalar bookkeeping; pcg_direction_x does x += alpha p for the iteration that just ran (also when it
 // was the last one) and then p = z + beta p unless the solve is done.  Element arithmetic unchanged.
+// di (optional): d as one byte per entry + its distinct values (the values travel in the kernels' parameter
+// block); d_i = di->dict.v[di->idx[i]] has the bits of d[i], and 1 instead of 8 bytes per entry are read.
+constexpr int kDiagDict = 32;
+struct DiagDict { double v[kDiagDict]; };
+struct DiagIndex { const uint8_t* idx = nullptr; DiagDict dict; };
 int pcg_update_r(size_t n, double* r, const double* q, const double* d, SolverScalars* S, double* hist,
-                 dd* part_out = nullptr);
-int pcg_direction_x(size_t n, double* x, double* p, const double* r, const double* d, SolverScalars* S);
+                 dd* part_out = nullptr, const DiagIndex* di = nullptr);
+int pcg_direction_x(size_t n, double* x, double* p, const double* r, const double* d, SolverScalars* S,
+                    const DiagIndex* di = nullptr);
 // x update carried by the SpMV of the NEXT iteration (SpmvArgs::xu, packed stream): the direction is then
 // written out of place, p_new = z + beta p_old (4 passes), because the SpMV that follows still reads
 // p_old for x += alpha p_old; pcg_flush_x applies the update of the last completed iteration after the

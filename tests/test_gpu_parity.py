@@ -366,6 +366,52 @@ def test_dictionary_in_the_parameter_block_keeps_every_bit(gpu, threads, spc, do
         _restore_pk(gpu)
 
 
+@pytest.mark.parametrize("graph,unroll2,unroll2_update,omega", [(1, 1, 0, 1.0), (0, 0, 1, 0.8), (1, 1, 1, 1.3)])
+def test_diagonal_as_byte_index_keeps_every_bit(gpu, graph, unroll2, unroll2_update, omega):
+    """"pcg.diag_index": on operators with a small value dictionary the row-ordered PCG reads the Jacobi diagonal as
+    one byte per position + a value list in the kernels' parameter block.  d_i keeps its bits, so iterates,
+    residuals and iteration counts equal the solve that reads the fp64 vector -- also after a value update
+    (index rebuilt) and with a diagonal of more than 32 distinct values (index not used)."""
+    g = load_golden("brick_fe2_N6_num1.npz")
+    n, rb, ci, va = gpu.brick_csr_host(2, 12, 1)
+    xs = gpu.brick_solution_host(2, 12, 1)
+    try:
+        gpu.set_option("sell.block_min_rows", 0)
+        gpu.set_option("pcg.graph", graph)
+        gpu.set_option("vec.unroll2", unroll2)
+        gpu.set_option("vec.unroll2_update", unroll2_update)
+        B = gpu.Matrix(n, n, rb, ci, va)
+        assert B.layout()["row_ordered_stream"]
+        b = B.spmv(xs)
+        A = gmat(gpu, g)
+        # 40 distinct diagonal values, off-diagonals untouched: the matrix still packs (<= 47 values), the diagonal index does not apply
+        va40 = va.copy()
+        dpos = np.flatnonzero(ci == np.repeat(np.arange(n, dtype=ci.dtype), np.diff(rb).astype(np.int64)))
+        va40[dpos] = va[dpos] * (1.0 + 0.125 * (np.arange(n) % 40))
+        res = {}
+        for on in (0, 1):
+            gpu.set_option("pcg.diag_index", on)
+            r = [B.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True, omega), B.pcg_jacobi(np.zeros(n), b, 9, 1e-30, True, omega),
+                 A.pcg_jacobi(np.zeros(A.rows), g["b"], 400, 1e-10, True)]
+            B.update_values(va * 2.0, 10 + 3 * on)
+            r.append(B.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True, omega))
+            B.update_values(va40, 11 + 3 * on)
+            r.append(B.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True, omega))
+            B.update_values(va, 12 + 3 * on)
+            res[on] = r
+        for r0, r1 in zip(res[0], res[1]):
+            assert r0[0] == r1[0] and r0[1] == r1[1] and r0[2] == r1[2] and np.array_equal(r0[3], r1[3])
+        assert res[1][2][1] == int(g["sym_pcgjac"][1]) and rel(res[1][2][3], g["sym_pcgjac_x"]) <= 1e-12
+        assert res[1][0][0] and rel(res[1][0][3], xs) <= 1e-8 and rel(res[1][3][3], 0.5 * xs) <= 1e-8
+    finally:
+        gpu.set_option("sell.block_min_rows", 2.0e6)
+        gpu.set_option("pcg.graph", 1)
+        gpu.set_option("vec.unroll2", 1)
+        gpu.set_option("vec.unroll2_update", 0)
+        gpu.set_option("pcg.diag_index", 1)
+        _restore_pk(gpu)
+
+
 @pytest.mark.parametrize("tile,sigma", [(1, 4096), (2, 64), (8, 4096), (3, 0)])
 def test_block_order_is_transparent(gpu, tile, sigma):
     """Rows cut into blocks of the matrix graph (reorder.cu): any tile size, also on graphs with isolated
