@@ -274,6 +274,11 @@ def run_ours(args):
     entry_bytes = (4.0 if vdict["packed"] else 6.0) if packed else 12.0
     passes = (12.0 if capi.get_option("pcg.defer_x", 1.0) != 0.0 else 13.0) + \
              (0.0 if capi.get_option("pcg.fused_dot", 1.0) != 0.0 else 2.0)
+    general_passes = passes                       # the 12-byte leg reads d as a vector
+    diag_values = A.diag_index()
+    if diag_values > 0 and capi.get_option("pcg.defer_x", 1.0) != 0.0:
+        # the update kernel reads d as one byte per row (and, with "pcg.diag_index_direction", the direction kernel too)
+        passes -= (7.0 / 8.0) * (2.0 if capi.get_option("pcg.diag_index_direction", 0.0) != 0.0 else 1.0)
     spmv_bytes = entry_bytes * nnz + 4.0 * (n + 1) + 16.0 * n
     iter_bytes = entry_bytes * nnz + 4.0 * (n + 1) + passes * 8.0 * n
     survey_spmv_bytes = 12.0 * nnz + 4.0 * (n + 1) + 16.0 * n
@@ -290,7 +295,7 @@ def run_ours(args):
                 "survey_12B_layout": {"algorithmic_bytes_per_launch": survey_spmv_bytes,
                                       "equivalent_gbs": survey_spmv_bytes / (spmv_avg_ms / 1e3) / 1e9,
                                       "note": "what a 12 B/entry stream would have to sustain to match this launch time"},
-                "iteration": {"algorithmic_bytes": iter_bytes, "vector_passes": passes,
+                "iteration": {"algorithmic_bytes": iter_bytes, "vector_passes": passes, "diagonal_value_list": diag_values,
                               "achieved_gbs": iter_bytes * args.steps * iters / (ms / 1e3) / 1e9,
                               "frac": iter_bytes * args.steps * iters / (ms / 1e3) / 1e9 / peak,
                               "survey_12B_13pass_equivalent_gbs": survey_iter_bytes * args.steps * iters / (ms / 1e3) / 1e9,
@@ -320,7 +325,7 @@ def run_ours(args):
         general = {"iterations_per_s": iters / (G["ms"] / 1e3), "spmv_avg_launch_ms": g_spmv_ms,
                    "spmv_achieved_gbs": survey_spmv_bytes / (g_spmv_ms / 1e3) / 1e9,
                    "spmv_frac": survey_spmv_bytes / (g_spmv_ms / 1e3) / 1e9 / peak,
-                   "iteration_frac": (12.0 * nnz + 4.0 * (n + 1) + passes * 8.0 * n) * iters / (G["ms"] / 1e3) / 1e9 / peak,
+                   "iteration_frac": (12.0 * nnz + 4.0 * (n + 1) + general_passes * 8.0 * n) * iters / (G["ms"] / 1e3) / 1e9 / peak,
                    "note": "sell.valdict = 0: int32 column + fp64 value per entry, caller's row order, 1 step after 1 warm-up"}
         assert abs(G["resid"] - resid) <= 1e-9 * abs(resid), (G["resid"], resid)     # same system, same 200 iterations
 

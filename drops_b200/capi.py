@@ -58,6 +58,7 @@ SIGNATURES = {
     "drops_b200_matrix_format": (_i, [_vp, _szpp, _szpp, _ip, _szpp]),
     "drops_b200_matrix_value_dictionary": (_i, [_vp, _i, _ip, _ip, _ip]),
     "drops_b200_matrix_layout": (_i, [_vp, _ip, _ip]),
+    "drops_b200_matrix_diag_index": (_i, [_vp, _ip]),
     "drops_b200_matrix_download": (_i, [_vp, _szp, _szp, _dp]),
     "drops_b200_spmv": (_i, [_vp, _dp, _dp]),
     "drops_b200_spmv_transpose": (_i, [_vp, _dp, _dp]),
@@ -400,6 +401,12 @@ class Matrix:
         bo, ro = C.c_int(), C.c_int()
         check(lib().drops_b200_matrix_layout(self.h, C.byref(bo), C.byref(ro)))
         return {"block_ordered": bool(bo.value), "row_ordered_stream": bool(ro.value)}
+
+    def diag_index(self):
+        """Length of the diagonal's value list when PCG reads the Jacobi diagonal as one byte per row (0: fp64 vector)."""
+        nv = C.c_int()
+        check(lib().drops_b200_matrix_diag_index(self.h, C.byref(nv)))
+        return nv.value
 
     def value_dictionary(self, transposed=False):
         nd, pk, cb = C.c_int(), C.c_int(), C.c_int()

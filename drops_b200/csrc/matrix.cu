@@ -1092,6 +1092,13 @@ int drops_b200_matrix_layout(drops_b200_matrix_t M, int* block_ordered, int* row
     return 0;
 }
 
+int drops_b200_matrix_diag_index(drops_b200_matrix_t M, int* n_values)
+{
+    DB_ARG(M != nullptr && n_values != nullptr, "null argument");
+    *n_values = (M->ro_diag_idx != nullptr && M->ro_diag_epoch == M->values_epoch && opt("pcg.diag_index", 1.0) != 0.0) ? M->ro_diag_count : 0;
+    return 0;
+}
+
 int drops_b200_matrix_format(drops_b200_matrix_t M, size_t* nslices, size_t* padded_nnz, int* compressed,
                              size_t* wide_slices)
 {

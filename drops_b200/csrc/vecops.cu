@@ -436,15 +436,27 @@ struct OpPcgUpdateR {
 };
 
 // d_i of the element pair i: from the vector, or (DIDX) from the byte index + the dictionary in the parameter block
+// Two steps so that every global load of a trip is issued before the first dictionary lookup: the lookup (an
+// indexed constant load) waits for its byte pair, and placed between the loads it would split them in two batches.
+struct DiagRaw { double2 v; uchar2 k; };
+
 template <bool DIDX>
-__device__ __forceinline__ double2 load_diag2(const double2* __restrict__ d2, const uint8_t* __restrict__ didx,
-                                              const DiagDict& dict, size_t i)
+__device__ __forceinline__ DiagRaw load_diag_raw(const double2* __restrict__ d2, const uint8_t* __restrict__ didx, size_t i)
 {
-    if (DIDX) {
-        const uchar2 k = __ldg(reinterpret_cast<const uchar2*>(didx) + i);
-        return make_double2(dict.v[k.x], dict.v[k.y]);
-    }
-    return d2[i];
+    DiagRaw w;
+    w.v = make_double2(1.0, 1.0); w.k = make_uchar2(0, 0);
+    if (DIDX) w.k = __ldg(reinterpret_cast<const uchar2*>(didx) + i);
+    else w.v = d2[i];
+    return w;
+}
+
+// (the value list is copied from the parameter block to shared memory: neighbouring positions hold rows of
+// different stencil types, and a constant load whose index diverges inside the warp is replayed per address --
+// measured on C2, direction kernel: 0.364 ms with the fp64 vector, 0.443 ms with indexed constant loads)
+template <bool DIDX>
+__device__ __forceinline__ double2 resolve_diag(const DiagRaw& w, const double* sdict)
+{
+    return DIDX ? make_double2(sdict[w.k.x], sdict[w.k.y]) : w.v;
 }
 
 template <int STEP, bool DIDX>
@@ -454,8 +466,13 @@ k_pcg_update_r(size_t n, double* __restrict__ r, const double* __restrict__ q, c
                const uint8_t* __restrict__ didx, const __grid_constant__ DiagDict dict)
 {
     __shared__ dd red_smem[2 * 32];
+    __shared__ double sdict[DIDX ? kDiagDict : 1];
     OpPcgUpdateR op{r, q, d, S, hist, part_out, 0.0, 0, 1.0};
     if (!op.begin()) return;
+    if (DIDX) {
+        if (threadIdx.x < kDiagDict) sdict[threadIdx.x] = dict.v[threadIdx.x];
+        __syncthreads();
+    }
     const double alpha = op.alpha, omega = op.omega;
     const bool jac = op.pc == DROPS_B200_PC_JACOBI;
     dd acc[2] = {dd_zero(), dd_zero()};
@@ -466,7 +483,8 @@ k_pcg_update_r(size_t n, double* __restrict__ r, const double* __restrict__ q, c
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     // two elements of the grid-stride sequence per trip: 6 independent 16 B loads in flight per thread; the
     // per-thread order of the accumulated products is unchanged (i, i + stride, i + 2 stride, ...)
-    auto body = [&](size_t i, double2 rv, const double2 qv, const double2 dv) {
+    auto body = [&](size_t i, double2 rv, const double2 qv, const DiagRaw& dw) {
+        const double2 dv = jac ? resolve_diag<DIDX>(dw, sdict) : make_double2(1.0, 1.0);
         rv.x = add(rv.x, mul(-alpha, qv.x)); rv.y = add(rv.y, mul(-alpha, qv.y));
         r2[i] = rv;
         const double zx = jac ? dvd(mul(omega, rv.x), dv.x) : rv.x;
@@ -479,11 +497,13 @@ k_pcg_update_r(size_t n, double* __restrict__ r, const double* __restrict__ q, c
         const size_t j = i + stride;
         const bool two = STEP == 2 && j < n2;
         const double2 rv0 = r2[i], qv0 = __ldcs(q2 + i);            // q is dead after this kernel
-        const double2 dv0 = jac ? load_diag2<DIDX>(d2, didx, dict, i) : one2;
-        double2 rv1 = one2, qv1 = one2, dv1 = one2;
-        if (two) { rv1 = r2[j]; qv1 = __ldcs(q2 + j); dv1 = jac ? load_diag2<DIDX>(d2, didx, dict, j) : one2; }
-        body(i, rv0, qv0, dv0);
-        if (two) body(j, rv1, qv1, dv1);
+        DiagRaw dw0, dw1;
+        dw0.v = one2; dw0.k = make_uchar2(0, 0); dw1 = dw0;
+        if (jac) dw0 = load_diag_raw<DIDX>(d2, didx, i);
+        double2 rv1 = one2, qv1 = one2;
+        if (two) { rv1 = r2[j]; qv1 = __ldcs(q2 + j); if (jac) dw1 = load_diag_raw<DIDX>(d2, didx, j); }
+        body(i, rv0, qv0, dw0);
+        if (two) body(j, rv1, qv1, dw1);
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) op.elem(n - 1, acc);
     if (grid_reduce_dd<2>(acc, red_smem, partials, ticket)) {
@@ -498,7 +518,7 @@ int pcg_update_r(size_t n, double* r, const double* q, const double* d, SolverSc
         Ctx& c = ctx();
         ScopedTiming t("pcg.update");
         const int grid = vec_grid(n, kReduceThreads, 4);
-        if (opt("vec.unroll2_update", 0.0) != 0.0)
+        if (opt("vec.unroll2_update_idx", 1.0) != 0.0)       // with the byte index two elements per trip pay: 0.263 -> 0.252 ms
             k_pcg_update_r<2, true><<<grid, kReduceThreads, 0, c.stream>>>(n, r, q, d, S, hist, part_out, c.partials, c.tickets, di->idx, di->dict);
         else
             k_pcg_update_r<1, true><<<grid, kReduceThreads, 0, c.stream>>>(n, r, q, d, S, hist, part_out, c.partials, c.tickets, di->idx, di->dict);
@@ -535,8 +555,13 @@ k_pcg_direction_x(size_t n, double* __restrict__ x, double* __restrict__ p, cons
                   const double* __restrict__ d, SolverScalars* S, unsigned* ticket,
                   const uint8_t* __restrict__ didx, const __grid_constant__ DiagDict dict)
 {
+    __shared__ double sdict[DIDX ? kDiagDict : 1];
     const int it = S->iter;
     if (S->x_iter == it) return;
+    if (DIDX) {
+        if (threadIdx.x < kDiagDict) sdict[threadIdx.x] = dict.v[threadIdx.x];
+        __syncthreads();
+    }
     const bool more = S->done == 0;
     const double alpha = dvd(S->rho_1, S->lambda);
     const double beta = more ? dvd(S->rho, S->rho_1) : 0.0;     // :173
@@ -548,10 +573,11 @@ k_pcg_direction_x(size_t n, double* __restrict__ x, double* __restrict__ p, cons
     const double2* r2 = reinterpret_cast<const double2*>(r);
     const double2* d2 = reinterpret_cast<const double2*>(d);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    auto body = [&](size_t i, double2 xv, double2 pv, const double2 rv, const double2 dv) {
+    auto body = [&](size_t i, double2 xv, double2 pv, const double2 rv, const DiagRaw& dw) {
         xv.x = add(xv.x, mul(alpha, pv.x)); xv.y = add(xv.y, mul(alpha, pv.y));   // :154
         x2[i] = xv;
         if (more) {
+            const double2 dv = jac ? resolve_diag<DIDX>(dw, sdict) : make_double2(1.0, 1.0);
             const double zx = jac ? dvd(mul(omega, rv.x), dv.x) : rv.x;
             const double zy = jac ? dvd(mul(omega, rv.y), dv.y) : rv.y;
             pv.x = add(zx, mul(beta, pv.x)); pv.y = add(zy, mul(beta, pv.y));     // :174
@@ -563,11 +589,14 @@ k_pcg_direction_x(size_t n, double* __restrict__ x, double* __restrict__ p, cons
         const size_t j = i + stride;
         const bool two = STEP == 2 && j < n2;
         const double2 xv0 = x2[i], pv0 = p2[i];
-        const double2 rv0 = more ? r2[i] : one2, dv0 = (more && jac) ? load_diag2<DIDX>(d2, didx, dict, i) : one2;
-        double2 xv1 = one2, pv1 = one2, rv1 = one2, dv1 = one2;
-        if (two) { xv1 = x2[j]; pv1 = p2[j]; if (more) { rv1 = r2[j]; if (jac) dv1 = load_diag2<DIDX>(d2, didx, dict, j); } }
-        body(i, xv0, pv0, rv0, dv0);
-        if (two) body(j, xv1, pv1, rv1, dv1);
+        const double2 rv0 = more ? r2[i] : one2;
+        DiagRaw dw0, dw1;
+        dw0.v = one2; dw0.k = make_uchar2(0, 0); dw1 = dw0;
+        if (more && jac) dw0 = load_diag_raw<DIDX>(d2, didx, i);
+        double2 xv1 = one2, pv1 = one2, rv1 = one2;
+        if (two) { xv1 = x2[j]; pv1 = p2[j]; if (more) { rv1 = r2[j]; if (jac) dw1 = load_diag_raw<DIDX>(d2, didx, j); } }
+        body(i, xv0, pv0, rv0, dw0);
+        if (two) body(j, xv1, pv1, rv1, dw1);
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const size_t i = n - 1;
@@ -582,16 +611,44 @@ k_pcg_direction_x(size_t n, double* __restrict__ x, double* __restrict__ p, cons
     }
 }
 
+// CTAs of `kernel` that are resident at once on the whole device: a grid-stride kernel launched with 8 CTAs per SM
+// but 3 resident (74 registers) runs 2.67 waves, the last one a third empty
+template <typename K>
+static int resident_ctas(K kernel, int threads)
+{
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 8;
+    }
+    return per_sm * ctx().sm_count;
+}
+
 int pcg_direction_x(size_t n, double* x, double* p, const double* r, const double* d, SolverScalars* S, const DiagIndex* di)
 {
     Ctx& c = ctx();
     DB_ARG(aligned16(x, p, r, d), "pcg_direction_x needs 16-byte aligned vectors");
     ScopedTiming t("pcg.direction");
-    const int grid = vec_grid(n, kReduceThreads, 4);
+    int grid = vec_grid(n, kReduceThreads, 4);
     unsigned* ticket = c.tickets + (size_t)2 * kTicketStride;
     static const DiagDict no_dict = {};
     const bool two = opt("vec.unroll2", 1.0) != 0.0;
-    if (di != nullptr && di->idx != nullptr && (n & 1) == 0) {
+    const bool idx = di != nullptr && di->idx != nullptr && (n & 1) == 0 && opt("pcg.diag_index_direction", 0.0) != 0.0;
+    // Measured on C2 (profiles/r01_notes.md, third part): both off.  One resident wave: 0.363 -> 0.385 ms (the block
+    // scheduler backfills an oversubscribed grid better than the stride loop balances one wave); the byte index in
+    // THIS kernel: 0.364 -> 0.42-0.45 ms although 0.35 GB less are read -- the kernel is bound by loads in flight
+    // at 3 CTAs/SM, and a 2-byte load in flight buys less bandwidth than the 16-byte load it replaces.
+    if (opt("vec.one_wave", 0.0) != 0.0) {           // (no reduction in this kernel: the grid does not touch any result)
+        static int res[4] = {0, 0, 0, 0};
+        const int which = (idx ? 2 : 0) + (two ? 1 : 0);
+        if (res[which] == 0)
+            res[which] = which == 3 ? resident_ctas(k_pcg_direction_x<2, true>, kReduceThreads)
+                       : which == 2 ? resident_ctas(k_pcg_direction_x<1, true>, kReduceThreads)
+                       : which == 1 ? resident_ctas(k_pcg_direction_x<2, false>, kReduceThreads)
+                                    : resident_ctas(k_pcg_direction_x<1, false>, kReduceThreads);
+        grid = std::min(grid, res[which]);
+    }
+    if (idx) {
         if (two) k_pcg_direction_x<2, true><<<grid, kReduceThreads, 0, c.stream>>>(n, x, p, r, d, S, ticket, di->idx, di->dict);
         else k_pcg_direction_x<1, true><<<grid, kReduceThreads, 0, c.stream>>>(n, x, p, r, d, S, ticket, di->idx, di->dict);
     } else if (two)

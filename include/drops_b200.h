@@ -135,6 +135,10 @@ DROPS_B200_API int drops_b200_matrix_value_dictionary(drops_b200_matrix_t A, int
  * cell); row_ordered_stream != 0 when the packed stream has its row-ordered twin, which is what
  * PCG iterates on ("pcg.reorder").  Both only change who shares a cache, never a result bit of A*x. */
 DROPS_B200_API int drops_b200_matrix_layout(drops_b200_matrix_t A, int* block_ordered, int* row_ordered_stream);
+/* Jacobi diagonal of the row-ordered PCG as one byte per row ("pcg.diag_index"; JACPcCL's diag_, num/precond.h:1162-1177,
+ * holds a handful of distinct values on constant-coefficient operators): *n_values = length of the value list the
+ * last PCG-Jacobi solve on A built, 0 when the diagonal is read as an fp64 vector.  Never changes a result bit. */
+DROPS_B200_API int drops_b200_matrix_diag_index(drops_b200_matrix_t A, int* n_values);
 /* Copies the device CSR back in the reference layout (for tests and the CPU baseline). */
 DROPS_B200_API int drops_b200_matrix_download(drops_b200_matrix_t A, size_t* rowbeg, size_t* colind, double* val);
 

@@ -380,6 +380,9 @@ def test_diagonal_as_byte_index_keeps_every_bit(gpu, graph, unroll2, unroll2_upd
         gpu.set_option("pcg.graph", graph)
         gpu.set_option("vec.unroll2", unroll2)
         gpu.set_option("vec.unroll2_update", unroll2_update)
+        gpu.set_option("vec.unroll2_update_idx", unroll2_update)     # same per-thread order of the reduction in both solves
+        gpu.set_option("pcg.diag_index_direction", unroll2)
+        gpu.set_option("vec.one_wave", graph)
         B = gpu.Matrix(n, n, rb, ci, va)
         assert B.layout()["row_ordered_stream"]
         b = B.spmv(xs)
@@ -408,6 +411,9 @@ def test_diagonal_as_byte_index_keeps_every_bit(gpu, graph, unroll2, unroll2_upd
         gpu.set_option("pcg.graph", 1)
         gpu.set_option("vec.unroll2", 1)
         gpu.set_option("vec.unroll2_update", 0)
+        gpu.set_option("vec.unroll2_update_idx", 1)
+        gpu.set_option("pcg.diag_index_direction", 0)
+        gpu.set_option("vec.one_wave", 0)
         gpu.set_option("pcg.diag_index", 1)
         _restore_pk(gpu)
 

@@ -1,0 +1,16 @@
+#!/bin/bash
+# Jacobi diagonal as a byte index: parity tests, then bench with / without
+set -u
+mkdir -p gpurun_out
+echo "=== pytest gpu all"
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_3g.log 2>&1; tail -5 gpurun_out/pytest_3g.log
+for o in "--opt pcg.diag_index=0" "" "--opt vec.unroll2_update=1" "--opt vec.unroll2=0" "--opt pcg.diag_index=0" ""; do
+  echo "--- $o"
+  timeout 600 python bench.py --no-cpu --no-small --no-host-matrix --no-general --steps 2 --warmup 2 $o 2> gpurun_out/bench_g.err | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+ms=d['ms_per_step']; sh=d['roofline']['iteration']['kernel_ms_share']
+print(round(d['value'],1),'it/s  e2e',round(d['e2e']['value'],1),' spmv ms',round(d['roofline']['avg_launch_ms'],3),' update ms', round(sh['pcg.update']*ms/200,4), ' direction ms', round(sh['pcg.direction']*ms/200,4), d['clocks']['sm_mhz'])
+"
+  tail -2 gpurun_out/bench_g.err
+done
