@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-small", action="store_true", help="skip the side measurement of BASELINE configs[0]")
     ap.add_argument("--no-pk", action="store_true", help="12-byte SELL stream only (value dictionary off)")
     ap.add_argument("--no-general", action="store_true", help="skip the side measurement of the 12-byte stream")
+    ap.add_argument("--no-solvers", action="store_true", help="skip the GMRES / MINRES side measurement on the C2 system")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (repeatable)")
     return ap.parse_args()
 
@@ -329,6 +330,14 @@ def run_ours(args):
                    "note": "sell.valdict = 0: int32 column + fp64 value per entry, caller's row order, 1 step after 1 warm-up"}
         assert abs(G["resid"] - resid) <= 1e-9 * abs(resid), (G["resid"], resid)     # same system, same 200 iterations
 
+    # ---- the other two solvers of the path on the same system (device-resident, fixed work) ---------
+    solvers = None
+    if not args.no_solvers:
+        try:
+            solvers = other_solvers(capi, A, x, b, n, nnz, entry_bytes, peak)
+        except Exception as exc:      # the headline line must survive a failure of the side measurement
+            solvers = {"error": repr(exc)}
+
     # ---- end to end through the host-buffer C ABI ----------------------------------------------
     import torch
     hb = torch.empty(n, dtype=torch.float64).pin_memory()
@@ -411,9 +420,48 @@ def run_ours(args):
                                 (", PCG on row-ordered vectors" if layout["row_ordered_stream"] and capi.get_option("pcg.reorder", 1.0) != 0.0 else ""),
                    "generate_s": gen_s},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        "final_relative_residual": resid, "general_12B_stream": general, "other_configs": {"C1_p1_n64": c1},
+        "final_relative_residual": resid, "general_12B_stream": general, "other_solvers_c2": solvers,
+        "other_configs": {"C1_p1_n64": c1},
     }
     print(json.dumps(line), flush=True)
+
+
+def other_solvers(capi, A, x, b, n, nnz, entry_bytes, peak):
+    """GMRESSolverCL<JACPcCL> (restart 30, left preconditioning, modified Gram-Schmidt as the serial reference,
+    krylovsolver.h:320-461) and MResSolverCL (krylovsolver.h:1069-1152) on the C2 system, device-resident, tol = 0 so
+    that the iteration count is fixed.  `survey_frac` uses SURVEY.md 8(d)'s byte counts with the matrix stream this
+    run reads: GMRES inner step i moves the matrix + 8n (4 (i + 1) + 5) bytes (MGS-faithful), MINRES matrix + 15 * 8n."""
+    out = {}
+    mat = entry_bytes * nnz + 4.0 * (n + 1)
+    restart, cycles = 30, 2
+    its = restart * cycles
+
+    def run_gmres():
+        x.fill(0.0)
+        return A.gmres_dev(x, b, restart, its, 0.0, True)
+    run_gmres()
+    capi.synchronize(); capi.timer_start()
+    conv, it, res = run_gmres()
+    ms = capi.timer_stop()
+    gm_bytes = cycles * sum(mat + 8.0 * n * (4.0 * (i + 1) + 5.0) for i in range(restart))
+    out["gmres_jacobi_restart30"] = {"iterations": it, "iterations_per_s": it / (ms / 1e3), "ms_per_iteration": ms / max(it, 1),
+                                     "relative_residual": res,
+                                     "survey_bytes_per_iteration": gm_bytes / its,
+                                     "survey_gbs": gm_bytes / (ms / 1e3) / 1e9, "survey_frac": gm_bytes / (ms / 1e3) / 1e9 / peak}
+    its_m = 100
+
+    def run_minres():
+        x.fill(0.0)
+        return A.minres_dev(x, b, its_m, 0.0, True)
+    run_minres()
+    capi.synchronize(); capi.timer_start()
+    conv, it, res = run_minres()
+    ms = capi.timer_stop()
+    mr_bytes = it * (mat + 15.0 * 8.0 * n)
+    out["minres"] = {"iterations": it, "iterations_per_s": it / (ms / 1e3), "ms_per_iteration": ms / max(it, 1),
+                     "relative_residual": res, "survey_bytes_per_iteration": mat + 15.0 * 8.0 * n,
+                     "survey_gbs": mr_bytes / (ms / 1e3) / 1e9, "survey_frac": mr_bytes / (ms / 1e3) / 1e9 / peak}
+    return out
 
 
 def small_config_c1(args):

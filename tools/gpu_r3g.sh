@@ -6,7 +6,7 @@ echo "=== pytest gpu all"
 timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_3g.log 2>&1; tail -5 gpurun_out/pytest_3g.log
 for o in "--opt pcg.diag_index=0" "" "--opt vec.unroll2_update=1" "--opt vec.unroll2=0" "--opt pcg.diag_index=0" ""; do
   echo "--- $o"
-  timeout 600 python bench.py --no-cpu --no-small --no-host-matrix --no-general --steps 2 --warmup 2 $o 2> gpurun_out/bench_g.err | python -c "
+  timeout 600 python bench.py --no-cpu --no-small --no-host-matrix --no-general --no-solvers --steps 2 --warmup 2 $o 2> gpurun_out/bench_g.err | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
 ms=d['ms_per_step']; sh=d['roofline']['iteration']['kernel_ms_share']

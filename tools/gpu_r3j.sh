@@ -5,7 +5,7 @@ echo "=== pytest diag/pcg"
 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "diagonal or pcg_forms" > gpurun_out/pytest_3j.log 2>&1; tail -3 gpurun_out/pytest_3j.log
 for o in "--opt pcg.diag_index=0 --opt vec.one_wave=0" "--opt pcg.diag_index=0" "" "--opt pcg.diag_index_direction=0" "--opt pcg.diag_index_direction=0 --opt vec.unroll2_update=1"; do
   echo "--- $o"
-  timeout 600 python bench.py --no-cpu --no-small --no-host-matrix --no-general --steps 2 --warmup 2 $o 2> gpurun_out/bench_g.err | python -c "
+  timeout 600 python bench.py --no-cpu --no-small --no-host-matrix --no-general --no-solvers --steps 2 --warmup 2 $o 2> gpurun_out/bench_g.err | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
 ms=d['ms_per_step']; sh=d['roofline']['iteration']['kernel_ms_share']
