@@ -31,8 +31,9 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
            "the carried x update needs the fused dot and its scalars");
     if (A.rows == 0) return 0;
     // the fused-dot product with the dictionary in the parameter block has its own geometry (measured on C2 inside
-    // PCG: 14 words in flight x 384-thread CTAs x 192 slices, 3 CTAs of <= 56 registers per SM)
-    const bool dot_geometry = a.dotv != nullptr && A.pk != nullptr && A.ndict_host > 0 && A.ndict_host == A.ndict &&
+    // PCG: 15 words in flight x 384-thread CTAs x 192 slices, 3 CTAs of <= 56 registers per SM)
+    const bool dot_geometry = a.dotv != nullptr && a.epilogue == EPI_NONE && opt("spmv.exact", 1.0) != 0.0 &&     // (the forms launch_pk has the U14 kernel for)
+                              A.pk != nullptr && A.ndict_host > 0 && A.ndict_host == A.ndict &&
                               A.ndict <= kPkDictSmem && opt("spmv.pkdict", 0.0) == 0.0 &&
                               opt("spmv.pk_cdict_dot", (double)kPkCdictDotVariant) != 0.0;
     int threads = dot_geometry ? (int)opt("spmv.pk_dot_threads", 384) : (int)opt("spmv.pk_threads", 512);

@@ -77,7 +77,13 @@ __device__ __forceinline__ double pk_gather(const double* __restrict__ x, const 
 // load of the unrolled body is unconditional and straight-line; the padded product is computed and
 // then dropped by a select (adding it could turn a -0.0 sum into +0.0, or poison it when x_0 is
 // not finite), which keeps the row sum bit-identical.
-template <bool EXACT, int U, bool SMEM, int LD, bool NOPAD = false, bool XW = false, bool CD = false>
+// TM (masked tail): the width % U entries left after the full batches are ONE more batch whose loads are
+// predicated on the (warp-uniform) remainder instead of a loop the compiler cuts into batches of 8, 4, 2, 1 --
+// every batch costs a round trip to the matrix stream plus one to x, so a row of 27 entries at U = 14 takes
+// 2 round-trip pairs instead of 4.  The masked slots hold the padding word and are dropped by the same select.
+// Measured on C2 (profiles/r01_probe_cdict2.json): no gain (U14 1.500 -> 1.499 ms, U15 1.467 -> 1.581) -- the
+// product is not bound by the number of round trips per row; variants 100 + n of "spmv.pk_cdict[_dot]".
+template <bool EXACT, int U, bool SMEM, int LD, bool NOPAD = false, bool XW = false, bool CD = false, bool TM = false>
 __device__ __forceinline__ double pk_row_sum(const PkView& A, int64_t base, int width, int lane,
                                              const double* __restrict__ x, const XWin& xw = XWin())
 {
@@ -101,6 +107,24 @@ __device__ __forceinline__ double pk_row_sum(const PkView& A, int64_t base, int 
             const double t = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv[u])) : fma(v, xv[u], sum);
             sum = (NOPAD || w[u] < wpad) ? t : sum;
         }
+    }
+    if (TM) {
+        const int rem = width - j;                      // < U, the same for all lanes of the slice
+        if (rem > 0) {
+            uint32_t w[U];
+            double xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) w[u] = u < rem ? ld_stream<LD>(pp + (size_t)(j + u) * 32) : wpad;
+#pragma unroll
+            for (int u = 0; u < U; ++u) xv[u] = u < rem ? pk_gather<XW>(x, xw, w[u] & cmask) : 0.0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double v = pk_value<SMEM, CD>(A, w[u] >> cbits);
+                const double t = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv[u])) : fma(v, xv[u], sum);
+                sum = w[u] < wpad ? t : sum;
+            }
+        }
+        return sum;
     }
     for (; j < width; ++j) {
         const uint32_t w = ld_stream<LD>(pp + (size_t)j * 32);
@@ -207,7 +231,7 @@ __device__ __forceinline__ double pk_row_sum_pipe(const PkView& A, int64_t base,
 //   2 = in the slice loop, but the partner is fetched AFTER the row sum (an L1 hit: the diagonal
 //       entry just gathered it) and the accumulator is parked in shared memory between slices, so
 //       the row sum runs with the registers of the plain product.
-template <int EPI, bool EXACT, int DOT, int U, int MAXT, int MINB, bool SMEM, int DF, bool V6 = false, bool XW = false, bool CD = false>
+template <int EPI, bool EXACT, int DOT, int U, int MAXT, int MINB, bool SMEM, int DF, bool V6 = false, bool XW = false, bool CD = false, bool TM = false>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_spmv_sell_pk(const __grid_constant__ PkView A, const double* __restrict__ x, double* __restrict__ y, EpiArgs e)
 {
@@ -265,8 +289,8 @@ k_spmv_sell_pk(const __grid_constant__ PkView A, const double* __restrict__ x, d
         const bool nopad = !V6 && U > 0 && A.nopad != nullptr && A.nopad[s] != 0;      // warp-uniform
         const double sum = V6 ? pk6_row_sum<EXACT, UU, SMEM>(A, base, width, lane, x)
                          : U <= 0 ? pk_row_sum_pipe<EXACT, UU, SMEM>(A, base, width, lane, x)
-                         : nopad ? pk_row_sum<EXACT, UU, SMEM, (U >= 100 ? 1 : 0), true, XW, CD>(A, base, width, lane, x, xw)
-                                 : pk_row_sum<EXACT, UU, SMEM, (U >= 100 ? 1 : 0), false, XW, CD>(A, base, width, lane, x, xw);
+                         : nopad ? pk_row_sum<EXACT, UU, SMEM, (U >= 100 ? 1 : 0), true, XW, CD, TM>(A, base, width, lane, x, xw)
+                                 : pk_row_sum<EXACT, UU, SMEM, (U >= 100 ? 1 : 0), false, XW, CD, TM>(A, base, width, lane, x, xw);
         if (row >= 0) {
             const double out = apply_epilogue<EPI>(sum, av, e, beta);
             y[row] = out;
@@ -306,26 +330,26 @@ static void allow_smem(K kernel, size_t sh)
     if (sh > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
 }
 
-template <int EPI, bool EXACT, int U, int MAXT, int MINB, bool SMEM, int DF, bool V6 = false, bool XW = false, bool CD = false>
+template <int EPI, bool EXACT, int U, int MAXT, int MINB, bool SMEM, int DF, bool V6 = false, bool XW = false, bool CD = false, bool TM = false>
 static void launch_pk_d(const PkView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads, cudaStream_t st)
 {
     if (threads > MAXT) threads = MAXT;
     const size_t sh = XW ? xw_smem_bytes(v, grid) : SMEM ? ((size_t)v.ndict + 1) * sizeof(double) : 0;
     if (a.dotv == nullptr) {
-        if (XW) allow_smem(k_spmv_sell_pk<EPI, EXACT, 0, U, MAXT, MINB, SMEM, 0, V6, XW, CD>, sh);
-        k_spmv_sell_pk<EPI, EXACT, 0, U, MAXT, MINB, SMEM, 0, V6, XW, CD><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
+        if (XW) allow_smem(k_spmv_sell_pk<EPI, EXACT, 0, U, MAXT, MINB, SMEM, 0, V6, XW, CD, TM>, sh);
+        k_spmv_sell_pk<EPI, EXACT, 0, U, MAXT, MINB, SMEM, 0, V6, XW, CD, TM><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
         return;
     }
     const long long nwarps = (long long)grid * (threads >> 5);
     const double mode = opt("spmv.dotmode", 0.0);
     const bool two_kernels = mode == 2.0 || (mode == 0.0 && grid > (int)kReduceFlat);
     if (two_kernels && nwarps <= kPartialStride) {
-        if (XW) allow_smem(k_spmv_sell_pk<EPI, EXACT, 2, U, MAXT, MINB, SMEM, DF, V6, XW, CD>, sh);
-        k_spmv_sell_pk<EPI, EXACT, 2, U, MAXT, MINB, SMEM, DF, V6, XW, CD><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
+        if (XW) allow_smem(k_spmv_sell_pk<EPI, EXACT, 2, U, MAXT, MINB, SMEM, DF, V6, XW, CD, TM>, sh);
+        k_spmv_sell_pk<EPI, EXACT, 2, U, MAXT, MINB, SMEM, DF, V6, XW, CD, TM><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
         sum_warp_partials(nwarps, e, st);
     } else {
-        if (XW) allow_smem(k_spmv_sell_pk<EPI, EXACT, 1, U, MAXT, MINB, SMEM, DF, V6, XW, CD>, sh);
-        k_spmv_sell_pk<EPI, EXACT, 1, U, MAXT, MINB, SMEM, DF, V6, XW, CD><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
+        if (XW) allow_smem(k_spmv_sell_pk<EPI, EXACT, 1, U, MAXT, MINB, SMEM, DF, V6, XW, CD, TM>, sh);
+        k_spmv_sell_pk<EPI, EXACT, 1, U, MAXT, MINB, SMEM, DF, V6, XW, CD, TM><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
     }
 }
 
@@ -346,7 +370,7 @@ static void launch_pk_v(const PkView& v, const SpmvArgs& a, const EpiArgs& e, in
 //   0 = U8/<=40 regs, 1 = U8/<=48, 2 = U4/<=32, 3 = U16/<=64, 4 = U16/<=48, 5 = U8/256 threads/<=40,
 //   6 = U12/<=48, 7 = U4/<=40, 8 = U8/CTAs up to 1024 threads/<=64, 9 = U8/<=512 threads/<=40,
 //   10 = U16/<=512 threads/<=64; software-pipelined: 11 = U4/<=40, 12 = U8/<=48, 13 = U6/<=40, 14 = U4/<=512 threads/<=40; 15 = variant 9 with the stream loaded L1::no_allocate
-constexpr int kPkCdictDotVariant = 8;  // measured on C2 inside PCG (profiles/r01_probe_cdict.json): U14, 384-thread CTAs, <= 56 registers
+constexpr int kPkCdictDotVariant = 17; // measured on C2 inside PCG (profiles/r01_probe_cdict*.json): U15, 384-thread CTAs, <= 56 registers
 constexpr int kPkDefaultVariant = 9;   // measured on C2 (profiles/r01_probe_blockorder.json): 512-thread CTAs x 128 slices
 
 template <int EPI, bool EXACT>
@@ -392,6 +416,26 @@ static bool launch_pk(const PkView& v, const SpmvArgs& a, const EpiArgs& e, int 
                 case 11: DB_CD(32, 512, 1);
                 case 12: DB_CD(24, 128, 5);
                 case 13: DB_CD(14, 192, 6);
+#define DB_CDT(U_, T_, B_) launch_pk_d<EPI_NONE, true, U_, T_, B_, false, 2, false, false, true, true>(v, a, e, grid, threads, st); return true
+                case 101: DB_CDT(8, 512, 3);           // 100 + n: variant n with the masked tail batch
+                case 102: DB_CDT(16, 512, 2);
+                case 103: DB_CDT(10, 512, 3);
+                case 108: DB_CDT(14, 384, 3);
+                case 109: DB_CDT(12, 384, 3);
+                case 110: DB_CDT(20, 256, 3);
+                case 117: DB_CDT(15, 384, 3);
+                case 118: DB_CDT(16, 384, 3);
+                case 120: DB_CDT(7, 512, 3);
+                case 121: DB_CDT(9, 512, 3);
+#undef DB_CDT
+#define DB_CDF(U_, T_, B_, DF_) launch_pk_d<EPI_NONE, true, U_, T_, B_, false, DF_, false, false, true>(v, a, e, grid, threads, st); return true
+                case 14: DB_CDF(14, 384, 3, 0);        // dot accumulator in registers
+                case 15: DB_CDF(12, 384, 3, 0);
+                case 16: DB_CDF(10, 384, 3, 0);
+                case 17: DB_CDF(15, 384, 3, 2);
+                case 18: DB_CDF(16, 384, 3, 2);
+                case 19: DB_CDF(14, 384, 3, 1);        // dot in a tail pass over the CTA's rows
+#undef DB_CDF
                 default: break;
             }
 #undef DB_CD

@@ -93,7 +93,7 @@ def test_spmv_layout_and_launch_options_do_not_change_results(gpu, sigma, thread
         gpu.set_option("spmv.prefetch", 0)
 
 
-CDICT_DOT_DEFAULT = 8 # library default of "spmv.pk_cdict_dot"
+CDICT_DOT_DEFAULT = 17  # library default of "spmv.pk_cdict_dot"
 CDICT_DEFAULT = 1     # library default of "spmv.pk_cdict"
 XWIN_DEFAULT = 0      # library default of "spmv.pk_xwin"
 
@@ -348,7 +348,7 @@ def test_dictionary_in_the_parameter_block_keeps_every_bit(gpu, threads, spc, do
         X, Y = gpu.Vector.from_host(xin), gpu.Vector(n)
         A, R = gmat(gpu, g), gmat(gpu, r)
         res = {}
-        for cd in range(14):
+        for cd in list(range(20)) + [101, 102, 103, 108, 109, 110, 117, 118, 120, 121]:
             gpu.set_option("spmv.pk_cdict", cd)
             gpu.set_option("spmv.pk_cdict_dot", cd)
             d = B.spmv_dot_dev(X, Y, X)
@@ -356,7 +356,7 @@ def test_dictionary_in_the_parameter_block_keeps_every_bit(gpu, threads, spc, do
                        B.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True)[3], np.float64(B.pcg_jacobi(np.zeros(n), b, 9, 1e-30, True)[2]),
                        B.gmres_jacobi(np.zeros(n), b, 20, 300, 1e-10, True, 1.0, True)[3],
                        A.spmv(g["x_in"]), A.spmv_transpose(g["x_in"]), R.spmv(r["x_in"]))
-        for cd in range(1, 14):
+        for cd in list(range(1, 20)) + [101, 102, 103, 108, 109, 110, 117, 118, 120, 121]:
             for u, v in zip(res[0], res[cd]):
                 assert np.array_equal(u, v)
         assert np.array_equal(res[1][7], g["y_Ax"]) and np.array_equal(res[1][8], g["y_ATx"]) and np.array_equal(res[1][9], r["y_Ax"])

@@ -35,22 +35,18 @@ def geo(thr, spc):
     capi.set_option("spmv.pk_threads", thr); capi.set_option("spmv.pk_slices_per_cta", spc)
     capi.set_option("spmv.pk_dot_threads", thr); capi.set_option("spmv.pk_dot_slices_per_cta", spc)
 both = lambda v: dict(spmv__pk_cdict=v, spmv__pk_cdict_dot=v)
-for rep in range(1):
-    geo(512, 128)
-    measure("dictionary in shared memory", **both(0))
-    measure("parameter block U8 512x3 (40 regs)", **both(1))
-    measure("parameter block U16 512x2 (64 regs)", **both(2))
-for spc in (96, 144, 192, 288, 384):
-    geo(384, spc); measure(f"U14 384x3 (56) spc{spc}", **both(8))
-for spc in (128, 192, 256, 384):
-    geo(256, spc); measure(f"U16 256x4 (64) spc{spc}", **both(7))
-for spc in (256, 384, 512):
-    geo(512, spc); measure(f"U16 512x2 (64) spc{spc}", **both(2))
-for spc in (128, 192, 256):
-    geo(256, spc); measure(f"U12 256x5 (48) spc{spc}", **both(6))
-for spc in (48, 96, 192):
-    geo(192, spc); measure(f"U14 192x6 (56) spc{spc}", **both(13))
-geo(384, 192); measure("U12 384x3 (56) spc192", **both(9))
+geo(384, 192)
+measure("U14 384x3 (default)", **both(8))
+measure("U15 384x3", **both(17))
+for cv, name in ((108, "U14 384x3"), (117, "U15 384x3"), (118, "U16 384x3"), (109, "U12 384x3")):
+    measure(name + " masked tail", **both(cv))
 geo(512, 128)
+for cv, name in ((101, "U8 512x3"), (103, "U10 512x3"), (120, "U7 512x3"), (121, "U9 512x3")):
+    measure(name + " masked tail", **both(cv))
+geo(512, 256); measure("U16 512x2 masked tail spc256", **both(102))
+geo(256, 64); measure("U20 256x3 masked tail", **both(110))
+geo(384, 192)
+measure("U14 384x3 (default)", **both(8))
+measure("U14 384x3 masked tail", **both(108))
 assert len({r["resid"] for r in out}) == 1, "variants disagree"
 json.dump(out, open("gpurun_out/probe_cdict.json", "w"), indent=1)
