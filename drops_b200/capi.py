@@ -846,7 +846,7 @@ class DistMatrix:
         check(lib().drops_b200_dist_matrix_format(self.h, C.byref(pk), C.byref(nd)))
         return {"interior_packed": bool(pk.value & 1), "six_byte": bool(pk.value & 2), "row_ordered": bool(pk.value & 4),
                 "block_ordered": bool(pk.value & 8), "p2p": bool(pk.value & 16), "p2p_fault": bool(pk.value & 32), "p2p_reduce": bool(pk.value & 64),
-                "n_distinct": nd.value}
+                "diag_index": bool(pk.value & 128), "n_distinct": nd.value}
 
     def diag(self):
         d = np.zeros(max(self.info()["n_owned"], 1))

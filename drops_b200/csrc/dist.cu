@@ -400,7 +400,7 @@ static void free_dist_matrix(drops_b200_dist_matrix_s* M)
     if (M->comm && M->comm->kind == COMM_LOCAL && M->rank < (int)M->comm->parts.size() && M->comm->parts[(size_t)M->rank] == M)
         M->comm->parts[(size_t)M->rank] = nullptr;
     free_sell(M->sell_int); free_sell(M->sell_bnd); free_sell(M->sell_bnd_ro);
-    dev_free(M->ro_perm); dev_free(M->diag_ro); dev_free(M->d_send_idx_ro);
+    dev_free(M->ro_perm); dev_free(M->diag_ro); dev_free(M->d_send_idx_ro); dev_free(M->diag_ro_idx);
     for (void* m : M->ipc_mapped) cudaIpcCloseMemHandle(m);
     dev_free(M->p2p_ticket); dev_free(M->p2p_fault); dev_free(M->d_peer_dst); dev_free(M->d_peer_flag);
     dev_free(M->d_send_off); dev_free(M->d_expect);
@@ -595,6 +595,9 @@ int dist_matrix_build(drops_b200_comm_s* comm, drops_b200_exchange_s* E, size_t 
                 if (M->n_send) k_gather_i32<<<blocks_for((long long)M->n_send, 256), 256, 0, st>>>((long long)M->n_send, M->d_send_idx, iperm, M->d_send_idx_ro);
                 count_launch(3);
                 s3 = vec_gather_perm(npos, M->ro_perm, M->diag, M->diag_ro, 1.0);
+                // constant-coefficient partitions: the permuted diagonal as a byte index (update kernel of dist_pcg)
+                if (s3 == 0 && M->diag_ok && M->sell_int.ndict_host > 0)
+                    s3 = build_value_index8(M->diag_ro, npos, kDiagDict, &M->diag_ro_idx, M->diag_ro_values, &M->diag_ro_count);
             }
             if (s3 == 0) {
                 cudaError_t e3 = cudaStreamSynchronize(st);
@@ -968,8 +971,14 @@ int dist_pcg(int np, drops_b200_dist_matrix_s* const* P, double* const* x, const
     std::vector<double*> xv(x, x + np);
     std::vector<const double*> bv(b, b + np), dg(np);
     std::vector<size_t> nv(np);
+    std::vector<DiagIndex> dix(np);               // (idx == nullptr: the kernels read the fp64 diagonal)
     for (int p = 0; p < np; ++p) {
         dg[p] = P[p]->diag; nv[p] = P[p]->n_owned;
+        if (ro && pc == DROPS_B200_PC_JACOBI && P[p]->diag_ro_idx != nullptr && P[p]->diag_ro_count > 0 &&
+            opt("pcg.diag_index", 1.0) != 0.0) {
+            dix[p].idx = P[p]->diag_ro_idx;
+            std::memcpy(dix[p].dict.v, P[p]->diag_ro_values, sizeof(double) * (size_t)P[p]->diag_ro_count);
+        }
         if (ro) {
             double* xp = dwork(P[p], 3); double* bp = dwork(P[p], 4);
             if (!xp || !bp) return DROPS_B200_E_NOMEM;
@@ -1048,7 +1057,7 @@ int dist_pcg(int np, drops_b200_dist_matrix_s* const* P, double* const* x, const
         for (int p = 0; p < np; ++p) DB_CHECK(scalars_kernel(PH_LAMBDA, P[p], nullptr, nullptr));
         // x += alpha p rides in the direction kernel (10 instead of 11 vector passes, vecops.cuh)
         for (int p = 0; p < np; ++p) {
-            if (defer_x[p]) DB_CHECK(pcg_update_r(nv[p], r[p], q[p], dg[p], S[p], nullptr, gather_slot(P[p], 2)));
+            if (defer_x[p]) DB_CHECK(pcg_update_r(nv[p], r[p], q[p], dg[p], S[p], nullptr, gather_slot(P[p], 2), &dix[p]));
             else DB_CHECK(pcg_update(nv[p], xv[p], r[p], pv[p], q[p], dg[p], S[p], nullptr, gather_slot(P[p], 2)));
         }
         DB_CHECK(allgather_partials(comm, 2, done_ptrs.data()));
@@ -1557,6 +1566,8 @@ int drops_b200_dist_matrix_format(drops_b200_dist_matrix_t A, int* interior_pack
         *interior_packed |= 64;                      // reductions go peer to peer as well
         if (f) *interior_packed |= 32;
     }
+    if (interior_packed && A->diag_ro_idx != nullptr && A->diag_ro_count > 0 && opt("pcg.diag_index", 1.0) != 0.0)
+        *interior_packed |= 128;                     // the update kernel reads the Jacobi diagonal as a byte index
     if (n_distinct) *n_distinct = A->sell_int.ndict;
     return 0;
 }

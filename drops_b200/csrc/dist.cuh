@@ -85,6 +85,9 @@ struct drops_b200_dist_matrix_s {
     int32_t* ro_perm = nullptr;              // position -> owned row (-1 = padding)
     db200::SellOp sell_bnd_ro;               // boundary rows with columns = positions / npos + ghost slot
     double* diag_ro = nullptr;
+    uint8_t* diag_ro_idx = nullptr;      // diag_ro as one byte per position + value list ("pcg.diag_index", krylov.cu)
+    int diag_ro_count = 0;
+    double diag_ro_values[32] = {};
     int32_t* d_send_idx_ro = nullptr;
     bool block_ordered = false;
     // Peer-to-peer halo ("dist.p2p"): the pack kernel stores the boundary entries of x straight into the

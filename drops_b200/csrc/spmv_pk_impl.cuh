@@ -108,7 +108,7 @@ __device__ __forceinline__ double pk_row_sum(const PkView& A, int64_t base, int 
             sum = (NOPAD || w[u] < wpad) ? t : sum;
         }
     }
-    if (TM) {
+    if constexpr (TM) {
         const int rem = width - j;                      // < U, the same for all lanes of the slice
         if (rem > 0) {
             uint32_t w[U];
@@ -124,14 +124,14 @@ __device__ __forceinline__ double pk_row_sum(const PkView& A, int64_t base, int 
                 sum = w[u] < wpad ? t : sum;
             }
         }
-        return sum;
-    }
-    for (; j < width; ++j) {
-        const uint32_t w = ld_stream<LD>(pp + (size_t)j * 32);
-        const double xv = pk_gather<XW>(x, xw, w & cmask);
-        const double v = pk_value<SMEM, CD>(A, w >> cbits);
-        const double t = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv)) : fma(v, xv, sum);
-        sum = (NOPAD || w < wpad) ? t : sum;
+    } else {
+        for (; j < width; ++j) {
+            const uint32_t w = ld_stream<LD>(pp + (size_t)j * 32);
+            const double xv = pk_gather<XW>(x, xw, w & cmask);
+            const double v = pk_value<SMEM, CD>(A, w >> cbits);
+            const double t = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv)) : fma(v, xv, sum);
+            sum = (NOPAD || w < wpad) ? t : sum;
+        }
     }
     return sum;
 }
