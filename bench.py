@@ -307,6 +307,7 @@ def run_ours(args):
         try:
             tr = json.load(open(prof))
             roofline["traffic"] = tr.get("dram_bytes_per_launch_pk" if packed else "dram_bytes_per_launch")
+            roofline["traffic_source"] = tr.get("pk_source" if packed else "source")
         except Exception:
             pass
 
