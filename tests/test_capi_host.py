@@ -146,3 +146,21 @@ def test_brick_solves_poisson(lib_built, port):
     conv, it, res, x = A.pcg_jacobi(np.zeros(n), b, 500, 1e-12, True)
     assert conv and np.linalg.norm(x - xs) / np.linalg.norm(xs) < 1e-10
     assert 0 < xs.max() <= 1.0
+
+
+def test_documented_options_exist_in_the_source():
+    """Every option DESIGN.md section 7 names is one the library reads (`opt("...")` in csrc/)."""
+    import glob
+    text = open(os.path.join(ROOT, "DESIGN.md")).read()
+    sec = text[text.index("## 7. Options"):text.index("## 8.")]
+    names = set(re.findall(r"`([a-z]+\.[a-z0-9_/]+)`", sec))
+    assert len(names) >= 40
+    src = "".join(open(f).read() for f in glob.glob(os.path.join(ROOT, "drops_b200", "csrc", "*.cu*")))
+    missing = []
+    for n in sorted(names):
+        cands = [n]
+        if "/" in n:                                   # `sell.block_tile_a/b/c`
+            base, parts = n[:n.rindex("_") + 1], n[n.rindex("_") + 1:].split("/")
+            cands = [base + p for p in parts]
+        missing += [c for c in cands if '"%s"' % c not in src]
+    assert not missing, missing
