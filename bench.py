@@ -8,10 +8,14 @@ One "step" = one PCGSolverCL<JACPcCL>::Solve of --iters iterations with tol = 0 
 krylovsolver.h:149,177-178).  `value` times the device-resident entry point; `e2e` times the
 host-buffer entry point (x, b copied host->device and x device->host inside the call, pinned
 buffers) on a matrix that went through the host upload path in the reference's own CSR layout.
-`roofline` is the SpMV kernel (fused with the p.Ap dot): algorithmic bytes 12 nnz + 4(n+1) + 16 n
-per launch over its CUDA-event time inside the timed steps, against MEASURED_PEAKS.json.
-`cpu_baseline` / --impl reference time the compiled DROPS reference (oracle/_ref) -- or the plain-C
-oracle when it is absent -- on a bounded sample of the same brick family, scaled by rows to C2.
+`roofline` is the SpMV kernel (fused with the p.Ap dot): algorithmic bytes E nnz + 4(n+1) + 16 n per
+launch, E = bytes per stored entry of the stream the kernel actually reads (4 dictionary-packed, 6, or
+12 = int32 column + fp64 value), over its CUDA-event time inside the timed steps, against
+MEASURED_PEAKS.json; the plain y = A x and y = A^T x products are timed beside it.
+--impl reference times the compiled DROPS reference (oracle/_ref; the plain-C oracle when it is absent)
+with all host cores on C2 ITSELF when the host has the memory for the 23 GB reference-layout matrix
+(a few PCG iterations per step), and on the P2 N=64 sample beside it; `cpu_baseline` of our own arm is
+the N=64 sample (seconds instead of minutes), scaled by rows to C2.
 """
 import argparse
 import json
@@ -40,14 +44,18 @@ def parse():
     ap.add_argument("--cells", type=int, default=185, help="N cells per direction (C2: 185)")
     ap.add_argument("--numbering", type=int, default=1, help="1 = DROPS order (vertices, then edges)")
     ap.add_argument("--iters", type=int, default=200, help="PCG iterations per step (cdrdrops Iter = 200)")
-    ap.add_argument("--cpu-cells", type=int, default=64, help="brick size of the CPU sample")
-    ap.add_argument("--cpu-iters", type=int, default=25)
+    ap.add_argument("--cpu-cells", type=int, default=0,
+                    help="brick size of the CPU run; 0 = the reference arm runs --cells itself when the host has the "
+                         "memory (else N=64), our arm's cpu_baseline the N=64 sample")
+    ap.add_argument("--cpu-iters", type=int, default=25, help="PCG iterations per CPU step (upper bound)")
+    ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds the reference arm's timed steps may take")
     ap.add_argument("--no-host-matrix", action="store_true", help="skip the host CSR upload path in e2e")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-small", action="store_true", help="skip the side measurement of BASELINE configs[0]")
     ap.add_argument("--no-pk", action="store_true", help="12-byte SELL stream only (value dictionary off)")
     ap.add_argument("--no-general", action="store_true", help="skip the side measurement of the 12-byte stream")
     ap.add_argument("--no-solvers", action="store_true", help="skip the GMRES / MINRES side measurement on the C2 system")
+    ap.add_argument("--no-dist-parity", action="store_true", help="skip the convergence parity check of the N-rank path")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (repeatable)")
     return ap.parse_args()
 
@@ -106,22 +114,50 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
-def cpu_reference_run(cells, iters, fe, numbering, repeats=1, warm=0):
+def host_threads():
+    """All the host threads the reference may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    omp_get_max_threads() then reports: the reference arm sets the team size explicitly instead."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_reference_run(cells, iters, fe, numbering, repeats=1, warm=0, budget_s=None):
     """Times the reference's PCG+JACPcCL (oracle/_ref when built, else the plain-C oracle) on a
-    P2 brick of `cells` cells per direction.  Returns dict(rows, nnz, sec_per_iter, kind, cores)."""
+    P2 brick of `cells` cells per direction, every call a Solve of `iters` iterations with tol = 0.
+    budget_s: shrink `iters` (not below 2) so that warm + repeats calls fit the budget.
+    sec_per_iter excludes the Solve's own setup (r = b - A x, two norms, one Jacobi: timed once as a
+    Solve with max_iter = 0), which would otherwise weigh 1.5 iterations against the CPU in a 5-iteration
+    sample and nothing in our arm's 200-iteration steps.
+    Returns dict(rows, nnz, sec_per_iter, kind, cores, ...)."""
     from drops_b200 import capi
     from oracle import ref as oref
     n, rb, ci, va = capi.brick_csr_host(fe, cells, numbering)
     xs = capi.brick_solution_host(fe, cells, numbering)
+    nnz = len(va)
     if oref.available():
+        oref.set_num_threads(host_threads())
         kind, cores = "reference", oref.num_threads()
         A = oref.RefMatrix(n, n, rb, ci, va)
     else:
         from oracle import port
-        kind, cores = "port", int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+        os.environ["OMP_NUM_THREADS"] = str(host_threads())
+        kind, cores = "port", host_threads()
         A = port.PortMatrix(n, n, rb, ci, va)
+    del rb, ci, va
     b = A.spmv(xs)
     x0 = np.zeros(n)
+    A.pcg_jacobi_timed(x0, b, 0, 0.0, True, 1.0)                 # page in
+    t0 = time.perf_counter()
+    A.pcg_jacobi_timed(x0, b, 0, 0.0, True, 1.0)
+    setup_s = time.perf_counter() - t0
+    if budget_s is not None:
+        t0 = time.perf_counter()
+        A.pcg_jacobi_timed(x0, b, 2, 0.0, True, 1.0)
+        spi = max((time.perf_counter() - t0 - setup_s) / 2.0, 1e-9)
+        per_call = budget_s / max(warm + repeats, 1)
+        iters = int(max(2, min(iters, (per_call - setup_s) / spi)))
     times = []
     for r in range(warm + repeats):
         t0 = time.perf_counter()
@@ -137,9 +173,11 @@ def cpu_reference_run(cells, iters, fe, numbering, repeats=1, warm=0):
         t0 = time.perf_counter()
         A.spmv_raw(xin, y)
         best = min(best, time.perf_counter() - t0)
-    return {"rows": n, "nnz": len(va), "sec_per_iter": float(np.mean(times)) / iters, "kind": kind, "cores": cores,
+    loop = max(float(np.mean(times)) - setup_s, 1e-9)
+    return {"rows": n, "nnz": nnz, "iters": iters, "sec_per_iter": loop / iters, "kind": kind, "cores": cores,
+            "sec_per_iter_with_setup": float(np.mean(times)) / iters, "setup_s": setup_s,
             "times": times, "resid": res, "spmv_s": best,
-            "spmv_gbs_ref_layout": (16.0 * len(va) + 8.0 * (n + 1) + 16.0 * n) / best / 1e9}
+            "spmv_gbs_ref_layout": (16.0 * nnz + 8.0 * (n + 1) + 16.0 * n) / best / 1e9}
 
 
 def dist_setup(n_gpus):
@@ -174,29 +212,51 @@ def cells_for(args, world):
 # reference arm
 # ------------------------------------------------------------------------------------------------
 def run_reference(args):
+    """The reference arm: DROPS' own PCG + JACPcCL (compiled from /root/reference into oracle/_ref) on the host
+    cores.  libdrops_b200.so is mapped by this process ONLY for the host-side brick generator
+    (capi.brick_csr_host: plain C++ on the CPU, no CUDA call, GPU busy 0 %) that hands both arms the same system."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import psutil
     from drops_b200 import capi
     N = cells_for(args, max(args.gpus, 1))
     n_total, nnz_full = capi.brick_sizes(args.fe, N)
-    r = cpu_reference_run(args.cpu_cells, args.cpu_iters, args.fe, args.numbering,
-                          repeats=max(args.steps, 1), warm=max(args.warmup, 0))
-    # same unit as our arm: C2-equivalent iterations/s = row-iterations/s / rows(C2); the host CPUs do
-    # not grow with --gpus, so this is the same number at every N
-    unit_rows = C2_ROWS if (args.fe == 2 and args.cells == 185) else capi.brick_sizes(args.fe, args.cells)[0]
+    n_unit, nnz_unit = capi.brick_sizes(args.fe, args.cells)
+    unit_rows = C2_ROWS if (args.fe == 2 and args.cells == 185) else n_unit
+    # the configuration itself (C2 at 1 GPU: 23 GB in the reference's layout, twice while it is handed over) when the
+    # host can hold it; the host CPUs do not grow with --gpus, so at N > 1 the unit system (C2) is what they are timed on
+    cells_full = args.cpu_cells if args.cpu_cells > 0 else args.cells
+    need = 2 * (16 * nnz_unit + 8 * (n_unit + 1)) + 12 * 8 * n_unit + (6 << 30)
+    full = None
+    if args.cpu_cells <= 0 and psutil.virtual_memory().available < need:
+        cells_full = 64
+    r = cpu_reference_run(cells_full, args.cpu_iters, args.fe, args.numbering, repeats=max(args.steps, 1),
+                          warm=max(args.warmup, 0), budget_s=args.cpu_budget)
+    same_config = (cells_full == args.cells and args.gpus <= 1)
+    # same unit as our arm: C2-equivalent iterations/s = row-iterations/s / rows(C2)
     value = (r["rows"] / unit_rows) / r["sec_per_iter"]
-    sample = (f"P{args.fe} brick N={args.cpu_cells} ({r['rows']} rows, {r['nnz']} nnz), {args.cpu_iters} PCG-Jacobi "
-              f"iterations per step; row-iterations/s divided by {unit_rows} rows (one C2-sized iteration)")
+    sample = (f"P{args.fe} brick N={cells_full} ({r['rows']} rows, {r['nnz']} nnz), {r['iters']} PCG-Jacobi "
+              f"iterations per step, Solve setup ({r['setup_s']:.3f} s) subtracted; row-iterations/s divided by "
+              f"{unit_rows} rows (one C2-sized iteration)")
+    small = None
+    if cells_full != 64 and not args.no_small:
+        q = cpu_reference_run(64, 25, args.fe, args.numbering, repeats=2, warm=1)
+        small = {"cells": 64, "rows": q["rows"], "value_scaled_by_rows": (q["rows"] / unit_rows) / q["sec_per_iter"],
+                 "iterations_per_s": 1.0 / q["sec_per_iter"], "spmv_gbs_reference_layout": q["spmv_gbs_ref_layout"],
+                 "note": "the sample our own arm's cpu_baseline uses"}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(r["times"])),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"P{args.fe} Poisson, Kuhn brick N={N} ({n_total} rows) at {args.gpus} GPU(s), PCG + JACPcCL, "
                                f"tol=0; value in C2-equivalent iterations/s ({unit_rows} rows per unit)",
-                   "numbering": args.numbering, "cpu_sample_cells": args.cpu_cells},
+                   "numbering": args.numbering, "cpu_sample_cells": cells_full, "same_config": same_config,
+                   "native_library_note": "libdrops_b200.so is loaded for the host-side brick generator only "
+                                          "(no CUDA call in this arm)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample,
-                         "spmv_gbs_reference_layout": r["spmv_gbs_ref_layout"]},
+                         "same_config": same_config, "value_with_solve_setup": (r["rows"] / unit_rows) / r["sec_per_iter_with_setup"],
+                         "spmv_gbs_reference_layout": r["spmv_gbs_ref_layout"], "sample_n64": small},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -311,6 +371,56 @@ def run_ours(args):
         except Exception:
             pass
 
+    # ---- the plain products of the path (BASELINE metric: "SpMV HBM GB/s"): y = A x (operator*, spmat.h:1712-1724)
+    #      and y = A^T x (transp_mul, spmat.h:1748-1760; its operator is built on first use), hash input vector,
+    #      caller's numbering, CUDA events around `reps` back-to-back launches after 3 warm-up launches
+    products = {}
+    try:
+        xin, yout = capi.Vector(n), capi.Vector(n)
+        xin.fill_hash()
+        for name, fn in (("y_Ax", A.spmv_dev), ("y_ATx", A.spmv_transpose_dev)):
+            for _ in range(3):
+                fn(xin, yout)
+            capi.synchronize()
+            reps = 20
+            capi.timer_start()
+            for _ in range(reps):
+                fn(xin, yout)
+            pms = capi.timer_stop() / reps
+            vd_ = A.value_dictionary(transposed=(name == "y_ATx"))
+            eb = ((4.0 if vd_["packed"] else 6.0) if (vd_["packed"] or vd_["six_byte"]) and capi.get_option("spmv.pk", 1.0) != 0.0 else 12.0)
+            pb = eb * nnz + 4.0 * (n + 1) + 16.0 * n
+            products[name] = {"ms": pms, "bytes_per_stored_entry": eb, "algorithmic_bytes": pb,
+                              "achieved_gbs": pb / (pms / 1e3) / 1e9, "frac": pb / (pms / 1e3) / 1e9 / peak,
+                              "survey_12B_equivalent_gbs": survey_spmv_bytes / (pms / 1e3) / 1e9}
+        xin.close(); yout.close()
+    except Exception as exc:
+        products["error"] = repr(exc)
+    roofline["products"] = products
+
+    # ---- one C2 solve to convergence (tol = 1e-10 relative, krylovsolver.h:107-179): iteration count, the
+    #      recurrence residual the solver reports, the TRUE residual |b - A x| / |b| and the error against x*
+    convergence = None
+    try:
+        x.fill(0.0)
+        capi.synchronize(); capi.timer_start()
+        conv_c, it_c2, res_c2 = A.pcg_dev(x, b, 5000, 1e-10, True)
+        ms_c2 = capi.timer_stop()
+        zt = capi.Vector(n)
+        A.spmv_dev(x, zt)
+        capi.axpy(-1.0, b, zt)
+        true_res = capi.norm(zt) / capi.norm(b)
+        zt.copy_from(x)
+        capi.axpy(-1.0, xs, zt)
+        convergence = {"converged": bool(conv_c), "iterations": it_c2, "relative_residual": res_c2,
+                       "true_relative_residual": true_res, "relative_error_vs_xstar": capi.norm(zt) / capi.norm(xs),
+                       "solve_ms": ms_c2, "iterations_per_s": it_c2 / (ms_c2 / 1e3), "tol": 1e-10,
+                       "note": "x* = 64xyz(1-x)(1-y)(1-z) sampled at the DOFs, b = A x*, x0 = 0; the error against x* is the "
+                               "algebraic error of the iteration (b was built from x*), bounded by cond(A) x residual"}
+        zt.close()
+    except Exception as exc:
+        convergence = {"error": repr(exc)}
+
     # ---- the same solve on the general 12-byte stream (what a matrix without a value dictionary runs):
     #      a second handle built with the dictionary switched off -- caller's row order, int32 column + fp64 value
     general = None
@@ -394,10 +504,13 @@ def run_ours(args):
     # ---- CPU baseline (bounded sample on the host cores) ----------------------------------------
     cpu = None
     if not args.no_cpu:
-        r = cpu_reference_run(args.cpu_cells, args.cpu_iters, fe, numbering)
+        cc = args.cpu_cells if args.cpu_cells > 0 else 64
+        r = cpu_reference_run(cc, args.cpu_iters, fe, numbering)
         cpu = {"value": (r["rows"] / n) / r["sec_per_iter"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
-               "sample": f"P{fe} brick N={args.cpu_cells} ({r['rows']} rows, {r['nnz']} nnz), {args.cpu_iters} "
-                         f"PCG-Jacobi iterations, iterations/s scaled by rows {r['rows']}/{n} to C2",
+               "sample": f"P{fe} brick N={cc} ({r['rows']} rows, {r['nnz']} nnz), {r['iters']} "
+                         f"PCG-Jacobi iterations (Solve setup subtracted), iterations/s scaled by rows {r['rows']}/{n} to C2; "
+                         f"the reference arm (--impl reference) runs C2 itself",
+               "same_config": cc == N,
                "sample_iterations_per_s": 1.0 / r["sec_per_iter"],
                "spmv_gbs_reference_layout": r["spmv_gbs_ref_layout"]}
 
@@ -421,7 +534,8 @@ def run_ours(args):
                                 (", PCG on row-ordered vectors" if layout["row_ordered_stream"] and capi.get_option("pcg.reorder", 1.0) != 0.0 else ""),
                    "generate_s": gen_s},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        "final_relative_residual": resid, "general_12B_stream": general, "other_solvers_c2": solvers,
+        "final_relative_residual": resid, "c2_to_convergence": convergence, "general_12B_stream": general,
+        "other_solvers_c2": solvers,
         "other_configs": {"C1_p1_n64": c1},
     }
     print(json.dumps(line), flush=True)
@@ -504,6 +618,67 @@ def small_config_c1(args):
     return out
 
 
+def dist_parity_check(capi, partition, dist, comm, rank, world, fe, numbering, tmax):
+    """PCG-Jacobi to convergence on a z-slab partition over the N ranks (peer-to-peer halo + reductions, the path
+    the timed steps run) against the single-GPU solve of the same brick that every rank runs for itself:
+    iteration counts (north star: +-1), relative difference of the solutions on the rank's own rows (<= 1e-10),
+    SpMV rows bit-identical.  Returns the record rank 0 prints as "dist_parity"."""
+    import hashlib
+    import torch
+    Np = 64
+    while (2 * Np - 1) ** 3 < 2.1e6 * world:
+        Np += 1
+    n, nnz = capi.brick_sizes(fe, Np)
+    slab, ex, A = partition.brick_partition(fe, Np, numbering, rank, world, comm, dist)
+    owned = slab.owned()
+    G = capi.Matrix.brick(fe, Np, numbering)
+    xs_g, b_g, x_g = capi.Vector(n), capi.Vector(n), capi.Vector(n)
+    capi.brick_solution_device(fe, Np, numbering, xs_g)
+    G.spmv_dev(xs_g, b_g)
+    x_g.fill(0.0)
+    conv1, it1, res1 = G.pcg_dev(x_g, b_g, 5000, 1e-10, True)
+    x1 = x_g.download()[owned]
+    b1 = b_g.download()[owned]
+    xs_l, b_l, x_l = capi.Vector(owned.size), capi.Vector(owned.size), capi.Vector(owned.size)
+    slab.solution(xs_l)
+    capi.dist_spmv([A], [xs_l], [b_l])
+    spmv_equal = bool(np.array_equal(b_l.download(), b1))
+    x_l.fill(0.0)
+    convn, itn, resn = capi.dist_pcg([A], [x_l], [b_l], 5000, 1e-10, True)
+    xn = x_l.download()
+    num, den = float(np.sum((xn - x1) ** 2)), float(np.sum(x1 ** 2))
+    t = torch.tensor([num, den], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    rel_diff = float(torch.sqrt(t[0] / t[1]).item())
+    fmt = A.format()
+    flags = torch.tensor([float(spmv_equal), float(convn and conv1), float(itn), float(it1), float(np.array_equal(xn, x1)),
+                          float(bool(fmt.get("p2p_fault")))], dtype=torch.float64, device="cuda")
+    fl = [torch.zeros_like(flags) for _ in range(world)]
+    dist.all_gather(fl, flags)
+    fl = torch.stack(fl).cpu().numpy()
+    h = hashlib.sha256(xn.tobytes()).hexdigest()[:16]
+    h1 = hashlib.sha256(x1.tobytes()).hexdigest()[:16]
+    hashes = [None] * world
+    dist.all_gather_object(hashes, (h, h1))
+    rec = {"workload": f"P{fe} brick N={Np}, {n} rows ({n / world:.0f} per rank), PCG + JACPcCL to tol 1e-10 relative, x0 = 0",
+           "iterations_dist": int(itn), "iterations_single_gpu": int(it1),
+           "iterations_equal_on_all_ranks": bool((fl[:, 2] == fl[0, 2]).all()),
+           "relative_residual_dist": resn, "relative_residual_single_gpu": res1,
+           "solution_rel_diff": rel_diff, "solution_bits_equal_ranks": int(fl[:, 4].sum()),
+           "spmv_rows_bit_identical_ranks": int(fl[:, 0].sum()), "converged_ranks": int(fl[:, 1].sum()),
+           "p2p_fault_ranks": int(fl[:, 5].sum()), "ranks": world,
+           "solution_sha256_16_per_rank_dist_vs_single": hashes,
+           "format_rank0": fmt,
+           "ok": bool((fl[:, 0] == 1).all() and (fl[:, 1] == 1).all() and (np.abs(fl[:, 2] - fl[:, 3]) <= 1).all()
+                      and rel_diff <= 1e-10 and fl[:, 5].sum() == 0)}
+    for v in (xs_g, b_g, x_g, xs_l, b_l, x_l):
+        v.close()
+    G.close(); A.close(); slab.close(); ex.close()
+    capi.synchronize()
+    dist.barrier()
+    return rec
+
+
 def run_ours_dist(args, rank, world, local, dist):
     """N > 1: the brick grows with N (weak scaling, ~50 M rows per GPU; N = 8 is BASELINE config 5, the
     400 M-DOF system), z-slab row partition, one process per GPU, halo + reductions over NCCL."""
@@ -539,6 +714,13 @@ def run_ours_dist(args, rank, world, local, dist):
         t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return t.item()
+
+    # ---- parity of the partitioned path on THIS box, before anything is timed: a brick with ~2.1 M rows per rank
+    #      (the size at which the production defaults -- graph blocks, row-ordered twins, byte diagonal -- switch on by
+    #      themselves in every partition) solved to tol = 1e-10 on the N ranks and, by every rank for itself, on one GPU
+    dist_parity = None
+    if not args.no_dist_parity:
+        dist_parity = dist_parity_check(capi, partition, dist, comm, rank, world, fe, numbering, tmax)
 
     for _ in range(args.warmup):
         solve_dev()
@@ -636,7 +818,7 @@ def run_ours_dist(args, rank, world, local, dist):
                        "cache": "per-GPU inputs (17 GB matrix, 0.4 GB vectors) far exceed the 126 MB L2; no flush needed",
                        "partition": {"ghost_entries_total": ghosts, "rank0": info, "rank0_format": fmt}, "generate_s": gen_s},
             "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "final_relative_residual": resid,
+            "final_relative_residual": resid, "dist_parity": dist_parity,
         }
         print(json.dumps(line), flush=True)
     dist.barrier()

@@ -264,6 +264,13 @@ __global__ void k_dist_scalars(int phase, SolverScalars* S, double* hist, const 
         }
         __threadfence_system();
         __syncthreads();
+        // a peer never showed up: its partial is stale.  Stop iterating on this rank (every later kernel of the
+        // solve returns on S->done) and leave the sticky fault flag for the host, which turns it into
+        // DROPS_B200_E_COMM (check_p2p_faults) instead of a plausible-looking residual.
+        if (*(volatile int*)fault != 0) {
+            if (threadIdx.x == 0 && S != nullptr) { S->done = 1; S->converged = 0; }
+            return;
+        }
     }
     if (threadIdx.x != 0) return;
     const int nq = phase == PH_SETUP ? 3 : (phase == PH_UPDATE ? 2 : 1);
@@ -429,9 +436,11 @@ __global__ void k_extract_diag_local(long long rows, const int64_t* __restrict__
     else { diag[i] = 0.0; atomicExch(missing, 1); }
 }
 
-// Builds the partition operator from device-resident rows with global column ids.
-int dist_matrix_build(drops_b200_comm_s* comm, drops_b200_exchange_s* E, size_t nnz, const int64_t* d_rowptr,
-                      const int64_t* d_colgid, const double* d_val, uint64_t version, drops_b200_dist_matrix_s** out)
+// Builds the partition operator from device-resident rows with global column ids: the rank-local part
+// (every failure exit in here is this rank's alone -- dist_matrix_build agrees on the outcome across the
+// ranks before anything collective happens).
+static int dist_matrix_build_local(drops_b200_comm_s* comm, drops_b200_exchange_s* E, size_t nnz, const int64_t* d_rowptr,
+                                   const int64_t* d_colgid, const double* d_val, uint64_t version, drops_b200_dist_matrix_s** out)
 {
     *out = nullptr;
     DB_ARG(comm != nullptr && E != nullptr, "null comm/exchange");
@@ -513,6 +522,8 @@ int dist_matrix_build(drops_b200_comm_s* comm, drops_b200_exchange_s* E, size_t 
             DM_CHECK(s2);
         } else {
             k_iota32<<<blocks_for((long long)n, 256), 256, 0, st>>>((long long)n, rows_all);
+            count_launch();
+            DM_CUDA(cudaGetLastError());
         }
         size_t tb = 0;
         DM_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, rows_all, f_int, rows_int, d_cnt, (long long)n, st));
@@ -618,13 +629,37 @@ int dist_matrix_build(drops_b200_comm_s* comm, drops_b200_exchange_s* E, size_t 
     cleanup();
 #undef DM_CHECK
 #undef DM_CUDA
+    *out = M;
+    return 0;
+}
+
+int dist_matrix_build(drops_b200_comm_s* comm, drops_b200_exchange_s* E, size_t nnz, const int64_t* d_rowptr,
+                      const int64_t* d_colgid, const double* d_val, uint64_t version, drops_b200_dist_matrix_s** out)
+{
+    drops_b200_dist_matrix_s* M = nullptr;
+    const int s = dist_matrix_build_local(comm, E, nnz, d_rowptr, d_colgid, d_val, version, &M);
+    *out = nullptr;
+    if (comm == nullptr) return s;
     if (comm->kind == COMM_LOCAL) {
+        if (s < 0) return s;
         if ((int)comm->parts.size() < comm->world) comm->parts.resize((size_t)comm->world, nullptr);
         comm->parts[(size_t)M->rank] = M;
-    } else {
-        const int ps = p2p_setup_nccl(M);          // collective; failure to map peers is not an error
-        if (ps < 0) { free_dist_matrix(M); return ps; }
+        *out = M;
+        return 0;
     }
+    // NCCL transport: the peer mapping below is collective (an all-gather of IPC handles).  A rank whose local build
+    // failed (unknown column id, out of memory) must not leave the others blocked in it: agree on the outcome first.
+    double bad = s < 0 ? 1.0 : 0.0;
+    const int sa = drops_b200_comm_allreduce_max(comm, &bad);
+    if (s < 0) return s;                           // this rank's own error text stands
+    if (sa < 0) { free_dist_matrix(M); return sa; }
+    if (bad != 0.0) {
+        free_dist_matrix(M);
+        set_error("dist_matrix: the build of the partition failed on another rank");
+        return DROPS_B200_E_COMM;
+    }
+    const int ps = p2p_setup_nccl(M);              // collective; failure to map peers is not an error
+    if (ps < 0) { free_dist_matrix(M); return ps; }
     *out = M;
     return 0;
 }
@@ -946,6 +981,30 @@ static int scalars_kernel(int phase, drops_b200_dist_matrix_s* M, double* hist, 
     return 0;
 }
 
+// The bounded peer-to-peer waits (k_halo_wait, k_dist_scalars) never hang the GPU: after 2^26 spins they give up and
+// raise a sticky device flag.  Every solver entry point reads the flags before it returns; a set flag means ghost
+// values or reduction partials of some step were stale (stalled host, crashed rank), so the solve is reported as
+// failed -- on this rank; the peers run into their own time-outs.
+static int check_p2p_faults(int np, drops_b200_dist_matrix_s* const* P)
+{
+    cudaStream_t st = ctx().stream;
+    int* h = reinterpret_cast<int*>(ctx().h_scalars + 24);       // pinned
+    int n = 0;
+    for (int p = 0; p < np; ++p)
+        if (P[p]->p2p_fault) DB_CUDA(cudaMemcpyAsync(h + n++, P[p]->p2p_fault, sizeof(int), cudaMemcpyDeviceToHost, st));
+    const int n_halo = n;
+    if (P[0]->comm->red_fault) DB_CUDA(cudaMemcpyAsync(h + n++, P[0]->comm->red_fault, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (n == 0) return 0;
+    DB_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; ++i)
+        if (h[i] != 0) {
+            set_error("peer-to-peer %s timed out: a rank of the partition stalled or died; the result of this solve is invalid",
+                      i < n_halo ? "halo wait" : "reduction wait");
+            return DROPS_B200_E_COMM;
+        }
+    return 0;
+}
+
 int dist_pcg(int np, drops_b200_dist_matrix_s* const* P, double* const* x, const double* const* b, int pc, double omega,
              int* max_iter, double* tol, int relative, double* hist, int hist_cap)
 {
@@ -1095,6 +1154,7 @@ int dist_pcg(int np, drops_b200_dist_matrix_s* const* P, double* const* x, const
     DB_CUDA(cudaMemcpyAsync(&h, S[0], sizeof h, cudaMemcpyDeviceToHost, st));
     DB_CUDA(cudaStreamSynchronize(st));
     if (comm->comm_stream) DB_CUDA(cudaStreamSynchronize(comm->comm_stream));
+    DB_CHECK(check_p2p_faults(np, P));
     if (hist && want_hist > 0) {
         const int cnt = std::min(want_hist, h.iter + 1);
         DB_CUDA(cudaMemcpyAsync(hist, P[0]->d_hist, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1278,6 +1338,7 @@ int dist_gmres(int np, drops_b200_dist_matrix_s* const* P, double* const* x, con
             gm_app_rot(Hat(i, i), Hat(i + 1, i), cs[(size_t)i], sn[(size_t)i]);
             gm_app_rot(s[(size_t)i], s[(size_t)i + 1], cs[(size_t)i], sn[(size_t)i]);
             resid = std::abs(s[(size_t)i + 1]) / normb;                       // :393
+            DB_CHECK(check_p2p_faults(np, P));                                // a stale column must not steer the rotations
             if (resid <= *tol) {                                              // :413-429
                 DB_CHECK(update_x(i));
                 *tol = resid; *max_iter = j;
@@ -1288,6 +1349,7 @@ int dist_gmres(int np, drops_b200_dist_matrix_s* const* P, double* const* x, con
         DB_CHECK(residual());
         DB_CHECK(norm_of(&Part::r, 0));
         DB_CHECK(fetch_host(W[0].d_scal, c.h_scalars, 1));
+        DB_CHECK(check_p2p_faults(np, P));
         beta = c.h_scalars[0];
         resid = beta / normb;
         if (resid <= *tol) { *tol = resid; *max_iter = j; return 1; }         // :449-456

@@ -1118,3 +1118,46 @@ def test_full_size_c2_properties(gpu):
     assert abs(true_res - res) <= 1e-8 * max(res, 1e-300) + 1e-13
     gpu.axpy(-1.0, y, x)
     assert gpu.norm(x) < gpu.norm(y)
+
+
+# ---------------------------------------------------------------------------------------------
+# production defaults against the compiled reference: P2 N=64 (2 048 383 rows) is the first size
+# of BASELINE.md's parity set at which "sell.block_min_rows" (2e6) switches the block order, the
+# row-ordered PCG, the U15/384 fused-dot kernel and the diagonal byte index on BY THEMSELVES.
+# No option is touched here; the oracle is oracle/_ref (the unmodified reference headers), with
+# the plain-C restatement (bit-identical to it, tests/test_oracle.py) as the stand-in on a box
+# where _ref was not built.  PCG: num/krylovsolver.h:107-179.
+# ---------------------------------------------------------------------------------------------
+def test_production_defaults_parity_p2_n64(gpu, port):
+    from oracle import ref as oref
+    fe, N, numbering = 2, 64, 1
+    n, rb, ci, va = gpu.brick_csr_host(fe, N, numbering)
+    assert n == 2048383
+    if oref.available():
+        oref.set_num_threads(max(1, __import__("os").cpu_count() or 1))
+        R = oref.RefMatrix(n, n, rb, ci, va)
+    else:
+        R = port.PortMatrix(n, n, rb, ci, va)
+    G = gpu.Matrix(n, n, rb, ci, va)               # host upload path, the reference's own layout
+    lay = G.layout()
+    assert lay["block_ordered"] and lay["row_ordered_stream"], lay
+    vd = G.value_dictionary()
+    assert vd["packed"] and 0 < vd["n_distinct"] <= 47, vd
+    xin = hash_vector(n)
+    assert np.array_equal(G.spmv(xin), R.spmv(xin))
+    assert np.array_equal(G.spmv_transpose(xin), R.spmv_transpose(xin))
+    xs = gpu.brick_solution_host(fe, N, numbering)
+    b = R.spmv(xs)
+    ref = R.pcg_jacobi(np.zeros(n), b, 5000, 1e-10, True)
+    out = G.pcg_jacobi(np.zeros(n), b, 5000, 1e-10, True)
+    assert ref[0] and out[0]
+    assert abs(out[1] - ref[1]) <= 1, (out[1], ref[1])
+    assert rel(out[3], ref[3]) <= X_RTOL
+    assert G.diag_index() > 0                      # the update kernel read d as one byte per row
+    # true residual of the GPU solution, evaluated by the reference
+    assert np.linalg.norm(b - R.spmv(out[3])) / np.linalg.norm(b) <= 2e-10
+    # the same defaults on the device-generated operator (what bench.py times) give the same bits
+    D = gpu.Matrix.brick(fe, N, numbering)
+    assert D.layout()["block_ordered"]
+    out2 = D.pcg_jacobi(np.zeros(n), b, 5000, 1e-10, True)
+    assert out2[1] == out[1] and np.array_equal(out2[3], out[3])
