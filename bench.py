@@ -521,6 +521,13 @@ def run_ours(args):
         except Exception as exc:      # the headline line must survive a failure of the side measurement
             c1 = {"error": repr(exc)}
 
+    exe0 = None
+    if not args.no_small:
+        try:
+            exe0 = cdrdrops_config0(args)
+        except Exception as exc:
+            exe0 = {"error": repr(exc)}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -536,7 +543,7 @@ def run_ours(args):
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "final_relative_residual": resid, "c2_to_convergence": convergence, "general_12B_stream": general,
         "other_solvers_c2": solvers,
-        "other_configs": {"C1_p1_n64": c1},
+        "other_configs": {"C1_p1_n64": c1, "C1_cdrdrops_executable": exe0},
     }
     print(json.dumps(line), flush=True)
 
@@ -576,6 +583,41 @@ def other_solvers(capi, A, x, b, n, nnz, entry_bytes, peak):
     out["minres"] = {"iterations": it, "iterations_per_s": it / (ms / 1e3), "ms_per_iteration": ms / max(it, 1),
                      "relative_residual": res, "survey_bytes_per_iteration": mat + 15.0 * 8.0 * n,
                      "survey_gbs": mr_bytes / (ms / 1e3) / 1e9, "survey_frac": mr_bytes / (ms / 1e3) / 1e9 / peak}
+    return out
+
+
+def cdrdrops_config0(args):
+    """BASELINE configs[0] as the reference runs it: its own executable cdrdrops (poisson/cdrdrops.cpp -- BrickBuilderCL
+    4x4x4, 4 uniform refinements, DROPS' P1 assembly, PoissonSolverFactoryCL code 202 = PCGSolverCL<JACPcCL> and 302 =
+    GMResSolverCL<JACPcCL>, Tol 1e-10) built from the UNMODIFIED sources twice (tests/cxx/drops_exe/Makefile): with the
+    overlay headers + libdrops_b200.so (our arm: the call a DROPS user makes) and against the reference headers
+    (oracle/_ref/drops_exe, the CPU baseline leg, all host cores).  `solve_s` is the time cdrdrops itself prints around
+    solver.Solve (cdrdrops.cpp:117-119): host vectors in, host vectors out, first-use matrix upload included."""
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests", "cxx", "drops_exe"))
+    import cases
+    out = {}
+    env = dict(os.environ, OMP_NUM_THREADS=str(host_threads()))
+    with tempfile.TemporaryDirectory() as tmp:
+        for case in ("c1_p1_pcg_jac", "c1_p1_gmres_jac"):
+            rec = {}
+            for variant in ("b200", "ref"):
+                if variant == "ref" and args.no_cpu:
+                    continue
+                if not os.path.exists(cases.exe(variant)):
+                    rec[variant] = {"unavailable": "binary not built (needs the DROPS source tree at build time)"}
+                    continue
+                if variant == "b200":
+                    cases.run(variant, case, os.path.join(tmp, variant), env=env)       # warm-up: CUDA context, page-in
+                _, r = cases.run(variant, case, os.path.join(tmp, variant), env=env)
+                rec[variant] = {"unknowns": r["unknowns"], "iterations": r["iterations"], "residuum": r["residuum"],
+                                "real_residuum": r["real_residuum"], "l2_error_vs_known_solution": r["l2_error"],
+                                "solve_s": r["solve_time_s"],
+                                "iterations_per_s": r["iterations"] / r["solve_time_s"] if r["solve_time_s"] else None}
+            if "solve_s" in rec.get("b200", {}) and "solve_s" in rec.get("ref", {}):
+                rec["solve_speedup"] = rec["ref"]["solve_s"] / rec["b200"]["solve_s"]
+                rec["ref_cores"] = host_threads()
+            out[case] = rec
     return out
 
 

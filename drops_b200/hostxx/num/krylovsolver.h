@@ -20,6 +20,7 @@
 #define DROPS_B200_OVERLAY_NUM_KRYLOVSOLVER_H
 
 #include "num/spmat.h"
+#include "num/precond.h"            // the preconditioner types the overloads below are written for
 #include_next "num/krylovsolver.h"
 
 #include <cstring>

@@ -25,6 +25,7 @@
 
 #include_next "num/spmat.h"
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
