@@ -521,12 +521,20 @@ def run_ours(args):
         except Exception as exc:      # the headline line must survive a failure of the side measurement
             c1 = {"error": repr(exc)}
 
-    exe0 = None
+    exe0 = c3 = c4 = None
     if not args.no_small:
         try:
             exe0 = cdrdrops_config0(args)
         except Exception as exc:
             exe0 = {"error": repr(exc)}
+        try:
+            c3 = config_c3_levelset(args)
+        except Exception as exc:
+            c3 = {"error": repr(exc)}
+        try:
+            c4 = config_c4_interface(args)
+        except Exception as exc:
+            c4 = {"error": repr(exc)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
@@ -543,7 +551,8 @@ def run_ours(args):
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "final_relative_residual": resid, "c2_to_convergence": convergence, "general_12B_stream": general,
         "other_solvers_c2": solvers,
-        "other_configs": {"C1_p1_n64": c1, "C1_cdrdrops_executable": exe0},
+        "other_configs": {"C1_p1_n64": c1, "C1_cdrdrops_executable": exe0, "C3_levelset_gmres_jacobi": c3,
+                          "C4_interface_pcg_jacobi": c4},
     }
     print(json.dumps(line), flush=True)
 
@@ -597,7 +606,7 @@ def cdrdrops_config0(args):
     sys.path.insert(0, os.path.join(ROOT, "tests", "cxx", "drops_exe"))
     import cases
     out = {}
-    env = dict(os.environ, OMP_NUM_THREADS=str(host_threads()))
+    env = dict(os.environ, OMP_NUM_THREADS=str(host_threads()), DROPS_B200_TRACE="1")
     with tempfile.TemporaryDirectory() as tmp:
         for case in ("c1_p1_pcg_jac", "c1_p1_gmres_jac"):
             rec = {}
@@ -614,11 +623,152 @@ def cdrdrops_config0(args):
                                 "real_residuum": r["real_residuum"], "l2_error_vs_known_solution": r["l2_error"],
                                 "solve_s": r["solve_time_s"],
                                 "iterations_per_s": r["iterations"] / r["solve_time_s"] if r["solve_time_s"] else None}
+                if variant == "b200" and r.get("trace"):
+                    # what the process paid once inside that first Solve, and the solve proper
+                    tr = r["trace"]
+                    rec[variant]["trace_s"] = tr
+                    solve = [v for k, v in tr.items() if "solve" in k]
+                    if solve:
+                        rec[variant]["solve_proper_s"] = solve[0]
+                        rec[variant]["iterations_per_s_solve_proper"] = r["iterations"] / solve[0]
             if "solve_s" in rec.get("b200", {}) and "solve_s" in rec.get("ref", {}):
-                rec["solve_speedup"] = rec["ref"]["solve_s"] / rec["b200"]["solve_s"]
+                rec["solve_speedup_as_printed"] = rec["ref"]["solve_s"] / rec["b200"]["solve_s"]
+                if "solve_proper_s" in rec["b200"]:
+                    rec["solve_speedup_without_one_time_costs"] = rec["ref"]["solve_s"] / rec["b200"]["solve_proper_s"]
                 rec["ref_cores"] = host_threads()
             out[case] = rec
     return out
+
+
+def _timed_solve(capi, fn, reps=3):
+    """Best-of-reps device time (CUDA events on the solver stream) and the launch count of one solve."""
+    best, out, launches = 1e30, None, 0
+    for _ in range(reps):
+        capi.synchronize()
+        l0 = capi.launch_count()
+        capi.timer_start()
+        out = fn()
+        ms = capi.timer_stop()
+        launches = capi.launch_count() - l0
+        best = min(best, ms)
+    return best, out, launches
+
+
+def config_c3_levelset(args):
+    """BASELINE configs[2] stand-in (twophasedrops, level-set advection L = E/dt + theta H, levelset/coupling.tpp:95-104:
+    nonsymmetric, P2 pattern, ~10^5 rows, GMResSolverCL<JACPcCL> with restart 200, twophasedrops.cpp:332-338).  The
+    executable itself needs the two-phase assembly; the stand-in is the P2 brick pattern at N = 24 (103 823 rows) with the
+    strict upper triangle scaled by 1.1 (convection) and the diagonal by 1.25 ("mass-dominated": few iterations, what the
+    real system looks like at dt = 3e-4) or 1.05 (a harder system that runs through a restart).  Reported per system:
+    iterations, us per inner step, kernel launches per step for the serial reference's modified Gram-Schmidt and for the
+    fused classical Gram-Schmidt of the reference's distributed ModGMRES ("gmres.ortho" = 1), host-buffer call included,
+    and the compiled reference on the host cores beside it.  These systems are launch-latency-bound on a GPU."""
+    from oracle import ref as oref
+    N, restart, tol = 24, 200, 1e-10
+    out = {"rows": None, "restart": restart, "tol": tol}
+    for tag, shift in (("mass_dominated_diag_x1.25", 1.25), ("harder_diag_x1.05", 1.05)):
+        n, rb, ci, va = capi_mod().brick_csr_host(2, N, 1, 1.1)
+        capi = capi_mod()
+        rows = np.repeat(np.arange(n), np.diff(rb.astype(np.int64)))
+        va = va.copy()
+        va[ci.astype(np.int64) == rows] *= shift
+        G = capi.Matrix(n, n, rb, ci, va)
+        xs = capi.brick_solution_host(2, N, 1)
+        b = G.spmv(xs)
+        xd, bd = capi.Vector(n), capi.Vector.from_host(b)
+        rec = {"nnz": int(len(va))}
+        out["rows"] = n
+        for name, ortho in (("modified_gram_schmidt", 0), ("classical_gram_schmidt_fused", 1)):
+            capi.set_option("gmres.ortho", ortho)
+
+            def solve():
+                xd.fill(0.0)
+                return G.gmres_dev(xd, bd, restart, 3000, tol, True)
+            solve()
+            ms, (conv, it, res), launches = _timed_solve(capi, solve)
+            t0 = time.perf_counter()
+            hconv = G.gmres_jacobi(np.zeros(n), b, restart, 3000, tol, True, 1.0, True)       # host buffers in and out
+            host_ms = 1e3 * (time.perf_counter() - t0)
+            x = xd.download()
+            rec[name] = {"converged": bool(conv), "iterations": it, "relative_residual": res, "solve_ms": ms,
+                         "us_per_inner_step": 1e3 * ms / max(it, 1), "launches_per_step": launches / max(it, 1),
+                         "iterations_per_s": it / (ms / 1e3), "host_buffer_call_ms": host_ms,
+                         "error_vs_xstar": float(np.linalg.norm(x - xs) / np.linalg.norm(xs)),
+                         "host_call_iterations": hconv[1]}
+        capi.set_option("gmres.ortho", 0)
+        if oref.available() and not args.no_cpu:
+            oref.set_num_threads(host_threads())
+            R = oref.RefMatrix(n, n, rb, ci, va)
+            t0 = time.perf_counter()
+            ro = R.gmres_jacobi(np.zeros(n), b, restart, 3000, tol, True, 1.0, True)
+            dt = time.perf_counter() - t0
+            rec["reference_cpu"] = {"converged": bool(ro[0]), "iterations": int(ro[1]), "relative_residual": ro[2], "solve_ms": 1e3 * dt,
+                                    "us_per_inner_step": 1e6 * dt / max(ro[1], 1), "cores": oref.num_threads(),
+                                    "x_rel_diff_vs_gpu_mgs": float(np.linalg.norm(ro[3] - x) / np.linalg.norm(ro[3]))}
+        out[tag] = rec
+        G.close()
+    return out
+
+
+def config_c4_interface(args):
+    """BASELINE configs[3] stand-in (surfactant, TraceFEM P1 on the tetrahedra cut by a sphere, CG + Jacobi, Iter 1000,
+    Tol 1e-9, param/surfactant/surfactant/surfactant.json:61-67): the P1 brick stiffness restricted to the DOFs within 2h
+    of the sphere |p - c| = 0.3 (irregular row lengths, numbering by first encounter = brick order) + 1e-3 on the diagonal,
+    N = 150 cells per direction -> ~10^5 rows.  PCGSolverCL<JACPcCL>, device-resident and through host buffers, with the
+    compiled reference beside it."""
+    import scipy.sparse as sp
+    from oracle import ref as oref
+    capi = capi_mod()
+    N = 150
+    n, rb, ci, va = capi.brick_csr_host(1, N, 0)
+    A = sp.csr_matrix((va, ci.astype(np.int64), rb.astype(np.int64)), shape=(n, n))
+    M = N - 1
+    idx = np.arange(n)
+    p = np.stack([idx % M + 1, (idx // M) % M + 1, idx // (M * M) + 1], 1) / N
+    keep = np.abs(np.linalg.norm(p - 0.5, axis=1) - 0.3) < 2.0 / N
+    S = A[keep][:, keep].tocsr()
+    S.sort_indices()
+    m = S.shape[0]
+    S.data[S.indices == np.repeat(np.arange(m), np.diff(S.indptr))] += 1e-3
+    del A
+    G = capi.Matrix(m, m, S.indptr, S.indices, S.data)
+    b = G.spmv(np.ones(m))
+    xd, bd = capi.Vector(m), capi.Vector.from_host(b)
+    lens = np.diff(S.indptr)
+    out = {"rows": int(m), "nnz": int(S.nnz), "row_lengths": {"min": int(lens.min()), "max": int(lens.max()), "distinct": int(len(set(lens)))},
+           "value_dictionary": G.value_dictionary(), "tol": 1e-9}
+    for graph in (1, 0):
+        capi.set_option("pcg.graph", graph)
+
+        def solve():
+            xd.fill(0.0)
+            return G.pcg_dev(xd, bd, 1000, 1e-9, True)
+        solve()
+        ms, (conv, it, res), launches = _timed_solve(capi, solve)
+        out["graph_replay" if graph else "eager"] = {"converged": bool(conv), "iterations": it, "relative_residual": res, "solve_ms": ms,
+                                                    "us_per_iteration": 1e3 * ms / max(it, 1), "iterations_per_s": it / (ms / 1e3),
+                                                    "launches_per_iteration": launches / max(it, 1)}
+    capi.set_option("pcg.graph", 1)
+    t0 = time.perf_counter()
+    h = G.pcg_jacobi(np.zeros(m), b, 1000, 1e-9, True)
+    out["host_buffer_call_ms"] = 1e3 * (time.perf_counter() - t0)
+    if oref.available() and not args.no_cpu:
+        oref.set_num_threads(host_threads())
+        R = oref.RefMatrix(m, m, S.indptr, S.indices, S.data)
+        R.pcg_jacobi(np.zeros(m), b, 5, 1e-9, True)
+        t0 = time.perf_counter()
+        ro = R.pcg_jacobi(np.zeros(m), b, 1000, 1e-9, True)
+        dt = time.perf_counter() - t0
+        out["reference_cpu"] = {"converged": bool(ro[0]), "iterations": int(ro[1]), "relative_residual": ro[2], "solve_ms": 1e3 * dt,
+                                "iterations_per_s": ro[1] / dt, "cores": oref.num_threads(),
+                                "x_rel_diff_vs_gpu": float(np.linalg.norm(ro[3] - h[3]) / np.linalg.norm(ro[3]))}
+    G.close()
+    return out
+
+
+def capi_mod():
+    from drops_b200 import capi
+    return capi
 
 
 def small_config_c1(args):

@@ -48,14 +48,13 @@ SIGNATURES = {
     "drops_b200_timer_stop": (_i, [_dpp]),
     "drops_b200_launch_count": (C.c_longlong, []),
     "drops_b200_synchronize": (_i, []),
-    "drops_b200_spmv_tma_fault": (_i, []),
     "drops_b200_matrix_create": (_i, [_sz, _sz, _sz, _szp, _szp, _dp, C.c_uint64, _vpp]),
     "drops_b200_matrix_create_device": (_i, [_sz, _sz, _sz, _vp, _vp, _vp, C.c_uint64, _vpp]),
     "drops_b200_matrix_update_values": (_i, [_vp, _dp, C.c_uint64]),
     "drops_b200_matrix_lincomb": (_i, [_d, _vp, _d, _vp, C.c_uint64, _vpp]),
     "drops_b200_matrix_destroy": (_i, [_vp]),
     "drops_b200_matrix_info": (_i, [_vp, _szpp, _szpp, _szpp, C.POINTER(C.c_uint64), _szpp, _szpp]),
-    "drops_b200_matrix_format": (_i, [_vp, _szpp, _szpp, _ip, _szpp]),
+    "drops_b200_matrix_format": (_i, [_vp, _szpp, _szpp]),
     "drops_b200_matrix_value_dictionary": (_i, [_vp, _i, _ip, _ip, _ip]),
     "drops_b200_matrix_layout": (_i, [_vp, _ip, _ip]),
     "drops_b200_matrix_diag_index": (_i, [_vp, _ip]),
@@ -233,10 +232,6 @@ def launch_count():
     return int(lib().drops_b200_launch_count())
 
 
-def spmv_tma_fault():
-    return int(lib().drops_b200_spmv_tma_fault())
-
-
 def synchronize():
     check(lib().drops_b200_synchronize())
 
@@ -392,15 +387,14 @@ class Matrix:
                 "device_bytes": db.value, "padded_nnz": pn.value}
 
     def format(self):
-        ns, pn, ws = C.c_size_t(), C.c_size_t(), C.c_size_t()
-        cmp_ = C.c_int()
-        check(lib().drops_b200_matrix_format(self.h, C.byref(ns), C.byref(pn), C.byref(cmp_), C.byref(ws)))
-        return {"nslices": ns.value, "padded_nnz": pn.value, "compressed": bool(cmp_.value), "wide_slices": ws.value}
+        ns, pn = C.c_size_t(), C.c_size_t()
+        check(lib().drops_b200_matrix_format(self.h, C.byref(ns), C.byref(pn)))
+        return {"nslices": ns.value, "padded_nnz": pn.value}
 
     def layout(self):
         bo, ro = C.c_int(), C.c_int()
         check(lib().drops_b200_matrix_layout(self.h, C.byref(bo), C.byref(ro)))
-        return {"block_ordered": bool(bo.value), "row_ordered_stream": bool(ro.value)}
+        return {"block_ordered": bool(bo.value), "row_ordered_stream": bool(ro.value), "row_ordered_kind": ro.value}
 
     def diag_index(self):
         """Length of the diagonal's value list when PCG reads the Jacobi diagonal as one byte per row (0: fp64 vector)."""

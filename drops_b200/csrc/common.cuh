@@ -308,14 +308,6 @@ struct SellOp {
     int32_t* perm = nullptr;         // sorted position -> original row, -1 beyond rows
     int max_width = 0;
     bool full_rows = true;           // built over all rows of the CSR (false: a row subset, dist.cu)
-    // 16-bit column deltas ("sell.compress"): entry j of the 32 rows of a slice are neighbouring
-    // rows with the same stencil, so their columns lie within 2^16 of each other: col = cbase[slice
-    // entry j] + col16 (0xFFFF = padding).  Slices where that fails are flagged wide and keep using
-    // col.  10.1 instead of 12 bytes per stored entry on the stream that bounds the kernel.
-    uint16_t* col16 = nullptr;       // padded entries, or nullptr when compression is off
-    int32_t* cbase = nullptr;        // padded/32 entries
-    uint8_t* wide = nullptr;         // nslices flags
-    size_t nwide = 0;
     // Value dictionary ("sell.valdict"): constant-coefficient systems on uniform meshes hold a handful
     // of distinct fp64 values (15 on the P2 Kuhn brick).  When the matrix has at most 65535 distinct
     // bit patterns, `dict` lists them (sorted by bit pattern) and every stored entry becomes one
@@ -337,6 +329,7 @@ struct SellOp {
     uint16_t* vidx = nullptr;        // instead of pk when the bits do not fit one word: 16-bit dictionary index beside col (6 B / entry)
     uint8_t* pk_nopad = nullptr;     // per slice: 1 = no padding word in the slice (the kernel then skips the selects)
     uint32_t* pkp = nullptr;         // padded entries: (dict index << cbits) | position of the column
+    int32_t* colp = nullptr;         // row-ordered twin of col for operators WITHOUT a packed stream (12-byte stream): position of the column, -1 = padding
     size_t npos = 0;
 };
 
@@ -367,6 +360,7 @@ struct drops_b200_matrix_s {
     double* bridge[2] = {nullptr, nullptr};   // device copies of host x / b (host-buffer entry points)
     std::vector<double*> ro_work;    // vectors in the row-ordered numbering (sell.npos doubles)
     uint64_t ro_diag_epoch = 0;      // values epoch ro_work[0] (the permuted diagonal) was gathered at
+    uint64_t ro_diag_idx_epoch = 0;  // values epoch the byte index of that diagonal was (tried to be) built at
     // the permuted diagonal as one byte per position + its distinct values, when there are at most kDiagDict
     // of them (constant-coefficient operators): the PCG vector kernels read 1 instead of 8 bytes of d ("pcg.diag_index")
     uint8_t* ro_diag_idx = nullptr;
@@ -410,6 +404,8 @@ int build_value_index8(const double* d_val, size_t n, int max_values, uint8_t** 
 int will_pack_one_word(const double* d_val, size_t nnz, size_t cols_and_positions, bool* yes);
 // (re)builds S.dict / S.pk from S.col / S.val; leaves them null when the matrix does not qualify
 int build_value_dictionary(SellOp& S, size_t* bytes);
+// row-ordered twin of S.col (12-byte stream) for square operators over all their rows that have no packed twin
+int build_row_ordered_columns(SellOp& S, size_t* bytes);
 // row-ordered twin of S.pk under a caller-supplied numbering iperm[column] = position (< npos)
 int pack_reorder(SellOp& S, const int32_t* iperm, size_t npos);
 }  // namespace db200

@@ -78,22 +78,30 @@ int pcg_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, doubl
     // gathered once, x is scattered back at the end.  Every row sum keeps its bits (entry order is
     // untouched); the reductions visit the same products in another order, which the double-double
     // accumulation absorbs.  Padding positions hold 0 (diagonal 1) and stay 0.
-    const bool ro = !unpreconditioned_cg && M->sell.pkp != nullptr && opt("pcg.reorder", 1.0) != 0.0 &&
-                    opt("spmv.pk", 1.0) != 0.0 && opt("spmv.kernel", 0.0) == 0.0;
+    const bool ro = !unpreconditioned_cg && opt("pcg.reorder", 1.0) != 0.0 && opt("spmv.kernel", 0.0) == 0.0 &&
+                    ((M->sell.pkp != nullptr && opt("spmv.pk", 1.0) != 0.0) || M->sell.colp != nullptr);
     double* x_user = x;
     const double* diag = M->diag;
     if (ro) {
         const size_t npos = M->sell.npos;
+        // 0 diagonal, 1 x, 2 b, 3 r, 4 p, 5 q; 6 = the second direction buffer of "pcg.fuse_x" (allocated with it only)
+        const bool want_fuse_x = opt("pcg.fuse_x", 0.0) != 0.0;
         if (M->ro_work.size() < 7) M->ro_work.resize(7, nullptr);
-        for (double*& w : M->ro_work) if (!w) DB_CHECK(dev_alloc(&w, npos));
+        for (size_t k = 0; k < M->ro_work.size(); ++k)
+            if (!M->ro_work[k] && (k < 6 || want_fuse_x)) DB_CHECK(dev_alloc(&M->ro_work[k], npos));
         double* dp = M->ro_work[0]; double* xp = M->ro_work[1]; double* bp = M->ro_work[2];
         if (M->ro_diag_epoch != M->values_epoch) {
             DB_CHECK(vec_gather_perm(npos, M->sell.perm, M->diag, dp, 1.0));
-            // constant-coefficient operators: a handful of distinct diagonal values -> one byte per position
             dev_free(M->ro_diag_idx); M->ro_diag_idx = nullptr; M->ro_diag_count = 0;
-            if (pc == DROPS_B200_PC_JACOBI && M->sell.ndict_host > 0)
-                DB_CHECK(build_value_index8(dp, npos, kDiagDict, &M->ro_diag_idx, M->ro_diag_values, &M->ro_diag_count));
+            M->ro_diag_idx_epoch = 0;
             M->ro_diag_epoch = M->values_epoch;
+        }
+        // constant-coefficient operators: a handful of distinct diagonal values -> one byte per position.  Built on the
+        // first JACOBI solve on these values (a DummyPcCL solve before it must not mark the index as done).
+        if (pc == DROPS_B200_PC_JACOBI && M->ro_diag_idx_epoch != M->values_epoch) {
+            if (M->sell.ndict_host > 0)
+                DB_CHECK(build_value_index8(dp, npos, kDiagDict, &M->ro_diag_idx, M->ro_diag_values, &M->ro_diag_count));
+            M->ro_diag_idx_epoch = M->values_epoch;
         }
         DB_CHECK(vec_gather_perm(npos, M->sell.perm, x, xp, 0.0));
         DB_CHECK(vec_gather_perm(npos, M->sell.perm, b, bp, 0.0));
@@ -159,7 +167,8 @@ int pcg_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, doubl
     // direction alternates between two buffers (iteration j reads pbuf[j & 1], writes pbuf[~j & 1]).
     // Off by default: measured on C2 the SpMV grows by 0.16 ms for the 1.2 GB it carries, the direction
     // kernel shrinks by 0.10 ms (374 vs 385 it/s in the same run, profiles/r01_notes.md).
-    const bool fuse_x = ro && fused_dot && defer_x && opt("pcg.fuse_x", 0.0) != 0.0 && (check_every % 2) == 0;
+    const bool fuse_x = ro && fused_dot && defer_x && opt("pcg.fuse_x", 0.0) != 0.0 && (check_every % 2) == 0 &&
+                        M->sell.pkp != nullptr && M->ro_work[6] != nullptr;
     double* pbuf[2] = {p, fuse_x ? M->ro_work[6] : p};
     int iter_no = 0;                                                                // iterations enqueued so far
     auto one_iteration = [&]() -> int {
@@ -290,6 +299,11 @@ int gmres_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, dou
     int m = restart <= *max_iter ? restart : *max_iter;                 // :327
     DB_ARG(m >= 2, "GMRES needs restart >= 2 and max_iter >= 2");
     const bool jac = (pc == DROPS_B200_PC_JACOBI);
+    // "gmres.ortho": 0 = modified Gram-Schmidt, the serial GMRES of the reference (:378-381) and what parity is judged
+    // against; 1 = classical Gram-Schmidt, the default of the reference's distributed ModGMRES (:862-866): one fused
+    // multi-dot + one fused update per column -- 2 kernels instead of i+1 dependent ones, which is what counts on the
+    // small, launch-bound level-set systems (twophasedrops, restart 200)
+    const bool cgs = opt("gmres.ortho", 0.0) == 1.0 && m <= 512;
 
     // work vectors: 0 r, 1 w, 2 tmp, 3 z (right precond), 4.. basis v[0..m-1]
     double* r = work_vec(M, 0); double* w = work_vec(M, 1); double* tmp = work_vec(M, 2); double* z = work_vec(M, 3);
@@ -370,10 +384,16 @@ int gmres_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, dou
                 a.x = tmp; a.y = w;
                 DB_CHECK(spmv_apply(M, false, a));
             }
-            // modified Gram-Schmidt: axpy of step k-1 fused with the dot of step k      :378-381
-            for (int k = 0; k <= i; ++k)
-                DB_CHECK(mgs_step(n, w, k > 0 ? v[k - 1] : nullptr, d_h + (k - 1), v[k], d_h + k, false));
-            DB_CHECK(mgs_step(n, w, v[i], d_h + i, nullptr, d_h + i + 1, true));    // H(i+1,i) = norm(w) :383
+            if (cgs) {
+                // classical Gram-Schmidt: all products against the unmodified w, then one update  :465-494, :862-866
+                DB_CHECK(cgs_dots(n, w, d_vptrs, i + 1, d_h));
+                DB_CHECK(cgs_update(n, w, d_vptrs, d_h, i + 1, d_h + i + 1));
+            } else {
+                // modified Gram-Schmidt: axpy of step k-1 fused with the dot of step k      :378-381
+                for (int k = 0; k <= i; ++k)
+                    DB_CHECK(mgs_step(n, w, k > 0 ? v[k - 1] : nullptr, d_h + (k - 1), v[k], d_h + k, false));
+                DB_CHECK(mgs_step(n, w, v[i], d_h + i, nullptr, d_h + i + 1, true));    // H(i+1,i) = norm(w) :383
+            }
             DB_CHECK(vec_scale_inv(n, v[i + 1], w, d_h + i + 1));                   // v[i+1] = w*(1/H(i+1,i))
             DB_CHECK(fetch(d_h, hcol.data(), (size_t)(i + 2) * sizeof(double)));
             for (int k = 0; k <= i + 1; ++k) Hat(k, i) = hcol[k];

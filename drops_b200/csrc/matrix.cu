@@ -206,36 +206,6 @@ k_dict_pack(long long n, const int32_t* __restrict__ col, const double* __restri
     pk[i] = ((uint32_t)lo << cbits) | (uint32_t)c;
 }
 
-// One warp per slice: column base per slice entry (minimum over the 32 rows) + 16-bit deltas.
-__global__ void k_sell_compress(long long nslices, const int64_t* __restrict__ slice_ptr,
-                                const int32_t* __restrict__ scol, uint16_t* __restrict__ col16,
-                                int32_t* __restrict__ cbase, uint8_t* __restrict__ wide,
-                                unsigned long long* __restrict__ nwide)
-{
-    const int lane = threadIdx.x & 31;
-    const long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (s >= nslices) return;
-    const int64_t base = slice_ptr[s];
-    const int width = (int)((slice_ptr[s + 1] - base) >> 5);
-    bool ok = true;
-    for (int j = 0; j < width; ++j) {
-        const int32_t c = scol[base + (int64_t)j * 32 + lane];
-        int32_t mn = c >= 0 ? c : 0x7fffffff;
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, m));
-        if (mn == 0x7fffffff) mn = 0;
-        const long long d = c >= 0 ? (long long)c - mn : 0xFFFF;
-        ok = ok && (c < 0 || d < 0xFFFF);
-        col16[base + (int64_t)j * 32 + lane] = (uint16_t)(c >= 0 && d < 0xFFFF ? d : 0xFFFF);
-        if (lane == 0) cbase[(base >> 5) + j] = mn;
-    }
-    ok = __all_sync(0xffffffffu, ok);
-    if (lane == 0) {
-        wide[s] = ok ? 0 : 1;
-        if (!ok) atomicAdd(nwide, 1ULL);
-    }
-}
-
 // Only the values change (same pattern): refill sval from the CSR values.
 __global__ void k_sell_refill_values(long long nslices, const int64_t* __restrict__ slice_ptr,
                                      const int32_t* __restrict__ perm, const int64_t* __restrict__ rowptr,
@@ -371,7 +341,7 @@ double* work_vec(drops_b200_matrix_s* M, int i)
 void free_sell(SellOp& s)
 {
     dev_free(s.slice_ptr); dev_free(s.col); dev_free(s.val); dev_free(s.perm);
-    dev_free(s.col16); dev_free(s.cbase); dev_free(s.wide);
+    dev_free(s.colp);
     dev_free(s.pk); dev_free(s.dict); dev_free(s.pkp); dev_free(s.vidx); dev_free(s.pk_nopad);
     s = SellOp();
 }
@@ -442,30 +412,10 @@ int build_sell(const CsrDev& A, SellOp& S, size_t* bytes, const int32_t* rowmap,
         DB_CUDA(cudaGetLastError());
     }
     DB_CUDA(cudaStreamSynchronize(st));
-    size_t col_bytes = S.padded * 4;
-    if (S.padded > 0 && opt("sell.compress", 0.0) != 0.0) {
-        unsigned long long* d_nwide = nullptr;
-        DB_CHECK(dev_alloc(&S.col16, S.padded));
-        DB_CHECK(dev_alloc(&S.cbase, S.padded / 32));
-        DB_CHECK(dev_alloc(&S.wide, S.nslices));
-        DB_CHECK(dev_alloc(&d_nwide, 1));
-        DB_CUDA(cudaMemsetAsync(d_nwide, 0, sizeof(unsigned long long), st));
-        k_sell_compress<<<blocks_for((long long)S.nslices * 32, 256), 256, 0, st>>>(
-            (long long)S.nslices, S.slice_ptr, S.col, S.col16, S.cbase, S.wide, d_nwide);
-        count_launch();
-        unsigned long long nw = 0;
-        cudaError_t e = cudaGetLastError();
-        if (e == cudaSuccess) e = cudaMemcpyAsync(&nw, d_nwide, sizeof nw, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        dev_free(d_nwide);
-        DB_CUDA(e);
-        S.nwide = (size_t)nw;
-        col_bytes = S.padded * 2 + S.padded / 32 * 4 + S.nslices;
-        if (S.nwide == 0) { dev_free(S.col); S.col = nullptr; }      // no slice needs the 32-bit columns
-        else col_bytes += S.padded * 4;
-    }
+    const size_t col_bytes = S.padded * 4;
     if (bytes) *bytes += S.padded * 8 + col_bytes + (S.nslices + 1) * 8 + padded_rows * 4;
-    return build_value_dictionary(S, bytes);
+    DB_CHECK(build_value_dictionary(S, bytes));
+    return build_row_ordered_columns(S, bytes);
 }
 
 // vidx = index of val in the sorted dictionary (16 bit); padding (col < 0) gets slot ndict = 0.0
@@ -635,7 +585,8 @@ int build_value_dictionary(SellOp& S, size_t* bytes)
 {
     cudaStream_t st = ctx().stream;
     dev_free(S.pk); dev_free(S.dict); dev_free(S.pkp); dev_free(S.vidx); dev_free(S.pk_nopad);
-    S.pk_nopad = nullptr; S.pk = nullptr; S.dict = nullptr; S.pkp = nullptr; S.vidx = nullptr; S.ndict = 0; S.ndict_host = 0; S.cbits = 0; S.npos = 0;
+    S.pk_nopad = nullptr; S.pk = nullptr; S.dict = nullptr; S.pkp = nullptr; S.vidx = nullptr; S.ndict = 0; S.ndict_host = 0; S.cbits = 0;
+    if (S.colp == nullptr) S.npos = 0;
     if (S.padded == 0 || S.col == nullptr || S.val == nullptr || opt("sell.valdict", 1.0) == 0.0) return 0;
     // columns and, for the row-ordered twin, positions (32 * nslices >= rows) share the low bits
     const int cbits = std::max(1, bits_for((unsigned long long)std::max<size_t>(std::max(S.cols, S.nslices * 32), 1)));
@@ -759,6 +710,46 @@ int pack_reorder(SellOp& S, const int32_t* iperm, size_t npos)
     return 0;
 }
 
+// Row-ordered twin of S.col for a square operator over all its rows that has NO packed stream (more than 65 535
+// distinct values: variable coefficients, cut cells): colp = position of the column in the operator's own slice
+// order, so that PCG iterates on row-ordered vectors on the 12-byte stream as well ("pcg.reorder"; the rows are then
+// cut in blocks of the matrix graph like those of a packed operator).  Depends on the pattern only.
+__global__ void k_col_positions(long long n, const int32_t* __restrict__ col, const int32_t* __restrict__ iperm,
+                                int32_t* __restrict__ colp)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t c = __ldcs(col + i);
+    colp[i] = c < 0 ? -1 : __ldg(iperm + c);
+}
+
+int build_row_ordered_columns(SellOp& S, size_t* bytes)
+{
+    dev_free(S.colp); S.colp = nullptr;
+    if (S.pkp != nullptr) return 0;                       // the packed twin exists
+    S.npos = 0;
+    if (S.vidx != nullptr) return 0;                      // six-byte form: faster in the caller's order than 12 bytes row-ordered
+    if (S.padded == 0 || S.col == nullptr || !S.full_rows || S.rows != S.cols || opt("sell.reorder", 1.0) == 0.0) return 0;
+    cudaStream_t st = ctx().stream;
+    const long long npos = (long long)S.nslices * 32;
+    int32_t* iperm = nullptr;
+    DB_CHECK(dev_alloc(&iperm, S.cols));
+    int status = dev_alloc(&S.colp, S.padded);
+    if (status == 0) {
+        k_inverse_perm<<<blocks_for(npos, 256), 256, 0, st>>>(npos, S.perm, iperm);
+        k_col_positions<<<blocks_for((long long)S.padded, 256), 256, 0, st>>>((long long)S.padded, S.col, iperm, S.colp);
+        count_launch(2);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) status = cuda_fail(e, "row-ordered columns", __FILE__, __LINE__);
+    }
+    dev_free(iperm);
+    if (status != 0) { dev_free(S.colp); S.colp = nullptr; return status; }
+    S.npos = (size_t)npos;
+    if (bytes) *bytes += S.padded * 4;
+    return 0;
+}
+
 int refill_sell_values(const CsrDev& A, SellOp& S)
 {
     if (S.padded == 0) return 0;
@@ -767,7 +758,8 @@ int refill_sell_values(const CsrDev& A, SellOp& S)
         (long long)S.nslices, S.slice_ptr, S.perm, A.rowptr, A.val, S.val);
     count_launch();
     DB_CUDA(cudaGetLastError());
-    return build_value_dictionary(S, nullptr);      // new values, new dictionary
+    DB_CHECK(build_value_dictionary(S, nullptr));      // new values, new dictionary
+    return build_row_ordered_columns(S, nullptr);       // (the packed twin may have come or gone with them)
 }
 
 int extract_diag(drops_b200_matrix_s* M)
@@ -849,7 +841,8 @@ int finalize_matrix(drops_b200_matrix_s* M)
     int32_t* order = nullptr;
     bool packs = false;
     DB_CHECK(will_pack_one_word(M->csr.val, M->csr.nnz, std::max(M->csr.cols, M->csr.rows + 4096), &packs));
-    if (packs && M->square && opt("sell.reorder", 1.0) != 0.0) DB_CHECK(compute_block_order(M->csr, &order));
+    // (every square operator gets a row-ordered twin, packed or not: graph blocks pay together with it)
+    if (M->square && opt("sell.reorder", 1.0) != 0.0) DB_CHECK(compute_block_order(M->csr, &order));
     const int s = build_sell(M->csr, M->sell, &M->device_bytes, order, order ? M->csr.rows : 0, order != nullptr, packs);
     dev_free(order);
     M->block_ordered = s == 0 && order != nullptr;
@@ -1088,7 +1081,7 @@ int drops_b200_matrix_layout(drops_b200_matrix_t M, int* block_ordered, int* row
 {
     DB_ARG(M != nullptr, "null matrix");
     if (block_ordered) *block_ordered = M->block_ordered;
-    if (row_ordered_stream) *row_ordered_stream = M->sell.pkp != nullptr;
+    if (row_ordered_stream) *row_ordered_stream = M->sell.pkp != nullptr ? 1 : (M->sell.colp != nullptr ? 2 : 0);
     return 0;
 }
 
@@ -1099,14 +1092,11 @@ int drops_b200_matrix_diag_index(drops_b200_matrix_t M, int* n_values)
     return 0;
 }
 
-int drops_b200_matrix_format(drops_b200_matrix_t M, size_t* nslices, size_t* padded_nnz, int* compressed,
-                             size_t* wide_slices)
+int drops_b200_matrix_format(drops_b200_matrix_t M, size_t* nslices, size_t* padded_nnz)
 {
     DB_ARG(M != nullptr, "null matrix");
     if (nslices) *nslices = M->sell.nslices;
     if (padded_nnz) *padded_nnz = M->sell.padded;
-    if (compressed) *compressed = M->sell.col16 != nullptr;
-    if (wide_slices) *wide_slices = M->sell.nwide;
     return 0;
 }
 

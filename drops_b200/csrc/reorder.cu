@@ -10,7 +10,7 @@
 // DROPS hands over matrices, not meshes, so the blocks come from the matrix graph: three
 // breadth-first distance fields from three far-apart rows (a = farthest from row 0, b = farthest
 // from a, c = the row maximising d_a + d_b) are pseudo-coordinates; rows are sorted by the Morton
-// code of (d_a, d_b, d_c) / T and by row index inside a cell.  The sliced-ELL windows are then cut
+// code of their cell (d_a / Ta, d_b / Tb, d_c / Tc) and, inside a cell, along the lines of the graph (k_block_keys).  The sliced-ELL windows are then cut
 // from this order (matrix.cu, build_sell with a row map), and the row-ordered twin stream numbers x
 // the same way.  Any permutation is valid -- the order only decides who shares an L1 -- so graphs
 // without mesh structure, several components or unreachable rows cost nothing but the setup pass.
@@ -73,17 +73,31 @@ __device__ __forceinline__ unsigned spread3(unsigned v)     // 10 bits -> every 
     return v;
 }
 
+// Sort key of a row: the Morton code of its cell (d_a / ta, d_b / tb, d_c / tc) in the high bits and, below it,
+// what orders the rows INSIDE a cell ("sell.block_inner"):
+//   0 = nothing (the stable sort keeps ascending row index: runs follow the caller's numbering),
+//   1 = (d_a, d_b, d_c) lexicographic, d_c fastest.  Neighbouring rows of the graph differ by at most 1 in every
+//       field, and on a mesh-like graph each field is piecewise an affine coordinate, so rows that agree in two
+//       fields and are consecutive in the third are a LINE of the mesh.  With a long cell in that direction
+//       ("sell.block_tile_c" = 64) the sigma windows, which then sort by row length, cut slices that are 32
+//       consecutive same-shape rows of one line: entry j of the 32 lanes gathers 32 consecutive positions of the
+//       row-ordered x (2-3 cache lines instead of ~5: the L1 wavefronts per gather are what bounds the packed
+//       product, profiles/r01_notes.md), and neighbouring lines reuse them from L1.
 __global__ void k_block_keys(long long n, const int32_t* __restrict__ da, const int32_t* __restrict__ db,
-                             const int32_t* __restrict__ dc, int ta, int tb, int tc, unsigned* __restrict__ key,
-                             int32_t* __restrict__ row)
+                             const int32_t* __restrict__ dc, int ta, int tb, int tc, int inner,
+                             unsigned long long* __restrict__ key, int32_t* __restrict__ row)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     row[i] = (int32_t)i;
     const int a = da[i], b = db[i], c = dc[i];
-    if (a < 0 || b < 0 || c < 0) { key[i] = 0x3fffffffu; return; }      // not reachable: after everything else
+    if (a < 0 || b < 0 || c < 0) { key[i] = 0x3fffffffull << 30; return; }      // not reachable: after everything else
     const unsigned ca = min(a / ta, 1022), cb = min(b / tb, 1022), cc = min(c / tc, 1022);
-    key[i] = spread3(ca) | (spread3(cb) << 1) | (spread3(cc) << 2);
+    unsigned long long k = (unsigned long long)(spread3(ca) | (spread3(cb) << 1) | (spread3(cc) << 2)) << 30;
+    if (inner == 1)
+        k |= ((unsigned long long)min(a - (int)ca * ta, 1023) << 20) | ((unsigned long long)min(b - (int)cb * tb, 1023) << 10) |
+             (unsigned long long)min(c - (int)cc * tc, 1023);
+    key[i] = k;
 }
 
 static inline int blocks_of(long long n, int t) { return (int)std::max<long long>(1, (n + t - 1) / t); }
@@ -147,7 +161,8 @@ int compute_block_order(const CsrDev& A, int32_t** d_order)
     cudaStream_t st = ctx().stream;
     const int n = (int)A.rows;
     int32_t *da = nullptr, *db = nullptr, *dc = nullptr, *q0 = nullptr, *q1 = nullptr, *rows_in = nullptr, *rows_out = nullptr;
-    unsigned *key_in = nullptr, *key_out = nullptr;
+    unsigned long long *key_in = nullptr, *key_out = nullptr;
+    const int inner = (int)opt("sell.block_inner", 1.0);
     int* d_count = nullptr;
     cub::KeyValuePair<int, int32_t>* d_kv = nullptr;
     void* tmp = nullptr;
@@ -175,17 +190,17 @@ int compute_block_order(const CsrDev& A, int32_t** d_order)
     dev_free(q0); q0 = nullptr; dev_free(q1); q1 = nullptr;
     RO_CHECK(dev_alloc(&key_in, (size_t)n)); RO_CHECK(dev_alloc(&key_out, (size_t)n));
     RO_CHECK(dev_alloc(&rows_in, (size_t)n)); RO_CHECK(dev_alloc(&rows_out, (size_t)n));
-    k_block_keys<<<blocks_of(n, 256), 256, 0, st>>>(n, da, db, dc, ta, tb, tc, key_in, rows_in);
+    k_block_keys<<<blocks_of(n, 256), 256, 0, st>>>(n, da, db, dc, ta, tb, tc, inner, key_in, rows_in);
     count_launch();
     size_t need = 0;
-    RO_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, key_in, key_out, rows_in, rows_out, n, 0, 30, st));
+    RO_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, key_in, key_out, rows_in, rows_out, n, 0, 60, st));
     if (need > tmp_bytes) {
         dev_free(tmp); tmp = nullptr; tmp_bytes = 0;
         char* p = nullptr;
         RO_CHECK(dev_alloc(&p, need));
         tmp = p; tmp_bytes = need;
     }
-    RO_CUDA(cub::DeviceRadixSort::SortPairs(tmp, need, key_in, key_out, rows_in, rows_out, n, 0, 30, st));   // stable: rows ascending inside a cell
+    RO_CUDA(cub::DeviceRadixSort::SortPairs(tmp, need, key_in, key_out, rows_in, rows_out, n, 0, 60, st));   // stable: equal keys keep ascending row index
     count_launch();
     RO_CUDA(cudaStreamSynchronize(st));
 #undef RO_CHECK

@@ -23,15 +23,14 @@
 
 namespace db200 {
 
-// Sum of one row of a slice, left to right.  C16: columns as cbase[entry] + 16-bit delta.
-template <bool EXACT, int U, bool SPLIT, bool C16>
+// Sum of one row of a slice, left to right.  (16-bit column deltas, "sell.compress", were measured slower --
+// the extra load per entry-row costs more than the bytes save, profiles/r01_notes.md -- and are gone.)
+template <bool EXACT, int U, bool SPLIT>
 __device__ __forceinline__ double slice_row_sum(const SellView& A, int64_t base, int width, int lane,
                                                 const double* __restrict__ x, const EpiArgs& e)
 {
     const double* vp = A.val + base + lane;
-    const int32_t* cp = C16 ? nullptr : A.col + base + lane;
-    const uint16_t* dp = C16 ? A.col16 + base + lane : nullptr;
-    const int32_t* bp = C16 ? A.cbase + (base >> 5) : nullptr;
+    const int32_t* cp = A.col + base + lane;
     double sum = 0.0;
     int j = 0;
     for (; j + U <= width; j += U) {
@@ -39,12 +38,7 @@ __device__ __forceinline__ double slice_row_sum(const SellView& A, int64_t base,
         double v[U], xv[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if (C16) {
-                const int d = (int)__ldcs(dp + (size_t)(j + u) * 32);
-                c[u] = d == 0xFFFF ? -1 : __ldg(bp + j + u) + d;
-            } else {
-                c[u] = __ldcs(cp + (size_t)(j + u) * 32);
-            }
+            c[u] = __ldcs(cp + (size_t)(j + u) * 32);
             v[u] = __ldcs(vp + (size_t)(j + u) * 32);
         }
 #pragma unroll
@@ -56,13 +50,7 @@ __device__ __forceinline__ double slice_row_sum(const SellView& A, int64_t base,
         }
     }
     for (; j < width; ++j) {
-        int c;
-        if (C16) {
-            const int d = (int)__ldcs(dp + (size_t)j * 32);
-            c = d == 0xFFFF ? -1 : __ldg(bp + j) + d;
-        } else {
-            c = __ldcs(cp + (size_t)j * 32);
-        }
+        const int c = __ldcs(cp + (size_t)j * 32);
         const double v = __ldcs(vp + (size_t)j * 32);
         if (c >= 0) {
             const double xv = load_x<SPLIT>(x, e, c);
@@ -91,23 +79,16 @@ k_spmv_sell(SellView A, const double* __restrict__ x, double* __restrict__ y, Ep
     for (long long s = s_begin + warp; s < s_end; s += nwarp) {
         const int64_t base = A.slice_ptr[s];
         const int width = (int)((A.slice_ptr[s + 1] - base) >> 5);
-        if (e.prefetch && s + nwarp < s_end) {
-            // pull the values of the slice this warp handles next into L2 while the current one is consumed
-            const int64_t nb = A.slice_ptr[s + nwarp];
-            const int nlines = (int)((A.slice_ptr[s + nwarp + 1] - nb) >> 5);
-            for (int l = lane; l < 2 * nlines; l += 32) prefetch_l2(A.val + nb + (int64_t)l * 16);
-        }
         // the row index and the row's epilogue operands are fetched up front: their latency hides
         // behind the matrix stream instead of trailing it (two dependent misses per slice otherwise)
-        const int row = A.perm[s * 32 + lane];
+        // row-ordered twin (perm == nullptr): position s*32+lane IS the row of y, aux and the dot partner
+        const int row = A.perm != nullptr ? A.perm[s * 32 + lane] : (int)(s * 32 + lane);
         double dv = 0.0, av = 0.0;
         if (row >= 0) {
             if (DOT) dv = __ldg(e.dotv + row);
             if (EPI != EPI_NONE) av = __ldg(e.aux + row);
         }
-        const bool c16 = A.col16 != nullptr && A.wide[s] == 0;     // warp-uniform
-        const double sum = c16 ? slice_row_sum<EXACT, kSellUnroll, SPLIT, true>(A, base, width, lane, x, e)
-                               : slice_row_sum<EXACT, kSellUnroll, SPLIT, false>(A, base, width, lane, x, e);
+        const double sum = slice_row_sum<EXACT, kSellUnroll, SPLIT>(A, base, width, lane, x, e);
         if (row >= 0) {
             const double out = apply_epilogue<EPI>(sum, av, e, beta);
             y[row] = out;
@@ -204,7 +185,6 @@ EpiArgs make_epi(const SpmvArgs& a)
     e.xghost = a.xghost;
     e.xu = a.xu; e.xu_p = a.xu_p; e.xu_alpha = a.xu_alpha; e.xu_iter = a.xu_iter; e.xu_applied = a.xu_applied;
     e.n_owned = (int)a.n_owned;
-    e.prefetch = (int)opt("spmv.prefetch", 0.0);
     e.partials = c.partials + (size_t)a.slot * kPartialStride;
     e.ticket = c.tickets + (size_t)a.slot * kTicketStride;
     return e;
@@ -232,9 +212,9 @@ static void launch_sell_v(const SellView& v, const SpmvArgs& a, const EpiArgs& e
     }
 }
 
-// "spmv.variant": 0 = U4/<=40 regs (default), 1 = U8/<=64, 2 = U4/<=64, 3 = U4/<=32, 4 = U2/<=32,
-// 5 = U8/<=40, 6 = U4/<=48 (128-thread CTAs only), 7 = U4/<=56, 8 = U8/<=48.  Only the plain product (the PCG kernel) is
-// built in all variants; the epilogue forms use the default.
+// Measured on B200 (profiles/r01_probe_dot.json, r01_sweep1_spmv.jsonl): the plain product is fastest with U4 and <= 40
+// registers (2.96 ms at C2), the product with the fused dot needs the room of U8 / <= 48 registers in 128-thread CTAs
+// (3.12 ms; 3.55 ms when squeezed into 40).  The other unroll x register-cap variants of round 1 are gone.
 template <int EPI, bool EXACT>
 static void launch_sell(const SellView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads,
                         cudaStream_t st)
@@ -242,24 +222,6 @@ static void launch_sell(const SellView& v, const SpmvArgs& a, const EpiArgs& e, 
     if (a.xghost != nullptr) {   // boundary rows of a partition: a thin operator, one variant
         launch_sell_v<EPI, EXACT, 4, 512, 2, true>(v, a, e, grid, threads, st);
         return;
-    }
-    // measured on B200 (profiles/r01_probe_dot.json): the plain product is fastest with U4 and <= 40
-    // registers (2.96 ms at C2), the product with the fused dot needs the room of U8 / <= 48
-    // registers (3.12 ms; 3.55 ms when squeezed into 40)
-    const int variant = (int)(a.dotv != nullptr ? opt("spmv.dotvariant", 8.0) : opt("spmv.variant", 0.0));
-    if (EPI == EPI_NONE) {
-        switch (variant) {
-            case 1: launch_sell_v<EPI_NONE, EXACT, 8, 512, 2>(v, a, e, grid, threads, st); return;
-            case 2: launch_sell_v<EPI_NONE, EXACT, 4, 512, 2>(v, a, e, grid, threads, st); return;
-            case 3: launch_sell_v<EPI_NONE, EXACT, 4, 512, 4>(v, a, e, grid, threads, st); return;
-            case 4: launch_sell_v<EPI_NONE, EXACT, 2, 512, 4>(v, a, e, grid, threads, st); return;
-            case 5: launch_sell_v<EPI_NONE, EXACT, 8, 512, 3>(v, a, e, grid, threads, st); return;
-            case 6: launch_sell_v<EPI_NONE, EXACT, 4, 128, 10>(v, a, e, grid, threads, st); return;   // <= 48 regs
-            case 7: launch_sell_v<EPI_NONE, EXACT, 4, 128, 9>(v, a, e, grid, threads, st); return;    // <= 56 regs
-            case 8: launch_sell_v<EPI_NONE, EXACT, 8, 128, 10>(v, a, e, grid, threads, st); return;
-            case 0: launch_sell_v<EPI_NONE, EXACT, 4, 512, 3>(v, a, e, grid, threads, st); return;
-            default: break;
-        }
     }
     if (a.dotv != nullptr) launch_sell_v<EPI, EXACT, 8, 128, 10>(v, a, e, grid, threads, st);
     else launch_sell_v<EPI, EXACT, 4, 512, 3>(v, a, e, grid, threads, st);
@@ -286,12 +248,11 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a)
     DB_ARG(a.dotv == nullptr || a.dot_out != nullptr || a.dd_out != nullptr, "fused dot needs an output scalar");
     if (A.rows == 0) return 0;
     // dictionary-packed stream (4 B per entry, spmv_pk.cu) when the operator has one
-    if ((A.pk != nullptr || A.vidx != nullptr) && a.xghost == nullptr && (a.row_ordered || opt("spmv.pk", 1.0) != 0.0)) {
-        // stream staged by TMA ("spmv.pktma") when the dictionary fits shared memory
-        if (opt("spmv.pktma", 0.0) != 0.0 && A.pk != nullptr && A.ndict <= 512 && a.xu == nullptr) return spmv_sell_pk_tma(A, a);
+    if ((A.pk != nullptr || A.vidx != nullptr) && a.xghost == nullptr && opt("spmv.pk", 1.0) != 0.0 &&
+        (!a.row_ordered || A.pkp != nullptr)) {
         return spmv_sell_pk(A, a);
     }
-    DB_ARG(!a.row_ordered, "row-ordered vectors need the operator's row-ordered stream");
+    DB_ARG(!a.row_ordered || A.colp != nullptr, "row-ordered vectors need the operator's row-ordered stream");
     DB_ARG(a.xu == nullptr, "only the packed stream carries the PCG x update");
     int threads = (int)opt("spmv.threads", 128);
     if (threads < 32) threads = 32;
@@ -319,7 +280,7 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a)
     if (grid > kMaxReduceGrid) grid = kMaxReduceGrid;
     if (grid < 1) grid = 1;
     cudaStream_t st = a.stream ? a.stream : c.stream;
-    SellView v{A.slice_ptr, A.col, A.val, A.perm, (long long)A.nslices, A.col16, A.cbase, A.wide};
+    SellView v{A.slice_ptr, a.row_ordered ? A.colp : A.col, A.val, a.row_ordered ? nullptr : A.perm, (long long)A.nslices};
     EpiArgs e = make_epi(a);
     if (opt("spmv.exact", 1.0) != 0.0) launch_sell_epi<true>(v, a, e, (int)grid, threads, st);
     else launch_sell_epi<false>(v, a, e, (int)grid, threads, st);
@@ -381,7 +342,6 @@ int spmv_apply(const drops_b200_matrix_s* M, bool transposed, const SpmvArgs& a)
         const int lanes = (int)opt("spmv.lanes", 8.0);
         return spmv_csr_vector(transposed ? M->csr_t : M->csr, a, lanes);
     }
-    if (kind == 2 && a.xghost == nullptr) return spmv_sell_tma(transposed ? M->sell_t : M->sell, a);
     return spmv_sell(transposed ? M->sell_t : M->sell, a);
 }
 

@@ -52,16 +52,10 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a);
 // Same operator on its dictionary-packed stream (SellOp::pk, 4 B per entry; spmv_pk.cu); spmv_sell
 // dispatches to it when the operator has one and option "spmv.pk" is not 0.
 int spmv_sell_pk(const SellOp& A, const SpmvArgs& a);
-// ... with the packed stream staged through shared memory by TMA bulk copies (spmv_pk_tma.cu)
-int spmv_sell_pk_tma(const SellOp& A, const SpmvArgs& a);
-int spmv_pk_tma_fault();
-// Same operator, matrix stream staged through shared memory with TMA bulk copies (spmv_tma.cu).
-int spmv_sell_tma(const SellOp& A, const SpmvArgs& a);
-int spmv_tma_fault();
 // y = A x straight from CSR, LANES threads per row (FMA, shuffle tree): comparison kernel.
 int spmv_csr_vector(const CsrDev& A, const SpmvArgs& a, int lanes);
 
-// dispatch on option "spmv.kernel": 0 = sell (register-staged), 1 = csr_vector, 2 = sell with TMA staging
+// dispatch on option "spmv.kernel": 0 = sell (register-staged), 1 = csr_vector
 int spmv_apply(const drops_b200_matrix_s* M, bool transposed, const SpmvArgs& a);
 
 }  // namespace db200

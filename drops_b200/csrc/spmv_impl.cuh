@@ -1,4 +1,4 @@
-// spmv_impl.cuh -- device-side pieces shared by the SpMV kernels (spmv.cu, spmv_tma.cu).
+// spmv_impl.cuh -- device-side pieces shared by the SpMV kernels (spmv.cu, spmv_pk*.cu).
 #pragma once
 #include "spmv.cuh"
 
@@ -10,9 +10,6 @@ struct SellView {
     const double* val;
     const int32_t* perm;
     long long nslices;
-    const uint16_t* col16;     // 16-bit column deltas (nullptr: not compressed)
-    const int32_t* cbase;
-    const uint8_t* wide;
 };
 
 struct EpiArgs {
@@ -27,7 +24,6 @@ struct EpiArgs {
     dd* dd_out;
     const double* xghost;
     int n_owned;
-    int prefetch;
     dd* partials;
     unsigned* ticket;
     double* xu;                 // carried x update (SpmvArgs::xu...)
@@ -45,11 +41,6 @@ __device__ __forceinline__ double apply_epilogue(double s, double av, const EpiA
     if (EPI == EPI_RESID)  return __dsub_rn(av, s);
     if (EPI == EPI_AXMBY)  return __dsub_rn(s, __dmul_rn(beta, av));
     return s;
-}
-
-__device__ __forceinline__ void prefetch_l2(const void* p)
-{
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 // U = entries per thread loaded before the first use (loads in flight), MINB = resident CTAs of

@@ -32,10 +32,10 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
     if (A.rows == 0) return 0;
     // the fused-dot product with the dictionary in the parameter block has its own geometry (measured on C2 inside
     // PCG: 15 words in flight x 384-thread CTAs x 192 slices, 3 CTAs of <= 56 registers per SM)
-    const bool dot_geometry = a.dotv != nullptr && a.epilogue == EPI_NONE && opt("spmv.exact", 1.0) != 0.0 &&     // (the forms launch_pk has the U14 kernel for)
+    const bool dot_geometry = a.dotv != nullptr && a.epilogue == EPI_NONE && opt("spmv.exact", 1.0) != 0.0 &&     // (the form launch_pk has the U15 kernel for)
                               A.pk != nullptr && A.ndict_host > 0 && A.ndict_host == A.ndict &&
                               A.ndict <= kPkDictSmem && opt("spmv.pkdict", 0.0) == 0.0 &&
-                              opt("spmv.pk_cdict_dot", (double)kPkCdictDotVariant) != 0.0;
+                              opt("spmv.pk_cdict", 1.0) != 0.0 && opt("spmv.pk_cdict_dot", 1.0) != 0.0;
     int threads = dot_geometry ? (int)opt("spmv.pk_dot_threads", 384) : (int)opt("spmv.pk_threads", 512);
     if (threads < 32) threads = 32;
     if (threads > 1024) threads = 1024;
@@ -62,10 +62,9 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
     cudaStream_t st = a.stream ? a.stream : c.stream;
     PkView v{A.slice_ptr, A.col, A.pk != nullptr ? nullptr : A.vidx, a.row_ordered ? A.pkp : A.pk, A.dict, a.row_ordered ? nullptr : A.perm, (long long)A.nslices,
              A.ndict, A.cbits, opt("spmv.pk_nopad", 1.0) != 0.0 ? A.pk_nopad : nullptr,
-             std::max(0, (int)opt("spmv.pk_xwin_halo", 0.0)), A.ndict_host == A.ndict ? A.ndict_host : 0, {}};
+             A.ndict_host == A.ndict ? A.ndict_host : 0, {}};
     if (v.cdict_n > 0) std::memcpy(v.cdict, A.dict_host, sizeof(double) * ((size_t)A.ndict_host + 1));
     EpiArgs e = make_epi(a);
-    e.prefetch = (int)opt("spmv.pk_prefetch", 0.0);        // slices ahead (in units of the CTA's warp count)
     if (opt("spmv.exact", 1.0) != 0.0) launch_pk_epi<true>(v, a, e, (int)grid, threads, st);
     else launch_pk_epi_fma(v, a, e, (int)grid, threads, st);
     count_launch();

@@ -7,6 +7,8 @@
 // before the add (__dmul_rn/__dadd_rn, no FMA contraction), divisions are IEEE divisions.
 #include "vecops.cuh"
 
+#include <algorithm>
+
 namespace db200 {
 
 // ------------------------------------------------------------------------------------------
@@ -965,6 +967,107 @@ struct OpMultiAxpy {
 int multi_axpy(size_t n, double* x, const double* const* d_vptrs, const double* d_y, int k)
 {
     return launch_stream<0>(n, OpMultiAxpy{x, d_vptrs, d_y, k}, "gmres.update");
+}
+
+// ------------------------------------------------------------------------------------------
+// Classical Gram-Schmidt: StandardGramSchmidt, num/krylovsolver.h:465-494 -- what the reference's distributed
+// ModGMRES runs by default (:862-866): all i+1 products h_k = w.v_k against the UNMODIFIED w, one synchronisation
+// point, then w -= sum_k h_k v_k.  Two kernels per Hessenberg column instead of i+1 dependent ones, and
+// 2(i+1) + 2 instead of 4(i+1) vector passes.
+//
+// k_cgs_dots: CTA c owns a contiguous range of rows and walks it in tiles of kCgsTile rows staged in shared
+// memory; its warps take the basis vectors round-robin (no two warps share an accumulator), every (vector, tile)
+// partial is reduced over the warp's lanes and added to the CTA's accumulator of that vector in tile order; the
+// CTA that draws the last ticket sums the per-CTA partials of each vector in CTA order.  w and every v_k are
+// read once; the result does not depend on scheduling.
+// ------------------------------------------------------------------------------------------
+constexpr int kCgsTile = 1024;
+constexpr int kCgsMaxVec = 512;
+
+__global__ void __launch_bounds__(256)
+k_cgs_dots(size_t n, const double* __restrict__ w, const double* const* __restrict__ v, int nv, dd* partials,
+           unsigned* ticket, double* h_out, dd* part_out)
+{
+    __shared__ double wt[kCgsTile];
+    __shared__ dd acc[kCgsMaxVec];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const size_t ntiles = (n + kCgsTile - 1) / kCgsTile;
+    const size_t t_begin = ntiles * blockIdx.x / gridDim.x, t_end = ntiles * (blockIdx.x + 1) / gridDim.x;
+    for (int k = threadIdx.x; k < nv; k += blockDim.x) acc[k] = dd_zero();
+    for (size_t t = t_begin; t < t_end; ++t) {
+        const size_t r0 = t * kCgsTile;
+        __syncthreads();                                   // the previous tile is consumed (and acc is initialised)
+        for (int j = threadIdx.x; j < kCgsTile; j += blockDim.x) wt[j] = r0 + j < n ? w[r0 + j] : 0.0;
+        __syncthreads();
+        const int len = (int)(n - r0 < (size_t)kCgsTile ? n - r0 : (size_t)kCgsTile);
+        for (int k = warp; k < nv; k += nwarp) {
+            const double* __restrict__ vk = v[k] + r0;
+            dd a = dd_zero();
+            for (int j = lane; j < len; j += 32) a = dd_add_prod(a, wt[j], __ldcs(vk + j));
+            a = warp_reduce_dd(a);
+            if (lane == 0) acc[k] = dd_add(acc[k], a);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nv; k += blockDim.x) partials[(size_t)k * gridDim.x + blockIdx.x] = acc[k];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int k = warp; k < nv; k += nwarp) {
+        dd a = dd_zero();
+        for (unsigned c = lane; c < gridDim.x; c += 32) {
+            const volatile dd* p = partials + (size_t)k * gridDim.x + c;
+            dd t; t.hi = p->hi; t.lo = p->lo;
+            a = dd_add(a, t);
+        }
+        a = warp_reduce_dd(a);
+        if (lane == 0) {
+            if (part_out) part_out[k] = a;                 // partitioned system: summed over the ranks later
+            else h_out[k] = dd_round(a);
+        }
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
+int cgs_dots(size_t n, const double* w, const double* const* d_vptrs, int nv, double* d_h, dd* part_out)
+{
+    DB_ARG(nv >= 1 && nv <= kCgsMaxVec, "classical Gram-Schmidt: more basis vectors than the kernel holds accumulators for");
+    Ctx& c = ctx();
+    ScopedTiming t("gmres.cgs");
+    const size_t ntiles = (n + kCgsTile - 1) / kCgsTile;
+    long long grid = std::min<long long>((long long)std::max<size_t>(ntiles, 1), 2LL * c.sm_count);
+    grid = std::min<long long>(grid, kPartialStride / nv);
+    k_cgs_dots<<<(int)grid, 256, 0, c.stream>>>(n, w, d_vptrs, nv, c.partials + (size_t)1 * kPartialStride,
+                                                c.tickets + (size_t)1 * kTicketStride, d_h, part_out);
+    count_launch();
+    DB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// w -= h_k v_k for k = 0 .. nv-1 in that order (the loop of :492-493), then *d_norm = |w|_2 (:383 / :868)
+struct OpCgsUpdate {
+    double* w; const double* const* v; const double* h; int nv; double* norm_out; dd* part_out;
+    __device__ bool begin() { return true; }
+    __device__ void elem(size_t i, dd* acc)
+    {
+        double wi = w[i];
+        for (int k = 0; k < nv; ++k) wi = sub(wi, mul(__ldg(h + k), __ldcs(v[k] + i)));
+        w[i] = wi;
+        acc[0] = dd_add_prod(acc[0], wi, wi);
+    }
+    __device__ void finish(const dd* acc)
+    {
+        if (part_out) { *part_out = acc[0]; return; }
+        *norm_out = sqrt(dd_round(acc[0]));
+    }
+};
+int cgs_update(size_t n, double* w, const double* const* d_vptrs, const double* d_h, int nv, double* d_norm, dd* part_out)
+{
+    return launch_stream<1>(n, OpCgsUpdate{w, d_vptrs, d_h, nv, d_norm, part_out}, "gmres.cgs");
 }
 
 // ------------------------------------------------------------------------------------------

@@ -111,6 +111,14 @@ int mgs_step(size_t n, double* w, const double* vprev, const double* d_hprev, co
 // x_e = (((x_e + y0 v0_e) + y1 v1_e) + ...) for k vectors; y on device.         :282-297
 int multi_axpy(size_t n, double* x, const double* const* d_vptrs, const double* d_y, int k);
 
+// Classical Gram-Schmidt (StandardGramSchmidt :465-494, the reference's ModGMRES default :862-866):
+// d_h[k] = dot(w, v_k), k < nv, all against the unmodified w in ONE pass (part_out != nullptr: unrounded local
+// partials part_out[k] instead, for a partitioned system) ...
+int cgs_dots(size_t n, const double* w, const double* const* d_vptrs, int nv, double* d_h, dd* part_out = nullptr);
+// ... then w -= d_h[k] v_k for k = 0..nv-1 in that order and *d_norm = |w|_2 (part_out: local partial of w.w)
+int cgs_update(size_t n, double* w, const double* const* d_vptrs, const double* d_h, int nv, double* d_norm,
+               dd* part_out = nullptr);
+
 // ---- MINRES building blocks (num/krylovsolver.h:926-1152) ----------------------------------------
 // q2 -= (*d_a1) * q1;  *d_b1 = |q2|_2                                           :933-934
 int lanczos_orth(size_t n, double* q2, const double* q1, const double* d_a1, double* d_b1);

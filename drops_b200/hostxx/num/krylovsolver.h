@@ -146,6 +146,7 @@ PCG(const Mat& A, VectorCL& x, const VectorCL& b, const DummyExchangeCL& ex, Pre
     if (M.NeedDiag()) M.SetDiag(A, ex);                 // :123-124 (ChebyshevPcCL: lambda_max, printed by the reference's code)
     const drops_b200_matrix_t h = b200::device(Mat0);
     b200::PcTraits<PreCon>::prepare(M, h, false);
+    b200::TraceCL trace("PCG solve (vectors up, iterations, solution down)");
     const int r = drops_b200_pcg(h, &x[0], Addr(b), b200::PcTraits<PreCon>::kind(), b200::PcTraits<PreCon>::omega(M), &it, &tol,
                                  measure_relative_tol ? 1 : 0, output ? hist.data() : 0, static_cast<int>(hist.size()));
     b200::check(r);
@@ -191,7 +192,9 @@ GMRES(const Mat& A, VectorCL& x, const VectorCL& b, const DummyExchangeCL&, PreC
     const MatrixCL& Mat0 = b200::finest(A);
     b200::check_dims(Mat0, x, b, "GMRES");
     int it = max_iter;
-    const int r = drops_b200_gmres(b200::device(Mat0), &x[0], Addr(b), b200::PcTraits<PreCon>::kind(), b200::PcTraits<PreCon>::omega(M),
+    const drops_b200_matrix_t h = b200::device(Mat0);
+    b200::TraceCL trace("GMRES solve (vectors up, iterations, solution down)");
+    const int r = drops_b200_gmres(h, &x[0], Addr(b), b200::PcTraits<PreCon>::kind(), b200::PcTraits<PreCon>::omega(M),
                                    m, &it, &tol, measure_relative_tol ? 1 : 0, method == LeftPreconditioning ? 1 : 0);
     b200::check(r);
     if (r == 1) max_iter = it;

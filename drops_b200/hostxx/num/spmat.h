@@ -26,7 +26,9 @@
 #include_next "num/spmat.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -45,11 +47,34 @@ inline void check(int status)
     if (status < 0) throw DROPSErrCL(std::string("drops_b200: ") + drops_b200_last_error());
 }
 
+/// DROPS_B200_TRACE=1: one line on stderr per one-time cost (CUDA context, matrix upload) and per solve, so that
+/// the time a DROPS driver prints around solver.Solve (e.g. poisson/cdrdrops.cpp:117-119) can be taken apart.
+inline bool trace_on()
+{
+    static const bool on = [] { const char* t = std::getenv("DROPS_B200_TRACE"); return t && std::atoi(t) != 0; }();
+    return on;
+}
+class TraceCL
+{
+  private:
+    const char* what_;
+    std::chrono::steady_clock::time_point t0_;
+  public:
+    explicit TraceCL(const char* what) : what_(what), t0_(std::chrono::steady_clock::now()) {}
+    ~TraceCL()
+    {
+        if (!trace_on()) return;
+        const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0_).count();
+        std::fprintf(stderr, "drops_b200 trace: %s %.6f s\n", what_, s);
+    }
+};
+
 /// Bind the process to its GPU on first use (DROPS_B200_DEVICE, else LOCAL_RANK, else 0).  There is no CPU
 /// path behind this boundary: without an sm_100 device the first product or solve throws.
 inline void ensure_init()
 {
     static const bool once = [] {
+        TraceCL t("init (CUDA context, streams, workspace)");
         const char* d = std::getenv("DROPS_B200_DEVICE");
         if (!d) d = std::getenv("LOCAL_RANK");
         check(drops_b200_init(d ? std::atoi(d) : 0));
@@ -147,6 +172,7 @@ class DeviceCacheCL
         if (same_pattern && e.version == A.Version() && e.val == A.raw_val() && e.col == A.raw_col() &&
             e.row == A.raw_row() && e.value_sum == vsum)
             return e.handle;
+        TraceCL t(same_pattern ? "matrix values refreshed on the device" : "matrix uploaded (CSR -> device operator)");
         if (same_pattern) {
             check(drops_b200_matrix_update_values(e.handle, A.raw_val(), A.Version()));
         } else {

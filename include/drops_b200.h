@@ -69,8 +69,7 @@ DROPS_B200_API int drops_b200_compiled_arch(void);
 /* Device facts: sm count, compute capability major*10+minor, free/total bytes. */
 DROPS_B200_API int drops_b200_device_info(int* sm_count, int* cc, size_t* free_bytes, size_t* total_bytes);
 /* Tunables: "spmv.kernel", "spmv.threads", "spmv.slices_per_cta", "spmv.exact",
- * "spmv.variant", "spmv.dotvariant", "spmv.dotmode", "sell.sigma", "sell.compress", "vec.wide",
- * "pcg.check_every", "timing". */
+ * "spmv.dotmode", "sell.sigma", "vec.wide", "pcg.check_every", "gmres.ortho", "timing", ... */
 DROPS_B200_API int drops_b200_set_option(const char* key, double value);
 DROPS_B200_API int drops_b200_get_option(const char* key, double* value);
 /* Accumulated CUDA-event time (ms) and launch count of a named kernel class since the last
@@ -85,9 +84,6 @@ DROPS_B200_API int drops_b200_timer_stop(double* ms);
 /* Number of kernels this library launched since init (all streams). */
 DROPS_B200_API long long drops_b200_launch_count(void);
 DROPS_B200_API int drops_b200_synchronize(void);
-/* 1 if a warp of the TMA-staged SpMV ("spmv.kernel" = 2) ever gave up waiting for a stage (the
- * kernel never spins forever); results of that launch are invalid.  0 in a healthy process. */
-DROPS_B200_API int drops_b200_spmv_tma_fault(void);
 
 /* ---- matrices: SparseMatBaseCL<double>, num/spmat.h:682-879 -------------------------------- */
 /* Copies a host CSR matrix in the reference layout to the device: narrows colind to int32,
@@ -115,11 +111,8 @@ DROPS_B200_API int drops_b200_matrix_lincomb(double a, drops_b200_matrix_t A, do
 DROPS_B200_API int drops_b200_matrix_destroy(drops_b200_matrix_t A);
 DROPS_B200_API int drops_b200_matrix_info(drops_b200_matrix_t A, size_t* rows, size_t* cols, size_t* nnz,
                                           uint64_t* version, size_t* device_bytes, size_t* padded_nnz);
-/* Storage facts of the sliced-ELL operator: slices of 32 rows, stored entries incl. padding, whether
- * columns are stored as 16-bit deltas ("sell.compress", default on) and how many slices had to keep
- * 32-bit columns because their columns spread over more than 2^16. */
-DROPS_B200_API int drops_b200_matrix_format(drops_b200_matrix_t A, size_t* nslices, size_t* padded_nnz,
-                                            int* compressed, size_t* wide_slices);
+/* Storage facts of the sliced-ELL operator: slices of 32 rows, stored entries incl. padding. */
+DROPS_B200_API int drops_b200_matrix_format(drops_b200_matrix_t A, size_t* nslices, size_t* padded_nnz);
 /* Value dictionary of the sliced-ELL operator ("sell.valdict", default on): a matrix with at most
  * 65535 distinct fp64 bit patterns whose column and dictionary-index bits fit 32 is ALSO stored as one
  * 32-bit word per entry (lossless; products stay bit-identical).  n_distinct = 0 and packed = 0 when
@@ -132,8 +125,9 @@ DROPS_B200_API int drops_b200_matrix_value_dictionary(drops_b200_matrix_t A, int
 /* Row order of the sliced-ELL operator: block_ordered != 0 when the slices were cut from the block
  * order of the matrix graph ("sell.block_order", operators of at least "sell.block_min_rows" rows:
  * three breadth-first distance fields as pseudo-coordinates, rows sorted by the Morton code of their
- * cell); row_ordered_stream != 0 when the packed stream has its row-ordered twin, which is what
- * PCG iterates on ("pcg.reorder").  Both only change who shares a cache, never a result bit of A*x. */
+ * cell); row_ordered_stream != 0 when the operator has its row-ordered twin, which is what PCG iterates on
+ * ("pcg.reorder"): 1 = twin of the packed stream, 2 = twin of the int32 columns of the 12-byte stream (operators
+ * without a value dictionary).  Both only change who shares a cache, never a result bit of A*x. */
 DROPS_B200_API int drops_b200_matrix_layout(drops_b200_matrix_t A, int* block_ordered, int* row_ordered_stream);
 /* Jacobi diagonal of the row-ordered PCG as one byte per row ("pcg.diag_index"; JACPcCL's diag_, num/precond.h:1162-1177,
  * holds a handful of distinct values on constant-coefficient operators): *n_values = length of the value list the

@@ -75,7 +75,11 @@ def run(variant, case, workdir, timeout=1200, env=None):
     r = subprocess.run([exe(variant), path], cwd=workdir, capture_output=True, text=True, timeout=timeout, env=env)
     if r.returncode != 0:
         raise RuntimeError(f"cdrdrops ({variant}, {case}) failed with {r.returncode}:\n{r.stdout[-3000:]}\n{r.stderr[-3000:]}")
-    return r.stdout, parse(r.stdout)
+    rec = parse(r.stdout)
+    # DROPS_B200_TRACE=1 (overlay binary): one stderr line per one-time cost and per solve
+    rec["trace"] = {m.group(1).strip(): float(m.group(2))
+                    for m in re.finditer(r"drops_b200 trace: (.*?) ([0-9.eE+-]+) s\n", r.stderr)}
+    return r.stdout, rec
 
 
 def parse(text):

@@ -74,9 +74,6 @@ def test_spmv_layout_and_launch_options_do_not_change_results(gpu, sigma, thread
         gpu.set_option("spmv.threads", threads)
         gpu.set_option("spmv.ctas_per_sm", ctas)
         gpu.set_option("spmv.slices_per_cta", spc)
-        gpu.set_option("spmv.variant", variant)
-        gpu.set_option("spmv.dotvariant", variant)
-        gpu.set_option("spmv.prefetch", prefetch)
         A = gmat(gpu, g)
         assert np.array_equal(A.spmv(g["x_in"]), g["y_Ax"])
         assert np.array_equal(A.spmv_transpose(g["x_in"]), g["y_ATx"])
@@ -88,75 +85,22 @@ def test_spmv_layout_and_launch_options_do_not_change_results(gpu, sigma, thread
         gpu.set_option("spmv.threads", 128)
         gpu.set_option("spmv.ctas_per_sm", 0)
         gpu.set_option("spmv.slices_per_cta", 16)
-        gpu.set_option("spmv.variant", 0)
-        gpu.set_option("spmv.dotvariant", 8)
-        gpu.set_option("spmv.prefetch", 0)
 
 
-CDICT_DOT_DEFAULT = 17  # library default of "spmv.pk_cdict_dot"
+CDICT_DOT_DEFAULT = 1  # library default of "spmv.pk_cdict_dot"
 CDICT_DEFAULT = 1     # library default of "spmv.pk_cdict"
-XWIN_DEFAULT = 0      # library default of "spmv.pk_xwin"
 
 
-PK_DEFAULTS = {"spmv.pktma": None, "spmv.pktma_geometry": 0, "spmv.pktma_slices_per_cta": None, "spmv.pk": 1, "spmv.pkdotform": 2, "pcg.reorder": 1, "pcg.defer_x": 1, "pcg.fused_dot": 1, "pcg.fuse_x": 0, "spmv.pk_threads": 512,
-               "spmv.pk_slices_per_cta": 128, "spmv.pkvariant": 9, "spmv.pkdotvariant": 9, "spmv.pkdict": 0, "spmv.dotmode": 0, "sell.sigma": 4096,
-               "sell.valdict": 1, "spmv.exact": 1, "spmv.pk_xwin": XWIN_DEFAULT, "spmv.pk_xwin_halo": 0,
+PK_DEFAULTS = {"spmv.pk": 1, "pcg.reorder": 1, "pcg.defer_x": 1, "pcg.fused_dot": 1, "pcg.fuse_x": 0, "spmv.pk_threads": 512,
+               "spmv.pk_slices_per_cta": 128, "spmv.pkdict": 0, "spmv.dotmode": 0, "sell.sigma": 4096,
+               "sell.valdict": 1, "spmv.exact": 1,
                "spmv.pk_cdict": CDICT_DEFAULT, "spmv.pk_cdict_dot": CDICT_DOT_DEFAULT,
                "spmv.pk_dot_threads": 384, "spmv.pk_dot_slices_per_cta": 192}
 
 
-PKTMA_DEFAULT = 0     # library default of "spmv.pktma"
-
-
 def _restore_pk(gpu):
     for k, v in PK_DEFAULTS.items():
-        if k == "spmv.pktma":
-            v = PKTMA_DEFAULT
-        elif k == "spmv.pktma_slices_per_cta":
-            v = 16
         gpu.set_option(k, v)
-
-
-@pytest.mark.parametrize("geometry,spc,dotmode", [(0, 16, 0), (1, 1, 0), (2, 3, 0), (3, 1000000, 0), (4, 32, 0), (5, 7, 0),
-                                                  (6, 16, 0), (7, 2, 0), (8, 5, 0)])
-def test_value_dictionary_tma_stream_is_bit_identical(gpu, geometry, spc, dotmode):
-    """"spmv.pktma" = 1: the packed words reach the SM through cp.async.bulk + mbarrier rings; same
-    arithmetic, so every product, fused dot and solve keeps its bits under every ring geometry."""
-    g = load_golden("brick_fe2_N6_num1.npz")
-    r = load_golden("random_ragged.npz")
-    n, rb, ci, va = gpu.brick_csr_host(2, 14, 1)
-    xin = hash_vector(n)
-    try:
-        gpu.set_option("spmv.pktma", 0)
-        B0 = gpu.Matrix(n, n, rb, ci, va)
-        y0, yt0 = B0.spmv(xin), B0.spmv_transpose(xin)
-        X, Y = gpu.Vector.from_host(xin), gpu.Vector(n)
-        d0 = B0.spmv_dot_dev(X, Y, X)
-        s0 = B0.pcg_jacobi(np.zeros(n), y0, 60, 1e-10, True)
-        gpu.set_option("spmv.pktma", 1)
-        gpu.set_option("spmv.pktma_geometry", geometry)
-        gpu.set_option("spmv.pktma_slices_per_cta", spc)
-        A = gmat(gpu, g)
-        assert np.array_equal(A.spmv(g["x_in"]), g["y_Ax"])
-        assert np.array_equal(A.spmv_transpose(g["x_in"]), g["y_ATx"])
-        out = A.pcg_jacobi(np.zeros(A.rows), g["b"], 400, 1e-10, True)
-        assert out[1] == int(g["sym_pcgjac"][1]) and rel(out[3], g["sym_pcgjac_x"]) <= 1e-12
-        if gmat(gpu, r).value_dictionary()["packed"]:
-            R = gmat(gpu, r)
-            assert np.array_equal(R.spmv(r["x_in"]), r["y_Ax"])
-            assert np.array_equal(R.spmv_transpose(r["xt_in"] if "xt_in" in r else r["x_in"]), r["y_ATx"])
-        B = gpu.Matrix(n, n, rb, ci, va)
-        assert np.array_equal(B.spmv(xin), y0) and np.array_equal(B.spmv_transpose(xin), yt0)
-        assert B.spmv_dot_dev(X, Y, X) == d0 and np.array_equal(Y.download(), y0)
-        s1 = B.pcg_jacobi(np.zeros(n), y0, 60, 1e-10, True)
-        assert s1[1] == s0[1] and s1[2] == s0[2] and np.array_equal(s1[3], s0[3])
-        check_solve_like = B.gmres_jacobi(np.zeros(n), y0, 20, 200, 1e-10, True, 1.0, True)
-        gpu.set_option("spmv.pktma", 0)
-        ref = B.gmres_jacobi(np.zeros(n), y0, 20, 200, 1e-10, True, 1.0, True)
-        assert check_solve_like[1] == ref[1] and np.array_equal(check_solve_like[3], ref[3])
-        assert gpu.lib().drops_b200_spmv_tma_fault() == 0
-    finally:
-        _restore_pk(gpu)
 
 
 def test_value_dictionary_qualifies_only_when_lossless_packing_fits(gpu):
@@ -208,15 +152,14 @@ def test_value_dictionary_stream_is_bit_identical(gpu, variant, threads, spc, di
         d0 = B0.spmv_dot_dev(X, Y, X)
         s0 = B0.pcg_jacobi(np.zeros(n), y0, 60, 1e-10, True)
         gpu.set_option("spmv.pk", 1)
-        gpu.set_option("spmv.pkvariant", variant)
-        gpu.set_option("spmv.pkdotvariant", variant)
+        gpu.set_option("spmv.pk_cdict", variant & 1)
+        gpu.set_option("spmv.pk_cdict_dot", (variant >> 1) & 1)
         gpu.set_option("spmv.pk_threads", threads)
         gpu.set_option("spmv.pk_slices_per_cta", spc)
         gpu.set_option("spmv.pk_dot_threads", threads)
         gpu.set_option("spmv.pk_dot_slices_per_cta", spc)
         gpu.set_option("spmv.pkdict", dictmode)
         gpu.set_option("spmv.dotmode", dotmode)
-        gpu.set_option("spmv.pkdotform", variant % 3)
         gpu.set_option("sell.sigma", sigma)
         A = gmat(gpu, g)
         assert A.value_dictionary()["packed"]
@@ -283,47 +226,6 @@ def test_pcg_forms_agree_with_reference(gpu, reorder, defer_x, fused_dot, graph,
         _restore_pk(gpu)
 
 
-@pytest.mark.parametrize("xwin,halo,threads,spc,tile,graph", [(1, 0, 512, 128, 8, 1), (2, 1, 64, 2, 2, 0), (3, 3, 1024, 256, 8, 1),
-                                                               (4, 0, 32, 1, 1, 0), (5, 7, 96, 5, 3, 1), (1, 100000, 128, 16, 8, 0)])
-def test_x_window_in_shared_memory_keeps_every_bit(gpu, xwin, halo, threads, spc, tile, graph):
-    """"spmv.pk_xwin": the row-ordered packed product gathers the x entries of the CTA's own stretch of rows
-    (+ halo slices) from shared memory and the others through L1.  Same operands, same order: the PCG iterates,
-    residuals and iteration counts are the bits of the solve without the window, for every CTA geometry
-    (windows of one slice, windows larger than the vector, windows cut at both ends)."""
-    g = load_golden("brick_fe2_N6_num1.npz")
-    n, rb, ci, va = gpu.brick_csr_host(2, 12, 1)
-    xs = gpu.brick_solution_host(2, 12, 1)
-    try:
-        gpu.set_option("sell.block_order", 1)
-        gpu.set_option("sell.block_min_rows", 0)
-        gpu.set_option("sell.block_tile", tile)
-        gpu.set_option("pcg.graph", graph)
-        gpu.set_option("spmv.pk_threads", threads)
-        gpu.set_option("spmv.pk_slices_per_cta", spc)
-        gpu.set_option("spmv.pk_dot_threads", threads)
-        gpu.set_option("spmv.pk_dot_slices_per_cta", spc)
-        B = gpu.Matrix(n, n, rb, ci, va)
-        assert B.layout()["row_ordered_stream"]
-        b = B.spmv(xs)
-        A = gmat(gpu, g)
-        res = {}
-        for w in (0, xwin):
-            gpu.set_option("spmv.pk_xwin", w)
-            gpu.set_option("spmv.pk_xwin_halo", halo if w else 0)
-            res[w] = (B.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True), B.pcg_jacobi(np.zeros(n), b, 9, 1e-30, True),
-                      A.pcg_jacobi(np.zeros(A.rows), g["b"], 400, 1e-10, True))
-        for r0, r1 in zip(res[0], res[xwin]):
-            assert r0[0] == r1[0] and r0[1] == r1[1] and r0[2] == r1[2] and np.array_equal(r0[3], r1[3])
-        assert res[xwin][2][1] == int(g["sym_pcgjac"][1]) and rel(res[xwin][2][3], g["sym_pcgjac_x"]) <= 1e-12
-        assert res[xwin][0][0] and rel(res[xwin][0][3], xs) <= 1e-8
-    finally:
-        gpu.set_option("sell.block_order", 1)
-        gpu.set_option("sell.block_min_rows", 2.0e6)
-        gpu.set_option("sell.block_tile", 8)
-        gpu.set_option("pcg.graph", 1)
-        _restore_pk(gpu)
-
-
 @pytest.mark.parametrize("threads,spc,dotmode,graph", [(512, 128, 0, 1), (64, 3, 1, 0), (1024, 1000000, 2, 1)])
 def test_dictionary_in_the_parameter_block_keeps_every_bit(gpu, threads, spc, dotmode, graph):
     """"spmv.pk_cdict": dictionaries of <= 47 values ride in the kernel's parameter block and a_ij comes from an
@@ -348,15 +250,15 @@ def test_dictionary_in_the_parameter_block_keeps_every_bit(gpu, threads, spc, do
         X, Y = gpu.Vector.from_host(xin), gpu.Vector(n)
         A, R = gmat(gpu, g), gmat(gpu, r)
         res = {}
-        for cd in list(range(20)) + [101, 102, 103, 108, 109, 110, 117, 118, 120, 121]:
-            gpu.set_option("spmv.pk_cdict", cd)
-            gpu.set_option("spmv.pk_cdict_dot", cd)
+        for cd in (0, 1, 2, 3):       # 0: shared-memory dictionary; 1: parameter block, U8 kernel also for the fused dot; 3: + U15 dot kernel
+            gpu.set_option("spmv.pk_cdict", cd & 1)
+            gpu.set_option("spmv.pk_cdict_dot", cd >> 1)
             d = B.spmv_dot_dev(X, Y, X)
             res[cd] = (B.spmv(xin), B.spmv_transpose(xin), np.float64(d), Y.download(),
                        B.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True)[3], np.float64(B.pcg_jacobi(np.zeros(n), b, 9, 1e-30, True)[2]),
                        B.gmres_jacobi(np.zeros(n), b, 20, 300, 1e-10, True, 1.0, True)[3],
                        A.spmv(g["x_in"]), A.spmv_transpose(g["x_in"]), R.spmv(r["x_in"]))
-        for cd in list(range(1, 20)) + [101, 102, 103, 108, 109, 110, 117, 118, 120, 121]:
+        for cd in (1, 2, 3):
             for u, v in zip(res[0], res[cd]):
                 assert np.array_equal(u, v)
         assert np.array_equal(res[1][7], g["y_Ax"]) and np.array_equal(res[1][8], g["y_ATx"]) and np.array_equal(res[1][9], r["y_Ax"])
@@ -549,11 +451,8 @@ def test_value_dictionary_padding_and_special_values(gpu):
             gpu.set_option("spmv.pk", 1)
             A = gpu.Matrix(rows, cols, rb, ci, va)
             assert A.value_dictionary()["packed"] and A.value_dictionary()["n_distinct"] == len(pool)
-            for tma in (0, 1):
-                gpu.set_option("spmv.pktma", tma)
-                y = A.spmv(x)
-                assert np.array_equal(y.view(np.uint64), y0.view(np.uint64))
-            gpu.set_option("spmv.pktma", PKTMA_DEFAULT)
+            y = A.spmv(x)
+            assert np.array_equal(y.view(np.uint64), y0.view(np.uint64))
             gpu.set_option("sell.pack_bits", 0)
             A6 = gpu.Matrix(rows, cols, rb, ci, va)
             gpu.set_option("sell.pack_bits", 32)
@@ -584,81 +483,115 @@ def test_value_dictionary_padding_and_special_values(gpu):
         _restore_pk(gpu)
 
 
-def test_column_compression_is_transparent(gpu):
-    """16-bit column deltas: brick slices compress completely, scattered columns fall back to 32 bit
-    per slice; results are bit-identical either way."""
+@pytest.mark.parametrize("inner,tiles,sigma", [(0, (8, 8, 8), 4096), (1, (8, 8, 64), 4096), (1, (2, 2, 1024), 512), (1, (1, 1, 1), 64),
+                                               (1, (16, 4, 64), 0)])
+def test_line_order_inside_graph_blocks_is_transparent(gpu, inner, tiles, sigma):
+    """"sell.block_inner" = 1: inside a cell of the graph blocks the rows follow the lines of the three distance
+    fields (reorder.cu, k_block_keys) instead of the caller's numbering.  A permutation like any other: every
+    product keeps its bits, PCG (row-ordered) and GMRES (caller's order) their iteration counts."""
     g = load_golden("brick_fe2_N6_num1.npz")
-    r = load_golden("random_ragged.npz")
-    n, rb, ci, va = gpu.brick_csr_host(2, 24, 1)
+    n, rb, ci, va = gpu.brick_csr_host(2, 12, 1)
     xin = hash_vector(n)
-    outs = {}
+    xs = gpu.brick_solution_host(2, 12, 1)
     try:
-        for comp in (1, 0):
-            gpu.set_option("sell.compress", comp)
-            A, R, B = gmat(gpu, g), gmat(gpu, r), gpu.Matrix(n, n, rb, ci, va)
-            assert A.format()["compressed"] == bool(comp)
-            assert np.array_equal(A.spmv(g["x_in"]), g["y_Ax"])
-            assert np.array_equal(R.spmv(r["x_in"]), r["y_Ax"])
-            assert np.array_equal(R.spmv_transpose(r["xt_in"] if "xt_in" in r else r["x_in"]), r["y_ATx"])
-            outs[comp] = B.spmv(xin)
-            if comp:
-                assert B.format()["wide_slices"] <= 0.05 * B.format()["nslices"]
-                # a matrix whose columns jump by more than 2^16 inside a slice must take the fallback
-                m = 70000
-                W = gpu.Matrix(64, m, np.arange(65), np.tile([0, m - 1], 32), np.ones(64))
-                assert W.format()["wide_slices"] > 0
-                xw = hash_vector(m)
-                assert np.array_equal(W.spmv(xw), np.tile([xw[0], xw[m - 1]], 32))
+        gpu.set_option("sell.block_order", 0)
+        B0 = gpu.Matrix(n, n, rb, ci, va)
+        y0, yt0 = B0.spmv(xin), B0.spmv_transpose(xin)
+        b = B0.spmv(xs)
+        s0 = B0.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True)
+        gpu.set_option("sell.block_order", 1)
+        gpu.set_option("sell.block_min_rows", 0)
+        gpu.set_option("sell.block_inner", inner)
+        gpu.set_option("sell.block_tile_a", tiles[0]); gpu.set_option("sell.block_tile_b", tiles[1]); gpu.set_option("sell.block_tile_c", tiles[2])
+        gpu.set_option("sell.sigma", sigma)
+        A = gmat(gpu, g)
+        assert A.layout()["block_ordered"]
+        assert np.array_equal(A.spmv(g["x_in"]), g["y_Ax"]) and np.array_equal(A.spmv_transpose(g["x_in"]), g["y_ATx"])
+        out = A.pcg_jacobi(np.zeros(A.rows), g["b"], 400, 1e-10, True)
+        assert out[1] == int(g["sym_pcgjac"][1]) and rel(out[3], g["sym_pcgjac_x"]) <= 1e-12
+        B = gpu.Matrix(n, n, rb, ci, va)
+        assert B.layout()["block_ordered"] and B.layout()["row_ordered_stream"]
+        assert np.array_equal(B.spmv(xin), y0) and np.array_equal(B.spmv_transpose(xin), yt0)
+        s1 = B.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True)
+        assert s1[0] and s1[1] == s0[1] and rel(s1[3], s0[3]) <= 1e-12
     finally:
-        gpu.set_option("sell.compress", 0)
-    assert np.array_equal(outs[0], outs[1])
+        gpu.set_option("sell.block_min_rows", 2.0e6)
+        gpu.set_option("sell.block_inner", 1)
+        gpu.set_option("sell.block_tile_a", 0); gpu.set_option("sell.block_tile_b", 0); gpu.set_option("sell.block_tile_c", 0)
+        gpu.set_option("sell.sigma", 4096)
 
 
-@pytest.mark.parametrize("compress,geometry", [(0, 0), (1, 0), (1, 1), (0, 2), (1, 3), (1, 4)])
-def test_tma_staged_kernel_is_bit_identical(gpu, compress, geometry):
-    """"spmv.kernel" = 2: the matrix stream goes through shared memory (cp.async.bulk + mbarrier);
-    same arithmetic, so every product is bit-identical to the reference and the solvers behave the same."""
+@pytest.mark.parametrize("block_min_rows,graph", [(0, 1), (2.0e6, 0)])
+def test_row_ordered_pcg_on_the_12_byte_stream(gpu, port, block_min_rows, graph):
+    """Operators without a value dictionary (variable coefficients: > 65 535 distinct values, or "sell.valdict" = 0)
+    get the row-ordered twin of their int32 columns, so PCG iterates on row-ordered vectors on the general
+    12-byte stream as well.  Products keep their bits, the solve its iteration count."""
+    n, rb, ci, va = gpu.brick_csr_host(2, 12, 1)
+    rng = np.random.default_rng(7)
+    # a symmetric positive definite operator with ~n distinct values: D A D with a smooth random diagonal D
+    d = 1.0 + 0.3 * rng.random(n)
+    rows = np.repeat(np.arange(n), np.diff(rb.astype(np.int64)))
+    vv = va * d[rows] * d[ci.astype(np.int64)]
+    P = port.PortMatrix(n, n, rb, ci, vv)
+    xs = gpu.brick_solution_host(2, 12, 1)
+    b = P.spmv(xs)
+    ref = P.pcg_jacobi(np.zeros(n), b, 2000, 1e-10, True)
+    xin = hash_vector(n)
     try:
-        gpu.set_option("sell.compress", compress)
-        gpu.set_option("spmv.kernel", 2)
-        gpu.set_option("spmv.tma_geometry", geometry)
-        for path in golden_files("brick_*.npz") + golden_files("random_*.npz"):
-            g = dict(np.load(path))
-            A = gmat(gpu, g)
-            assert np.array_equal(A.spmv(g["x_in"]), g["y_Ax"]), path
-            xt = g["xt_in"] if "xt_in" in g else g["x_in"]
-            assert np.array_equal(A.spmv_transpose(xt), g["y_ATx"]), path
-            if "sym_pcgjac" in g:
-                out = A.pcg_jacobi(np.zeros(A.rows), g["b"], 400, 1e-10, True)
-                assert out[1] == int(g["sym_pcgjac"][1]) and rel(out[3], g["sym_pcgjac_x"]) <= 1e-12
-            if "sym_minres" in g:
-                check_solve(A.minres(np.zeros(A.rows), g["b"], 400, 1e-9), g, "sym_minres", x_rtol=1e-8)
-            tag = "nonsym" if "nonsym" in path else "sym"
-            if f"{tag}_gmresjac_l1" in g:
-                check_solve(A.gmres_jacobi(np.zeros(A.rows), g["b"], 20, 400, 1e-10, True, 1.0, True), g, f"{tag}_gmresjac_l1")
-        # a larger brick (many CTAs, slices ending inside stages), several slices-per-CTA settings, fused dot
-        B = gpu.Matrix.brick(2, 20, 1)
-        n = B.rows
-        x, y, y2 = gpu.Vector(n), gpu.Vector(n), gpu.Vector(n)
-        x.fill_hash()
-        for spc in (1, 3, 16, 1000):
-            gpu.set_option("spmv.tma_slices_per_cta", spc)
-            d = B.spmv_dot_dev(x, y, x)
-            gpu.set_option("spmv.kernel", 0)
-            B.spmv_dev(x, y2)
-            gpu.set_option("spmv.kernel", 2)
-            assert np.array_equal(y.download(), y2.download()), spc
-            assert abs(d - gpu.dot(y2, x)) <= 4e-16 * float(np.abs(y2.download() * x.download()).sum())
-        # empty rows / empty matrix
-        E = gpu.Matrix(70, 70, np.r_[np.zeros(40), np.arange(31)].astype(np.uint64), np.arange(30), np.ones(30))
-        xe = hash_vector(70)
-        assert np.array_equal(E.spmv(xe), np.r_[np.zeros(40), xe[:30]])
-        assert gpu.spmv_tma_fault() == 0
+        gpu.set_option("sell.block_min_rows", block_min_rows)
+        gpu.set_option("pcg.graph", graph)
+        G = gpu.Matrix(n, n, rb, ci, vv)
+        assert G.value_dictionary()["n_distinct"] == 0 and G.layout()["row_ordered_kind"] == 2
+        assert G.layout()["block_ordered"] == (block_min_rows == 0)
+        assert np.array_equal(G.spmv(xin), P.spmv(xin)) and np.array_equal(G.spmv_transpose(xin), P.spmv_transpose(xin))
+        out = G.pcg_jacobi(np.zeros(n), b, 2000, 1e-10, True)
+        assert ref[0] and out[0] and abs(out[1] - ref[1]) <= 1 and rel(out[3], ref[3]) <= X_RTOL
+        gpu.set_option("pcg.reorder", 0)                      # the same solve in the caller's numbering
+        out0 = G.pcg_jacobi(np.zeros(n), b, 2000, 1e-10, True)
+        assert out0[1] == out[1] and rel(out0[3], out[3]) <= 1e-12
+        # a constant-coefficient matrix forced onto the 12-byte stream takes the same path
+        gpu.set_option("pcg.reorder", 1)
+        gpu.set_option("sell.valdict", 0)
+        H = gpu.Matrix(n, n, rb, ci, va)
+        assert H.layout()["row_ordered_kind"] == 2
+        Pc = port.PortMatrix(n, n, rb, ci, va)
+        bc = Pc.spmv(xs)
+        rc = Pc.pcg_jacobi(np.zeros(n), bc, 2000, 1e-10, True)
+        oc = H.pcg_jacobi(np.zeros(n), bc, 2000, 1e-10, True)
+        assert oc[0] and abs(oc[1] - rc[1]) <= 1 and rel(oc[3], rc[3]) <= X_RTOL
     finally:
-        gpu.set_option("sell.compress", 0)
-        gpu.set_option("spmv.kernel", 0)
-        gpu.set_option("spmv.tma_geometry", 0)
-        gpu.set_option("spmv.tma_slices_per_cta", 16)
+        gpu.set_option("sell.block_min_rows", 2.0e6)
+        gpu.set_option("pcg.graph", 1)
+        gpu.set_option("pcg.reorder", 1)
+        gpu.set_option("sell.valdict", 1)
+
+
+@pytest.mark.parametrize("m,left", [(8, True), (30, True), (30, False), (200, True)])
+def test_gmres_classical_gram_schmidt_option(gpu, port, m, left):
+    """"gmres.ortho" = 1: classical Gram-Schmidt as in the reference's distributed ModGMRES (StandardGramSchmidt,
+    krylovsolver.h:465-494, :862-866) -- all products of a column against the unmodified w in one fused kernel, then one
+    fused update.  Same Krylov space: iteration counts within +-1 of the serial (modified Gram-Schmidt) reference on a
+    well-conditioned nonsymmetric system (the level-set stand-in), solutions within 1e-8."""
+    n, rb, ci, va = gpu.brick_csr_host(2, 12, 1, 1.1)
+    rows = np.repeat(np.arange(n), np.diff(rb.astype(np.int64)))
+    va = va.copy()
+    va[ci.astype(np.int64) == rows] *= 1.25
+    P = port.PortMatrix(n, n, rb, ci, va)
+    G = gpu.Matrix(n, n, rb, ci, va)
+    xs = gpu.brick_solution_host(2, 12, 1)
+    b = P.spmv(xs)
+    r = P.gmres_jacobi(np.zeros(n), b, m, 2000, 1e-9, True, 1.0, left)
+    try:
+        gpu.set_option("gmres.ortho", 1)
+        l0 = gpu.launch_count()
+        o = G.gmres_jacobi(np.zeros(n), b, m, 2000, 1e-9, True, 1.0, left)
+        launches = gpu.launch_count() - l0
+    finally:
+        gpu.set_option("gmres.ortho", 0)
+    assert r[0] and o[0]
+    assert abs(o[1] - r[1]) <= 1, (o[1], r[1])
+    assert rel(o[3], r[3]) <= 1e-8
+    assert launches <= 8 * o[1] + 40                       # a handful of kernels per column, however long the basis
 
 
 def test_wide_and_scalar_vector_kernels_agree(gpu):
