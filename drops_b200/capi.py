@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _build
 
-PC_DUMMY, PC_JACOBI, PC_CHEBYSHEV = 0, 1, 2
+PC_DUMMY, PC_JACOBI, PC_CHEBYSHEV, PC_DIAG = 0, 1, 2, 3
 OP_MUL, OP_TRANSP_MUL = 0, 1
 
 _lib = None
@@ -96,6 +96,8 @@ SIGNATURES = {
     "drops_b200_gcr_dev": (_i, [_vp, _vp, _vp, _i, _d, _i, _ip, _dpp, _i]),
     "drops_b200_matrix_set_chebyshev": (_i, [_vp, _i, _d, _i, _d]),
     "drops_b200_chebyshev_lambda_max": (_i, [_vp, _i, _dpp]),
+    "drops_b200_matrix_set_diag_pc": (_i, [_vp, C.c_void_p]),
+    "drops_b200_diagpc_apply": (_i, [_vp, _vp, _vp]),
     "drops_b200_matrix_bbt_diag": (_i, [_vp, _dp]),
     "drops_b200_precond_apply_dev": (_i, [_vp, _i, _d, _i, _vp, _vp]),
     "drops_b200_pcg_general_dev": (_i, [_vp, _vp, _vp, _i, _d, _ip, _dpp, _i, _vp, _i]),
@@ -330,6 +332,11 @@ def supnorm(x):
     r = C.c_double()
     check(lib().drops_b200_supnorm(x.h, C.byref(r)))
     return r.value
+
+
+def diagpc_apply(D, b, x):
+    """DiagPcCL::Apply: x = D o b."""
+    check(lib().drops_b200_diagpc_apply(D.h, b.h, x.h))
 
 
 def axpy(a, x, y):
@@ -572,6 +579,15 @@ class Matrix:
             lambda_scale = 1.0 if normal_eq else 1.1
         check(lib().drops_b200_matrix_set_chebyshev(self.h, int(normal_eq), float(lambda_scale), int(degree),
                                                     float(ratio)))
+
+    def set_diag_pc(self, D):
+        """DiagPcCL(D): the vector PC_DIAG multiplies with (None forgets it)."""
+        if D is None:
+            check(lib().drops_b200_matrix_set_diag_pc(self.h, None))
+            return
+        D = _f64(D)
+        assert D.size == self.rows
+        check(lib().drops_b200_matrix_set_diag_pc(self.h, D.ctypes.data_as(C.c_void_p)))
 
     def chebyshev_lambda_max(self, normal_eq=False):
         r = C.c_double()

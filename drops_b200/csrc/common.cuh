@@ -383,6 +383,7 @@ struct drops_b200_matrix_s {
     double cheb_lambda[2] = {0.0, 0.0};
     double cheb_lambda_scale[2] = {0.0, 0.0};
     uint64_t cheb_lambda_epoch[2] = {0, 0};
+    double* diag_pc = nullptr;       // DiagPcCL's vector D (num/precond.h:618-642), rows entries, set by the caller
     double* bbt_diag = nullptr;      // diag(A A^T), BBTDiag num/precond.h:56-75
     uint64_t bbt_epoch = 0;
     uint64_t values_epoch = 1;       // bumped whenever the stored values change

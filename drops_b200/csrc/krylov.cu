@@ -899,7 +899,7 @@ int drops_b200_pcg_dev(drops_b200_matrix_t A, drops_b200_vector_t x, drops_b200_
 {
     DB_CHECK(require_ctx());
     DB_ARG(A && x && b && x->n == A->csr.rows && b->n == A->csr.rows, "PCG: incompatible dimensions");
-    if (pc == DROPS_B200_PC_CHEBYSHEV)      // PCGSolverCL<ChebyshevPcCL>: the preconditioner is a procedure
+    if (pc == DROPS_B200_PC_CHEBYSHEV || pc == DROPS_B200_PC_DIAG)      // ChebyshevPcCL is a procedure, DiagPcCL carries its own vector
         return pcg_general_device(A, false, x->d, b->d, pc, omega, max_iter, tol, relative, hist, hist_cap);
     return pcg_device(A, x->d, b->d, pc, omega, max_iter, tol, relative, hist, hist_cap, false);
 }
@@ -911,7 +911,7 @@ int drops_b200_pcg(drops_b200_matrix_t A, double* x, const double* b, int pc, do
     DB_ARG(A && x && b, "null argument");
     HostBridge hb(A);
     DB_CHECK(hb.up(A->csr.rows, x, b));
-    const int r = pc == DROPS_B200_PC_CHEBYSHEV
+    const int r = (pc == DROPS_B200_PC_CHEBYSHEV || pc == DROPS_B200_PC_DIAG)
         ? pcg_general_device(A, false, hb.dx, hb.db, pc, omega, max_iter, tol, relative, hist, hist_cap)
         : pcg_device(A, hb.dx, hb.db, pc, omega, max_iter, tol, relative, hist, hist_cap, false);
     if (r < 0) return r;

@@ -208,6 +208,10 @@ int precond_apply(drops_b200_matrix_s* M, int pc, double omega, bool ne, const d
         return vec_jacobi(n, omega, d, b, x);
     }
     if (pc == DROPS_B200_PC_CHEBYSHEV) return cheb_apply(M, ne, x, b);
+    if (pc == DROPS_B200_PC_DIAG) {                       // DiagPcCL::Apply: x = D_ * b   precond.h:626-631
+        if (M->diag_pc == nullptr) { set_error("DiagPcCL: no vector set (drops_b200_matrix_set_diag_pc)"); return DROPS_B200_E_ARG; }
+        return vec_mul(n, x, M->diag_pc, b);
+    }
     set_error("unknown preconditioner %d", pc);
     return DROPS_B200_E_ARG;
 }
@@ -226,15 +230,18 @@ int pcg_general_device(drops_b200_matrix_s* M, bool ne, double* x, const double*
     DB_ARG(M != nullptr, "null matrix");
     DB_ARG(ne || M->square, "PCG needs a square matrix");
     DB_ARG(max_iter && tol, "null max_iter/tol");
-    DB_ARG(pc == DROPS_B200_PC_DUMMY || pc == DROPS_B200_PC_JACOBI || pc == DROPS_B200_PC_CHEBYSHEV,
+    DB_ARG(pc == DROPS_B200_PC_DUMMY || pc == DROPS_B200_PC_JACOBI || pc == DROPS_B200_PC_CHEBYSHEV || pc == DROPS_B200_PC_DIAG,
            "unknown preconditioner");
+    DB_ARG(pc != DROPS_B200_PC_DIAG || M->diag_pc != nullptr, "DiagPcCL: no vector set (drops_b200_matrix_set_diag_pc)");
     Ctx& c = ctx();
     cudaStream_t st = c.stream;
     const size_t n = M->csr.rows;
-    const bool external = pc == DROPS_B200_PC_CHEBYSHEV;
+    // preconditioners that are a procedure (ChebyshevPcCL) or carry their own vector (DiagPcCL): z = M^-1 r is a separate
+    // step after the fused update, which then runs as if unpreconditioned
+    const bool external = pc == DROPS_B200_PC_CHEBYSHEV || pc == DROPS_B200_PC_DIAG;
     const double* d = M->diag;
-    if (pc != DROPS_B200_PC_DUMMY) DB_CHECK(cheb_diag(M, ne, &d));
-    if (external) { double l; DB_CHECK(cheb_lambda(M, ne, &l)); }    // M.SetDiag(...)        :122, :204
+    if (pc == DROPS_B200_PC_JACOBI || pc == DROPS_B200_PC_CHEBYSHEV) DB_CHECK(cheb_diag(M, ne, &d));
+    if (pc == DROPS_B200_PC_CHEBYSHEV) { double l; DB_CHECK(cheb_lambda(M, ne, &l)); }    // M.SetDiag(...)        :122, :204
     const int want_hist = hist ? std::max(hist_cap, 0) : 0;
     if (!M->d_scalars) DB_CHECK(dev_alloc((SolverScalars**)&M->d_scalars, 1));
     if (std::max(want_hist, 1) > M->hist_alloc) {
@@ -259,7 +266,7 @@ int pcg_general_device(drops_b200_matrix_s* M, bool ne, double* x, const double*
     DB_CHECK(op.apply(x, r, b, pt));                                 // r = b - Op x          :125, :205-207
     DB_CHECK(pcg_setup(n, r, b, d, p, S, dh));                       // normb, resid, z, rho, p = z
     if (external) {
-        DB_CHECK(cheb_apply(M, ne, z, r));
+        DB_CHECK(precond_apply(M, pc, omega, ne, r, z));
         DB_CHECK(pcg_set_rho(n, z, r, S));
         DB_CHECK(vec_copy(n, p, z));
     }
@@ -285,7 +292,7 @@ int pcg_general_device(drops_b200_matrix_s* M, bool ne, double* x, const double*
             }
             DB_CHECK(pcg_update(n, x, r, p, q, d, S, dh));
             if (external) {
-                DB_CHECK(cheb_apply(M, ne, z, r));
+                DB_CHECK(precond_apply(M, pc, omega, ne, r, z));
                 DB_CHECK(pcg_set_rho(n, z, r, S));
                 DB_CHECK(pcg_direction_z(n, p, z, S));
             } else {
@@ -529,8 +536,12 @@ struct Bridge {
 int check_pc_system(drops_b200_matrix_t A, int pc, bool ne)
 {
     DB_ARG(A != nullptr, "null matrix");
-    DB_ARG(pc == DROPS_B200_PC_DUMMY || pc == DROPS_B200_PC_JACOBI || pc == DROPS_B200_PC_CHEBYSHEV,
+    DB_ARG(pc == DROPS_B200_PC_DUMMY || pc == DROPS_B200_PC_JACOBI || pc == DROPS_B200_PC_CHEBYSHEV || pc == DROPS_B200_PC_DIAG,
            "unknown preconditioner");
+    if (pc == DROPS_B200_PC_DIAG) {
+        DB_ARG(!ne && A->diag_pc != nullptr, "DiagPcCL: no vector set (drops_b200_matrix_set_diag_pc)");
+        return 0;
+    }
     if (!ne && pc != DROPS_B200_PC_DUMMY && !A->diag_ok) {
         set_error("preconditioner needs a stored diagonal entry in every row");
         return DROPS_B200_E_NODIAG;
@@ -548,6 +559,25 @@ int drops_b200_matrix_set_chebyshev(drops_b200_matrix_t A, int normal_eq, double
     const int k = normal_eq ? 1 : 0;
     A->cheb_scale[k] = lambda_scale; A->cheb_degree[k] = degree; A->cheb_ratio[k] = eig_ratio;
     return 0;
+}
+
+int drops_b200_matrix_set_diag_pc(drops_b200_matrix_t A, const double* D)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(A != nullptr, "null matrix");
+    if (D == nullptr) { dev_free(A->diag_pc); A->diag_pc = nullptr; return 0; }
+    if (!A->diag_pc) DB_CHECK(dev_alloc(&A->diag_pc, A->csr.rows));
+    cudaStream_t st = ctx().stream;
+    if (A->csr.rows) DB_CUDA(cudaMemcpyAsync(A->diag_pc, D, A->csr.rows * sizeof(double), cudaMemcpyHostToDevice, st));
+    DB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int drops_b200_diagpc_apply(drops_b200_vector_t D, drops_b200_vector_t b, drops_b200_vector_t x)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(D && b && x && D->n == b->n && x->n == b->n, "DiagPcCL: incompatible dimensions");     // precond.h:629
+    return vec_mul(b->n, x->d, D->d, b->d);
 }
 
 int drops_b200_chebyshev_lambda_max(drops_b200_matrix_t A, int normal_eq, double* lambda_max)

@@ -1042,7 +1042,7 @@ int drops_b200_matrix_destroy(drops_b200_matrix_t M)
     if (ctx().inited) cudaStreamSynchronize(ctx().stream);
     free_csr(M->csr); free_sell(M->sell);
     free_csr(M->csr_t); free_sell(M->sell_t);
-    dev_free(M->diag); dev_free(M->diag_missing); dev_free(M->bbt_diag);
+    dev_free(M->diag); dev_free(M->diag_missing); dev_free(M->bbt_diag); dev_free(M->diag_pc);
     for (double* w : M->work) dev_free(w);
     for (double* w : M->ro_work) dev_free(w);
     dev_free(M->ro_diag_idx);

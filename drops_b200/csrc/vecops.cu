@@ -788,6 +788,17 @@ int cheb_step(size_t n, double* W, double* x, const double* res, const double* d
     return launch_stream<0>(n, OpChebStep{W, x, res, d, dt1, dt2}, "cheb");
 }
 
+struct OpMul {
+    double* z; const double* x; const double* y;
+    __device__ bool begin() { return true; }
+    __device__ void elem(size_t i, dd*) { z[i] = mul(x[i], y[i]); }
+    __device__ void finish(const dd*) {}
+};
+int vec_mul(size_t n, double* z, const double* x, const double* y)
+{
+    return launch_stream<0>(n, OpMul{z, x, y}, "vec");
+}
+
 struct OpAxpby {
     double a; double* y; double b; const double* x;
     __device__ bool begin() { return true; }

@@ -51,6 +51,7 @@ int vec_axpy(size_t n, double a, const double* x, double* y);                   
 int vec_z_xpay(size_t n, double* z, const double* x, double a, const double* y); // z = x + a*y
 int vec_z_xpaypby2(size_t n, double* z, const double* x, double a, const double* y, double b, const double* y2);
 int vec_jacobi(size_t n, double omega, const double* d, const double* b, double* x);  // x = (omega*b)/d
+int vec_mul(size_t n, double* z, const double* x, const double* y);               // z = x o y   (DiagPcCL::Apply, precond.h:626-631)
 int vec_fill(size_t n, double* x, double v);
 int vec_fill_hash(size_t n, double* x);
 int vec_copy(size_t n, double* dst, const double* src);

@@ -84,6 +84,28 @@ template <> struct PcTraits<ChebyshevPcCL> {
     }
 };
 template <> struct PcTraits<ChebyshevBBTPcCL> : public PcTraits<ChebyshevPcCL> {};   // precond.h:1531-1567
+/// DiagPcCL (precond.h:618-642): x = D o b with the caller's vector D.  Its only data member is the private
+/// reference `const VectorCL& D_` (stored as a pointer), read through the object representation; the vector is
+/// sent to the device with every Solve (the reference re-reads it in every Apply, so it may change between solves).
+template <> struct PcTraits<DiagPcCL> {
+    static const bool on_device = true;
+    static int kind() { return DROPS_B200_PC_DIAG; }
+    static double omega(const DiagPcCL&) { return 1.0; }
+    static void prepare(const DiagPcCL& pc, drops_b200_matrix_t h, bool normal_eq)
+    {
+        static_assert(sizeof(DiagPcCL) == sizeof(const VectorCL*), "DiagPcCL is expected to hold exactly the reference D_");
+        if (normal_eq) throw DROPSErrCL("DiagPcCL: not a preconditioner of the normal equations");
+        const VectorCL* D;
+        std::memcpy(&D, &pc, sizeof D);
+        size_t rows = 0;
+        check(drops_b200_matrix_info(h, &rows, 0, 0, 0, 0, 0));
+        if (D->size() != rows) throw DROPSErrCL("DiagPcCL: incompatible dimensions");           // precond.h:629
+        check(drops_b200_matrix_set_diag_pc(h, Addr(*D)));
+    }
+};
+/// Preconditioners the device runs inside PCG only: with them GMRES, BiCGStab, GCR ... keep the reference's templates.
+template <typename PC> struct PcgOnly
+    : std::integral_constant<bool, std::is_base_of<ChebyshevPcCL, PC>::value || std::is_same<DiagPcCL, PC>::value> {};
 
 template <typename Mat, typename PC>
 struct OnDevice : std::integral_constant<bool, IsHostMatrix<Mat>::value && PcTraits<PC>::on_device> {};
@@ -184,7 +206,7 @@ PCGNE(const Mat& A, VectorCL& u, const VectorCL& b, const DummyExchangeCL& ExAX,
 /// serial GMRES(m) :320-461 on the device, modified Gram-Schmidt (GMResSolverCL<JACPcCL>: factory code 302).
 /// calculate2norm (a debugging aid of the reference) is accepted and ignored.
 template <typename Mat, typename PreCon>
-DROPS_B200_IF(b200::OnDevice<Mat, PreCon>::value && !std::is_base_of<ChebyshevPcCL, PreCon>::value)
+DROPS_B200_IF(b200::OnDevice<Mat, PreCon>::value && !b200::PcgOnly<PreCon>::value)
 GMRES(const Mat& A, VectorCL& x, const VectorCL& b, const DummyExchangeCL&, PreCon& M, int m, int& max_iter, double& tol,
       bool measure_relative_tol = true, bool /*calculate2norm*/ = false, PreMethGMRES method = RightPreconditioning,
       std::ostream* output = 0)
@@ -225,7 +247,7 @@ PMINRES(const Mat& A, VectorCL& x, const VectorCL& rhs, const DummyExchangeCL&, 
     return b200::run_minres(b200::finest(A), x, rhs, 0, DROPS_B200_PC_DUMMY, 1.0, max_iter, tol, measure_relative_tol);
 }
 template <typename Mat, typename PreCon>
-DROPS_B200_IF(b200::OnDevice<Mat, PreCon>::value && !std::is_base_of<ChebyshevPcCL, PreCon>::value)
+DROPS_B200_IF(b200::OnDevice<Mat, PreCon>::value && !b200::PcgOnly<PreCon>::value)
 PMINRES(const Mat& A, VectorCL& x, const VectorCL& rhs, const DummyExchangeCL&, PLanczosONBCL<VectorCL, PreCon>& q,
         int& max_iter, double& tol, bool measure_relative_tol = false)
 {
@@ -236,7 +258,7 @@ PMINRES(const Mat& A, VectorCL& x, const VectorCL& rhs, const DummyExchangeCL&, 
 /// BICGSTAB :1189-1258 on the device.  On a breakdown the reference prints a message, sets max_iter to the
 /// iteration and returns false; so does this.
 template <typename Mat, typename PreCon>
-DROPS_B200_IF(b200::OnDevice<Mat, PreCon>::value && !std::is_base_of<ChebyshevPcCL, PreCon>::value)
+DROPS_B200_IF(b200::OnDevice<Mat, PreCon>::value && !b200::PcgOnly<PreCon>::value)
 BICGSTAB(const Mat& A, VectorCL& x, const VectorCL& b, const DummyExchangeCL&, PreCon& M, int& max_iter, double& tol,
          bool measure_relative_tol = true)
 {
@@ -254,7 +276,7 @@ BICGSTAB(const Mat& A, VectorCL& x, const VectorCL& b, const DummyExchangeCL&, P
 
 /// GCR(m) :1407-1483 on the device (min-alpha truncation).
 template <typename Mat, typename PreCon>
-DROPS_B200_IF(b200::OnDevice<Mat, PreCon>::value && !std::is_base_of<ChebyshevPcCL, PreCon>::value)
+DROPS_B200_IF(b200::OnDevice<Mat, PreCon>::value && !b200::PcgOnly<PreCon>::value)
 GCR(const Mat& A, VectorCL& x, const VectorCL& b, const DummyExchangeCL&, PreCon& M, int m, int& max_iter, double& tol,
     bool measure_relative_tol = true, std::ostream* output = 0)
 {
@@ -273,7 +295,7 @@ GCR(const Mat& A, VectorCL& x, const VectorCL& b, const DummyExchangeCL&, PreCon
 /// rand()); outputs follow the reference literally: tol returns the ABSOLUTE residual norm, max_iter the
 /// iterations done, and the bool is false when the tolerance was beaten inside the loop (:1689-1693).
 template <typename Mat, typename PreCon>
-DROPS_B200_IF(b200::OnDevice<Mat, PreCon>::value && !std::is_base_of<ChebyshevPcCL, PreCon>::value)
+DROPS_B200_IF(b200::OnDevice<Mat, PreCon>::value && !b200::PcgOnly<PreCon>::value)
 IDRS(const Mat& A, VectorCL& x, const VectorCL& rhs, const DummyExchangeCL&, PreCon& pc, int& max_iter, double& tol,
      bool measure_relative_tol = false, const int s = 4, double omega_bound = 0.7)
 {

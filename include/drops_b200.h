@@ -50,6 +50,8 @@ extern "C" {
 #define DROPS_B200_PC_JACOBI     1   /* JACPcCL,   num/precond.h:874 / :1155-1188: x = omega*b/a_ii */
 #define DROPS_B200_PC_CHEBYSHEV  2   /* ChebyshevPcCL num/precond.h:1463-1529 (PCG); ChebyshevBBTPcCL :1531-1567
                                       * (PCGNE).  Parameters: drops_b200_matrix_set_chebyshev.              */
+#define DROPS_B200_PC_DIAG       3   /* DiagPcCL, num/precond.h:618-642: x = D o b with a caller-supplied vector D
+                                      * (drops_b200_matrix_set_diag_pc); PCG only.                           */
 /* BlockMatrixOperationT of num/spblockmat.h:40 */
 #define DROPS_B200_OP_MUL        0
 #define DROPS_B200_OP_TRANSP_MUL 1
@@ -244,6 +246,11 @@ DROPS_B200_API int drops_b200_matrix_set_chebyshev(drops_b200_matrix_t A, int no
 /* What SetDiag computes (num/precond.h:1481-1491, :1537-1553): lambda_scale * MaxEigenvalueScaledMatrix
  * (:1080-1096, 10 power iterations on D^-1 A or D^-1 A A^T with D = BBTDiag).  Cached on the handle. */
 DROPS_B200_API int drops_b200_chebyshev_lambda_max(drops_b200_matrix_t A, int normal_eq, double* lambda_max);
+/* DiagPcCL(D), num/precond.h:618-642 (the Schur-complement preconditioner of num/oseenprecond.h:911-919): the vector
+ * the preconditioner multiplies with, rows entries; copied to the device and kept with the handle.  NULL forgets it.
+ * DiagPcCL::Apply itself is drops_b200_diagpc_apply: x_i = D_i * b_i (product rounded once, as the valarray expression). */
+DROPS_B200_API int drops_b200_matrix_set_diag_pc(drops_b200_matrix_t A, const double* D);
+DROPS_B200_API int drops_b200_diagpc_apply(drops_b200_vector_t D, drops_b200_vector_t b, drops_b200_vector_t x);
 /* BBTDiag, num/precond.h:56-75: diag(A A^T). */
 DROPS_B200_API int drops_b200_matrix_bbt_diag(drops_b200_matrix_t A, double* diag);
 /* x = M^-1 b: PC::Apply(A, x, b, ex) (normal_eq = 0) or PC::Apply(A, x, b, rowex, colex) on A A^T

@@ -140,7 +140,8 @@ ORC_API void orc_chebyshev(size_t rows, size_t cols, const double* Aval, const s
  *   kind 0: x = b (DummyPcCL)
  *   kind 1: x = omega*b/diag   (JACPcCL on A; for the normal equations the diagonal is BBTDiag --
  *           the _PAR JACPcCL specialisation for CompositeMatrixBaseCL, precond.h:1190-1229)
- *   kind 2: ChebyshevPcCL / ChebyshevBBTPcCL */
+ *   kind 2: ChebyshevPcCL / ChebyshevBBTPcCL
+ *   kind 3: DiagPcCL, x = D o b with the caller's vector (precond.h:618-642); diag holds D */
 typedef struct {
     int kind; double omega; double* diag; int degree; double lmax, ratio;
 } ext_pc;
@@ -159,14 +160,15 @@ static void pc_run(const ext_pc* P, const ext_op* O, double* x, const double* b)
     size_t k;
     if (P->kind == 0) memcpy(x, b, O->rows * sizeof(double));
     else if (P->kind == 1) for (k = 0; k < O->rows; ++k) x[k] = P->omega * b[k] / P->diag[k];
+    else if (P->kind == 3) for (k = 0; k < O->rows; ++k) x[k] = P->diag[k] * b[k];               /* x= D_*b  :630 */
     else chebyshev0(O, x, b, P->diag, P->degree, P->lmax, P->ratio);
 }
 
 /* PCG (krylovsolver.h:107-179) on a square A, and PCGNE (:199-252) on A A^T.  Same loop shape;
  * the differences are kept literal: PCG takes lambda = ParDot(q, p) with q = A*p (:149-151),
  * PCGNE alpha = rho / Norm_sq(A^T q) (:233-234) and r -= alpha*(A*pt) (:236). */
-ORC_API int orc_pcg_ext(size_t rows, size_t cols, const double* Aval, const size_t* Arow, const size_t* Acol, int ne,
-                        int pc_kind, double omega, double scale, int degree, double ratio,
+static int pcg_ext_core(size_t rows, size_t cols, const double* Aval, const size_t* Arow, const size_t* Acol, int ne,
+                        int pc_kind, double omega, double scale, int degree, double ratio, const double* user_D,
                         double* x, const double* b, int* max_iter, double* tol, int relative,
                         double* hist, int hist_cap, double* lambda_out)
 {
@@ -178,6 +180,7 @@ ORC_API int orc_pcg_ext(size_t rows, size_t cols, const double* Aval, const size
     size_t k; int i, conv = 0;
     O.tmp = vnew(cols);
     pc_setup(&P, &O, pc_kind, omega, scale, degree, ratio);
+    if (pc_kind == 3) memcpy(P.diag, user_D, n * sizeof(double));
     if (lambda_out) *lambda_out = P.lmax;
 
     op_mul(&O, r, x);
@@ -229,6 +232,23 @@ ORC_API int orc_pcg_ext(size_t rows, size_t cols, const double* Aval, const size
 done:
     free(r); free(z); free(p); free(q); free(pt); free(O.tmp); free(P.diag);
     return conv;
+}
+
+ORC_API int orc_pcg_ext(size_t rows, size_t cols, const double* Aval, const size_t* Arow, const size_t* Acol, int ne,
+                        int pc_kind, double omega, double scale, int degree, double ratio,
+                        double* x, const double* b, int* max_iter, double* tol, int relative,
+                        double* hist, int hist_cap, double* lambda_out)
+{
+    if (pc_kind < 0 || pc_kind > 2) return -1;
+    return pcg_ext_core(rows, cols, Aval, Arow, Acol, ne, pc_kind, omega, scale, degree, ratio, NULL, x, b, max_iter, tol,
+                        relative, hist, hist_cap, lambda_out);
+}
+
+/* PCGSolverCL<DiagPcCL> (krylovsolver.h:107-179 with precond.h:618-642): D has n entries. */
+ORC_API int orc_pcg_diagpc(size_t n, const double* Aval, const size_t* Arow, const size_t* Acol, const double* D,
+                           double* x, const double* b, int* max_iter, double* tol, int relative, double* hist, int hist_cap)
+{
+    return pcg_ext_core(n, n, Aval, Arow, Acol, 0, 3, 1.0, 1.0, 0, 1.0, D, x, b, max_iter, tol, relative, hist, hist_cap, NULL);
 }
 
 /* IDRS, krylovsolver.h:1579-1698.  Praw: the s shadow vectors as drawn at :1603-1608 (s*n, vector i

@@ -103,6 +103,12 @@ def main():
     out["comp_BtB"] = ref.composite_mul(B, 0, B, 1, gA["x_in"])      # B^T * (B x)
     out["comp_AB_T"] = ref.composite_mul(B, 1, A, 0, gA["x_in"], transposed=True)   # (A B^T)^T x = B (A^T x)
     out["comp_WWt"] = ref.composite_mul(W, 1, W, 0, xw)
+    # DiagPcCL (precond.h:618-642): a vector that is NOT the Jacobi diagonal; no random draws (keeps the arrays above)
+    D = 1.0 / (A.diag() * (1.0 + 0.05 * (np.arange(n) % 5)))
+    out["A_diagpc_D"] = D
+    out["A_diagpc_apply"] = ref.diagpc_apply(D, bA)
+    put("A_pcg_diagpc", A.pcg_diagpc(np.zeros(n), bA, 200, 1e-10, True, D))
+    put("A_pcg_diagpc_abs_maxit", A.pcg_diagpc(np.zeros(n), bA, 4, 1e-14, False, D))
     np.savez_compressed(os.path.join(GOLDEN, "ext_callers.npz"), **out)
     print("wrote ext_callers.npz with", len(out), "arrays")
 

@@ -60,6 +60,7 @@ def lib():
         "orc_max_eig_scaled": (d, [sz, sz] + csr + [i, _dp, i]),
         "orc_chebyshev": (None, [sz, sz] + csr + [i, _dp, _dp, _dp, i, d, d]),
         "orc_pcg_ext": (i, [sz, sz] + csr + [i, i, d, d, i, d, _dp, _dp, ip, dpp, i, vp, i, dpp]),
+        "orc_pcg_diagpc": (i, [sz] + csr + [_dp, _dp, _dp, ip, dpp, i, vp, i]),
         "orc_idrs": (i, [sz] + csr + [i, d, i, d, _dp, _dp, _dp, ip, dpp, i]),
         "orc_block_mul": (None, [vp, vp, vp, _szp, _szp, C.POINTER(C.c_int), _szp, _szp, _dp, _dp]),
     }
@@ -229,6 +230,15 @@ class PortMatrix:
 
     def pcg_chebyshev(self, x0, b, max_iter, tol, relative=False, scale=1.1, degree=3, ratio=30.0, hist=False):
         return self._pcg_ext(0, 2, 1.0, scale, degree, ratio, x0, b, max_iter, tol, relative, hist)
+
+    def pcg_diagpc(self, x0, b, max_iter, tol, relative, D, hist=False):
+        """PCGSolverCL<DiagPcCL> with DiagPcCL(D) (precond.h:618-642)."""
+        x = _f64(x0).copy()
+        it, res = C.c_int(int(max_iter)), C.c_double(float(tol))
+        h, hargs = self._hist(max_iter, hist)
+        conv = lib().orc_pcg_diagpc(self.rows, *self._csr, _f64(D), x, _f64(b), C.byref(it), C.byref(res), int(relative), *hargs)
+        out = (bool(conv), it.value, res.value, x)
+        return out + (h,) if hist else out
 
     def pcgne(self, u0, b, max_iter, tol, relative=False, pc=0, omega=1.0, scale=1.0, degree=3, ratio=30.0, hist=False):
         """pc 0 identity, 1 Jacobi on BBTDiag, 2 ChebyshevBBTPcCL."""

@@ -63,6 +63,8 @@ def lib():
         "ref_pcg_dummy": (i, [vp, _dp, _dp, ip, dpp, i, vp, i]),
         "ref_pcg_jacobi_timed": (i, [vp, _dp, _dp, d, ip, dpp, i]),
         "ref_cg": (i, [vp, _dp, _dp, ip, dpp, i, vp, i]),
+        "ref_pcg_diagpc": (i, [vp, _dp, _dp, _dp, ip, dpp, i]),
+        "ref_diagpc_apply": (None, [sz, _dp, _dp, _dp]),
         "ref_gmres_jacobi": (i, [vp, _dp, _dp, d, i, ip, dpp, i, i]),
         "ref_gmres_dummy": (i, [vp, _dp, _dp, i, ip, dpp, i, i]),
         "ref_bicgstab": (i, [vp, _dp, _dp, i, d, ip, dpp, i]),
@@ -222,6 +224,10 @@ class RefMatrix:
         return self._solve(lib().ref_pcg_jacobi_timed, x0, b, max_iter, tol,
                            pre=(float(omega),), post=(int(relative),), hist=None)
 
+    def pcg_diagpc(self, x0, b, max_iter, tol, relative, D):
+        """PCGSolverCL<DiagPcCL> with DiagPcCL(D) (precond.h:618-642)."""
+        return self._solve(lib().ref_pcg_diagpc, x0, b, max_iter, tol, pre=(_f64(D),), post=(int(relative),), hist=None)
+
     def cg(self, x0, b, max_iter, tol, relative=False, hist=False):
         return self._solve(lib().ref_cg, x0, b, max_iter, tol, post=(int(relative),), hist=hist)
 
@@ -324,6 +330,12 @@ def kahan_dot(x, y):
 
 def kahan_norm(x):
     return lib().ref_kahan_norm(len(x), _f64(x))
+
+
+def diagpc_apply(D, b):
+    x = np.zeros(len(b))
+    lib().ref_diagpc_apply(len(b), _f64(D), _f64(b), x)
+    return x
 
 
 def axpy(a, x, y):

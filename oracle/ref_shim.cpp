@@ -317,6 +317,32 @@ int ref_pcg_jacobi_timed(void* h, double* x, const double* b, double omega,
     return conv ? 1 : 0;
 }
 
+// PCGSolverCL<DiagPcCL>::Solve with DiagPcCL(D) (precond.h:618-642): x = D o b.
+int ref_pcg_diagpc(void* h, double* x, const double* b, const double* D, int* max_iter, double* tol, int relative)
+{
+    const DROPS::MatrixCL& A = static_cast<RefMatrix*>(h)->A;
+    const size_t n = A.num_rows();
+    DROPS::VectorCL xv(to_vec(x, n)), bv(to_vec(b, n)), Dv(to_vec(D, n));
+    DROPS::DiagPcCL pc(Dv);
+    DROPS::PCGSolverCL<DROPS::DiagPcCL> solver(pc, *max_iter, *tol, relative != 0);
+    solver.Solve(A, xv, bv, DROPS::DummyExchangeCL());
+    from_vec(xv, x);
+    const bool conv = solver.GetResid() <= *tol;
+    *max_iter = solver.GetIter();
+    *tol = solver.GetResid();
+    return conv ? 1 : 0;
+}
+
+// DiagPcCL::Apply (precond.h:626-631).
+void ref_diagpc_apply(size_t n, const double* D, const double* b, double* x)
+{
+    DROPS::VectorCL Dv(to_vec(D, n)), bv(to_vec(b, n)), xv(n);
+    DROPS::DiagPcCL pc(Dv);
+    DROPS::MatrixCL dummy;
+    pc.Apply(dummy, xv, bv, DROPS::DummyExchangeCL());
+    from_vec(xv, x);
+}
+
 // CGSolverCL::Solve (krylovsolver.h:1782-1802).
 int ref_cg(void* h, double* x, const double* b, int* max_iter, double* tol, int relative,
            double* hist, int hist_cap)

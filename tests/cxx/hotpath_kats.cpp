@@ -292,6 +292,20 @@ int main()
             std::printf("JACAPPLY z7: %.15e z100: %.15e\n", z[7], z[100]);
         }
         {
+            // PCG with DiagPcCL (precond.h:618-642): D = 1 / (a_ii + a perturbation that is not the Jacobi diagonal)
+            x = 0.;
+            VectorCL D(A.GetDiag());
+            for (size_t i = 0; i < N; ++i) D[i] = 1. / (D[i] * (1. + 0.05 * double(i % 5)));
+            DiagPcCL dpc(D);
+            PCGSolverCL<DiagPcCL> solver(dpc, 500, 1e-10, true);
+            solver.Solve(A, x, b, ex);
+            std::printf("PCGDIAG iterations: %d residual: %.3e error: %.3e\n", solver.GetIter(), solver.GetResid(),
+                        norm(VectorCL(x - xs)) / norm(xs));
+            VectorCL z(N);
+            dpc.Apply(A, z, b, ex);
+            std::printf("DIAGAPPLY z7: %.15e z100: %.15e\n", z[7], z[100]);
+        }
+        {
             // PCG with the Chebyshev polynomial preconditioner (precond.h:1463-1529); SetDiag prints lambda_max
             x = 0.;
             ChebyshevPcCL cpc(1.1, 3, 30.0);

@@ -124,6 +124,33 @@ def test_pcg_chebyshev_and_pcgne_against_reference(gpu, sysm):
         Cm.pcg(np.zeros(m2), E["bC"], 10, 1e-10, True, gpu.PC_CHEBYSHEV)       # not square
 
 
+def test_pcg_diagpc_against_reference(gpu, sysm):
+    """PCGSolverCL<DiagPcCL> and DiagPcCL::Apply (precond.h:618-642) against the compiled reference's fixtures."""
+    E, gA, gN, A, N, B, Cm = sysm
+    n = A.rows
+    D = E["A_diagpc_D"]
+    with pytest.raises(gpu.DropsB200Error):
+        A.pcg(np.zeros(n), gA["b"], 10, 1e-10, True, gpu.PC_DIAG)             # no vector set
+    A.set_diag_pc(D)
+    near(A.pcg(np.zeros(n), gA["b"], 200, 1e-10, True, gpu.PC_DIAG), E, "A_pcg_diagpc", 1e-10)
+    out = A.pcg(np.zeros(n), gA["b"], 4, 1e-14, False, gpu.PC_DIAG)
+    assert out[0] is False and out[1] == 4 and rel(out[3], E["A_pcg_diagpc_abs_maxit_x"]) <= 1e-12
+    assert abs(out[2] - E["A_pcg_diagpc_abs_maxit"][2]) <= 1e-10 * E["A_pcg_diagpc_abs_maxit"][2]
+    # D = omega / diag(A) is the Jacobi preconditioner: same iterates as the fused JACPcCL path
+    A.set_diag_pc(0.9 / A.diag())
+    a = A.pcg(np.zeros(n), gA["b"], 200, 1e-10, True, gpu.PC_DIAG)
+    b = A.pcg(np.zeros(n), gA["b"], 200, 1e-10, True, gpu.PC_JACOBI, 0.9)
+    assert a[0] and abs(a[1] - b[1]) <= 1 and rel(a[3], b[3]) <= 1e-10
+    A.set_diag_pc(None)
+    with pytest.raises(gpu.DropsB200Error):
+        A.pcg(np.zeros(n), gA["b"], 10, 1e-10, True, gpu.PC_DIAG)
+    with pytest.raises(gpu.DropsB200Error):
+        A.gmres(np.zeros(n), gA["b"], 10, 20, 1e-10, True, gpu.PC_DIAG)       # PCG only
+    dv, bv, xv = gpu.Vector.from_host(D), gpu.Vector.from_host(gA["b"]), gpu.Vector(n)
+    gpu.diagpc_apply(dv, bv, xv)
+    assert np.array_equal(xv.download(), E["A_diagpc_apply"])                  # bit-identical
+
+
 def test_idrs_against_reference(gpu, sysm):
     from oracle import ref as refconst       # RAND_MAX / shadow_from_draws: numpy only
     E, gA, gN, A, N, B, Cm = sysm

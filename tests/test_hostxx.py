@@ -20,7 +20,7 @@ EXPECTED = os.path.join(ROOT, "tests", "golden", "hotpath_kats.expected.txt")
 KEYS = ("LANCZOS", "MINRES2", "MINRES4", "PMINRES4", "PMINRES4D", "TRANSP_MUL", "B*c", "VECEXPR", "VECOPS",
         "EXCHANGE", "LAPLACE", "PCGJAC", "PCGJAC08", "CG", "PCGJAC5", "JACAPPLY", "GMRESJAC", "GMRESJACR",
         "VERSIONED", "hotpath_kats", "BICGSTAB2", "BICGSTAB4", "GCR2", "GCR4", "BICGSTABJAC", "GCRJAC", "IO out", "IO mtx", "IO vec", "LINCOMB", "BLOCK", "COMPOSITE", "PCGCHEB", "PCGNE",
-        "BBTDIAG", "CHEBAPPLY", "IDRS")
+        "BBTDIAG", "CHEBAPPLY", "IDRS", "PCGDIAG", "DIAGAPPLY")
 
 
 def parse(text):
@@ -126,7 +126,8 @@ def test_dropin_binary_matches_reference_output(lib_built):
     for key in ("BLOCK dims", "BLOCK S*b", "BLOCK transp_mul", "BLOCK nodiag", "BLOCK built", "COMPOSITE dims",
                 "COMPOSITE BBt", "COMPOSITE ABt", "COMPOSITE ABt_T", "BBTDIAG d0", "IDRS solved"):
         assert got[key] == exp[key], (key, got[key], exp[key])
-    for key in ("PCGCHEB iterations", "PCGNE iterations"):
+    assert got["DIAGAPPLY z7"] == exp["DIAGAPPLY z7"]                          # DiagPcCL::Apply, precond.h:626-631
+    for key in ("PCGCHEB iterations", "PCGNE iterations", "PCGDIAG iterations"):
         assert abs(got[key][0] - exp[key][0]) <= 1, (key, got[key], exp[key])
         assert got[key][1] <= 1e-10 and got[key][2] <= 1e-8, (key, got[key])
     assert got["PCGCHEB lambda_max"] == exp["PCGCHEB lambda_max"]              # as printed by SetDiag (6 digits)

@@ -39,6 +39,10 @@ def test_oracle_chebyshev_pcgne_match_reference_fixture(port):
     same(A.pcg_chebyshev(np.zeros(n), gA["b"], 200, 1e-10, True), E, "A_pcg_cheb")
     same(A.pcg_chebyshev(np.zeros(n), gA["b"], 200, 1e-8, False, 1.1, 5, 30.0), E, "A_pcg_cheb_d5_abs")
     same(A.pcg_chebyshev(np.zeros(n), gA["b"], 3, 1e-14, True), E, "A_pcg_cheb_maxit")
+    # DiagPcCL (precond.h:618-642)
+    same(A.pcg_diagpc(np.zeros(n), gA["b"], 200, 1e-10, True, E["A_diagpc_D"]), E, "A_pcg_diagpc")
+    same(A.pcg_diagpc(np.zeros(n), gA["b"], 4, 1e-14, False, E["A_diagpc_D"]), E, "A_pcg_diagpc_abs_maxit")
+    assert np.array_equal(E["A_diagpc_D"] * gA["b"], E["A_diagpc_apply"])
     for pc in (0, 1, 2):
         same(B.pcgne(np.zeros(m), E["bB"], 500, 1e-10, True, pc=pc, omega=1.0), E, f"B_pcgne_pc{pc}")
         same(Cm.pcgne(np.zeros(m2), E["bC"], 500, 1e-9, False, pc=pc, omega=0.8), E, f"C_pcgne_pc{pc}")
