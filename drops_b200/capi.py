@@ -96,6 +96,7 @@ SIGNATURES = {
     "drops_b200_gcr_dev": (_i, [_vp, _vp, _vp, _i, _d, _i, _ip, _dpp, _i]),
     "drops_b200_matrix_set_chebyshev": (_i, [_vp, _i, _d, _i, _d]),
     "drops_b200_chebyshev_lambda_max": (_i, [_vp, _i, _dpp]),
+    "drops_b200_matrix_line_segments": (_i, [_vp, C.POINTER(C.c_size_t)]),
     "drops_b200_matrix_set_diag_pc": (_i, [_vp, C.c_void_p]),
     "drops_b200_diagpc_apply": (_i, [_vp, _vp, _vp]),
     "drops_b200_matrix_bbt_diag": (_i, [_vp, _dp]),
@@ -401,7 +402,10 @@ class Matrix:
     def layout(self):
         bo, ro = C.c_int(), C.c_int()
         check(lib().drops_b200_matrix_layout(self.h, C.byref(bo), C.byref(ro)))
-        return {"block_ordered": bool(bo.value), "row_ordered_stream": bool(ro.value), "row_ordered_kind": ro.value}
+        ls = C.c_size_t()
+        check(lib().drops_b200_matrix_line_segments(self.h, C.byref(ls)))
+        return {"block_ordered": bool(bo.value), "row_ordered_stream": bool(ro.value), "row_ordered_kind": ro.value,
+                "line_segments": ls.value}
 
     def diag_index(self):
         """Length of the diagonal's value list when PCG reads the Jacobi diagonal as one byte per row (0: fp64 vector)."""

@@ -353,6 +353,7 @@ struct drops_b200_matrix_s {
     bool diag_ok = false;
     bool square = false;
     bool block_ordered = false;      // sell was built over the block order of reorder.cu
+    size_t line_segments = 0;        // complete 32-row line segments at the head of that order ("sell.line_order")
     uint64_t version = 0;
     size_t device_bytes = 0;
     // solver workspace cached with the matrix: vectors of max(rows, cols) doubles, grown on demand
@@ -398,7 +399,8 @@ int build_transpose(drops_b200_matrix_s* M);
 int build_sell(const CsrDev& A, SellOp& S, size_t* bytes, const int32_t* rowmap, size_t nsub,
                bool rowmap_is_permutation = false, bool type_sort = false);
 // block order of the rows of a square operator from its graph (reorder.cu); *d_order = nullptr: keep the caller's order
-int compute_block_order(const CsrDev& A, int32_t** d_order);
+// n_segments (optional): complete 32-row line segments at the head of the order ("sell.line_order")
+int compute_block_order(const CsrDev& A, int32_t** d_order, size_t* n_segments = nullptr);
 // a vector of <= max_values distinct bit patterns as one byte per entry + the sorted value list (matrix.cu)
 int build_value_index8(const double* d_val, size_t n, int max_values, uint8_t** d_idx, double* host_values, int* count);
 // one pass over the values: will this operator get the one-word packed stream (and with it the row-ordered twin)?

@@ -84,11 +84,10 @@ int pcg_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, doubl
     const double* diag = M->diag;
     if (ro) {
         const size_t npos = M->sell.npos;
-        // 0 diagonal, 1 x, 2 b, 3 r, 4 p, 5 q; 6 = the second direction buffer of "pcg.fuse_x" (allocated with it only)
-        const bool want_fuse_x = opt("pcg.fuse_x", 0.0) != 0.0;
-        if (M->ro_work.size() < 7) M->ro_work.resize(7, nullptr);
+        // 0 diagonal, 1 x, 2 b, 3 r, 4 p, 5 q
+        if (M->ro_work.size() < 6) M->ro_work.resize(6, nullptr);
         for (size_t k = 0; k < M->ro_work.size(); ++k)
-            if (!M->ro_work[k] && (k < 6 || want_fuse_x)) DB_CHECK(dev_alloc(&M->ro_work[k], npos));
+            if (!M->ro_work[k]) DB_CHECK(dev_alloc(&M->ro_work[k], npos));
         double* dp = M->ro_work[0]; double* xp = M->ro_work[1]; double* bp = M->ro_work[2];
         if (M->ro_diag_epoch != M->values_epoch) {
             DB_CHECK(vec_gather_perm(npos, M->sell.perm, M->diag, dp, 1.0));
@@ -163,28 +162,12 @@ int pcg_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, doubl
     const bool defer_x = !unpreconditioned_cg && opt("pcg.defer_x", 1.0) != 0.0 && opt("vec.wide", 1.0) != 0.0 &&
                          ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(r) |
                            reinterpret_cast<uintptr_t>(diag)) & 15u) == 0;
-    // "pcg.fuse_x" = 1 (row-ordered solves): x += alpha p rides on the SpMV of the next iteration, the
-    // direction alternates between two buffers (iteration j reads pbuf[j & 1], writes pbuf[~j & 1]).
-    // Off by default: measured on C2 the SpMV grows by 0.16 ms for the 1.2 GB it carries, the direction
-    // kernel shrinks by 0.10 ms (374 vs 385 it/s in the same run, profiles/r01_notes.md).
-    const bool fuse_x = ro && fused_dot && defer_x && opt("pcg.fuse_x", 0.0) != 0.0 && (check_every % 2) == 0 &&
-                        M->sell.pkp != nullptr && M->ro_work[6] != nullptr;
-    double* pbuf[2] = {p, fuse_x ? M->ro_work[6] : p};
     int iter_no = 0;                                                                // iterations enqueued so far
     auto one_iteration = [&]() -> int {
         SpmvArgs s;
-        double* pc_ = pbuf[iter_no & 1];
-        double* pn_ = pbuf[(iter_no + 1) & 1];
         ++iter_no;
-        s.x = pc_; s.y = q; s.done = &S->done; s.row_ordered = ro;                  // q = A p, lambda = q.p  :149-151
-        if (fused_dot) { s.dotv = pc_; s.dot_out = &S->lambda; }
-        if (fuse_x) {
-            s.xu = x; s.xu_p = pn_; s.xu_alpha = &S->alpha_prev; s.xu_iter = &S->iter; s.xu_applied = &S->x_iter;
-            DB_CHECK(spmv_apply(M, false, s));
-            DB_CHECK(pcg_update_r(nv, r, q, diag, S, dh));
-            DB_CHECK(pcg_direction_oop(nv, pn_, pc_, r, diag, S));
-            return 0;
-        }
+        s.x = p; s.y = q; s.done = &S->done; s.row_ordered = ro;                    // q = A p, lambda = q.p  :149-151
+        if (fused_dot) { s.dotv = p; s.dot_out = &S->lambda; }
         DB_CHECK(spmv_apply(M, false, s));
         if (!fused_dot) DB_CHECK(vec_dot_unless(nv, q, p, &S->lambda, &S->done));
         if (defer_x) {
@@ -213,7 +196,7 @@ int pcg_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, doubl
             cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
             if (ce != cudaSuccess) status = cuda_fail(ce, "begin capture", __FILE__, __LINE__);
             for (int k = 0; k < check_every && status == 0; ++k) status = one_iteration();
-            iter_no = 0;                                       // captured, not run: the chunk starts on buffer 0
+            iter_no = 0;                                       // captured, not run
             ce = cudaStreamEndCapture(st, &graph);
             if (status == 0 && ce != cudaSuccess) status = cuda_fail(ce, "end capture", __FILE__, __LINE__);
             if (status == 0) {
@@ -237,7 +220,7 @@ int pcg_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, doubl
             cudaError_t ce = cudaGraphLaunch(M->pcg_graph, st);
             if (ce != cudaSuccess) status = cuda_fail(ce, "graph launch", __FILE__, __LINE__);
             c.launches += M->pcg_graph_launches;
-            iter_no += check_every;                            // even: the next chunk starts on the same buffer
+            iter_no += check_every;
         } else {
             for (int k = 0; k < chunk && status == 0; ++k) status = one_iteration();
         }
@@ -261,7 +244,6 @@ int pcg_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, doubl
     cudaEventDestroy(ev[1]);
     if (status != 0) { cudaStreamSynchronize(st); return status; }
 
-    if (fuse_x) DB_CHECK(pcg_flush_x(nv, x, pbuf[0], pbuf[1], S));       // the update of the last completed iteration
     if (ro) DB_CHECK(vec_scatter_perm(M->sell.npos, M->sell.perm, x, x_user));
     DB_CHECK(fetch(S, &h, sizeof h));
     if (hist && want_hist > 0) {

@@ -842,7 +842,8 @@ int finalize_matrix(drops_b200_matrix_s* M)
     bool packs = false;
     DB_CHECK(will_pack_one_word(M->csr.val, M->csr.nnz, std::max(M->csr.cols, M->csr.rows + 4096), &packs));
     // (every square operator gets a row-ordered twin, packed or not: graph blocks pay together with it)
-    if (M->square && opt("sell.reorder", 1.0) != 0.0) DB_CHECK(compute_block_order(M->csr, &order));
+    M->line_segments = 0;
+    if (M->square && opt("sell.reorder", 1.0) != 0.0) DB_CHECK(compute_block_order(M->csr, &order, &M->line_segments));
     const int s = build_sell(M->csr, M->sell, &M->device_bytes, order, order ? M->csr.rows : 0, order != nullptr, packs);
     dev_free(order);
     M->block_ordered = s == 0 && order != nullptr;
@@ -1082,6 +1083,13 @@ int drops_b200_matrix_layout(drops_b200_matrix_t M, int* block_ordered, int* row
     DB_ARG(M != nullptr, "null matrix");
     if (block_ordered) *block_ordered = M->block_ordered;
     if (row_ordered_stream) *row_ordered_stream = M->sell.pkp != nullptr ? 1 : (M->sell.colp != nullptr ? 2 : 0);
+    return 0;
+}
+
+int drops_b200_matrix_line_segments(drops_b200_matrix_t M, size_t* n_segments)
+{
+    DB_ARG(M != nullptr && n_segments != nullptr, "null argument");
+    *n_segments = M->block_ordered ? M->line_segments : 0;
     return 0;
 }
 

@@ -10,9 +10,17 @@
 // DROPS hands over matrices, not meshes, so the blocks come from the matrix graph: three
 // breadth-first distance fields from three far-apart rows (a = farthest from row 0, b = farthest
 // from a, c = the row maximising d_a + d_b) are pseudo-coordinates; rows are sorted by the Morton
-// code of their cell (d_a / Ta, d_b / Tb, d_c / Tc) and, inside a cell, along the lines of the graph (k_block_keys).  The sliced-ELL windows are then cut
-// from this order (matrix.cu, build_sell with a row map), and the row-ordered twin stream numbers x
-// the same way.  Any permutation is valid -- the order only decides who shares an L1 -- so graphs
+// code of their cell (d_a / Ta, d_b / Tb, d_c / Tc).  The sliced-ELL windows are then cut from this order (matrix.cu,
+// build_sell with a row map), and the row-ordered twin stream numbers x the same way.
+//
+// Line segments ("sell.line_order", round 2): what bounds the packed product after the blocks is the L1 data pipe --
+// one wavefront per 128-byte line a 32-lane gather touches, 4.8 lines per gather with blocks of 8^3 (runs of 8
+// rows), floor 2 (profiles/r02_*).  Stencil matrices are translation invariant along the fastest direction of their
+// numbering: row r + s repeats row r with every column moved up by a small amount.  Such rows are chained
+// (k_line_next: same length, all column differences in [1, D], smallest s <= S), chains are ranked by pointer
+// jumping and cut into segments of 32; a complete segment is ONE slice, the unit the blocks are built from.  Entry j
+// of its 32 lanes is then a segment of another chain -- 32 consecutive positions of the row-ordered x, 2 to 3 lines --
+// and the rows left over (chain tails, boundary rows, graphs without lines) follow in the old per-row block order.  Any permutation is valid -- the order only decides who shares an L1 -- so graphs
 // without mesh structure, several components or unreachable rows cost nothing but the setup pass.
 #include "common.cuh"
 
@@ -73,31 +81,119 @@ __device__ __forceinline__ unsigned spread3(unsigned v)     // 10 bits -> every 
     return v;
 }
 
-// Sort key of a row: the Morton code of its cell (d_a / ta, d_b / tb, d_c / tc) in the high bits and, below it,
-// what orders the rows INSIDE a cell ("sell.block_inner"):
-//   0 = nothing (the stable sort keeps ascending row index: runs follow the caller's numbering),
-//   1 = (d_a, d_b, d_c) lexicographic, d_c fastest.  Neighbouring rows of the graph differ by at most 1 in every
-//       field, and on a mesh-like graph each field is piecewise an affine coordinate, so rows that agree in two
-//       fields and are consecutive in the third are a LINE of the mesh.  With a long cell in that direction
-//       ("sell.block_tile_c" = 64) the sigma windows, which then sort by row length, cut slices that are 32
-//       consecutive same-shape rows of one line: entry j of the 32 lanes gathers 32 consecutive positions of the
-//       row-ordered x (2-3 cache lines instead of ~5: the L1 wavefronts per gather are what bounds the packed
-//       product, profiles/r01_notes.md), and neighbouring lines reuse them from L1.
+// Morton code of the cell (d_a / ta, d_b / tb, d_c / tc) of a row (30 bits); rows the searches did not reach sort last.
+__device__ __forceinline__ unsigned cell_code(int a, int b, int c, int ta, int tb, int tc)
+{
+    if (a < 0 || b < 0 || c < 0) return 0x3fffffffu;
+    const unsigned ca = min(a / ta, 1022), cb = min(b / tb, 1022), cc = min(c / tc, 1022);
+    return spread3(ca) | (spread3(cb) << 1) | (spread3(cc) << 2);
+}
+
+// Sort key of a row without line segments: its cell; the stable sort keeps ascending row index inside a cell.
 __global__ void k_block_keys(long long n, const int32_t* __restrict__ da, const int32_t* __restrict__ db,
-                             const int32_t* __restrict__ dc, int ta, int tb, int tc, int inner,
+                             const int32_t* __restrict__ dc, int ta, int tb, int tc,
                              unsigned long long* __restrict__ key, int32_t* __restrict__ row)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     row[i] = (int32_t)i;
-    const int a = da[i], b = db[i], c = dc[i];
-    if (a < 0 || b < 0 || c < 0) { key[i] = 0x3fffffffull << 30; return; }      // not reachable: after everything else
-    const unsigned ca = min(a / ta, 1022), cb = min(b / tb, 1022), cc = min(c / tc, 1022);
-    unsigned long long k = (unsigned long long)(spread3(ca) | (spread3(cb) << 1) | (spread3(cc) << 2)) << 30;
-    if (inner == 1)
-        k |= ((unsigned long long)min(a - (int)ca * ta, 1023) << 20) | ((unsigned long long)min(b - (int)cb * tb, 1023) << 10) |
-             (unsigned long long)min(c - (int)cc * tc, 1023);
-    key[i] = k;
+    key[i] = cell_code(da[i], db[i], dc[i], ta, tb, tc);
+}
+
+// ---- line segments --------------------------------------------------------------------------------------------
+// nxt[r] = the first r' in (r, r + S] whose row repeats row r translated: same length and every column difference in
+// [1, D].  Two rows may claim the same successor; prv keeps the nearest one (atomicMax) and k_line_validate drops the other link.
+__global__ void k_line_next(int n, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int S, int D,
+                            int32_t* __restrict__ nxt, int32_t* __restrict__ prv)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int64_t b = rowptr[r];
+    const int len = (int)(rowptr[r + 1] - b);
+    int found = -1;
+    if (len > 0) {
+        for (int s = 1; s <= S && r + s < n && found < 0; ++s) {
+            const int64_t b2 = rowptr[r + s];
+            if ((int)(rowptr[r + s + 1] - b2) != len) continue;
+            bool ok = true;
+            for (int j = 0; j < len && ok; ++j) {
+                const int d = col[b2 + j] - col[b + j];
+                ok = d >= 1 && d <= D;
+            }
+            if (ok) found = r + s;
+        }
+    }
+    nxt[r] = found;
+    if (found >= 0) atomicMax(&prv[found], r);
+}
+
+// Keeps nxt[r] only where r is the predecessor its successor kept; anc/dist start the ranking: a head is its own
+// ancestor at distance 0, every other row points at its predecessor at distance 1.
+__global__ void k_line_validate(int n, int32_t* __restrict__ nxt, const int32_t* __restrict__ prv,
+                                int32_t* __restrict__ anc, int32_t* __restrict__ dist)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int f = nxt[r];
+    if (f >= 0 && prv[f] != r) nxt[r] = -1;
+    const int p = prv[r];
+    anc[r] = p >= 0 ? p : r;
+    dist[r] = p >= 0 ? 1 : 0;
+}
+
+// One round of pointer jumping (Wyllie): dist = steps to anc; *again is raised while some ancestor is not a head.
+__global__ void k_line_jump(int n, const int32_t* __restrict__ anc, const int32_t* __restrict__ dist,
+                            int32_t* __restrict__ anc2, int32_t* __restrict__ dist2, int* __restrict__ again)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int a = anc[r];
+    const int aa = anc[a];
+    anc2[r] = aa;
+    dist2[r] = dist[r] + dist[a];
+    if (anc[aa] != aa) *again = 1;
+}
+
+// The last row of a chain records the chain's length with its head.
+__global__ void k_line_length(int n, const int32_t* __restrict__ nxt, const int32_t* __restrict__ anc,
+                              const int32_t* __restrict__ dist, int32_t* __restrict__ clen)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    if (nxt[r] < 0) clen[anc[r]] = dist[r] + 1;
+}
+
+// Keys of the two stable sorts.  keyA puts the 32 rows of a complete segment side by side, in chain order (first row
+// of the segment, rank inside it); keyB is the cell of the segment's first row.  Rows outside complete segments keep
+// their own index and cell and sort after all segments (bit 30 of keyB).
+__global__ void k_line_keys(int n, const int32_t* __restrict__ prv, const int32_t* __restrict__ anc,
+                            const int32_t* __restrict__ dist, const int32_t* __restrict__ clen,
+                            const int32_t* __restrict__ da, const int32_t* __restrict__ db, const int32_t* __restrict__ dc,
+                            int ta, int tb, int tc, unsigned long long* __restrict__ keyA, unsigned* __restrict__ keyB,
+                            int32_t* __restrict__ row, unsigned long long* __restrict__ nfull)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    row[r] = r;
+    const int rank = dist[r];
+    const bool full = ((rank >> 5) + 1) * 32 <= clen[anc[r]];
+    int first = r;
+    if (full) for (int t = rank & 31; t > 0; --t) first = prv[first];
+    keyA[r] = ((unsigned long long)(unsigned)first << 5) | (unsigned long long)(full ? (rank & 31) : 0);
+    keyB[r] = cell_code(da[first], db[first], dc[first], ta, tb, tc) | (full ? 0u : (1u << 30));
+    if (full && (rank & 31) == 0) atomicAdd(nfull, 1ull);
+}
+
+__global__ void k_widen_u32(long long n, const unsigned* __restrict__ src, unsigned long long* __restrict__ dst)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+__global__ void k_gather_u32(long long n, const unsigned* __restrict__ src, const int32_t* __restrict__ idx, unsigned* __restrict__ dst)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
 }
 
 static inline int blocks_of(long long n, int t) { return (int)std::max<long long>(1, (n + t - 1) / t); }
@@ -146,7 +242,7 @@ static int argmax_i32(const int32_t* d, int n, int* out, void** tmp, size_t* tmp
 
 // *d_order (rows entries, caller frees) lists the rows in block order; nullptr when the option is off,
 // the operator has more rows than columns or is too small to profit ("sell.block_min_rows").
-int compute_block_order(const CsrDev& A, int32_t** d_order)
+int compute_block_order(const CsrDev& A, int32_t** d_order, size_t* n_segments)
 {
     *d_order = nullptr;
     // columns >= rows (the ghost columns of a partition) are no graph vertices: k_bfs_expand skips them
@@ -162,7 +258,8 @@ int compute_block_order(const CsrDev& A, int32_t** d_order)
     const int n = (int)A.rows;
     int32_t *da = nullptr, *db = nullptr, *dc = nullptr, *q0 = nullptr, *q1 = nullptr, *rows_in = nullptr, *rows_out = nullptr;
     unsigned long long *key_in = nullptr, *key_out = nullptr;
-    const int inner = (int)opt("sell.block_inner", 1.0);
+    const bool lines = opt("sell.line_order", 1.0) != 0.0;
+    if (n_segments) *n_segments = 0;
     int* d_count = nullptr;
     cub::KeyValuePair<int, int32_t>* d_kv = nullptr;
     void* tmp = nullptr;
@@ -187,21 +284,76 @@ int compute_block_order(const CsrDev& A, int32_t** d_order)
     count_launch();
     RO_CHECK(argmax_i32(dc, n, &c, &tmp, &tmp_bytes, d_kv, st));
     RO_CHECK(bfs(A, c, dc, q0, q1, d_count, st));
-    dev_free(q0); q0 = nullptr; dev_free(q1); q1 = nullptr;
     RO_CHECK(dev_alloc(&key_in, (size_t)n)); RO_CHECK(dev_alloc(&key_out, (size_t)n));
     RO_CHECK(dev_alloc(&rows_in, (size_t)n)); RO_CHECK(dev_alloc(&rows_out, (size_t)n));
-    k_block_keys<<<blocks_of(n, 256), 256, 0, st>>>(n, da, db, dc, ta, tb, tc, inner, key_in, rows_in);
-    count_launch();
-    size_t need = 0;
-    RO_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, key_in, key_out, rows_in, rows_out, n, 0, 60, st));
-    if (need > tmp_bytes) {
-        dev_free(tmp); tmp = nullptr; tmp_bytes = 0;
-        char* p = nullptr;
-        RO_CHECK(dev_alloc(&p, need));
-        tmp = p; tmp_bytes = need;
+    auto sort_pairs = [&](int bits) -> int {          // key_in/rows_in -> key_out/rows_out, stable
+        size_t need = 0;
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, need, key_in, key_out, rows_in, rows_out, n, 0, bits, st);
+        if (e != cudaSuccess) return cuda_fail(e, "block order: sort", __FILE__, __LINE__);
+        if (need > tmp_bytes) {
+            dev_free(tmp); tmp = nullptr; tmp_bytes = 0;
+            char* p = nullptr;
+            const int r = dev_alloc(&p, need);
+            if (r < 0) return r;
+            tmp = p; tmp_bytes = need;
+        }
+        e = cub::DeviceRadixSort::SortPairs(tmp, need, key_in, key_out, rows_in, rows_out, n, 0, bits, st);
+        if (e != cudaSuccess) return cuda_fail(e, "block order: sort", __FILE__, __LINE__);
+        count_launch();
+        return 0;
+    };
+    if (lines) {
+        // q0 = nxt, q1 = prv, then the ranking ping-pongs between (anc, dist) pairs
+        int32_t *anc[2] = {nullptr, nullptr}, *dst[2] = {nullptr, nullptr}, *clen = nullptr;
+        unsigned *kb = nullptr, *kb2 = nullptr;
+        unsigned long long* d_nfull = nullptr;
+        auto lfree = [&]() { dev_free(anc[0]); dev_free(anc[1]); dev_free(dst[0]); dev_free(dst[1]); dev_free(clen); dev_free(kb);
+                             dev_free(kb2); dev_free(d_nfull); };
+#define LN_CHECK(call) do { status = (call); if (status < 0) { lfree(); cleanup(); dev_free(rows_out); return status; } } while (0)
+#define LN_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { lfree(); cleanup(); dev_free(rows_out); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
+        for (int i = 0; i < 2; ++i) { LN_CHECK(dev_alloc(&anc[i], (size_t)n)); LN_CHECK(dev_alloc(&dst[i], (size_t)n)); }
+        LN_CHECK(dev_alloc(&clen, (size_t)n)); LN_CHECK(dev_alloc(&kb, (size_t)n)); LN_CHECK(dev_alloc(&kb2, (size_t)n));
+        LN_CHECK(dev_alloc(&d_nfull, 1));
+        const int S = std::max(1, (int)opt("sell.line_stride", 8.0)), D = std::max(1, (int)opt("sell.line_maxdiff", 64.0));
+        const int g = blocks_of(n, 256);
+        k_fill_i32<<<g, 256, 0, st>>>(n, q1, -1);
+        k_line_next<<<g, 256, 0, st>>>(n, A.rowptr, A.col, S, D, q0, q1);
+        k_line_validate<<<g, 256, 0, st>>>(n, q0, q1, anc[0], dst[0]);
+        count_launch(); count_launch(); count_launch();
+        int cur = 0;
+        for (int round = 0; round < 32; ++round) {
+            int again = 0;
+            LN_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), st));
+            k_line_jump<<<g, 256, 0, st>>>(n, anc[cur], dst[cur], anc[cur ^ 1], dst[cur ^ 1], d_count);
+            count_launch();
+            LN_CUDA(cudaMemcpyAsync(&again, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+            LN_CUDA(cudaStreamSynchronize(st));
+            cur ^= 1;
+            if (!again) break;
+        }
+        k_fill_i32<<<g, 256, 0, st>>>(n, clen, 0);
+        k_line_length<<<g, 256, 0, st>>>(n, q0, anc[cur], dst[cur], clen);
+        LN_CUDA(cudaMemsetAsync(d_nfull, 0, sizeof(unsigned long long), st));
+        k_line_keys<<<g, 256, 0, st>>>(n, q1, anc[cur], dst[cur], clen, da, db, dc, ta, tb, tc, key_in, kb, rows_in, d_nfull);
+        count_launch(); count_launch(); count_launch();
+        LN_CHECK(sort_pairs(37));                                            // keyA: (first row of the segment, rank in it)
+        k_gather_u32<<<g, 256, 0, st>>>(n, kb, rows_out, kb2);               // keyB in that order, widened for the sorter
+        k_widen_u32<<<g, 256, 0, st>>>(n, kb2, key_in);
+        count_launch(); count_launch();
+        std::swap(rows_in, rows_out);
+        LN_CHECK(sort_pairs(31));                                            // keyB: segments before single rows, by cell
+        unsigned long long nfull = 0;
+        LN_CUDA(cudaMemcpyAsync(&nfull, d_nfull, sizeof nfull, cudaMemcpyDeviceToHost, st));
+        LN_CUDA(cudaStreamSynchronize(st));
+        if (n_segments) *n_segments = (size_t)nfull;
+        lfree();
+#undef LN_CHECK
+#undef LN_CUDA
+    } else {
+        k_block_keys<<<blocks_of(n, 256), 256, 0, st>>>(n, da, db, dc, ta, tb, tc, key_in, rows_in);
+        count_launch();
+        RO_CHECK(sort_pairs(30));                                            // stable: equal keys keep ascending row index
     }
-    RO_CUDA(cub::DeviceRadixSort::SortPairs(tmp, need, key_in, key_out, rows_in, rows_out, n, 0, 60, st));   // stable: equal keys keep ascending row index
-    count_launch();
     RO_CUDA(cudaStreamSynchronize(st));
 #undef RO_CHECK
 #undef RO_CUDA

@@ -183,7 +183,6 @@ EpiArgs make_epi(const SpmvArgs& a)
     e.dd_in = a.dd_in;
     e.dd_out = a.dd_out;
     e.xghost = a.xghost;
-    e.xu = a.xu; e.xu_p = a.xu_p; e.xu_alpha = a.xu_alpha; e.xu_iter = a.xu_iter; e.xu_applied = a.xu_applied;
     e.n_owned = (int)a.n_owned;
     e.partials = c.partials + (size_t)a.slot * kPartialStride;
     e.ticket = c.tickets + (size_t)a.slot * kTicketStride;
@@ -253,7 +252,6 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a)
         return spmv_sell_pk(A, a);
     }
     DB_ARG(!a.row_ordered || A.colp != nullptr, "row-ordered vectors need the operator's row-ordered stream");
-    DB_ARG(a.xu == nullptr, "only the packed stream carries the PCG x update");
     int threads = (int)opt("spmv.threads", 128);
     if (threads < 32) threads = 32;
     if (threads > 512) threads = 512;

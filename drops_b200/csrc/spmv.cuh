@@ -33,14 +33,6 @@ struct SpmvArgs {
     long long n_owned = 0;
     // x, y, aux and dotv are vectors in the operator's row-ordered numbering (SellOp::pkp, npos entries)
     bool row_ordered = false;
-    // PCG x update carried by the product (packed stream only): every row also does
-    // xu_i += *xu_alpha * xu_p_i  when *xu_applied != *xu_iter, and the kernel that finishes the fused
-    // dot then sets *xu_applied = *xu_iter.  Needs the fused dot (its finishing step does the marking).
-    double* xu = nullptr;
-    const double* xu_p = nullptr;
-    const double* xu_alpha = nullptr;
-    const int* xu_iter = nullptr;
-    int* xu_applied = nullptr;
     const int* done = nullptr;     // optional device flag: kernel is a no-op when *done != 0
     int slot = 0;                  // reduction workspace slot (kernels that may overlap use different slots)
     cudaStream_t stream = nullptr; // default: ctx().stream

@@ -26,11 +26,6 @@ struct EpiArgs {
     int n_owned;
     dd* partials;
     unsigned* ticket;
-    double* xu;                 // carried x update (SpmvArgs::xu...)
-    const double* xu_p;
-    const double* xu_alpha;
-    const int* xu_iter;
-    int* xu_applied;
 };
 
 // s = row sum, av = the row's aux entry (d_i, b_i or z_i)
@@ -49,7 +44,6 @@ __device__ __forceinline__ double apply_epilogue(double s, double av, const EpiA
 // partitioned product -- unrounded (plus the earlier launches' *dd_in) to *dd_out.
 __device__ __forceinline__ void store_dot(const EpiArgs& e, dd total)
 {
-    if (e.xu_applied != nullptr) *e.xu_applied = *e.xu_iter;      // the carried x update of this launch is in
     if (e.dd_in != nullptr) total = dd_add(total, *e.dd_in);
     if (e.dd_out != nullptr) *e.dd_out = total;
     else *e.dot_out = dd_round(total);

@@ -27,8 +27,6 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
     DB_ARG(a.epilogue == EPI_NONE || a.aux != nullptr, "epilogue needs aux vector");
     DB_ARG(a.dotv == nullptr || a.dot_out != nullptr || a.dd_out != nullptr, "fused dot needs an output scalar");
     DB_ARG(a.dotv != a.y, "the partner of the fused dot must not be the output vector");   // the tail pass re-reads y
-    DB_ARG(a.xu == nullptr || (a.dotv != nullptr && a.xu_p && a.xu_alpha && a.xu_iter && a.xu_applied),
-           "the carried x update needs the fused dot and its scalars");
     if (A.rows == 0) return 0;
     // the fused-dot product with the dictionary in the parameter block has its own geometry (measured on C2 inside
     // PCG: 15 words in flight x 384-thread CTAs x 192 slices, 3 CTAs of <= 56 registers per SM)

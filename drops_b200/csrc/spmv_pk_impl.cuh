@@ -45,7 +45,29 @@ __device__ __forceinline__ double pk_value(const PkView& A, uint32_t idx)
 // of round 1): L2 prefetch of the next slice, a software-pipelined batch loop, a TMA-staged ring, a shared-memory
 // window of x, L1::no_allocate stream loads, a masked tail batch, the dot accumulator in registers or in a tail
 // pass -- none of them beat this form.
-template <bool EXACT, int U, bool SMEM, bool NOPAD, bool CD>
+// One batch: UB words in flight, then their UB gathers, then the UB products added left to right.
+template <bool EXACT, int UB, bool SMEM, bool NOPAD, bool CD>
+__device__ __forceinline__ double pk_batch(const PkView& A, const uint32_t* __restrict__ pp, int j, double sum, uint32_t cmask,
+                                           uint32_t wpad, int cbits, const double* __restrict__ x)
+{
+    uint32_t w[UB];
+    double xv[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) w[u] = __ldcs(pp + (size_t)(j + u) * 32);
+#pragma unroll
+    for (int u = 0; u < UB; ++u) xv[u] = __ldg(x + (w[u] & cmask));
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+        const double v = pk_value<SMEM, CD>(A, w[u] >> cbits);
+        const double t = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv[u])) : fma(v, xv[u], sum);
+        sum = (NOPAD || w[u] < wpad) ? t : sum;
+    }
+    return sum;
+}
+
+// TAIL: what the batches of U leave over runs as batches of 8, 4, 2 (a row of 27 entries is 15 + 8 + 4: three round
+// trips to memory) instead of one entry at a time.
+template <bool EXACT, int U, bool SMEM, bool NOPAD, bool CD, bool TAIL>
 __device__ __forceinline__ double pk_row_sum(const PkView& A, int64_t base, int width, int lane,
                                              const double* __restrict__ x)
 {
@@ -55,27 +77,13 @@ __device__ __forceinline__ double pk_row_sum(const PkView& A, int64_t base, int 
     const uint32_t wpad = (uint32_t)A.ndict << cbits;
     double sum = 0.0;
     int j = 0;
-    for (; j + U <= width; j += U) {
-        uint32_t w[U];
-        double xv[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) w[u] = __ldcs(pp + (size_t)(j + u) * 32);
-#pragma unroll
-        for (int u = 0; u < U; ++u) xv[u] = __ldg(x + (w[u] & cmask));
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const double v = pk_value<SMEM, CD>(A, w[u] >> cbits);
-            const double t = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv[u])) : fma(v, xv[u], sum);
-            sum = (NOPAD || w[u] < wpad) ? t : sum;
-        }
+    for (; j + U <= width; j += U) sum = pk_batch<EXACT, U, SMEM, NOPAD, CD>(A, pp, j, sum, cmask, wpad, cbits, x);
+    if (TAIL) {
+        if (U > 8 && j + 8 <= width) { sum = pk_batch<EXACT, 8, SMEM, NOPAD, CD>(A, pp, j, sum, cmask, wpad, cbits, x); j += 8; }
+        if (U > 4 && j + 4 <= width) { sum = pk_batch<EXACT, 4, SMEM, NOPAD, CD>(A, pp, j, sum, cmask, wpad, cbits, x); j += 4; }
+        if (U > 2 && j + 2 <= width) { sum = pk_batch<EXACT, 2, SMEM, NOPAD, CD>(A, pp, j, sum, cmask, wpad, cbits, x); j += 2; }
     }
-    for (; j < width; ++j) {
-        const uint32_t w = __ldcs(pp + (size_t)j * 32);
-        const double xv = __ldg(x + (w & cmask));
-        const double v = pk_value<SMEM, CD>(A, w >> cbits);
-        const double t = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv)) : fma(v, xv, sum);
-        sum = (NOPAD || w < wpad) ? t : sum;
-    }
+    for (; j < width; ++j) sum = pk_batch<EXACT, 1, SMEM, NOPAD, CD>(A, pp, j, sum, cmask, wpad, cbits, x);
     return sum;
 }
 
@@ -120,7 +128,10 @@ __device__ __forceinline__ double pk6_row_sum(const PkView& A, int64_t base, int
 // The fused dot fetches its partner AFTER the row sum (an L1 hit: the diagonal entry just gathered it) and
 // parks the accumulator in shared memory between slices, so the row sum runs with the registers of the
 // plain product (same per-thread order of the same products as any other form: bit-identical results).
-template <int EPI, bool EXACT, int DOT, int U, int MAXT, int MINB, bool SMEM, bool V6, bool CD>
+// LEAN (the U15 fused-dot form the PCG loop runs): 1 = batched tail; 2 = batched tail, and every warp asks L2 for
+// the stream of its NEXT slice (prefetch.global.L2, one 128-byte line per lane and round) before it sums the current one;
+// the extent of that slice was read one iteration earlier, so the prefetch waits for nothing.
+template <int EPI, bool EXACT, int DOT, int U, int MAXT, int MINB, bool SMEM, bool V6, bool CD, int LEAN = 0>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_spmv_sell_pk(const __grid_constant__ PkView A, const double* __restrict__ x, double* __restrict__ y, EpiArgs e)
 {
@@ -130,35 +141,57 @@ k_spmv_sell_pk(const __grid_constant__ PkView A, const double* __restrict__ x, d
     __shared__ dd acc_smem[DOT != 0 ? MAXT : 1];
     if (DOT != 0) acc_smem[threadIdx.x] = dd_zero();     // the thread's own slot: no barrier needed
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const long long s_begin = A.nslices * (long long)blockIdx.x / gridDim.x;
-    const long long s_end   = A.nslices * (long long)(blockIdx.x + 1) / gridDim.x;
+    const int s_begin = (int)(A.nslices * (long long)blockIdx.x / gridDim.x);
+    const int s_end   = (int)(A.nslices * (long long)(blockIdx.x + 1) / gridDim.x);
     if (SMEM) {
         for (int i = threadIdx.x; i <= A.ndict; i += blockDim.x) sdict[i] = A.dict[i];
         __syncthreads();
     }
     const double beta = (EPI == EPI_AXMBY) ? (e.beta != nullptr ? *e.beta : e.beta_val) : 0.0;
-    // PCG: x += alpha p of the previous iteration may ride on this product ("pcg.fuse_x")
-    const bool xupd = DOT != 0 && e.xu != nullptr && *e.xu_applied != *e.xu_iter;
-    const double xalpha = xupd ? *e.xu_alpha : 0.0;
 
-    for (long long s = s_begin + warp; s < s_end; s += nwarp) {
-        const int64_t base = A.slice_ptr[s];
-        const int width = (int)((A.slice_ptr[s + 1] - base) >> 5);
+    // LEAN: the extents of this warp's slices run two iterations ahead of their use -- (base, width) of slice s were read
+    // while s - 2 nwarp was summed, those of s + nwarp while s - nwarp was: neither the row sum nor the prefetch waits
+    int64_t base = 0, nbase = 0;
+    int width = 0, nwidth = 0;
+    if (LEAN == 2) {
+        if (s_begin + warp < s_end) {
+            base = A.slice_ptr[s_begin + warp];
+            width = (int)((A.slice_ptr[s_begin + warp + 1] - base) >> 5);
+        }
+        if (s_begin + warp + nwarp < s_end) {
+            nbase = A.slice_ptr[s_begin + warp + nwarp];
+            nwidth = (int)((A.slice_ptr[s_begin + warp + nwarp + 1] - nbase) >> 5);
+        }
+    }
+    for (int s = s_begin + warp; s < s_end; s += nwarp) {
+        int64_t n2base = 0;
+        int n2width = 0;
+        if (LEAN == 2) {
+            for (int l = lane; l < nwidth; l += 32) asm volatile("prefetch.global.L2 [%0];" :: "l"(A.pk + nbase + (size_t)l * 32));
+            const int s2 = s + 2 * nwarp;
+            if (s2 < s_end) {
+                n2base = A.slice_ptr[s2];
+                n2width = (int)((A.slice_ptr[s2 + 1] - n2base) >> 5);
+            }
+        } else {
+            base = A.slice_ptr[s];
+            width = (int)((A.slice_ptr[s + 1] - base) >> 5);
+        }
         // row-ordered twin (perm == nullptr): position s*32+lane IS the row of y, aux and the dot partner
-        const int row = A.perm != nullptr ? A.perm[s * 32 + lane] : (int)(s * 32 + lane);
+        const int row = A.perm != nullptr ? A.perm[(size_t)s * 32 + lane] : s * 32 + lane;
         double av = 0.0;
         if (row >= 0 && EPI != EPI_NONE) av = __ldg(e.aux + row);
         // 99.8 % of the slices of a sorted operator hold no padding word: their row sum needs no selects
         const bool nopad = !V6 && A.nopad != nullptr && A.nopad[s] != 0;      // warp-uniform
         const double sum = V6 ? pk6_row_sum<EXACT, U, SMEM>(A, base, width, lane, x)
-                         : nopad ? pk_row_sum<EXACT, U, SMEM, true, CD>(A, base, width, lane, x)
-                                 : pk_row_sum<EXACT, U, SMEM, false, CD>(A, base, width, lane, x);
+                         : nopad ? pk_row_sum<EXACT, U, SMEM, true, CD, (LEAN >= 1)>(A, base, width, lane, x)
+                                 : pk_row_sum<EXACT, U, SMEM, false, CD, (LEAN >= 1)>(A, base, width, lane, x);
         if (row >= 0) {
             const double out = apply_epilogue<EPI>(sum, av, e, beta);
             y[row] = out;
             if (DOT) acc_smem[threadIdx.x] = dd_add_prod(acc_smem[threadIdx.x], out, __ldg(e.dotv + row));
-            if (xupd) e.xu[row] = __dadd_rn(e.xu[row], __dmul_rn(xalpha, __ldcs(e.xu_p + row)));
         }
+        if (LEAN == 2) { base = nbase; width = nwidth; nbase = n2base; nwidth = n2width; }
     }
     dd acc[1] = {DOT != 0 ? acc_smem[threadIdx.x] : dd_zero()};
     if (DOT == 1) {
@@ -172,23 +205,23 @@ k_spmv_sell_pk(const __grid_constant__ PkView A, const double* __restrict__ x, d
     }
 }
 
-template <int EPI, bool EXACT, int U, int MAXT, int MINB, bool SMEM, bool V6, bool CD>
+template <int EPI, bool EXACT, int U, int MAXT, int MINB, bool SMEM, bool V6, bool CD, int LEAN = 0>
 static void launch_pk_d(const PkView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads, cudaStream_t st)
 {
     if (threads > MAXT) threads = MAXT;
     const size_t sh = SMEM ? ((size_t)v.ndict + 1) * sizeof(double) : 0;
     if (a.dotv == nullptr) {
-        k_spmv_sell_pk<EPI, EXACT, 0, U, MAXT, MINB, SMEM, V6, CD><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
+        k_spmv_sell_pk<EPI, EXACT, 0, U, MAXT, MINB, SMEM, V6, CD, LEAN><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
         return;
     }
     const long long nwarps = (long long)grid * (threads >> 5);
     const double mode = opt("spmv.dotmode", 0.0);
     const bool two_kernels = mode == 2.0 || (mode == 0.0 && grid > (int)kReduceFlat);
     if (two_kernels && nwarps <= kPartialStride) {
-        k_spmv_sell_pk<EPI, EXACT, 2, U, MAXT, MINB, SMEM, V6, CD><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
+        k_spmv_sell_pk<EPI, EXACT, 2, U, MAXT, MINB, SMEM, V6, CD, LEAN><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
         sum_warp_partials(nwarps, e, st);
     } else {
-        k_spmv_sell_pk<EPI, EXACT, 1, U, MAXT, MINB, SMEM, V6, CD><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
+        k_spmv_sell_pk<EPI, EXACT, 1, U, MAXT, MINB, SMEM, V6, CD, LEAN><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
     }
 }
 
@@ -208,9 +241,12 @@ static bool launch_pk(const PkView& v, const SpmvArgs& a, const EpiArgs& e, int 
         return true;
     }
     if (smem_ok && v.cdict_n > 0 && opt("spmv.pk_cdict", 1.0) != 0.0) {
-        if (EPI == EPI_NONE && EXACT && a.dotv != nullptr && opt("spmv.pk_cdict_dot", 1.0) != 0.0)
-            launch_pk_d<EPI_NONE, true, 15, 384, 3, false, false, true>(v, a, e, grid, threads, st);
-        else
+        if (EPI == EPI_NONE && EXACT && a.dotv != nullptr && opt("spmv.pk_cdict_dot", 1.0) != 0.0) {
+            const int lean = (int)opt("spmv.pk_lean", 2.0);    // 1: batched tail, 2: + L2 prefetch of the warp's next slice
+            if (lean == 2) launch_pk_d<EPI_NONE, true, 15, 384, 3, false, false, true, 2>(v, a, e, grid, threads, st);
+            else if (lean == 1) launch_pk_d<EPI_NONE, true, 15, 384, 3, false, false, true, 1>(v, a, e, grid, threads, st);
+            else launch_pk_d<EPI_NONE, true, 15, 384, 3, false, false, true>(v, a, e, grid, threads, st);
+        } else
             launch_pk_d<EPI, EXACT, 8, 512, 3, false, false, true>(v, a, e, grid, threads, st);
         return true;
     }

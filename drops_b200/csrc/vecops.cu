@@ -662,71 +662,6 @@ int pcg_direction_x(size_t n, double* x, double* p, const double* r, const doubl
     return 0;
 }
 
-__global__ void __launch_bounds__(kReduceThreads)
-k_pcg_direction_oop(size_t n, double* __restrict__ pn, const double* __restrict__ po, const double* __restrict__ r,
-                    const double* __restrict__ d, SolverScalars* S)
-{
-    if (S->done) return;
-    const double beta = dvd(S->rho, S->rho_1);                  // :173
-    const double omega = S->omega;
-    const bool jac = S->pc == DROPS_B200_PC_JACOBI;
-    const size_t n2 = n >> 1;
-    double2* pn2 = reinterpret_cast<double2*>(pn);
-    const double2* po2 = reinterpret_cast<const double2*>(po);
-    const double2* r2 = reinterpret_cast<const double2*>(r);
-    const double2* d2 = reinterpret_cast<const double2*>(d);
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
-        double2 pv = po2[i];
-        const double2 rv = r2[i];
-        double2 dv = make_double2(1.0, 1.0);
-        if (jac) dv = d2[i];
-        const double zx = jac ? dvd(mul(omega, rv.x), dv.x) : rv.x;
-        const double zy = jac ? dvd(mul(omega, rv.y), dv.y) : rv.y;
-        pv.x = add(zx, mul(beta, pv.x)); pv.y = add(zy, mul(beta, pv.y));   // :174
-        pn2[i] = pv;
-    }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-        const size_t i = n - 1;
-        pn[i] = add(precond(S->pc, omega, r[i], d, i), mul(beta, po[i]));
-    }
-}
-
-int pcg_direction_oop(size_t n, double* p_new, const double* p_old, const double* r, const double* d, SolverScalars* S)
-{
-    Ctx& c = ctx();
-    DB_ARG(aligned16(p_new, p_old, r, d), "pcg_direction_oop needs 16-byte aligned vectors");
-    ScopedTiming t("pcg.direction");
-    const int grid = vec_grid(n, kReduceThreads, 4);
-    k_pcg_direction_oop<<<grid, kReduceThreads, 0, c.stream>>>(n, p_new, p_old, r, d, S);
-    count_launch();
-    DB_CUDA(cudaGetLastError());
-    return 0;
-}
-
-__global__ void __launch_bounds__(kReduceThreads)
-k_pcg_flush_x(size_t n, double* __restrict__ x, const double* __restrict__ p_even, const double* __restrict__ p_odd,
-              const SolverScalars* S)
-{
-    const int it = S->iter;
-    if (S->x_iter == it) return;                                // nothing pending (no iteration ran)
-    const double* p = ((it - 1) & 1) ? p_odd : p_even;          // direction of the last completed iteration
-    const double alpha = S->alpha_prev;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        x[i] = add(x[i], mul(alpha, p[i]));                     // :154
-}
-
-int pcg_flush_x(size_t n, double* x, const double* p_even, const double* p_odd, SolverScalars* S)
-{
-    Ctx& c = ctx();
-    const int grid = vec_grid(n, kReduceThreads, 4);
-    k_pcg_flush_x<<<grid, kReduceThreads, 0, c.stream>>>(n, x, p_even, p_odd, S);
-    count_launch();
-    DB_CUDA(cudaGetLastError());
-    return 0;
-}
-
 // ------------------------------------------------------------------------------------------
 // PCG with an external preconditioner, Chebyshev, IDR(s) helpers
 // ------------------------------------------------------------------------------------------

@@ -87,12 +87,6 @@ int pcg_update_r(size_t n, double* r, const double* q, const double* d, SolverSc
                  dd* part_out = nullptr, const DiagIndex* di = nullptr);
 int pcg_direction_x(size_t n, double* x, double* p, const double* r, const double* d, SolverScalars* S,
                     const DiagIndex* di = nullptr);
-// x update carried by the SpMV of the NEXT iteration (SpmvArgs::xu, packed stream): the direction is then
-// written out of place, p_new = z + beta p_old (4 passes), because the SpMV that follows still reads
-// p_old for x += alpha p_old; pcg_flush_x applies the update of the last completed iteration after the
-// loop (p_even / p_odd: the two direction buffers, iteration j uses buffer j & 1).
-int pcg_direction_oop(size_t n, double* p_new, const double* p_old, const double* r, const double* d, SolverScalars* S);
-int pcg_flush_x(size_t n, double* x, const double* p_even, const double* p_odd, SolverScalars* S);
 // dot product into a device scalar, skipped while *done != 0
 int vec_dot_unless(size_t n, const double* x, const double* y, double* d_out, const int* done);
 

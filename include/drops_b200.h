@@ -131,6 +131,12 @@ DROPS_B200_API int drops_b200_matrix_value_dictionary(drops_b200_matrix_t A, int
  * ("pcg.reorder"): 1 = twin of the packed stream, 2 = twin of the int32 columns of the 12-byte stream (operators
  * without a value dictionary).  Both only change who shares a cache, never a result bit of A*x. */
 DROPS_B200_API int drops_b200_matrix_layout(drops_b200_matrix_t A, int* block_ordered, int* row_ordered_stream);
+/* "sell.line_order" (default on, part of the block order): rows that repeat each other translated along the fastest
+ * direction of the caller's numbering (same length, every column moved up by 1..."sell.line_maxdiff", at most
+ * "sell.line_stride" rows apart) are chained and cut into segments of 32; a complete segment is one slice, so entry j of
+ * its lanes gathers 32 consecutive positions of the row-ordered x.  *n_segments = complete segments of A's operator
+ * (0: no lines found, or A is not block ordered).  Never changes a result bit of A*x. */
+DROPS_B200_API int drops_b200_matrix_line_segments(drops_b200_matrix_t A, size_t* n_segments);
 /* Jacobi diagonal of the row-ordered PCG as one byte per row ("pcg.diag_index"; JACPcCL's diag_, num/precond.h:1162-1177,
  * holds a handful of distinct values on constant-coefficient operators): *n_values = length of the value list the
  * last PCG-Jacobi solve on A built, 0 when the diagonal is read as an fp64 vector.  Never changes a result bit. */

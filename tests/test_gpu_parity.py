@@ -483,42 +483,88 @@ def test_value_dictionary_padding_and_special_values(gpu):
         _restore_pk(gpu)
 
 
-@pytest.mark.parametrize("inner,tiles,sigma", [(0, (8, 8, 8), 4096), (1, (8, 8, 64), 4096), (1, (2, 2, 1024), 512), (1, (1, 1, 1), 64),
-                                               (1, (16, 4, 64), 0)])
-def test_line_order_inside_graph_blocks_is_transparent(gpu, inner, tiles, sigma):
-    """"sell.block_inner" = 1: inside a cell of the graph blocks the rows follow the lines of the three distance
-    fields (reorder.cu, k_block_keys) instead of the caller's numbering.  A permutation like any other: every
-    product keeps its bits, PCG (row-ordered) and GMRES (caller's order) their iteration counts."""
-    g = load_golden("brick_fe2_N6_num1.npz")
-    n, rb, ci, va = gpu.brick_csr_host(2, 12, 1)
+@pytest.mark.parametrize("cells,lines,tiles,sigma,stride", [(12, 1, (8, 8, 8), 4096, 8), (40, 0, (8, 8, 8), 4096, 8), (40, 1, (8, 8, 8), 4096, 8),
+                                                            (40, 1, (3, 5, 2), 512, 2), (40, 1, (16, 16, 16), 64, 1), (36, 1, (8, 8, 8), 0, 8)])
+def test_line_segments_in_graph_blocks_are_transparent(gpu, cells, lines, tiles, sigma, stride):
+    """"sell.line_order": rows that repeat each other translated along the caller's numbering are chained and cut into
+    segments of 32 = one slice each (reorder.cu).  A permutation like any other: every product keeps its bits, PCG
+    (row-ordered) its iteration count; the P2 brick has lines of cells - 3 ... cells - 1 same-shape rows."""
+    n, rb, ci, va = gpu.brick_csr_host(2, cells, 1)
     xin = hash_vector(n)
-    xs = gpu.brick_solution_host(2, 12, 1)
+    xs = gpu.brick_solution_host(2, cells, 1)
     try:
         gpu.set_option("sell.block_order", 0)
         B0 = gpu.Matrix(n, n, rb, ci, va)
+        assert B0.layout()["line_segments"] == 0
         y0, yt0 = B0.spmv(xin), B0.spmv_transpose(xin)
         b = B0.spmv(xs)
         s0 = B0.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True)
         gpu.set_option("sell.block_order", 1)
         gpu.set_option("sell.block_min_rows", 0)
-        gpu.set_option("sell.block_inner", inner)
+        gpu.set_option("sell.line_order", lines)
+        gpu.set_option("sell.line_stride", stride)
         gpu.set_option("sell.block_tile_a", tiles[0]); gpu.set_option("sell.block_tile_b", tiles[1]); gpu.set_option("sell.block_tile_c", tiles[2])
         gpu.set_option("sell.sigma", sigma)
-        A = gmat(gpu, g)
-        assert A.layout()["block_ordered"]
-        assert np.array_equal(A.spmv(g["x_in"]), g["y_Ax"]) and np.array_equal(A.spmv_transpose(g["x_in"]), g["y_ATx"])
-        out = A.pcg_jacobi(np.zeros(A.rows), g["b"], 400, 1e-10, True)
-        assert out[1] == int(g["sym_pcgjac"][1]) and rel(out[3], g["sym_pcgjac_x"]) <= 1e-12
         B = gpu.Matrix(n, n, rb, ci, va)
-        assert B.layout()["block_ordered"] and B.layout()["row_ordered_stream"]
+        lay = B.layout()
+        assert lay["block_ordered"] and lay["row_ordered_stream"]
+        if lines and cells >= 36 and stride >= 2:
+            # 8 DOF classes, (cells - 1)^2 lines each, at least one complete segment per interior line
+            assert lay["line_segments"] >= 6 * (cells - 3) ** 2, lay
+        elif not lines:
+            assert lay["line_segments"] == 0
         assert np.array_equal(B.spmv(xin), y0) and np.array_equal(B.spmv_transpose(xin), yt0)
         s1 = B.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True)
         assert s1[0] and s1[1] == s0[1] and rel(s1[3], s0[3]) <= 1e-12
+        gm0 = B0.gmres_jacobi(np.zeros(n), b, 20, 60, 1e-10, True, 1.0, True)
+        gm1 = B.gmres_jacobi(np.zeros(n), b, 20, 60, 1e-10, True, 1.0, True)
+        assert gm1[1] == gm0[1] and np.array_equal(gm1[3], gm0[3])      # caller's order: same bits
     finally:
         gpu.set_option("sell.block_min_rows", 2.0e6)
-        gpu.set_option("sell.block_inner", 1)
+        gpu.set_option("sell.line_order", 1)
+        gpu.set_option("sell.line_stride", 8)
         gpu.set_option("sell.block_tile_a", 0); gpu.set_option("sell.block_tile_b", 0); gpu.set_option("sell.block_tile_c", 0)
         gpu.set_option("sell.sigma", 4096)
+
+
+def test_line_segments_on_matrices_without_lines(gpu):
+    """Random patterns, a tridiagonal matrix (ONE chain of all rows) and a matrix of empty rows: the chain search finds
+    nothing or everything, the products keep their bits."""
+    rng = np.random.default_rng(11)
+    try:
+        gpu.set_option("sell.block_min_rows", 0)
+        n = 5000
+        rows = [np.unique(np.r_[i, rng.choice(n, rng.integers(0, 12), replace=False)]) for i in range(n)]
+        rb = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.uint64)
+        ci = np.concatenate(rows)
+        ci = ci.astype(np.uint64)
+        va = rng.standard_normal(len(ci))
+        x = rng.standard_normal(n)
+        gpu.set_option("sell.block_order", 0)
+        y0 = gpu.Matrix(n, n, rb, ci, va).spmv(x)
+        gpu.set_option("sell.block_order", 1)
+        A = gpu.Matrix(n, n, rb, ci, va)
+        assert A.layout()["block_ordered"] and np.array_equal(A.spmv(x), y0)
+        # tridiagonal: rows 1..n-2 are one chain
+        n = 4099
+        lens = np.full(n, 3); lens[0] = lens[-1] = 2
+        rb = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        ci = np.concatenate([[0, 1]] + [[i - 1, i, i + 1] for i in range(1, n - 1)] + [[n - 2, n - 1]]).astype(np.uint64)
+        va = np.concatenate([[2.0, -1.0]] + [[-1.0, 2.0, -1.0]] * (n - 2) + [[-1.0, 2.0]])
+        x = rng.standard_normal(n)
+        gpu.set_option("sell.block_order", 0)
+        T0 = gpu.Matrix(n, n, rb, ci, va)
+        y0 = T0.spmv(x)
+        s0 = T0.pcg_jacobi(np.zeros(n), y0, 50, 1e-30, True)
+        gpu.set_option("sell.block_order", 1)
+        T = gpu.Matrix(n, n, rb, ci, va)
+        assert T.layout()["line_segments"] == (n - 2) // 32
+        assert np.array_equal(T.spmv(x), y0) and np.array_equal(T.spmv_transpose(x), T0.spmv_transpose(x))
+        s1 = T.pcg_jacobi(np.zeros(n), y0, 50, 1e-30, True)
+        assert s1[1] == s0[1] == 50 and rel(s1[3], s0[3]) <= 1e-12
+    finally:
+        gpu.set_option("sell.block_order", 1)
+        gpu.set_option("sell.block_min_rows", 2.0e6)
 
 
 @pytest.mark.parametrize("block_min_rows,graph", [(0, 1), (2.0e6, 0)])
