@@ -430,15 +430,21 @@ def run_ours(args):
         capi.set_option("sell.valdict", 1)
         A_main = A
         A = G12
-        G = timed_steps(1, 1, False)
+        g_layout = G12.layout()
+        G = timed_steps(args.warmup, args.steps, False)
         A = A_main
         G12.close()
         g_spmv_ms = G["spmv"][0] / max(G["spmv"][1], 1)
-        general = {"iterations_per_s": iters / (G["ms"] / 1e3), "spmv_avg_launch_ms": g_spmv_ms,
+        general = {"iterations_per_s": args.steps * iters / (G["ms"] / 1e3), "spmv_avg_launch_ms": g_spmv_ms,
+                   "steps": args.steps, "warmup": args.warmup, "block_ordered": g_layout["block_ordered"],
+                   "row_ordered_stream": g_layout["row_ordered_kind"], "line_segments": g_layout["line_segments"],
                    "spmv_achieved_gbs": survey_spmv_bytes / (g_spmv_ms / 1e3) / 1e9,
                    "spmv_frac": survey_spmv_bytes / (g_spmv_ms / 1e3) / 1e9 / peak,
-                   "iteration_frac": (12.0 * nnz + 4.0 * (n + 1) + general_passes * 8.0 * n) * iters / (G["ms"] / 1e3) / 1e9 / peak,
-                   "note": "sell.valdict = 0: int32 column + fp64 value per entry, caller's row order, 1 step after 1 warm-up"}
+                   "iteration_frac": (12.0 * nnz + 4.0 * (n + 1) + general_passes * 8.0 * n) * args.steps * iters / (G["ms"] / 1e3) / 1e9 / peak,
+                   "traffic_source": "profiles/r02_ncu_spmv_12B.raw.csv",
+                   "note": "sell.valdict = 0: int32 column + fp64 value per entry (what a matrix without a value dictionary runs), graph "
+                           "blocks + line segments + row-ordered PCG as on the packed stream (row_ordered_stream 2 = twin of the int32 "
+                           "columns), same warm-up and step count as the headline"}
         assert abs(G["resid"] - resid) <= 1e-9 * abs(resid), (G["resid"], resid)     # same system, same 200 iterations
 
     # ---- the other two solvers of the path on the same system (device-resident, fixed work) ---------
@@ -558,27 +564,32 @@ def run_ours(args):
 
 
 def other_solvers(capi, A, x, b, n, nnz, entry_bytes, peak):
-    """GMRESSolverCL<JACPcCL> (restart 30, left preconditioning, modified Gram-Schmidt as the serial reference,
-    krylovsolver.h:320-461) and MResSolverCL (krylovsolver.h:1069-1152) on the C2 system, device-resident, tol = 0 so
-    that the iteration count is fixed.  `survey_frac` uses SURVEY.md 8(d)'s byte counts with the matrix stream this
-    run reads: GMRES inner step i moves the matrix + 8n (4 (i + 1) + 5) bytes (MGS-faithful), MINRES matrix + 15 * 8n."""
+    """GMResSolverCL<JACPcCL> at the restart cdrdrops uses (100, poisson/cdrdrops.cpp + its json; left preconditioning) and
+    MResSolverCL (krylovsolver.h:1069-1152) on the C2 system, device-resident, tol = 0 so that the iteration count is
+    fixed.  GMRES twice: modified Gram-Schmidt, the serial reference (krylovsolver.h:378-381; step i moves the matrix +
+    8n (4 (i + 1) + 5) bytes), and the fused classical Gram-Schmidt of the reference's distributed ModGMRES
+    ("gmres.ortho" = 1, :465-494: matrix + 8n (2 (i + 1) + 7)).  MINRES: matrix + 15 * 8n.  `survey_frac` applies these
+    SURVEY.md 8(d) counts to the matrix stream this run reads."""
     out = {}
     mat = entry_bytes * nnz + 4.0 * (n + 1)
-    restart, cycles = 30, 2
+    restart, cycles = 100, 1
     its = restart * cycles
+    for name, ortho, passes in (("gmres_jacobi_restart100_mgs", 0, lambda i: 4.0 * (i + 1) + 5.0),
+                                ("gmres_jacobi_restart100_cgs", 1, lambda i: 2.0 * (i + 1) + 7.0)):
+        capi.set_option("gmres.ortho", ortho)
 
-    def run_gmres():
-        x.fill(0.0)
-        return A.gmres_dev(x, b, restart, its, 0.0, True)
-    run_gmres()
-    capi.synchronize(); capi.timer_start()
-    conv, it, res = run_gmres()
-    ms = capi.timer_stop()
-    gm_bytes = cycles * sum(mat + 8.0 * n * (4.0 * (i + 1) + 5.0) for i in range(restart))
-    out["gmres_jacobi_restart30"] = {"iterations": it, "iterations_per_s": it / (ms / 1e3), "ms_per_iteration": ms / max(it, 1),
-                                     "relative_residual": res,
-                                     "survey_bytes_per_iteration": gm_bytes / its,
-                                     "survey_gbs": gm_bytes / (ms / 1e3) / 1e9, "survey_frac": gm_bytes / (ms / 1e3) / 1e9 / peak}
+        def run_gmres(k=its):
+            x.fill(0.0)
+            return A.gmres_dev(x, b, restart, k, 0.0, True)
+        run_gmres()                                     # warm-up: workspace allocation (100 basis vectors), first launches
+        capi.synchronize(); capi.timer_start()
+        conv, it, res = run_gmres()
+        ms = capi.timer_stop()
+        gm_bytes = cycles * sum(mat + 8.0 * n * passes(i) for i in range(restart - 1))
+        out[name] = {"iterations": it, "iterations_per_s": it / (ms / 1e3), "ms_per_iteration": ms / max(it, 1),
+                     "relative_residual": res, "survey_bytes_per_iteration": gm_bytes / max(it, 1),
+                     "survey_gbs": gm_bytes / (ms / 1e3) / 1e9, "survey_frac": gm_bytes / (ms / 1e3) / 1e9 / peak}
+    capi.set_option("gmres.ortho", 0)
     its_m = 100
 
     def run_minres():

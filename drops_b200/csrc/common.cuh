@@ -308,6 +308,7 @@ struct SellOp {
     int32_t* perm = nullptr;         // sorted position -> original row, -1 beyond rows
     int max_width = 0;
     bool full_rows = true;           // built over all rows of the CSR (false: a row subset, dist.cu)
+    bool general_released = false;   // col / val were freed after the packed stream was built ("sell.release_general")
     // Value dictionary ("sell.valdict"): constant-coefficient systems on uniform meshes hold a handful
     // of distinct fp64 values (15 on the P2 Kuhn brick).  When the matrix has at most 65535 distinct
     // bit patterns, `dict` lists them (sorted by bit pattern) and every stored entry becomes one

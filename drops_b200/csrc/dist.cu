@@ -182,6 +182,17 @@ __global__ void k_gather_flags(long long n, const int32_t* __restrict__ order, c
     if (i < n) { ao[i] = a[order[i]]; bo[i] = b[order[i]]; }
 }
 
+// Line segments (reorder.cu) stay whole: a segment with a boundary row goes to the boundary operator with all its 32
+// rows (an interior row there only reads owned columns), so the segments behind it keep their 32-row alignment in the
+// interior operator.  One warp per segment.
+__global__ void k_segment_flags(long long nseg, char* __restrict__ fi, char* __restrict__ fb)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nseg * 32) return;                     // nseg * 32 is a multiple of the warp size: whole warps leave
+    const bool any_bnd = __any_sync(0xffffffffu, fb[i] != 0);
+    if (any_bnd && fi[i] != 0) { fi[i] = 0; fb[i] = 1; }
+}
+
 // ---- peer-to-peer halo ------------------------------------------------------------------------
 // pack + push: entry i of my send list goes straight into the ghost buffer of the rank that needs it.
 // Every block fences its stores system-wide and takes a ticket; the block that draws the last ticket
@@ -496,13 +507,14 @@ static int dist_matrix_build_local(drops_b200_comm_s* comm, drops_b200_exchange_
     if (n > 0) {
         // rows in blocks of the partition's own graph (reorder.cu) when it is large enough to profit
         int32_t* order = nullptr;
+        size_t n_segments = 0;
         {
             CsrDev L;
             L.rows = n; L.cols = n + ng; L.nnz = nnz;
             L.rowptr = const_cast<int64_t*>(d_rowptr); L.col = col; L.val = const_cast<double*>(d_val);
             packs = false;               // graph blocks only pay together with the row-ordered twins
             DM_CHECK(will_pack_one_word(d_val, nnz, n + ng + 2 * 4096 + 64, &packs));
-            if (packs && opt("dist.reorder", 1.0) != 0.0) DM_CHECK(compute_block_order(L, &order));
+            if (packs && opt("dist.reorder", 1.0) != 0.0) DM_CHECK(compute_block_order(L, &order, &n_segments));
         }
         if (order) {
             char *fi = nullptr, *fb = nullptr;
@@ -511,6 +523,10 @@ static int dist_matrix_build_local(drops_b200_comm_s* comm, drops_b200_exchange_
             if (s2 == 0) {
                 k_gather_flags<<<blocks_for((long long)n, 256), 256, 0, st>>>((long long)n, order, f_int, f_bnd, fi, fb);
                 count_launch();
+                if (n_segments > 0) {
+                    k_segment_flags<<<blocks_for((long long)n_segments * 32, 256), 256, 0, st>>>((long long)n_segments, fi, fb);
+                    count_launch();
+                }
                 cudaError_t e2 = cudaMemcpyAsync(rows_all, order, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
                 if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(f_int, fi, n, cudaMemcpyDeviceToDevice, st);
                 if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(f_bnd, fb, n, cudaMemcpyDeviceToDevice, st);

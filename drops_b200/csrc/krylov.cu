@@ -60,6 +60,60 @@ static int fetch(const void* dsrc, void* hdst_pinned_or_not, size_t bytes)
 }
 
 // ------------------------------------------------------------------------------------------
+// Row-ordered solves ("pcg.reorder" for PCG, "krylov.reorder" for GMRES / MINRES; operators with a row-ordered
+// stream): the whole iteration runs on vectors renumbered by the operator's slice order -- x, b and the diagonal are
+// gathered once, x is scattered back at the end.  Every row sum keeps its bits (entry order is untouched); the
+// reductions visit the same products in another order, which the double-double accumulation absorbs.  Padding
+// positions hold 0 (diagonal 1) and stay 0: a padding row of the twin stream sums to 0.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct RoScope {
+    drops_b200_matrix_s* M = nullptr;
+    bool on = false;
+    size_t nv = 0;                 // length of the vectors the iteration works on
+    double* x = nullptr;           // where the iteration reads / writes the solution
+    const double* b = nullptr;
+    const double* diag = nullptr;
+    double* x_user = nullptr;
+};
+
+bool ro_available(const drops_b200_matrix_s* M)
+{
+    return opt("spmv.kernel", 0.0) == 0.0 &&
+           ((M->sell.pkp != nullptr && opt("spmv.pk", 1.0) != 0.0) || M->sell.colp != nullptr);
+}
+
+int ro_enter(drops_b200_matrix_s* M, bool want, double* x, const double* b, RoScope* R)
+{
+    R->M = M; R->on = want && ro_available(M);
+    R->nv = M->csr.rows; R->x = x; R->b = b; R->diag = M->diag; R->x_user = x;
+    if (!R->on) return 0;
+    const size_t npos = M->sell.npos;
+    // 0 diagonal, 1 x, 2 b (3 r, 4 p, 5 q of PCG)
+    if (M->ro_work.size() < 6) M->ro_work.resize(6, nullptr);
+    for (size_t k = 0; k < 3; ++k)
+        if (!M->ro_work[k]) DB_CHECK(dev_alloc(&M->ro_work[k], npos));
+    double* dp = M->ro_work[0]; double* xp = M->ro_work[1]; double* bp = M->ro_work[2];
+    if (M->ro_diag_epoch != M->values_epoch) {
+        DB_CHECK(vec_gather_perm(npos, M->sell.perm, M->diag, dp, 1.0));
+        dev_free(M->ro_diag_idx); M->ro_diag_idx = nullptr; M->ro_diag_count = 0;
+        M->ro_diag_idx_epoch = 0;
+        M->ro_diag_epoch = M->values_epoch;
+    }
+    DB_CHECK(vec_gather_perm(npos, M->sell.perm, x, xp, 0.0));
+    DB_CHECK(vec_gather_perm(npos, M->sell.perm, b, bp, 0.0));
+    R->nv = npos; R->x = xp; R->b = bp; R->diag = dp;
+    return 0;
+}
+
+int ro_leave(const RoScope& R)
+{
+    if (!R.on) return 0;
+    return vec_scatter_perm(R.M->sell.npos, R.M->sell.perm, R.x, R.x_user);
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
 // PCG -- num/krylovsolver.h:107-179
 // ------------------------------------------------------------------------------------------
 int pcg_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, double omega, int* max_iter,
@@ -73,28 +127,14 @@ int pcg_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, doubl
     const int want_hist = hist ? std::max(hist_cap, 0) : 0;
     DB_CHECK(ensure_scalars(M, std::max(want_hist, 1)));
     SolverScalars* S = (SolverScalars*)M->d_scalars;
-    // Row-ordered solve ("pcg.reorder", operators with a row-ordered packed stream): the whole
-    // iteration runs on vectors renumbered by the operator's slice order -- x, b and the diagonal are
-    // gathered once, x is scattered back at the end.  Every row sum keeps its bits (entry order is
-    // untouched); the reductions visit the same products in another order, which the double-double
-    // accumulation absorbs.  Padding positions hold 0 (diagonal 1) and stay 0.
-    const bool ro = !unpreconditioned_cg && opt("pcg.reorder", 1.0) != 0.0 && opt("spmv.kernel", 0.0) == 0.0 &&
-                    ((M->sell.pkp != nullptr && opt("spmv.pk", 1.0) != 0.0) || M->sell.colp != nullptr);
-    double* x_user = x;
-    const double* diag = M->diag;
+    RoScope R;
+    DB_CHECK(ro_enter(M, !unpreconditioned_cg && opt("pcg.reorder", 1.0) != 0.0, x, b, &R));
+    const bool ro = R.on;
     if (ro) {
         const size_t npos = M->sell.npos;
-        // 0 diagonal, 1 x, 2 b, 3 r, 4 p, 5 q
-        if (M->ro_work.size() < 6) M->ro_work.resize(6, nullptr);
-        for (size_t k = 0; k < M->ro_work.size(); ++k)
+        for (size_t k = 3; k < 6; ++k)
             if (!M->ro_work[k]) DB_CHECK(dev_alloc(&M->ro_work[k], npos));
-        double* dp = M->ro_work[0]; double* xp = M->ro_work[1]; double* bp = M->ro_work[2];
-        if (M->ro_diag_epoch != M->values_epoch) {
-            DB_CHECK(vec_gather_perm(npos, M->sell.perm, M->diag, dp, 1.0));
-            dev_free(M->ro_diag_idx); M->ro_diag_idx = nullptr; M->ro_diag_count = 0;
-            M->ro_diag_idx_epoch = 0;
-            M->ro_diag_epoch = M->values_epoch;
-        }
+        double* dp = M->ro_work[0];
         // constant-coefficient operators: a handful of distinct diagonal values -> one byte per position.  Built on the
         // first JACOBI solve on these values (a DummyPcCL solve before it must not mark the index as done).
         if (pc == DROPS_B200_PC_JACOBI && M->ro_diag_idx_epoch != M->values_epoch) {
@@ -102,11 +142,10 @@ int pcg_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, doubl
                 DB_CHECK(build_value_index8(dp, npos, kDiagDict, &M->ro_diag_idx, M->ro_diag_values, &M->ro_diag_count));
             M->ro_diag_idx_epoch = M->values_epoch;
         }
-        DB_CHECK(vec_gather_perm(npos, M->sell.perm, x, xp, 0.0));
-        DB_CHECK(vec_gather_perm(npos, M->sell.perm, b, bp, 0.0));
-        x = xp; b = bp; diag = dp;
     }
-    const size_t nv = ro ? M->sell.npos : n;      // length of the vectors the iteration works on
+    x = R.x; b = R.b;
+    const double* diag = R.diag;
+    const size_t nv = R.nv;                       // length of the vectors the iteration works on
     DiagIndex dix;
     const bool use_dix = ro && M->ro_diag_idx != nullptr && M->ro_diag_count > 0 && opt("pcg.diag_index", 1.0) != 0.0;
     if (use_dix) {
@@ -244,7 +283,7 @@ int pcg_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, doubl
     cudaEventDestroy(ev[1]);
     if (status != 0) { cudaStreamSynchronize(st); return status; }
 
-    if (ro) DB_CHECK(vec_scatter_perm(M->sell.npos, M->sell.perm, x, x_user));
+    DB_CHECK(ro_leave(R));
     DB_CHECK(fetch(S, &h, sizeof h));
     if (hist && want_hist > 0) {
         const int cnt = std::min(want_hist, h.iter + 1);
@@ -277,7 +316,13 @@ int gmres_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, dou
     DB_ARG(max_iter && tol, "null max_iter/tol");
     Ctx& c = ctx();
     cudaStream_t st = c.stream;
-    const size_t n = M->csr.rows;
+    // "krylov.reorder" (1): the iteration runs on row-ordered vectors (RoScope above)
+    RoScope R;
+    DB_CHECK(ro_enter(M, opt("krylov.reorder", 1.0) != 0.0, x, b, &R));
+    x = R.x; b = R.b;
+    const double* diag = R.diag;
+    const bool ro = R.on;
+    const size_t n = R.nv;
     int m = restart <= *max_iter ? restart : *max_iter;                 // :327
     DB_ARG(m >= 2, "GMRES needs restart >= 2 and max_iter >= 2");
     const bool jac = (pc == DROPS_B200_PC_JACOBI);
@@ -304,11 +349,11 @@ int gmres_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, dou
     auto Hat = [&](int i, int j) -> double& { return H[(size_t)j * m + i]; };
 
     auto apply_pc = [&](double* out, const double* in) -> int {         // M.Apply(A, out, in)
-        if (jac) return vec_jacobi(n, omega, M->diag, in, out);
+        if (jac) return vec_jacobi(n, omega, diag, in, out);
         return vec_copy(n, out, in);
     };
     auto residual = [&](double* out) -> int {                           // out = [M^-1](b - A x)
-        SpmvArgs a; a.x = x; a.epilogue = EPI_RESID; a.aux = b;
+        SpmvArgs a; a.x = x; a.epilogue = EPI_RESID; a.aux = b; a.row_ordered = ro;
         if (left && jac) { a.y = tmp; DB_CHECK(spmv_apply(M, false, a)); return apply_pc(out, tmp); }
         a.y = out;
         return spmv_apply(M, false, a);
@@ -347,7 +392,7 @@ int gmres_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, dou
     beta = c.h_scalars[0]; normb = c.h_scalars[1];
     if (normb == 0.0 || !relative) normb = 1.0;
     resid = beta / normb;
-    if (resid <= *tol) { *tol = resid; *max_iter = 0; return 1; }                   // :352-364
+    if (resid <= *tol) { *tol = resid; *max_iter = 0; return 1; }                   // :352-364 (x untouched)
 
     int j = 1;
     while (j <= *max_iter) {
@@ -357,9 +402,10 @@ int gmres_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, dou
         int i;
         for (i = 0; i < m - 1 && j <= *max_iter; ++i, ++j) {
             SpmvArgs a;
+            a.row_ordered = ro;
             if (left) {                                                             // w = M^-1 (A v[i])  :377
                 a.x = v[i]; a.y = w;
-                if (jac) { a.epilogue = EPI_JACOBI; a.aux = M->diag; a.omega = omega; }
+                if (jac) { a.epilogue = EPI_JACOBI; a.aux = diag; a.omega = omega; }
                 DB_CHECK(spmv_apply(M, false, a));
             } else {                                                                // w = A (M^-1 v[i])  :372-376
                 DB_CHECK(apply_pc(tmp, v[i]));
@@ -386,6 +432,7 @@ int gmres_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, dou
             resid = std::abs(s[i + 1]) / normb;                                     // :393
             if (resid <= *tol) {                                                    // :413-429
                 DB_CHECK(update_x(i));
+                DB_CHECK(ro_leave(R));
                 *tol = resid; *max_iter = j;
                 return 1;
             }
@@ -396,8 +443,9 @@ int gmres_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, dou
         DB_CHECK(fetch(d_scal, c.h_scalars, sizeof(double)));
         beta = c.h_scalars[0];
         resid = beta / normb;
-        if (resid <= *tol) { *tol = resid; *max_iter = j; return 1; }               // :449-456
+        if (resid <= *tol) { DB_CHECK(ro_leave(R)); *tol = resid; *max_iter = j; return 1; }   // :449-456
     }
+    DB_CHECK(ro_leave(R));
     *tol = resid;
     return 0;
 }
@@ -422,6 +470,7 @@ struct LanczosDev {
     drops_b200_matrix_s* M;
     size_t n;
     bool precond; int pc; double omega;
+    bool ro = false; const double* diag = nullptr;   // row-ordered solve (RoScope): every product on the twin stream, its diagonal
     double* qv[3]; Ring3 q3; Ring2 q2r;      // q ring: 3 slots (plain) / 2 slots (preconditioned)
     double* tv[3]; Ring3 t3;
     double bb[2]; Ring2 br;
@@ -438,6 +487,7 @@ struct LanczosDev {
         Ctx& c = ctx();
         if (!precond) {                                                     // LanczosStep :926-943
             SpmvArgs a;
+            a.row_ordered = ro;
             a.x = Q(0); a.y = Q(1); a.epilogue = EPI_AXMBY; a.aux = Q(-1); a.beta_val = B(-1);
             a.dotv = Q(0); a.dot_out = d_scal + 0;                          // q2 = A q1 - b0 q0; a1 = q2.q1
             DB_CHECK(spmv_apply(M, false, a));
@@ -450,10 +500,11 @@ struct LanczosDev {
             DB_CHECK(vec_div_scalar(n, Q(1), Q(1), b1, 0));                 // q2 /= b1
         } else {                                                            // PLanczosStep :989-1008
             SpmvArgs a;
+            a.row_ordered = ro;
             a.x = Q(0); a.y = T(1); a.epilogue = EPI_AXMBY; a.aux = T(-1); a.beta_val = B(-1);
             a.dotv = Q(0); a.dot_out = d_scal + 0;                          // t2 = A q1 - b0 t0; a1 = t2.q1
             DB_CHECK(spmv_apply(M, false, a));
-            DB_CHECK(planczos_orth(n, T(1), T(0), d_scal + 0, Q(1), pc, omega, M->diag, d_scal + 1));
+            DB_CHECK(planczos_orth(n, T(1), T(0), d_scal + 0, Q(1), pc, omega, diag, d_scal + 1));
             DB_CHECK(fetch(d_scal, c.h_scalars, 2 * sizeof(double)));
             a0 = c.h_scalars[0];
             const double b1 = std::sqrt(c.h_scalars[1]);
@@ -479,7 +530,7 @@ struct LanczosDev {
             DB_CHECK(vec_fill(n, Q(1), 0.0));
         } else {                                                            // :1030-1040
             DB_CHECK(vec_fill(n, T(-1), 0.0));
-            if (pc == DROPS_B200_PC_JACOBI) DB_CHECK(vec_jacobi(n, omega, M->diag, r0, Q(-1)));
+            if (pc == DROPS_B200_PC_JACOBI) DB_CHECK(vec_jacobi(n, omega, diag, r0, Q(-1)));
             else DB_CHECK(vec_copy(n, Q(-1), r0));
             DB_CHECK(vec_dot(n, Q(-1), r0, d_scal + 0));
             DB_CHECK(fetch(d_scal, c.h_scalars, sizeof(double)));
@@ -508,11 +559,14 @@ int minres_device(drops_b200_matrix_s* M, double* x, const double* b, int precon
     DB_CHECK(check_system(M, precond ? pc : DROPS_B200_PC_DUMMY));
     DB_ARG(max_iter && tol, "null max_iter/tol");
     Ctx& c = ctx();
-    const size_t n = M->csr.rows;
+    RoScope R;                                                              // "krylov.reorder"
+    DB_CHECK(ro_enter(M, opt("krylov.reorder", 1.0) != 0.0, x, b, &R));
+    x = R.x; b = R.b;
+    const size_t n = R.nv;
     // work: 0 tmp/r0, 1-3 q, 4-6 t, 7-9 p
     double* tmp = work_vec(M, 0);
     LanczosDev L;
-    L.M = M; L.n = n; L.precond = precond != 0; L.pc = pc; L.omega = omega;
+    L.M = M; L.n = n; L.precond = precond != 0; L.pc = pc; L.omega = omega; L.ro = R.on; L.diag = R.diag;
     for (int i = 0; i < 3; ++i) {
         L.qv[i] = work_vec(M, 1 + i);
         L.tv[i] = work_vec(M, 4 + i);
@@ -525,7 +579,7 @@ int minres_device(drops_b200_matrix_s* M, double* x, const double* b, int precon
     L.d_scal = M->d_small;
 
     {   // r0 = b - A x                                                     :1158
-        SpmvArgs a; a.x = x; a.y = tmp; a.epilogue = EPI_RESID; a.aux = b;
+        SpmvArgs a; a.x = x; a.y = tmp; a.epilogue = EPI_RESID; a.aux = b; a.row_ordered = R.on;
         DB_CHECK(spmv_apply(M, false, a));
     }
     DB_CHECK(L.new_basis(tmp));
@@ -576,17 +630,18 @@ int minres_device(drops_b200_matrix_s* M, double* x, const double* b, int precon
                                R0[0], R0[1], R0[2], norm_r0 * B0[0]));
         res = std::fabs(norm_r0 * B0[1]) / normb;
         if (res <= *tol || lucky) {                                         // :1132-1141
-            SpmvArgs a; a.x = x; a.y = tmp; a.epilogue = EPI_RESID; a.aux = b;
+            SpmvArgs a; a.x = x; a.y = tmp; a.epilogue = EPI_RESID; a.aux = b; a.row_ordered = R.on;
             DB_CHECK(spmv_apply(M, false, a));
             DB_CHECK(vec_dot(n, tmp, tmp, L.d_scal + 2));
             DB_CHECK(fetch(L.d_scal + 2, c.h_scalars, sizeof(double)));
             const double realRes = std::sqrt(c.h_scalars[0]);
-            if (!(realRes > *tol)) { *tol = res; *max_iter = k; return 1; }
+            if (!(realRes > *tol)) { DB_CHECK(ro_leave(R)); *tol = res; *max_iter = k; return 1; }
         }
         DB_CHECK(L.next());
         if (!L.nobreakdown) lucky = true;
         cr.rotate(); sr.rotate(); rrg.rotate(); pr.rotate(); bqr.rotate();
     }
+    DB_CHECK(ro_leave(R));
     *tol = res;
     return 0;
 }

@@ -332,7 +332,7 @@ double* work_vec(drops_b200_matrix_s* M, int i)
 {
     if ((int)M->work.size() <= i) M->work.resize(i + 1, nullptr);
     if (!M->work[i]) {
-        const size_t n = std::max(M->csr.rows, M->csr.cols);
+        const size_t n = std::max(std::max(M->csr.rows, M->csr.cols), M->sell.npos);   // row-ordered solves: 32 * nslices positions
         if (dev_alloc(&M->work[i], n) < 0) return nullptr;
     }
     return M->work[i];
@@ -750,16 +750,46 @@ int build_row_ordered_columns(SellOp& S, size_t* bytes)
     return 0;
 }
 
+// Footprint ("sell.release_general", operators of at least "sell.release_min_rows" rows): once the one-word packed
+// stream exists, nothing on the solver path reads the int32 column + fp64 value arrays of the sliced-ELL operator any
+// more (products, solvers and the transposed product all run on pk / pkp); they are 12 of the 16-20 bytes per stored
+// entry the operator holds.  A value update rebuilds them from the CSR copy for the time of the rebuild.
+static void release_general(SellOp& S, size_t* bytes)
+{
+    if (S.pk == nullptr || S.val == nullptr || opt("sell.release_general", 1.0) == 0.0) return;
+    if ((double)S.rows < opt("sell.release_min_rows", 2.0e6)) return;
+    dev_free(S.col); S.col = nullptr;
+    dev_free(S.val); S.val = nullptr;
+    S.general_released = true;
+    if (bytes && *bytes >= S.padded * 12) *bytes -= S.padded * 12;
+}
+
+static int restore_general(const CsrDev& A, SellOp& S)
+{
+    if (!S.general_released || S.val != nullptr) return 0;
+    DB_CHECK(dev_alloc(&S.col, S.padded));
+    DB_CHECK(dev_alloc(&S.val, S.padded));
+    k_sell_fill<<<blocks_for((long long)S.nslices * 32, 256), 256, 0, ctx().stream>>>(
+        (long long)S.nslices, S.slice_ptr, S.perm, A.rowptr, A.col, A.val, S.col, S.val);
+    count_launch();
+    DB_CUDA(cudaGetLastError());
+    S.general_released = false;
+    return 0;
+}
+
 int refill_sell_values(const CsrDev& A, SellOp& S)
 {
     if (S.padded == 0) return 0;
     cudaStream_t st = ctx().stream;
+    DB_CHECK(restore_general(A, S));
     k_sell_refill_values<<<blocks_for((long long)S.nslices * 32, 256), 256, 0, st>>>(
         (long long)S.nslices, S.slice_ptr, S.perm, A.rowptr, A.val, S.val);
     count_launch();
     DB_CUDA(cudaGetLastError());
     DB_CHECK(build_value_dictionary(S, nullptr));      // new values, new dictionary
-    return build_row_ordered_columns(S, nullptr);       // (the packed twin may have come or gone with them)
+    DB_CHECK(build_row_ordered_columns(S, nullptr));    // (the packed twin may have come or gone with them)
+    release_general(S, nullptr);
+    return 0;
 }
 
 int extract_diag(drops_b200_matrix_s* M)
@@ -817,6 +847,13 @@ int build_transpose(drops_b200_matrix_s* M)
     dev_free(cursor);
     size_t bytes = T.nnz * 12 + (T.rows + 1) * 8;
     DB_CHECK(build_sell(T, M->sell_t, &bytes, nullptr, 0));
+    release_general(M->sell_t, &bytes);
+    if (M->sell_t.general_released) {                  // the CSR form of A^T only existed to build the operator
+        bytes -= std::min(bytes, T.nnz * 12 + (T.rows + 1) * 8);
+        const size_t r = T.rows, cc = T.cols, z = T.nnz;
+        free_csr(T);
+        T.rows = r; T.cols = cc; T.nnz = z;
+    }
     M->device_bytes += bytes;
     M->has_t = true;
     return 0;
@@ -847,6 +884,7 @@ int finalize_matrix(drops_b200_matrix_s* M)
     const int s = build_sell(M->csr, M->sell, &M->device_bytes, order, order ? M->csr.rows : 0, order != nullptr, packs);
     dev_free(order);
     M->block_ordered = s == 0 && order != nullptr;
+    if (s == 0) release_general(M->sell, &M->device_bytes);
     return s;
 }
 

@@ -252,6 +252,8 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a)
         return spmv_sell_pk(A, a);
     }
     DB_ARG(!a.row_ordered || A.colp != nullptr, "row-ordered vectors need the operator's row-ordered stream");
+    DB_ARG(A.val != nullptr, "the 12-byte stream of this operator was released once its packed stream existed "
+                             "(\"sell.release_general\" = 0 keeps it)");
     int threads = (int)opt("spmv.threads", 128);
     if (threads < 32) threads = 32;
     if (threads > 512) threads = 512;
@@ -338,6 +340,8 @@ int spmv_apply(const drops_b200_matrix_s* M, bool transposed, const SpmvArgs& a)
     const int kind = a.row_ordered ? 0 : (int)opt("spmv.kernel", 0.0);
     if (kind == 1) {
         const int lanes = (int)opt("spmv.lanes", 8.0);
+        DB_ARG(!transposed || M->csr_t.rowptr != nullptr || M->csr_t.nnz == 0,
+               "the CSR form of A^T was released with its 12-byte stream (\"sell.release_general\" = 0 keeps it)");
         return spmv_csr_vector(transposed ? M->csr_t : M->csr, a, lanes);
     }
     return spmv_sell(transposed ? M->sell_t : M->sell, a);

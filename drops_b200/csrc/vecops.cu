@@ -949,8 +949,16 @@ k_cgs_dots(size_t n, const double* __restrict__ w, const double* const* __restri
         const int len = (int)(n - r0 < (size_t)kCgsTile ? n - r0 : (size_t)kCgsTile);
         for (int k = warp; k < nv; k += nwarp) {
             const double* __restrict__ vk = v[k] + r0;
-            dd a = dd_zero();
-            for (int j = lane; j < len; j += 32) a = dd_add_prod(a, wt[j], __ldcs(vk + j));
+            // four independent accumulators per lane: the double-double update is a long dependent chain
+            dd a = dd_zero(), a1 = dd_zero(), a2 = dd_zero(), a3 = dd_zero();
+            int j = lane;
+            for (; j + 96 < len; j += 128) {
+                const double v0 = __ldcs(vk + j), v1 = __ldcs(vk + j + 32), v2 = __ldcs(vk + j + 64), v3 = __ldcs(vk + j + 96);
+                a = dd_add_prod(a, wt[j], v0); a1 = dd_add_prod(a1, wt[j + 32], v1);
+                a2 = dd_add_prod(a2, wt[j + 64], v2); a3 = dd_add_prod(a3, wt[j + 96], v3);
+            }
+            for (; j < len; j += 32) a = dd_add_prod(a, wt[j], __ldcs(vk + j));
+            a = dd_add(dd_add(a, a1), dd_add(a2, a3));
             a = warp_reduce_dd(a);
             if (lane == 0) acc[k] = dd_add(acc[k], a);
         }
@@ -985,7 +993,9 @@ int cgs_dots(size_t n, const double* w, const double* const* d_vptrs, int nv, do
     Ctx& c = ctx();
     ScopedTiming t("gmres.cgs");
     const size_t ntiles = (n + kCgsTile - 1) / kCgsTile;
-    long long grid = std::min<long long>((long long)std::max<size_t>(ntiles, 1), 2LL * c.sm_count);
+    // small systems (level-set, 10^5 rows): 2 CTAs per SM keep the finishing pass short; large ones need the whole
+    // machine in flight (8 CTAs of 256 threads per SM)
+    long long grid = std::min<long long>((long long)std::max<size_t>(ntiles, 1), (n >= ((size_t)1 << 22) ? 8LL : 2LL) * c.sm_count);
     grid = std::min<long long>(grid, kPartialStride / nv);
     k_cgs_dots<<<(int)grid, 256, 0, c.stream>>>(n, w, d_vptrs, nv, c.partials + (size_t)1 * kPartialStride,
                                                 c.tickets + (size_t)1 * kTicketStride, d_h, part_out);
@@ -1001,7 +1011,13 @@ struct OpCgsUpdate {
     __device__ void elem(size_t i, dd* acc)
     {
         double wi = w[i];
-        for (int k = 0; k < nv; ++k) wi = sub(wi, mul(__ldg(h + k), __ldcs(v[k] + i)));
+        int k = 0;
+        for (; k + 4 <= nv; k += 4) {                  // four loads in flight; the subtractions stay in order
+            const double v0 = __ldcs(v[k] + i), v1 = __ldcs(v[k + 1] + i), v2 = __ldcs(v[k + 2] + i), v3 = __ldcs(v[k + 3] + i);
+            wi = sub(wi, mul(__ldg(h + k), v0)); wi = sub(wi, mul(__ldg(h + k + 1), v1));
+            wi = sub(wi, mul(__ldg(h + k + 2), v2)); wi = sub(wi, mul(__ldg(h + k + 3), v3));
+        }
+        for (; k < nv; ++k) wi = sub(wi, mul(__ldg(h + k), __ldcs(v[k] + i)));
         w[i] = wi;
         acc[0] = dd_add_prod(acc[0], wi, wi);
     }

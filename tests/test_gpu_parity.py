@@ -91,7 +91,7 @@ CDICT_DOT_DEFAULT = 1  # library default of "spmv.pk_cdict_dot"
 CDICT_DEFAULT = 1     # library default of "spmv.pk_cdict"
 
 
-PK_DEFAULTS = {"spmv.pk": 1, "pcg.reorder": 1, "pcg.defer_x": 1, "pcg.fused_dot": 1, "pcg.fuse_x": 0, "spmv.pk_threads": 512,
+PK_DEFAULTS = {"spmv.pk": 1, "pcg.reorder": 1, "pcg.defer_x": 1, "pcg.fused_dot": 1, "krylov.reorder": 1, "spmv.pk_threads": 512,
                "spmv.pk_slices_per_cta": 128, "spmv.pkdict": 0, "spmv.dotmode": 0, "sell.sigma": 4096,
                "sell.valdict": 1, "spmv.exact": 1,
                "spmv.pk_cdict": CDICT_DEFAULT, "spmv.pk_cdict_dot": CDICT_DOT_DEFAULT,
@@ -181,9 +181,9 @@ def test_value_dictionary_stream_is_bit_identical(gpu, variant, threads, spc, di
         _restore_pk(gpu)
 
 
-@pytest.mark.parametrize("reorder,defer_x,fused_dot,graph,fuse_x",
-                         [(1, 1, 1, 1, 1), (1, 1, 1, 0, 1), (1, 1, 1, 1, 0), (1, 0, 0, 0, 0), (0, 1, 0, 1, 1), (0, 0, 1, 0, 0), (1, 1, 0, 0, 1)])
-def test_pcg_forms_agree_with_reference(gpu, reorder, defer_x, fused_dot, graph, fuse_x):
+@pytest.mark.parametrize("reorder,defer_x,fused_dot,graph,lean",
+                         [(1, 1, 1, 1, 2), (1, 1, 1, 0, 1), (1, 1, 1, 1, 0), (1, 0, 0, 0, 2), (0, 1, 0, 1, 2), (0, 0, 1, 0, 1), (1, 1, 0, 0, 0)])
+def test_pcg_forms_agree_with_reference(gpu, reorder, defer_x, fused_dot, graph, lean):
     """Row-ordered solve, deferred x update, separate dot kernel, graph replay: every combination gives
     the reference's iteration count and solution, also when the solve stops inside a chunk, at
     max_iter, or before the first iteration."""
@@ -194,7 +194,7 @@ def test_pcg_forms_agree_with_reference(gpu, reorder, defer_x, fused_dot, graph,
         gpu.set_option("pcg.defer_x", defer_x)
         gpu.set_option("pcg.fused_dot", fused_dot)
         gpu.set_option("pcg.graph", graph)
-        gpu.set_option("pcg.fuse_x", fuse_x)
+        gpu.set_option("spmv.pk_lean", lean)
         A = gmat(gpu, g)
         out = A.pcg_jacobi(np.zeros(A.rows), g["b"], 400, 1e-10, True)
         assert out[0] and out[1] == int(g["sym_pcgjac"][1]) and rel(out[3], g["sym_pcgjac_x"]) <= 1e-12
@@ -203,26 +203,26 @@ def test_pcg_forms_agree_with_reference(gpu, reorder, defer_x, fused_dot, graph,
         out = A.pcg_jacobi(g["sym_pcgjac_x"].copy(), g["b"], 50, 1e-6, True)  # converged at iteration 0 or 1
         assert out[0] and out[1] <= 1
         for maxit in (1, 2, 5, 16, 17, 33):                                    # x = the reference's iterate after maxit steps
-            gpu.set_option("pcg.reorder", reorder); gpu.set_option("pcg.defer_x", defer_x); gpu.set_option("pcg.fuse_x", fuse_x)
+            gpu.set_option("pcg.reorder", reorder); gpu.set_option("pcg.defer_x", defer_x)
             out = A.pcg_jacobi(np.zeros(A.rows), g["b"], maxit, 1e-30, True)
-            gpu.set_option("pcg.reorder", 0); gpu.set_option("pcg.defer_x", 0); gpu.set_option("pcg.fuse_x", 0)
+            gpu.set_option("pcg.reorder", 0); gpu.set_option("pcg.defer_x", 0)
             ref = A.pcg_jacobi(np.zeros(A.rows), g["b"], maxit, 1e-30, True)
             assert not out[0] and out[1] == ref[1] and rel(out[3], ref[3]) <= 1e-12 and abs(out[2] - ref[2]) <= 1e-9 * ref[2]
-        gpu.set_option("pcg.reorder", reorder); gpu.set_option("pcg.defer_x", defer_x); gpu.set_option("pcg.fuse_x", fuse_x)
+        gpu.set_option("pcg.reorder", reorder); gpu.set_option("pcg.defer_x", defer_x)
         for check_every in (1, 2, 3, 16):
             gpu.set_option("pcg.check_every", check_every)
             B = gpu.Matrix(n, n, rb, ci, va)
             xs = gpu.brick_solution_host(2, 10, 1)
             b = B.spmv(xs)
             out = B.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True)
-            gpu.set_option("pcg.reorder", 0); gpu.set_option("pcg.defer_x", 0); gpu.set_option("pcg.fused_dot", 1); gpu.set_option("pcg.fuse_x", 0)
+            gpu.set_option("pcg.reorder", 0); gpu.set_option("pcg.defer_x", 0); gpu.set_option("pcg.fused_dot", 1)
             ref = B.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True)
             gpu.set_option("pcg.reorder", reorder); gpu.set_option("pcg.defer_x", defer_x); gpu.set_option("pcg.fused_dot", fused_dot)
-            gpu.set_option("pcg.fuse_x", fuse_x)
             assert out[0] and out[1] == ref[1] and rel(out[3], ref[3]) <= 1e-12 and rel(out[3], xs) <= 1e-8
     finally:
         gpu.set_option("pcg.check_every", 16)
         gpu.set_option("pcg.graph", 1)
+        gpu.set_option("spmv.pk_lean", 2)
         _restore_pk(gpu)
 
 
@@ -518,7 +518,12 @@ def test_line_segments_in_graph_blocks_are_transparent(gpu, cells, lines, tiles,
         assert s1[0] and s1[1] == s0[1] and rel(s1[3], s0[3]) <= 1e-12
         gm0 = B0.gmres_jacobi(np.zeros(n), b, 20, 60, 1e-10, True, 1.0, True)
         gm1 = B.gmres_jacobi(np.zeros(n), b, 20, 60, 1e-10, True, 1.0, True)
-        assert gm1[1] == gm0[1] and np.array_equal(gm1[3], gm0[3])      # caller's order: same bits
+        assert gm1[1] == gm0[1] and rel(gm1[3], gm0[3]) <= 1e-12        # row-ordered in two different orders
+        gpu.set_option("krylov.reorder", 0)
+        gm2 = B.gmres_jacobi(np.zeros(n), b, 20, 60, 1e-10, True, 1.0, True)
+        gm3 = B0.gmres_jacobi(np.zeros(n), b, 20, 60, 1e-10, True, 1.0, True)
+        gpu.set_option("krylov.reorder", 1)
+        assert gm2[1] == gm3[1] and np.array_equal(gm2[3], gm3[3])      # caller's order: same bits
     finally:
         gpu.set_option("sell.block_min_rows", 2.0e6)
         gpu.set_option("sell.line_order", 1)
@@ -1140,3 +1145,26 @@ def test_production_defaults_parity_p2_n64(gpu, port):
     assert D.layout()["block_ordered"]
     out2 = D.pcg_jacobi(np.zeros(n), b, 5000, 1e-10, True)
     assert out2[1] == out[1] and np.array_equal(out2[3], out[3])
+    # line segments are the unit of the blocks at this size: 8 DOF classes x ~63^2 lines x 1 complete segment each
+    assert lay["line_segments"] >= 6 * 61 ** 2, lay
+    # footprint ("sell.release_general"): the 12-byte stream of an operator this large is gone once the packed stream
+    # exists -- A: 12 (csr) + 2 x 4 (pk, pkp) bytes per entry, A^T (built by the transp_mul above): 2 x 4, instead of 32 + 32
+    nnz = len(va)
+    assert G.info()["device_bytes"] < 30 * nnz, (G.info()["device_bytes"], nnz)
+    try:
+        gpu.set_option("spmv.pk", 0)
+        with pytest.raises(gpu.DropsB200Error):
+            G.spmv(xin)                            # asked for the released stream: fails loudly
+    finally:
+        gpu.set_option("spmv.pk", 1)
+    # a value update rebuilds the streams from the CSR copy (and releases the general one again)
+    G.update_values(va * 2.0, 2)
+    assert np.array_equal(G.spmv(xin), 2.0 * R.spmv(xin)) and np.array_equal(G.spmv_transpose(xin), 2.0 * R.spmv_transpose(xin))
+    # GMRES and MINRES iterate on the same row-ordered vectors ("krylov.reorder"): iteration counts of the reference
+    G.update_values(va, 3)
+    og = G.gmres_jacobi(np.zeros(n), b, 30, 70, 1e-30, True, 1.0, True)
+    orf = R.gmres_jacobi(np.zeros(n), b, 30, 70, 1e-30, True, 1.0, True)
+    assert og[1] == orf[1] and rel(og[3], orf[3]) <= 1e-9, (og[1], orf[1], rel(og[3], orf[3]))
+    og = G.minres(np.zeros(n), b, 60, 1e-30, True)
+    orf = R.minres(np.zeros(n), b, 60, 1e-30, True)
+    assert og[1] == orf[1] and rel(og[3], orf[3]) <= 1e-9, (og[1], orf[1], rel(og[3], orf[3]))
