@@ -143,6 +143,7 @@ SIGNATURES = {
     "drops_b200_dist_dot": (_i, [_i, _vpp, _vpp, _vpp, _dpp]),
     "drops_b200_dist_pcg_dev": (_i, [_i, _vpp, _vpp, _vpp, _i, _d, _ip, _dpp, _i, _vp, _i]),
     "drops_b200_dist_gmres_dev": (_i, [_i, _vpp, _vpp, _vpp, _i, _d, _i, _ip, _dpp, _i, _i]),
+    "drops_b200_dist_minres_dev": (_i, [_i, _vpp, _vpp, _vpp, _i, _i, _d, _ip, _dpp, _i]),
     "drops_b200_brick_slab_generate": (_i, [_i, _i, _i, _d, _i, _i, _vpp]),
     "drops_b200_brick_slab_destroy": (_i, [_vp]),
     "drops_b200_brick_slab_info": (_i, [_vp, _szpp, _szpp, _szpp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
@@ -902,6 +903,14 @@ def dist_gmres(parts, xs, bs, restart, max_iter, tol, relative=True, pc=PC_JACOB
     it, res = C.c_int(int(max_iter)), C.c_double(float(tol))
     conv = check(lib().drops_b200_dist_gmres_dev(len(parts), _harr(parts), _harr(xs), _harr(bs), int(pc), float(omega),
                                                  int(restart), C.byref(it), C.byref(res), int(relative), int(left)))
+    return bool(conv), it.value, res.value
+
+
+def dist_minres(parts, xs, bs, max_iter, tol, relative=False, precond=0, pc=PC_DUMMY, omega=1.0):
+    """MINRES (precond = 0) / PMINRES on the partitioned system; (converged, iterations, residual)."""
+    it, res = C.c_int(int(max_iter)), C.c_double(float(tol))
+    conv = check(lib().drops_b200_dist_minres_dev(len(parts), _harr(parts), _harr(xs), _harr(bs), int(precond), int(pc),
+                                                  float(omega), C.byref(it), C.byref(res), int(relative)))
     return bool(conv), it.value, res.value
 
 

@@ -257,6 +257,7 @@ int timing_flush();
 inline void count_launch(int n = 1) { ctx().launches += n; }
 
 constexpr int kMaxQ = 4;            // quantities per fused reduction
+constexpr int kWideQ = 512;         // quantities of a wide reduction (classical Gram-Schmidt column of the partitioned GMRES)
 constexpr int kPartialStride = 1 << 20;   // dd entries of reduction workspace per slot (>= NQ * grid)
 constexpr int kPartialSlots = 4;          // kernels that may overlap use different slots
 constexpr int kTicketStride = 8192;       // counters per slot: 1 + groups of the two-level grid reduction

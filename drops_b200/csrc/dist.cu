@@ -686,6 +686,7 @@ int dist_matrix_build(drops_b200_comm_s* comm, drops_b200_exchange_s* E, size_t 
 struct PartArgs {
     const double* x = nullptr; double* y = nullptr;
     int epilogue = EPI_NONE; const double* aux = nullptr; double omega = 1.0;
+    double beta_val = 0.0;              // EPI_AXMBY: y = A x - beta_val * aux
     const double* dotv = nullptr;       // fused dot partner (local partial -> gathered slot)
     const int* done = nullptr;
     bool ro = false;                    // x, y, aux, dotv are in the partition's row-ordered numbering (npos entries)
@@ -733,6 +734,32 @@ static int allgather_partials(drops_b200_comm_s* comm, int nq, const int* const*
                                  (ncclComm_t)comm->nccl, ctx().stream));
     }
     return 0;
+}
+
+// Wide reduction: nq <= kWideQ double-double partials per rank (the i+1 products of a classical Gram-Schmidt column,
+// krylovsolver.h:465-494) -> every rank holds all of them (ONE all-gather per column; in-process transport: the
+// partitions wrote into the shared buffer themselves) -> k_wide_sum adds them in rank order, so all ranks round the
+// same sums.
+static inline dd* wide_slot(drops_b200_dist_matrix_s* M, int nq) { return M->comm->wide + (size_t)M->rank * nq; }
+
+static int wide_allgather(drops_b200_comm_s* comm, int nq)
+{
+    DB_ARG(nq >= 1 && nq <= kWideQ, "wide reduction: too many quantities");
+    if (comm->kind == COMM_NCCL && comm->world > 1) {
+        ScopedTiming t("allgather");
+        DB_NCCL(nccl().AllGather(comm->wide + (size_t)comm->rank * nq, comm->wide, (size_t)nq * 2, ncclDouble,
+                                 (ncclComm_t)comm->nccl, ctx().stream));
+    }
+    return 0;
+}
+
+__global__ void k_wide_sum(const dd* __restrict__ wide, int world, int nq, double* __restrict__ out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nq) return;
+    dd a = wide[k];
+    for (int r = 1; r < world; ++r) a = dd_add(a, wide[(size_t)r * nq + k]);
+    out[k] = dd_round(a);
 }
 
 // Peer mappings of one partition.  NCCL transport: IPC handles of every rank's ghost buffer and flag
@@ -936,6 +963,7 @@ static int dist_spmv_run(int np, drops_b200_dist_matrix_s* const* P, const PartA
         ScopedTiming t("spmv");
         SpmvArgs s;
         s.x = a[p].x; s.y = a[p].y; s.epilogue = a[p].epilogue; s.aux = a[p].aux; s.omega = a[p].omega; s.done = a[p].done;
+        s.beta_val = a[p].beta_val;
         if (a[p].dotv) { s.dotv = a[p].dotv; s.dd_out = M->n_bnd ? (dd*)M->d_scalars + 32 : gather_slot(M, 1); }
         s.row_ordered = a[p].ro;
         DB_CHECK(spmv_sell(M->sell_int, s));
@@ -958,6 +986,7 @@ static int dist_spmv_run(int np, drops_b200_dist_matrix_s* const* P, const PartA
         ScopedTiming t("spmv.bnd");
         SpmvArgs s;
         s.x = a[p].x; s.y = a[p].y; s.epilogue = a[p].epilogue; s.aux = a[p].aux; s.omega = a[p].omega; s.done = a[p].done;
+        s.beta_val = a[p].beta_val;
         s.xghost = M->ghost; s.n_owned = a[p].ro ? (long long)M->npos : (long long)M->n_owned;
         if (a[p].dotv) { s.dotv = a[p].dotv; s.dd_in = M->n_int ? (dd*)M->d_scalars + 32 : nullptr; s.dd_out = gather_slot(M, 1); }
         DB_CHECK(spmv_sell(a[p].ro ? M->sell_bnd_ro : M->sell_bnd, s));
@@ -1214,6 +1243,7 @@ int dist_gmres(int np, drops_b200_dist_matrix_s* const* P, double* const* x, con
     const int m = restart <= *max_iter ? restart : *max_iter;                  // :327
     DB_ARG(m >= 2, "GMRES needs restart >= 2 and max_iter >= 2");
     const bool jac = pc == DROPS_B200_PC_JACOBI;
+    const bool cgs = opt("gmres.ortho", 0.0) == 1.0 && m <= kWideQ;          // "gmres.ortho" as in the single-GPU driver
     {
         double flag = 0.0;
         for (int p = 0; p < np; ++p) if (jac && !P[p]->diag_ok) flag = 1.0;
@@ -1333,17 +1363,33 @@ int dist_gmres(int np, drops_b200_dist_matrix_s* const* P, double* const* x, con
                 }
             }
             DB_CHECK(dist_spmv_run(np, P, a.data()));
-            for (int k = 0; k <= i; ++k) {                                    // modified Gram-Schmidt  :378-381
+            if (cgs) {
+                // classical Gram-Schmidt, the default of the reference's distributed ModGMRES (:465-494, :862-866): all
+                // i+1 products against the unmodified w in ONE pass and ONE reduction over the ranks, then one update
                 for (int p = 0; p < np; ++p) {
                     Part& w = W[(size_t)p];
-                    DB_CHECK(mgs_step(w.n, w.w, k > 0 ? w.v[(size_t)k - 1] : nullptr, w.d_h + (k - 1), w.v[(size_t)k], nullptr, false,
-                                      gather_slot(P[p], 1)));
+                    DB_CHECK(cgs_dots(w.n, w.w, w.d_vptrs, i + 1, nullptr, wide_slot(P[p], i + 1)));
                 }
-                DB_CHECK(reduce_to(PH_DOT, h_slot, k));
-            }
-            for (int p = 0; p < np; ++p) {
-                Part& w = W[(size_t)p];
-                DB_CHECK(mgs_step(w.n, w.w, w.v[(size_t)i], w.d_h + i, nullptr, nullptr, true, gather_slot(P[p], 1)));   // H(i+1,i) = |w|  :383
+                DB_CHECK(wide_allgather(comm, i + 1));
+                for (int p = 0; p < np; ++p) {
+                    Part& w = W[(size_t)p];
+                    k_wide_sum<<<(i + 1 + 127) / 128, 128, 0, st>>>(comm->wide, comm->world, i + 1, w.d_h);
+                    count_launch();
+                    DB_CHECK(cgs_update(w.n, w.w, w.d_vptrs, w.d_h, i + 1, nullptr, gather_slot(P[p], 1)));              // + partial of |w|^2
+                }
+            } else {
+                for (int k = 0; k <= i; ++k) {                                // modified Gram-Schmidt  :378-381
+                    for (int p = 0; p < np; ++p) {
+                        Part& w = W[(size_t)p];
+                        DB_CHECK(mgs_step(w.n, w.w, k > 0 ? w.v[(size_t)k - 1] : nullptr, w.d_h + (k - 1), w.v[(size_t)k], nullptr, false,
+                                          gather_slot(P[p], 1)));
+                    }
+                    DB_CHECK(reduce_to(PH_DOT, h_slot, k));
+                }
+                for (int p = 0; p < np; ++p) {
+                    Part& w = W[(size_t)p];
+                    DB_CHECK(mgs_step(w.n, w.w, w.v[(size_t)i], w.d_h + i, nullptr, nullptr, true, gather_slot(P[p], 1)));   // H(i+1,i) = |w|  :383
+                }
             }
             DB_CHECK(reduce_to(PH_NORM, h_slot, i + 1));
             for (int p = 0; p < np; ++p) DB_CHECK(vec_scale_inv(W[(size_t)p].n, W[(size_t)p].v[(size_t)i + 1], W[(size_t)p].w, W[(size_t)p].d_h + i + 1));
@@ -1371,6 +1417,240 @@ int dist_gmres(int np, drops_b200_dist_matrix_s* const* P, double* const* x, con
         if (resid <= *tol) { *tol = resid; *max_iter = j; return 1; }         // :449-456
     }
     *tol = resid;
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// MINRES / PMINRES on the partitioned system -- num/krylovsolver.h:926-1161 (MResSolverCL :1918-1941, PMResSolverCL
+// :1944-1972 with PLanczosONBCL over JACPcCL / DummyPcCL).  The serial driver of krylov.cu with every vector step on
+// all partitions and every reduction as partial -> gather -> rank-ordered sum; the Lanczos scalars a1, b1 are fetched
+// once per step (all ranks read identical values), the rotations run on the host of every rank, so all ranks stop in
+// the same iteration.  Products carry the fused dot (a1 = (A q1 - b0 q0) . q1) over the peer-to-peer halo.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct DRing3 { int front = 0; int at(int k) const { int i = k; if (i < 0) i += 3; else if (i >= 3) i -= 3; i += front; return i < 3 ? i : i - 3; } void rotate() { front = (front + 1) % 3; } };
+struct DRing2 { int front = 0; int at(int k) const { int i = k; if (i < 0) i += 2; else if (i >= 2) i -= 2; i += front; return i < 2 ? i : i - 2; } void rotate() { front = (front + 1) % 2; } };
+inline void mr_gen_rot(double& dx, double& dy, double& cs, double& sn) { gm_gen_rot(dx, dy, cs, sn); }
+inline void mr_app_rot(double& dx, double& dy, double cs, double sn) { gm_app_rot(dx, dy, cs, sn); }
+}  // namespace
+
+int dist_minres(int np, drops_b200_dist_matrix_s* const* P, double* const* x, const double* const* b, int precond, int pc,
+                double omega, int* max_iter, double* tol, int relative)
+{
+    DB_CHECK(check_parts(np, P));
+    DB_ARG(max_iter && tol, "null max_iter/tol");
+    DB_ARG(!precond || pc == DROPS_B200_PC_DUMMY || pc == DROPS_B200_PC_JACOBI, "unknown preconditioner");
+    Ctx& c = ctx();
+    cudaStream_t st = c.stream;
+    drops_b200_comm_s* comm = P[0]->comm;
+    const bool pre = precond != 0;
+    const bool jac = pre && pc == DROPS_B200_PC_JACOBI;
+    {
+        double flag = 0.0;
+        for (int p = 0; p < np; ++p) if (jac && !P[p]->diag_ok) flag = 1.0;
+        DB_CHECK(drops_b200_comm_allreduce_max(comm, &flag));
+        if (flag != 0.0) { set_error("JACPcCL: at least one row (on some rank) stores no diagonal entry"); return DROPS_B200_E_NODIAG; }
+    }
+    // per partition: 0 tmp / r0, 1-3 q ring, 4-6 t ring, 7-9 p ring; scalars [0] a1, [1] b1 or b1^2, [2] |r|^2
+    struct Part { double* tmp; double* qv[3]; double* tv[3]; double* pv[3]; double* d_scal; size_t n; };
+    std::vector<Part> W((size_t)np);
+    for (int p = 0; p < np; ++p) {
+        Part& w = W[(size_t)p];
+        w.n = P[p]->n_owned;
+        DB_CHECK(ensure_part_scalars(P[p], 1));
+        w.tmp = dwork(P[p], 0);
+        for (int i = 0; i < 3; ++i) { w.qv[i] = dwork(P[p], 1 + i); w.tv[i] = dwork(P[p], 4 + i); w.pv[i] = dwork(P[p], 7 + i); }
+        for (int i = 0; i < 3; ++i) if (!w.tmp || !w.qv[i] || !w.tv[i] || !w.pv[i]) return DROPS_B200_E_NOMEM;
+        if (P[p]->small_alloc < 8) {
+            dev_free(P[p]->d_small); P[p]->d_small = nullptr; P[p]->small_alloc = 0;
+            DB_CHECK(dev_alloc(&P[p]->d_small, (size_t)8));
+            P[p]->small_alloc = 8;
+        }
+        w.d_scal = P[p]->d_small;
+    }
+    std::vector<PartArgs> a((size_t)np);
+    DRing3 q3, t3; DRing2 q2r, br;
+    double bb[2] = {0.0, 0.0};
+    auto Q = [&](Part& w, int k) -> double* { return pre ? w.qv[q2r.at(k)] : w.qv[q3.at(k)]; };
+    auto T = [&](Part& w, int k) -> double* { return w.tv[t3.at(k)]; };
+    auto B = [&](int k) -> double& { return bb[br.at(k)]; };
+    auto reduce_to = [&](int phase, int idx) -> int {             // gathered partials -> d_scal[idx] on every partition
+        DB_CHECK(allgather_partials(comm, 1));
+        for (int p = 0; p < np; ++p) DB_CHECK(scalars_kernel(phase, P[p], nullptr, W[(size_t)p].d_scal + idx));
+        return 0;
+    };
+    auto fetch_host = [&](int cnt) -> int {
+        DB_CUDA(cudaMemcpyAsync(c.h_scalars, W[0].d_scal, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
+        DB_CUDA(cudaStreamSynchronize(st));
+        return check_p2p_faults(np, P);                           // a stale partial must not steer the rotations
+    };
+    auto apply_pc = [&](int p, double* out, const double* in) -> int {
+        if (jac) return vec_jacobi(W[(size_t)p].n, omega, P[p]->diag, in, out);
+        return vec_copy(W[(size_t)p].n, out, in);
+    };
+    double a0 = 0.0, norm_r0 = 0.0;
+    bool nobreakdown = true;
+    auto step = [&]() -> int {
+        if (!pre) {                                                           // LanczosStep :926-943
+            for (int p = 0; p < np; ++p) {
+                Part& w = W[(size_t)p];
+                a[(size_t)p] = PartArgs(); a[(size_t)p].p2p = true;
+                a[(size_t)p].x = Q(w, 0); a[(size_t)p].y = Q(w, 1); a[(size_t)p].epilogue = EPI_AXMBY; a[(size_t)p].aux = Q(w, -1);
+                a[(size_t)p].beta_val = B(-1); a[(size_t)p].dotv = Q(w, 0);    // q2 = A q1 - b0 q0; a1 = q2.q1
+            }
+            DB_CHECK(dist_spmv_run(np, P, a.data()));
+            DB_CHECK(reduce_to(PH_DOT, 0));
+            for (int p = 0; p < np; ++p) {
+                Part& w = W[(size_t)p];
+                DB_CHECK(lanczos_orth(w.n, Q(w, 1), Q(w, 0), w.d_scal + 0, nullptr, gather_slot(P[p], 1)));   // q2 -= a1 q1; |q2|^2
+            }
+            DB_CHECK(reduce_to(PH_NORM, 1));
+            DB_CHECK(fetch_host(2));
+            a0 = c.h_scalars[0];
+            const double b1 = c.h_scalars[1];
+            B(0) = b1;
+            if (b1 < 1e-15) { nobreakdown = false; return 0; }
+            for (int p = 0; p < np; ++p) DB_CHECK(vec_div_scalar(W[(size_t)p].n, Q(W[(size_t)p], 1), Q(W[(size_t)p], 1), b1, 0));
+        } else {                                                              // PLanczosStep :989-1008
+            for (int p = 0; p < np; ++p) {
+                Part& w = W[(size_t)p];
+                a[(size_t)p] = PartArgs(); a[(size_t)p].p2p = true;
+                a[(size_t)p].x = Q(w, 0); a[(size_t)p].y = T(w, 1); a[(size_t)p].epilogue = EPI_AXMBY; a[(size_t)p].aux = T(w, -1);
+                a[(size_t)p].beta_val = B(-1); a[(size_t)p].dotv = Q(w, 0);    // t2 = A q1 - b0 t0; a1 = t2.q1
+            }
+            DB_CHECK(dist_spmv_run(np, P, a.data()));
+            DB_CHECK(reduce_to(PH_DOT, 0));
+            for (int p = 0; p < np; ++p) {
+                Part& w = W[(size_t)p];
+                DB_CHECK(planczos_orth(w.n, T(w, 1), T(w, 0), w.d_scal + 0, Q(w, 1), pc, omega, P[p]->diag, nullptr, gather_slot(P[p], 1)));
+            }
+            DB_CHECK(reduce_to(PH_DOT, 1));
+            DB_CHECK(fetch_host(2));
+            a0 = c.h_scalars[0];
+            const double b1 = std::sqrt(c.h_scalars[1]);
+            B(0) = b1;
+            if (b1 < 1e-15) { nobreakdown = false; return 0; }
+            for (int p = 0; p < np; ++p) {
+                Part& w = W[(size_t)p];
+                DB_CHECK(vec_div_scalar(w.n, T(w, 1), T(w, 1), b1, 1));
+                DB_CHECK(vec_div_scalar(w.n, Q(w, 1), Q(w, 1), b1, 1));
+            }
+        }
+        nobreakdown = true;
+        return 0;
+    };
+    auto true_residual_sq = [&]() -> int {                                    // tmp = b - A x; d_scal[2] = |tmp|^2 over all ranks
+        for (int p = 0; p < np; ++p) {
+            a[(size_t)p] = PartArgs(); a[(size_t)p].x = x[p]; a[(size_t)p].y = W[(size_t)p].tmp;
+            a[(size_t)p].epilogue = EPI_RESID; a[(size_t)p].aux = b[p];
+        }
+        DB_CHECK(dist_spmv_run(np, P, a.data()));
+        for (int p = 0; p < np; ++p) DB_CHECK(vec_dot_partial(W[(size_t)p].n, W[(size_t)p].tmp, W[(size_t)p].tmp, gather_slot(P[p], 1)));
+        return reduce_to(PH_DOT, 2);
+    };
+
+    // r0 = b - A x :1158, new basis :958-967 / :1030-1040
+    for (int p = 0; p < np; ++p) {
+        a[(size_t)p] = PartArgs(); a[(size_t)p].x = x[p]; a[(size_t)p].y = W[(size_t)p].tmp;
+        a[(size_t)p].epilogue = EPI_RESID; a[(size_t)p].aux = b[p];
+    }
+    DB_CHECK(dist_spmv_run(np, P, a.data()));
+    if (!pre) {
+        for (int p = 0; p < np; ++p) {
+            Part& w = W[(size_t)p];
+            DB_CHECK(vec_fill(w.n, Q(w, -1), 0.0));
+            DB_CHECK(vec_dot_partial(w.n, w.tmp, w.tmp, gather_slot(P[p], 1)));
+        }
+        DB_CHECK(reduce_to(PH_DOT, 0));
+        DB_CHECK(fetch_host(1));
+        norm_r0 = std::sqrt(c.h_scalars[0]);
+        for (int p = 0; p < np; ++p) {
+            Part& w = W[(size_t)p];
+            DB_CHECK(vec_div_scalar(w.n, Q(w, 0), w.tmp, norm_r0, 0));
+            DB_CHECK(vec_fill(w.n, Q(w, 1), 0.0));
+        }
+    } else {
+        for (int p = 0; p < np; ++p) {
+            Part& w = W[(size_t)p];
+            DB_CHECK(vec_fill(w.n, T(w, -1), 0.0));
+            DB_CHECK(apply_pc(p, Q(w, -1), w.tmp));
+            DB_CHECK(vec_dot_partial(w.n, Q(w, -1), w.tmp, gather_slot(P[p], 1)));
+        }
+        DB_CHECK(reduce_to(PH_DOT, 0));
+        DB_CHECK(fetch_host(1));
+        norm_r0 = std::sqrt(c.h_scalars[0]);
+        for (int p = 0; p < np; ++p) {
+            Part& w = W[(size_t)p];
+            DB_CHECK(vec_div_scalar(w.n, T(w, 0), w.tmp, norm_r0, 0));
+            DB_CHECK(vec_div_scalar(w.n, Q(w, 0), Q(w, -1), norm_r0, 0));
+            DB_CHECK(vec_fill(w.n, T(w, 1), 0.0));
+        }
+    }
+    B(-1) = 0.;
+    DB_CHECK(step());
+
+    // PMINRES :1069-1152
+    double normb = std::fabs(norm_r0), res = norm_r0;
+    bool lucky = !nobreakdown;
+    double cc[3] = {0, 0, 0}, ss[3] = {0, 0, 0}, rr[3][3] = {{0}}, bq[2][2] = {{0}};
+    DRing3 cr, sr, rrg, pr; DRing2 bqr;
+    if (normb == 0.0 || !relative) normb = 1.0;
+    if ((res = norm_r0 / normb) <= *tol) { *tol = res; *max_iter = 0; return 1; }
+    for (int k = 1; k <= *max_iter; ++k) {
+        double* R0 = rr[rrg.at(0)];
+        double* B0 = bq[bqr.at(0)];
+        const double* Bm1 = bq[bqr.at(-1)];
+        int mode;
+        switch (k) {
+        case 1:
+            mr_gen_rot(a0, B(0), cc[cr.at(0)], ss[sr.at(0)]);
+            R0[0] = std::sqrt(a0 * a0 + B(0) * B(0));
+            B0[0] = 1.; B0[1] = 0.;
+            mr_app_rot(B0[0], B0[1], cc[cr.at(0)], ss[sr.at(0)]);
+            mode = 1;
+            break;
+        case 2:
+            R0[0] = B(-1); R0[1] = a0; R0[2] = B(0);
+            mr_app_rot(R0[0], R0[1], cc[cr.at(-1)], ss[sr.at(-1)]);
+            mr_gen_rot(R0[1], R0[2], cc[cr.at(0)], ss[sr.at(0)]);
+            mr_app_rot(R0[1], R0[2], cc[cr.at(0)], ss[sr.at(0)]);
+            B0[0] = Bm1[1]; B0[1] = 0.;
+            mr_app_rot(B0[0], B0[1], cc[cr.at(0)], ss[sr.at(0)]);
+            mode = 2;
+            break;
+        default: {
+            R0[0] = 0.; R0[1] = B(-1); R0[2] = a0;
+            double tmpb = B(0);
+            mr_app_rot(R0[0], R0[1], cc[cr.at(-2)], ss[sr.at(-2)]);
+            mr_app_rot(R0[1], R0[2], cc[cr.at(-1)], ss[sr.at(-1)]);
+            mr_gen_rot(R0[2], tmpb, cc[cr.at(0)], ss[sr.at(0)]);
+            mr_app_rot(R0[2], tmpb, cc[cr.at(0)], ss[sr.at(0)]);
+            B0[0] = Bm1[1]; B0[1] = 0.;
+            mr_app_rot(B0[0], B0[1], cc[cr.at(0)], ss[sr.at(0)]);
+            mode = 3;
+        } }
+        for (int p = 0; p < np; ++p) {                                        // p[0] = ...; x += norm_r0 b[0][0] p[0]  :1095-1129
+            Part& w = W[(size_t)p];
+            DB_CHECK(minres_update(w.n, mode, Q(w, 0), w.pv[pr.at(-2)], w.pv[pr.at(-1)], w.pv[pr.at(0)], x[p],
+                                   R0[0], R0[1], R0[2], norm_r0 * B0[0]));
+        }
+        res = std::fabs(norm_r0 * B0[1]) / normb;
+        if (res <= *tol || lucky) {                                           // :1132-1141
+            DB_CHECK(true_residual_sq());
+            DB_CUDA(cudaMemcpyAsync(c.h_scalars, W[0].d_scal + 2, sizeof(double), cudaMemcpyDeviceToHost, st));
+            DB_CUDA(cudaStreamSynchronize(st));
+            DB_CHECK(check_p2p_faults(np, P));
+            const double realRes = std::sqrt(c.h_scalars[0]);
+            if (!(realRes > *tol)) { *tol = res; *max_iter = k; return 1; }
+        }
+        if (pre) { q2r.rotate(); t3.rotate(); } else q3.rotate();            // :973-978 / :1046-1051
+        br.rotate();
+        DB_CHECK(step());
+        if (!nobreakdown) lucky = true;
+        cr.rotate(); sr.rotate(); rrg.rotate(); pr.rotate(); bqr.rotate();
+    }
+    *tol = res;
     return 0;
 }
 
@@ -1404,6 +1684,8 @@ static int comm_common(drops_b200_comm_s* C)
     DB_CUDA(cudaEventCreateWithFlags(&C->ev_halo, cudaEventDisableTiming));
     DB_CHECK(dev_alloc(&C->gathered, (size_t)C->world * kMaxQ));
     DB_CUDA(cudaMemset(C->gathered, 0, (size_t)C->world * kMaxQ * sizeof(dd)));
+    DB_CHECK(dev_alloc(&C->wide, (size_t)C->world * kWideQ));
+    DB_CUDA(cudaMemset(C->wide, 0, (size_t)C->world * kWideQ * sizeof(dd)));
     // buffer of the peer-to-peer reductions: 2 parity halves of world x kMaxQ partials, then world flags; one
     // allocation of >= 2 MB so that a single CUDA IPC handle maps it into the peers
     {
@@ -1537,7 +1819,7 @@ int drops_b200_comm_destroy(drops_b200_comm_t C)
     if (C->ev_pack) cudaEventDestroy(C->ev_pack);
     if (C->ev_halo) cudaEventDestroy(C->ev_halo);
     if (C->comm_stream) cudaStreamDestroy(C->comm_stream);
-    dev_free(C->gathered);
+    dev_free(C->gathered); dev_free(C->wide);
     for (void* m : C->ipc_mapped) cudaIpcCloseMemHandle(m);
     dev_free(C->red_buf); dev_free(C->red_fault); dev_free(C->d_peer_red); dev_free(C->d_peer_redflag);
     delete C;
@@ -1709,6 +1991,22 @@ int drops_b200_dist_gmres_dev(int nparts, const drops_b200_dist_matrix_t* A, con
         xs[(size_t)p] = x[p]->d; bs[(size_t)p] = b[p]->d;
     }
     return dist_gmres(nparts, A, xs.data(), bs.data(), pc, omega, restart, max_iter, tol, relative, left_precond);
+}
+
+int drops_b200_dist_minres_dev(int nparts, const drops_b200_dist_matrix_t* A, const drops_b200_vector_t* x,
+                               const drops_b200_vector_t* b, int precond, int pc, double omega, int* max_iter, double* tol,
+                               int relative)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(A && x && b, "null argument");
+    DB_CHECK(check_parts(nparts, A));
+    std::vector<double*> xs((size_t)nparts);
+    std::vector<const double*> bs((size_t)nparts);
+    for (int p = 0; p < nparts; ++p) {
+        DB_ARG(x[p] && b[p] && x[p]->n == A[p]->n_owned && b[p]->n == A[p]->n_owned, "vector size != owned rows of the partition");
+        xs[(size_t)p] = x[p]->d; bs[(size_t)p] = b[p]->d;
+    }
+    return dist_minres(nparts, A, xs.data(), bs.data(), precond, pc, omega, max_iter, tol, relative);
 }
 
 int drops_b200_dist_pcg_dev(int nparts, const drops_b200_dist_matrix_t* A, const drops_b200_vector_t* x,

@@ -45,6 +45,7 @@ struct drops_b200_comm_s {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_pack = nullptr, ev_halo = nullptr;
     db200::dd* gathered = nullptr;           // world * kMaxQ reduction partials, rank-major
+    db200::dd* wide = nullptr;               // world * kWideQ partials: the i+1 products of a classical Gram-Schmidt column
     std::vector<drops_b200_dist_matrix_s*> parts;   // COMM_LOCAL: registered partitions by rank
     // Peer-to-peer reductions ("dist.p2p_reduce"): every rank stores its partials straight into all ranks'
     // buffers (CUDA IPC mappings over NVLink) and raises its sequence number there; k_dist_scalars waits for

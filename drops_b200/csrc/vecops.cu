@@ -1036,7 +1036,7 @@ int cgs_update(size_t n, double* w, const double* const* d_vptrs, const double* 
 // MINRES pieces
 // ------------------------------------------------------------------------------------------
 struct OpLanczosOrth {
-    double* q2; const double* q1; const double* a1p; double* b1; double a1;
+    double* q2; const double* q1; const double* a1p; double* b1; double a1; dd* part_out;
     __device__ bool begin() { a1 = *a1p; return true; }
     __device__ void elem(size_t i, dd* acc)
     {
@@ -1044,16 +1044,20 @@ struct OpLanczosOrth {
         q2[i] = v;
         acc[0] = dd_add_prod(acc[0], v, v);
     }
-    __device__ void finish(const dd* acc) { *b1 = sqrt(dd_round(acc[0])); }   // :934
+    __device__ void finish(const dd* acc)
+    {
+        if (part_out) { *part_out = acc[0]; return; }           // partitioned system: |q2|^2 summed over the ranks later
+        *b1 = sqrt(dd_round(acc[0]));                           // :934
+    }
 };
-int lanczos_orth(size_t n, double* q2, const double* q1, const double* d_a1, double* d_b1)
+int lanczos_orth(size_t n, double* q2, const double* q1, const double* d_a1, double* d_b1, dd* part_out)
 {
-    return launch_stream<1>(n, OpLanczosOrth{q2, q1, d_a1, d_b1, 0.0}, "minres.orth");
+    return launch_stream<1>(n, OpLanczosOrth{q2, q1, d_a1, d_b1, 0.0, part_out}, "minres.orth");
 }
 
 struct OpPLanczosOrth {
     double* t2; const double* t1; const double* a1p; double* q2; int pc; double omega; const double* d;
-    double* b1sq; double a1;
+    double* b1sq; double a1; dd* part_out;
     __device__ bool begin() { a1 = *a1p; return true; }
     __device__ void elem(size_t i, dd* acc)
     {
@@ -1063,12 +1067,16 @@ struct OpPLanczosOrth {
         q2[i] = q;
         acc[0] = dd_add_prod(acc[0], q, t);                     // dot(q2,t2)      :1002
     }
-    __device__ void finish(const dd* acc) { *b1sq = dd_round(acc[0]); }
+    __device__ void finish(const dd* acc)
+    {
+        if (part_out) { *part_out = acc[0]; return; }
+        *b1sq = dd_round(acc[0]);
+    }
 };
 int planczos_orth(size_t n, double* t2, const double* t1, const double* d_a1, double* q2, int pc,
-                  double omega, const double* d, double* d_b1sq)
+                  double omega, const double* d, double* d_b1sq, dd* part_out)
 {
-    return launch_stream<1>(n, OpPLanczosOrth{t2, t1, d_a1, q2, pc, omega, d, d_b1sq, 0.0}, "minres.orth");
+    return launch_stream<1>(n, OpPLanczosOrth{t2, t1, d_a1, q2, pc, omega, d, d_b1sq, 0.0, part_out}, "minres.orth");
 }
 
 struct OpDivScalar {

@@ -116,10 +116,10 @@ int cgs_update(size_t n, double* w, const double* const* d_vptrs, const double* 
 
 // ---- MINRES building blocks (num/krylovsolver.h:926-1152) ----------------------------------------
 // q2 -= (*d_a1) * q1;  *d_b1 = |q2|_2                                           :933-934
-int lanczos_orth(size_t n, double* q2, const double* q1, const double* d_a1, double* d_b1);
+int lanczos_orth(size_t n, double* q2, const double* q1, const double* d_a1, double* d_b1, dd* part_out = nullptr);
 // PLanczos: t2 -= a1*t1 (t1 may differ from the dot partner), then q2 = M^-1 t2, b1sq = q2.t2
 int planczos_orth(size_t n, double* t2, const double* t1, const double* d_a1, double* q2,
-                  int pc, double omega, const double* d, double* d_b1sq);
+                  int pc, double omega, const double* d, double* d_b1sq, dd* part_out = nullptr);
 // out = in / s (mode 0, :941, :965)  or  out = in * (1/s) (mode 1, :1005-1006); out may alias in
 int vec_div_scalar(size_t n, double* out, const double* in, double s, int mode);
 // p0 = (q - r0*pm2 - r1*pm1) {/ r2 | * (1/r2)};  x += f*p0                        :1090-1131

@@ -422,11 +422,21 @@ DROPS_B200_API int drops_b200_dist_pcg_dev(int nparts, const drops_b200_dist_mat
 /* GMRES(m) on the partitioned system: the serial driver of num/krylovsolver.h:320-461 (modified Gram-Schmidt,
  * left or right preconditioning with JACPcCL / DummyPcCL), every dot product summed over the ranks in rank
  * order (one small all-gather per Gram-Schmidt step -- what the reference's distributed variants,
- * krylovsolver.h:528-916, do with GlobalSum).  All ranks compute identical Hessenberg columns and stop in the
+ * krylovsolver.h:528-916, do with GlobalSum; "gmres.ortho" = 1: classical Gram-Schmidt as ModGMRES :465-494, :862-866,
+ * all i+1 products of a column in one pass and ONE reduction over the ranks).  All ranks compute identical Hessenberg columns and stop in the
  * same iteration.  Arguments and return value as drops_b200_gmres_dev. */
 DROPS_B200_API int drops_b200_dist_gmres_dev(int nparts, const drops_b200_dist_matrix_t* A, const drops_b200_vector_t* x,
                                              const drops_b200_vector_t* b, int pc, double omega, int restart,
                                              int* max_iter, double* tol, int relative, int left_precond);
+
+/* MINRES / PMINRES on the partitioned system (num/krylovsolver.h:926-1161; MResSolverCL :1918-1941, PMResSolverCL
+ * :1944-1972 -- the solvers the reference's parallel Stokes drivers instantiate with ExchangeCL): precond = 0 plain
+ * Lanczos, 1 = preconditioned Lanczos with pc in {DUMMY, JACOBI}.  Two rank-ordered reductions per Lanczos step (the
+ * reference: ParDot + Norm, exchange.h), rotations on the host of every rank from identical scalars.  Arguments and
+ * return value as drops_b200_minres_dev. */
+DROPS_B200_API int drops_b200_dist_minres_dev(int nparts, const drops_b200_dist_matrix_t* A, const drops_b200_vector_t* x,
+                                              const drops_b200_vector_t* b, int precond, int pc, double omega,
+                                              int* max_iter, double* tol, int relative);
 
 /* -- synthetic brick, z-slab partition: rank r owns the lattice planes [k0, k1) (1-based, M planes
  *    split evenly), rows in ascending global id.  Generated on the device, global ids as above. */

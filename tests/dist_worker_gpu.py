@@ -64,6 +64,27 @@ def main():
         tl = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(tl, t)
         assert all(torch.equal(a, t) for a in tl)
+        # the same with classical Gram-Schmidt (ModGMRES, krylovsolver.h:465-494): one wide reduction per column
+        capi.set_option("gmres.ortho", 1)
+        xc = capi.Vector(owned.size)
+        cconv, cit, cres = capi.dist_gmres([A], [xc], [b], 20, 3000, 1e-10, True)
+        capi.set_option("gmres.ortho", 0)
+        assert cconv and abs(cit - git) <= 1, (cit, git)
+        cerr = np.linalg.norm(xc.download() - gref[3][owned]) / np.linalg.norm(gref[3][owned])
+        assert cerr <= 1e-8, cerr
+        # MINRES and PMINRES<JACPcCL> over the ranks against the single-GPU driver
+        merr = []
+        for precond, pc in ((0, capi.PC_DUMMY), (1, capi.PC_JACOBI)):
+            mref = G.minres(np.zeros(n), bref, 3000, 1e-9, True) if not precond else G.pminres_jacobi(np.zeros(n), bref, 3000, 1e-9, True)
+            xm = capi.Vector(owned.size)
+            mconv, mit, mres = capi.dist_minres([A], [xm], [b], 3000, 1e-9, True, precond, pc)
+            assert mconv and mref[0] and abs(mit - mref[1]) <= 1, (mit, mref[1])
+            merr.append(np.linalg.norm(xm.download() - mref[3][owned]) / np.linalg.norm(mref[3][owned]))
+            assert merr[-1] <= 1e-8, merr
+            t = torch.tensor([float(mit), mres], dtype=torch.float64, device="cuda")
+            tl = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(tl, t)
+            assert all(torch.equal(a, t) for a in tl)
         fmt = A.format()
         assert not fmt["p2p_fault"]
         if fmt["p2p"]:                          # the same solve with the halo over ncclSend/ncclRecv: same bits
@@ -74,7 +95,8 @@ def main():
             assert it1 == it and res1 == res and np.array_equal(x1.download(), x0.download())
         if rank == 0:
             print(f"P{fe} N={N} numbering={numbering} world={world} p2p={fmt['p2p']} p2p_reduce={fmt['p2p_reduce']}: iters {it} (single GPU {ref[1]}), "
-                  f"rel.diff {err:.2e}, gmres iters {git} (single GPU {gref[1]}), rel.diff {gerr:.2e}, "
+                  f"rel.diff {err:.2e}, gmres iters {git} (single GPU {gref[1]}), rel.diff {gerr:.2e}, cgs iters {cit}, rel.diff {cerr:.2e}, "
+                  f"minres/pminres rel.diff {merr[0]:.2e}/{merr[1]:.2e}, "
                   f"ghosts {ex.n_ghost}, info {A.info()}", flush=True)
     dist.barrier()
     print("WORKER_OK", rank, flush=True)

@@ -167,6 +167,19 @@ def test_partitioned_gmres_matches_reference_golden(gpu, name, tag, world):
             assert rel(xg, g[key + "_x"]) <= x_rtol, (key, rel(xg, g[key + "_x"]))
         one = single.gmres_jacobi(np.zeros(n), g["b"], restart, 400, 1e-10, True, 1.0, left)
         assert one[1] == it and rel(xg, one[3]) <= 1e-9
+        # "gmres.ortho" = 1: classical Gram-Schmidt, the reference's distributed ModGMRES (krylovsolver.h:465-494, :862-866) --
+        # one multi-dot and ONE reduction over the ranks per column; same iteration count, same solution to 1e-8, and the
+        # single-GPU driver in the same mode agrees with it
+        try:
+            gpu.set_option("gmres.ortho", 1)
+            x1 = [gpu.Vector(l[0].size) for l in loc]
+            conv1, it1, res1 = gpu.dist_gmres(mats, x1, bs, restart, 400, 1e-10, True, left=left)
+            assert conv1 == conv and abs(it1 - it) <= 1, (key, it1, it)
+            assert rel(gather(loc, x1, n), g[key + "_x"]) <= max(x_rtol, 1e-8), (key, rel(gather(loc, x1, n), g[key + "_x"]))
+            one1 = single.gmres_jacobi(np.zeros(n), g["b"], restart, 400, 1e-10, True, 1.0, left)
+            assert one1[1] == it1 and rel(gather(loc, x1, n), one1[3]) <= 1e-9
+        finally:
+            gpu.set_option("gmres.ortho", 0)
     if tag == "sym":
         x0 = [gpu.Vector(l[0].size) for l in loc]
         conv, it, res = gpu.dist_gmres(mats, x0, bs, 20, 400, 1e-10, False, pc=gpu.PC_DUMMY)
@@ -176,6 +189,39 @@ def test_partitioned_gmres_matches_reference_golden(gpu, name, tag, world):
     x0 = [gpu.Vector(l[0].size) for l in loc]
     conv, it, res = gpu.dist_gmres(mats, x0, bs, 4, 6, 1e-30, True)
     assert not conv and it == 6
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_partitioned_minres_matches_reference_golden(gpu, world):
+    """MINRES and PMINRES<JACPcCL> on the partitioned system (krylovsolver.h:926-1161, the solvers of the reference's
+    parallel Stokes drivers) against the compiled reference's serial run: iteration counts +-1, solutions to 1e-8, and
+    the single-GPU driver with the same arguments."""
+    g = load_golden("brick_fe2_N6_num1.npz")
+    n = int(g["rows"])
+    rb, ci, va = g["rowbeg"], g["colind"], g["val"]
+    part = gpu.partition_rows(rb, ci, world)
+    comm, loc, mats = build_parts(gpu, rb, ci, va, part, world)
+    bs = scatter(gpu, loc, g["b"])
+    single = gpu.Matrix(n, n, rb, ci, va)
+    for key, precond, pc in (("sym_minres", 0, gpu.PC_DUMMY), ("sym_pminresjac", 1, gpu.PC_JACOBI)):
+        x0 = [gpu.Vector(l[0].size) for l in loc]
+        conv, it, res = gpu.dist_minres(mats, x0, bs, 400, 1e-9, False, precond, pc)
+        rconv, rit, rres = bool(g[key][0]), int(g[key][1]), float(g[key][2])
+        assert conv == rconv and abs(it - rit) <= 1, (key, it, rit)
+        xg = gather(loc, x0, n)
+        if it == rit:
+            assert abs(res - rres) <= 1e-3 * abs(rres) + 1e-15
+            assert rel(xg, g[key + "_x"]) <= 1e-8, (key, rel(xg, g[key + "_x"]))
+        one = single.minres(np.zeros(n), g["b"], 400, 1e-9) if not precond else single.pminres_jacobi(np.zeros(n), g["b"], 400, 1e-9)
+        assert one[1] == it and rel(xg, one[3]) <= 1e-9
+    # zero right-hand side: converged before the first step; max_iter reached: not converged
+    zs = [gpu.Vector(l[0].size) for l in loc]
+    x0 = [gpu.Vector(l[0].size) for l in loc]
+    conv, it, res = gpu.dist_minres(mats, x0, zs, 10, 1e-10, False)
+    assert conv and it == 0 and res == 0.0
+    x0 = [gpu.Vector(l[0].size) for l in loc]
+    conv, it, res = gpu.dist_minres(mats, x0, bs, 3, 1e-30, False)
+    assert not conv
 
 
 @pytest.mark.parametrize("fe,N,numbering,world", [(2, 16, 1, 4), (2, 16, 0, 3), (1, 24, 0, 2), (2, 12, 1, 8)])
