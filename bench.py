@@ -333,6 +333,12 @@ def run_ours(args):
     layout = A.layout()
     packed = (vdict["packed"] or vdict["six_byte"]) and capi.get_option("spmv.pk", 1.0) != 0.0
     entry_bytes = (4.0 if vdict["packed"] else 6.0) if packed else 12.0
+    # segment descriptors: slices that are one line segment are read as ONE 16-byte record per
+    # entry-row (0.5 B per stored entry), the rest as packed words
+    info_A = A.info()
+    seg_entries = float(layout.get("segment_entries", 0)) if (vdict["packed"] and capi.get_option("spmv.segments", 1.0) != 0.0 and
+                                                             capi.get_option("pcg.reorder", 1.0) != 0.0) else 0.0
+    segments = seg_entries > 0
     passes = (12.0 if capi.get_option("pcg.defer_x", 1.0) != 0.0 else 13.0) + \
              (0.0 if capi.get_option("pcg.fused_dot", 1.0) != 0.0 else 2.0)
     general_passes = passes                       # the 12-byte leg reads d as a vector
@@ -340,36 +346,83 @@ def run_ours(args):
     if diag_values > 0 and capi.get_option("pcg.defer_x", 1.0) != 0.0:
         # the update kernel reads d as one byte per row (and, with "pcg.diag_index_direction", the direction kernel too)
         passes -= (7.0 / 8.0) * (2.0 if capi.get_option("pcg.diag_index_direction", 0.0) != 0.0 else 1.0)
-    spmv_bytes = entry_bytes * nnz + 4.0 * (n + 1) + 16.0 * n
-    iter_bytes = entry_bytes * nnz + 4.0 * (n + 1) + passes * 8.0 * n
+    packed_spmv_bytes = entry_bytes * nnz + 4.0 * (n + 1) + 16.0 * n
+    if segments:
+        stream_bytes = 0.5 * seg_entries + 4.0 * (float(info_A["padded_nnz"]) - seg_entries)
+        spmv_bytes = stream_bytes + 4.0 * (n + 1) + 16.0 * n
+    else:
+        stream_bytes = entry_bytes * nnz
+        spmv_bytes = packed_spmv_bytes
+    iter_bytes = stream_bytes + 4.0 * (n + 1) + passes * 8.0 * n
     survey_spmv_bytes = 12.0 * nnz + 4.0 * (n + 1) + 16.0 * n
     survey_iter_bytes = 12.0 * nnz + 4.0 * (n + 1) + 13.0 * 8.0 * n
     spmv_avg_ms = spmv_ms / max(spmv_cnt, 1)
     achieved = spmv_bytes / (spmv_avg_ms / 1e3) / 1e9
-    kernel_name = ("k_spmv_sell_pk<EPI_NONE,exact,dot> (q = A p fused with p.q, dictionary-packed %d-byte stream, dictionary in the kernel's parameter block)" % int(entry_bytes)
-                   if packed else "k_spmv_sell<EPI_NONE,exact,dot> (q = A p fused with p.q)")
+    if segments:
+        kernel_name = ("k_spmv_sell_sc<EPI_NONE,exact,dot> (q = A p fused with p.q; %.0f %% of the stored entries run from 16-byte segment "
+                       "descriptors -- 0.5 B per entry --, the rest from the dictionary-packed 4-byte stream; dictionary in the kernel's "
+                       "parameter block)" % (100.0 * seg_entries / float(info_A["padded_nnz"])))
+    elif packed:
+        kernel_name = "k_spmv_sell_pk<EPI_NONE,exact,dot> (q = A p fused with p.q, dictionary-packed %d-byte stream, dictionary in the kernel's parameter block)" % int(entry_bytes)
+    else:
+        kernel_name = "k_spmv_sell<EPI_NONE,exact,dot> (q = A p fused with p.q)"
     roofline = {"bound": "hbm", "kernel": kernel_name,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "traffic": None,
-                "algorithmic_bytes_per_launch": spmv_bytes, "bytes_per_stored_entry": entry_bytes,
+                "algorithmic_bytes_per_launch": spmv_bytes, "bytes_per_stored_entry": stream_bytes / max(nnz, 1),
                 "avg_launch_ms": spmv_avg_ms, "launches": spmv_cnt,
                 "survey_12B_layout": {"algorithmic_bytes_per_launch": survey_spmv_bytes,
                                       "equivalent_gbs": survey_spmv_bytes / (spmv_avg_ms / 1e3) / 1e9,
-                                      "note": "what a 12 B/entry stream would have to sustain to match this launch time"},
+                                      "frac": survey_spmv_bytes / (spmv_avg_ms / 1e3) / 1e9 / peak,
+                                      "note": "SURVEY.md 8(d)'s own byte count (12 B/entry CSR): what a 12 B/entry stream would have to sustain to match this launch time"},
                 "iteration": {"algorithmic_bytes": iter_bytes, "vector_passes": passes, "diagonal_value_list": diag_values,
                               "achieved_gbs": iter_bytes * args.steps * iters / (ms / 1e3) / 1e9,
                               "frac": iter_bytes * args.steps * iters / (ms / 1e3) / 1e9 / peak,
                               "survey_12B_13pass_equivalent_gbs": survey_iter_bytes * args.steps * iters / (ms / 1e3) / 1e9,
                               "kernel_ms_share": {"spmv": spmv_ms / ms, "pcg.update": upd_ms / ms,
                                                   "pcg.direction": dir_ms / ms, "dot": vec_ms / ms}}}
+    if segments:
+        roofline["note"] = ("the segment kernel streams a third of the packed kernel's bytes and is bound by the L1 data pipe (gathers of x), "
+                            "not by HBM (profiles/r02_ncu_spmv_sc.raw.csv: l1tex data-pipe wavefronts 80 %, DRAM 24 % busy): `frac` is the fraction "
+                            "of the HBM peak of the bytes it actually reads; `packed_4B_equivalent` is what the packed 4-byte stream would have "
+                            "to sustain for this launch time, `packed_stream_kernel` the packed kernel itself measured in this run")
+        roofline["packed_4B_equivalent"] = {"algorithmic_bytes_per_launch": packed_spmv_bytes,
+                                            "equivalent_gbs": packed_spmv_bytes / (spmv_avg_ms / 1e3) / 1e9,
+                                            "frac": packed_spmv_bytes / (spmv_avg_ms / 1e3) / 1e9 / peak}
     prof = os.path.join(ROOT, "profiles", "spmv_traffic.json")
     if os.path.exists(prof):
         try:
             tr = json.load(open(prof))
-            roofline["traffic"] = tr.get("dram_bytes_per_launch_pk" if packed else "dram_bytes_per_launch")
-            roofline["traffic_source"] = tr.get("pk_source" if packed else "source")
+            key = "sc" if segments else ("pk" if packed else "")
+            roofline["traffic"] = tr.get("dram_bytes_per_launch_" + key if key else "dram_bytes_per_launch")
+            roofline["traffic_source"] = tr.get(key + "_source" if key else "source")
         except Exception:
             pass
+
+    # ---- the packed 4-byte kernel itself (k_spmv_sell_pk, the HBM-bound form of round 1 / VERDICT item 4), same handle,
+    #      same warm-up and step count, segment descriptors switched off
+    if segments:
+        try:
+            capi.set_option("spmv.segments", 0)
+            P = timed_steps(args.warmup, args.steps, False)
+            p_ms = P["spmv"][0] / max(P["spmv"][1], 1)
+            roofline["packed_stream_kernel"] = {
+                "kernel": "k_spmv_sell_pk<EPI_NONE,exact,dot> (dictionary-packed 4-byte stream, 15 words in flight, batched tail, L2 prefetch)",
+                "avg_launch_ms": p_ms, "algorithmic_bytes_per_launch": packed_spmv_bytes,
+                "achieved": packed_spmv_bytes / (p_ms / 1e3) / 1e9, "frac": packed_spmv_bytes / (p_ms / 1e3) / 1e9 / peak,
+                "iterations_per_s": args.steps * iters / (P["ms"] / 1e3),
+                "traffic": None, "traffic_source": None}
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", "spmv_traffic.json")))
+                roofline["packed_stream_kernel"]["traffic"] = tr.get("dram_bytes_per_launch_pk")
+                roofline["packed_stream_kernel"]["traffic_source"] = tr.get("pk_source")
+            except Exception:
+                pass
+            assert abs(P["resid"] - resid) <= 1e-12 * abs(resid), (P["resid"], resid)     # same bits, same residual
+        except Exception as exc:
+            roofline["packed_stream_kernel"] = {"error": repr(exc)}
+        finally:
+            capi.set_option("spmv.segments", 1)
 
     # ---- the plain products of the path (BASELINE metric: "SpMV HBM GB/s"): y = A x (operator*, spmat.h:1712-1724)
     #      and y = A^T x (transp_mul, spmat.h:1748-1760; its operator is built on first use), hash input vector,
@@ -451,7 +504,7 @@ def run_ours(args):
     solvers = None
     if not args.no_solvers:
         try:
-            solvers = other_solvers(capi, A, x, b, n, nnz, entry_bytes, peak)
+            solvers = other_solvers(capi, A, x, b, n, nnz, stream_bytes / max(nnz, 1), peak)
         except Exception as exc:      # the headline line must survive a failure of the side measurement
             solvers = {"error": repr(exc)}
 
@@ -963,13 +1016,26 @@ def run_ours_dist(args, rank, world, local, dist):
     passes = 12.0 if capi.get_option("pcg.defer_x", 1.0) != 0.0 else 13.0
     if passes == 12.0 and fmt.get("diag_index"):
         passes -= 7.0 / 8.0                       # the update kernel reads d as one byte per row
-    spmv_bytes = (entry_bytes * info["nnz"] + 4.0 * (no + 1) + 16.0 * no) * frac_int
+    packed_spmv_bytes = (entry_bytes * info["nnz"] + 4.0 * (no + 1) + 16.0 * no) * frac_int
+    seg = A.segment_stream() if (fmt.get("segments") and capi.get_option("spmv.segments", 1.0) != 0.0) else None
+    if seg and seg["segment_entries"] > 0:
+        # interior rows: segment descriptors (0.5 B per stored entry) + packed words for the rest; boundary rows: 12 B
+        int_stream = 0.5 * seg["segment_entries"] + 4.0 * (seg["interior_padded_entries"] - seg["segment_entries"])
+        spmv_bytes = int_stream + (4.0 * (no + 1) + 16.0 * no) * frac_int
+        stream_all = int_stream + 12.0 * info["nnz"] * (1.0 - frac_int)
+        kname = "k_spmv_sell_sc"
+    else:
+        seg = None
+        spmv_bytes = packed_spmv_bytes
+        stream_all = entry_bytes * info["nnz"]
+        kname = "k_spmv_sell_pk" if packed else "k_spmv_sell"
     spmv_avg_ms = t_int / max(c_int, 1)
     achieved = spmv_bytes / (spmv_avg_ms / 1e3) / 1e9
-    iter_bytes = entry_bytes * info["nnz"] + 4.0 * (no + 1) + passes * 8.0 * no
-    roofline = {"bound": "hbm", "kernel": ("k_spmv_sell_pk" if packed else "k_spmv_sell") +
-                "<EPI_NONE,exact,dot> on the interior rows of rank 0's partition",
-                "bytes_per_stored_entry": entry_bytes,
+    iter_bytes = stream_all + 4.0 * (no + 1) + passes * 8.0 * no
+    roofline = {"bound": "hbm", "kernel": kname + "<EPI_NONE,exact,dot> on the interior rows of rank 0's partition",
+                "bytes_per_stored_entry": stream_all / max(info["nnz"], 1),
+                "packed_4B_equivalent": {"algorithmic_bytes_per_launch": packed_spmv_bytes,
+                                         "frac": packed_spmv_bytes / (t_int / max(c_int, 1) / 1e3) / 1e9 / peak},
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "traffic": None, "algorithmic_bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_avg_ms,
                 "launches": c_int,

@@ -97,6 +97,7 @@ SIGNATURES = {
     "drops_b200_matrix_set_chebyshev": (_i, [_vp, _i, _d, _i, _d]),
     "drops_b200_chebyshev_lambda_max": (_i, [_vp, _i, _dpp]),
     "drops_b200_matrix_line_segments": (_i, [_vp, C.POINTER(C.c_size_t)]),
+    "drops_b200_matrix_segment_stream": (_i, [_vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "drops_b200_matrix_set_diag_pc": (_i, [_vp, C.c_void_p]),
     "drops_b200_diagpc_apply": (_i, [_vp, _vp, _vp]),
     "drops_b200_matrix_bbt_diag": (_i, [_vp, _dp]),
@@ -142,6 +143,7 @@ SIGNATURES = {
     "drops_b200_dist_spmv_dev": (_i, [_i, _vpp, _vpp, _vpp]),
     "drops_b200_dist_dot": (_i, [_i, _vpp, _vpp, _vpp, _dpp]),
     "drops_b200_dist_pcg_dev": (_i, [_i, _vpp, _vpp, _vpp, _i, _d, _ip, _dpp, _i, _vp, _i]),
+    "drops_b200_dist_matrix_segment_stream": (_i, [_vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "drops_b200_dist_gmres_dev": (_i, [_i, _vpp, _vpp, _vpp, _i, _d, _i, _ip, _dpp, _i, _i]),
     "drops_b200_dist_minres_dev": (_i, [_i, _vpp, _vpp, _vpp, _i, _i, _d, _ip, _dpp, _i]),
     "drops_b200_brick_slab_generate": (_i, [_i, _i, _i, _d, _i, _i, _vpp]),
@@ -405,8 +407,10 @@ class Matrix:
         check(lib().drops_b200_matrix_layout(self.h, C.byref(bo), C.byref(ro)))
         ls = C.c_size_t()
         check(lib().drops_b200_matrix_line_segments(self.h, C.byref(ls)))
+        ss, se = C.c_size_t(), C.c_size_t()
+        check(lib().drops_b200_matrix_segment_stream(self.h, C.byref(ss), C.byref(se)))
         return {"block_ordered": bool(bo.value), "row_ordered_stream": bool(ro.value), "row_ordered_kind": ro.value,
-                "line_segments": ls.value}
+                "line_segments": ls.value, "segment_slices": ss.value, "segment_entries": se.value}
 
     def diag_index(self):
         """Length of the diagonal's value list when PCG reads the Jacobi diagonal as one byte per row (0: fp64 vector)."""
@@ -861,7 +865,12 @@ class DistMatrix:
         check(lib().drops_b200_dist_matrix_format(self.h, C.byref(pk), C.byref(nd)))
         return {"interior_packed": bool(pk.value & 1), "six_byte": bool(pk.value & 2), "row_ordered": bool(pk.value & 4),
                 "block_ordered": bool(pk.value & 8), "p2p": bool(pk.value & 16), "p2p_fault": bool(pk.value & 32), "p2p_reduce": bool(pk.value & 64),
-                "diag_index": bool(pk.value & 128), "n_distinct": nd.value}
+                "diag_index": bool(pk.value & 128), "segments": bool(pk.value & 256), "n_distinct": nd.value}
+
+    def segment_stream(self):
+        a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        check(lib().drops_b200_dist_matrix_segment_stream(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"segment_slices": a.value, "segment_entries": b.value, "interior_padded_entries": c.value}
 
     def diag(self):
         d = np.zeros(max(self.info()["n_owned"], 1))

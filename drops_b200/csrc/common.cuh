@@ -297,6 +297,7 @@ struct drops_b200_vector_s {
 namespace db200 {
 
 // Sliced-ELL (C = 32, sigma-sorted) operator + the CSR it was built from.
+constexpr int kScMaxWidth = 80;      // widest slice the segment kernel stages in shared memory (P2 brick: 65)
 constexpr int kDictConst = 48;       // dictionary entries (values + the padding slot) a kernel parameter block carries
 
 struct SellOp {
@@ -331,6 +332,13 @@ struct SellOp {
     uint16_t* vidx = nullptr;        // instead of pk when the bits do not fit one word: 16-bit dictionary index beside col (6 B / entry)
     uint8_t* pk_nopad = nullptr;     // per slice: 1 = no padding word in the slice (the kernel then skips the selects)
     uint32_t* pkp = nullptr;         // padded entries: (dict index << cbits) | position of the column
+    // Segment descriptors of the row-ordered twin ("sell.segments"): in a slice whose 32 rows are one line segment
+    // (reorder.cu) entry j of all lanes holds the same dictionary index and columns that are at most two runs of
+    // consecutive positions -- (d0, d1, brk, idx): lane l reads position (l < brk ? d0 : d1) + l.  Such a slice is
+    // described by ONE 16-byte record per entry instead of 32 words: scd[(slice_ptr[s] >> 5) + j], sc[s] = 1.
+    uint4* scd = nullptr;            // padded / 32 records (only those of flagged slices are meaningful)
+    uint8_t* sc = nullptr;           // per slice: 1 = described by scd
+    size_t sc_slices = 0, sc_entries = 0;    // flagged slices and the stored entries they cover
     int32_t* colp = nullptr;         // row-ordered twin of col for operators WITHOUT a packed stream (12-byte stream): position of the column, -1 = padding
     size_t npos = 0;
 };
@@ -413,4 +421,6 @@ int build_value_dictionary(SellOp& S, size_t* bytes);
 int build_row_ordered_columns(SellOp& S, size_t* bytes);
 // row-ordered twin of S.pk under a caller-supplied numbering iperm[column] = position (< npos)
 int pack_reorder(SellOp& S, const int32_t* iperm, size_t npos);
+// segment descriptors of the row-ordered twin (SellOp::scd) where most slices are line segments
+int build_segment_descriptors(SellOp& S, size_t* bytes);
 }  // namespace db200

@@ -1907,6 +1907,16 @@ int drops_b200_dist_matrix_info(drops_b200_dist_matrix_t A, size_t* n_owned, siz
     return 0;
 }
 
+int drops_b200_dist_matrix_segment_stream(drops_b200_dist_matrix_t A, size_t* n_slices, size_t* n_entries, size_t* padded_entries)
+{
+    DB_ARG(A != nullptr, "null matrix");
+    const bool on = A->sell_int.scd != nullptr && A->npos > 0;
+    if (n_slices) *n_slices = on ? A->sell_int.sc_slices : 0;
+    if (n_entries) *n_entries = on ? A->sell_int.sc_entries : 0;
+    if (padded_entries) *padded_entries = A->sell_int.padded;
+    return 0;
+}
+
 int drops_b200_dist_matrix_format(drops_b200_dist_matrix_t A, int* interior_packed, int* n_distinct)
 {
     DB_ARG(A != nullptr, "null matrix");
@@ -1928,6 +1938,8 @@ int drops_b200_dist_matrix_format(drops_b200_dist_matrix_t A, int* interior_pack
     }
     if (interior_packed && A->diag_ro_idx != nullptr && A->diag_ro_count > 0 && opt("pcg.diag_index", 1.0) != 0.0)
         *interior_packed |= 128;                     // the update kernel reads the Jacobi diagonal as a byte index
+    if (interior_packed && A->sell_int.scd != nullptr && A->npos > 0 && opt("spmv.segments", 1.0) != 0.0)
+        *interior_packed |= 256;                     // interior rows run from segment descriptors (SellOp::scd)
     if (n_distinct) *n_distinct = A->sell_int.ndict;
     return 0;
 }

@@ -343,6 +343,7 @@ void free_sell(SellOp& s)
     dev_free(s.slice_ptr); dev_free(s.col); dev_free(s.val); dev_free(s.perm);
     dev_free(s.colp);
     dev_free(s.pk); dev_free(s.dict); dev_free(s.pkp); dev_free(s.vidx); dev_free(s.pk_nopad);
+    dev_free(s.scd); dev_free(s.sc);
     s = SellOp();
 }
 
@@ -586,6 +587,7 @@ int build_value_dictionary(SellOp& S, size_t* bytes)
     cudaStream_t st = ctx().stream;
     dev_free(S.pk); dev_free(S.dict); dev_free(S.pkp); dev_free(S.vidx); dev_free(S.pk_nopad);
     S.pk_nopad = nullptr; S.pk = nullptr; S.dict = nullptr; S.pkp = nullptr; S.vidx = nullptr; S.ndict = 0; S.ndict_host = 0; S.cbits = 0;
+    dev_free(S.scd); S.scd = nullptr; dev_free(S.sc); S.sc = nullptr; S.sc_slices = S.sc_entries = 0;
     if (S.colp == nullptr) S.npos = 0;
     if (S.padded == 0 || S.col == nullptr || S.val == nullptr || opt("sell.valdict", 1.0) == 0.0) return 0;
     // columns and, for the row-ordered twin, positions (32 * nslices >= rows) share the low bits
@@ -684,6 +686,7 @@ int build_value_dictionary(SellOp& S, size_t* bytes)
             dev_free(iperm);
             if (status == 0) { S.npos = (size_t)npos; if (bytes) *bytes += S.padded * 4; }
             else { dev_free(S.pkp); S.pkp = nullptr; }
+            if (status == 0) status = build_segment_descriptors(S, bytes);
         }
         if (status != 0) {
             dev_free(S.pk); dev_free(S.dict); dev_free(S.vidx); dev_free(S.pk_nopad);
@@ -694,11 +697,84 @@ int build_value_dictionary(SellOp& S, size_t* bytes)
     return status;
 }
 
+// One warp per slice of the row-ordered twin: is every entry-row (a) one dictionary index on all lanes and (b) at most
+// two runs of consecutive positions?  Then the slice is flagged and gets its descriptors (SellOp::scd).
+__global__ void __launch_bounds__(256)
+k_sc_build(long long nslices, const int64_t* __restrict__ slice_ptr, const uint32_t* __restrict__ pkp,
+           const uint8_t* __restrict__ nopad, int cbits, uint4* __restrict__ scd, uint8_t* __restrict__ sc,
+           unsigned long long* __restrict__ counts)
+{
+    const int lane = threadIdx.x & 31;
+    const long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= nslices) return;
+    const int64_t base = slice_ptr[s];
+    const int width = (int)((slice_ptr[s + 1] - base) >> 5);
+    bool ok = width > 0 && width <= kScMaxWidth && nopad != nullptr && nopad[s] != 0;
+    const uint32_t cmask = (1u << cbits) - 1u;
+    for (int j = 0; j < width && ok; ++j) {
+        const uint32_t w = pkp[base + (int64_t)j * 32 + lane];
+        const uint32_t idx = w >> cbits;
+        const int d = (int)(w & cmask) - lane;
+        const uint32_t idx0 = __shfl_sync(0xffffffffu, idx, 0);
+        const int d0 = __shfl_sync(0xffffffffu, d, 0);
+        const unsigned m0 = __ballot_sync(0xffffffffu, d == d0);
+        const int brk = __popc(m0);
+        bool good = __all_sync(0xffffffffu, idx == idx0) && (brk == 32 || m0 == ((1u << brk) - 1u));
+        int d1 = d0;
+        if (good && brk < 32) {
+            d1 = __shfl_sync(0xffffffffu, d, brk);
+            const unsigned m1 = __ballot_sync(0xffffffffu, d == d1);
+            good = (m0 | m1) == 0xffffffffu;
+        }
+        // positions are >= 0 and lane < 32: d0, d1 > -32; they are stored as signed 32-bit values
+        if (good) { if (lane == 0) scd[(base >> 5) + j] = make_uint4((unsigned)d0, (unsigned)d1, (unsigned)brk, idx0); }
+        else ok = false;
+    }
+    if (lane == 0) {
+        sc[s] = ok ? 1 : 0;
+        if (ok) { atomicAdd(counts, 1ull); atomicAdd(counts + 1, (unsigned long long)width * 32ull); }
+    }
+}
+
+// Segment descriptors of the row-ordered twin (SellOp::scd): operators whose dictionary rides in the kernel's parameter
+// block ("sell.segments", default on).  Costs one pass over pkp; 16 bytes per 32 stored entries.
+int build_segment_descriptors(SellOp& S, size_t* bytes)
+{
+    dev_free(S.scd); S.scd = nullptr; dev_free(S.sc); S.sc = nullptr; S.sc_slices = S.sc_entries = 0;
+    if (S.pkp == nullptr || S.pk_nopad == nullptr || S.nslices == 0 || S.ndict_host == 0 || opt("sell.segments", 1.0) == 0.0) return 0;
+    cudaStream_t st = ctx().stream;
+    unsigned long long* d_counts = nullptr;
+    DB_CHECK(dev_alloc(&d_counts, 2));
+    int status = dev_alloc(&S.scd, S.padded / 32 + 1);
+    if (status == 0) status = dev_alloc(&S.sc, S.nslices);
+    if (status == 0) {
+        cudaError_t e = cudaMemsetAsync(d_counts, 0, 2 * sizeof(unsigned long long), st);
+        k_sc_build<<<blocks_for((long long)S.nslices * 32, 256), 256, 0, st>>>((long long)S.nslices, S.slice_ptr, S.pkp, S.pk_nopad,
+                                                                              S.cbits, S.scd, S.sc, d_counts);
+        count_launch();
+        if (e == cudaSuccess) e = cudaGetLastError();
+        unsigned long long h[2] = {0, 0};
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_counts, sizeof h, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) status = cuda_fail(e, "segment descriptors", __FILE__, __LINE__);
+        S.sc_slices = (size_t)h[0]; S.sc_entries = (size_t)h[1];
+    }
+    dev_free(d_counts);
+    // not worth a second stream for a handful of slices
+    if (status != 0 || S.sc_entries * 4 < S.padded) {
+        dev_free(S.scd); S.scd = nullptr; dev_free(S.sc); S.sc = nullptr; S.sc_slices = S.sc_entries = 0;
+        return status;
+    }
+    if (bytes) *bytes += (S.padded / 32 + 1) * 16 + S.nslices;
+    return 0;
+}
+
 // Row-ordered twin of S.pk for a caller-supplied numbering: iperm[column] = position (dist.cu: the
 // positions of a partition run over its interior and its boundary operator).
 int pack_reorder(SellOp& S, const int32_t* iperm, size_t npos)
 {
     dev_free(S.pkp); S.pkp = nullptr; S.npos = 0;
+    dev_free(S.scd); S.scd = nullptr; dev_free(S.sc); S.sc = nullptr; S.sc_slices = S.sc_entries = 0;
     if (S.pk == nullptr || S.padded == 0 || npos > ((size_t)1 << S.cbits)) return 0;
     cudaStream_t st = ctx().stream;
     DB_CHECK(dev_alloc(&S.pkp, S.padded));
@@ -707,7 +783,7 @@ int pack_reorder(SellOp& S, const int32_t* iperm, size_t npos)
     count_launch();
     DB_CUDA(cudaGetLastError());
     S.npos = npos;
-    return 0;
+    return build_segment_descriptors(S, nullptr);
 }
 
 // Row-ordered twin of S.col for a square operator over all its rows that has NO packed stream (more than 65 535
@@ -1128,6 +1204,14 @@ int drops_b200_matrix_line_segments(drops_b200_matrix_t M, size_t* n_segments)
 {
     DB_ARG(M != nullptr && n_segments != nullptr, "null argument");
     *n_segments = M->block_ordered ? M->line_segments : 0;
+    return 0;
+}
+
+int drops_b200_matrix_segment_stream(drops_b200_matrix_t M, size_t* n_slices, size_t* n_entries)
+{
+    DB_ARG(M != nullptr, "null matrix");
+    if (n_slices) *n_slices = M->sell.scd != nullptr ? M->sell.sc_slices : 0;
+    if (n_entries) *n_entries = M->sell.scd != nullptr ? M->sell.sc_entries : 0;
     return 0;
 }
 

@@ -34,7 +34,11 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
                               A.pk != nullptr && A.ndict_host > 0 && A.ndict_host == A.ndict &&
                               A.ndict <= kPkDictSmem && opt("spmv.pkdict", 0.0) == 0.0 &&
                               opt("spmv.pk_cdict", 1.0) != 0.0 && opt("spmv.pk_cdict_dot", 1.0) != 0.0;
-    int threads = dot_geometry ? (int)opt("spmv.pk_dot_threads", 384) : (int)opt("spmv.pk_threads", 512);
+    // segment descriptors: the row-ordered twin of an operator that is mostly line segments ("spmv.segments")
+    const bool use_sc = a.row_ordered && A.scd != nullptr && A.sc != nullptr && opt("spmv.segments", 1.0) != 0.0 &&
+                        A.pk != nullptr && A.ndict_host > 0 && A.ndict_host == A.ndict && A.ndict <= kPkDictSmem &&
+                        opt("spmv.pkdict", 0.0) == 0.0 && opt("spmv.pk_cdict", 1.0) != 0.0;
+    int threads = use_sc ? (int)opt("spmv.sc_threads", 512) : dot_geometry ? (int)opt("spmv.pk_dot_threads", 384) : (int)opt("spmv.pk_threads", 512);
     if (threads < 32) threads = 32;
     if (threads > 1024) threads = 1024;
     threads &= ~31;
@@ -43,7 +47,7 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
     long long grid;
     if (per_sm > 0.0) grid = (long long)(per_sm * c.sm_count + 0.5);
     else {
-        long long spc = dot_geometry ? (long long)opt("spmv.pk_dot_slices_per_cta", 192.0) : (long long)opt("spmv.pk_slices_per_cta", 128.0);
+        long long spc = use_sc ? (long long)opt("spmv.sc_slices_per_cta", 256.0) : dot_geometry ? (long long)opt("spmv.pk_dot_slices_per_cta", 192.0) : (long long)opt("spmv.pk_slices_per_cta", 128.0);
         if (spc < 1) spc = 1;
         grid = ((long long)A.nslices + spc - 1) / spc;
     }
@@ -60,6 +64,7 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
     cudaStream_t st = a.stream ? a.stream : c.stream;
     PkView v{A.slice_ptr, A.col, A.pk != nullptr ? nullptr : A.vidx, a.row_ordered ? A.pkp : A.pk, A.dict, a.row_ordered ? nullptr : A.perm, (long long)A.nslices,
              A.ndict, A.cbits, opt("spmv.pk_nopad", 1.0) != 0.0 ? A.pk_nopad : nullptr,
+             use_sc ? A.scd : nullptr, use_sc ? A.sc : nullptr,
              A.ndict_host == A.ndict ? A.ndict_host : 0, {}};
     if (v.cdict_n > 0) std::memcpy(v.cdict, A.dict_host, sizeof(double) * ((size_t)A.ndict_host + 1));
     EpiArgs e = make_epi(a);

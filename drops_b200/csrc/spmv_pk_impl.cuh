@@ -22,6 +22,8 @@ struct PkView {
     int ndict;
     int cbits;
     const uint8_t* nopad;       // per slice: 1 = no padding word (nullptr: unknown, keep the selects)
+    const uint4* scd;           // segment descriptors of the row-ordered twin (SellOp::scd), nullptr: none
+    const uint8_t* sc;          // per slice: 1 = run from scd
     int cdict_n;                // > 0: cdict holds the dictionary (values + padding slot)
     double cdict[kDictConst];   // CD kernels: the dictionary inside the parameter block (constant bank)
 };
@@ -205,6 +207,144 @@ k_spmv_sell_pk(const __grid_constant__ PkView A, const double* __restrict__ x, d
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Segment kernel ("spmv.segments"): the row-ordered twin of an operator whose slices are mostly line segments.
+// A flagged slice is described by one 16-byte record per entry-row (SellOp::scd) instead of 32 words: the warp
+// copies the records of its slice into shared memory with cp.async (the copy of the NEXT slice travels while the
+// epilogue of this one runs), every lane then forms its column as (lane < brk ? d0 : d1) + lane -- 32 consecutive
+// positions, at most two runs -- and all lanes share the dictionary index.  Same products, same left-to-right order
+// as the packed row sum: bit-identical.  Slices that are not flagged (chain tails, boundary rows) run the packed row
+// sum in the same kernel.  The stream of a flagged slice is 0.5 instead of 4 bytes per stored entry.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sc_issue(const PkView& A, uint32_t sd_addr, int64_t base, int width, int lane)
+{
+    const uint4* src = A.scd + (base >> 5);
+    for (int j = lane; j < width; j += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sd_addr + (uint32_t)j * 16u), "l"(src + j) : "memory");
+}
+
+template <bool EXACT, int UB>
+__device__ __forceinline__ double sc_batch(const PkView& A, const uint4* __restrict__ sd, int j, double sum, int lane,
+                                           const double* __restrict__ x)
+{
+    double xv[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+        const uint4 d = sd[j + u];                                       // one broadcast 16-byte read
+        const int c = (lane < (int)d.z ? (int)d.x : (int)d.y) + lane;
+        xv[u] = __ldg(x + c);
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+        // the index is read again: a register per entry is dearer than an LDS (packing four indices into a register was
+        // measured too: more spills, slower)
+        const double v = A.cdict[sd[j + u].w];
+        sum = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv[u])) : fma(v, xv[u], sum);
+    }
+    return sum;
+}
+
+template <bool EXACT, int U>
+__device__ __forceinline__ double sc_row_sum(const PkView& A, const uint4* __restrict__ sd, int width, int lane,
+                                             const double* __restrict__ x)
+{
+    double sum = 0.0;
+    int j = 0;
+    for (; j + U <= width; j += U) sum = sc_batch<EXACT, U>(A, sd, j, sum, lane, x);
+    if (U > 8 && j + 8 <= width) { sum = sc_batch<EXACT, 8>(A, sd, j, sum, lane, x); j += 8; }
+    if (U > 4 && j + 4 <= width) { sum = sc_batch<EXACT, 4>(A, sd, j, sum, lane, x); j += 4; }
+    if (U > 2 && j + 2 <= width) { sum = sc_batch<EXACT, 2>(A, sd, j, sum, lane, x); j += 2; }
+    for (; j < width; ++j) sum = sc_batch<EXACT, 1>(A, sd, j, sum, lane, x);
+    return sum;
+}
+
+template <int EPI, bool EXACT, int DOT, int U, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+k_spmv_sell_sc(const __grid_constant__ PkView A, const double* __restrict__ x, double* __restrict__ y, EpiArgs e)
+{
+    if (e.done != nullptr && *e.done != 0) return;
+    __shared__ dd red_smem[DOT == 1 ? 32 : 1];
+    __shared__ dd acc_smem[DOT != 0 ? MAXT : 1];
+    __shared__ uint4 sdesc[(MAXT / 32) * kScMaxWidth];
+    if (DOT != 0) acc_smem[threadIdx.x] = dd_zero();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int s_begin = (int)(A.nslices * (long long)blockIdx.x / gridDim.x);
+    const int s_end   = (int)(A.nslices * (long long)(blockIdx.x + 1) / gridDim.x);
+    const double beta = (EPI == EPI_AXMBY) ? (e.beta != nullptr ? *e.beta : e.beta_val) : 0.0;
+    const uint4* sd = sdesc + warp * kScMaxWidth;
+    const uint32_t sd_addr = (uint32_t)__cvta_generic_to_shared(sd);
+
+    // extents and flag of the warp's next slice are read while the current one is summed
+    int64_t base = 0;
+    int width = 0;
+    bool seg = false;
+    if (s_begin + warp < s_end) {
+        const int s0 = s_begin + warp;
+        base = A.slice_ptr[s0];
+        width = (int)((A.slice_ptr[s0 + 1] - base) >> 5);
+        seg = A.sc[s0] != 0;
+        if (seg) sc_issue(A, sd_addr, base, width, lane);
+    }
+    for (int s = s_begin + warp; s < s_end; s += nwarp) {
+        int64_t nbase = 0;
+        int nwidth = 0;
+        bool nseg = false;
+        const int s1 = s + nwarp;
+        if (s1 < s_end) {
+            nbase = A.slice_ptr[s1];
+            nwidth = (int)((A.slice_ptr[s1 + 1] - nbase) >> 5);
+            nseg = A.sc[s1] != 0;
+        }
+        const int row = s * 32 + lane;                        // row-ordered twin: the position IS the row
+        double av = 0.0;
+        if (EPI != EPI_NONE) av = __ldg(e.aux + row);
+        double sum;
+        if (seg) {
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            sum = sc_row_sum<EXACT, U>(A, sd, width, lane, x);
+            __syncwarp();                                     // every lane is done with the records
+        } else {
+            sum = pk_row_sum<EXACT, U, false, false, true, true>(A, base, width, lane, x);
+        }
+        if (nseg) sc_issue(A, sd_addr, nbase, nwidth, lane);  // travels during the epilogue
+        const double out = apply_epilogue<EPI>(sum, av, e, beta);
+        y[row] = out;
+        if (DOT) acc_smem[threadIdx.x] = dd_add_prod(acc_smem[threadIdx.x], out, __ldg(e.dotv + row));
+        base = nbase; width = nwidth; seg = nseg;
+    }
+    dd acc[1] = {DOT != 0 ? acc_smem[threadIdx.x] : dd_zero()};
+    if (DOT == 1) {
+        if (grid_reduce_dd<1>(acc, red_smem, e.partials, e.ticket)) {
+            if (threadIdx.x == 0) store_dot(e, acc[0]);
+        }
+    }
+    if (DOT == 2) {
+        const dd w = warp_reduce_dd(acc[0]);
+        if (lane == 0) e.partials[(size_t)blockIdx.x * nwarp + warp] = w;
+    }
+}
+
+template <int EPI, bool EXACT, int U, int MAXT, int MINB>
+static void launch_sc_d(const PkView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads, cudaStream_t st)
+{
+    if (threads > MAXT) threads = MAXT;
+    if (a.dotv == nullptr) {
+        k_spmv_sell_sc<EPI, EXACT, 0, U, MAXT, MINB><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
+        return;
+    }
+    const long long nwarps = (long long)grid * (threads >> 5);
+    const double mode = opt("spmv.dotmode", 0.0);
+    const bool two_kernels = mode == 2.0 || (mode == 0.0 && grid > (int)kReduceFlat);
+    if (two_kernels && nwarps <= kPartialStride) {
+        k_spmv_sell_sc<EPI, EXACT, 2, U, MAXT, MINB><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
+        sum_warp_partials(nwarps, e, st);
+    } else {
+        k_spmv_sell_sc<EPI, EXACT, 1, U, MAXT, MINB><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
+    }
+}
+
 template <int EPI, bool EXACT, int U, int MAXT, int MINB, bool SMEM, bool V6, bool CD, int LEAN = 0>
 static void launch_pk_d(const PkView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads, cudaStream_t st)
 {
@@ -241,6 +381,12 @@ static bool launch_pk(const PkView& v, const SpmvArgs& a, const EpiArgs& e, int 
         return true;
     }
     if (smem_ok && v.cdict_n > 0 && opt("spmv.pk_cdict", 1.0) != 0.0) {
+        if (v.scd != nullptr && v.sc != nullptr && v.perm == nullptr) {       // row-ordered twin with segment descriptors
+            // measured on C2 (profiles/r02_probe_sc*.json): 12 gathers in flight x 512-thread CTAs x 3 per SM (40 registers)
+            // 1.22 ms; 15 x 384 x 3: 1.26-1.33; 10 x 384 x 4: 1.26; 19 x 384 x 3: 1.34; 8 x 512 x 4: 1.48
+            launch_sc_d<EPI, EXACT, 12, 512, 3>(v, a, e, grid, threads, st);
+            return true;
+        }
         if (EPI == EPI_NONE && EXACT && a.dotv != nullptr && opt("spmv.pk_cdict_dot", 1.0) != 0.0) {
             const int lean = (int)opt("spmv.pk_lean", 2.0);    // 1: batched tail, 2: + L2 prefetch of the warp's next slice
             if (lean == 2) launch_pk_d<EPI_NONE, true, 15, 384, 3, false, false, true, 2>(v, a, e, grid, threads, st);

@@ -137,6 +137,12 @@ DROPS_B200_API int drops_b200_matrix_layout(drops_b200_matrix_t A, int* block_or
  * its lanes gathers 32 consecutive positions of the row-ordered x.  *n_segments = complete segments of A's operator
  * (0: no lines found, or A is not block ordered).  Never changes a result bit of A*x. */
 DROPS_B200_API int drops_b200_matrix_line_segments(drops_b200_matrix_t A, size_t* n_segments);
+/* "sell.segments" (default on): slices of the row-ordered twin whose 32 rows are one line segment hold, entry by entry,
+ * ONE dictionary index and columns that are at most two runs of consecutive positions; they are described by one 16-byte
+ * record per entry-row instead of 32 packed words (0.5 instead of 4 bytes per stored entry) and run by the segment kernel
+ * ("spmv.segments").  *n_slices / *n_entries = such slices and the stored entries they cover (0: none, or too few to
+ * pay).  Same products in the same order: never changes a result bit. */
+DROPS_B200_API int drops_b200_matrix_segment_stream(drops_b200_matrix_t A, size_t* n_slices, size_t* n_entries);
 /* Jacobi diagonal of the row-ordered PCG as one byte per row ("pcg.diag_index"; JACPcCL's diag_, num/precond.h:1162-1177,
  * holds a handful of distinct values on constant-coefficient operators): *n_values = length of the value list the
  * last PCG-Jacobi solve on A built, 0 when the diagonal is read as an fp64 vector.  Never changes a result bit. */
@@ -402,9 +408,14 @@ DROPS_B200_API int drops_b200_dist_matrix_info(drops_b200_dist_matrix_t A, size_
  * iterates in the numbering of the operators' own slices, "dist.reorder"), 8: rows were cut in blocks of the
  * partition's graph, 16: the peer-to-peer halo is set up (the pack kernel stores into the neighbours' ghost
  * buffers over NVLink, "dist.p2p"; otherwise ncclSend/ncclRecv), 32: a peer-to-peer wait timed out, 64: the
- * reduction partials travel peer to peer as well ("dist.p2p_reduce"; otherwise ncclAllGather);
- * n_distinct = size of the interior operator's dictionary. */
+ * reduction partials travel peer to peer as well ("dist.p2p_reduce"; otherwise ncclAllGather), 128: the update kernel of the
+ * partitioned PCG reads the Jacobi diagonal as a byte index, 256: the interior rows run from segment descriptors
+ * (drops_b200_matrix_segment_stream); n_distinct = size of the interior operator's dictionary. */
 DROPS_B200_API int drops_b200_dist_matrix_format(drops_b200_dist_matrix_t A, int* interior_packed, int* n_distinct);
+/* Segment descriptors of the interior-row operator (see drops_b200_matrix_segment_stream); padded_entries = stored
+ * entries of that operator incl. padding. */
+DROPS_B200_API int drops_b200_dist_matrix_segment_stream(drops_b200_dist_matrix_t A, size_t* n_slices, size_t* n_entries,
+                                                         size_t* padded_entries);
 DROPS_B200_API int drops_b200_dist_matrix_diag(drops_b200_dist_matrix_t A, double* diag);
 
 /* Collective operations.  `nparts` partitions driven by this process: 1 with an NCCL communicator

@@ -270,6 +270,50 @@ def test_brick_slabs_match_single_gpu(gpu, fe, N, numbering, world):
     assert np.allclose(hist[:k + 1], ref[4][:k + 1], rtol=1e-6, atol=1e-15)
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_interiors_run_from_segment_descriptors(gpu, world):
+    """z-slabs of a P2 brick with lines of 37-39 same-shape rows: the interior operator of every partition is cut in line
+    segments (kept whole across the interior / boundary split) and runs from segment descriptors; PCG, GMRES and MINRES
+    give the bits of the packed kernel ("spmv.segments" = 0) and the single-GPU iteration counts."""
+    from drops_b200 import partition
+    fe, N, numbering = 2, 40, 1
+    n, nnz = gpu.brick_sizes(fe, N)
+    try:
+        gpu.set_option("sell.block_min_rows", 0)
+        G = gpu.Matrix.brick(fe, N, numbering)
+        comm = gpu.Comm.local(world)
+        slabs, exs, mats = partition.brick_partition_in_process(fe, N, numbering, world, comm)
+        assert all(m.format()["block_ordered"] and m.format()["row_ordered"] and m.format()["segments"] for m in mats)
+        owned = [s.owned() for s in slabs]
+        xstar = gpu.brick_solution_host(fe, N, numbering)
+        b = G.spmv(xstar)
+        bs = [gpu.Vector.from_host(b[o]) for o in owned]
+        ref = G.pcg_jacobi(np.zeros(n), b, 2000, 1e-10, True)
+
+        def run_all():
+            out = []
+            x0 = [gpu.Vector(o.size) for o in owned]
+            out.append(gpu.dist_pcg(mats, x0, bs, 2000, 1e-10, True) + (np.concatenate([v.download() for v in x0]),))
+            x1 = [gpu.Vector(o.size) for o in owned]
+            out.append(gpu.dist_gmres(mats, x1, bs, 10, 30, 1e-30, True) + (np.concatenate([v.download() for v in x1]),))
+            x2 = [gpu.Vector(o.size) for o in owned]
+            out.append(gpu.dist_minres(mats, x2, bs, 40, 1e-30, True) + (np.concatenate([v.download() for v in x2]),))
+            return out
+        seg = run_all()
+        gpu.set_option("spmv.segments", 0)
+        pk = run_all()
+        gpu.set_option("spmv.segments", 1)
+        for a, c in zip(seg, pk):
+            assert a[1] == c[1] and a[2] == c[2] and np.array_equal(a[3], c[3])
+        assert seg[0][0] and abs(seg[0][1] - ref[1]) <= 1
+        x = np.full(n, np.nan)
+        x[np.concatenate(owned)] = seg[0][3]
+        assert rel(x, ref[3]) <= 1e-10
+    finally:
+        gpu.set_option("spmv.segments", 1)
+        gpu.set_option("sell.block_min_rows", 2.0e6)
+
+
 def test_partition_with_empty_rank_and_nccl_world1(gpu):
     g = load_golden("brick_fe1_N6_num0.npz")
     n = int(g["rows"])

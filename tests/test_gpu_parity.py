@@ -516,6 +516,19 @@ def test_line_segments_in_graph_blocks_are_transparent(gpu, cells, lines, tiles,
         assert np.array_equal(B.spmv(xin), y0) and np.array_equal(B.spmv_transpose(xin), yt0)
         s1 = B.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True)
         assert s1[0] and s1[1] == s0[1] and rel(s1[3], s0[3]) <= 1e-12
+        if lines and cells >= 36 and stride >= 2:
+            # segment descriptors ("sell.segments"): most slices of the twin are one dictionary index + two runs of positions
+            # per entry-row; the segment kernel gives the bits of the packed kernel in PCG, GMRES (Jacobi epilogue) and MINRES
+            assert lay["segment_slices"] >= 0.8 * lay["line_segments"] and lay["segment_entries"] >= 0.4 * len(va), lay
+            m1 = B.minres(np.zeros(n), b, 40, 1e-30, True)
+            g1 = B.gmres_jacobi(np.zeros(n), b, 10, 25, 1e-30, True, 1.0, True)
+            gpu.set_option("spmv.segments", 0)
+            s2 = B.pcg_jacobi(np.zeros(n), b, 500, 1e-10, True)
+            m2 = B.minres(np.zeros(n), b, 40, 1e-30, True)
+            g2 = B.gmres_jacobi(np.zeros(n), b, 10, 25, 1e-30, True, 1.0, True)
+            gpu.set_option("spmv.segments", 1)
+            assert s2[1] == s1[1] and s2[2] == s1[2] and np.array_equal(s2[3], s1[3])
+            assert m2[1] == m1[1] and np.array_equal(m2[3], m1[3]) and g2[1] == g1[1] and np.array_equal(g2[3], g1[3])
         gm0 = B0.gmres_jacobi(np.zeros(n), b, 20, 60, 1e-10, True, 1.0, True)
         gm1 = B.gmres_jacobi(np.zeros(n), b, 20, 60, 1e-10, True, 1.0, True)
         assert gm1[1] == gm0[1] and rel(gm1[3], gm0[3]) <= 1e-12        # row-ordered in two different orders
@@ -525,6 +538,7 @@ def test_line_segments_in_graph_blocks_are_transparent(gpu, cells, lines, tiles,
         gpu.set_option("krylov.reorder", 1)
         assert gm2[1] == gm3[1] and np.array_equal(gm2[3], gm3[3])      # caller's order: same bits
     finally:
+        gpu.set_option("spmv.segments", 1)
         gpu.set_option("sell.block_min_rows", 2.0e6)
         gpu.set_option("sell.line_order", 1)
         gpu.set_option("sell.line_stride", 8)
@@ -1147,6 +1161,7 @@ def test_production_defaults_parity_p2_n64(gpu, port):
     assert out2[1] == out[1] and np.array_equal(out2[3], out[3])
     # line segments are the unit of the blocks at this size: 8 DOF classes x ~63^2 lines x 1 complete segment each
     assert lay["line_segments"] >= 6 * 61 ** 2, lay
+    assert lay["segment_entries"] >= 0.4 * len(va), lay     # ... and most of them run from segment descriptors
     # footprint ("sell.release_general"): the 12-byte stream of an operator this large is gone once the packed stream
     # exists -- A: 12 (csr) + 2 x 4 (pk, pkp) bytes per entry, A^T (built by the transp_mul above): 2 x 4, instead of 32 + 32
     nnz = len(va)
