@@ -249,7 +249,8 @@ double opt(const char* key, double dflt);
 struct ScopedTiming {
     TimingSlot* slot = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    explicit ScopedTiming(const char* key);
+    cudaStream_t stream = nullptr;
+    explicit ScopedTiming(const char* key, cudaStream_t st = nullptr);     // st: the stream the timed launches go to (default: the solver stream)
     ~ScopedTiming();
 };
 int timing_flush();

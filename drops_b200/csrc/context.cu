@@ -72,20 +72,21 @@ static cudaEvent_t get_event()
     return e;
 }
 
-ScopedTiming::ScopedTiming(const char* key)
+ScopedTiming::ScopedTiming(const char* key, cudaStream_t st)
 {
     Ctx& c = ctx();
     if (opt("timing", 0.0) == 0.0) return;
     slot = &c.timing[key];
+    stream = st ? st : c.stream;
     e0 = get_event();
     e1 = get_event();
-    cudaEventRecord(e0, c.stream);
+    cudaEventRecord(e0, stream);
 }
 
 ScopedTiming::~ScopedTiming()
 {
     if (!slot) return;
-    cudaEventRecord(e1, ctx().stream);
+    cudaEventRecord(e1, stream);
     slot->pending.emplace_back(e0, e1);
     slot->launches += 1;
 }

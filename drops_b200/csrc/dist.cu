@@ -299,6 +299,16 @@ __global__ void k_dist_scalars(int phase, SolverScalars* S, double* hist, const 
     else pcg_update_finish(S, hist, dd_round(acc[0]), dd_round(acc[1]));
 }
 
+// dot partial of a partition whose boundary rows ran beside the interior rows: boundary + interior, the order of the
+// chained form (store_dot: total = dd_add(total, *dd_in) with total = the boundary rows' sum)
+__global__ void k_combine_dd(dd* out, const dd* bnd, const dd* interior, const int* done)
+{
+    if (done != nullptr && *done != 0) return;
+    dd t = *bnd;
+    if (interior != nullptr) t = dd_add(t, *interior);
+    *out = t;
+}
+
 __global__ void k_zero_dd(dd* p, int n)
 {
     if (threadIdx.x < n) p[threadIdx.x] = dd_zero();
@@ -967,6 +977,47 @@ static int dist_spmv_run(int np, drops_b200_dist_matrix_s* const* P, const PartA
         if (a[p].dotv) { s.dotv = a[p].dotv; s.dd_out = M->n_bnd ? (dd*)M->d_scalars + 32 : gather_slot(M, 1); }
         s.row_ordered = a[p].ro;
         DB_CHECK(spmv_sell(M->sell_int, s));
+    }
+    // "dist.overlap_bnd" (peer path): the boundary rows run on the communication stream, behind the pack-and-push and the
+    // halo wait, BESIDE the interior rows (high-priority stream: their CTAs take the next free slots) instead of after them --
+    // ranks with two faces no longer finish later than ranks with one.  The two dot partials are combined in the order of
+    // the chained form, so the sum keeps its bits.
+    const bool overlap = peer && opt("dist.overlap_bnd", 1.0) != 0.0;
+    if (overlap) {
+        cudaStream_t cs = comm->comm_stream;
+        {
+            ScopedTiming t("halo.wait", cs);
+            for (int p = 0; p < np; ++p) {
+                drops_b200_dist_matrix_s* M = P[p];
+                if (M->n_ghost == 0) continue;
+                k_halo_wait<<<1, std::max(32, (M->world + 31) / 32 * 32), 0, cs>>>(M->world, M->halo_flags, M->d_expect, M->p2p_seq,
+                                                                                 a[p].done, M->p2p_fault);
+                count_launch();
+            }
+            DB_CUDA(cudaGetLastError());
+        }
+        for (int p = 0; p < np; ++p) {
+            drops_b200_dist_matrix_s* M = P[p];
+            if (M->n_bnd == 0) continue;
+            ScopedTiming t("spmv.bnd", cs);
+            SpmvArgs s;
+            s.x = a[p].x; s.y = a[p].y; s.epilogue = a[p].epilogue; s.aux = a[p].aux; s.omega = a[p].omega; s.done = a[p].done;
+            s.beta_val = a[p].beta_val;
+            s.xghost = M->ghost; s.n_owned = a[p].ro ? (long long)M->npos : (long long)M->n_owned;
+            s.stream = cs; s.slot = 2;                                   // (the interior rows reduce in slot 0 at the same time)
+            if (a[p].dotv) { s.dotv = a[p].dotv; s.dd_out = (dd*)M->d_scalars + 33; }
+            DB_CHECK(spmv_sell(a[p].ro ? M->sell_bnd_ro : M->sell_bnd, s));
+        }
+        DB_CUDA(cudaEventRecord(comm->ev_bnd, cs));
+        DB_CUDA(cudaStreamWaitEvent(st, comm->ev_bnd, 0));               // also: my pushes have left
+        for (int p = 0; p < np; ++p) {
+            drops_b200_dist_matrix_s* M = P[p];
+            if (!a[p].dotv || M->n_bnd == 0) continue;
+            k_combine_dd<<<1, 1, 0, st>>>(gather_slot(M, 1), (dd*)M->d_scalars + 33, M->n_int ? (dd*)M->d_scalars + 32 : nullptr, a[p].done);
+            count_launch();
+        }
+        DB_CUDA(cudaGetLastError());
+        return 0;
     }
     if (comm->world > 1) DB_CUDA(cudaStreamWaitEvent(st, comm->ev_halo, 0));     // my sends / pushes have left
     if (peer) {
@@ -1682,6 +1733,7 @@ static int comm_common(drops_b200_comm_s* C)
     DB_CUDA(cudaStreamCreateWithPriority(&C->comm_stream, cudaStreamNonBlocking, prio_hi));
     DB_CUDA(cudaEventCreateWithFlags(&C->ev_pack, cudaEventDisableTiming));
     DB_CUDA(cudaEventCreateWithFlags(&C->ev_halo, cudaEventDisableTiming));
+    DB_CUDA(cudaEventCreateWithFlags(&C->ev_bnd, cudaEventDisableTiming));
     DB_CHECK(dev_alloc(&C->gathered, (size_t)C->world * kMaxQ));
     DB_CUDA(cudaMemset(C->gathered, 0, (size_t)C->world * kMaxQ * sizeof(dd)));
     DB_CHECK(dev_alloc(&C->wide, (size_t)C->world * kWideQ));
@@ -1818,6 +1870,7 @@ int drops_b200_comm_destroy(drops_b200_comm_t C)
     if (C->nccl && nccl().ok) nccl().CommDestroy((ncclComm_t)C->nccl);
     if (C->ev_pack) cudaEventDestroy(C->ev_pack);
     if (C->ev_halo) cudaEventDestroy(C->ev_halo);
+    if (C->ev_bnd) cudaEventDestroy(C->ev_bnd);
     if (C->comm_stream) cudaStreamDestroy(C->comm_stream);
     dev_free(C->gathered); dev_free(C->wide);
     for (void* m : C->ipc_mapped) cudaIpcCloseMemHandle(m);

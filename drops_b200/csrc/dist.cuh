@@ -43,7 +43,7 @@ struct drops_b200_comm_s {
     int rank = 0, world = 1;
     void* nccl = nullptr;                    // ncclComm_t
     cudaStream_t comm_stream = nullptr;
-    cudaEvent_t ev_pack = nullptr, ev_halo = nullptr;
+    cudaEvent_t ev_pack = nullptr, ev_halo = nullptr, ev_bnd = nullptr;
     db200::dd* gathered = nullptr;           // world * kMaxQ reduction partials, rank-major
     db200::dd* wide = nullptr;               // world * kWideQ partials: the i+1 products of a classical Gram-Schmidt column
     std::vector<drops_b200_dist_matrix_s*> parts;   // COMM_LOCAL: registered partitions by rank
