@@ -180,6 +180,28 @@ def cpu_reference_run(cells, iters, fe, numbering, repeats=1, warm=0, budget_s=N
             "spmv_gbs_ref_layout": (16.0 * nnz + 8.0 * (n + 1) + 16.0 * n) / best / 1e9}
 
 
+def numa_local_affinity(local):
+    """Pins this rank's host threads to the CPUs next to its GPU (NVML's affinity mask) before any pinned staging
+    buffer is allocated: first touch then places the buffers in the NUMA node the GPU's PCIe root hangs off, and the
+    eight ranks of a box stop sharing one socket's memory controllers.  Plumbing; a failure changes nothing."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+        if vis and local < len(vis):
+            h = pynvml.nvmlDeviceGetHandleByIndex(int(vis[local])) if vis[local].isdigit() else pynvml.nvmlDeviceGetHandleByUUID(vis[local])
+        else:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def dist_setup(n_gpus):
     """torch.distributed is plumbing only: rank discovery, barrier, max-over-ranks."""
     rank = int(os.environ.get("RANK", "0"))
@@ -187,6 +209,7 @@ def dist_setup(n_gpus):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
+        numa_local_affinity(local)
         import torch
         import torch.distributed as dist_mod
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

@@ -422,6 +422,8 @@ int build_value_dictionary(SellOp& S, size_t* bytes);
 int build_row_ordered_columns(SellOp& S, size_t* bytes);
 // row-ordered twin of S.pk under a caller-supplied numbering iperm[column] = position (< npos)
 int pack_reorder(SellOp& S, const int32_t* iperm, size_t npos);
+// frees col / val of an operator that holds the one-word packed stream ("sell.release_general", large operators)
+void release_general(SellOp& S, size_t* bytes);
 // segment descriptors of the row-ordered twin (SellOp::scd) where most slices are line segments
 int build_segment_descriptors(SellOp& S, size_t* bytes);
 }  // namespace db200

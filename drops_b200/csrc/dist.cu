@@ -652,6 +652,8 @@ static int dist_matrix_build_local(drops_b200_comm_s* comm, drops_b200_exchange_
             free_sell(M->sell_bnd_ro); dev_free(M->ro_perm); M->ro_perm = nullptr;
         }
     }
+    // the interior rows never read ghost columns: once their packed stream exists its 12-byte form is dead weight
+    release_general(M->sell_int, &M->device_bytes);
     cleanup();
 #undef DM_CHECK
 #undef DM_CUDA

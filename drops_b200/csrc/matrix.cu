@@ -830,7 +830,7 @@ int build_row_ordered_columns(SellOp& S, size_t* bytes)
 // stream exists, nothing on the solver path reads the int32 column + fp64 value arrays of the sliced-ELL operator any
 // more (products, solvers and the transposed product all run on pk / pkp); they are 12 of the 16-20 bytes per stored
 // entry the operator holds.  A value update rebuilds them from the CSR copy for the time of the rebuild.
-static void release_general(SellOp& S, size_t* bytes)
+void release_general(SellOp& S, size_t* bytes)
 {
     if (S.pk == nullptr || S.val == nullptr || opt("sell.release_general", 1.0) == 0.0) return;
     if ((double)S.rows < opt("sell.release_min_rows", 2.0e6)) return;
