@@ -507,20 +507,30 @@ def run_ours(args):
         A_main = A
         A = G12
         g_layout = G12.layout()
+        g_padded = float(G12.info()["padded_nnz"])
         G = timed_steps(args.warmup, args.steps, False)
         A = A_main
         G12.close()
         g_spmv_ms = G["spmv"][0] / max(G["spmv"][1], 1)
+        # bytes of the stream this leg reads: fp64 values for every stored entry; columns as 16-byte segment records
+        # (0.5 B per entry) where the slice is a line segment, int32 otherwise
+        g_seg = float(g_layout.get("segment_entries", 0)) if capi.get_option("spmv.segments", 1.0) != 0.0 else 0.0
+        g_stream = 8.0 * g_padded + 0.5 * g_seg + 4.0 * (g_padded - g_seg) if g_seg > 0 else 12.0 * nnz
+        g_spmv_bytes = g_stream + 4.0 * (n + 1) + 16.0 * n
         general = {"iterations_per_s": args.steps * iters / (G["ms"] / 1e3), "spmv_avg_launch_ms": g_spmv_ms,
                    "steps": args.steps, "warmup": args.warmup, "block_ordered": g_layout["block_ordered"],
                    "row_ordered_stream": g_layout["row_ordered_kind"], "line_segments": g_layout["line_segments"],
-                   "spmv_achieved_gbs": survey_spmv_bytes / (g_spmv_ms / 1e3) / 1e9,
-                   "spmv_frac": survey_spmv_bytes / (g_spmv_ms / 1e3) / 1e9 / peak,
-                   "iteration_frac": (12.0 * nnz + 4.0 * (n + 1) + general_passes * 8.0 * n) * args.steps * iters / (G["ms"] / 1e3) / 1e9 / peak,
-                   "traffic_source": "profiles/r02_ncu_spmv_12B.raw.csv",
-                   "note": "sell.valdict = 0: int32 column + fp64 value per entry (what a matrix without a value dictionary runs), graph "
-                           "blocks + line segments + row-ordered PCG as on the packed stream (row_ordered_stream 2 = twin of the int32 "
-                           "columns), same warm-up and step count as the headline"}
+                   "segment_entries": g_seg, "bytes_per_stored_entry": g_stream / max(nnz, 1),
+                   "kernel": "k_spmv_sell_scv<EPI_NONE,exact,dot>" if g_seg > 0 else "k_spmv_sell<EPI_NONE,exact,dot>",
+                   "algorithmic_bytes_per_launch": g_spmv_bytes,
+                   "spmv_achieved_gbs": g_spmv_bytes / (g_spmv_ms / 1e3) / 1e9,
+                   "spmv_frac": g_spmv_bytes / (g_spmv_ms / 1e3) / 1e9 / peak,
+                   "survey_12B_frac": survey_spmv_bytes / (g_spmv_ms / 1e3) / 1e9 / peak,
+                   "iteration_frac": (g_stream + 4.0 * (n + 1) + general_passes * 8.0 * n) * args.steps * iters / (G["ms"] / 1e3) / 1e9 / peak,
+                   "traffic_source": "profiles/r02_ncu_spmv_12B.raw.csv (k_spmv_sell, int32 columns), profiles/r02_ncu_spmv_scv.raw.csv (segment records)",
+                   "note": "sell.valdict = 0: fp64 value per entry (what a matrix without a value dictionary runs), graph blocks + line "
+                           "segments + row-ordered PCG as on the packed stream (row_ordered_stream 2 = twin of the int32 columns); columns of "
+                           "line-segment slices come from 16-byte records (8.5 instead of 12 B per entry); same warm-up and step count as the headline"}
         assert abs(G["resid"] - resid) <= 1e-9 * abs(resid), (G["resid"], resid)     # same system, same 200 iterations
 
     # ---- the other two solvers of the path on the same system (device-resident, fixed work) ---------

@@ -697,10 +697,12 @@ int build_value_dictionary(SellOp& S, size_t* bytes)
     return status;
 }
 
-// One warp per slice of the row-ordered twin: is every entry-row (a) one dictionary index on all lanes and (b) at most
-// two runs of consecutive positions?  Then the slice is flagged and gets its descriptors (SellOp::scd).
+// One warp per slice of the row-ordered twin: is every entry-row (a) one dictionary index on all lanes (packed twin; the
+// twin of the 12-byte stream keeps its values per lane) and (b) at most two runs of consecutive positions?  Then the
+// slice is flagged and gets its descriptors (SellOp::scd).
+template <bool PACKED>
 __global__ void __launch_bounds__(256)
-k_sc_build(long long nslices, const int64_t* __restrict__ slice_ptr, const uint32_t* __restrict__ pkp,
+k_sc_build(long long nslices, const int64_t* __restrict__ slice_ptr, const uint32_t* __restrict__ pkp, const int32_t* __restrict__ colp,
            const uint8_t* __restrict__ nopad, int cbits, uint4* __restrict__ scd, uint8_t* __restrict__ sc,
            unsigned long long* __restrict__ counts)
 {
@@ -709,17 +711,24 @@ k_sc_build(long long nslices, const int64_t* __restrict__ slice_ptr, const uint3
     if (s >= nslices) return;
     const int64_t base = slice_ptr[s];
     const int width = (int)((slice_ptr[s + 1] - base) >> 5);
-    bool ok = width > 0 && width <= kScMaxWidth && nopad != nullptr && nopad[s] != 0;
-    const uint32_t cmask = (1u << cbits) - 1u;
+    bool ok = width > 0 && width <= kScMaxWidth && (!PACKED || (nopad != nullptr && nopad[s] != 0));
+    const uint32_t cmask = PACKED ? (1u << cbits) - 1u : 0u;
     for (int j = 0; j < width && ok; ++j) {
-        const uint32_t w = pkp[base + (int64_t)j * 32 + lane];
-        const uint32_t idx = w >> cbits;
-        const int d = (int)(w & cmask) - lane;
+        uint32_t idx = 0;
+        int pos;
+        if (PACKED) {
+            const uint32_t w = pkp[base + (int64_t)j * 32 + lane];
+            idx = w >> cbits;
+            pos = (int)(w & cmask);
+        } else {
+            pos = colp[base + (int64_t)j * 32 + lane];
+        }
+        const int d = pos - lane;
         const uint32_t idx0 = __shfl_sync(0xffffffffu, idx, 0);
         const int d0 = __shfl_sync(0xffffffffu, d, 0);
         const unsigned m0 = __ballot_sync(0xffffffffu, d == d0);
         const int brk = __popc(m0);
-        bool good = __all_sync(0xffffffffu, idx == idx0) && (brk == 32 || m0 == ((1u << brk) - 1u));
+        bool good = __all_sync(0xffffffffu, idx == idx0 && pos >= 0) && (brk == 32 || m0 == ((1u << brk) - 1u));
         int d1 = d0;
         if (good && brk < 32) {
             d1 = __shfl_sync(0xffffffffu, d, brk);
@@ -736,12 +745,17 @@ k_sc_build(long long nslices, const int64_t* __restrict__ slice_ptr, const uint3
     }
 }
 
-// Segment descriptors of the row-ordered twin (SellOp::scd): operators whose dictionary rides in the kernel's parameter
-// block ("sell.segments", default on).  Costs one pass over pkp; 16 bytes per 32 stored entries.
+// Segment descriptors of the row-ordered twin (SellOp::scd; "sell.segments", default on): of the packed twin when the
+// dictionary rides in the kernel's parameter block, of the int32 twin of the 12-byte stream otherwise (variable
+// coefficients on a structured mesh: the columns are described by 0.5 bytes per entry, the fp64 values stay -- 8.5
+// instead of 12 bytes per entry).  Costs one pass over the twin; 16 bytes per 32 stored entries.
 int build_segment_descriptors(SellOp& S, size_t* bytes)
 {
     dev_free(S.scd); S.scd = nullptr; dev_free(S.sc); S.sc = nullptr; S.sc_slices = S.sc_entries = 0;
-    if (S.pkp == nullptr || S.pk_nopad == nullptr || S.nslices == 0 || S.ndict_host == 0 || opt("sell.segments", 1.0) == 0.0) return 0;
+    if (S.nslices == 0 || opt("sell.segments", 1.0) == 0.0) return 0;
+    const bool packed = S.pkp != nullptr;
+    if (packed && (S.pk_nopad == nullptr || S.ndict_host == 0)) return 0;
+    if (!packed && (S.colp == nullptr || S.vidx != nullptr)) return 0;
     cudaStream_t st = ctx().stream;
     unsigned long long* d_counts = nullptr;
     DB_CHECK(dev_alloc(&d_counts, 2));
@@ -749,8 +763,11 @@ int build_segment_descriptors(SellOp& S, size_t* bytes)
     if (status == 0) status = dev_alloc(&S.sc, S.nslices);
     if (status == 0) {
         cudaError_t e = cudaMemsetAsync(d_counts, 0, 2 * sizeof(unsigned long long), st);
-        k_sc_build<<<blocks_for((long long)S.nslices * 32, 256), 256, 0, st>>>((long long)S.nslices, S.slice_ptr, S.pkp, S.pk_nopad,
-                                                                              S.cbits, S.scd, S.sc, d_counts);
+        const int g = blocks_for((long long)S.nslices * 32, 256);
+        if (packed)
+            k_sc_build<true><<<g, 256, 0, st>>>((long long)S.nslices, S.slice_ptr, S.pkp, nullptr, S.pk_nopad, S.cbits, S.scd, S.sc, d_counts);
+        else
+            k_sc_build<false><<<g, 256, 0, st>>>((long long)S.nslices, S.slice_ptr, nullptr, S.colp, nullptr, 0, S.scd, S.sc, d_counts);
         count_launch();
         if (e == cudaSuccess) e = cudaGetLastError();
         unsigned long long h[2] = {0, 0};
@@ -760,7 +777,7 @@ int build_segment_descriptors(SellOp& S, size_t* bytes)
         S.sc_slices = (size_t)h[0]; S.sc_entries = (size_t)h[1];
     }
     dev_free(d_counts);
-    // not worth a second stream for a handful of slices
+    // not worth a second code path for a handful of slices
     if (status != 0 || S.sc_entries * 4 < S.padded) {
         dev_free(S.scd); S.scd = nullptr; dev_free(S.sc); S.sc = nullptr; S.sc_slices = S.sc_entries = 0;
         return status;
@@ -823,7 +840,7 @@ int build_row_ordered_columns(SellOp& S, size_t* bytes)
     if (status != 0) { dev_free(S.colp); S.colp = nullptr; return status; }
     S.npos = (size_t)npos;
     if (bytes) *bytes += S.padded * 4;
-    return 0;
+    return build_segment_descriptors(S, bytes);
 }
 
 // Footprint ("sell.release_general", operators of at least "sell.release_min_rows" rows): once the one-word packed

@@ -211,6 +211,128 @@ static void launch_sell_v(const SellView& v, const SpmvArgs& a, const EpiArgs& e
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// k_spmv_sell_scv: the row-ordered product on the 12-byte stream of an operator with segment descriptors ("spmv.segments").
+// In a slice that is one line segment the columns of entry-row j are at most two runs of consecutive positions --
+// a 16-byte record (SellOp::scd) instead of 32 int32 columns --, the fp64 values stay per lane: 8.5 instead of 12 bytes
+// per stored entry on the stream that bounds this kernel.  Records are staged per warp in shared memory with cp.async
+// (the copy for the warp's next slice travels during the epilogue).  Unflagged slices run slice_row_sum.  Same
+// products in the same order as k_spmv_sell: bit-identical.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void scv_issue(const SellView& A, uint32_t sd_addr, int64_t base, int width, int lane)
+{
+    const uint4* src = A.scd + (base >> 5);
+    for (int j = lane; j < width; j += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sd_addr + (uint32_t)j * 16u), "l"(src + j) : "memory");
+}
+
+template <bool EXACT, int UB>
+__device__ __forceinline__ double scv_batch(const double* __restrict__ vp, const uint4* __restrict__ sd, int j, double sum, int lane,
+                                            const double* __restrict__ x)
+{
+    double v[UB], xv[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) v[u] = __ldcs(vp + (size_t)(j + u) * 32);
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+        const uint4 d = sd[j + u];
+        const int c = (lane < (int)d.z ? (int)d.x : (int)d.y) + lane;
+        xv[u] = __ldg(x + c);
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) sum = EXACT ? __dadd_rn(sum, __dmul_rn(v[u], xv[u])) : fma(v[u], xv[u], sum);
+    return sum;
+}
+
+template <int EPI, bool EXACT, int DOT, int U, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+k_spmv_sell_scv(SellView A, const double* __restrict__ x, double* __restrict__ y, EpiArgs e)
+{
+    if (e.done != nullptr && *e.done != 0) return;
+    __shared__ dd red_smem[DOT == 1 ? 32 : 1];
+    __shared__ uint4 sdesc[(MAXT / 32) * kScMaxWidth];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int s_begin = (int)(A.nslices * (long long)blockIdx.x / gridDim.x);
+    const int s_end   = (int)(A.nslices * (long long)(blockIdx.x + 1) / gridDim.x);
+    const double beta = (EPI == EPI_AXMBY) ? (e.beta != nullptr ? *e.beta : e.beta_val) : 0.0;
+    const uint4* sd = sdesc + warp * kScMaxWidth;
+    const uint32_t sd_addr = (uint32_t)__cvta_generic_to_shared(sd);
+    dd acc[1] = {dd_zero()};
+    int64_t base = 0;
+    int width = 0;
+    bool seg = false;
+    if (s_begin + warp < s_end) {
+        const int s0 = s_begin + warp;
+        base = A.slice_ptr[s0];
+        width = (int)((A.slice_ptr[s0 + 1] - base) >> 5);
+        seg = A.sc[s0] != 0;
+        if (seg) scv_issue(A, sd_addr, base, width, lane);
+    }
+    for (int s = s_begin + warp; s < s_end; s += nwarp) {
+        int64_t nbase = 0;
+        int nwidth = 0;
+        bool nseg = false;
+        const int s1 = s + nwarp;
+        if (s1 < s_end) {
+            nbase = A.slice_ptr[s1];
+            nwidth = (int)((A.slice_ptr[s1 + 1] - nbase) >> 5);
+            nseg = A.sc[s1] != 0;
+        }
+        const int row = s * 32 + lane;                        // row-ordered twin: the position IS the row
+        double dv = 0.0, av = 0.0;
+        if (DOT) dv = __ldg(e.dotv + row);
+        if (EPI != EPI_NONE) av = __ldg(e.aux + row);
+        double sum = 0.0;
+        if (seg) {
+            const double* vp = A.val + base + lane;
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            int j = 0;
+            for (; j + U <= width; j += U) sum = scv_batch<EXACT, U>(vp, sd, j, sum, lane, x);
+            if (U > 4 && j + 4 <= width) { sum = scv_batch<EXACT, 4>(vp, sd, j, sum, lane, x); j += 4; }
+            if (U > 2 && j + 2 <= width) { sum = scv_batch<EXACT, 2>(vp, sd, j, sum, lane, x); j += 2; }
+            for (; j < width; ++j) sum = scv_batch<EXACT, 1>(vp, sd, j, sum, lane, x);
+            __syncwarp();                                     // every lane is done with the records
+        } else {
+            sum = slice_row_sum<EXACT, U, false>(A, base, width, lane, x, e);
+        }
+        if (nseg) scv_issue(A, sd_addr, nbase, nwidth, lane);
+        const double out = apply_epilogue<EPI>(sum, av, e, beta);
+        y[row] = out;
+        if (DOT) acc[0] = dd_add_prod(acc[0], out, dv);
+        base = nbase; width = nwidth; seg = nseg;
+    }
+    if (DOT == 1) {
+        if (grid_reduce_dd<1>(acc, red_smem, e.partials, e.ticket)) {
+            if (threadIdx.x == 0) store_dot(e, acc[0]);
+        }
+    }
+    if (DOT == 2) {
+        const dd w = warp_reduce_dd(acc[0]);
+        if (lane == 0) e.partials[(size_t)blockIdx.x * nwarp + warp] = w;
+    }
+}
+
+template <int EPI, bool EXACT, int U, int MAXT, int MINB>
+static void launch_scv(const SellView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads, cudaStream_t st)
+{
+    if (threads > MAXT) threads = MAXT;
+    if (a.dotv == nullptr) {
+        k_spmv_sell_scv<EPI, EXACT, 0, U, MAXT, MINB><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
+        return;
+    }
+    const long long nwarps = (long long)grid * (threads >> 5);
+    const double mode = opt("spmv.dotmode", 0.0);
+    const bool two_kernels = mode == 2.0 || (mode == 0.0 && grid > (int)kReduceFlat);
+    if (two_kernels && nwarps <= kPartialStride) {
+        k_spmv_sell_scv<EPI, EXACT, 2, U, MAXT, MINB><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
+        sum_warp_partials(nwarps, e, st);
+    } else {
+        k_spmv_sell_scv<EPI, EXACT, 1, U, MAXT, MINB><<<grid, threads, 0, st>>>(v, a.x, a.y, e);
+    }
+}
+
 // Measured on B200 (profiles/r01_probe_dot.json, r01_sweep1_spmv.jsonl): the plain product is fastest with U4 and <= 40
 // registers (2.96 ms at C2), the product with the fused dot needs the room of U8 / <= 48 registers in 128-thread CTAs
 // (3.12 ms; 3.55 ms when squeezed into 40).  The other unroll x register-cap variants of round 1 are gone.
@@ -220,6 +342,12 @@ static void launch_sell(const SellView& v, const SpmvArgs& a, const EpiArgs& e, 
 {
     if (a.xghost != nullptr) {   // boundary rows of a partition: a thin operator, one variant
         launch_sell_v<EPI, EXACT, 4, 512, 2, true>(v, a, e, grid, threads, st);
+        return;
+    }
+    if (v.scd != nullptr && v.sc != nullptr && v.perm == nullptr) {     // row-ordered twin with segment descriptors
+        // measured on C2 (profiles/r02_probe_scv.json): 8 entries in flight x 256-thread CTAs x 5 per SM 2.54 ms (k_spmv_sell: 3.14);
+        // 10 x 256 x 4: 2.53, 6 x 256 x 6: 2.70; 16-64 slices per CTA and 128-thread CTAs: the same
+        launch_scv<EPI, EXACT, 8, 256, 5>(v, a, e, grid, threads, st);
         return;
     }
     if (a.dotv != nullptr) launch_sell_v<EPI, EXACT, 8, 128, 10>(v, a, e, grid, threads, st);
@@ -254,7 +382,8 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a)
     DB_ARG(!a.row_ordered || A.colp != nullptr, "row-ordered vectors need the operator's row-ordered stream");
     DB_ARG(A.val != nullptr, "the 12-byte stream of this operator was released once its packed stream existed "
                              "(\"sell.release_general\" = 0 keeps it)");
-    int threads = (int)opt("spmv.threads", 128);
+    const bool use_sc = a.row_ordered && a.xghost == nullptr && A.scd != nullptr && A.sc != nullptr && opt("spmv.segments", 1.0) != 0.0;
+    int threads = use_sc ? (int)opt("spmv.scv_threads", 256) : (int)opt("spmv.threads", 128);
     if (threads < 32) threads = 32;
     if (threads > 512) threads = 512;
     threads &= ~31;
@@ -271,7 +400,8 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a)
     else {
         // boundary rows of a partition are a thin operator (0.4 % of the rows at C5): short CTAs, or the
         // launch does not even fill the machine once
-        long long spc = (long long)(a.xghost != nullptr ? opt("spmv.bnd_slices_per_cta", 2.0) : opt("spmv.slices_per_cta", 16.0));
+        long long spc = (long long)(a.xghost != nullptr ? opt("spmv.bnd_slices_per_cta", 2.0)
+                                    : use_sc ? opt("spmv.scv_slices_per_cta", 32.0) : opt("spmv.slices_per_cta", 16.0));
         if (spc < 1) spc = 1;
         grid = ((long long)A.nslices + spc - 1) / spc;
     }
@@ -280,7 +410,8 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a)
     if (grid > kMaxReduceGrid) grid = kMaxReduceGrid;
     if (grid < 1) grid = 1;
     cudaStream_t st = a.stream ? a.stream : c.stream;
-    SellView v{A.slice_ptr, a.row_ordered ? A.colp : A.col, A.val, a.row_ordered ? nullptr : A.perm, (long long)A.nslices};
+    SellView v{A.slice_ptr, a.row_ordered ? A.colp : A.col, A.val, a.row_ordered ? nullptr : A.perm, (long long)A.nslices,
+               use_sc ? A.scd : nullptr, use_sc ? A.sc : nullptr};
     EpiArgs e = make_epi(a);
     if (opt("spmv.exact", 1.0) != 0.0) launch_sell_epi<true>(v, a, e, (int)grid, threads, st);
     else launch_sell_epi<false>(v, a, e, (int)grid, threads, st);

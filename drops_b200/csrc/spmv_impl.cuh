@@ -10,6 +10,8 @@ struct SellView {
     const double* val;
     const int32_t* perm;
     long long nslices;
+    const uint4* scd = nullptr;     // segment descriptors of the row-ordered twin (SellOp::scd), nullptr: none
+    const uint8_t* sc = nullptr;    // per slice: 1 = columns come from scd
 };
 
 struct EpiArgs {

@@ -631,6 +631,43 @@ def test_row_ordered_pcg_on_the_12_byte_stream(gpu, port, block_min_rows, graph)
         gpu.set_option("sell.valdict", 1)
 
 
+def test_segment_descriptors_on_the_12_byte_stream(gpu):
+    """Variable coefficients on a structured mesh: the VALUES differ from row to row, the column structure is still
+    translation invariant.  The twin of the int32 columns gets segment descriptors (0.5 instead of 4 bytes per column,
+    8.5 instead of 12 per entry) and k_spmv_sell_scv gives the bits of k_spmv_sell in PCG, GMRES and MINRES."""
+    cells = 40
+    n, rb, ci, va = gpu.brick_csr_host(2, cells, 1)
+    rng = np.random.default_rng(3)
+    d = 1.0 + 0.3 * rng.random(n)
+    rows = np.repeat(np.arange(n), np.diff(rb.astype(np.int64)))
+    vv = va * d[rows] * d[ci.astype(np.int64)]                # D A D: symmetric positive definite, ~nnz distinct values
+    xs = gpu.brick_solution_host(2, cells, 1)
+    try:
+        gpu.set_option("sell.block_min_rows", 0)
+        G = gpu.Matrix(n, n, rb, ci, vv)
+        lay = G.layout()
+        assert G.value_dictionary()["n_distinct"] == 0 and lay["row_ordered_kind"] == 2 and lay["block_ordered"]
+        assert lay["line_segments"] >= 6 * (cells - 3) ** 2 and lay["segment_entries"] >= 0.4 * len(vv), lay
+        b = G.spmv(xs)
+        seg = (G.pcg_jacobi(np.zeros(n), b, 3000, 1e-10, True), G.gmres_jacobi(np.zeros(n), b, 10, 25, 1e-30, True, 1.0, True),
+               G.minres(np.zeros(n), b, 40, 1e-30, True))
+        gpu.set_option("spmv.segments", 0)
+        gen = (G.pcg_jacobi(np.zeros(n), b, 3000, 1e-10, True), G.gmres_jacobi(np.zeros(n), b, 10, 25, 1e-30, True, 1.0, True),
+               G.minres(np.zeros(n), b, 40, 1e-30, True))
+        gpu.set_option("spmv.segments", 1)
+        for a, c in zip(seg, gen):
+            assert a[1] == c[1] and a[2] == c[2] and np.array_equal(a[3], c[3])
+        assert seg[0][0] and rel(seg[0][3], xs) <= 1e-7
+        # new values on the old pattern keep the descriptors' structure
+        G.update_values(vv * 0.5, 2)
+        assert G.layout()["segment_entries"] == lay["segment_entries"]
+        o2 = G.pcg_jacobi(np.zeros(n), 0.5 * b, 3000, 1e-10, True)
+        assert o2[1] == seg[0][1] and rel(o2[3], seg[0][3]) <= 1e-12
+    finally:
+        gpu.set_option("spmv.segments", 1)
+        gpu.set_option("sell.block_min_rows", 2.0e6)
+
+
 @pytest.mark.parametrize("m,left", [(8, True), (30, True), (30, False), (200, True)])
 def test_gmres_classical_gram_schmidt_option(gpu, port, m, left):
     """"gmres.ortho" = 1: classical Gram-Schmidt as in the reference's distributed ModGMRES (StandardGramSchmidt,
