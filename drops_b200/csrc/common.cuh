@@ -232,6 +232,12 @@ struct Ctx {
     unsigned* tickets = nullptr;        // kPartialSlots * kTicketStride counters
     double* scratch_scalars = nullptr;  // device doubles for standalone dot/norm results
     double* h_scalars = nullptr;        // pinned host mirror
+    // small results the host waits for inside a solver loop (Hessenberg columns, Lanczos scalars): a kernel stores them
+    // into mapped pinned memory and raises a sequence number the host polls -- 2-3 us instead of the ~10 us of a
+    // copy + stream synchronisation ("fetch.poll", fetch_small)
+    double* h_pub = nullptr;            // kPubDoubles payload doubles, then the sequence word
+    double* d_pub = nullptr;            // the same memory, device view
+    unsigned pub_seq = 0;
     int max_grid = 0;
     long long launches = 0;
     unsigned long long options_epoch = 0;   // bumped by every set_option: cached CUDA graphs are keyed on it
@@ -242,6 +248,9 @@ struct Ctx {
 
 Ctx& ctx();
 int require_ctx();
+constexpr int kPubDoubles = 600;
+// hdst[0 .. count) = dsrc[0 .. count) after everything enqueued on the solver stream so far; count doubles
+int fetch_small(const double* dsrc, double* hdst, size_t count);
 
 double opt(const char* key, double dflt);
 

@@ -1,6 +1,9 @@
 // context.cu -- process-wide context, options, timing and error text of libdrops_b200.
 #include "common.cuh"
 
+#include <atomic>
+#include <cstring>
+
 #include <cstdarg>
 #include <cstring>
 #include <mutex>
@@ -91,6 +94,48 @@ ScopedTiming::~ScopedTiming()
     slot->launches += 1;
 }
 
+// payload first, system-wide fence, then the sequence word: the host reads the payload only after it saw the word
+__global__ void k_publish(const double* __restrict__ src, int count, double* __restrict__ pub, unsigned seq)
+{
+    for (int i = threadIdx.x; i < count; i += blockDim.x) pub[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *reinterpret_cast<volatile unsigned*>(pub + kPubDoubles) = seq;
+        __threadfence_system();
+    }
+}
+
+int fetch_small(const double* dsrc, double* hdst, size_t count)
+{
+    Ctx& c = ctx();
+    if (c.h_pub == nullptr || count > (size_t)kPubDoubles || opt("fetch.poll", 1.0) == 0.0) {
+        DB_CUDA(cudaMemcpyAsync(hdst, dsrc, count * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        DB_CUDA(cudaStreamSynchronize(c.stream));
+        return 0;
+    }
+    const unsigned seq = ++c.pub_seq;
+    k_publish<<<1, count > 32 ? 128 : 32, 0, c.stream>>>(dsrc, (int)count, c.d_pub, seq);
+    count_launch();
+    DB_CUDA(cudaGetLastError());
+    volatile unsigned* flag = reinterpret_cast<volatile unsigned*>(c.h_pub + kPubDoubles);
+    unsigned long long spins = 0;
+    while (*flag != seq) {
+        if ((++spins & 0x3fffu) == 0) {                       // every 16 k polls: is the stream still alive?
+            const cudaError_t q = cudaStreamQuery(c.stream);
+            if (q == cudaSuccess) break;                      // drained: the word is there (or the kernel never ran)
+            if (q != cudaErrorNotReady) return cuda_fail(q, "fetch_small", __FILE__, __LINE__);
+        }
+    }
+    if (*flag != seq) {                                       // stream drained without the word: report whatever went wrong
+        DB_CUDA(cudaStreamSynchronize(c.stream));
+        if (*flag != seq) { set_error("fetch_small: the publishing kernel did not run"); return DROPS_B200_E_CUDA; }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    std::memcpy(hdst, c.h_pub, count * sizeof(double));
+    return 0;
+}
+
 int timing_flush()
 {
     Ctx& c = ctx();
@@ -155,6 +200,14 @@ int drops_b200_init(int device)
     DB_CUDA(cudaMemset(c.tickets, 0, (size_t)kPartialSlots * kTicketStride * sizeof(unsigned)));
     DB_CHECK(dev_alloc(&c.scratch_scalars, 64));
     DB_CUDA(cudaMallocHost((void**)&c.h_scalars, 64 * sizeof(double)));
+    c.h_pub = nullptr; c.d_pub = nullptr; c.pub_seq = 0;
+    if (cudaHostAlloc((void**)&c.h_pub, (kPubDoubles + 2) * sizeof(double), cudaHostAllocMapped) == cudaSuccess) {
+        std::memset(c.h_pub, 0, (kPubDoubles + 2) * sizeof(double));
+        if (cudaHostGetDevicePointer((void**)&c.d_pub, c.h_pub, 0) != cudaSuccess) { cudaFreeHost(c.h_pub); c.h_pub = nullptr; c.d_pub = nullptr; }
+    } else {
+        cudaGetLastError();
+        c.h_pub = nullptr;
+    }
     DB_CUDA(cudaDeviceSynchronize());   // the memsets above ran on the legacy stream
     c.inited = true;
     return 0;
@@ -173,6 +226,8 @@ int drops_b200_shutdown(void)
     dev_free(c.scratch_scalars); c.scratch_scalars = nullptr;
     if (c.h_scalars) cudaFreeHost(c.h_scalars);
     c.h_scalars = nullptr;
+    if (c.h_pub) cudaFreeHost(c.h_pub);
+    c.h_pub = nullptr; c.d_pub = nullptr;
     cudaStreamDestroy(c.stream);
     cudaStreamDestroy(c.copy_stream);
     c.stream = c.copy_stream = nullptr;

@@ -1355,11 +1355,7 @@ int dist_gmres(int np, drops_b200_dist_matrix_s* const* P, double* const* x, con
         if (left && jac) for (int p = 0; p < np; ++p) DB_CHECK(apply_pc(p, W[(size_t)p].r, W[(size_t)p].tmp));
         return 0;
     };
-    auto fetch_host = [&](const double* d, double* h, size_t cnt) -> int {
-        DB_CUDA(cudaMemcpyAsync(h, d, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
-        DB_CUDA(cudaStreamSynchronize(st));
-        return 0;
-    };
+    auto fetch_host = [&](const double* d, double* h, size_t cnt) -> int { return fetch_small(d, h, cnt); };
     auto update_x = [&](int k) -> int {                                       // GMRES_Update :282-297
         if (k < 0) return 0;
         y = s;
@@ -1534,8 +1530,7 @@ int dist_minres(int np, drops_b200_dist_matrix_s* const* P, double* const* x, co
         return 0;
     };
     auto fetch_host = [&](int cnt) -> int {
-        DB_CUDA(cudaMemcpyAsync(c.h_scalars, W[0].d_scal, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
-        DB_CUDA(cudaStreamSynchronize(st));
+        DB_CHECK(fetch_small(W[0].d_scal, c.h_scalars, (size_t)cnt));
         return check_p2p_faults(np, P);                           // a stale partial must not steer the rotations
     };
     auto apply_pc = [&](int p, double* out, const double* in) -> int {

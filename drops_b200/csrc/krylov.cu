@@ -53,6 +53,8 @@ static int check_system(drops_b200_matrix_s* M, int pc)
 
 static int fetch(const void* dsrc, void* hdst_pinned_or_not, size_t bytes)
 {
+    if (bytes % sizeof(double) == 0)         // scalars and Hessenberg columns: published to mapped memory, the host polls
+        return fetch_small(static_cast<const double*>(dsrc), static_cast<double*>(hdst_pinned_or_not), bytes / sizeof(double));
     Ctx& c = ctx();
     DB_CUDA(cudaMemcpyAsync(hdst_pinned_or_not, dsrc, bytes, cudaMemcpyDeviceToHost, c.stream));
     DB_CUDA(cudaStreamSynchronize(c.stream));
