@@ -10,8 +10,8 @@
 //     padding is < 1 % on the P2 brick (65/27/27/19 entries per row).
 //   * each thread walks ITS row left to right: sum = ((0 + a0*x0) + a1*x1) + ... with the product
 //     rounded before the add -- the reference's summation order, so the result is bit-identical
-//     to y_Ax compiled without FMA contraction ("spmv.exact" = 1, the default).  The kernel is
-//     nowhere near FP64-bound, so the unfused mul/add costs nothing.
+//     to y_Ax compiled without FMA contraction.  The kernel is nowhere near FP64-bound, so the unfused
+//     mul/add costs nothing.
 //   * matrix stream: ld.global.cs (evict-first, does not displace x); x: ld.global.nc (L1).
 //   * a CTA owns a contiguous range of slices and its warps walk it round-robin, so the x lines
 //     touched by neighbouring mesh lines are reused out of the SM's L1.
@@ -413,8 +413,7 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a)
     SellView v{A.slice_ptr, a.row_ordered ? A.colp : A.col, A.val, a.row_ordered ? nullptr : A.perm, (long long)A.nslices,
                use_sc ? A.scd : nullptr, use_sc ? A.sc : nullptr};
     EpiArgs e = make_epi(a);
-    if (opt("spmv.exact", 1.0) != 0.0) launch_sell_epi<true>(v, a, e, (int)grid, threads, st);
-    else launch_sell_epi<false>(v, a, e, (int)grid, threads, st);
+    launch_sell_epi<true>(v, a, e, (int)grid, threads, st);
     count_launch();
     DB_CUDA(cudaGetLastError());
     return 0;

@@ -38,8 +38,7 @@ struct SpmvArgs {
     cudaStream_t stream = nullptr; // default: ctx().stream
 };
 
-// y = A x through the sliced-ELL operator (exact reference summation order unless option
-// "spmv.exact" is 0, in which case FMA is used).
+// y = A x through the sliced-ELL operator (exact reference summation order, product rounded before the add).
 int spmv_sell(const SellOp& A, const SpmvArgs& a);
 // Same operator on its dictionary-packed stream (SellOp::pk, 4 B per entry; spmv_pk.cu); spmv_sell
 // dispatches to it when the operator has one and option "spmv.pk" is not 0.

@@ -30,7 +30,7 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
     if (A.rows == 0) return 0;
     // the fused-dot product with the dictionary in the parameter block has its own geometry (measured on C2 inside
     // PCG: 15 words in flight x 384-thread CTAs x 192 slices, 3 CTAs of <= 56 registers per SM)
-    const bool dot_geometry = a.dotv != nullptr && a.epilogue == EPI_NONE && opt("spmv.exact", 1.0) != 0.0 &&     // (the form launch_pk has the U15 kernel for)
+    const bool dot_geometry = a.dotv != nullptr && a.epilogue == EPI_NONE &&     // (the form launch_pk has the U15 kernel for)
                               A.pk != nullptr && A.ndict_host > 0 && A.ndict_host == A.ndict &&
                               A.ndict <= kPkDictSmem && opt("spmv.pkdict", 0.0) == 0.0 &&
                               opt("spmv.pk_cdict", 1.0) != 0.0 && opt("spmv.pk_cdict_dot", 1.0) != 0.0;
@@ -68,8 +68,7 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
              A.ndict_host == A.ndict ? A.ndict_host : 0, {}};
     if (v.cdict_n > 0) std::memcpy(v.cdict, A.dict_host, sizeof(double) * ((size_t)A.ndict_host + 1));
     EpiArgs e = make_epi(a);
-    if (opt("spmv.exact", 1.0) != 0.0) launch_pk_epi<true>(v, a, e, (int)grid, threads, st);
-    else launch_pk_epi_fma(v, a, e, (int)grid, threads, st);
+    launch_pk_epi<true>(v, a, e, (int)grid, threads, st);      // reference arithmetic: the product is rounded before the add
     count_launch();
     DB_CUDA(cudaGetLastError());
     return 0;

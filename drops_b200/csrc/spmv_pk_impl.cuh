@@ -1,6 +1,6 @@
-// spmv_pk_impl.cuh -- kernels and launch tables of the dictionary-packed SpMV, shared by the two translation
-// units that instantiate them: spmv_pk.cu (exact reference arithmetic: product rounded before the add) and
-// spmv_pk_fma.cu ("spmv.exact" = 0: fused multiply-add).  Split so that the two halves compile in parallel.
+// spmv_pk_impl.cuh -- kernels and launch tables of the dictionary-packed SpMV and of the segment kernel (spmv_pk.cu).
+// EXACT = reference arithmetic (product rounded before the add); the fused-multiply-add instantiations of round 1
+// ("spmv.exact" = 0) bought nothing on kernels that are nowhere near FP64-bound and are gone.
 #pragma once
 #include "spmv_impl.cuh"
 
@@ -411,8 +411,5 @@ static void launch_pk_epi(const PkView& v, const SpmvArgs& a, const EpiArgs& e, 
         default:         launch_pk<EPI_NONE, EXACT>(v, a, e, grid, threads, st); break;
     }
 }
-
-// defined in spmv_pk_fma.cu
-void launch_pk_epi_fma(const PkView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads, cudaStream_t st);
 
 }  // namespace db200

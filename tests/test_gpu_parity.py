@@ -45,13 +45,12 @@ def test_spmv_bit_identical_to_reference(gpu, path):
     assert np.array_equal(rb, g["rowbeg"]) and np.array_equal(ci, g["colind"]) and np.array_equal(va, g["val"])
 
 
-@pytest.mark.parametrize("kernel,lanes,exact", [(0, 0, 0), (1, 2, 0), (1, 8, 0), (1, 32, 0)])
-def test_spmv_fast_modes_within_tolerance(gpu, kernel, lanes, exact):
-    """FMA / tree-summed variants: |y - y_ref|_i <= 1e-14 (|A||x|)_i."""
+@pytest.mark.parametrize("kernel,lanes", [(1, 2), (1, 8), (1, 32)])
+def test_spmv_fast_modes_within_tolerance(gpu, kernel, lanes):
+    """The tree-summed CSR-vector comparison kernel: |y - y_ref|_i <= 1e-14 (|A||x|)_i."""
     try:
         gpu.set_option("spmv.kernel", kernel)
         gpu.set_option("spmv.lanes", lanes or 8)
-        gpu.set_option("spmv.exact", exact)
         for path in golden_files("brick_fe2_N6*.npz") + golden_files("random_ragged.npz"):
             g = dict(np.load(path))
             A = gmat(gpu, g)
@@ -60,7 +59,6 @@ def test_spmv_fast_modes_within_tolerance(gpu, kernel, lanes, exact):
             assert np.all(np.abs(y - g["y_Ax"]) <= SPMV_RTOL * scale + 1e-300)
     finally:
         gpu.set_option("spmv.kernel", 0)
-        gpu.set_option("spmv.exact", 1)
 
 
 @pytest.mark.parametrize("sigma,threads,ctas,spc,variant,prefetch",
@@ -93,7 +91,7 @@ CDICT_DEFAULT = 1     # library default of "spmv.pk_cdict"
 
 PK_DEFAULTS = {"spmv.pk": 1, "pcg.reorder": 1, "pcg.defer_x": 1, "pcg.fused_dot": 1, "krylov.reorder": 1, "spmv.pk_threads": 512,
                "spmv.pk_slices_per_cta": 128, "spmv.pkdict": 0, "spmv.dotmode": 0, "sell.sigma": 4096,
-               "sell.valdict": 1, "spmv.exact": 1,
+               "sell.valdict": 1,
                "spmv.pk_cdict": CDICT_DEFAULT, "spmv.pk_cdict_dot": CDICT_DOT_DEFAULT,
                "spmv.pk_dot_threads": 384, "spmv.pk_dot_slices_per_cta": 192}
 
