@@ -391,7 +391,7 @@ def run_ours(args):
         kernel_name = "k_spmv_sell<EPI_NONE,exact,dot> (q = A p fused with p.q)"
     roofline = {"bound": "hbm", "kernel": kernel_name,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "traffic": None,
+                "peak_source": peak_src, "nominal_peak": 8000.0, "frac_of_nominal": achieved / 8000.0, "traffic": None,
                 "algorithmic_bytes_per_launch": spmv_bytes, "bytes_per_stored_entry": stream_bytes / max(nnz, 1),
                 "avg_launch_ms": spmv_avg_ms, "launches": spmv_cnt,
                 "survey_12B_layout": {"algorithmic_bytes_per_launch": survey_spmv_bytes,
@@ -1070,6 +1070,7 @@ def run_ours_dist(args, rank, world, local, dist):
                 "packed_4B_equivalent": {"algorithmic_bytes_per_launch": packed_spmv_bytes,
                                          "frac": packed_spmv_bytes / (t_int / max(c_int, 1) / 1e3) / 1e9 / peak},
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "nominal_peak": 8000.0, "frac_of_nominal": achieved / 8000.0,
                 "traffic": None, "algorithmic_bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_avg_ms,
                 "launches": c_int,
                 "iteration": {"algorithmic_bytes_per_gpu": iter_bytes,
