@@ -533,6 +533,39 @@ def run_ours(args):
                            "line-segment slices come from 16-byte records (8.5 instead of 12 B per entry); same warm-up and step count as the headline"}
         assert abs(G["resid"] - resid) <= 1e-9 * abs(resid), (G["resid"], resid)     # same system, same 200 iterations
 
+    # ---- the form a matrix DROPS assembled itself takes at this size: its values are equal only up to the rounding of the
+    #      assembly (757 distinct bit patterns on a 40^3 P2 brick, tests/test_drops_exe.py), and 26 column bits + >= 10 index
+    #      bits do not fit one word -- int32 position / segment records + a 16-bit value index per entry ("sell.pack_bits" = 0
+    #      forces that form on the synthetic matrix)
+    six = None
+    if packed and not args.no_general:
+        try:
+            capi.set_option("sell.pack_bits", 0)
+            S6 = capi.Matrix.brick(fe, N, numbering)
+            capi.set_option("sell.pack_bits", 32)
+            s_layout, s_vd, s_padded = S6.layout(), S6.value_dictionary(), float(S6.info()["padded_nnz"])
+            A_main = A
+            A = S6
+            T6 = timed_steps(args.warmup, args.steps, False)
+            A = A_main
+            S6.close()
+            s_ms = T6["spmv"][0] / max(T6["spmv"][1], 1)
+            s_seg = float(s_layout.get("segment_entries", 0)) if capi.get_option("spmv.segments", 1.0) != 0.0 else 0.0
+            s_stream = 2.0 * s_padded + 0.5 * s_seg + 4.0 * (s_padded - s_seg)
+            s_bytes = s_stream + 4.0 * (n + 1) + 16.0 * n
+            six = {"iterations_per_s": args.steps * iters / (T6["ms"] / 1e3), "spmv_avg_launch_ms": s_ms, "six_byte": bool(s_vd["six_byte"]),
+                   "row_ordered_stream": s_layout["row_ordered_kind"], "segment_entries": s_seg,
+                   "kernel": "k_spmv_sell_sci<EPI_NONE,exact,dot>" if s_seg > 0 else "k_spmv_sell_pk<...,V6>",
+                   "bytes_per_stored_entry": s_stream / max(nnz, 1), "algorithmic_bytes_per_launch": s_bytes,
+                   "spmv_frac": s_bytes / (s_ms / 1e3) / 1e9 / peak, "packed_4B_equivalent_frac": packed_spmv_bytes / (s_ms / 1e3) / 1e9 / peak,
+                   "note": "what a C2-size matrix from DROPS' own assembly runs (rounding variants of the stencil values: dictionary of "
+                           "hundreds to thousands of values, no one-word packing); bound by the per-lane index loads and dictionary look-ups, "
+                           "not by HBM (profiles/r02_ncu_spmv_sci.raw.csv)"}
+            assert abs(T6["resid"] - resid) <= 1e-9 * abs(resid), (T6["resid"], resid)
+        except Exception as exc:
+            capi.set_option("sell.pack_bits", 32)
+            six = {"error": repr(exc)}
+
     # ---- the other two solvers of the path on the same system (device-resident, fixed work) ---------
     solvers = None
     if not args.no_solvers:
@@ -641,7 +674,7 @@ def run_ours(args):
                                 (", PCG on row-ordered vectors" if layout["row_ordered_stream"] and capi.get_option("pcg.reorder", 1.0) != 0.0 else ""),
                    "generate_s": gen_s},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        "final_relative_residual": resid, "c2_to_convergence": convergence, "general_12B_stream": general,
+        "final_relative_residual": resid, "c2_to_convergence": convergence, "general_12B_stream": general, "rounding_variants_six_byte_stream": six,
         "other_solvers_c2": solvers,
         "other_configs": {"C1_p1_n64": c1, "C1_cdrdrops_executable": exe0, "C3_levelset_gmres_jacobi": c3,
                           "C4_interface_pcg_jacobi": c4},

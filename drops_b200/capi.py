@@ -97,6 +97,7 @@ SIGNATURES = {
     "drops_b200_matrix_set_chebyshev": (_i, [_vp, _i, _d, _i, _d]),
     "drops_b200_chebyshev_lambda_max": (_i, [_vp, _i, _dpp]),
     "drops_b200_matrix_line_segments": (_i, [_vp, C.POINTER(C.c_size_t)]),
+    "drops_b200_matrix_row_order": (_i, [_vp, C.c_void_p, C.c_size_t]),
     "drops_b200_matrix_segment_stream": (_i, [_vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "drops_b200_matrix_set_diag_pc": (_i, [_vp, C.c_void_p]),
     "drops_b200_diagpc_apply": (_i, [_vp, _vp, _vp]),
@@ -401,6 +402,12 @@ class Matrix:
         ns, pn = C.c_size_t(), C.c_size_t()
         check(lib().drops_b200_matrix_format(self.h, C.byref(ns), C.byref(pn)))
         return {"nslices": ns.value, "padded_nnz": pn.value}
+
+    def row_order(self):
+        """perm[32 * slice + lane] = row summed there (-1: padding position)."""
+        perm = np.full(self.format()["nslices"] * 32, -1, dtype=np.int32)
+        check(lib().drops_b200_matrix_row_order(self.h, perm.ctypes.data_as(C.c_void_p), perm.size))
+        return perm
 
     def layout(self):
         bo, ro = C.c_int(), C.c_int()

@@ -735,7 +735,10 @@ k_sc_build(long long nslices, const int64_t* __restrict__ slice_ptr, const uint3
             const unsigned m1 = __ballot_sync(0xffffffffu, d == d1);
             good = (m0 | m1) == 0xffffffffu;
         }
-        // positions are >= 0 and lane < 32: d0, d1 > -32; they are stored as signed 32-bit values
+        // positions are >= 0 and lane < 32: d0, d1 > -32; they are stored as signed 32-bit values.
+        // (A per-entry-row fall-back -- records for the regular entry-rows of a slice, the twin's own words for the others --
+        // was measured: the dependent load in the middle of a batch of gathers costs more than the records save, 1.22 -> 1.63 ms
+        // on C2; a slice either runs from records entirely or not at all.)
         if (good) { if (lane == 0) scd[(base >> 5) + j] = make_uint4((unsigned)d0, (unsigned)d1, (unsigned)brk, idx0); }
         else ok = false;
     }
@@ -755,7 +758,7 @@ int build_segment_descriptors(SellOp& S, size_t* bytes)
     if (S.nslices == 0 || opt("sell.segments", 1.0) == 0.0) return 0;
     const bool packed = S.pkp != nullptr;
     if (packed && (S.pk_nopad == nullptr || S.ndict_host == 0)) return 0;
-    if (!packed && (S.colp == nullptr || S.vidx != nullptr)) return 0;
+    if (!packed && S.colp == nullptr) return 0;
     cudaStream_t st = ctx().stream;
     unsigned long long* d_counts = nullptr;
     DB_CHECK(dev_alloc(&d_counts, 2));
@@ -778,7 +781,7 @@ int build_segment_descriptors(SellOp& S, size_t* bytes)
     }
     dev_free(d_counts);
     // not worth a second code path for a handful of slices
-    if (status != 0 || S.sc_entries * 4 < S.padded) {
+    if (status != 0 || S.sc_entries * 10 < S.padded) {
         dev_free(S.scd); S.scd = nullptr; dev_free(S.sc); S.sc = nullptr; S.sc_slices = S.sc_entries = 0;
         return status;
     }
@@ -821,7 +824,9 @@ int build_row_ordered_columns(SellOp& S, size_t* bytes)
     dev_free(S.colp); S.colp = nullptr;
     if (S.pkp != nullptr) return 0;                       // the packed twin exists
     S.npos = 0;
-    if (S.vidx != nullptr) return 0;                      // six-byte form: faster in the caller's order than 12 bytes row-ordered
+    // six-byte form (16-bit value index beside the int32 column): its twin pairs the positions with the same indices, and
+    // where the rows are line segments the positions collapse into segment records (k_spmv_sell_sci: 2.5 B per entry)
+    if (S.vidx != nullptr && opt("sell.reorder_six", 1.0) == 0.0) return 0;
     if (S.padded == 0 || S.col == nullptr || !S.full_rows || S.rows != S.cols || opt("sell.reorder", 1.0) == 0.0) return 0;
     cudaStream_t st = ctx().stream;
     const long long npos = (long long)S.nslices * 32;
@@ -849,18 +854,19 @@ int build_row_ordered_columns(SellOp& S, size_t* bytes)
 // entry the operator holds.  A value update rebuilds them from the CSR copy for the time of the rebuild.
 void release_general(SellOp& S, size_t* bytes)
 {
-    if (S.pk == nullptr || S.val == nullptr || opt("sell.release_general", 1.0) == 0.0) return;
+    if ((S.pk == nullptr && S.vidx == nullptr) || S.val == nullptr || opt("sell.release_general", 1.0) == 0.0) return;
     if ((double)S.rows < opt("sell.release_min_rows", 2.0e6)) return;
-    dev_free(S.col); S.col = nullptr;
+    size_t freed = S.padded * 8;
+    if (S.pk != nullptr) { dev_free(S.col); S.col = nullptr; freed += S.padded * 4; }     // (the six-byte form reads col)
     dev_free(S.val); S.val = nullptr;
     S.general_released = true;
-    if (bytes && *bytes >= S.padded * 12) *bytes -= S.padded * 12;
+    if (bytes && *bytes >= freed) *bytes -= freed;
 }
 
 static int restore_general(const CsrDev& A, SellOp& S)
 {
     if (!S.general_released || S.val != nullptr) return 0;
-    DB_CHECK(dev_alloc(&S.col, S.padded));
+    if (S.col == nullptr) DB_CHECK(dev_alloc(&S.col, S.padded));
     DB_CHECK(dev_alloc(&S.val, S.padded));
     k_sell_fill<<<blocks_for((long long)S.nslices * 32, 256), 256, 0, ctx().stream>>>(
         (long long)S.nslices, S.slice_ptr, S.perm, A.rowptr, A.col, A.val, S.col, S.val);
@@ -1221,6 +1227,16 @@ int drops_b200_matrix_line_segments(drops_b200_matrix_t M, size_t* n_segments)
 {
     DB_ARG(M != nullptr && n_segments != nullptr, "null argument");
     *n_segments = M->block_ordered ? M->line_segments : 0;
+    return 0;
+}
+
+int drops_b200_matrix_row_order(drops_b200_matrix_t M, int32_t* perm, size_t capacity)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(M != nullptr && perm != nullptr, "null argument");
+    const size_t npos = M->sell.nslices * 32;
+    DB_ARG(capacity >= npos, "row order: buffer too small (32 * nslices entries)");
+    if (npos) DB_CUDA(cudaMemcpy(perm, M->sell.perm, npos * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return 0;
 }
 

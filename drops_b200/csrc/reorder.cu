@@ -115,10 +115,20 @@ __global__ void k_line_next(int n, const int64_t* __restrict__ rowptr, const int
         for (int s = 1; s <= S && r + s < n && found < 0; ++s) {
             const int64_t b2 = rowptr[r + s];
             if ((int)(rowptr[r + s + 1] - b2) != len) continue;
+            // a translate moves every column by the stride of that column's own line: on a mesh with k kinds of lines the
+            // differences take at most a few distinct values (1 for vertices and 2 or 7 for edges on the P2 bricks); a row of
+            // ANOTHER stencil class that happens to sit next to r (DROPS numbers the edges cell by cell) has all kinds of
+            // differences -- at most two distinct values are accepted
             bool ok = true;
+            int da = 0, db = 0;
             for (int j = 0; j < len && ok; ++j) {
                 const int d = col[b2 + j] - col[b + j];
                 ok = d >= 1 && d <= D;
+                if (d != da && d != db) {
+                    if (da == 0) da = d;
+                    else if (db == 0) db = d;
+                    else ok = false;
+                }
             }
             if (ok) found = r + s;
         }
@@ -127,16 +137,39 @@ __global__ void k_line_next(int n, const int64_t* __restrict__ rowptr, const int
     if (found >= 0) atomicMax(&prv[found], r);
 }
 
-// Keeps nxt[r] only where r is the predecessor its successor kept; anc/dist start the ranking: a head is its own
-// ancestor at distance 0, every other row points at its predecessor at distance 1.
-__global__ void k_line_validate(int n, int32_t* __restrict__ nxt, const int32_t* __restrict__ prv,
-                                int32_t* __restrict__ anc, int32_t* __restrict__ dist)
+// Keeps nxt[r] only where r is the predecessor its successor kept.
+__global__ void k_line_validate(int n, int32_t* __restrict__ nxt, const int32_t* __restrict__ prv)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const int f = nxt[r];
     if (f >= 0 && prv[f] != r) nxt[r] = -1;
-    const int p = prv[r];
+}
+
+// A line ends where the stride changes: DROPS leaves the eliminated boundary unknowns out of the numbering, so the last
+// vertex of a mesh line finds the first vertex of the NEXT line three rows on and would carry the chain across the
+// wrap (segments with a jump in every column).  cut[r] = the link r -> nxt[r] goes; decided from the links as they are.
+__global__ void k_line_cut(int n, const int32_t* __restrict__ nxt, const int32_t* __restrict__ prv, uint8_t* __restrict__ cut)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int f = nxt[r], p = prv[r];
+    cut[r] = (f >= 0 && p >= 0 && nxt[p] == r && (r - p) != (f - r)) ? 1 : 0;
+}
+
+// Applies the cuts; anc/dist start the ranking: a head is its own ancestor at distance 0, every other row points at its
+// predecessor at distance 1.
+__global__ void k_line_apply(int n, int32_t* __restrict__ nxt, int32_t* __restrict__ prv, const uint8_t* __restrict__ cut,
+                             int32_t* __restrict__ anc, int32_t* __restrict__ dist)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int p = prv[r];
+    if (p >= 0 && (nxt[p] != r || cut[p])) p = -1;        // (prv may still name a claimant that lost)
+    // the links are rewritten by their owners only (nxt[r] by r, prv[r] by r); a reader that sees nxt[p] already reset
+    // comes to the same conclusion as one that sees cut[p]
+    if (cut[r]) nxt[r] = -1;
+    prv[r] = p;
     anc[r] = p >= 0 ? p : r;
     dist[r] = p >= 0 ? 1 : 0;
 }
@@ -177,9 +210,12 @@ __global__ void k_line_keys(int n, const int32_t* __restrict__ prv, const int32_
     row[r] = r;
     const int rank = dist[r];
     const bool full = ((rank >> 5) + 1) * 32 <= clen[anc[r]];
+    // the tail of a chain (fewer than 32 rows) stays together in chain order as well: columns that point into it are then
+    // one run of positions, although the tail shares its slices with other tails (DROPS numbers edges cell by cell, so in
+    // ascending row order the tails of seven edge classes would interleave)
     int first = r;
-    if (full) for (int t = rank & 31; t > 0; --t) first = prv[first];
-    keyA[r] = ((unsigned long long)(unsigned)first << 5) | (unsigned long long)(full ? (rank & 31) : 0);
+    for (int t = rank & 31; t > 0; --t) first = prv[first];
+    keyA[r] = ((unsigned long long)(unsigned)first << 5) | (unsigned long long)(rank & 31);
     keyB[r] = cell_code(da[first], db[first], dc[first], ta, tb, tc) | (full ? 0u : (1u << 30));
     if (full && (rank & 31) == 0) atomicAdd(nfull, 1ull);
 }
@@ -318,8 +354,11 @@ int compute_block_order(const CsrDev& A, int32_t** d_order, size_t* n_segments)
         const int g = blocks_of(n, 256);
         k_fill_i32<<<g, 256, 0, st>>>(n, q1, -1);
         k_line_next<<<g, 256, 0, st>>>(n, A.rowptr, A.col, S, D, q0, q1);
-        k_line_validate<<<g, 256, 0, st>>>(n, q0, q1, anc[0], dst[0]);
-        count_launch(); count_launch(); count_launch();
+        k_line_validate<<<g, 256, 0, st>>>(n, q0, q1);
+        // kb2 doubles as the cut flags (n bytes of its 4 n)
+        k_line_cut<<<g, 256, 0, st>>>(n, q0, q1, reinterpret_cast<uint8_t*>(kb2));
+        k_line_apply<<<g, 256, 0, st>>>(n, q0, q1, reinterpret_cast<const uint8_t*>(kb2), anc[0], dst[0]);
+        count_launch(5);
         int cur = 0;
         for (int round = 0; round < 32; ++round) {
             int again = 0;

@@ -376,7 +376,7 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a)
     if (A.rows == 0) return 0;
     // dictionary-packed stream (4 B per entry, spmv_pk.cu) when the operator has one
     if ((A.pk != nullptr || A.vidx != nullptr) && a.xghost == nullptr && opt("spmv.pk", 1.0) != 0.0 &&
-        (!a.row_ordered || A.pkp != nullptr)) {
+        (!a.row_ordered || A.pkp != nullptr || (A.pk == nullptr && A.vidx != nullptr && A.colp != nullptr))) {
         return spmv_sell_pk(A, a);
     }
     DB_ARG(!a.row_ordered || A.colp != nullptr, "row-ordered vectors need the operator's row-ordered stream");

@@ -20,7 +20,7 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
 {
     Ctx& c = ctx();
     DB_ARG((A.pk != nullptr || A.vidx != nullptr) && A.dict != nullptr, "operator holds no packed stream");
-    DB_ARG(!a.row_ordered || A.pkp != nullptr, "operator holds no row-ordered stream");
+    DB_ARG(!a.row_ordered || A.pkp != nullptr || (A.vidx != nullptr && A.colp != nullptr), "operator holds no row-ordered stream");
     DB_ARG(a.x != nullptr && a.y != nullptr, "null vector");
     DB_ARG(a.x != a.y, "x and y must not alias");
     DB_ARG(a.xghost == nullptr, "the packed stream has no split-x form");
@@ -35,10 +35,11 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
                               A.ndict <= kPkDictSmem && opt("spmv.pkdict", 0.0) == 0.0 &&
                               opt("spmv.pk_cdict", 1.0) != 0.0 && opt("spmv.pk_cdict_dot", 1.0) != 0.0;
     // segment descriptors: the row-ordered twin of an operator that is mostly line segments ("spmv.segments")
+    const bool six_ro = a.row_ordered && A.pk == nullptr && A.vidx != nullptr && A.colp != nullptr;     // twin of the six-byte form
     const bool use_sc = a.row_ordered && A.scd != nullptr && A.sc != nullptr && opt("spmv.segments", 1.0) != 0.0 &&
-                        A.pk != nullptr && A.ndict_host > 0 && A.ndict_host == A.ndict && A.ndict <= kPkDictSmem &&
-                        opt("spmv.pkdict", 0.0) == 0.0 && opt("spmv.pk_cdict", 1.0) != 0.0;
-    int threads = use_sc ? (int)opt("spmv.sc_threads", 512) : dot_geometry ? (int)opt("spmv.pk_dot_threads", 384) : (int)opt("spmv.pk_threads", 512);
+                        (six_ro || (A.pk != nullptr && A.ndict_host > 0 && A.ndict_host == A.ndict && A.ndict <= kPkDictSmem &&
+                                    opt("spmv.pkdict", 0.0) == 0.0 && opt("spmv.pk_cdict", 1.0) != 0.0));
+    int threads = (use_sc && six_ro) ? (int)opt("spmv.sci_threads", 512) : use_sc ? (int)opt("spmv.sc_threads", 512) : dot_geometry ? (int)opt("spmv.pk_dot_threads", 384) : (int)opt("spmv.pk_threads", 512);
     if (threads < 32) threads = 32;
     if (threads > 1024) threads = 1024;
     threads &= ~31;
@@ -47,7 +48,7 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
     long long grid;
     if (per_sm > 0.0) grid = (long long)(per_sm * c.sm_count + 0.5);
     else {
-        long long spc = use_sc ? (long long)opt("spmv.sc_slices_per_cta", 256.0) : dot_geometry ? (long long)opt("spmv.pk_dot_slices_per_cta", 192.0) : (long long)opt("spmv.pk_slices_per_cta", 128.0);
+        long long spc = (use_sc && six_ro) ? (long long)opt("spmv.sci_slices_per_cta", 256.0) : use_sc ? (long long)opt("spmv.sc_slices_per_cta", 256.0) : dot_geometry ? (long long)opt("spmv.pk_dot_slices_per_cta", 192.0) : (long long)opt("spmv.pk_slices_per_cta", 128.0);
         if (spc < 1) spc = 1;
         grid = ((long long)A.nslices + spc - 1) / spc;
     }
@@ -62,7 +63,7 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
     if (grid > kMaxReduceGrid) grid = kMaxReduceGrid;
     if (grid < 1) grid = 1;
     cudaStream_t st = a.stream ? a.stream : c.stream;
-    PkView v{A.slice_ptr, A.col, A.pk != nullptr ? nullptr : A.vidx, a.row_ordered ? A.pkp : A.pk, A.dict, a.row_ordered ? nullptr : A.perm, (long long)A.nslices,
+    PkView v{A.slice_ptr, six_ro ? A.colp : A.col, A.pk != nullptr ? nullptr : A.vidx, a.row_ordered ? A.pkp : A.pk, A.dict, a.row_ordered ? nullptr : A.perm, (long long)A.nslices,
              A.ndict, A.cbits, opt("spmv.pk_nopad", 1.0) != 0.0 ? A.pk_nopad : nullptr,
              use_sc ? A.scd : nullptr, use_sc ? A.sc : nullptr,
              A.ndict_host == A.ndict ? A.ndict_host : 0, {}};

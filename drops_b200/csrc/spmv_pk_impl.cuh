@@ -345,6 +345,135 @@ static void launch_sc_d(const PkView& v, const SpmvArgs& a, const EpiArgs& e, in
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// k_spmv_sell_sci: segment records for the COLUMNS, a 16-bit dictionary index per stored entry for the VALUES -- 2.5 bytes
+// per entry.  This is the form of a matrix DROPS assembled itself on a structured mesh: the columns are translates of
+// each other, the values are equal only up to the rounding of the assembly (757 distinct bit patterns on a 40^3 P2 brick
+// where exact arithmetic has 21), so lanes do not share an index, and at C2 size column bits + index bits no longer fit
+// one word.  Row-ordered twin of the six-byte form: PkView::col = positions (SellOp::colp), vidx, scd / sc.  Dictionary in
+// shared memory (SMEM, <= kSciDictSmem values) or through L1.  Unflagged slices read the int32 position of every entry.
+// Same products in the same order as the six-byte kernel: bit-identical.
+// ------------------------------------------------------------------------------------------
+constexpr int kSciDictSmem = 3072;         // (24 KB of dynamic shared memory beside the 15 KB of records)
+
+template <bool EXACT, int UB, bool SMEM>
+__device__ __forceinline__ double sci_batch(const PkView& A, const uint16_t* __restrict__ ip, const uint4* __restrict__ sd, int j,
+                                            double sum, int lane, const double* __restrict__ x, const double* __restrict__ sdict)
+{
+    unsigned vi[UB];
+    double xv[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) vi[u] = __ldcs(ip + (size_t)(j + u) * 32);
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+        const uint4 d = sd[j + u];
+        const int c = (lane < (int)d.z ? (int)d.x : (int)d.y) + lane;
+        xv[u] = __ldg(x + c);
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+        const double v = SMEM ? sdict[vi[u]] : __ldg(A.dict + vi[u]);
+        sum = EXACT ? __dadd_rn(sum, __dmul_rn(v, xv[u])) : fma(v, xv[u], sum);
+    }
+    return sum;
+}
+
+template <int EPI, bool EXACT, int DOT, int U, int MAXT, int MINB, bool SMEM>
+__global__ void __launch_bounds__(MAXT, MINB)
+k_spmv_sell_sci(const __grid_constant__ PkView A, const double* __restrict__ x, double* __restrict__ y, EpiArgs e)
+{
+    if (e.done != nullptr && *e.done != 0) return;
+    extern __shared__ double sdict[];                      // SMEM: ndict + 1 values
+    __shared__ dd red_smem[DOT == 1 ? 32 : 1];
+    __shared__ uint4 sdesc[(MAXT / 32) * kScMaxWidth];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int s_begin = (int)(A.nslices * (long long)blockIdx.x / gridDim.x);
+    const int s_end   = (int)(A.nslices * (long long)(blockIdx.x + 1) / gridDim.x);
+    if (SMEM) {
+        for (int i = threadIdx.x; i <= A.ndict; i += blockDim.x) sdict[i] = A.dict[i];
+        __syncthreads();
+    }
+    const double beta = (EPI == EPI_AXMBY) ? (e.beta != nullptr ? *e.beta : e.beta_val) : 0.0;
+    const uint4* sd = sdesc + warp * kScMaxWidth;
+    const uint32_t sd_addr = (uint32_t)__cvta_generic_to_shared(sd);
+    dd acc[1] = {dd_zero()};
+    int64_t base = 0;
+    int width = 0;
+    bool seg = false;
+    if (s_begin + warp < s_end) {
+        const int s0 = s_begin + warp;
+        base = A.slice_ptr[s0];
+        width = (int)((A.slice_ptr[s0 + 1] - base) >> 5);
+        seg = A.sc[s0] != 0;
+        if (seg) sc_issue(A, sd_addr, base, width, lane);
+    }
+    for (int s = s_begin + warp; s < s_end; s += nwarp) {
+        int64_t nbase = 0;
+        int nwidth = 0;
+        bool nseg = false;
+        const int s1 = s + nwarp;
+        if (s1 < s_end) {
+            nbase = A.slice_ptr[s1];
+            nwidth = (int)((A.slice_ptr[s1 + 1] - nbase) >> 5);
+            nseg = A.sc[s1] != 0;
+        }
+        const int row = s * 32 + lane;                        // row-ordered twin: the position IS the row
+        double dv = 0.0, av = 0.0;
+        if (DOT) dv = __ldg(e.dotv + row);
+        if (EPI != EPI_NONE) av = __ldg(e.aux + row);
+        double sum = 0.0;
+        if (seg) {
+            const uint16_t* ip = A.vidx + base + lane;
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            int j = 0;
+            for (; j + U <= width; j += U) sum = sci_batch<EXACT, U, SMEM>(A, ip, sd, j, sum, lane, x, sdict);
+            if (U > 8 && j + 8 <= width) { sum = sci_batch<EXACT, 8, SMEM>(A, ip, sd, j, sum, lane, x, sdict); j += 8; }
+            if (U > 4 && j + 4 <= width) { sum = sci_batch<EXACT, 4, SMEM>(A, ip, sd, j, sum, lane, x, sdict); j += 4; }
+            if (U > 2 && j + 2 <= width) { sum = sci_batch<EXACT, 2, SMEM>(A, ip, sd, j, sum, lane, x, sdict); j += 2; }
+            for (; j < width; ++j) sum = sci_batch<EXACT, 1, SMEM>(A, ip, sd, j, sum, lane, x, sdict);
+            __syncwarp();
+        } else {
+            sum = pk6_row_sum<EXACT, 8, SMEM>(A, base, width, lane, x);      // int32 position (-1 = padding) + index per entry
+        }
+        if (nseg) sc_issue(A, sd_addr, nbase, nwidth, lane);
+        const double out = apply_epilogue<EPI>(sum, av, e, beta);
+        y[row] = out;
+        if (DOT) acc[0] = dd_add_prod(acc[0], out, dv);
+        base = nbase; width = nwidth; seg = nseg;
+    }
+    if (DOT == 1) {
+        if (grid_reduce_dd<1>(acc, red_smem, e.partials, e.ticket)) {
+            if (threadIdx.x == 0) store_dot(e, acc[0]);
+        }
+    }
+    if (DOT == 2) {
+        const dd w = warp_reduce_dd(acc[0]);
+        if (lane == 0) e.partials[(size_t)blockIdx.x * nwarp + warp] = w;
+    }
+}
+
+template <int EPI, bool EXACT, int U, int MAXT, int MINB, bool SMEM>
+static void launch_sci_d(const PkView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads, cudaStream_t st)
+{
+    if (threads > MAXT) threads = MAXT;
+    const size_t sh = SMEM ? ((size_t)v.ndict + 1) * sizeof(double) : 0;
+    if (a.dotv == nullptr) {
+        k_spmv_sell_sci<EPI, EXACT, 0, U, MAXT, MINB, SMEM><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
+        return;
+    }
+    const long long nwarps = (long long)grid * (threads >> 5);
+    const double mode = opt("spmv.dotmode", 0.0);
+    const bool two_kernels = mode == 2.0 || (mode == 0.0 && grid > (int)kReduceFlat);
+    if (two_kernels && nwarps <= kPartialStride) {
+        k_spmv_sell_sci<EPI, EXACT, 2, U, MAXT, MINB, SMEM><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
+        sum_warp_partials(nwarps, e, st);
+    } else {
+        k_spmv_sell_sci<EPI, EXACT, 1, U, MAXT, MINB, SMEM><<<grid, threads, sh, st>>>(v, a.x, a.y, e);
+    }
+}
+
 template <int EPI, bool EXACT, int U, int MAXT, int MINB, bool SMEM, bool V6, bool CD, int LEAN = 0>
 static void launch_pk_d(const PkView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads, cudaStream_t st)
 {
@@ -375,6 +504,13 @@ template <int EPI, bool EXACT>
 static bool launch_pk(const PkView& v, const SpmvArgs& a, const EpiArgs& e, int grid, int threads, cudaStream_t st)
 {
     const bool smem_ok = v.ndict <= kPkDictSmem && opt("spmv.pkdict", 0.0) == 0.0;
+    if (v.vidx != nullptr && v.scd != nullptr && v.sc != nullptr && v.perm == nullptr) {   // row-ordered twin of the six-byte form
+        // measured on C2 forced into this form (profiles/r02_probe_sci2.json): 8 entries in flight x 512 threads x 3 CTAs per SM
+        // 2.09 ms, 12 x 384 x 3: 2.14, the twin without records: 2.22
+        if (v.ndict <= kSciDictSmem && opt("spmv.pkdict", 0.0) == 0.0) launch_sci_d<EPI, EXACT, 8, 512, 3, true>(v, a, e, grid, threads, st);
+        else launch_sci_d<EPI, EXACT, 8, 512, 3, false>(v, a, e, grid, threads, st);
+        return true;
+    }
     if (v.vidx != nullptr) {       // six-byte form: dictionary in shared memory or through L1
         if (smem_ok) launch_pk_d<EPI, EXACT, 8, 512, 3, true, true, false>(v, a, e, grid, threads, st);
         else launch_pk_d<EPI, EXACT, 8, 512, 3, false, true, false>(v, a, e, grid, threads, st);

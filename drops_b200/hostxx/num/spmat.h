@@ -78,6 +78,20 @@ inline void ensure_init()
         const char* d = std::getenv("DROPS_B200_DEVICE");
         if (!d) d = std::getenv("LOCAL_RANK");
         check(drops_b200_init(d ? std::atoi(d) : 0));
+        // DROPS_B200_OPTIONS="key=value,key=value": library options (include/drops_b200.h, drops_b200_set_option) for an
+        // executable that has no other way to pass them
+        if (const char* o = std::getenv("DROPS_B200_OPTIONS")) {
+            std::string all(o);
+            size_t pos = 0;
+            while (pos < all.size()) {
+                size_t end = all.find(',', pos);
+                if (end == std::string::npos) end = all.size();
+                const std::string kv = all.substr(pos, end - pos);
+                const size_t eq = kv.find('=');
+                if (eq != std::string::npos) check(drops_b200_set_option(kv.substr(0, eq).c_str(), std::atof(kv.c_str() + eq + 1)));
+                pos = end + 1;
+            }
+        }
         return true;
     }();
     (void)once;
@@ -186,6 +200,17 @@ class DeviceCacheCL
                                              A.Version(), &e.handle);
             }
             if (s < 0) { table_.erase(&A); check(s); }
+        }
+        if (trace_on()) {                    // how the operator is stored: one stderr line per upload
+            int bo = 0, ro = 0, nd = 0, pk = 0, cb = 0;
+            size_t ls = 0, ss = 0, se = 0;
+            drops_b200_matrix_layout(e.handle, &bo, &ro);
+            drops_b200_matrix_line_segments(e.handle, &ls);
+            drops_b200_matrix_segment_stream(e.handle, &ss, &se);
+            drops_b200_matrix_value_dictionary(e.handle, 0, &nd, &pk, &cb);
+            std::fprintf(stderr, "drops_b200 layout: rows %zu nnz %zu dictionary %d packed %d block_ordered %d row_ordered %d "
+                                 "line_segments %zu segment_slices %zu segment_entries %zu\n",
+                         (size_t)A.num_rows(), nnz, nd, pk, bo, ro, ls, ss, se);
         }
         e.version = A.Version(); e.rows = A.num_rows(); e.cols = A.num_cols(); e.nnz = nnz;
         e.val = A.raw_val(); e.col = A.raw_col(); e.row = A.raw_row();

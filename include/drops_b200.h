@@ -137,6 +137,10 @@ DROPS_B200_API int drops_b200_matrix_layout(drops_b200_matrix_t A, int* block_or
  * its lanes gathers 32 consecutive positions of the row-ordered x.  *n_segments = complete segments of A's operator
  * (0: no lines found, or A is not block ordered).  Never changes a result bit of A*x. */
 DROPS_B200_API int drops_b200_matrix_line_segments(drops_b200_matrix_t A, size_t* n_segments);
+/* The row order of the sliced-ELL operator: perm[32 * s + l] = row that lane l of slice s sums (-1: padding position);
+ * capacity >= 32 * nslices (drops_b200_matrix_format).  Position p of this order is entry p of the row-ordered vectors
+ * the solvers iterate on.  Introspection for tests and tools. */
+DROPS_B200_API int drops_b200_matrix_row_order(drops_b200_matrix_t A, int32_t* perm, size_t capacity);
 /* "sell.segments" (default on): slices of the row-ordered twin whose 32 rows are one line segment hold, entry by entry,
  * ONE dictionary index and columns that are at most two runs of consecutive positions; they are described by one 16-byte
  * record per entry-row instead of 32 packed words (0.5 instead of 4 bytes per stored entry) and run by the segment kernel

@@ -50,12 +50,18 @@ CASES = {
     "p2_pcg_jac":        (0, 3, 202, "device"),     # P2 elements, 254 016 unknowns as well
     "p1_pcg_chebyshev":  (1, 3, 207, "device"),     # PCGSolverCL<ChebyshevPcCL>
     "small_p1_pcg_ssor": (1, 2, 203, "reference template, products on the GPU"),   # out of scope: must keep working
+    # BrickBuilder with 40 cells per direction and NO refinement (the way a 185^3 mesh -- BASELINE configs[1] -- has to be
+    # built: 185 is not 4 * 2^k): DROPS numbers vertices lexicographically and edges cell by cell, so rows that are
+    # translates of each other are a few rows apart -- the matrix the line segments / segment descriptors are for
+    "p2_brick40_pcg_jac": (0, 0, 202, "device", 40),
 }
 
 
 def params(case):
-    p1, level, code, _ = CASES[case]
+    p1, level, code = CASES[case][:3]
     P = copy.deepcopy(BASE)
+    if len(CASES[case]) > 4:
+        P["Mesh"]["N1"] = P["Mesh"]["N2"] = P["Mesh"]["N3"] = CASES[case][4]
     P["Poisson"]["P1"] = p1
     P["Poisson"]["Solver"]["Solver"] = code
     P["Mesh"]["AdaptRef"]["FinestLevel"] = level
@@ -79,6 +85,9 @@ def run(variant, case, workdir, timeout=1200, env=None):
     # DROPS_B200_TRACE=1 (overlay binary): one stderr line per one-time cost and per solve
     rec["trace"] = {m.group(1).strip(): float(m.group(2))
                     for m in re.finditer(r"drops_b200 trace: (.*?) ([0-9.eE+-]+) s\n", r.stderr)}
+    # ... and one "drops_b200 layout:" line per uploaded operator
+    rec["layouts"] = [dict((k, int(v)) for k, v in re.findall(r"(\w+) (\d+)", m.group(1)))
+                      for m in re.finditer(r"drops_b200 layout: (.*)\n", r.stderr)]
     return r.stdout, rec
 
 

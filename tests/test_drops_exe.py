@@ -98,6 +98,42 @@ def test_overlay_binary_matches_the_reference(gpu, case, tmp_path):
 
 
 @pytest.mark.gpu
+def test_line_segments_on_a_matrix_drops_assembled_itself(gpu, tmp_path):
+    """The segment path is not a property of the synthetic generator: DROPS' own mesh (BrickBuilderCL, 40 cells per
+    direction, unrefined), numbering (misc/problem.cpp) and P2 assembly hand over a matrix in which 94 % of the rows have a
+    translate at most 8 rows away; with the size threshold lifted the overlay cuts it into line segments, runs most stored
+    entries from segment descriptors, and cdrdrops prints the reference's iteration count and discretisation error.
+    (The hierarchical numbering after uniform refinement -- case p2_pcg_jac -- has no such rows: the per-row graph blocks
+    and the packed kernel run there.)"""
+    ensure_built("b200")
+    env = dict(os.environ, DROPS_B200_TRACE="1", DROPS_B200_OPTIONS="sell.block_min_rows=0")
+    out, rec = cases.run("b200", "p2_brick40_pcg_jac", str(tmp_path), env=env)
+    g = golden()["p2_brick40_pcg_jac"]
+    assert rec["finished"] and rec["unknowns"] == g["unknowns"] and abs(rec["iterations"] - g["iterations"]) <= 1
+    assert abs(rec["l2_error"] - g["l2_error"]) <= 2e-6 * g["l2_error"]
+    lay = max(rec["layouts"], key=lambda l: l["rows"])
+    assert lay["rows"] == g["unknowns"] and lay["block_ordered"] == 1 and lay["row_ordered"] >= 1, lay
+    assert lay["line_segments"] * 32 >= 0.75 * lay["rows"], lay            # 82 % of the rows in complete segments at N = 40
+    # DROPS' assembly rounds: hundreds of distinct values where exact arithmetic has 21 -- no shared index per entry-row, so
+    # the one-word form keeps its packed words; the six-byte form (what C2 size needs: 26 column bits + 10 index bits)
+    # takes the segment records
+    assert lay["dictionary"] > 100, lay
+    env6 = dict(env, DROPS_B200_OPTIONS="sell.block_min_rows=0,sell.pack_bits=0")
+    out6, rec6 = cases.run("b200", "p2_brick40_pcg_jac", str(tmp_path / "six"), env=env6)
+    lay6 = max(rec6["layouts"], key=lambda l: l["rows"])
+    # (lines of 39 rows: every complete segment starts next to the boundary rows of its line, and an entry-row that meets
+    #  them is three runs, not two -- a fifth of the slices qualify here, most of them on a mesh with longer lines)
+    assert lay6["packed"] == 2 and lay6["row_ordered"] == 2 and lay6["segment_entries"] >= 0.1 * lay6["nnz"], lay6
+    assert rec6["finished"] and abs(rec6["iterations"] - g["iterations"]) <= 1
+    assert abs(rec6["l2_error"] - g["l2_error"]) <= 2e-6 * g["l2_error"]
+    # the refined-mesh numbering: no lines, graph blocks per row
+    out2, rec2 = cases.run("b200", "p2_pcg_jac", str(tmp_path / "refined"), env=env)
+    lay2 = max(rec2["layouts"], key=lambda l: l["rows"])
+    assert lay2["block_ordered"] == 1 and lay2["line_segments"] * 32 <= 0.05 * lay2["rows"], lay2
+    assert abs(rec2["iterations"] - golden()["p2_pcg_jac"]["iterations"]) <= 1
+
+
+@pytest.mark.gpu
 def test_overlay_binary_against_live_reference_binary(gpu, tmp_path):
     """Both binaries run side by side on this box (the ref one travels prebuilt)."""
     ensure_built("b200")
