@@ -683,6 +683,24 @@ def test_segment_records_with_value_indices(gpu, pkdict):
         _restore_pk(gpu)
 
 
+def test_polled_fetch_gives_the_same_solves(gpu):
+    """"fetch.poll": Hessenberg columns and Lanczos scalars published to mapped pinned memory and polled, against the copy +
+    stream synchronisation they replace -- the same bytes reach the host, so GMRES, MINRES and BiCGStab are bit for bit the same."""
+    g = load_golden("brick_fe2_N6_num1.npz")
+    A = gmat(gpu, g)
+    n = A.rows
+    try:
+        outs = []
+        for poll in (1, 0):
+            gpu.set_option("fetch.poll", poll)
+            outs.append((A.gmres_jacobi(np.zeros(n), g["b"], 20, 400, 1e-10, True, 1.0, True), A.minres(np.zeros(n), g["b"], 400, 1e-9),
+                         A.pminres_jacobi(np.zeros(n), g["b"], 400, 1e-9), A.bicgstab(np.zeros(n), g["b"], 400, 1e-10, True)))
+        for a, c in zip(*outs):
+            assert a[0] == c[0] and a[1] == c[1] and a[2] == c[2] and np.array_equal(a[3], c[3])
+    finally:
+        gpu.set_option("fetch.poll", 1)
+
+
 def test_segment_descriptors_on_the_12_byte_stream(gpu):
     """Variable coefficients on a structured mesh: the VALUES differ from row to row, the column structure is still
     translation invariant.  The twin of the int32 columns gets segment descriptors (0.5 instead of 4 bytes per column,
