@@ -297,7 +297,13 @@ k_spmv_sell_scv(SellView A, const double* __restrict__ x, double* __restrict__ y
         } else {
             sum = slice_row_sum<EXACT, U, false>(A, base, width, lane, x, e);
         }
-        if (nseg) scv_issue(A, sd_addr, nbase, nwidth, lane);
+        if (nseg) {
+            scv_issue(A, sd_addr, nbase, nwidth, lane);
+            // ... and L2 is asked for the next slice's values (two 128-byte lines per entry-row)
+            if (A.prefetch != 0)
+                for (int l = lane; l < 2 * nwidth; l += 32)
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(A.val + nbase + (size_t)l * 16));
+        }
         const double out = apply_epilogue<EPI>(sum, av, e, beta);
         y[row] = out;
         if (DOT) acc[0] = dd_add_prod(acc[0], out, dv);
@@ -411,7 +417,7 @@ int spmv_sell(const SellOp& A, const SpmvArgs& a)
     if (grid < 1) grid = 1;
     cudaStream_t st = a.stream ? a.stream : c.stream;
     SellView v{A.slice_ptr, a.row_ordered ? A.colp : A.col, A.val, a.row_ordered ? nullptr : A.perm, (long long)A.nslices,
-               use_sc ? A.scd : nullptr, use_sc ? A.sc : nullptr};
+               use_sc ? A.scd : nullptr, use_sc ? A.sc : nullptr, (int)opt("spmv.scv_prefetch", 1.0)};
     EpiArgs e = make_epi(a);
     launch_sell_epi<true>(v, a, e, (int)grid, threads, st);
     count_launch();

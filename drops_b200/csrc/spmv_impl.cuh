@@ -12,6 +12,7 @@ struct SellView {
     long long nslices;
     const uint4* scd = nullptr;     // segment descriptors of the row-ordered twin (SellOp::scd), nullptr: none
     const uint8_t* sc = nullptr;    // per slice: 1 = columns come from scd
+    int prefetch = 0;               // k_spmv_sell_scv: ask L2 for the next slice's values ("spmv.scv_prefetch")
 };
 
 struct EpiArgs {

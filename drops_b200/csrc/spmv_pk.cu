@@ -65,7 +65,7 @@ int spmv_sell_pk(const SellOp& A, const SpmvArgs& a)
     cudaStream_t st = a.stream ? a.stream : c.stream;
     PkView v{A.slice_ptr, six_ro ? A.colp : A.col, A.pk != nullptr ? nullptr : A.vidx, a.row_ordered ? A.pkp : A.pk, A.dict, a.row_ordered ? nullptr : A.perm, (long long)A.nslices,
              A.ndict, A.cbits, opt("spmv.pk_nopad", 1.0) != 0.0 ? A.pk_nopad : nullptr,
-             use_sc ? A.scd : nullptr, use_sc ? A.sc : nullptr,
+             (int)opt("spmv.sc_prefetch", 1.0), use_sc ? A.scd : nullptr, use_sc ? A.sc : nullptr,
              A.ndict_host == A.ndict ? A.ndict_host : 0, {}};
     if (v.cdict_n > 0) std::memcpy(v.cdict, A.dict_host, sizeof(double) * ((size_t)A.ndict_host + 1));
     EpiArgs e = make_epi(a);

@@ -22,6 +22,7 @@ struct PkView {
     int ndict;
     int cbits;
     const uint8_t* nopad;       // per slice: 1 = no padding word (nullptr: unknown, keep the selects)
+    int prefetch;               // k_spmv_sell_sci: ask L2 for the next slice's index stream ("spmv.sc_prefetch")
     const uint4* scd;           // segment descriptors of the row-ordered twin (SellOp::scd), nullptr: none
     const uint8_t* sc;          // per slice: 1 = run from scd
     int cdict_n;                // > 0: cdict holds the dictionary (values + padding slot)
@@ -309,6 +310,8 @@ k_spmv_sell_sc(const __grid_constant__ PkView A, const double* __restrict__ x, d
             sum = pk_row_sum<EXACT, U, false, false, true, true>(A, base, width, lane, x);
         }
         if (nseg) sc_issue(A, sd_addr, nbase, nwidth, lane);  // travels during the epilogue
+        else if (A.prefetch != 0)                             // a slice that keeps its packed words: L2 is asked for them
+            for (int l = lane; l < nwidth; l += 32) asm volatile("prefetch.global.L2 [%0];" :: "l"(A.pk + nbase + (size_t)l * 32));
         const double out = apply_epilogue<EPI>(sum, av, e, beta);
         y[row] = out;
         if (DOT) acc_smem[threadIdx.x] = dd_add_prod(acc_smem[threadIdx.x], out, __ldg(e.dotv + row));
@@ -437,7 +440,14 @@ k_spmv_sell_sci(const __grid_constant__ PkView A, const double* __restrict__ x, 
         } else {
             sum = pk6_row_sum<EXACT, 8, SMEM>(A, base, width, lane, x);      // int32 position (-1 = padding) + index per entry
         }
-        if (nseg) sc_issue(A, sd_addr, nbase, nwidth, lane);
+        if (nseg) {
+            sc_issue(A, sd_addr, nbase, nwidth, lane);
+            // ... and L2 is asked for the next slice's index stream (64 bytes per entry-row): its batches then wait for L2,
+            // not for HBM
+            if (A.prefetch != 0)
+                for (int l = lane; 2 * l < nwidth; l += 32)
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(A.vidx + nbase + (size_t)l * 64));
+        }
         const double out = apply_epilogue<EPI>(sum, av, e, beta);
         y[row] = out;
         if (DOT) acc[0] = dd_add_prod(acc[0], out, dv);
