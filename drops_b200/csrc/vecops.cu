@@ -862,14 +862,14 @@ int cg_direction(size_t n, double* dvec, const double* r, SolverScalars* S)
 // GMRES pieces
 // ------------------------------------------------------------------------------------------
 struct OpScaleInv {
-    double* out; const double* in; const double* scale; double inv;
-    __device__ bool begin() { inv = dvd(1.0, *scale); return true; }
+    double* out; const double* in; const double* scale; double inv; const int* done;
+    __device__ bool begin() { if (done != nullptr && *done != 0) return false; inv = dvd(1.0, *scale); return true; }
     __device__ void elem(size_t i, dd*) { out[i] = mul(in[i], inv); }
     __device__ void finish(const dd*) {}
 };
-int vec_scale_inv(size_t n, double* out, const double* in, const double* d_scale)
+int vec_scale_inv(size_t n, double* out, const double* in, const double* d_scale, const int* done)
 {
-    return launch_stream<0>(n, OpScaleInv{out, in, d_scale, 0.0}, "vec");
+    return launch_stream<0>(n, OpScaleInv{out, in, d_scale, 0.0, done}, "vec");
 }
 
 template <bool PREV, bool NORM>
@@ -932,8 +932,9 @@ constexpr int kCgsMaxVec = 512;
 
 __global__ void __launch_bounds__(256)
 k_cgs_dots(size_t n, const double* __restrict__ w, const double* const* __restrict__ v, int nv, dd* partials,
-           unsigned* ticket, double* h_out, dd* part_out)
+           unsigned* ticket, double* h_out, dd* part_out, const int* done)
 {
+    if (done != nullptr && *done != 0) return;
     __shared__ double wt[kCgsTile];
     __shared__ dd acc[kCgsMaxVec];
     __shared__ bool is_last;
@@ -987,7 +988,7 @@ k_cgs_dots(size_t n, const double* __restrict__ w, const double* const* __restri
     if (threadIdx.x == 0) *ticket = 0u;
 }
 
-int cgs_dots(size_t n, const double* w, const double* const* d_vptrs, int nv, double* d_h, dd* part_out)
+int cgs_dots(size_t n, const double* w, const double* const* d_vptrs, int nv, double* d_h, dd* part_out, const int* done)
 {
     DB_ARG(nv >= 1 && nv <= kCgsMaxVec, "classical Gram-Schmidt: more basis vectors than the kernel holds accumulators for");
     Ctx& c = ctx();
@@ -998,7 +999,7 @@ int cgs_dots(size_t n, const double* w, const double* const* d_vptrs, int nv, do
     long long grid = std::min<long long>((long long)std::max<size_t>(ntiles, 1), (n >= ((size_t)1 << 22) ? 8LL : 2LL) * c.sm_count);
     grid = std::min<long long>(grid, kPartialStride / nv);
     k_cgs_dots<<<(int)grid, 256, 0, c.stream>>>(n, w, d_vptrs, nv, c.partials + (size_t)1 * kPartialStride,
-                                                c.tickets + (size_t)1 * kTicketStride, d_h, part_out);
+                                                c.tickets + (size_t)1 * kTicketStride, d_h, part_out, done);
     count_launch();
     DB_CUDA(cudaGetLastError());
     return 0;
@@ -1006,8 +1007,8 @@ int cgs_dots(size_t n, const double* w, const double* const* d_vptrs, int nv, do
 
 // w -= h_k v_k for k = 0 .. nv-1 in that order (the loop of :492-493), then *d_norm = |w|_2 (:383 / :868)
 struct OpCgsUpdate {
-    double* w; const double* const* v; const double* h; int nv; double* norm_out; dd* part_out;
-    __device__ bool begin() { return true; }
+    double* w; const double* const* v; const double* h; int nv; double* norm_out; dd* part_out; const int* done;
+    __device__ bool begin() { return !(done != nullptr && *done != 0); }
     __device__ void elem(size_t i, dd* acc)
     {
         double wi = w[i];
@@ -1027,9 +1028,76 @@ struct OpCgsUpdate {
         *norm_out = sqrt(dd_round(acc[0]));
     }
 };
-int cgs_update(size_t n, double* w, const double* const* d_vptrs, const double* d_h, int nv, double* d_norm, dd* part_out)
+int cgs_update(size_t n, double* w, const double* const* d_vptrs, const double* d_h, int nv, double* d_norm, dd* part_out,
+               const int* done)
 {
-    return launch_stream<1>(n, OpCgsUpdate{w, d_vptrs, d_h, nv, d_norm, part_out}, "gmres.cgs");
+    return launch_stream<1>(n, OpCgsUpdate{w, d_vptrs, d_h, nv, d_norm, part_out, done}, "gmres.cgs");
+}
+
+// Givens rotations of one GMRES column on the device (krylovsolver.h:258-279, :385-393): the new column h[0 .. i+1] gets the
+// i rotations of the earlier columns, a new rotation zeroes h[i+1], the right-hand side s follows; the rotated column is
+// kept in H (column-major, ld = m) for the back substitution on the host, the residual estimate |s[i+1]| / normb decides
+// whether the solve stops.  The same operations in the same order as the host loop, rounded one by one (no contraction):
+// the same bits.  Thread 0 of block 0 runs the dependent chain out of shared memory.
+// It rides on the kernel that scales the new basis vector, v_{i+1} = w / h_{i+1,i}: block 0 rotates the column while the
+// grid scales (one launch less per step: on 10^5 rows every launch is a sixth of the step).  A block that sees the stop
+// flag raised by block 0 of this very launch skips a vector nobody reads any more.
+__global__ void __launch_bounds__(256)
+k_gmres_scale_givens(size_t n, double* __restrict__ out, const double* __restrict__ in, int i, int m, const double* __restrict__ h,
+                     double* __restrict__ cs, double* __restrict__ sn, double* __restrict__ s, double* __restrict__ H, GmresCtrl* ctrl)
+{
+    if (ctrl->done != 0) return;
+    const double inv = dvd(1.0, h[i + 1]);
+    if (blockIdx.x == 0) {
+        extern __shared__ double sm[];
+        double* col = sm;
+        double* cc = sm + (i + 2);
+        double* ss = cc + i;
+        for (int k = threadIdx.x; k <= i + 1; k += blockDim.x) col[k] = h[k];
+        for (int k = threadIdx.x; k < i; k += blockDim.x) { cc[k] = cs[k]; ss[k] = sn[k]; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int k = 0; k < i; ++k) {
+                const double dx = col[k], dy = col[k + 1];
+                col[k] = __dadd_rn(__dmul_rn(cc[k], dx), __dmul_rn(ss[k], dy));
+                col[k + 1] = __dadd_rn(__dmul_rn(-ss[k], dx), __dmul_rn(cc[k], dy));
+            }
+            double c1, s1;
+            const double dx = col[i], dy = col[i + 1];
+            if (dy == 0.0) { c1 = 1.0; s1 = 0.0; }
+            else {
+                const double r = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                c1 = __ddiv_rn(dx, r); s1 = __ddiv_rn(dy, r);
+            }
+            col[i] = __dadd_rn(__dmul_rn(c1, dx), __dmul_rn(s1, dy));
+            col[i + 1] = __dadd_rn(__dmul_rn(-s1, dx), __dmul_rn(c1, dy));
+            cs[i] = c1; sn[i] = s1;
+            const double sx = s[i], sy = s[i + 1];
+            s[i] = __dadd_rn(__dmul_rn(c1, sx), __dmul_rn(s1, sy));
+            const double s_next = __dadd_rn(__dmul_rn(-s1, sx), __dmul_rn(c1, sy));
+            s[i + 1] = s_next;
+            const double resid = __ddiv_rn(fabs(s_next), ctrl->normb);
+            ctrl->resid = resid;
+            ctrl->steps = i + 1;
+            if (resid <= ctrl->tol) ctrl->done = 1;
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k <= i + 1 && k < m; k += blockDim.x) H[(size_t)i * m + k] = col[k];
+    }
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) out[e] = mul(in[e], inv);
+}
+
+int gmres_scale_givens(size_t n, double* out, const double* in, int i, int m, const double* d_h, double* d_cs, double* d_sn,
+                       double* d_s, double* d_H, GmresCtrl* ctrl)
+{
+    Ctx& c = ctx();
+    ScopedTiming t("vec");
+    const int grid = vec_grid(n, 256, 4);
+    k_gmres_scale_givens<<<grid, 256, (size_t)(3 * i + 4) * sizeof(double), c.stream>>>(n, out, in, i, m, d_h, d_cs, d_sn, d_s, d_H, ctrl);
+    count_launch();
+    DB_CUDA(cudaGetLastError());
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------

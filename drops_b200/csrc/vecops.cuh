@@ -97,7 +97,7 @@ int cg_direction(size_t n, double* dvec, const double* r, SolverScalars* S);
 
 // ---- GMRES building blocks (num/krylovsolver.h:320-461) -------------------------------------------
 // out = in * (1/(*d_scale))                                                      :366, :384
-int vec_scale_inv(size_t n, double* out, const double* in, const double* d_scale);
+int vec_scale_inv(size_t n, double* out, const double* in, const double* d_scale, const int* done = nullptr);
 // if vprev: w -= (*d_hprev) * vprev.  Then *d_hout = dot(w, vk) (vk != null) or |w|_2 (vk == null).
 // part_out != nullptr (partitioned system): the local double-double partial of the reduction goes to
 // *part_out unrounded (for the norm: of w.w, without the sqrt) and d_hout is not written.
@@ -109,10 +109,17 @@ int multi_axpy(size_t n, double* x, const double* const* d_vptrs, const double* 
 // Classical Gram-Schmidt (StandardGramSchmidt :465-494, the reference's ModGMRES default :862-866):
 // d_h[k] = dot(w, v_k), k < nv, all against the unmodified w in ONE pass (part_out != nullptr: unrounded local
 // partials part_out[k] instead, for a partitioned system) ...
-int cgs_dots(size_t n, const double* w, const double* const* d_vptrs, int nv, double* d_h, dd* part_out = nullptr);
+int cgs_dots(size_t n, const double* w, const double* const* d_vptrs, int nv, double* d_h, dd* part_out = nullptr,
+             const int* done = nullptr);
 // ... then w -= d_h[k] v_k for k = 0..nv-1 in that order and *d_norm = |w|_2 (part_out: local partial of w.w)
 int cgs_update(size_t n, double* w, const double* const* d_vptrs, const double* d_h, int nv, double* d_norm,
-               dd* part_out = nullptr);
+               dd* part_out = nullptr, const int* done = nullptr);
+// Device-side Givens step of GMRES column i ("gmres.device_givens"): see k_gmres_scale_givens.  done stays the first member:
+// the kernels of later steps take &ctrl->done as their stop flag.
+struct GmresCtrl { int done; int steps; double resid; double normb; double tol; };
+// v_{i+1} = w / h_{i+1,i} and the Givens step of column i in one launch
+int gmres_scale_givens(size_t n, double* out, const double* in, int i, int m, const double* d_h, double* d_cs, double* d_sn,
+                       double* d_s, double* d_H, GmresCtrl* ctrl);
 
 // ---- MINRES building blocks (num/krylovsolver.h:926-1152) ----------------------------------------
 // q2 -= (*d_a1) * q1;  *d_b1 = |q2|_2                                           :933-934

@@ -683,6 +683,36 @@ def test_segment_records_with_value_indices(gpu, pkdict):
         _restore_pk(gpu)
 
 
+@pytest.mark.parametrize("m,left,maxit", [(8, True, 400), (30, False, 400), (200, True, 400), (30, True, 17), (12, True, 12)])
+def test_gmres_device_side_givens_keeps_every_bit(gpu, m, left, maxit):
+    """"gmres.device_givens" (classical Gram-Schmidt path): the rotations of every column run in a one-block kernel and the
+    host enqueues the steps of a cycle without waiting for the columns.  The same operations in the same order: iteration
+    count, residual and solution of the host-driven loop, bit for bit -- through restarts, at convergence inside a chunk,
+    and when max_iter ends the solve."""
+    n, rb, ci, va = gpu.brick_csr_host(2, 12, 1, 1.1)
+    rows = np.repeat(np.arange(n), np.diff(rb.astype(np.int64)))
+    va = va.copy()
+    va[ci.astype(np.int64) == rows] *= 1.05
+    xs = gpu.brick_solution_host(2, 12, 1)
+    G = gpu.Matrix(n, n, rb, ci, va)
+    b = G.spmv(xs)
+    try:
+        gpu.set_option("gmres.ortho", 1)
+        outs = []
+        for dg, chunk in ((0, 8), (1, 8), (1, 1), (1, 5)):
+            gpu.set_option("gmres.device_givens", dg)
+            gpu.set_option("gmres.check_every", chunk)
+            outs.append(G.gmres_jacobi(np.zeros(n), b, m, maxit, 1e-10, True, 1.0, left))
+        for o in outs[1:]:
+            assert o[0] == outs[0][0] and o[1] == outs[0][1] and o[2] == outs[0][2] and np.array_equal(o[3], outs[0][3]), (o[:3], outs[0][:3])
+        if maxit == 400:
+            assert outs[0][0] and rel(outs[0][3], xs) <= 1e-7
+    finally:
+        gpu.set_option("gmres.ortho", 0)
+        gpu.set_option("gmres.device_givens", 1)
+        gpu.set_option("gmres.check_every", 8)
+
+
 def test_polled_fetch_gives_the_same_solves(gpu):
     """"fetch.poll": Hessenberg columns and Lanczos scalars published to mapped pinned memory and polled, against the copy +
     stream synchronisation they replace -- the same bytes reach the host, so GMRES, MINRES and BiCGStab are bit for bit the same."""
