@@ -1048,6 +1048,7 @@ def run_ours_dist(args, rank, world, local, dist):
         solve_dev()
     capi.set_option("timing", 1)
     capi.timing_reset()
+    A.wait_stats(reset=True)
     sampler = ClockSampler(local)
     sampler.start()
     capi.synchronize()
@@ -1061,6 +1062,16 @@ def run_ours_dist(args, rank, world, local, dist):
     torch.cuda.synchronize()
     dist.barrier()
     ms = tmax(ms_local)
+    # how long every rank waited for its peers at the three sync points of an iteration (measured inside the waiting
+    # kernels: kernel start -> last peer's sequence number), microseconds per iteration, one entry per rank
+    ws = A.wait_stats()
+    wt = torch.tensor([ws[k][0] / max(args.steps * iters, 1) for k in ("halo", "reduce_pAp", "reduce_rho_resid")],
+                      dtype=torch.float64, device="cuda")
+    wall_ = [torch.zeros_like(wt) for _ in range(world)]
+    dist.all_gather(wall_, wt)
+    peer_wait = {"unit": "us per iteration, per rank", "halo": [round(t[0].item(), 2) for t in wall_],
+                 "reduce_pAp": [round(t[1].item(), 2) for t in wall_], "reduce_rho_resid": [round(t[2].item(), 2) for t in wall_],
+                 "iteration_us": 1e3 * ms / max(args.steps * iters, 1)}
     launches = tsum(capi.launch_count() - l0)
     clocks = sampler.stop()
     t_int, c_int = capi.timing("spmv")
@@ -1154,7 +1165,7 @@ def run_ours_dist(args, rank, world, local, dist):
                        "cache": "per-GPU inputs (17 GB matrix, 0.4 GB vectors) far exceed the 126 MB L2; no flush needed",
                        "partition": {"ghost_entries_total": ghosts, "rank0": info, "rank0_format": fmt}, "generate_s": gen_s},
             "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "final_relative_residual": resid, "dist_parity": dist_parity,
+            "final_relative_residual": resid, "dist_parity": dist_parity, "peer_wait": peer_wait,
         }
         print(json.dumps(line), flush=True)
     dist.barrier()

@@ -145,6 +145,7 @@ SIGNATURES = {
     "drops_b200_dist_dot": (_i, [_i, _vpp, _vpp, _vpp, _dpp]),
     "drops_b200_dist_pcg_dev": (_i, [_i, _vpp, _vpp, _vpp, _i, _d, _ip, _dpp, _i, _vp, _i]),
     "drops_b200_dist_matrix_segment_stream": (_i, [_vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "drops_b200_dist_matrix_wait_stats": (_i, [_vp, _dp, _i]),
     "drops_b200_dist_gmres_dev": (_i, [_i, _vpp, _vpp, _vpp, _i, _d, _i, _ip, _dpp, _i, _i]),
     "drops_b200_dist_minres_dev": (_i, [_i, _vpp, _vpp, _vpp, _i, _i, _d, _ip, _dpp, _i]),
     "drops_b200_brick_slab_generate": (_i, [_i, _i, _i, _d, _i, _i, _vpp]),
@@ -878,6 +879,13 @@ class DistMatrix:
         a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
         check(lib().drops_b200_dist_matrix_segment_stream(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return {"segment_slices": a.value, "segment_entries": b.value, "interior_padded_entries": c.value}
+
+    def wait_stats(self, reset=False):
+        """Time spent waiting for peers inside the iteration: {point: (microseconds, waits)} (drops_b200_dist_matrix_wait_stats)."""
+        o = np.zeros(8)
+        check(lib().drops_b200_dist_matrix_wait_stats(self.h, o, 1 if reset else 0))
+        names = ["halo", "reduce_pAp", "reduce_rho_resid", "reduce_other"]
+        return {nm: (o[2 * k] / 1e3, int(o[2 * k + 1])) for k, nm in enumerate(names)}
 
     def diag(self):
         d = np.zeros(max(self.info()["n_owned"], 1))

@@ -220,11 +220,20 @@ k_pack_push(long long n_send, const int32_t* __restrict__ idx, const double* __r
     }
 }
 
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 // Consumer side: one lane per sender spins (bounded) until that sender's sequence number has arrived.
+// stat (nullable): {nanoseconds this rank spent in the wait, number of waits} (drops_b200_dist_matrix_wait_stats).
 __global__ void k_halo_wait(int world, const unsigned* flags, const unsigned char* __restrict__ expect, unsigned seq,
-                            const int* done, int* fault)
+                            const int* done, int* fault, unsigned long long* stat)
 {
     if (done != nullptr && *done != 0) return;
+    const unsigned long long t0 = (stat != nullptr && threadIdx.x == 0) ? global_ns() : 0ull;
     const int q = threadIdx.x;
     if (q < world && expect[q]) {
         unsigned long long spins = 0;
@@ -234,6 +243,10 @@ __global__ void k_halo_wait(int world, const unsigned* flags, const unsigned cha
         }
     }
     __threadfence_system();
+    if (stat != nullptr) {
+        __syncthreads();
+        if (threadIdx.x == 0) { stat[0] += global_ns() - t0; stat[1] += 1ull; }
+    }
 }
 
 // peer-to-peer all-gather of reduction partials: my nq partials go into slot `me` of the current parity half
@@ -261,10 +274,11 @@ enum ScalarPhase { PH_DOT = 0, PH_LAMBDA = 1, PH_SETUP = 2, PH_UPDATE = 3, PH_NO
 // Sums the ranks' partials in rank order (the same on every rank) and does the scalar bookkeeping
 // that the last block of the fused kernels does on a single GPU.
 __global__ void k_dist_scalars(int phase, SolverScalars* S, double* hist, const dd* gathered, int world,
-                               double* out, const unsigned* flags, unsigned seq, int* fault)
+                               double* out, const unsigned* flags, unsigned seq, int* fault, unsigned long long* stat)
 {
     if ((phase == PH_LAMBDA || phase == PH_UPDATE) && S->done) return;
     if (flags != nullptr) {                          // peer path: wait (bounded) for every rank's sequence number
+        const unsigned long long t0 = (stat != nullptr && threadIdx.x == 0) ? global_ns() : 0ull;
         const int q = threadIdx.x;
         if (q < world) {
             unsigned long long spins = 0;
@@ -275,6 +289,10 @@ __global__ void k_dist_scalars(int phase, SolverScalars* S, double* hist, const 
         }
         __threadfence_system();
         __syncthreads();
+        if (stat != nullptr && threadIdx.x == 0) {   // slots: 2 = the p.Ap reduction, 4 = the (rho, residual) pair, 6 = others
+            const int slot = phase == PH_LAMBDA ? 2 : (phase == PH_UPDATE ? 4 : 6);
+            stat[slot] += global_ns() - t0; stat[slot + 1] += 1ull;
+        }
         // a peer never showed up: its partial is stale.  Stop iterating on this rank (every later kernel of the
         // solve returns on S->done) and leave the sticky fault flag for the host, which turns it into
         // DROPS_B200_E_COMM (check_p2p_faults) instead of a plausible-looking residual.
@@ -430,7 +448,7 @@ static void free_dist_matrix(drops_b200_dist_matrix_s* M)
     free_sell(M->sell_int); free_sell(M->sell_bnd); free_sell(M->sell_bnd_ro);
     dev_free(M->ro_perm); dev_free(M->diag_ro); dev_free(M->d_send_idx_ro); dev_free(M->diag_ro_idx);
     for (void* m : M->ipc_mapped) cudaIpcCloseMemHandle(m);
-    dev_free(M->p2p_ticket); dev_free(M->p2p_fault); dev_free(M->d_peer_dst); dev_free(M->d_peer_flag);
+    dev_free(M->p2p_ticket); dev_free(M->p2p_fault); dev_free(M->wait_stats); dev_free(M->d_peer_dst); dev_free(M->d_peer_flag);
     dev_free(M->d_send_off); dev_free(M->d_expect);
     dev_free(M->diag); dev_free(M->ghost); dev_free(M->sendbuf); dev_free(M->d_send_idx);
     for (double* w : M->work) dev_free(w);
@@ -796,6 +814,10 @@ static int p2p_finish(drops_b200_dist_matrix_s* M, const std::vector<double*>& g
     DB_CHECK(dev_alloc(&M->d_peer_dst, (size_t)world)); DB_CHECK(dev_alloc(&M->d_peer_flag, (size_t)world));
     DB_CHECK(dev_alloc(&M->d_send_off, (size_t)world + 1)); DB_CHECK(dev_alloc(&M->d_expect, (size_t)world));
     DB_CHECK(dev_alloc(&M->p2p_ticket, 1)); DB_CHECK(dev_alloc(&M->p2p_fault, 1));
+    if (opt("dist.wait_stats", 1.0) != 0.0 && !M->wait_stats) {
+        DB_CHECK(dev_alloc(&M->wait_stats, 8));
+        DB_CUDA(cudaMemsetAsync(M->wait_stats, 0, 8 * sizeof(unsigned long long), st));
+    }
     DB_CUDA(cudaMemcpyAsync(M->d_peer_dst, dst.data(), (size_t)world * sizeof(double*), cudaMemcpyHostToDevice, st));
     DB_CUDA(cudaMemcpyAsync(M->d_peer_flag, flg.data(), (size_t)world * sizeof(unsigned*), cudaMemcpyHostToDevice, st));
     DB_CUDA(cudaMemcpyAsync(M->d_send_off, M->send_off.data(), ((size_t)world + 1) * sizeof(size_t), cudaMemcpyHostToDevice, st));
@@ -993,7 +1015,7 @@ static int dist_spmv_run(int np, drops_b200_dist_matrix_s* const* P, const PartA
                 drops_b200_dist_matrix_s* M = P[p];
                 if (M->n_ghost == 0) continue;
                 k_halo_wait<<<1, std::max(32, (M->world + 31) / 32 * 32), 0, cs>>>(M->world, M->halo_flags, M->d_expect, M->p2p_seq,
-                                                                                 a[p].done, M->p2p_fault);
+                                                                                 a[p].done, M->p2p_fault, M->wait_stats);
                 count_launch();
             }
             DB_CUDA(cudaGetLastError());
@@ -1028,7 +1050,7 @@ static int dist_spmv_run(int np, drops_b200_dist_matrix_s* const* P, const PartA
             drops_b200_dist_matrix_s* M = P[p];
             if (M->n_ghost == 0) continue;
             k_halo_wait<<<1, std::max(32, (M->world + 31) / 32 * 32), 0, st>>>(M->world, M->halo_flags, M->d_expect, M->p2p_seq,
-                                                                             a[p].done, M->p2p_fault);
+                                                                             a[p].done, M->p2p_fault, M->wait_stats);
             count_launch();
         }
         DB_CUDA(cudaGetLastError());
@@ -1071,9 +1093,9 @@ static int scalars_kernel(int phase, drops_b200_dist_matrix_s* M, double* hist, 
     if (C->red_last_p2p)
         k_dist_scalars<<<1, std::max(32, (M->world + 31) / 32 * 32), 0, ctx().stream>>>(
             phase, (SolverScalars*)M->d_scalars, hist, C->red_buf + (size_t)(C->red_seq & 1u) * M->world * kMaxQ, M->world, out,
-            C->red_flags, C->red_seq, C->red_fault);
+            C->red_flags, C->red_seq, C->red_fault, M->wait_stats);
     else
-        k_dist_scalars<<<1, 32, 0, ctx().stream>>>(phase, (SolverScalars*)M->d_scalars, hist, C->gathered, M->world, out, nullptr, 0u, nullptr);
+        k_dist_scalars<<<1, 32, 0, ctx().stream>>>(phase, (SolverScalars*)M->d_scalars, hist, C->gathered, M->world, out, nullptr, 0u, nullptr, nullptr);
     count_launch();
     DB_CUDA(cudaGetLastError());
     return 0;
@@ -1991,6 +2013,21 @@ int drops_b200_dist_matrix_format(drops_b200_dist_matrix_t A, int* interior_pack
     if (interior_packed && A->sell_int.scd != nullptr && A->npos > 0 && opt("spmv.segments", 1.0) != 0.0)
         *interior_packed |= 256;                     // interior rows run from segment descriptors (SellOp::scd)
     if (n_distinct) *n_distinct = A->sell_int.ndict;
+    return 0;
+}
+
+int drops_b200_dist_matrix_wait_stats(drops_b200_dist_matrix_t A, double* out8, int reset)
+{
+    DB_CHECK(require_ctx());
+    DB_ARG(A != nullptr && out8 != nullptr, "null argument");
+    for (int k = 0; k < 8; ++k) out8[k] = 0.0;
+    if (!A->wait_stats) return 0;                    // no peer path on this partition: nothing waits inside a kernel
+    unsigned long long h[8];
+    DB_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (A->comm && A->comm->comm_stream) DB_CUDA(cudaStreamSynchronize(A->comm->comm_stream));
+    DB_CUDA(cudaMemcpy(h, A->wait_stats, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 8; ++k) out8[k] = (double)h[k];
+    if (reset) DB_CUDA(cudaMemset(A->wait_stats, 0, sizeof(h)));
     return 0;
 }
 

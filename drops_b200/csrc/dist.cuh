@@ -100,6 +100,7 @@ struct drops_b200_dist_matrix_s {
     size_t halo_flag_offset = 0;             // byte offset of halo_flags inside the ghost allocation
     unsigned* p2p_ticket = nullptr;
     int* p2p_fault = nullptr;                // a wait timed out
+    unsigned long long* wait_stats = nullptr;   // 4 x {ns, count}: halo wait, p.Ap reduction, (rho, residual) reduction, other reductions
     double** d_peer_dst = nullptr;           // world entries: where my entries for q land (q's ghost + offset)
     unsigned** d_peer_flag = nullptr;        // world entries: my slot in q's flag array
     size_t* d_send_off = nullptr;            // world + 1

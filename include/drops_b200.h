@@ -420,6 +420,11 @@ DROPS_B200_API int drops_b200_dist_matrix_format(drops_b200_dist_matrix_t A, int
  * entries of that operator incl. padding. */
 DROPS_B200_API int drops_b200_dist_matrix_segment_stream(drops_b200_dist_matrix_t A, size_t* n_slices, size_t* n_entries,
                                                          size_t* padded_entries);
+/* Time this partition spent waiting for its peers inside the iteration (peer-to-peer path only; zeros otherwise):
+ * out8 = 4 x {nanoseconds, number of waits} for the halo wait before the boundary rows, the p.Ap reduction, the
+ * (rho, residual) reduction of PCG and all other reductions.  A wait is the time between the start of the waiting
+ * kernel and the arrival of the last peer's sequence number; reset != 0 clears the counters.  "dist.wait_stats" (1). */
+DROPS_B200_API int drops_b200_dist_matrix_wait_stats(drops_b200_dist_matrix_t A, double* out8, int reset);
 DROPS_B200_API int drops_b200_dist_matrix_diag(drops_b200_dist_matrix_t A, double* diag);
 
 /* Collective operations.  `nparts` partitions driven by this process: 1 with an NCCL communicator

@@ -87,6 +87,13 @@ def main():
             assert all(torch.equal(a, t) for a in tl)
         fmt = A.format()
         assert not fmt["p2p_fault"]
+        ws = A.wait_stats()
+        if fmt["p2p"] and world > 1:            # every halo exchange and every reduction of the solves above was counted
+            assert ws["halo"][1] > 0 and ws["halo"][0] >= 0.0, ws
+        if fmt["p2p_reduce"] and world > 1:
+            assert ws["reduce_pAp"][1] >= it and ws["reduce_rho_resid"][1] >= it and ws["reduce_other"][1] > 0, ws
+            A.wait_stats(reset=True)
+            assert A.wait_stats()["reduce_pAp"] == (0.0, 0)
         if fmt["p2p"]:                          # the same solve with the halo over ncclSend/ncclRecv: same bits
             capi.set_option("dist.p2p", 0); capi.set_option("dist.p2p_reduce", 0)
             x1 = capi.Vector(owned.size)

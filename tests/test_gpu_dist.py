@@ -268,6 +268,13 @@ def test_brick_slabs_match_single_gpu(gpu, fe, N, numbering, world):
     assert rel(x, ref[3]) <= 1e-10
     k = min(it, ref[1])
     assert np.allclose(hist[:k + 1], ref[4][:k + 1], rtol=1e-6, atol=1e-15)
+    # peer waits are only counted on the peer-to-peer path; the call itself works on every partition
+    for m in mats:
+        ws = m.wait_stats()
+        assert set(ws) == {"halo", "reduce_pAp", "reduce_rho_resid", "reduce_other"}
+        assert all(v[0] >= 0.0 and v[1] >= 0 for v in ws.values())
+        if m.format()["p2p_reduce"] and world > 1:
+            assert ws["reduce_pAp"][1] >= it
 
 
 @pytest.mark.parametrize("world", [2, 3])
