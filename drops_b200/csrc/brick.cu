@@ -270,11 +270,12 @@ __global__ void k_brick_xstar(BrickGeom g, long long n, double* __restrict__ x)
 // slabs have one face where the others have two: with an even split they idle at every reduction (8 GPUs, measured
 // inside the waiting kernels: 170 of 1955 us per iteration).  "brick.face_weight" = w counts a face as w planes: every
 // rank gets the same planes + w * faces, i.e. the end slabs a few more planes (4 GPUs, w = 0 -> 6: waits of the end
-// slabs 166 / 77 -> 20 / 32 us, 2088 -> 2134 C2-equivalent it/s; the inner slabs then wait a little longer than the
-// end slabs, hence 5).  w = 0: the even split.
+// slabs 166 / 77 -> 20 / 32 us, 2088 -> 2134 C2-equivalent it/s; 8 GPUs: 4050 -> 4053, there the P2 slabs of 91 planes
+// alternate between starting on an even and on an odd plane and the waits alternate with them, profiles/r02_notes.md
+// section 12).  w = 0: the even split.
 static inline long long slab_begin(long long M, int world, int r)
 {
-    const long long w1000 = world > 2 ? (long long)(opt("brick.face_weight", 5.0) * 1000.0 + 0.5) : 0;
+    const long long w1000 = world > 2 ? (long long)(opt("brick.face_weight", 6.0) * 1000.0 + 0.5) : 0;
     if (r <= 0) return 1;
     if (w1000 <= 0) return 1 + M * r / world;
     const long long units = 1000 * M + w1000 * (2LL * world - 2);          // milli-planes incl. the faces

@@ -164,3 +164,30 @@ def test_documented_options_exist_in_the_source():
             cands = [base + p for p in parts]
         missing += [c for c in cands if '"%s"' % c not in src]
     assert not missing, missing
+
+
+def test_slab_split_counts_a_cut_face_as_planes():
+    """"brick.face_weight": the end slabs of a z-slab partition have one cut face, the others two; the split gives every
+    rank the same planes + w * faces.  0 = the even split; two ranks (one face each) are always even.  Host code: no GPU."""
+    from drops_b200 import capi as gpu
+    fe, N, world = 1, 40, 4
+    n, _ = gpu.brick_sizes(fe, N)
+    M = round(n ** (1.0 / 3.0))                      # interior lattice planes (Dirichlet boundary removed)
+    assert M ** 3 == n
+    gids = np.arange(n, dtype=np.int64)
+    try:
+        planes = {}
+        for w in (0.0, 5.0):
+            gpu.set_option("brick.face_weight", w)
+            own = gpu.brick_owner(fe, N, 0, world, gids)
+            assert np.all(np.diff(own) >= 0) and own[0] == 0 and own[-1] == world - 1
+            cnt = np.bincount(own, minlength=world)
+            assert np.all(cnt % (M * M) == 0)
+            planes[w] = (cnt // (M * M)).tolist()
+            two = np.bincount(gpu.brick_owner(fe, N, 0, 2, gids), minlength=2) // (M * M)
+            assert abs(int(two[0]) - int(two[1])) <= 1
+        assert max(planes[0.0]) - min(planes[0.0]) <= 1
+        p = planes[5.0]
+        assert sum(p) == M and min(p[0], p[-1]) >= max(p[1:-1]) + 3 and max(p[1:-1]) - min(p[1:-1]) <= 1, p
+    finally:
+        gpu.set_option("brick.face_weight", 6.0)
