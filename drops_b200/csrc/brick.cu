@@ -270,10 +270,8 @@ __global__ void k_brick_xstar(BrickGeom g, long long n, double* __restrict__ x)
 // slabs have one face where the others have two: with an even split they idle at every reduction (8 GPUs, measured
 // inside the waiting kernels: 170 of 1955 us per iteration).  "brick.face_weight" = w counts a face as w planes: every
 // rank gets the same planes + w * faces, i.e. the end slabs a few more planes (4 GPUs, w = 0 -> 6: waits of the end
-// slabs 166 / 77 -> 20 / 32 us, 2088 -> 2134 C2-equivalent it/s; 8 GPUs: 4050 -> 4053, there the P2 slabs of 91 planes
-// alternate between starting on an even and on an odd plane and the waits alternate with them, profiles/r02_notes.md
-// section 12).  w = 0: the even split.
-static inline long long slab_begin(long long M, int world, int r)
+// slabs 166 / 77 -> 20 / 32 us, 2088 -> 2134 C2-equivalent it/s).  w = 0: the even split.
+static inline long long slab_begin(long long M, int world, int r, int fe)
 {
     const long long w1000 = world > 2 ? (long long)(opt("brick.face_weight", 6.0) * 1000.0 + 0.5) : 0;
     if (r <= 0) return 1;
@@ -281,14 +279,20 @@ static inline long long slab_begin(long long M, int world, int r)
     const long long units = 1000 * M + w1000 * (2LL * world - 2);          // milli-planes incl. the faces
     if (units / world - 2 * w1000 < 2000) return 1 + M * r / world;        // slabs of a few planes: nothing to balance
     const long long before = (long long)r * units / world - w1000 * (2LL * r - 1);
-    return 1 + before / 1000;
+    long long b = 1 + before / 1000;
+    // P2: rows of even lattice planes reach two planes, rows of odd planes one, so a slab with an odd number of planes has
+    // 2 boundary + 4 ghost planes or 4 + 2, alternating from rank to rank, and the ranks with 4 boundary planes are 130 us
+    // per iteration behind (8 GPUs, 91-plane slabs, r02_notes.md section 12).  Cut above even planes only -- between
+    // element layers, where DROPS' element-wise partition cuts -- and every inner slab has 3 + 3.
+    if (fe == 2 && (b & 1) == 0) b += 1;
+    return b;
 }
 
-static inline int slab_owner(long long M, int world, long long k)
+static inline int slab_owner(long long M, int world, long long k, int fe)
 {
     int r = (int)(((k - 1) * world) / M);          // first guess, then walk to the slab that holds k
-    while (r > 0 && k < slab_begin(M, world, r)) --r;
-    while (r + 1 < world && k >= slab_begin(M, world, r + 1)) ++r;
+    while (r > 0 && k < slab_begin(M, world, r, fe)) --r;
+    while (r + 1 < world && k >= slab_begin(M, world, r + 1, fe)) ++r;
     return r;
 }
 
@@ -521,8 +525,8 @@ int drops_b200_brick_slab_generate(int fe, int N, int numbering, double upper_sc
     cudaStream_t st = ctx().stream;
     drops_b200_brick_slab_s* S = new drops_b200_brick_slab_s;
     S->g = g; S->world = world; S->rank = rank;
-    S->k0 = slab_begin(g.M, world, rank);
-    S->k1 = rank + 1 == world ? g.M + 1 : slab_begin(g.M, world, rank + 1);
+    S->k0 = slab_begin(g.M, world, rank, g.fe);
+    S->k1 = rank + 1 == world ? g.M + 1 : slab_begin(g.M, world, rank + 1, g.fe);
     const long long n = (S->k1 - S->k0) * g.M * g.M;
     S->n_owned = (size_t)n;
     StencilTable* dT = nullptr; void* tmp = nullptr; int64_t* gid2 = nullptr; int64_t* lat2 = nullptr;
@@ -572,7 +576,7 @@ int drops_b200_brick_slab_generate(int fe, int N, int numbering, double upper_sc
     SL_CHECK(find_ghosts_device(S->n_owned, S->owned.data(), S->nnz, S->d_col, &S->ghost_gid));
     S->ghost_owner.resize(S->ghost_gid.size());
     for (size_t i = 0; i < S->ghost_gid.size(); ++i)
-        S->ghost_owner[i] = slab_owner(g.M, world, plane_of_gid(g, S->ghost_gid[i]));
+        S->ghost_owner[i] = slab_owner(g.M, world, plane_of_gid(g, S->ghost_gid[i]), g.fe);
     cleanup();
 #undef SL_CUDA
 #undef SL_CHECK
@@ -640,7 +644,7 @@ int drops_b200_brick_owner(int fe, int N, int numbering, int world, size_t count
     DB_ARG(world >= 1 && (count == 0 || (gids != nullptr && owner != nullptr)), "bad argument");
     for (size_t i = 0; i < count; ++i) {
         DB_ARG(gids[i] >= 0 && gids[i] < g.M * g.M * g.M, "global id outside the brick");
-        owner[i] = slab_owner(g.M, world, plane_of_gid(g, gids[i]));
+        owner[i] = slab_owner(g.M, world, plane_of_gid(g, gids[i]), g.fe);
     }
     return 0;
 }
