@@ -343,7 +343,8 @@ int gmres_device(drops_b200_matrix_s* M, double* x, const double* b, int pc, dou
     // scales the new basis vector and the stop flag lives on the device, so the host enqueues "gmres.check_every" steps
     // of a cycle without waiting for each Hessenberg column and a step is 4 launches instead of 5 (10^5 rows, GMRES(200):
     // 57.7 -> 54.0 us per step; the same bits, test_gmres_device_side_givens_keeps_every_bit)
-    const bool dev_givens = cgs && opt("gmres.device_givens", 1.0) != 0.0;
+    // (restart lengths up to 1024: the column and the rotations sit in shared memory, the rotated columns in an m x m block)
+    const bool dev_givens = cgs && m <= 1024 && opt("gmres.device_givens", 1.0) != 0.0;
     // small device block: h[m+1] | y[m] | vptrs[m] | scal[4] | cs[m] | sn[m] | s[m+1] | ctrl (8 doubles) | H[m*m]
     DB_CHECK(ensure_small(M, (size_t)3 * m + 8 + (dev_givens ? (size_t)3 * m + 16 + (size_t)m * m : 0)));
     double* d_h = M->d_small;
